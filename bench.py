@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Headline benchmark: KSG-1 mutual information 1D;1D, n = 1e6, k = 5 (BASELINE.json
+configs[1], "C2"), samples/sec.
+
+    python bench.py --gpus 1 --steps K --warmup W                 this repo's arm
+    torchrun ... bench.py --gpus N ...                            N ranks, query rows sharded
+    python bench.py --impl reference ...                          CPU arm (scipy cKDTree port)
+
+One "step" = one full pass of the hot path over the n-sample data set: joint k-NN radius
+-> strict marginal counts -> psi pointwise sum -> all-gather -> deterministic mean.
+`value` times the step with the point set already resident in HBM; `e2e` times the public
+call ``syntropy_b200.knn.mutual_information`` on HOST numpy arrays (H2D of the data and
+D2H of the pointwise vector + average inside the timed region).  Rank 0 prints ONE JSON
+line.  See DESIGN.md "Measurement" for the roofline accounting.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "KSG MI query samples/sec at n=1M,k=5"
+UNIT = "samples/s"
+# algorithmic FP-pipe lane-ops per (query, candidate) pair, SURVEY.md 8(d):
+# pass 1 (radius) = D FADD + (D-1) FMNMX + 1 FSETP = 2D; pass 2 (counts) = D FADD + M FMNMX + S FSETP
+OPS_PER_PAIR = {"c1": (4, 4), "c2": (4, 4)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="samples (default: the metric's n = 1e6)")
+    ap.add_argument("--k", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=200_000,
+                    help="samples of the C2 generator the in-line CPU baseline runs on")
+    return ap.parse_args()
+
+
+def workload(n):
+    from syntropy_b200 import workloads
+
+    data, call = workloads.c2_mi_1m(n=n, seed=0)
+    return data, call
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arms
+def cpu_port_run(data, call, mode):
+    from oracle import ref_port
+
+    t0 = time.perf_counter()
+    ptw, avg = ref_port.mutual_information_1(call["idxs_x"], call["idxs_y"], call["k"], data, mode=mode)
+    return time.perf_counter() - t0, float(avg)
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU algorithm for this path on the host cores.
+    The reference itself is pure Python on scipy and cannot travel to the GPU box
+    (/root/reference does not exist there); oracle/ref_port.py issues the same scipy
+    cKDTree calls, here in its all-threads mode (workers=-1, vectorised ball counts)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_port
+
+    data, call = workload(args.n)
+    mode = "fast"
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_run(data[:, :50_000], call, mode)
+    times = []
+    for _ in range(args.steps):
+        dt, avg = cpu_port_run(data, call, mode)
+        times.append(dt)
+    total = sum(times)
+    value = args.n * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"C2: KSG-1 MI 1D;1D n={args.n} k={args.k}, x vs x^2+noise"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref_port.cores_used(mode), "kind": "port",
+                         "sample": f"full workload per step (n={args.n}); scipy cKDTree, workers=-1, vectorised counts"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "mi_nats": avg,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ B200 arm
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as td
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the KSG path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    from syntropy_b200 import _engine as E
+    from syntropy_b200 import knn
+    from syntropy_b200.knn.shannon import mi1_program, _xy_masks
+
+    data, call = workload(args.n)
+    n = data.shape[1]
+    k = call["k"]
+    masks = _xy_masks(call["idxs_x"], call["idxs_y"])
+    rows = data[call["idxs_x"] + call["idxs_y"], :]
+    dev = torch.device("cuda", local)
+    pts = E.to_device_points(rows)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        ptw = E.ksg1_device(pts, k, masks, mi1_program)
+        full, total = E.finish_device(ptw, n)
+        return full, total
+
+    def e2e_step():
+        return knn.mutual_information(call["idxs_x"], call["idxs_y"], k, data)
+
+    def timed(fn, steps, count_launches=False):
+        """K steps, each bracketed by its own CUDA events; L2 flushed between steps outside
+        the events; device time = sum over steps; max over ranks."""
+        barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        l0 = E.launch_count()
+        out = None
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            out = fn()
+            ends[i].record()
+        barrier()
+        launches = E.launch_count() - l0
+        ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item()), launches, out
+
+    # warm-up (also builds the psi table and pays first-launch costs)
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    e2e_step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    E.timer.enabled = True
+    E.timer.reset()
+    ms_total, launches, (full, total) = timed(device_step, args.steps)
+    kernel_ms = E.timer.totals_ms()
+    E.timer.enabled = False
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the public API, host buffers in / host arrays out
+    def e2e_wall(steps):
+        barrier()
+        t0 = time.perf_counter()
+        res = None
+        for _ in range(steps):
+            res = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item()), res
+
+    e2e_s, (ptw_host, avg_host) = e2e_wall(args.steps)
+
+    if rank == 0:
+        value = n * args.steps / (ms_total * 1e-3)
+        e2e_value = n * args.steps / e2e_s
+        # roofline of the dominant kernel(s): FP-pipe lane-ops, SURVEY.md 8(d)
+        nq = E._dist.slice_of(n, 0, world)
+        nq = nq[1] - nq[0]
+        pairs = float(n) * float(nq)
+        a1, a2 = OPS_PER_PAIR["c2"]
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        sm_max_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+        peak = sms * 128 * sm_max_mhz * 1e6
+        knn_ms = statistics.mean(kernel_ms.get("knn_radius", [float("nan")]))
+        cnt_ms = statistics.mean(kernel_ms.get("count_subspaces", [float("nan")]))
+        psi_ms = statistics.mean(kernel_ms.get("psi_epilogue", [float("nan")]))
+        ach_knn = a1 * pairs / (knn_ms * 1e-3)
+        ach_cnt = a2 * pairs / (cnt_ms * 1e-3)
+        dominant = "knn_radius" if knn_ms >= cnt_ms else "count_subspaces"
+        ach = ach_knn if dominant == "knn_radius" else ach_cnt
+        sm_load = (clocks or {}).get("sm_mhz")
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = 6453.1
+        if os.path.exists(peaks_file):
+            try:
+                hbm_peak = float(json.load(open(peaks_file))["hbm_gbs"])
+            except Exception:
+                pass
+        psi_bytes = nq * (4 * len(masks) + 8)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2: KSG-1 MI 1D;1D n={n} k={k}, x vs x^2+noise (BASELINE configs[1])",
+                       "parallelism": f"query-sharded x{world}", "l2": "flushed between timed steps (256 MiB write)",
+                       "engine": "dense exact fp64"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rows.nbytes),
+                    "d2h_bytes_per_step": int(8 * n + 16), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp_pipe", "kernel": dominant, "achieved": ach / 1e12, "peak": peak / 1e12,
+                         "unit": "Tlane-op/s", "frac": ach / peak, "traffic": None,
+                         "peak_basis": f"{sms} SMs x 128 lanes x {sm_max_mhz:.0f} MHz (max clock)",
+                         "frac_at_load_clock": (ach / (sms * 128 * sm_load * 1e6)) if sm_load else None,
+                         "ops_per_pair": {"knn_radius": a1, "count_subspaces": a2}, "pairs_per_launch": pairs,
+                         "kernels_ms": {"knn_radius": knn_ms, "count_subspaces": cnt_ms, "psi_epilogue": psi_ms},
+                         "frac_knn_radius": ach_knn / peak, "frac_count_subspaces": ach_cnt / peak,
+                         "whole_step_frac": (a1 + a2) * pairs / (ms_total / args.steps * 1e-3) / peak},
+            "roofline_hbm": {"bound": "hbm", "kernel": "psi_epilogue", "achieved": psi_bytes / (psi_ms * 1e-3) / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s", "frac": psi_bytes / (psi_ms * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": None},
+            "mi_nats": float(avg_host),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import ref_port
+
+            ns = min(args.cpu_sample, n)
+            dt, _ = cpu_port_run(data[:, :ns], call, "faithful")
+            line["cpu_baseline"] = {
+                "value": ns / dt, "unit": UNIT, "cores": ref_port.cores_used("faithful"), "kind": "port",
+                "sample": f"first {ns} samples of the same generator, one pass ({dt:.1f} s); the reference's own "
+                          f"scipy call sequence incl. its per-sample Python loop (single-threaded, as the reference is); "
+                          f"host has {os.cpu_count()} cores"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

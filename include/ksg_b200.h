@@ -1,0 +1,208 @@
+/*
+ * ksg_b200.h -- C ABI of the B200-native KSG hot path (libksg_b200.so).
+ *
+ * The reference (thosvarley/syntropy, package `syntropy.knn`) has no FFI of its
+ * own: the path is pure Python over scipy's compiled cKDTree.  The entry points
+ * below are therefore what a binding for this path has to offer the reference's
+ * Python call sites; each one names the reference interface it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes
+ * stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain C types only; every buffer is a caller-owned DEVICE pointer unless the
+ *    name starts with h_ (small host arrays read before launch);
+ *  - point sets are float64, structure-of-arrays: coordinate d of point j lives at
+ *    base[d * ld + j]  (`data` of shape (n_variables, n_samples), row stride ld);
+ *  - every function returns 0 on success or a negative KSG_E* code, never throws;
+ *    ksg_last_error() gives the message for the calling thread;
+ *  - no hidden allocation: scratch comes from the caller (size from *_workspace);
+ *  - `stream` is a cudaStream_t passed as void*; work is only enqueued, the caller
+ *    synchronises;
+ *  - there is no CPU fallback anywhere: without a CUDA device every compute entry
+ *    point returns KSG_ECUDA.
+ */
+#ifndef KSG_B200_H
+#define KSG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KSG_OK 0
+#define KSG_EINVAL (-1)   /* bad argument */
+#define KSG_ECUDA (-2)    /* CUDA runtime error / no device */
+#define KSG_EWORKSPACE (-3) /* workspace too small */
+#define KSG_EUNSUPPORTED (-4)
+
+#define KSG_MAX_DIM 32        /* joint-space dimensionality limit */
+#define KSG_MAX_KPRIME 64     /* k+1 limit */
+#define KSG_MAX_SUBSPACES 64  /* subspaces per count call */
+
+/* ABI version (major*1000 + minor). */
+int ksg_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* ksg_last_error(void);
+
+/* Number of kernels this library has launched in this process so far (bench.py's
+ * gpu_launches is a difference of two readings). */
+unsigned long long ksg_launch_count(void);
+
+/* SM count, compute capability and SM clock (kHz) of the current device. */
+int ksg_device_info(int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_khz);
+
+/*
+ * Sets *d_flag (device int32, caller-zeroed) to 1 if any of the `count` values is
+ * NaN or +-inf.  Replaces the ValueError scipy's cKDTree constructor raises on
+ * non-finite input (reached from syntropy/knn/utils.py:29).
+ */
+int ksg_check_finite(const double* d_values, int64_t count, int32_t* d_flag, void* stream);
+
+/*
+ * d_table[i] = digamma(i) for i in [0, n_entries): table[0] = -inf, harmonic sum
+ * minus Euler's constant for i <= 10, the cephes asymptotic series above.
+ * Replaces scipy.special.digamma at the reference's call sites, which only ever
+ * pass integers (counts+1, k, N): syntropy/knn/shannon.py:74-75,182-183,194,323,
+ * 342-344; syntropy/knn/multivariate_mi.py:97-98,113,238-239,257,305,329-330,388,
+ * 409-410.
+ */
+int ksg_psi_table(double* d_table, int64_t n_entries, void* stream);
+
+/* ------------------------------------------------------------------ K1: radius
+ *
+ * eps[i - q_begin] = kprime-th smallest Chebyshev distance
+ *                    max_d |fl64(q_id - p_jd)|  over ALL points j in [0, n)
+ * for queries i in [q_begin, q_end).  d_queries == NULL means "the point set
+ * itself" (self is then one of the candidates, at distance 0, exactly as in
+ * tree.query(data.T, k=k+1)); kprime = k+1 within-set, k cross-set.  If kprime > n
+ * the radius is +inf.  Replaces build_tree_and_get_distances
+ * (syntropy/knn/utils.py:6-35: cKDTree(data.T) :29 + tree.query(..., k=k+1, p=inf)
+ * :33) as used for `distances[:, -1]`, and the two cKDTree queries of
+ * kullback_leibler_divergence (syntropy/knn/shannon.py:401-402).
+ *
+ * d_idx_out (optional, may be NULL): int64 [nq][kprime], neighbour indices in
+ * ascending (distance, index) order -- `indices` of the same reference call, needed
+ * by the KSG-2 variants (syntropy/knn/shannon.py:249; multivariate_mi.py:169).
+ */
+size_t ksg_knn_radius_workspace(int64_t n, int64_t nq, int dim, int kprime);
+int ksg_knn_radius(const double* d_points, int64_t ld, int64_t n, int dim,
+                   const double* d_queries, int64_t ldq,
+                   int64_t q_begin, int64_t q_end, int kprime,
+                   double* d_eps_out, int64_t* d_idx_out,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K2: counts
+ *
+ * For every subspace s (bit d of h_masks[s] set = joint dimension d belongs to s)
+ * and every query i in [q_begin, q_end):
+ *   counts[s * nq + (i - q_begin)] =
+ *        #{ j in [0,n) : max_{d in s} |fl64(q_id - p_jd)| <  eps }  + bias   (strict)
+ *        #{ ...                                           <= eps }  + bias   (closed)
+ * with eps = d_eps[s * eps_stride + (i - q_begin)]  (eps_stride = 0: one radius
+ * vector shared by all subspaces, the KSG-1 family; eps_stride = nq: one per
+ * subspace, the KSG-2 family).  bias = -1 removes the query itself, as
+ * get_counts_from_tree does (syntropy/knn/utils.py:38-86: nextafter :75-76, the
+ * per-sample query_ball_point(..., return_length=True) - 1 loop :79-84).  One call
+ * serves every marginal an estimator needs from the single joint radius
+ * (shannon.py:189-194,335-344; multivariate_mi.py:103-113,247-257,314-330,396-410).
+ */
+size_t ksg_count_subspaces_workspace(int64_t n, int64_t nq, int dim, int n_subspaces);
+int ksg_count_subspaces(const double* d_points, int64_t ld, int64_t n, int dim,
+                        const double* d_queries, int64_t ldq,
+                        int64_t q_begin, int64_t q_end,
+                        const uint32_t* h_masks, int n_subspaces,
+                        const double* d_eps, int64_t eps_stride,
+                        int strict, int32_t bias,
+                        int32_t* d_counts,
+                        void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K3: psi epilogue
+ *
+ * Pointwise estimator values in the reference's float64 operation order:
+ *   v = init
+ *   for each step t (in order):
+ *       p    = psi_table[ clamp(counts[step.subspace][i] + step.count_offset, 0, ..) ]
+ *       term = step.centered ? (p - psi_n) / step.divisor : p
+ *       v    = step.sign > 0 ? v + term : v - term
+ *   if (apply_scale) v = v * scale
+ *   ptw[i] = v
+ * which covers mutual_information_1/_2 (shannon.py:188-194,251-263),
+ * conditional_mutual_information (:329-344), total_correlation_1/_2
+ * (multivariate_mi.py:100-113,164-191), dual_total_correlation (:241-258),
+ * s_information (:311-333) and o_information (:394-413).
+ */
+typedef struct {
+    int32_t subspace;     /* row of d_counts */
+    int32_t count_offset; /* +1 for the KSG-1 family, 0 for KSG-2 */
+    int32_t sign;         /* +1: add the term, -1: subtract it */
+    int32_t centered;     /* 0: psi(c+off); 1: (psi(c+off) - psi_n) / divisor */
+    double divisor;
+} ksg_psi_step;
+
+int ksg_psi_epilogue(const int32_t* d_counts, int64_t nq, int n_subspaces,
+                     const ksg_psi_step* h_steps, int n_steps,
+                     double init, double psi_n, int apply_scale, double scale,
+                     const double* d_psi_table, int64_t table_entries,
+                     double* d_ptw, void* stream);
+
+/*
+ * ptw[i] = 0 + ((-psi_k + psi_n) + dim * log(2 * eps[i]))   -- Kozachenko-Leonenko,
+ * syntropy/knn/shannon.py:84-85.
+ */
+int ksg_entropy_epilogue(const double* d_eps, int64_t nq, int dim, double psi_k, double psi_n,
+                         double* d_ptw, void* stream);
+
+/*
+ * ptw[i] = dim * log(nu[i] / rho[i]) + log_ratio   -- kNN KL divergence,
+ * syntropy/knn/shannon.py:407 (log_ratio = log(m / (n - 1)) computed by the host).
+ */
+int ksg_kl_epilogue(const double* d_nu, const double* d_rho, int64_t nq, int dim, double log_ratio,
+                    double* d_ptw, void* stream);
+
+/*
+ * Deterministic float64 sum of n values into d_out[0] (fixed-shape tree, independent
+ * of launch geometry).  Replaces ptw.mean()'s sum (shannon.py:87,196,347;
+ * multivariate_mi.py:115,260,335,415); the caller divides by n.
+ * Workspace: ksg_sum_workspace(n) bytes.
+ */
+size_t ksg_sum_workspace(int64_t n);
+int ksg_sum_f64(const double* d_values, int64_t n, double* d_out,
+                void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ KSG-2 helper
+ *
+ * eps_out[s * nq + i] = max_{j < k} max_{d in s} |p_id - p_{nbr(i,j), d}|  for the k
+ * joint-space neighbours nbr(i, 1..k) of each query (column 0, the point itself, is
+ * skipped by the caller passing idx + 1 semantics via `skip_first`).
+ * Replaces the per-marginal radius loops of mutual_information_2
+ * (syntropy/knn/shannon.py:253-259) and total_correlation_2
+ * (syntropy/knn/multivariate_mi.py:176-183).
+ */
+int ksg_subspace_radius_from_neighbours(const double* d_points, int64_t ld, int64_t n, int dim,
+                                        int64_t q_begin, int64_t q_end,
+                                        const int64_t* d_idx, int kprime, int skip_first,
+                                        const uint32_t* h_masks, int n_subspaces,
+                                        double* d_eps_out, void* stream);
+
+/* ------------------------------------------------------------------ K4: fixed-radius pair count
+ *
+ * Templates u_i = (x[i], ..., x[i+m-1]) and v_j = (y[j], ..., y[j+m-1]) ("small"),
+ * and their (m+1)-long extensions ("big"), i, j in [0, n_templates).
+ *   d_counts[0] += #{(i, j), i in [i_begin, i_end) : max_w |x[i+w] - y[j+w]| <= r, w < m}
+ *   d_counts[1] += the same with w <= m
+ * (closed ball, ordered pairs, self pairs included; d_counts is caller-zeroed
+ * uint64[2]).  Both series need n_templates + m readable values.  Replaces the two
+ * cKDTree.count_neighbors calls of sample_entropy (syntropy/knn/temporal.py:65-72)
+ * and cross_sample_entropy (:136-143).
+ */
+int ksg_paircount_fixed_radius(const double* d_x, const double* d_y, int64_t n_templates, int m,
+                               double r, int64_t i_begin, int64_t i_end,
+                               unsigned long long* d_counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSG_B200_H */

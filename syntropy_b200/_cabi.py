@@ -1,0 +1,93 @@
+"""ctypes view of libksg_b200.so -- one Python callable per symbol of include/ksg_b200.h.
+
+Loading never falls back to anything: if the library cannot be built or loaded the
+import of the compute path fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+_c_i64 = C.c_int64
+_c_vp = C.c_void_p
+
+
+class PsiStep(C.Structure):
+    _fields_ = [
+        ("subspace", C.c_int32),
+        ("count_offset", C.c_int32),
+        ("sign", C.c_int32),
+        ("centered", C.c_int32),
+        ("divisor", C.c_double),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/ksg_b200.h one to one
+SIGNATURES = {
+    "ksg_version": (C.c_int, []),
+    "ksg_last_error": (C.c_char_p, []),
+    "ksg_launch_count": (C.c_ulonglong, []),
+    "ksg_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
+    "ksg_check_finite": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_vp]),
+    "ksg_psi_table": (C.c_int, [_c_vp, _c_i64, _c_vp]),
+    "ksg_knn_radius_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int, C.c_int]),
+    "ksg_knn_radius": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, _c_vp, _c_i64, _c_i64, _c_i64, C.c_int,
+                                 _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),
+    "ksg_count_subspaces_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int, C.c_int]),
+    "ksg_count_subspaces": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, _c_vp, _c_i64, _c_i64, _c_i64,
+                                      C.POINTER(C.c_uint32), C.c_int, _c_vp, _c_i64, C.c_int, C.c_int32,
+                                      _c_vp, _c_vp, C.c_size_t, _c_vp]),
+    "ksg_psi_epilogue": (C.c_int, [_c_vp, _c_i64, C.c_int, C.POINTER(PsiStep), C.c_int, C.c_double,
+                                   C.c_double, C.c_int, C.c_double, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "ksg_entropy_epilogue": (C.c_int, [_c_vp, _c_i64, C.c_int, C.c_double, C.c_double, _c_vp, _c_vp]),
+    "ksg_kl_epilogue": (C.c_int, [_c_vp, _c_vp, _c_i64, C.c_int, C.c_double, _c_vp, _c_vp]),
+    "ksg_sum_workspace": (C.c_size_t, [_c_i64]),
+    "ksg_sum_f64": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, C.c_size_t, _c_vp]),
+    "ksg_subspace_radius_from_neighbours": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, _c_i64, _c_i64, _c_vp,
+                                                      C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int,
+                                                      _c_vp, _c_vp]),
+    "ksg_paircount_fixed_radius": (C.c_int, [_c_vp, _c_vp, _c_i64, C.c_int, C.c_double, _c_i64, _c_i64,
+                                             _c_vp, _c_vp]),
+}
+
+_lib = None
+
+
+class KsgError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building in-tree first if sources are newer) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.is_stale():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on this host: use the shipped binary if any
+            if not os.path.exists(path):
+                raise ImportError(
+                    "libksg_b200.so is missing and could not be built; the KSG path has no "
+                    "CPU fallback (%s)" % exc
+                ) from exc
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().ksg_last_error().decode("utf-8", "replace")
+        raise KsgError(f"{what} failed with code {rc}: {msg}")

@@ -1,0 +1,329 @@
+"""Host orchestration of the KSG path on one B200 (per rank).
+
+PyTorch is used for device memory, streams and (in ``dist.py``) the NCCL process
+group only; every kernel is reached through the C ABI of ``include/ksg_b200.h``.
+There is no CPU fallback: without a CUDA device ``require_cuda`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import dist as _dist
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "syntropy_b200 needs a CUDA device (B200 / sm_100a): the KSG path is CUDA-only "
+            "and has no CPU fallback"
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _masks(masks):
+    arr = (C.c_uint32 * len(masks))(*[int(m) for m in masks])
+    return arr
+
+
+def mask_of(dims) -> int:
+    m = 0
+    for d in dims:
+        m |= 1 << int(d)
+    return m
+
+
+# ------------------------------------------------------------------ device helpers
+_psi_tables: dict = {}
+_psi_host: dict = {}
+
+
+def psi_table(n_entries: int) -> torch.Tensor:
+    """Device table psi(0..n_entries-1), cached per device and grown geometrically."""
+    dev = require_cuda()
+    key = dev.index
+    cur = _psi_tables.get(key)
+    if cur is None or cur.numel() < n_entries:
+        size = max(int(n_entries), 1024, 0 if cur is None else 2 * cur.numel())
+        t = torch.empty(size, dtype=torch.float64, device=dev)
+        _cabi.check(_cabi.load().ksg_psi_table(_ptr(t), size, _stream()), "ksg_psi_table")
+        _psi_tables[key] = t
+        cur = t
+    return cur
+
+
+def psi_host(n: int) -> float:
+    """psi(n) as computed by the device table (so host constants and device terms agree)."""
+    dev = require_cuda()
+    key = (dev.index, int(n))
+    v = _psi_host.get(key)
+    if v is None:
+        v = float(psi_table(int(n) + 1)[int(n)].item())
+        _psi_host[key] = v
+    return v
+
+
+def to_device_points(rows: np.ndarray) -> torch.Tensor:
+    """(D, n) array of any real dtype -> contiguous float64 SoA tensor on the GPU.
+
+    cKDTree converts its input to C-contiguous float64 the same way
+    (integer and float32 inputs are legal)."""
+    dev = require_cuda()
+    arr = np.ascontiguousarray(rows, dtype=np.float64)
+    if arr.ndim != 2:
+        raise ValueError("data must be (n_variables, n_samples)")
+    return torch.from_numpy(arr).to(dev, non_blocking=False)
+
+
+@dataclass
+class PsiProgram:
+    """The reference's pointwise accumulation, step by step (see ksg_psi_epilogue)."""
+    init: float
+    psi_n: float = 0.0
+    scale: float | None = None
+    steps: list = field(default_factory=list)  # (subspace, count_offset, sign, centered, divisor)
+
+    def add(self, subspace, sign, count_offset=1, centered=False, divisor=1.0):
+        self.steps.append((subspace, count_offset, sign, 1 if centered else 0, float(divisor)))
+
+
+# ------------------------------------------------------------------ per-kernel timing hook
+class KernelTimer:
+    """CUDA-event timing of the C-ABI calls, on the stream they are launched on.
+    ``bench.py`` switches it on to get the live duration of the dominant kernels for the
+    roofline; it is off (zero overhead) otherwise."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []  # (name, start_event, end_event)
+
+    def reset(self):
+        self.records = []
+
+    def span(self, name):
+        return _Span(self, name)
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.records:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+
+class _Span:
+    def __init__(self, timer, name):
+        self.timer, self.name = timer, name
+
+    def __enter__(self):
+        if self.timer.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        if self.timer.enabled:
+            self.b.record(torch.cuda.current_stream())
+            self.timer.records.append((self.name, self.a, self.b))
+        return False
+
+
+timer = KernelTimer()
+
+
+def launch_count() -> int:
+    return int(_cabi.load().ksg_launch_count())
+
+
+# ------------------------------------------------------------------ kernel wrappers
+def knn_radius(points: torch.Tensor, kprime: int, q_begin: int, q_end: int,
+               queries: torch.Tensor | None = None, want_indices: bool = False):
+    lib = _cabi.load()
+    dim, n = points.shape
+    nq = q_end - q_begin
+    eps = torch.empty(nq, dtype=torch.float64, device=points.device)
+    idx = torch.empty((nq, kprime), dtype=torch.int64, device=points.device) if want_indices else None
+    ws_bytes = lib.ksg_knn_radius_workspace(n, max(nq, 1), dim, kprime)
+    ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=points.device)
+    with timer.span("knn_radius"):
+        rc = lib.ksg_knn_radius(_ptr(points), points.stride(0), n, dim,
+                                _ptr(queries), 0 if queries is None else queries.stride(0),
+                                q_begin, q_end, kprime, _ptr(eps), _ptr(idx), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "ksg_knn_radius")
+    return (eps, idx) if want_indices else eps
+
+
+def count_subspaces(points: torch.Tensor, masks, eps: torch.Tensor, q_begin: int, q_end: int,
+                    strict: bool = True, bias: int = -1, per_subspace_eps: bool = False,
+                    queries: torch.Tensor | None = None) -> torch.Tensor:
+    lib = _cabi.load()
+    dim, n = points.shape
+    nq = q_end - q_begin
+    counts = torch.empty((len(masks), nq), dtype=torch.int32, device=points.device)
+    ws = torch.empty(256, dtype=torch.uint8, device=points.device)
+    with timer.span("count_subspaces"):
+        rc = lib.ksg_count_subspaces(_ptr(points), points.stride(0), n, dim,
+                                     _ptr(queries), 0 if queries is None else queries.stride(0),
+                                     q_begin, q_end, _masks(masks), len(masks), _ptr(eps),
+                                     nq if per_subspace_eps else 0, 1 if strict else 0, bias,
+                                     _ptr(counts), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "ksg_count_subspaces")
+    return counts
+
+
+def psi_epilogue(counts: torch.Tensor, prog: PsiProgram, n_total: int) -> torch.Tensor:
+    lib = _cabi.load()
+    n_sub, nq = counts.shape
+    table = psi_table(n_total + 2)
+    steps = (_cabi.PsiStep * max(len(prog.steps), 1))()
+    for t, (sub, off, sign, centered, div) in enumerate(prog.steps):
+        steps[t] = _cabi.PsiStep(sub, off, sign, centered, div)
+    ptw = torch.empty(nq, dtype=torch.float64, device=counts.device)
+    with timer.span("psi_epilogue"):
+        rc = lib.ksg_psi_epilogue(_ptr(counts), nq, n_sub, steps, len(prog.steps), prog.init, prog.psi_n,
+                                  0 if prog.scale is None else 1, 0.0 if prog.scale is None else prog.scale,
+                                  _ptr(table), table.numel(), _ptr(ptw), _stream())
+    _cabi.check(rc, "ksg_psi_epilogue")
+    return ptw
+
+
+def device_sum(values: torch.Tensor) -> torch.Tensor:
+    lib = _cabi.load()
+    out = torch.empty(1, dtype=torch.float64, device=values.device)
+    ws = torch.empty(int(lib.ksg_sum_workspace(values.numel())), dtype=torch.uint8, device=values.device)
+    with timer.span("sum_f64"):
+        rc = lib.ksg_sum_f64(_ptr(values), values.numel(), _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "ksg_sum_f64")
+    return out
+
+
+def check_finite(points: torch.Tensor) -> torch.Tensor:
+    flag = torch.zeros(1, dtype=torch.int32, device=points.device)
+    assert points.is_contiguous()
+    rc = _cabi.load().ksg_check_finite(_ptr(points), points.numel(), _ptr(flag), _stream())
+    _cabi.check(rc, "ksg_check_finite")
+    return flag
+
+
+def finish_device(ptw_slice: torch.Tensor, n_total: int):
+    """All-gather the pointwise slices (NCCL) and reduce the full vector in a fixed order."""
+    ptw_full = _dist.gather_slices(ptw_slice, n_total)
+    return ptw_full, device_sum(ptw_full)
+
+
+def _finish(ptw_slice: torch.Tensor, n_total: int, flag: torch.Tensor):
+    """Gather the pointwise slices of all ranks, reduce deterministically, copy out."""
+    ptw_full, total = finish_device(ptw_slice, n_total)
+    host = torch.cat([ptw_full, total, flag.to(torch.float64)]).cpu().numpy()
+    if host[-1] != 0.0:
+        # what scipy's cKDTree constructor raises, reached from knn/utils.py:29
+        raise ValueError("data must be finite, check for nan or inf values")
+    ptw = host[:n_total].copy()
+    with np.errstate(all="ignore"):
+        avg = np.float64(host[n_total]) / n_total  # ndarray.mean(): sum / N
+    return ptw, avg
+
+
+# ------------------------------------------------------------------ estimator drivers
+def ksg1_family(rows: np.ndarray, k: int, masks, prog_builder):
+    """Joint radius -> strict counts in every subspace -> psi program -> (ptw, avg).
+
+    ``rows`` is the (D, n) joint-space selection in the reference's concatenation
+    order; ``masks`` are subspace bitmasks over those D rows; ``prog_builder(psi_k,
+    psi_N)`` returns the PsiProgram.
+    """
+    pts = to_device_points(rows)
+    flag = check_finite(pts)
+    ptw = ksg1_device(pts, k, masks, prog_builder)
+    return _finish(ptw, pts.shape[1], flag)
+
+
+def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder) -> torch.Tensor:
+    """The device-resident part of ``ksg1_family``: this rank's pointwise slice."""
+    n = pts.shape[1]
+    q0, q1 = _dist.my_slice(n)
+    eps = knn_radius(pts, k + 1, q0, q1)
+    counts = count_subspaces(pts, masks, eps, q0, q1, strict=True, bias=-1)
+    prog = prog_builder(psi_host(k), psi_host(n))
+    return psi_epilogue(counts, prog, n)
+
+
+def ksg2_family(rows: np.ndarray, k: int, masks, prog_builder):
+    """KSG algorithm 2: per-subspace radii from the k joint neighbours, closed counts."""
+    lib = _cabi.load()
+    pts = to_device_points(rows)
+    dim, n = pts.shape
+    flag = check_finite(pts)
+    q0, q1 = _dist.my_slice(n)
+    nq = q1 - q0
+    _, idx = knn_radius(pts, k + 1, q0, q1, want_indices=True)
+    eps_s = torch.empty((len(masks), nq), dtype=torch.float64, device=pts.device)
+    rc = lib.ksg_subspace_radius_from_neighbours(_ptr(pts), pts.stride(0), n, dim, q0, q1, _ptr(idx), k + 1, 1,
+                                                 _masks(masks), len(masks), _ptr(eps_s), _stream())
+    _cabi.check(rc, "ksg_subspace_radius_from_neighbours")
+    counts = count_subspaces(pts, masks, eps_s, q0, q1, strict=False, bias=-1, per_subspace_eps=True)
+    prog = prog_builder(psi_host(k), psi_host(n))
+    ptw = psi_epilogue(counts, prog, n)
+    return _finish(ptw, n, flag)
+
+
+def kl_entropy(rows: np.ndarray, k: int):
+    pts = to_device_points(rows)
+    dim, n = pts.shape
+    flag = check_finite(pts)
+    q0, q1 = _dist.my_slice(n)
+    eps = knn_radius(pts, k + 1, q0, q1)
+    ptw = torch.empty(q1 - q0, dtype=torch.float64, device=pts.device)
+    rc = _cabi.load().ksg_entropy_epilogue(_ptr(eps), q1 - q0, dim, psi_host(k), psi_host(n), _ptr(ptw), _stream())
+    _cabi.check(rc, "ksg_entropy_epilogue")
+    return _finish(ptw, n, flag)
+
+
+def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
+    P = to_device_points(post_rows)
+    Q = to_device_points(prior_rows)
+    dim, n = P.shape
+    m = Q.shape[1]
+    flag = check_finite(P) | check_finite(Q)
+    q0, q1 = _dist.my_slice(n)
+    rho = knn_radius(P, k + 1, q0, q1)
+    nu = knn_radius(Q, k, q0, q1, queries=P)
+    ptw = torch.empty(q1 - q0, dtype=torch.float64, device=P.device)
+    with np.errstate(all="ignore"):
+        log_ratio = float(np.log(m / (n - 1)))
+    rc = _cabi.load().ksg_kl_epilogue(_ptr(nu), _ptr(rho), q1 - q0, dim, log_ratio, _ptr(ptw), _stream())
+    _cabi.check(rc, "ksg_kl_epilogue")
+    return _finish(ptw, n, flag)
+
+
+def pair_counts(x: np.ndarray, y: np.ndarray, m: int, r: float):
+    """(small, big) closed-ball ordered pair counts of the m / (m+1) templates."""
+    dev = require_cuda()
+    xs = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    ys = xs if y is x else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).to(dev)
+    nt = xs.numel() - m
+    if nt <= 0:
+        raise ValueError("series shorter than the template length")
+    flag = check_finite(xs) | check_finite(ys)
+    i0, i1 = _dist.my_slice(nt)
+    out = torch.zeros(2, dtype=torch.int64, device=dev)
+    rc = _cabi.load().ksg_paircount_fixed_radius(_ptr(xs), _ptr(ys), nt, m, float(r), i0, i1, _ptr(out), _stream())
+    _cabi.check(rc, "ksg_paircount_fixed_radius")
+    out = _dist.sum_counts(out)
+    host = torch.cat([out, flag.to(torch.int64)]).cpu().numpy()
+    if host[2] != 0:
+        raise ValueError("data must be finite, check for nan or inf values")
+    return int(host[0]), int(host[1])

@@ -1,0 +1,386 @@
+// libksg_b200: the extern "C" surface declared in include/ksg_b200.h.
+// Argument checking, launch geometry and dispatch only; the kernels live in the
+// .cuh files next to this one.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "exact_f64.cuh"
+
+namespace ksg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
+        cached = sms;
+    } else {
+        (void)cudaGetLastError();
+        return 148;
+    }
+    return cached;
+}
+
+static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
+
+// every kernel launch of the library goes through this: error check + launch counter
+static unsigned long long g_launches = 0;
+#define KSG_LAUNCHED()                           \
+    do {                                         \
+        __atomic_add_fetch(&ksg::g_launches, 1ull, __ATOMIC_RELAXED); \
+        KSG_CUDA_TRY(cudaGetLastError());        \
+    } while (0)
+
+template <typename K>
+static int allow_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        KSG_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return KSG_OK;
+}
+
+// ------------------------------------------------------------------ K1 dispatch
+struct KnnPlan {
+    int64_t qblocks;
+    int splits;
+    int64_t cand_per_split;
+    size_t dist_bytes;
+    size_t idx_bytes;
+};
+
+static KnnPlan knn_plan(int64_t n, int64_t nq, int kp) {
+    KnnPlan p;
+    p.qblocks = ceil_div(nq, F64_THREADS);
+    p.splits = choose_splits(p.qblocks, n, F64_TILE);
+    int64_t per = ceil_div(n, p.splits);
+    per = ceil_div(per, F64_TILE) * F64_TILE;
+    p.cand_per_split = per;
+    p.splits = (int)ceil_div(n, per);
+    if (p.splits < 1) p.splits = 1;
+    p.dist_bytes = (size_t)p.splits * kp * nq * sizeof(double);
+    p.idx_bytes = (size_t)p.splits * kp * nq * sizeof(int64_t);
+    return p;
+}
+
+template <int DT, bool WITH_IDX>
+static int launch_knn_f64(const double* pts, int64_t ld, int64_t n, int dim, const double* qry, int64_t ldq,
+                          int64_t q_begin, int64_t nq, int kp, const KnnPlan& p, double* part_dist,
+                          int64_t* part_idx, cudaStream_t st) {
+    size_t smem = (size_t)dim * F64_TILE * sizeof(double) + (size_t)kp * F64_THREADS * sizeof(double) +
+                  (WITH_IDX ? (size_t)kp * F64_THREADS * sizeof(int64_t) : 0);
+    int rc = allow_smem(knn_f64_kernel<DT, WITH_IDX>, smem);
+    if (rc) return rc;
+    dim3 grid((unsigned)p.qblocks, (unsigned)p.splits, 1);
+    knn_f64_kernel<DT, WITH_IDX><<<grid, F64_THREADS, smem, st>>>(pts, ld, n, qry, ldq, q_begin, nq, dim, kp,
+                                                                   p.cand_per_split, part_dist, part_idx);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+template <bool WITH_IDX>
+static int dispatch_knn_f64(const double* pts, int64_t ld, int64_t n, int dim, const double* qry, int64_t ldq,
+                            int64_t q_begin, int64_t nq, int kp, const KnnPlan& p, double* part_dist,
+                            int64_t* part_idx, cudaStream_t st) {
+#define KSG_CASE(D)                                                                                        \
+    case D:                                                                                                \
+        return launch_knn_f64<D, WITH_IDX>(pts, ld, n, dim, qry, ldq, q_begin, nq, kp, p, part_dist,       \
+                                           part_idx, st);
+    switch (dim) {
+        KSG_CASE(1) KSG_CASE(2) KSG_CASE(3) KSG_CASE(4) KSG_CASE(5) KSG_CASE(6) KSG_CASE(7) KSG_CASE(8)
+        default:
+            return launch_knn_f64<0, WITH_IDX>(pts, ld, n, dim, qry, ldq, q_begin, nq, kp, p, part_dist,
+                                               part_idx, st);
+    }
+#undef KSG_CASE
+}
+
+template <int DT>
+static int launch_count_f64(const double* pts, int64_t ld, int64_t n, int dim, const double* qry, int64_t ldq,
+                            int64_t q_begin, int64_t nq, const MaskTable& masks, int n_sub, const double* eps,
+                            int64_t eps_stride, int strict, int32_t* counts, cudaStream_t st) {
+    int64_t qblocks = ceil_div(nq, F64_THREADS);
+    int zchunks = (int)ceil_div(n_sub, F64_SUBCHUNK);
+    int splits = choose_splits(qblocks * zchunks, n, F64_TILE);
+    int64_t per = ceil_div(ceil_div(n, splits), F64_TILE) * F64_TILE;
+    splits = (int)ceil_div(n, per);
+    if (splits < 1) splits = 1;
+    size_t smem = (size_t)dim * F64_TILE * sizeof(double);
+    int rc = allow_smem(count_f64_kernel<DT>, smem);
+    if (rc) return rc;
+    dim3 grid((unsigned)qblocks, (unsigned)splits, (unsigned)zchunks);
+    count_f64_kernel<DT><<<grid, F64_THREADS, smem, st>>>(pts, ld, n, qry, ldq, q_begin, nq, dim, masks, n_sub,
+                                                          eps, eps_stride, strict, per, counts);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+template <int MT>
+static int launch_paircount(const double* x, const double* y, int64_t nt, int m, double r, int64_t i_begin,
+                            int64_t ni, unsigned long long* out, cudaStream_t st) {
+    int64_t iblocks = ceil_div(ni, PC_THREADS);
+    int splits = choose_splits(iblocks, nt, PC_TILE);
+    int64_t per = ceil_div(ceil_div(nt, splits), PC_TILE) * PC_TILE;
+    splits = (int)ceil_div(nt, per);
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)iblocks, (unsigned)splits, 1);
+    paircount_f64_kernel<MT><<<grid, PC_THREADS, 0, st>>>(x, y, nt, m, r, i_begin, ni, per, out);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+}  // namespace ksg
+
+using namespace ksg;
+
+extern "C" {
+
+int ksg_version(void) { return 1000; }
+
+const char* ksg_last_error(void) { return g_err; }
+
+unsigned long long ksg_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int ksg_device_info(int* sms, int* cc_major, int* cc_minor, int* sm_clock_khz) {
+    int dev = 0;
+    KSG_CUDA_TRY(cudaGetDevice(&dev));
+    if (sms) KSG_CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+    if (cc_major) KSG_CUDA_TRY(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc_minor) KSG_CUDA_TRY(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (sm_clock_khz) KSG_CUDA_TRY(cudaDeviceGetAttribute(sm_clock_khz, cudaDevAttrClockRate, dev));
+    return KSG_OK;
+}
+
+int ksg_check_finite(const double* d_values, int64_t count, int32_t* d_flag, void* stream) {
+    KSG_REQUIRE(d_values && d_flag && count >= 0, "ksg_check_finite: null pointer or negative count");
+    if (count == 0) return KSG_OK;
+    int blocks = (int)(ceil_div(count, 256) < 4 * sm_count() ? ceil_div(count, 256) : 4 * sm_count());
+    check_finite_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_values, count, d_flag);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_psi_table(double* d_table, int64_t n_entries, void* stream) {
+    KSG_REQUIRE(d_table && n_entries > 0, "ksg_psi_table: null table or non-positive size");
+    psi_table_kernel<<<(unsigned)ceil_div(n_entries, 256), 256, 0, as_stream(stream)>>>(d_table, n_entries);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+size_t ksg_knn_radius_workspace(int64_t n, int64_t nq, int dim, int kprime) {
+    (void)dim;
+    if (n <= 0 || nq <= 0 || kprime <= 0) return 0;
+    KnnPlan p = knn_plan(n, nq, kprime);
+    return p.dist_bytes + p.idx_bytes + 256;
+}
+
+int ksg_knn_radius(const double* d_points, int64_t ld, int64_t n, int dim, const double* d_queries,
+                   int64_t ldq, int64_t q_begin, int64_t q_end, int kprime, double* d_eps_out,
+                   int64_t* d_idx_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    KSG_REQUIRE(d_points && d_eps_out, "ksg_knn_radius: null pointer");
+    KSG_REQUIRE(n > 0 && ld >= n, "ksg_knn_radius: need n > 0 and ld >= n");
+    KSG_REQUIRE(dim >= 1 && dim <= KSG_MAX_DIM, "ksg_knn_radius: dim out of range");
+    KSG_REQUIRE(kprime >= 1 && kprime <= KSG_MAX_KPRIME, "ksg_knn_radius: kprime out of range");
+    if (!d_queries) {
+        d_queries = d_points;
+        ldq = ld;
+        KSG_REQUIRE(q_end <= n, "ksg_knn_radius: query range exceeds the point set");
+    }
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && ldq >= q_end, "ksg_knn_radius: bad query range");
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    KnnPlan p = knn_plan(n, nq, kprime);
+    if (workspace_bytes < p.dist_bytes + p.idx_bytes || !d_workspace) {
+        set_error("ksg_knn_radius: workspace of %zu bytes needed, %zu given", p.dist_bytes + p.idx_bytes,
+                  workspace_bytes);
+        return KSG_EWORKSPACE;
+    }
+    double* part_dist = (double*)d_workspace;
+    int64_t* part_idx = (int64_t*)((char*)d_workspace + p.dist_bytes);
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    if (d_idx_out)
+        rc = dispatch_knn_f64<true>(d_points, ld, n, dim, d_queries, ldq, q_begin, nq, kprime, p, part_dist,
+                                    part_idx, st);
+    else
+        rc = dispatch_knn_f64<false>(d_points, ld, n, dim, d_queries, ldq, q_begin, nq, kprime, p, part_dist,
+                                     part_idx, st);
+    if (rc) return rc;
+    unsigned mb = (unsigned)ceil_div(nq, 128);
+    if (d_idx_out)
+        knn_merge_kernel<true><<<mb, 128, 0, st>>>(part_dist, part_idx, nq, kprime, p.splits, d_eps_out, d_idx_out);
+    else
+        knn_merge_kernel<false><<<mb, 128, 0, st>>>(part_dist, part_idx, nq, kprime, p.splits, d_eps_out, nullptr);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+size_t ksg_count_subspaces_workspace(int64_t n, int64_t nq, int dim, int n_subspaces) {
+    (void)n; (void)nq; (void)dim; (void)n_subspaces;
+    return 256;
+}
+
+int ksg_count_subspaces(const double* d_points, int64_t ld, int64_t n, int dim, const double* d_queries,
+                        int64_t ldq, int64_t q_begin, int64_t q_end, const uint32_t* h_masks, int n_subspaces,
+                        const double* d_eps, int64_t eps_stride, int strict, int32_t bias, int32_t* d_counts,
+                        void* d_workspace, size_t workspace_bytes, void* stream) {
+    (void)d_workspace; (void)workspace_bytes;
+    KSG_REQUIRE(d_points && h_masks && d_eps && d_counts, "ksg_count_subspaces: null pointer");
+    KSG_REQUIRE(n > 0 && ld >= n, "ksg_count_subspaces: need n > 0 and ld >= n");
+    KSG_REQUIRE(dim >= 1 && dim <= KSG_MAX_DIM, "ksg_count_subspaces: dim out of range");
+    KSG_REQUIRE(n_subspaces >= 1 && n_subspaces <= KSG_MAX_SUBSPACES, "ksg_count_subspaces: subspace count");
+    if (!d_queries) {
+        d_queries = d_points;
+        ldq = ld;
+        KSG_REQUIRE(q_end <= n, "ksg_count_subspaces: query range exceeds the point set");
+    }
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && ldq >= q_end, "ksg_count_subspaces: bad query range");
+    const int64_t nq = q_end - q_begin;
+    KSG_REQUIRE(eps_stride == 0 || eps_stride >= nq, "ksg_count_subspaces: eps_stride must be 0 or >= nq");
+    if (nq == 0) return KSG_OK;
+    MaskTable masks;
+    memset(&masks, 0, sizeof(masks));
+    const uint32_t all = dim == 32 ? 0xffffffffu : ((1u << dim) - 1u);
+    for (int s = 0; s < n_subspaces; ++s) {
+        KSG_REQUIRE(h_masks[s] != 0 && (h_masks[s] & ~all) == 0, "ksg_count_subspaces: empty or out-of-range mask");
+        masks.m[s] = h_masks[s];
+    }
+    cudaStream_t st = as_stream(stream);
+    const int64_t total = (int64_t)n_subspaces * nq;
+    fill_i32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(d_counts, total, bias);
+    KSG_LAUNCHED();
+#define KSG_CASE(D)                                                                                           \
+    case D:                                                                                                   \
+        return launch_count_f64<D>(d_points, ld, n, dim, d_queries, ldq, q_begin, nq, masks, n_subspaces,     \
+                                   d_eps, eps_stride, strict, d_counts, st);
+    switch (dim) {
+        KSG_CASE(1) KSG_CASE(2) KSG_CASE(3) KSG_CASE(4) KSG_CASE(5) KSG_CASE(6) KSG_CASE(7) KSG_CASE(8)
+        default:
+            return launch_count_f64<0>(d_points, ld, n, dim, d_queries, ldq, q_begin, nq, masks, n_subspaces,
+                                       d_eps, eps_stride, strict, d_counts, st);
+    }
+#undef KSG_CASE
+}
+
+int ksg_psi_epilogue(const int32_t* d_counts, int64_t nq, int n_subspaces, const ksg_psi_step* h_steps,
+                     int n_steps, double init, double psi_n, int apply_scale, double scale,
+                     const double* d_psi_table, int64_t table_entries, double* d_ptw, void* stream) {
+    KSG_REQUIRE(d_counts && h_steps && d_psi_table && d_ptw, "ksg_psi_epilogue: null pointer");
+    KSG_REQUIRE(n_steps >= 0 && n_steps <= MAX_PSI_STEPS, "ksg_psi_epilogue: too many steps");
+    KSG_REQUIRE(table_entries >= 1 && nq >= 0, "ksg_psi_epilogue: bad sizes");
+    if (nq == 0) return KSG_OK;
+    PsiProgram prog;
+    memset(&prog, 0, sizeof(prog));
+    prog.n_steps = n_steps;
+    prog.apply_scale = apply_scale;
+    prog.init = init;
+    prog.psi_n = psi_n;
+    prog.scale = scale;
+    for (int t = 0; t < n_steps; ++t) {
+        KSG_REQUIRE(h_steps[t].subspace >= 0 && h_steps[t].subspace < n_subspaces,
+                    "ksg_psi_epilogue: step refers to a missing subspace");
+        KSG_REQUIRE(h_steps[t].count_offset >= -100 && h_steps[t].count_offset <= 100,
+                    "ksg_psi_epilogue: count_offset out of range");
+        prog.subspace[t] = (int16_t)h_steps[t].subspace;
+        prog.offset[t] = (int8_t)h_steps[t].count_offset;
+        prog.sign[t] = (int8_t)(h_steps[t].sign >= 0 ? 1 : -1);
+        prog.centered[t] = (int8_t)(h_steps[t].centered != 0);
+        prog.divisor[t] = h_steps[t].divisor;
+    }
+    psi_epilogue_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, as_stream(stream)>>>(d_counts, nq, prog, d_psi_table,
+                                                                                   table_entries, d_ptw);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_entropy_epilogue(const double* d_eps, int64_t nq, int dim, double psi_k, double psi_n, double* d_ptw,
+                         void* stream) {
+    KSG_REQUIRE(d_eps && d_ptw && nq >= 0 && dim >= 1, "ksg_entropy_epilogue: bad argument");
+    if (nq == 0) return KSG_OK;
+    const double base = -psi_k + psi_n;
+    entropy_epilogue_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, as_stream(stream)>>>(d_eps, nq, (double)dim,
+                                                                                       base, d_ptw);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_kl_epilogue(const double* d_nu, const double* d_rho, int64_t nq, int dim, double log_ratio,
+                    double* d_ptw, void* stream) {
+    KSG_REQUIRE(d_nu && d_rho && d_ptw && nq >= 0 && dim >= 1, "ksg_kl_epilogue: bad argument");
+    if (nq == 0) return KSG_OK;
+    kl_epilogue_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, as_stream(stream)>>>(d_nu, d_rho, nq, (double)dim,
+                                                                                  log_ratio, d_ptw);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+size_t ksg_sum_workspace(int64_t n) {
+    (void)n;
+    return SUM_BLOCKS * sizeof(double);
+}
+
+int ksg_sum_f64(const double* d_values, int64_t n, double* d_out, void* d_workspace, size_t workspace_bytes,
+                void* stream) {
+    KSG_REQUIRE(d_values && d_out && n >= 0, "ksg_sum_f64: bad argument");
+    if (!d_workspace || workspace_bytes < SUM_BLOCKS * sizeof(double)) {
+        set_error("ksg_sum_f64: workspace of %zu bytes needed", SUM_BLOCKS * sizeof(double));
+        return KSG_EWORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    sum_stage1_kernel<<<SUM_BLOCKS, SUM_THREADS, 0, st>>>(d_values, n, (double*)d_workspace);
+    KSG_LAUNCHED();
+    sum_stage2_kernel<<<1, SUM_THREADS, 0, st>>>((const double*)d_workspace, d_out);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_subspace_radius_from_neighbours(const double* d_points, int64_t ld, int64_t n, int dim,
+                                        int64_t q_begin, int64_t q_end, const int64_t* d_idx, int kprime,
+                                        int skip_first, const uint32_t* h_masks, int n_subspaces,
+                                        double* d_eps_out, void* stream) {
+    KSG_REQUIRE(d_points && d_idx && h_masks && d_eps_out, "ksg_subspace_radius_from_neighbours: null pointer");
+    KSG_REQUIRE(n > 0 && ld >= n && dim >= 1 && dim <= KSG_MAX_DIM, "ksg_subspace_radius_from_neighbours: sizes");
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= n, "ksg_subspace_radius_from_neighbours: query range");
+    KSG_REQUIRE(n_subspaces >= 1 && n_subspaces <= KSG_MAX_SUBSPACES, "ksg_subspace_radius_from_neighbours: subspaces");
+    KSG_REQUIRE(kprime >= 1 && kprime <= KSG_MAX_KPRIME, "ksg_subspace_radius_from_neighbours: kprime");
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    MaskTable masks;
+    memset(&masks, 0, sizeof(masks));
+    for (int s = 0; s < n_subspaces; ++s) masks.m[s] = h_masks[s];
+    subspace_radius_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, as_stream(stream)>>>(
+        d_points, ld, dim, q_begin, nq, n, d_idx, kprime, skip_first, masks, n_subspaces, d_eps_out);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_paircount_fixed_radius(const double* d_x, const double* d_y, int64_t n_templates, int m, double r,
+                               int64_t i_begin, int64_t i_end, unsigned long long* d_counts, void* stream) {
+    KSG_REQUIRE(d_x && d_y && d_counts, "ksg_paircount_fixed_radius: null pointer");
+    KSG_REQUIRE(n_templates > 0 && m >= 1 && m < KSG_MAX_DIM, "ksg_paircount_fixed_radius: sizes");
+    KSG_REQUIRE(i_begin >= 0 && i_end >= i_begin && i_end <= n_templates, "ksg_paircount_fixed_radius: range");
+    const int64_t ni = i_end - i_begin;
+    if (ni == 0) return KSG_OK;
+    cudaStream_t st = as_stream(stream);
+#define KSG_CASE(M) \
+    case M:         \
+        return launch_paircount<M>(d_x, d_y, n_templates, m, r, i_begin, ni, d_counts, st);
+    switch (m) {
+        KSG_CASE(1) KSG_CASE(2) KSG_CASE(3) KSG_CASE(4) KSG_CASE(5) KSG_CASE(6)
+        default:
+            return launch_paircount<0>(d_x, d_y, n_templates, m, r, i_begin, ni, d_counts, st);
+    }
+#undef KSG_CASE
+}
+
+}  // extern "C"

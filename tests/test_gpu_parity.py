@@ -1,0 +1,336 @@
+"""GPU parity tests proper (run with ``-m gpu`` on the B200 box).
+
+Everything goes through the C ABI of include/ksg_b200.h (via syntropy_b200._engine /
+the public syntropy_b200.knn functions) and is compared with
+ (a) the committed golden fixtures produced by the unmodified reference, and
+ (b) the CPU oracle on the same seeded inputs.
+Bars: radii and neighbour counts bit-exact; pointwise / average nats within 1e-12
+relative (the only non-bit-exact ingredient is log() inside digamma for arguments
+above 10, where CUDA's libdevice and the host libm may differ in the last ulp).
+"""
+import numpy as np
+import pytest
+
+from oracle import ksg_oracle as orc
+from syntropy_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def knn():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from syntropy_b200 import knn as mod
+
+    return mod
+
+
+@pytest.fixture(scope="module")
+def E():
+    from syntropy_b200 import _engine
+
+    return _engine
+
+
+def close(a, b):
+    """|a-b| <= 1e-12 * max(|b|, 1): relative 1e-12, with an absolute floor for pointwise
+    values that cancel to ~0 (every psi term is O(1..20))."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    both_nan = np.isnan(a) & np.isnan(b)
+    ok = both_inf | both_nan | (np.abs(a - b) <= RTOL * np.maximum(np.abs(b), 1.0))
+    assert ok.all(), f"max abs diff {np.nanmax(np.abs(a - b)[~(both_inf | both_nan)])}"
+
+
+def radius_and_counts(E, rows, k, subspaces, strict=True):
+    import torch
+
+    pts = E.to_device_points(rows)
+    n = pts.shape[1]
+    eps = E.knn_radius(pts, k + 1, 0, n)
+    masks = [E.mask_of(s) for s in subspaces]
+    counts = E.count_subspaces(pts, masks, eps, 0, n, strict=strict)
+    torch.cuda.synchronize()
+    return eps.cpu().numpy(), counts.cpu().numpy().astype(np.int64)
+
+
+# ------------------------------------------------------------------ golden fixtures
+def test_psi_table_vs_scipy_golden(E, golden):
+    g = golden("digamma")
+    args = g["args"]
+    small = args[args < 3_000_000]
+    table = E.psi_table(int(small.max()) + 1).cpu().numpy()
+    ref = g["psi"][: small.size]
+    mine = table[small]
+    assert np.isneginf(mine[0])
+    assert np.array_equal(mine[small <= 10], ref[small <= 10])  # harmonic sums: bit-exact
+    rel = np.abs(mine[1:] - ref[1:]) / np.abs(ref[1:])
+    assert rel.max() < 4e-16
+
+
+def test_golden_tie_fixture(knn, E, golden):
+    g = golden("tie_fixture")
+    data = workloads.tie_fixture()
+    for k in (1, 4):
+        ptw, avg = knn.differential_entropy(data=data, idxs=(0,), k=k)
+        close(ptw, g[f"entropy_k{k}_ptw"]); close(avg, g[f"entropy_k{k}_avg"])
+    ptw, avg = knn.mutual_information((0,), (1,), k=1, data=data, algorithm=1)
+    close(ptw, g["mi1_ptw"]); close(avg, g["mi1_avg"])
+    assert avg == pytest.approx(5.177377517639623, 1e-6)   # tests/test_knn.py:44 (JIDT)
+    mi2 = knn.mutual_information((0,), (1,), k=1, data=data, algorithm=2)[1]
+    assert mi2 == pytest.approx(2.2173775176396227, 1e-6)  # tests/test_knn.py:50 (JIDT)
+    ptw, avg = knn.conditional_mutual_information((0,), (1,), (2,), k=1, data=data)
+    close(ptw, g["cmi_ptw"]); close(avg, g["cmi_avg"])
+    assert avg == pytest.approx(4.479205338329424, 1e-6)   # tests/test_knn.py:57
+    known = {"total_correlation": 5.875549696949821, "dual_total_correlation": 5.1773775176396235,
+             "o_information": 0.6981721793101983, "s_information": 11.052927214589442}
+    for name, val in known.items():
+        ptw, avg = getattr(knn, name)(data=data, k=1)
+        close(ptw, g[name + "_ptw"]); close(avg, g[name + "_avg"])
+        assert avg == pytest.approx(val, 1e-6)               # tests/test_knn.py:60-75
+    subs = {"x": (0,), "y": (1,), "z": (2,), "xy": (0, 1), "yz": (1, 2)}
+    eps, counts = radius_and_counts(E, data, 1, list(subs.values()))
+    assert np.array_equal(eps, g["rc_eps"])
+    for row, name in enumerate(subs):
+        assert np.array_equal(counts[row], g["rc_counts_" + name]), name
+
+
+def test_golden_c1_readme_case(knn, E, golden):
+    g = golden("c1_mi")
+    data, call = workloads.c1_readme_mi(n=int(g["n"]), seed=0)
+    eps, counts = radius_and_counts(E, data, 5, [(0,), (1,)])
+    assert np.array_equal(eps, g["eps"])
+    assert np.array_equal(counts[0], g["counts_x"])
+    assert np.array_equal(counts[1], g["counts_y"])
+    ptw, avg = knn.mutual_information((0,), (1,), k=5, data=data)
+    assert ptw.shape == (1, 5000) and isinstance(avg, np.float64)
+    close(ptw, g["ptw"]); close(avg, g["avg"])
+    assert avg == pytest.approx(0.780399359365535, rel=1e-12)
+    ptw, avg = knn.mutual_information((0,), (1,), k=5, data=data, algorithm=2)
+    close(ptw, g["ptw_alg2"]); close(avg, g["avg_alg2"])
+
+
+def test_golden_c3_cmi(knn, E, golden):
+    g = golden("c3_cmi")
+    data, call = workloads.c3_cmi(n=int(g["n"]), seed=0)
+    eps, counts = radius_and_counts(E, data, 4, [(4, 5), (0, 1, 4, 5), (2, 3, 4, 5)])
+    assert np.array_equal(eps, g["eps"])
+    for row, name in enumerate(("z", "xz", "yz")):
+        assert np.array_equal(counts[row], g["counts_" + name]), name
+    ptw, avg = knn.conditional_mutual_information((0, 1), (2, 3), (4, 5), k=4, data=data)
+    close(ptw, g["ptw"]); close(avg, g["avg"])
+
+
+def test_golden_c4_multivariate(knn, E, golden):
+    g = golden("c4_multivariate")
+    data, _ = workloads.c4_oinfo(n=int(g["n"]), seed=0)
+    subs = [(d,) for d in range(8)] + [tuple(j for j in range(8) if j != d) for d in range(8)]
+    eps, counts = radius_and_counts(E, data, 4, subs)
+    assert np.array_equal(eps, g["eps"])
+    for d in range(8):
+        assert np.array_equal(counts[d], g[f"counts_small{d}"])
+        assert np.array_equal(counts[8 + d], g[f"counts_big{d}"])
+    for name in ("total_correlation", "dual_total_correlation", "o_information", "s_information"):
+        ptw, avg = getattr(knn, name)(data=data, k=4)
+        close(ptw, g[name + "_ptw"]); close(avg, g[name + "_avg"])
+        ptw, avg = getattr(knn, name)(data=data, k=3, idxs=(5, 1, 6, 2))
+        close(ptw, g[name + "_sel_ptw"]); close(avg, g[name + "_sel_avg"])
+    ptw, avg = knn.total_correlation(data=data, k=4, algorithm=2)
+    close(ptw, g["total_correlation2_ptw"]); close(avg, g["total_correlation2_avg"])
+    for k in (1, 4):
+        ptw, avg = knn.differential_entropy(data=data, k=k, idxs=(0, 3, 7))
+        close(ptw, g[f"entropy_k{k}_ptw"]); close(avg, g[f"entropy_k{k}_avg"])
+    ptw, avg = knn.differential_entropy(data=data, k=3, noise_level=0.05, seed=7)
+    close(ptw, g["entropy_noise_ptw"]); close(avg, g["entropy_noise_avg"])
+    # identities O = TC - DTC, S = TC + DTC hold on the outputs
+    tc = knn.total_correlation(data, 4)[1]; dtc = knn.dual_total_correlation(data, 4)[1]
+    assert knn.o_information(data, 4)[1] == pytest.approx(tc - dtc, abs=1e-9)
+    assert knn.s_information(data, 4)[1] == pytest.approx(tc + dtc, abs=1e-9)
+
+
+def test_golden_c5_and_temporal(knn, E, golden):
+    g = golden("c5_temporal")
+    n = int(g["n"])
+    data, call = workloads.c5_info_rate(n=n, seed=0)
+    eps, counts = radius_and_counts(E, data, 5, [(0, 1, 2, 3), (4, 5, 6, 7)])
+    assert np.array_equal(eps, g["eps"])
+    assert np.array_equal(counts[0], g["counts_x"]) and np.array_equal(counts[1], g["counts_y"])
+    ptw, avg = knn.mutual_information((0, 1, 2, 3), (4, 5, 6, 7), k=5, data=data)
+    close(ptw, g["ptw"]); close(avg, g["avg"])
+    series = workloads.c5_series(n=n, seed=0)
+    # pair counts are integers: the entropies are bit-exact up to the host log
+    assert [knn.sample_entropy((c,), series) for c in range(4)] == list(g["sampen"])
+    assert [knn.sample_entropy((c,), series, m=3, r=0.15) for c in range(4)] == list(g["sampen_m3_r015"])
+    assert knn.sample_entropy((0,), series, m=2, r=0.3, normalize_r=False) == g["sampen_abs_r"]
+    assert knn.cross_sample_entropy((0,), (1,), series) == g["cross_sampen_01"]
+    assert knn.cross_sample_entropy((2,), (3,), series, m=3, r=0.25) == g["cross_sampen_23_m3"]
+
+
+def test_golden_kl_divergence(knn, golden):
+    g = golden("kl_divergence")
+    rng = np.random.default_rng(int(g["seed"]))
+    post = rng.standard_normal((3, 2000))
+    prior = 1.3 * rng.standard_normal((3, 2500)) + 0.2
+    for k in (1, 3):
+        ptw, avg = knn.kullback_leibler_divergence(post, prior, k=k)
+        assert ptw.shape == (2000,)
+        close(ptw, g[f"k{k}_ptw"]); close(avg, g[f"k{k}_avg"])
+
+
+def test_golden_edge_cases(knn, E, golden):
+    g = golden("edge_cases")
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((2, 40))
+    dup = np.concatenate([base, base[:, :10], base[:, :10]], axis=1)
+    eps, counts = radius_and_counts(E, dup, 2, [(0,), (1,)])
+    assert np.array_equal(eps, g["dup_eps"]) and (eps == 0).sum() == 30
+    assert np.array_equal(counts[0], g["dup_counts_x"]) and counts[0].min() == -1
+    assert np.array_equal(counts[1], g["dup_counts_y"])
+    ptw, avg = knn.mutual_information((0,), (1,), k=2, data=dup)
+    close(ptw, g["dup_mi_ptw"]); close(avg, g["dup_mi_avg"])     # +inf entries from psi(0)
+    tiny = rng.standard_normal((2, 4))
+    eps, counts = radius_and_counts(E, tiny, 5, [(0,), (1,)])     # k+1 > n -> eps = inf
+    assert np.isinf(eps).all() and np.array_equal(counts[0], g["tiny_counts_x"])
+    ptw, avg = knn.mutual_information((0,), (1,), k=5, data=tiny)
+    close(ptw, g["tiny_mi_ptw"]); close(avg, g["tiny_mi_avg"])
+    f32 = rng.standard_normal((3, 500)).astype(np.float32)
+    ptw, avg = knn.conditional_mutual_information((0,), (1,), (2,), k=3, data=f32)
+    close(ptw, g["f32_cmi_ptw"]); close(avg, g["f32_cmi_avg"])
+    i32 = rng.integers(-50, 50, size=(3, 400)).astype(np.int32)
+    ptw, avg = knn.total_correlation(data=i32, k=3)
+    close(ptw, g["i32_tc_ptw"]); close(avg, g["i32_tc_avg"])
+
+
+# ------------------------------------------------------------------ reference-test semantics
+def test_reference_utils_semantics(E):
+    # tests/test_knn_utils.py:10-30, 64-92 restated at the C-ABI level
+    eps, _ = radius_and_counts(E, np.array([[0.0, 1.0, 2.0, 4.0]]), 1, [(0,)])
+    assert np.array_equal(eps, [1.0, 1.0, 1.0, 2.0])
+    import torch
+    pts = E.to_device_points(np.array([[0.0, 1.0, 2.0, 5.0]]))
+    for radius, strict, want in ((1.5, True, [1, 2, 1, 0]), (1.0, True, [0, 0, 0, 0]), (1.0, False, [1, 2, 1, 0])):
+        e = torch.full((4,), radius, dtype=torch.float64, device=pts.device)
+        c = E.count_subspaces(pts, [1], e, 0, 4, strict=strict).cpu().numpy()[0]
+        assert np.array_equal(c, want), (radius, strict)
+    single = E.to_device_points(np.array([[0.0]]))
+    e = torch.full((1,), 100.0, dtype=torch.float64, device=pts.device)
+    assert E.count_subspaces(single, [1], e, 0, 1).cpu().numpy()[0, 0] == 0
+
+
+def test_errors_mirror_reference(knn):
+    data = np.random.default_rng(0).standard_normal((3, 64))
+    with pytest.raises(AssertionError):
+        knn.mutual_information((0,), (1,), 3, data, algorithm=3)
+    with pytest.raises(AssertionError):
+        knn.total_correlation(data, 3, algorithm=0)
+    with pytest.raises(AssertionError):
+        knn.kullback_leibler_divergence(data, data[:2], 3)
+    bad = data.copy(); bad[1, 5] = np.nan
+    with pytest.raises(ValueError):
+        knn.mutual_information((0,), (1,), 3, bad)
+    with pytest.raises(NotImplementedError):
+        knn.mutual_information((0,), (1,), 3, data, p=2)
+    ptw, avg = knn.o_information(data[:2], 3)
+    assert ptw.shape == (64,) and avg == 0.0 and not ptw.any()
+
+
+# ------------------------------------------------------------------ oracle at moderate n
+@pytest.mark.parametrize("dim,k,n", [(1, 1, 777), (2, 5, 6000), (3, 3, 4097), (5, 4, 3000), (8, 4, 5000), (11, 2, 1500)])
+def test_radius_counts_vs_oracle(E, dim, k, n):
+    rng = np.random.default_rng(100 + dim)
+    rows = rng.standard_normal((dim, n)) * rng.uniform(0.5, 3.0, size=(dim, 1))
+    subs = [(d,) for d in range(dim)]
+    if dim > 1:
+        subs += [tuple(range(dim // 2)), tuple(range(dim // 2, dim)), tuple(range(1, dim))]
+    eps, counts = radius_and_counts(E, rows, k, subs)
+    ref_eps = orc.knn_radius(rows, k)
+    assert np.array_equal(eps, ref_eps)
+    for row, s in enumerate(subs):
+        assert np.array_equal(counts[row], orc.count_within(rows[list(s), :], ref_eps)), s
+    _, closed = radius_and_counts(E, rows, k, subs[:2], strict=False)
+    assert np.array_equal(closed[0], orc.count_within(rows[list(subs[0]), :], ref_eps, strict=False))
+
+
+def test_quantised_data_ties(E, knn):
+    rng = np.random.default_rng(3)
+    rows = np.round(rng.standard_normal((3, 3000)) * 4) / 4  # heavy exact ties
+    eps, counts = radius_and_counts(E, rows, 3, [(0,), (1, 2), (0, 1, 2)])
+    ref = orc.knn_radius(rows, 3)
+    assert np.array_equal(eps, ref)
+    assert np.array_equal(counts[0], orc.count_within(rows[(0,), :], ref))
+    assert np.array_equal(counts[1], orc.count_within(rows[(1, 2), :], ref))
+    assert np.array_equal(counts[2], orc.count_within(rows, ref))
+    with np.errstate(all="ignore"):
+        close(knn.total_correlation(rows, 3)[0], orc.total_correlation(rows, 3)[0])
+
+
+def test_query_slices_compose(E):
+    """Sharding invariant: any query slice equals the same rows of the full result."""
+    rows = np.random.default_rng(9).standard_normal((4, 5000))
+    pts = E.to_device_points(rows)
+    full = E.knn_radius(pts, 5, 0, 5000)
+    part = E.knn_radius(pts, 5, 1234, 3999)
+    assert np.array_equal(full[1234:3999].cpu().numpy(), part.cpu().numpy())
+    cf = E.count_subspaces(pts, [3, 12], full, 0, 5000)
+    cp = E.count_subspaces(pts, [3, 12], part, 1234, 3999)
+    assert np.array_equal(cf[:, 1234:3999].cpu().numpy(), cp.cpu().numpy())
+
+
+def test_knn_indices_vs_oracle(E):
+    rows = np.random.default_rng(21).standard_normal((3, 2500))
+    pts = E.to_device_points(rows)
+    eps, idx = E.knn_radius(pts, 5, 0, 2500, want_indices=True)
+    ref_eps, ref_idx = orc.knn_radius(rows, 4, return_indices=True)
+    assert np.array_equal(eps.cpu().numpy(), ref_eps)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+def test_pair_counts_vs_oracle(E):
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(3000); y = rng.standard_normal(3000)
+    for m in (1, 2, 3, 7):
+        nt = x.size - m
+        small, big = E.pair_counts(x, y, m, 0.35)
+        assert small == orc.pair_count(orc._embed(x, m, nt), orc._embed(y, m, nt), 0.35)
+        assert big == orc.pair_count(orc._embed(x, m + 1, nt), orc._embed(y, m + 1, nt), 0.35)
+
+
+def test_deterministic_sum(E):
+    import torch
+    v = np.random.default_rng(0).standard_normal(1_000_003)
+    t = torch.from_numpy(v).cuda()
+    s1 = E.device_sum(t).item(); s2 = E.device_sum(t).item()
+    assert s1 == s2
+    assert s1 == pytest.approx(float(np.sum(v)), rel=1e-13)
+
+
+# ------------------------------------------------------------------ full-size properties (C2)
+def test_c2_full_size_query_subset(E, knn):
+    """n = 1e6 (the metric's configuration): oracle on a random query subset against the
+    full point set, plus size-independent properties of the counts."""
+    data, call = workloads.c2_mi_1m()
+    n = data.shape[1]
+    pts = E.to_device_points(data)
+    sub = np.sort(np.random.default_rng(1).choice(n, size=768, replace=False))
+    lo, hi = 400_000, 400_000 + 4096
+    eps = E.knn_radius(pts, 6, lo, hi).cpu().numpy()
+    ref = orc.knn_radius(data, 6, queries=data[:, lo:lo + 512])  # k' = 6 = k+1, self included
+    assert np.array_equal(eps[:512], ref)
+    import torch
+    eps_d = torch.from_numpy(eps).cuda()
+    counts = E.count_subspaces(pts, [1, 2, 3], eps_d, lo, hi).cpu().numpy()
+    for row, s in enumerate(((0,), (1,))):
+        want = orc.count_within(data[list(s), :], ref, queries=data[list(s), lo:lo + 512])
+        assert np.array_equal(counts[row, :512], want)
+    # property: in the joint space exactly k points other than the query lie strictly
+    # inside the (k+1)-th-neighbour radius unless distances tie (continuous data: never)
+    assert (counts[2] == 4).all()
+    # property: marginal counts dominate the joint count
+    assert (counts[0] >= counts[2]).all() and (counts[1] >= counts[2]).all()
+    del sub
