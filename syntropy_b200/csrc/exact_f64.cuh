@@ -74,14 +74,22 @@ knn_f64_kernel(const double* __restrict__ pts, int64_t ld, int64_t n,
         __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < F64_TILE; ++j) {
-            double m = fabs(q[0] - tile[j]);
-#pragma unroll
-            for (int d = 1; d < DimOf<DT>::CAP; ++d)
-                if (d < dim) m = fmax(m, fabs(q[d] - tile[d * F64_TILE + j]));
+            // fp64 max is a 3-instruction sequence on sm_100 (DSETP + 2 FSEL); the hot
+            // test is a chain of predicated compares instead, the max is formed on a hit.
             // strict '<': a candidate tying the current kp-th value cannot change it.
-            // With indices requested, ties must still enter when the list is not yet
-            // full of finite entries -- handled by '<' against +inf.
-            if (m < thr) {
+            double a[DimOf<DT>::CAP];
+            bool hit = true;
+#pragma unroll
+            for (int d = 0; d < DimOf<DT>::CAP; ++d)
+                if (d < dim) {
+                    a[d] = fabs(q[d] - tile[d * F64_TILE + j]);
+                    hit = hit && (a[d] < thr);
+                }
+            if (hit) {
+                double m = a[0];
+#pragma unroll
+                for (int d = 1; d < DimOf<DT>::CAP; ++d)
+                    if (d < dim) m = fmax(m, a[d]);
                 int r = kp - 1;
                 while (r > 0 && lst[(r - 1) * F64_THREADS + tid] > m) {
                     lst[r * F64_THREADS + tid] = lst[(r - 1) * F64_THREADS + tid];
@@ -200,11 +208,12 @@ count_f64_kernel(const double* __restrict__ pts, int64_t ld, int64_t n,
                 if (d < dim) a[d] = fabs(q[d] - tile[d * F64_TILE + j]);
 #pragma unroll
             for (int s = 0; s < F64_SUBCHUNK; ++s) {
-                double m = 0.0;
+                // max_{d in s} a_d < e  <=>  every a_d of the subspace is < e
+                bool in = true;
 #pragma unroll
                 for (int d = 0; d < DimOf<DT>::CAP; ++d)
-                    if (d < dim && ((mk[s] >> d) & 1u)) m = fmax(m, a[d]);
-                cnt[s] += strict ? (m < e[s]) : (m <= e[s]);
+                    if (d < dim && ((mk[s] >> d) & 1u)) in = in && (strict ? (a[d] < e[s]) : (a[d] <= e[s]));
+                cnt[s] += in;
             }
         }
     }
@@ -275,16 +284,17 @@ paircount_f64_kernel(const double* __restrict__ x, const double* __restrict__ y,
         unsigned int cs = 0, cb = 0;
 #pragma unroll 2
         for (int j = 0; j < jn; ++j) {
-            double sm = fabs(xi[0] - ys[j]);
+            // max_w |.| <= r  <=>  every |.| <= r  (no fp64 max in the hot loop)
+            bool sm = fabs(xi[0] - ys[j]) <= r;
 #pragma unroll
             for (int w = 1; w < CAP - 1; ++w)
-                if (w < m) sm = fmax(sm, fabs(xi[w] - ys[j + w]));
-            double bg = sm;
+                if (w < m) sm = sm && (fabs(xi[w] - ys[j + w]) <= r);
+            bool bg = sm;
 #pragma unroll
             for (int w = 1; w < CAP; ++w)
-                if (w == m) bg = fmax(sm, fabs(xi[w] - ys[j + w]));
-            cs += (sm <= r);
-            cb += (bg <= r);
+                if (w == m) bg = sm && (fabs(xi[w] - ys[j + w]) <= r);
+            cs += sm;
+            cb += bg;
         }
         small_total += cs;
         big_total += cb;
