@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000, help="samples (default: the metric's n = 1e6)")
     ap.add_argument("--k", type=int, default=5)
+    ap.add_argument("--engine", default="windowed", choices=["windowed", "dense", "exact"],
+                    help="windowed: fp32 filter + window pruning (default); dense: same kernels over all "
+                         "pairs (brute-force roofline case); exact: float64 dense kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=200_000,
                     help="samples of the C2 generator the in-line CPU baseline runs on")
@@ -187,9 +190,14 @@ def run_b200_arm(args):
             td.barrier()
         torch.cuda.synchronize()
 
+    E.config.engine = args.engine
+
+    last = {}
+
     def device_step():
-        ptw = E.ksg1_device(pts, k, masks, mi1_program)
-        full, total = E.finish_device(ptw, n)
+        ptw, prep = E.ksg1_device(pts, k, masks, mi1_program)
+        full, total = E.finish_device(ptw, n, prep)
+        last["prep"] = prep
         return full, total
 
     def e2e_step():
@@ -254,24 +262,33 @@ def run_b200_arm(args):
         # roofline of the dominant kernel(s): FP-pipe lane-ops, SURVEY.md 8(d)
         nq = E._dist.slice_of(n, 0, world)
         nq = nq[1] - nq[0]
-        pairs = float(n) * float(nq)
         a1, a2 = OPS_PER_PAIR["c2"]
         sms = torch.cuda.get_device_properties(local).multi_processor_count
         sm_max_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
-        peak = sms * 128 * sm_max_mhz * 1e6
-        knn_ms = statistics.mean(kernel_ms.get("knn_radius", [float("nan")]))
-        cnt_ms = statistics.mean(kernel_ms.get("count_subspaces", [float("nan")]))
-        psi_ms = statistics.mean(kernel_ms.get("psi_epilogue", [float("nan")]))
-        ach_knn = a1 * pairs / (knn_ms * 1e-3)
-        ach_cnt = a2 * pairs / (cnt_ms * 1e-3)
-        dominant = "knn_radius" if knn_ms >= cnt_ms else "count_subspaces"
-        ach = ach_knn if dominant == "knn_radius" else ach_cnt
         sm_load = (clocks or {}).get("sm_mhz")
+        peak = sms * 128 * sm_max_mhz * 1e6
+        mean_ms = {name: statistics.mean(v) for name, v in kernel_ms.items()}
+        if args.engine == "exact":
+            knn_name, cnt_name = "knn_radius", "count_subspaces"
+            pairs_knn = pairs_cnt = float(n) * float(nq)
+        else:
+            knn_name, cnt_name = "fast_knn", "fast_count"
+            tiles_knn, tiles_cnt = last["prep"].tiles_visited()
+            qb = 512 if rows.shape[0] <= 4 else 256          # queries per CTA of the filter kernels
+            pairs_knn = float(tiles_knn) * 512.0 * qb         # executed (query, candidate) pairs, this rank
+            pairs_cnt = float(tiles_cnt) * 512.0 * qb
+        knn_ms = mean_ms.get(knn_name, float("nan"))
+        cnt_ms = mean_ms.get(cnt_name, 0.0)
+        psi_ms = mean_ms.get("psi_epilogue", float("nan"))
+        ach_knn = a1 * pairs_knn / (knn_ms * 1e-3)
+        ach_cnt = a2 * pairs_cnt / (cnt_ms * 1e-3) if cnt_ms else 0.0
+        dominant = knn_name if knn_ms >= cnt_ms else cnt_name
+        ach = ach_knn if dominant == knn_name else ach_cnt
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        hbm_peak = 6453.1
+        hbm_peak, hbm_src = 6650.0, "fallback"
         if os.path.exists(peaks_file):
             try:
-                hbm_peak = float(json.load(open(peaks_file))["hbm_gbs"])
+                hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured"
             except Exception:
                 pass
         psi_bytes = nq * (4 * len(masks) + 8)
@@ -281,7 +298,7 @@ def run_b200_arm(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C2: KSG-1 MI 1D;1D n={n} k={k}, x vs x^2+noise (BASELINE configs[1])",
                        "parallelism": f"query-sharded x{world}", "l2": "flushed between timed steps (256 MiB write)",
-                       "engine": "dense exact fp64"},
+                       "engine": args.engine},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rows.nbytes),
                     "d2h_bytes_per_step": int(8 * n + 16), "ms_per_step": 1e3 * e2e_s / args.steps},
@@ -290,13 +307,15 @@ def run_b200_arm(args):
                          "unit": "Tlane-op/s", "frac": ach / peak, "traffic": None,
                          "peak_basis": f"{sms} SMs x 128 lanes x {sm_max_mhz:.0f} MHz (max clock)",
                          "frac_at_load_clock": (ach / (sms * 128 * sm_load * 1e6)) if sm_load else None,
-                         "ops_per_pair": {"knn_radius": a1, "count_subspaces": a2}, "pairs_per_launch": pairs,
-                         "kernels_ms": {"knn_radius": knn_ms, "count_subspaces": cnt_ms, "psi_epilogue": psi_ms},
-                         "frac_knn_radius": ach_knn / peak, "frac_count_subspaces": ach_cnt / peak,
-                         "whole_step_frac": (a1 + a2) * pairs / (ms_total / args.steps * 1e-3) / peak},
+                         "ops_per_pair": {knn_name: a1, cnt_name: a2},
+                         "pairs_per_launch": {knn_name: pairs_knn, cnt_name: pairs_cnt},
+                         "dense_pairs": float(n) * float(nq),
+                         "kernels_ms": mean_ms,
+                         "frac_" + knn_name: ach_knn / peak, "frac_" + cnt_name: ach_cnt / peak},
             "roofline_hbm": {"bound": "hbm", "kernel": "psi_epilogue", "achieved": psi_bytes / (psi_ms * 1e-3) / 1e9,
-                             "peak": hbm_peak, "unit": "GB/s", "frac": psi_bytes / (psi_ms * 1e-3) / 1e9 / hbm_peak,
-                             "traffic": None},
+                             "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
+                             "frac": psi_bytes / (psi_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+            "fallback_queries": dict(E.stats),
             "mi_nats": float(avg_host),
         }
         if not args.no_cpu_baseline and world == 1:

@@ -202,6 +202,91 @@ int ksg_paircount_fixed_radius(const double* d_x, const double* d_y, int64_t n_t
                                double r, int64_t i_begin, int64_t i_end,
                                unsigned long long* d_counts, void* stream);
 
+
+/* ================================================================== fast path
+ *
+ * The entry points above are the exact float64 dense kernels (correctness anchor and
+ * fallback).  The ones below are the production path: same results, bit for bit, from
+ * an fp32 tile filter whose boundary cases are re-decided in float64 on the device.
+ * They work on a "prepared" point set built once per estimator call.
+ */
+
+/* Device-side views of a prepared point set (all pointers into the caller's buffer). */
+typedef struct {
+    int64_t n;           /* points */
+    int32_t dim;         /* joint dimensionality D */
+    int32_t dim_padded;  /* D rounded up to even: row length of shadow_f32 */
+    int32_t primary;     /* coordinate the set is sorted by */
+    int32_t reserved;
+    int64_t ld;          /* row stride (elements) of the [dim][ld] arrays */
+    int64_t n_padded;    /* rows of shadow_f32: n rounded up to the tile length, +inf padded */
+    int32_t* perm;       /* [n]        sorted position -> original sample index */
+    double* sorted_f64;  /* [dim][ld]  the points in primary-sorted order */
+    float* shadow_f32;   /* [n_padded][dim_padded] centred fp32 copy, array-of-structures */
+    double* axis_vals;   /* [dim][ld]  every coordinate sorted ascending on its own */
+    int32_t* axis_pos;   /* [dim][ld]  sorted position (primary order) of each axis_vals entry */
+    double* center;      /* [dim]      per-coordinate centre of the fp32 copy */
+    double* maxabs;      /* [dim]      max |x - centre| (bounds the fp32 rounding error) */
+    int32_t* flags;      /* 64 bytes: int32 [0] = 1 if the input held a NaN or an infinity;
+                            uint64 at byte 16 / 24 = candidate tiles visited so far by the
+                            k-NN / count filter kernels (x 512 candidates x queries per CTA =
+                            executed pairs; for the roofline of the windowed engine) */
+} ksg_prepared;
+
+/*
+ * Sort the n points of d_points ([dim][ld] float64) by coordinate `primary`
+ * (0 <= primary < dim) and build the views above inside d_buffer
+ * (ksg_prepare_workspace(n, dim) bytes).  *h_out is filled on the host; the device
+ * work is only enqueued.  Replaces the cKDTree constructions of the path
+ * (syntropy/knn/utils.py:29 and every per-marginal tree: shannon.py:190,336;
+ * multivariate_mi.py:106,251,318-323,399-404) -- one sorted layout serves the joint
+ * space and all marginals.
+ */
+size_t ksg_prepare_workspace(int64_t n, int dim);
+int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int primary,
+                void* d_buffer, size_t buffer_bytes, ksg_prepared* h_out, void* stream);
+
+/*
+ * K1 on the prepared set: d_eps_out[i - q_begin] = exact kprime-th smallest Chebyshev
+ * distance (self included) of the point at SORTED position i, i in [q_begin, q_end).
+ * windowed != 0 prunes candidate tiles by the primary coordinate (same result, fewer
+ * pairs).  d_flags[i - q_begin] = 1 and *d_n_flagged += 1 for queries the fp32 filter
+ * could not decide (tie-saturated neighbourhoods): the caller recomputes those with
+ * ksg_knn_radius (queries = the flagged rows of sorted_f64).  d_n_flagged is caller-zeroed.
+ * Same reference call sites as ksg_knn_radius.
+ */
+size_t ksg_fast_knn_workspace(int64_t n, int64_t nq, int dim, int kprime);
+int ksg_fast_knn(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end, int kprime, int windowed,
+                 double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged,
+                 void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * K2 on the prepared set, multi-dimensional subspaces: semantics of ksg_count_subspaces
+ * with one shared radius vector (d_eps, sorted order, exact float64), queries = sorted
+ * positions [q_begin, q_end).  Recognised subspace structures (x|y, z|xz|yz,
+ * leave-one-out) run fused kernels that share partial maxima; anything else runs four
+ * masks at a time.  Flagging as in ksg_fast_knn (fallback: ksg_count_subspaces).
+ * Same reference call sites as ksg_count_subspaces.
+ */
+size_t ksg_fast_count_workspace(int64_t n, int64_t nq, int dim, int n_subspaces);
+int ksg_fast_count(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end,
+                   const uint32_t* h_masks, int n_subspaces, const double* d_eps,
+                   int strict, int32_t bias, int windowed,
+                   int32_t* d_counts, int32_t* d_flags, int32_t* d_n_flagged,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * K2 for a ONE-dimensional subspace (coordinate `axis`): the count is the length of the
+ * run around x_q in that coordinate's sorted array satisfying |fl64(x_q - v)| < eps
+ * (<= when strict == 0), found by two binary searches with the exact predicate.
+ * d_counts[i - q_begin] = run length + bias.  Always exact, never flags.
+ */
+int ksg_axis_count(const ksg_prepared* h_prep, int axis, int64_t q_begin, int64_t q_end,
+                   const double* d_eps, int strict, int32_t bias, int32_t* d_counts, void* stream);
+
+/* d_dst[perm[i]] = d_src[i], i in [0, n): pointwise values back to the caller's sample order. */
+int ksg_scatter_f64(const double* d_src, const int32_t* d_perm, int64_t n, double* d_dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

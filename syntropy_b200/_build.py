@@ -16,14 +16,15 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libksg_b200.so")
 
-NVCC_FLAGS = [
+OBJDIR = os.path.join(PKG, "build")
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     # exactness first: never contract a*b+c; the hot loops are add / compare only
     "-fmad=false",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 
 
 def _sources():
@@ -51,20 +52,43 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found; libksg_b200.so cannot be built")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if it is missing or older than its sources; return its path."""
-    if not force and not is_stale():
-        return LIB
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS]
+def _compile_one(args):
+    src, obj, verbose = args
+    cmd = [nvcc_path(), *COMPILE_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-I", os.path.join(ROOT, "include"), "-o", LIB, *_sources()]
+    cmd += ["-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return proc.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library if it is missing or older than its sources; return its path.
+    One object per translation unit, compiled in parallel, then linked."""
+    if not force and not is_stale():
+        return LIB
+    from concurrent.futures import ThreadPoolExecutor
+
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    jobs = []
+    objs = []
+    newest_header = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
+    for src in _sources():
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            jobs.append((src, obj, verbose))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        logs = list(pool.map(_compile_one, jobs))
     if verbose:
-        print(proc.stderr)
+        print("\n".join(logs))
+    cmd = [nvcc_path(), *LINK_FLAGS, "-o", LIB, *objs]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     return LIB
 
 

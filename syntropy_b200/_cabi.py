@@ -24,6 +24,29 @@ class PsiStep(C.Structure):
     ]
 
 
+class Prepared(C.Structure):
+    """ksg_prepared of include/ksg_b200.h (host struct of device pointers)."""
+    _fields_ = [
+        ("n", C.c_int64),
+        ("dim", C.c_int32),
+        ("dim_padded", C.c_int32),
+        ("primary", C.c_int32),
+        ("reserved", C.c_int32),
+        ("ld", C.c_int64),
+        ("n_padded", C.c_int64),
+        ("perm", C.c_void_p),
+        ("sorted_f64", C.c_void_p),
+        ("shadow_f32", C.c_void_p),
+        ("axis_vals", C.c_void_p),
+        ("axis_pos", C.c_void_p),
+        ("center", C.c_void_p),
+        ("maxabs", C.c_void_p),
+        ("flags", C.c_void_p),
+    ]
+
+
+_c_prep = C.POINTER(Prepared)
+
 # name -> (restype, argtypes); mirrors include/ksg_b200.h one to one
 SIGNATURES = {
     "ksg_version": (C.c_int, []),
@@ -50,6 +73,16 @@ SIGNATURES = {
                                                       _c_vp, _c_vp]),
     "ksg_paircount_fixed_radius": (C.c_int, [_c_vp, _c_vp, _c_i64, C.c_int, C.c_double, _c_i64, _c_i64,
                                              _c_vp, _c_vp]),
+    "ksg_prepare_workspace": (C.c_size_t, [_c_i64, C.c_int]),
+    "ksg_prepare": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, C.c_int, _c_vp, C.c_size_t, _c_prep, _c_vp]),
+    "ksg_fast_knn_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int, C.c_int]),
+    "ksg_fast_knn": (C.c_int, [_c_prep, _c_i64, _c_i64, C.c_int, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp,
+                               C.c_size_t, _c_vp]),
+    "ksg_fast_count_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int, C.c_int]),
+    "ksg_fast_count": (C.c_int, [_c_prep, _c_i64, _c_i64, C.POINTER(C.c_uint32), C.c_int, _c_vp, C.c_int,
+                                 C.c_int32, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),
+    "ksg_axis_count": (C.c_int, [_c_prep, C.c_int, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int32, _c_vp, _c_vp]),
+    "ksg_scatter_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
 }
 
 _lib = None

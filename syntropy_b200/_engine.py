@@ -210,6 +210,139 @@ def device_sum(values: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------ fast path (prepared set)
+class Config:
+    """Engine selection.  ``engine``:
+      "windowed" (default) fp32 tile filter + exact fp64 resolution, candidate tiles pruned
+                           by the sort coordinate;
+      "dense"              the same kernels scanning every tile (the brute-force roofline case);
+      "exact"              the float64 dense kernels (anchor / fallback; also used for > 8 dims).
+    All three give identical radii and counts."""
+    engine = "windowed"
+    primary = 0
+
+
+config = Config()
+
+
+class PreparedSet:
+    """Host handle of a ksg_prepared: the struct, the owning buffer and typed views."""
+
+    def __init__(self, pts: torch.Tensor, primary: int):
+        lib = _cabi.load()
+        dim, n = pts.shape
+        size = int(lib.ksg_prepare_workspace(n, dim))
+        self.buf = torch.empty(size, dtype=torch.uint8, device=pts.device)
+        self.c = _cabi.Prepared()
+        with timer.span("prepare"):
+            rc = lib.ksg_prepare(_ptr(pts), pts.stride(0), n, dim, primary, _ptr(self.buf), size,
+                                 C.byref(self.c), _stream())
+        _cabi.check(rc, "ksg_prepare")
+        self.n, self.dim, self.ld = n, dim, int(self.c.ld)
+
+    def _view(self, ptr, nbytes, dtype):
+        off = int(ptr) - self.buf.data_ptr()
+        return self.buf[off:off + nbytes].view(dtype)
+
+    @property
+    def sorted_f64(self) -> torch.Tensor:  # (dim, n) view with row stride ld
+        return self._view(self.c.sorted_f64, self.dim * self.ld * 8, torch.float64).view(self.dim, self.ld)[:, :self.n]
+
+    @property
+    def perm(self) -> torch.Tensor:
+        return self._view(self.c.perm, self.n * 4, torch.int32)
+
+    @property
+    def flags(self) -> torch.Tensor:
+        return self._view(self.c.flags, 4, torch.int32)
+
+    def tiles_visited(self):
+        """(k-NN filter tiles, count filter tiles) visited so far (uint64 counters)."""
+        t = self._view(self.c.flags, 64, torch.int64).cpu()
+        return int(t[2]), int(t[3])
+
+
+def fast_knn(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool) -> torch.Tensor:
+    """Exact k'-th-neighbour radii of sorted positions [q0, q1) (fp32 filter, fp64 refine,
+    dense-fp64 recomputation of the queries the filter could not decide)."""
+    lib = _cabi.load()
+    nq = q1 - q0
+    dev = prep.buf.device
+    eps = torch.empty(nq, dtype=torch.float64, device=dev)
+    flags = torch.empty(nq, dtype=torch.int32, device=dev)
+    nflag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(int(lib.ksg_fast_knn_workspace(prep.n, max(nq, 1), prep.dim, kprime)), 1),
+                     dtype=torch.uint8, device=dev)
+    with timer.span("fast_knn"):
+        rc = lib.ksg_fast_knn(C.byref(prep.c), q0, q1, kprime, 1 if windowed else 0, _ptr(eps), _ptr(flags),
+                              _ptr(nflag), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "ksg_fast_knn")
+    if nq and int(nflag.item()):
+        idx = flags.nonzero().flatten()
+        stats["knn_fallback_queries"] += int(idx.numel())
+        pts = prep.sorted_f64
+        queries = pts[:, q0 + idx].contiguous()
+        eps[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries)
+    return eps
+
+
+def fast_counts(prep: PreparedSet, masks, eps: torch.Tensor, q0: int, q1: int, windowed: bool,
+                strict: bool = True, bias: int = -1) -> torch.Tensor:
+    """counts[s][q] for sorted positions [q0, q1): 1-D subspaces by binary search in the
+    coordinate's sorted array, the others by one fused fp32 pass + exact band resolution."""
+    lib = _cabi.load()
+    nq = q1 - q0
+    dev = prep.buf.device
+    counts = torch.empty((len(masks), nq), dtype=torch.int32, device=dev)
+    multi = [s for s, m in enumerate(masks) if bin(m).count("1") > 1]
+    single = [s for s, m in enumerate(masks) if bin(m).count("1") == 1]
+    if multi:
+        mm = [masks[s] for s in multi]
+        out = counts if len(multi) == len(masks) else torch.empty((len(mm), nq), dtype=torch.int32, device=dev)
+        flags = torch.empty(nq, dtype=torch.int32, device=dev)
+        nflag = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(max(int(lib.ksg_fast_count_workspace(prep.n, max(nq, 1), prep.dim, len(mm))), 1),
+                         dtype=torch.uint8, device=dev)
+        with timer.span("fast_count"):
+            rc = lib.ksg_fast_count(C.byref(prep.c), q0, q1, _masks(mm), len(mm), _ptr(eps), 1 if strict else 0,
+                                    bias, 1 if windowed else 0, _ptr(out), _ptr(flags), _ptr(nflag), _ptr(ws),
+                                    ws.numel(), _stream())
+        _cabi.check(rc, "ksg_fast_count")
+        if nq and int(nflag.item()):
+            idx = flags.nonzero().flatten()
+            stats["count_fallback_queries"] += int(idx.numel())
+            pts = prep.sorted_f64
+            queries = pts[:, q0 + idx].contiguous()
+            out[:, idx] = count_subspaces(pts, mm, eps[idx].contiguous(), 0, int(idx.numel()), strict=strict,
+                                          bias=bias, queries=queries)
+        if out is not counts:
+            for row, s in enumerate(multi):
+                counts[s] = out[row]
+    for s in single:
+        axis = int(masks[s]).bit_length() - 1
+        with timer.span("axis_count"):
+            rc = lib.ksg_axis_count(C.byref(prep.c), axis, q0, q1, _ptr(eps), 1 if strict else 0, bias,
+                                    _ptr(counts[s]), _stream())
+        _cabi.check(rc, "ksg_axis_count")
+    return counts
+
+
+def scatter_to_original(values_sorted: torch.Tensor, prep: PreparedSet) -> torch.Tensor:
+    out = torch.empty_like(values_sorted)
+    rc = _cabi.load().ksg_scatter_f64(_ptr(values_sorted), _ptr(prep.perm), prep.n, _ptr(out), _stream())
+    _cabi.check(rc, "ksg_scatter_f64")
+    return out
+
+
+stats = {"knn_fallback_queries": 0, "count_fallback_queries": 0}
+
+
+def _use_fast(dim: int) -> bool:
+    if config.engine not in ("windowed", "dense", "exact"):
+        raise ValueError("config.engine must be 'windowed', 'dense' or 'exact'")
+    return config.engine != "exact" and dim <= 8
+
+
 def check_finite(points: torch.Tensor) -> torch.Tensor:
     flag = torch.zeros(1, dtype=torch.int32, device=points.device)
     assert points.is_contiguous()
@@ -218,15 +351,18 @@ def check_finite(points: torch.Tensor) -> torch.Tensor:
     return flag
 
 
-def finish_device(ptw_slice: torch.Tensor, n_total: int):
-    """All-gather the pointwise slices (NCCL) and reduce the full vector in a fixed order."""
+def finish_device(ptw_slice: torch.Tensor, n_total: int, prep=None):
+    """All-gather the pointwise slices (NCCL), put them back into the caller's sample order
+    if they were computed in sorted order, and reduce the full vector in a fixed order."""
     ptw_full = _dist.gather_slices(ptw_slice, n_total)
+    if prep is not None:
+        ptw_full = scatter_to_original(ptw_full, prep)
     return ptw_full, device_sum(ptw_full)
 
 
-def _finish(ptw_slice: torch.Tensor, n_total: int, flag: torch.Tensor):
+def _finish(ptw_slice: torch.Tensor, n_total: int, flag: torch.Tensor, prep=None):
     """Gather the pointwise slices of all ranks, reduce deterministically, copy out."""
-    ptw_full, total = finish_device(ptw_slice, n_total)
+    ptw_full, total = finish_device(ptw_slice, n_total, prep)
     host = torch.cat([ptw_full, total, flag.to(torch.float64)]).cpu().numpy()
     if host[-1] != 0.0:
         # what scipy's cKDTree constructor raises, reached from knn/utils.py:29
@@ -247,18 +383,25 @@ def ksg1_family(rows: np.ndarray, k: int, masks, prog_builder):
     """
     pts = to_device_points(rows)
     flag = check_finite(pts)
-    ptw = ksg1_device(pts, k, masks, prog_builder)
-    return _finish(ptw, pts.shape[1], flag)
+    ptw, prep = ksg1_device(pts, k, masks, prog_builder)
+    return _finish(ptw, pts.shape[1], flag, prep)
 
 
-def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder) -> torch.Tensor:
-    """The device-resident part of ``ksg1_family``: this rank's pointwise slice."""
-    n = pts.shape[1]
+def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder):
+    """The device-resident part of ``ksg1_family``: this rank's pointwise slice, plus the
+    prepared set when the slice is in sorted order (``None`` for the exact engine)."""
+    dim, n = pts.shape
     q0, q1 = _dist.my_slice(n)
-    eps = knn_radius(pts, k + 1, q0, q1)
-    counts = count_subspaces(pts, masks, eps, q0, q1, strict=True, bias=-1)
     prog = prog_builder(psi_host(k), psi_host(n))
-    return psi_epilogue(counts, prog, n)
+    if not _use_fast(dim):
+        eps = knn_radius(pts, k + 1, q0, q1)
+        counts = count_subspaces(pts, masks, eps, q0, q1, strict=True, bias=-1)
+        return psi_epilogue(counts, prog, n), None
+    windowed = config.engine == "windowed"
+    prep = PreparedSet(pts, min(config.primary, dim - 1))
+    eps = fast_knn(prep, k + 1, q0, q1, windowed)
+    counts = fast_counts(prep, masks, eps, q0, q1, windowed)
+    return psi_epilogue(counts, prog, n), prep
 
 
 def ksg2_family(rows: np.ndarray, k: int, masks, prog_builder):
@@ -285,11 +428,16 @@ def kl_entropy(rows: np.ndarray, k: int):
     dim, n = pts.shape
     flag = check_finite(pts)
     q0, q1 = _dist.my_slice(n)
-    eps = knn_radius(pts, k + 1, q0, q1)
+    prep = None
+    if _use_fast(dim):
+        prep = PreparedSet(pts, min(config.primary, dim - 1))
+        eps = fast_knn(prep, k + 1, q0, q1, config.engine == "windowed")
+    else:
+        eps = knn_radius(pts, k + 1, q0, q1)
     ptw = torch.empty(q1 - q0, dtype=torch.float64, device=pts.device)
     rc = _cabi.load().ksg_entropy_epilogue(_ptr(eps), q1 - q0, dim, psi_host(k), psi_host(n), _ptr(ptw), _stream())
     _cabi.check(rc, "ksg_entropy_epilogue")
-    return _finish(ptw, n, flag)
+    return _finish(ptw, n, flag, prep)
 
 
 def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):

@@ -31,7 +31,7 @@ __device__ inline double psi_of_int(int64_t n) {
     return __dsub_rn(__dsub_rn(log(s), __ddiv_rn(0.5, s)), y);
 }
 
-__global__ void psi_table_kernel(double* __restrict__ table, int64_t entries) {
+static __global__ void psi_table_kernel(double* __restrict__ table, int64_t entries) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < entries) table[i] = psi_of_int(i);
 }
@@ -51,7 +51,7 @@ struct PsiProgram {
     double divisor[MAX_PSI_STEPS];
 };
 
-__global__ void psi_epilogue_kernel(const int32_t* __restrict__ counts, int64_t nq,
+static __global__ void psi_epilogue_kernel(const int32_t* __restrict__ counts, int64_t nq,
                                     const __grid_constant__ PsiProgram prog,
                                     const double* __restrict__ table, int64_t entries,
                                     double* __restrict__ ptw) {
@@ -69,7 +69,7 @@ __global__ void psi_epilogue_kernel(const int32_t* __restrict__ counts, int64_t 
     ptw[qi] = v;
 }
 
-__global__ void entropy_epilogue_kernel(const double* __restrict__ eps, int64_t nq, double dimf,
+static __global__ void entropy_epilogue_kernel(const double* __restrict__ eps, int64_t nq, double dimf,
                                         double base, double* __restrict__ ptw) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -78,7 +78,7 @@ __global__ void entropy_epilogue_kernel(const double* __restrict__ eps, int64_t 
     ptw[qi] = __dadd_rn(0.0, __dadd_rn(base, t));
 }
 
-__global__ void kl_epilogue_kernel(const double* __restrict__ nu, const double* __restrict__ rho,
+static __global__ void kl_epilogue_kernel(const double* __restrict__ nu, const double* __restrict__ rho,
                                    int64_t nq, double dimf, double log_ratio, double* __restrict__ ptw) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -86,7 +86,7 @@ __global__ void kl_epilogue_kernel(const double* __restrict__ nu, const double* 
     ptw[qi] = __dadd_rn(__dmul_rn(dimf, log(__ddiv_rn(nu[qi], rho[qi]))), log_ratio);
 }
 
-__global__ void check_finite_kernel(const double* __restrict__ v, int64_t count, int32_t* __restrict__ flag) {
+static __global__ void check_finite_kernel(const double* __restrict__ v, int64_t count, int32_t* __restrict__ flag) {
     int bad = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
          i += (int64_t)gridDim.x * blockDim.x)
@@ -111,7 +111,7 @@ __device__ inline double block_tree_sum(double v) {
     return sh[0];
 }
 
-__global__ void __launch_bounds__(SUM_THREADS)
+static __global__ void __launch_bounds__(SUM_THREADS)
 sum_stage1_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ partial) {
     const int64_t chunk = (n + SUM_BLOCKS - 1) / SUM_BLOCKS;
     const int64_t lo = (int64_t)blockIdx.x * chunk;
@@ -122,7 +122,7 @@ sum_stage1_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ 
     if (threadIdx.x == 0) partial[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(SUM_THREADS)
+static __global__ void __launch_bounds__(SUM_THREADS)
 sum_stage2_kernel(const double* __restrict__ partial, double* __restrict__ out) {
     double acc = 0.0;
     for (int i = threadIdx.x; i < SUM_BLOCKS; i += SUM_THREADS) acc = __dadd_rn(acc, partial[i]);

@@ -38,7 +38,7 @@ __device__ __forceinline__ void stage_tile_f64(double* __restrict__ tile, const 
 // ---------------------------------------------------------------------------------- K1
 // part_dist[(split * kp + r) * nq + q] = r-th smallest distance seen by this split.
 template <int DT, bool WITH_IDX>
-__global__ void __launch_bounds__(F64_THREADS)
+static __global__ void __launch_bounds__(F64_THREADS)
 knn_f64_kernel(const double* __restrict__ pts, int64_t ld, int64_t n,
                const double* __restrict__ qry, int64_t ldq, int64_t q_begin, int64_t nq,
                int dim_rt, int kp, int64_t cand_per_split,
@@ -114,7 +114,7 @@ knn_f64_kernel(const double* __restrict__ pts, int64_t ld, int64_t n,
 // Merge the per-split lists: kp-th smallest of the union (and the kp (dist, idx)
 // pairs in ascending lexicographic order when indices are requested).
 template <bool WITH_IDX>
-__global__ void knn_merge_kernel(const double* __restrict__ part_dist, const int64_t* __restrict__ part_idx,
+static __global__ void knn_merge_kernel(const double* __restrict__ part_dist, const int64_t* __restrict__ part_idx,
                                  int64_t nq, int kp, int splits,
                                  double* __restrict__ eps_out, int64_t* __restrict__ idx_out) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,14 +154,14 @@ struct MaskTable {
     uint32_t m[KSG_MAX_SUBSPACES];
 };
 
-__global__ void fill_i32_kernel(int32_t* __restrict__ p, int64_t count, int32_t v) {
+static __global__ void fill_i32_kernel(int32_t* __restrict__ p, int64_t count, int32_t v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) p[i] = v;
 }
 
 // counts[(s0 + s) * nq + q] += #{candidates in this split inside the ball of subspace s}
 template <int DT>
-__global__ void __launch_bounds__(F64_THREADS)
+static __global__ void __launch_bounds__(F64_THREADS)
 count_f64_kernel(const double* __restrict__ pts, int64_t ld, int64_t n,
                  const double* __restrict__ qry, int64_t ldq, int64_t q_begin, int64_t nq,
                  int dim_rt, const MaskTable masks, int n_sub,
@@ -225,7 +225,7 @@ count_f64_kernel(const double* __restrict__ pts, int64_t ld, int64_t n,
 }
 
 // ---------------------------------------------------------------------------------- KSG-2 helper
-__global__ void subspace_radius_kernel(const double* __restrict__ pts, int64_t ld, int dim,
+static __global__ void subspace_radius_kernel(const double* __restrict__ pts, int64_t ld, int dim,
                                        int64_t q_begin, int64_t nq, int64_t n,
                                        const int64_t* __restrict__ idx, int kp, int skip_first,
                                        const MaskTable masks, int n_sub,
@@ -254,7 +254,7 @@ constexpr int PC_TILE = 1024;
 
 // MT > 0: compile-time small-template length m; MT == 0: run-time m (<= KSG_MAX_DIM - 1).
 template <int MT>
-__global__ void __launch_bounds__(PC_THREADS)
+static __global__ void __launch_bounds__(PC_THREADS)
 paircount_f64_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t nt, int m_rt,
                      double r, int64_t i_begin, int64_t ni, int64_t cand_per_split,
                      unsigned long long* __restrict__ out) {

@@ -1,0 +1,310 @@
+// extern "C" entry points of the fast path (prepare / fast_knn / fast_count / axis_count).
+#include <string.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "exact_f64.cuh"
+#include "fast_count.cuh"
+#include "fast_knn.cuh"
+#include "fast_launch.h"
+#include "prepare.cuh"
+
+namespace ksg {
+
+static inline size_t cub_sort_bytes(int64_t n) {
+    size_t bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const double*)nullptr, (double*)nullptr,
+                                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+    if (e != cudaSuccess || bytes == 0) {
+        (void)cudaGetLastError();
+        bytes = (size_t)n * 16 + (16u << 20);  // no device visible: conservative estimate
+    }
+    return bytes;
+}
+
+static inline PreparedLayout prepared_layout(int64_t n, int dim) {
+    PreparedLayout L;
+    L.ld = (int64_t)align_up((size_t)n, 32);
+    L.n_padded = (int64_t)align_up((size_t)n, FAST_TILE);
+    L.dim_padded = (dim + 1) & ~1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    L.off_perm = take((size_t)L.ld * 4);
+    L.off_sorted = take((size_t)dim * L.ld * 8);
+    L.off_shadow = take((size_t)L.n_padded * L.dim_padded * 4);
+    L.off_axis_vals = take((size_t)dim * L.ld * 8);
+    L.off_axis_pos = take((size_t)dim * L.ld * 4);
+    L.off_center = take((size_t)KSG_MAX_DIM * 8);
+    L.off_maxabs = take((size_t)KSG_MAX_DIM * 8);
+    L.off_flags = take(64);
+    L.off_stats = take((size_t)dim * STATS_BLOCKS * 2 * 8);
+    L.off_iota = take((size_t)L.ld * 4);
+    L.off_keys_tmp = take((size_t)L.ld * 8);
+    L.cub_bytes = cub_sort_bytes(n);
+    L.off_cub = take(L.cub_bytes);
+    L.total = o;
+    return L;
+}
+
+
+#define KSG_LAUNCHED2()                   \
+    do {                                  \
+        note_launch();                    \
+        KSG_CUDA_TRY(cudaGetLastError()); \
+    } while (0)
+
+static inline cudaStream_t as_stream2(void* s) { return (cudaStream_t)s; }
+
+static int sort_pairs(void* cub_tmp, size_t cub_bytes, const double* keys_in, double* keys_out,
+                      const int32_t* vals_in, int32_t* vals_out, int64_t n, cudaStream_t st) {
+    size_t need = cub_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, keys_in, keys_out, vals_in, vals_out, (int)n, 0,
+                                                    64, st);
+    if (e != cudaSuccess) {
+        set_error("cub::DeviceRadixSort::SortPairs: %s", cudaGetErrorString(e));
+        return KSG_ECUDA;
+    }
+    note_launch();
+    return KSG_OK;
+}
+
+struct FastKnnPlan {
+    int kcap, splits, qb;
+    size_t d32_bytes, idx_bytes;
+};
+static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int windowed) {
+    FastKnnPlan p;
+    const int dp = (dim + 1) & ~1;
+    p.kcap = kprime + KNN_MARGIN;
+    p.qb = knn_f32_queries_per_block(dp);
+    const int64_t qblocks = ceil_div(nq, p.qb);
+    p.splits = windowed ? 1 : choose_splits(qblocks, n, FAST_TILE);
+    p.d32_bytes = align_up((size_t)p.splits * p.kcap * nq * sizeof(float), 256);
+    p.idx_bytes = align_up((size_t)p.splits * p.kcap * nq * sizeof(int32_t), 256);
+    return p;
+}
+
+}  // namespace ksg
+
+using namespace ksg;
+
+extern "C" {
+
+size_t ksg_prepare_workspace(int64_t n, int dim) {
+    if (n <= 0 || dim < 1 || dim > KSG_MAX_DIM) return 0;
+    return prepared_layout(n, dim).total;
+}
+
+int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int primary, void* d_buffer,
+                size_t buffer_bytes, ksg_prepared* h_out, void* stream) {
+    KSG_REQUIRE(d_points && d_buffer && h_out, "ksg_prepare: null pointer");
+    KSG_REQUIRE(n > 0 && n < (1ll << 31) - 1024 && ld >= n, "ksg_prepare: need 0 < n < 2^31 and ld >= n");
+    KSG_REQUIRE(dim >= 1 && dim <= KSG_MAX_DIM, "ksg_prepare: dim out of range");
+    KSG_REQUIRE(primary >= 0 && primary < dim, "ksg_prepare: primary coordinate out of range");
+    const PreparedLayout L = prepared_layout(n, dim);
+    if (buffer_bytes < L.total) {
+        set_error("ksg_prepare: buffer of %zu bytes needed, %zu given", L.total, buffer_bytes);
+        return KSG_EWORKSPACE;
+    }
+    char* base = (char*)d_buffer;
+    ksg_prepared P;
+    memset(&P, 0, sizeof(P));
+    P.n = n; P.dim = dim; P.dim_padded = L.dim_padded; P.primary = primary; P.ld = L.ld; P.n_padded = L.n_padded;
+    P.perm = (int32_t*)(base + L.off_perm);
+    P.sorted_f64 = (double*)(base + L.off_sorted);
+    P.shadow_f32 = (float*)(base + L.off_shadow);
+    P.axis_vals = (double*)(base + L.off_axis_vals);
+    P.axis_pos = (int32_t*)(base + L.off_axis_pos);
+    P.center = (double*)(base + L.off_center);
+    P.maxabs = (double*)(base + L.off_maxabs);
+    P.flags = (int32_t*)(base + L.off_flags);
+    double* stats = (double*)(base + L.off_stats);
+    int32_t* iota = (int32_t*)(base + L.off_iota);
+    double* keys_tmp = (double*)(base + L.off_keys_tmp);
+    void* cub_tmp = base + L.off_cub;
+    cudaStream_t st = as_stream2(stream);
+
+    KSG_CUDA_TRY(cudaMemsetAsync(P.flags, 0, 64, st));
+    stats_stage1_kernel<<<dim3(STATS_BLOCKS, dim), 256, 0, st>>>(d_points, ld, n, stats, P.flags);
+    KSG_LAUNCHED2();
+    stats_stage2_kernel<<<1, KSG_MAX_DIM, 0, st>>>(stats, dim, P.center, P.maxabs);
+    KSG_LAUNCHED2();
+    iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
+    KSG_LAUNCHED2();
+    // primary sort: keys = the primary coordinate, values = original index -> perm
+    int rc = sort_pairs(cub_tmp, L.cub_bytes, d_points + (int64_t)primary * ld, keys_tmp, iota, P.perm, n, st);
+    if (rc) return rc;
+    gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
+        d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
+    KSG_LAUNCHED2();
+    // every coordinate sorted on its own, remembering the primary-order position
+    for (int d = 0; d < dim; ++d) {
+        double* vals = P.axis_vals + (int64_t)d * L.ld;
+        int32_t* pos = P.axis_pos + (int64_t)d * L.ld;
+        if (d == primary) {
+            copy_axis_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(P.sorted_f64 + (int64_t)d * L.ld, vals, pos, n);
+            KSG_LAUNCHED2();
+        } else {
+            rc = sort_pairs(cub_tmp, L.cub_bytes, P.sorted_f64 + (int64_t)d * L.ld, vals, iota, pos, n, st);
+            if (rc) return rc;
+        }
+    }
+    *h_out = P;
+    return KSG_OK;
+}
+
+size_t ksg_fast_knn_workspace(int64_t n, int64_t nq, int dim, int kprime) {
+    if (n <= 0 || nq <= 0 || dim < 1 || kprime < 1) return 0;
+    // sized for the dense (split) launch; the windowed launch needs less
+    FastKnnPlan p = fast_knn_plan(n, nq, dim, kprime, 0);
+    return p.d32_bytes + p.idx_bytes + 256;
+}
+
+int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, int kprime, int windowed,
+                 double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged, void* d_workspace,
+                 size_t workspace_bytes, void* stream) {
+    KSG_REQUIRE(P && d_eps_out && d_flags && d_n_flagged && d_workspace, "ksg_fast_knn: null pointer");
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_fast_knn: bad query range");
+    KSG_REQUIRE(kprime >= 1 && kprime + KNN_MARGIN <= KSG_MAX_KPRIME, "ksg_fast_knn: kprime out of range");
+    if (P->dim_padded > 8) {
+        set_error("ksg_fast_knn: the fp32 filter is instantiated for up to 8 dimensions (got %d); use ksg_knn_radius",
+                  P->dim);
+        return KSG_EUNSUPPORTED;
+    }
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    FastKnnPlan p = fast_knn_plan(P->n, nq, P->dim, kprime, windowed);
+    if (workspace_bytes < p.d32_bytes + p.idx_bytes) {
+        set_error("ksg_fast_knn: workspace of %zu bytes needed, %zu given", p.d32_bytes + p.idx_bytes, workspace_bytes);
+        return KSG_EWORKSPACE;
+    }
+    cudaStream_t st = as_stream2(stream);
+    KnnF32Args a;
+    a.shadow = P->shadow_f32; a.n_tiles = P->n_padded / FAST_TILE; a.primary = P->primary;
+    a.q_begin = q_begin; a.nq = nq; a.kcap = p.kcap; a.splits = p.splits; a.windowed = windowed ? 1 : 0;
+    a.maxabs = P->maxabs; a.dim = P->dim;
+    a.part_d32 = (float*)d_workspace;
+    a.part_idx = (int32_t*)((char*)d_workspace + p.d32_bytes);
+    a.tile_counter = (unsigned long long*)((char*)P->flags + 16);
+    a.st = st;
+    int rc = launch_knn_f32(P->dim_padded, a);
+    if (rc) return rc;
+    knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, p.splits, kprime,
+                                                                   P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
+                                                                   P->maxabs, d_eps_out, d_flags, d_n_flagged);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+size_t ksg_fast_count_workspace(int64_t n, int64_t nq, int dim, int n_subspaces) {
+    (void)n; (void)dim; (void)n_subspaces;
+    return align_up((size_t)(nq > 0 ? nq : 1) * sizeof(float), 256);
+}
+
+int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const uint32_t* h_masks,
+                   int n_subspaces, const double* d_eps, int strict, int32_t bias, int windowed,
+                   int32_t* d_counts, int32_t* d_flags, int32_t* d_n_flagged, void* d_workspace,
+                   size_t workspace_bytes, void* stream) {
+    KSG_REQUIRE(P && h_masks && d_eps && d_counts && d_flags && d_n_flagged && d_workspace,
+                "ksg_fast_count: null pointer");
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_fast_count: bad query range");
+    KSG_REQUIRE(n_subspaces >= 1 && n_subspaces <= KSG_MAX_SUBSPACES, "ksg_fast_count: subspace count");
+    if (P->dim_padded > 8) {
+        set_error("ksg_fast_count: the fp32 filter is instantiated for up to 8 dimensions (got %d)", P->dim);
+        return KSG_EUNSUPPORTED;
+    }
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    KSG_REQUIRE(workspace_bytes >= (size_t)nq * sizeof(float), "ksg_fast_count: workspace too small");
+    const int dim = P->dim;
+    const uint32_t all = dim == 32 ? 0xffffffffu : ((1u << dim) - 1u);
+    bool all_have_primary = true;
+    for (int s = 0; s < n_subspaces; ++s) {
+        KSG_REQUIRE(h_masks[s] != 0 && (h_masks[s] & ~all) == 0, "ksg_fast_count: empty or out-of-range mask");
+        all_have_primary = all_have_primary && ((h_masks[s] >> P->primary) & 1u);
+    }
+    cudaStream_t st = as_stream2(stream);
+    float* thresholds = (float*)d_workspace;
+    const int64_t total = (int64_t)n_subspaces * nq;
+    fill_i32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(d_counts, total, bias);
+    KSG_LAUNCHED2();
+    KSG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)nq * sizeof(int32_t), st));
+    count_thresholds_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(d_eps, nq, P->maxabs, dim, thresholds);
+    KSG_LAUNCHED2();
+
+    CountF32Args a;
+    memset(&a, 0, sizeof(a));
+    a.shadow = P->shadow_f32; a.n_tiles = P->n_padded / FAST_TILE; a.primary = P->primary;
+    a.q_begin = q_begin; a.nq = nq; a.thresholds = thresholds;
+    a.windowed = (windowed && all_have_primary) ? 1 : 0;
+    a.n_sub = n_subspaces; a.counts = d_counts; a.st = st;
+    a.tile_counter = (unsigned long long*)((char*)P->flags + 24);
+    const int64_t qblocks = ceil_div(nq, count_f32_queries_per_block(P->dim_padded));
+    a.splits = a.windowed ? 1 : choose_splits(qblocks, P->n, FAST_TILE);
+
+    // recognise the fused structures
+    int rc = KSG_EUNSUPPORTED;
+    auto low = [](int bits) { return bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u); };
+    if (n_subspaces == 2) {
+        const int dx = __builtin_popcount(h_masks[0]), dy = __builtin_popcount(h_masks[1]);
+        if (dx + dy == dim && h_masks[0] == low(dx) && h_masks[1] == (low(dy) << dx)) rc = launch_count_pair(dx, dy, a);
+    } else if (n_subspaces == 3) {
+        const int dz = __builtin_popcount(h_masks[0]);
+        const int dx = __builtin_popcount(h_masks[1]) - dz, dy = __builtin_popcount(h_masks[2]) - dz;
+        if (dx >= 1 && dy >= 1 && dx + dy + dz == dim) {
+            const uint32_t mz = low(dz) << (dx + dy), mx = low(dx), my = low(dy) << dx;
+            if (h_masks[0] == mz && h_masks[1] == (mx | mz) && h_masks[2] == (my | mz)) rc = launch_count_cmi(dx, dy, dz, a);
+        }
+    }
+    if (rc == KSG_EUNSUPPORTED && n_subspaces == dim && dim >= 3) {
+        bool loo = true;
+        for (int s = 0; s < dim; ++s) loo = loo && (h_masks[s] == (all & ~(1u << s)));
+        if (loo) rc = launch_count_loo(dim, a);
+    }
+    if (rc == KSG_EUNSUPPORTED) {
+        // generic: four run-time masks per launch
+        for (int s0 = 0; s0 < n_subspaces; s0 += 4) {
+            CountF32Args b = a;
+            b.n_sub = n_subspaces - s0 < 4 ? n_subspaces - s0 : 4;
+            for (int i = 0; i < 4; ++i) b.masks[i] = i < b.n_sub ? h_masks[s0 + i] : 0u;
+            b.counts = d_counts + (int64_t)s0 * nq;
+            rc = launch_count_masked(P->dim_padded, b);
+            if (rc) return rc;
+        }
+    }
+    if (rc) return rc;
+
+    MaskTable64 mt;
+    memset(&mt, 0, sizeof(mt));
+    for (int s = 0; s < n_subspaces; ++s) mt.m[s] = h_masks[s];
+    count_fix_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(
+        P->sorted_f64, P->ld, P->shadow_f32, dim, P->dim_padded, P->n, P->axis_vals, P->axis_pos, P->maxabs, q_begin,
+        nq, d_eps, thresholds, mt, n_subspaces, strict ? 1 : 0, d_counts, d_flags, d_n_flagged);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+int ksg_axis_count(const ksg_prepared* P, int axis, int64_t q_begin, int64_t q_end, const double* d_eps, int strict,
+                   int32_t bias, int32_t* d_counts, void* stream) {
+    KSG_REQUIRE(P && d_eps && d_counts, "ksg_axis_count: null pointer");
+    KSG_REQUIRE(axis >= 0 && axis < P->dim, "ksg_axis_count: axis out of range");
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_axis_count: bad query range");
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    axis_count_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, as_stream2(stream)>>>(
+        P->sorted_f64 + (int64_t)axis * P->ld, P->axis_vals + (int64_t)axis * P->ld, P->n, q_begin, nq, d_eps,
+        strict ? 1 : 0, bias, d_counts);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+int ksg_scatter_f64(const double* d_src, const int32_t* d_perm, int64_t n, double* d_dst, void* stream) {
+    KSG_REQUIRE(d_src && d_perm && d_dst && n >= 0, "ksg_scatter_f64: bad argument");
+    if (n == 0) return KSG_OK;
+    scatter_f64_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream2(stream)>>>(d_src, d_perm, n, d_dst);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+}  // extern "C"

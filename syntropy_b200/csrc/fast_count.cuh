@@ -1,0 +1,435 @@
+// K2 fast path: strict-radius neighbour counts in several subspaces from ONE pass over
+// the candidates, fp32 filter + exact fp64 resolution of the boundary band.
+//
+// count_f32_kernel<Spec, Q>: same tiling as the k-NN filter (prepared fp32 AoS shadow,
+// bulk-copied tiles, Q queries per thread in registers).  Per (query, candidate):
+// DP/2 FADD2 form all coordinate differences once; the Spec turns their magnitudes into
+// the S subspace maxima sharing partial maxima (3-input FMNMX3); each subspace costs one
+// FSET (1.0f / 0.0f) against the query's threshold T and half a packed FADD2 into a
+// float counter (exact: flushed to int32 every tile).  T = fp32_up(eps + delta) so the
+// pass over-counts only inside the error band; no branch, no second compare.
+//
+// count_fix_kernel: for every query, the only candidates the filter can have
+// misjudged have, in some coordinate, | |x_q - x_j| - eps | <= 4*delta.  They are found
+// in the per-coordinate sorted arrays of the prepared set by binary search (a handful
+// per query), re-evaluated with the filter's exact fp32 arithmetic AND in float64, and
+// the counts corrected.  Queries whose band is too crowded (tie-saturated data) are
+// flagged for the dense fp64 kernel.
+//
+// axis_count_kernel: a 1-D marginal needs no pass at all -- its count is the length of
+// the run around x_q in that coordinate's sorted array that satisfies the exact
+// predicate |fl64(x_q - v)| < eps, found by two binary searches.
+#pragma once
+
+#include "common.cuh"
+#include "fast_knn.cuh"
+#include "prepare.cuh"
+
+namespace ksg {
+
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "add.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+
+// The filter threshold for a query: the smallest fp32 >= eps + delta(eps), one ulp up.
+__device__ __forceinline__ float count_threshold(double eps, double mmax) {
+    if (!(eps < CUDART_INF)) return CUDART_INF_F;
+    const float t = __double2float_ru(eps + band_f64(mmax, eps));
+    return nextafterf(t, CUDART_INF_F);
+}
+
+// ---------------------------------------------------------------- subspace specs
+// a[d] = |q_d - c_d| for the DP (even-padded) joint dimensions; m[s] = subspace maxima.
+template <int LO, int HI>
+__device__ __forceinline__ float max_range(const float* a) {
+    static_assert(HI > LO, "empty range");
+    if constexpr (HI - LO == 1) return a[LO];
+    else if constexpr (HI - LO == 2) return fmaxf(a[LO], a[LO + 1]);
+    else if constexpr (HI - LO == 3) return max3f(a[LO], a[LO + 1], a[LO + 2]);
+    else return max3f(a[LO], a[LO + 1], max_range<LO + 2, HI>(a));
+}
+
+// two disjoint groups: x = [0,DX), y = [DX,DX+DY)            (mutual information)
+template <int DX, int DY>
+struct SpecPair {
+    static constexpr int D = DX + DY, DP = (D + 1) & ~1, S = 2;
+    __device__ __forceinline__ static void eval(const float* a, float* m) {
+        m[0] = max_range<0, DX>(a);
+        m[1] = max_range<DX, DX + DY>(a);
+    }
+};
+
+// three groups x, y, z; subspaces z, xz, yz                   (conditional MI)
+template <int DX, int DY, int DZ>
+struct SpecCmi {
+    static constexpr int D = DX + DY + DZ, DP = (D + 1) & ~1, S = 3;
+    __device__ __forceinline__ static void eval(const float* a, float* m) {
+        const float mz = max_range<DX + DY, D>(a);
+        m[0] = mz;
+        if constexpr (DX == 1) m[1] = fmaxf(a[0], mz);
+        else if constexpr (DX == 2) m[1] = max3f(a[0], a[1], mz);
+        else m[1] = fmaxf(max_range<0, DX>(a), mz);
+        if constexpr (DY == 1) m[2] = fmaxf(a[DX], mz);
+        else if constexpr (DY == 2) m[2] = max3f(a[DX], a[DX + 1], mz);
+        else m[2] = fmaxf(max_range<DX, DX + DY>(a), mz);
+    }
+};
+
+// all D leave-one-out subspaces                               (DTC, O-, S-information)
+template <int DD>
+struct SpecLoo {
+    static constexpr int D = DD, DP = (D + 1) & ~1, S = DD;
+    __device__ __forceinline__ static void eval(const float* a, float* m) {
+        if constexpr (D == 3) {
+            m[0] = fmaxf(a[1], a[2]); m[1] = fmaxf(a[0], a[2]); m[2] = fmaxf(a[0], a[1]);
+        } else if constexpr (D == 4) {
+            const float p01 = fmaxf(a[0], a[1]), p23 = fmaxf(a[2], a[3]);
+            m[0] = fmaxf(a[1], p23); m[1] = fmaxf(a[0], p23); m[2] = fmaxf(a[3], p01); m[3] = fmaxf(a[2], p01);
+        } else if constexpr (D == 5) {
+            const float p01 = fmaxf(a[0], a[1]), p23 = fmaxf(a[2], a[3]);
+            m[0] = max3f(a[1], p23, a[4]); m[1] = max3f(a[0], p23, a[4]);
+            m[2] = max3f(a[3], p01, a[4]); m[3] = max3f(a[2], p01, a[4]); m[4] = fmaxf(p01, p23);
+        } else if constexpr (D == 6) {
+            const float p01 = fmaxf(a[0], a[1]), p23 = fmaxf(a[2], a[3]), p45 = fmaxf(a[4], a[5]);
+            m[0] = max3f(a[1], p23, p45); m[1] = max3f(a[0], p23, p45);
+            m[2] = max3f(a[3], p01, p45); m[3] = max3f(a[2], p01, p45);
+            m[4] = max3f(a[5], p01, p23); m[5] = max3f(a[4], p01, p23);
+        } else if constexpr (D == 7) {
+            const float p01 = fmaxf(a[0], a[1]), p23 = fmaxf(a[2], a[3]), p45 = fmaxf(a[4], a[5]);
+            const float r = fmaxf(p45, a[6]), s = fmaxf(p01, p23);
+            m[0] = max3f(a[1], p23, r); m[1] = max3f(a[0], p23, r);
+            m[2] = max3f(a[3], p01, r); m[3] = max3f(a[2], p01, r);
+            m[4] = max3f(a[5], a[6], s); m[5] = max3f(a[4], a[6], s); m[6] = fmaxf(p45, s);
+        } else {
+            static_assert(D == 8, "SpecLoo supports 3..8 dimensions");
+            const float p01 = fmaxf(a[0], a[1]), p23 = fmaxf(a[2], a[3]);
+            const float p45 = fmaxf(a[4], a[5]), p67 = fmaxf(a[6], a[7]);
+            const float lo = fmaxf(p01, p23), hi = fmaxf(p45, p67);
+            m[0] = max3f(a[1], p23, hi); m[1] = max3f(a[0], p23, hi);
+            m[2] = max3f(a[3], p01, hi); m[3] = max3f(a[2], p01, hi);
+            m[4] = max3f(a[5], p67, lo); m[5] = max3f(a[4], p67, lo);
+            m[6] = max3f(a[7], p45, lo); m[7] = max3f(a[6], p45, lo);
+        }
+    }
+};
+
+// up to 4 arbitrary subspaces given as run-time bitmasks (uniform) -- generic fallback
+template <int DPP>
+struct SpecMasked {
+    static constexpr int D = DPP, DP = DPP, S = 4;
+};
+
+struct MaskQuad {
+    uint32_t m[4];
+};
+
+// ---------------------------------------------------------------- filter kernel
+// counts32[s][nq] (int32) are ADDED to (atomicAdd when the candidate range is split).
+template <class Spec, int Q, int STAGES, bool MASKED>
+static __global__ void __launch_bounds__(FAST_THREADS)
+count_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary, int64_t q_begin, int64_t nq,
+                 const float* __restrict__ thresholds, int windowed, MaskQuad masks, int n_sub,
+                 int32_t* __restrict__ counts, unsigned long long* __restrict__ tile_counter) {
+    constexpr int DP = Spec::DP, S = Spec::S, SP = (S + 1) / 2;
+    constexpr int QB = FAST_THREADS * Q;
+    constexpr int TILE_FLOATS = FAST_TILE * DP;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+
+    const int tid = threadIdx.x;
+    const int64_t qb0 = (int64_t)blockIdx.x * QB;
+    const int splits = gridDim.y;
+
+    float2 q[Q][DP / 2];
+    float qp[Q], T[Q];
+    bool live[Q];
+    int cnt[Q][S];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const int64_t qi = qb0 + j * FAST_THREADS + tid;
+        live[j] = qi < nq;
+        const int64_t row = q_begin + (live[j] ? qi : 0);
+        load_row<DP>(shadow + row * DP, q[j]);
+        qp[j] = shadow[row * DP + primary];
+        T[j] = live[j] ? thresholds[qi] : -1.0f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) cnt[j][s] = 0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
+    TileWalk walk(mid / FAST_TILE, n_tiles, blockIdx.y, splits);
+    int64_t pend_tile[STAGES];
+    int head = 0, count = 0;
+    uint32_t phase_bits = 0;
+    auto issue = [&](int slot, int64_t t) {
+        if (tid == 0) {
+            mbar_expect_tx(&full_bar[slot], TILE_FLOATS * 4);
+            bulk_g2s(tiles + (size_t)slot * TILE_FLOATS, shadow + t * TILE_FLOATS, TILE_FLOATS * 4, &full_bar[slot]);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+        const int64_t t = walk.next();
+        if (t >= 0) { pend_tile[s] = t; issue(s, t); ++count; }
+    }
+
+    int tiles_done = 0;
+    while (count > 0) {
+        ++tiles_done;
+        const int slot = head;
+        mbar_wait(&full_bar[slot], (phase_bits >> slot) & 1u);
+        phase_bits ^= 1u << slot;
+        const float* tile = tiles + (size_t)slot * TILE_FLOATS;
+
+        float2 acc[Q][SP];
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+#pragma unroll
+            for (int h = 0; h < SP; ++h) acc[j][h] = make_float2(0.0f, 0.0f);
+
+#pragma unroll 2
+        for (int c = 0; c < FAST_TILE; ++c) {
+            float2 cc[DP / 2];
+            load_row<DP>(tile + c * DP, cc);
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                float a[DP];
+#pragma unroll
+                for (int h = 0; h < DP / 2; ++h) {
+                    const float2 d = sub2(q[j][h], cc[h]);
+                    a[2 * h] = fabsf(d.x);
+                    a[2 * h + 1] = fabsf(d.y);
+                }
+                float m[S];
+                if constexpr (MASKED) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        float v = 0.0f;
+#pragma unroll
+                        for (int d = 0; d < DP; ++d)
+                            if ((masks.m[s] >> d) & 1u) v = fmaxf(v, a[d]);
+                        m[s] = masks.m[s] ? v : CUDART_INF_F;  // unused slot: never inside
+                    }
+                } else {
+                    Spec::eval(a, m);
+                }
+                float ind[2 * SP];
+#pragma unroll
+                for (int s = 0; s < S; ++s) ind[s] = (m[s] < T[j]) ? 1.0f : 0.0f;
+                if constexpr (S & 1) ind[S] = 0.0f;
+#pragma unroll
+                for (int h = 0; h < SP; ++h) acc[j][h] = add2(acc[j][h], make_float2(ind[2 * h], ind[2 * h + 1]));
+            }
+        }
+        // flush the float counters (<= FAST_TILE, exact) into integers
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+#pragma unroll
+            for (int s = 0; s < S; ++s) cnt[j][s] += (int)((s & 1) ? acc[j][s / 2].y : acc[j][s / 2].x);
+
+        int keep_left = 0, keep_right = 0;
+        if (windowed) {
+            // a candidate whose primary-coordinate difference is >= T is outside every
+            // subspace of this launch (all of them contain the primary coordinate)
+            if (walk.right_open && walk.hi < n_tiles) {
+                const float edge = __ldg(shadow + (walk.hi * FAST_TILE) * DP + primary);
+#pragma unroll
+                for (int j = 0; j < Q; ++j)
+                    if (live[j]) keep_right |= ((edge - qp[j]) < T[j]);
+            }
+            if (walk.left_open && walk.lo >= 0) {
+                const float edge = __ldg(shadow + ((walk.lo + 1) * FAST_TILE - 1) * DP + primary);
+#pragma unroll
+                for (int j = 0; j < Q; ++j)
+                    if (live[j]) keep_left |= ((qp[j] - edge) < T[j]);
+            }
+            const int votes = __syncthreads_or((keep_left ? 1 : 0) | (keep_right ? 2 : 0));
+            if (!(votes & 1)) walk.left_open = false;
+            if (!(votes & 2)) walk.right_open = false;
+        } else {
+            __syncthreads();
+        }
+        head = (head + 1) % STAGES;
+        --count;
+        const int64_t tn = walk.next();
+        if (tn >= 0) { pend_tile[slot] = tn; issue(slot, tn); ++count; }
+    }
+
+    if (tid == 0 && tile_counter) atomicAdd(tile_counter, (unsigned long long)tiles_done);
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const int64_t qi = qb0 + j * FAST_THREADS + tid;
+        if (qi < nq) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                if (s < n_sub) {
+                    if (splits == 1) counts[(int64_t)s * nq + qi] += cnt[j][s];
+                    else if (cnt[j][s]) atomicAdd(&counts[(int64_t)s * nq + qi], cnt[j][s]);
+                }
+        }
+    }
+}
+
+// thresholds[qi] = count_threshold(eps[qi]);  counts initialised to `bias`
+static __global__ void count_thresholds_kernel(const double* __restrict__ eps, int64_t nq, const double* __restrict__ maxabs,
+                                        int dim, float* __restrict__ thresholds) {
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    double mmax = 0.0;
+    for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
+    thresholds[qi] = count_threshold(eps[qi], mmax);
+}
+
+// ---------------------------------------------------------------- exact resolution of the band
+constexpr int FIX_CAP = 48;  // band candidates examined per query and coordinate
+
+__device__ __forceinline__ int64_t lower_bound_f64(const double* __restrict__ v, int64_t n, double x) {
+    int64_t lo = 0, hi = n;  // first index with v[i] >= x
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (v[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int64_t upper_bound_f64(const double* __restrict__ v, int64_t n, double x) {
+    int64_t lo = 0, hi = n;  // first index with v[i] > x
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (v[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+struct MaskTable64 {
+    uint32_t m[KSG_MAX_SUBSPACES];
+};
+
+static __global__ void __launch_bounds__(128)
+count_fix_kernel(const double* __restrict__ sorted, int64_t ld, const float* __restrict__ shadow, int dim,
+                 int dim_padded, int64_t n, const double* __restrict__ axis_vals,
+                 const int32_t* __restrict__ axis_pos, const double* __restrict__ maxabs, int64_t q_begin,
+                 int64_t nq, const double* __restrict__ eps, const float* __restrict__ thresholds,
+                 MaskTable64 masks, int n_sub, int strict, int32_t* __restrict__ counts,
+                 int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const double e = eps[qi];
+    if (!(e < CUDART_INF)) return;  // infinite radius: the filter is exact (everything finite is inside)
+    const float T = thresholds[qi];
+    double mmax = 0.0;
+    uint32_t used = 0;
+    for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
+    for (int s = 0; s < n_sub; ++s) used |= masks.m[s];
+    const double w = 4.0 * band_f64(mmax, e);
+    const int64_t row_q = q_begin + qi;
+
+    double xq[KSG_MAX_DIM];
+    for (int d = 0; d < dim; ++d) xq[d] = sorted[(int64_t)d * ld + row_q];
+    bool crowded = false;
+
+    for (int d = 0; d < dim && !crowded; ++d) {
+        if (!((used >> d) & 1u)) continue;
+        const double* vals = axis_vals + (int64_t)d * ld;
+        const int32_t* pos = axis_pos + (int64_t)d * ld;
+        // superset of {v : | |xq - v| - e | <= w}: two intervals (or one when they touch)
+        const double ws = w * 1.01 + 1e-300;
+        double lo_a = xq[d] - e - ws, hi_a = xq[d] - e + ws;
+        double lo_b = xq[d] + e - ws, hi_b = xq[d] + e + ws;
+        int n_int = 2;
+        if (hi_a >= lo_b) { hi_a = hi_b; n_int = 1; }
+        for (int side = 0; side < n_int && !crowded; ++side) {
+            const double lo_v = side == 0 ? lo_a : lo_b, hi_v = side == 0 ? hi_a : hi_b;
+            const int64_t i0 = lower_bound_f64(vals, n, lo_v), i1 = upper_bound_f64(vals, n, hi_v);
+            if (i1 - i0 > FIX_CAP) { crowded = true; break; }
+            for (int64_t i = i0; i < i1; ++i) {
+                const int64_t j = pos[i];
+                // in-band test in float64, the same for every coordinate (also dedupes)
+                double a64[KSG_MAX_DIM];
+                bool first_band = true, in_band_d = false;
+                for (int dd = 0; dd < dim; ++dd) {
+                    a64[dd] = fabs(xq[dd] - sorted[(int64_t)dd * ld + j]);
+                    const bool inb = ((used >> dd) & 1u) && fabs(a64[dd] - e) <= w;
+                    if (dd < d && inb) first_band = false;   // handled when coordinate dd was visited
+                    if (dd == d) in_band_d = inb;
+                }
+                if (!in_band_d || !first_band) continue;
+                for (int s = 0; s < n_sub; ++s) {
+                    float m32 = 0.0f;
+                    double m64 = 0.0;
+                    for (int dd = 0; dd < dim; ++dd)
+                        if ((masks.m[s] >> dd) & 1u) {
+                            const float df = __fsub_rn(shadow[row_q * dim_padded + dd], shadow[j * dim_padded + dd]);
+                            m32 = fmaxf(m32, fabsf(df));
+                            m64 = fmax(m64, a64[dd]);
+                        }
+                    const int counted = m32 < T;
+                    const int truth = strict ? (m64 < e) : (m64 <= e);
+                    if (counted != truth) atomicAdd(&counts[(int64_t)s * nq + qi], truth - counted);
+                }
+            }
+        }
+    }
+    if (crowded) {
+        flags[qi] = 1;
+        atomicAdd(n_flagged, 1);
+    }
+}
+
+// ---------------------------------------------------------------- 1-D marginals
+// counts[qi] = #{j : |fl64(x_q - v_j)| < eps} + bias   over the coordinate's sorted array.
+static __global__ void __launch_bounds__(128)
+axis_count_kernel(const double* __restrict__ sorted_row, const double* __restrict__ vals, int64_t n,
+                  int64_t q_begin, int64_t nq, const double* __restrict__ eps, int strict, int32_t bias,
+                  int32_t* __restrict__ counts) {
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const double x = sorted_row[q_begin + qi];
+    const double e = eps[qi];
+    // first index inside on the left: predicate (v > x) || inside(x - v) is monotone in v
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const double v = vals[mid];
+        const double dl = x - v;
+        const bool p = (v > x) || (strict ? (dl < e) : (dl <= e));
+        if (p) hi = mid; else lo = mid + 1;
+    }
+    const int64_t left = lo;
+    // first index beyond the run on the right: (v > x) && !inside(v - x)
+    lo = left; hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const double v = vals[mid];
+        const double dr = v - x;
+        const bool p = (v > x) && !(strict ? (dr < e) : (dr <= e));
+        if (p) hi = mid; else lo = mid + 1;
+    }
+    counts[qi] = (int32_t)(lo - left) + bias;
+}
+
+static __global__ void scatter_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ perm, int64_t n,
+                                   double* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[perm[i]] = src[i];
+}
+
+}  // namespace ksg

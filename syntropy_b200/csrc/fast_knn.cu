@@ -1,0 +1,37 @@
+// k-NN filter instantiations (DP = 2, 4, 6, 8) and their launcher.
+#include "fast_count_launch.cuh"
+#include "fast_knn.cuh"
+
+namespace ksg {
+
+int knn_f32_queries_per_block(int dim_padded) { return FAST_THREADS * (dim_padded <= 4 ? 4 : 2); }
+
+template <int DP>
+static int launch_knn_dp(const KnnF32Args& a) {
+    constexpr int Q = FastGeom<DP>::Q, ST = FastGeom<DP>::STAGES;
+    auto kern = knn_f32_kernel<DP, Q, ST>;
+    const size_t smem = (size_t)ST * FAST_TILE * DP * sizeof(float) + (size_t)a.kcap * FAST_THREADS * Q * 8;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    }
+    dim3 grid((unsigned)ceil_div(a.nq, FAST_THREADS * Q), (unsigned)a.splits, 1);
+    kern<<<grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.n_tiles, a.primary, a.q_begin, a.nq, a.kcap, a.windowed,
+                                              a.maxabs, a.dim, a.part_d32, a.part_idx, a.tile_counter);
+    note_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("knn_f32_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    return KSG_OK;
+}
+
+int launch_knn_f32(int dim_padded, const KnnF32Args& a) {
+    switch (dim_padded) {
+        case 2: return launch_knn_dp<2>(a);
+        case 4: return launch_knn_dp<4>(a);
+        case 6: return launch_knn_dp<6>(a);
+        case 8: return launch_knn_dp<8>(a);
+        default: return KSG_EUNSUPPORTED;
+    }
+}
+
+}  // namespace ksg

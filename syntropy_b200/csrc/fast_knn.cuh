@@ -1,0 +1,388 @@
+// K1 fast path: k-NN radius with an fp32 tile filter and an exact fp64 refine.
+//
+// Filter (knn_f32_kernel).  Works on the prepared set (prepare.cuh): fp32 AoS shadow
+// rows, sorted by the primary coordinate, +inf padded.  One thread owns Q queries whose
+// coordinates live in registers as packed pairs; candidate tiles are bulk-copied
+// (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) into a STAGES-deep ring of
+// shared-memory buffers; all lanes read the same candidate (LDS.128 broadcasts).
+// Per (query, candidate) the hot loop is   DP/2 FADD2 (packed subtract, two dimensions
+// per issue slot) + ~DP/2 FMNMX/FMNMX3 (|.| folded into the operands) + 1/2 FMNMX3
+// (running minimum over two candidates) -- no compare, no branch.  Every BATCH
+// candidates the running minima are tested against the per-query thresholds; only on a
+// hit is the batch re-walked to insert (d32, index) into the query's sorted list in
+// shared memory.  Tiles are visited outward from the query block's own tile, so the
+// thresholds are tight after the first tile; in windowed mode a side is closed as soon
+// as the primary-coordinate gap to its next tile exceeds every threshold (+ band).
+//
+// Refine (knn_refine_kernel).  The list keeps the KCAP = k' + margin smallest fp32
+// distances.  With r32 the k'-th smallest of them and delta the fp32 error bound,
+// every point whose exact distance is <= the exact radius has d32 <= r32 + 2*delta;
+// if the list provably contains all of those (its tail lies above that bound) the exact
+// radius is the k'-th smallest float64 distance among them.  Otherwise the query is
+// flagged and recomputed by the dense fp64 kernel.
+#pragma once
+
+#include "common.cuh"
+#include "prepare.cuh"
+
+namespace ksg {
+
+constexpr int FAST_THREADS = 128;
+constexpr int KNN_BATCH = 16;   // candidates between threshold checks
+constexpr int KNN_MARGIN = 3;   // list entries kept beyond k'
+
+// ---- fp32 error band of the shadow copy (see DESIGN.md "Exactness")
+// |d32 - d64| <= 2^-24 * (2*M + |d|) * (1 + tiny) per dimension; kept as a pair of
+// coefficients so that band(T) = c0 + c1 * T, evaluated with upward slack.
+struct Band {
+    float c0, c1;
+};
+// band(T) = c0 + c1*T  >=  2 * delta(T), with ~1% upward slack for its own fp32 evaluation
+__device__ __forceinline__ Band make_band(const double* __restrict__ maxabs, int dim) {
+    double mmax = 0.0;
+    for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
+    Band b;
+    b.c0 = __double2float_ru(2.0 * 5.9604644775390625e-08 * 2.0 * mmax * 1.02 + 1e-37);
+    b.c1 = __double2float_ru(2.0 * 5.9604644775390625e-08 * 1.02);
+    return b;
+}
+__host__ __device__ inline double band_f64(double maxabs, double t) {
+    return 5.9604644775390625e-08 * (2.0 * maxabs + t) * 1.001 + 1e-37;
+}
+
+// ---- packed helpers
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "sub.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+
+template <int DP>
+__device__ __forceinline__ float cheb32(const float2 (&q)[DP / 2], const float2 (&c)[DP / 2]) {
+    const float2 d0 = sub2(q[0], c[0]);
+    float m = fmaxf(fabsf(d0.x), fabsf(d0.y));
+#pragma unroll
+    for (int h = 1; h < DP / 2; ++h) {
+        const float2 d = sub2(q[h], c[h]);
+        m = fmaxf(m, fmaxf(fabsf(d.x), fabsf(d.y)));
+    }
+    return m;
+}
+
+template <int DP>
+__device__ __forceinline__ void load_row(const float* __restrict__ row, float2 (&c)[DP / 2]) {
+    if constexpr (DP % 4 == 0) {
+#pragma unroll
+        for (int h = 0; h < DP / 4; ++h) {
+            const float4 v = reinterpret_cast<const float4*>(row)[h];
+            c[2 * h] = make_float2(v.x, v.y);
+            c[2 * h + 1] = make_float2(v.z, v.w);
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < DP / 2; ++h) c[h] = reinterpret_cast<const float2*>(row)[h];
+    }
+}
+
+// ---- mbarrier / bulk-copy primitives (shared::cta addresses)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{ .reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Outward tile walk shared by the filter kernels: own tile, then alternately the next
+// tile to the right and to the left; a side can be closed (window pruning).  `split`
+// keeps every splits-th element of the walk.
+struct TileWalk {
+    int64_t lo, hi, n_tiles;
+    bool left_open, right_open, turn_right;
+    int counter, split, splits;
+    __device__ TileWalk(int64_t own, int64_t n_tiles_, int split_, int splits_)
+        : lo(own - 1), hi(own), n_tiles(n_tiles_), left_open(true), right_open(true), turn_right(true),
+          counter(0), split(split_), splits(splits_) {}
+    // next tile of the full walk, or -1 when exhausted
+    __device__ int64_t next_any() {
+        const bool can_r = right_open && hi < n_tiles;
+        const bool can_l = left_open && lo >= 0;
+        if (!can_r && !can_l) return -1;
+        bool go_right = turn_right ? can_r : !can_l;
+        turn_right = !turn_right;
+        return go_right ? hi++ : lo--;
+    }
+    __device__ int64_t next() {
+        for (;;) {
+            const int64_t t = next_any();
+            if (t < 0) return -1;
+            if ((counter++ % splits) == split) return t;
+        }
+    }
+};
+
+// part_d32 / part_idx: [split][rank][nq]
+template <int DP, int Q, int STAGES>
+static __global__ void __launch_bounds__(FAST_THREADS)
+knn_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary, int64_t q_begin, int64_t nq,
+               int kcap, int windowed, const double* __restrict__ maxabs, int dim,
+               float* __restrict__ part_d32, int32_t* __restrict__ part_idx,
+               unsigned long long* __restrict__ tile_counter) {
+    constexpr int QB = FAST_THREADS * Q;
+    constexpr int TILE_FLOATS = FAST_TILE * DP;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // STAGES * TILE_FLOATS
+    float* lst_d = tiles + STAGES * TILE_FLOATS;                             // kcap * QB
+    int32_t* lst_i = reinterpret_cast<int32_t*>(lst_d + (size_t)kcap * QB);  // kcap * QB
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+
+    const int tid = threadIdx.x;
+    const int64_t qb0 = (int64_t)blockIdx.x * QB;  // first query of the block (relative to q_begin)
+    const int splits = gridDim.y;
+    const Band band = make_band(maxabs, dim);
+
+    // queries: slot j of thread t is query qb0 + j*THREADS + t
+    float2 q[Q][DP / 2];
+    float qp[Q];      // primary coordinate (window test)
+    float thr[Q];     // kcap-th smallest so far
+    bool live[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const int64_t qi = qb0 + j * FAST_THREADS + tid;
+        live[j] = qi < nq;
+        const int64_t row = q_begin + (live[j] ? qi : 0);
+        load_row<DP>(shadow + row * DP, q[j]);
+        qp[j] = shadow[row * DP + primary];
+        thr[j] = live[j] ? CUDART_INF_F : -1.0f;  // dead slots never insert
+    }
+    for (int r = 0; r < kcap; ++r)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            lst_d[(size_t)r * QB + j * FAST_THREADS + tid] = CUDART_INF_F;
+            lst_i[(size_t)r * QB + j * FAST_THREADS + tid] = -1;
+        }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // the block's own tile: the one holding its middle query
+    const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
+    TileWalk walk(mid / FAST_TILE, n_tiles, blockIdx.y, splits);
+
+    int64_t pend_tile[STAGES];
+    int head = 0, count = 0;     // ring of issued tiles: slot = (head + i) % STAGES
+    uint32_t phase_bits = 0;     // per-slot parity
+    auto issue = [&](int slot, int64_t t) {
+        if (tid == 0) {
+            mbar_expect_tx(&full_bar[slot], TILE_FLOATS * 4);
+            bulk_g2s(tiles + (size_t)slot * TILE_FLOATS, shadow + t * TILE_FLOATS, TILE_FLOATS * 4, &full_bar[slot]);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+        const int64_t t = walk.next();
+        if (t >= 0) {
+            pend_tile[s] = t;
+            issue(s, t);
+            ++count;
+        }
+    }
+
+    int tiles_done = 0;
+    while (count > 0) {
+        ++tiles_done;
+        const int slot = head;
+        const int64_t t = pend_tile[slot];
+        mbar_wait(&full_bar[slot], (phase_bits >> slot) & 1u);
+        phase_bits ^= 1u << slot;
+        const float* tile = tiles + (size_t)slot * TILE_FLOATS;
+        const int64_t tile_base = t * FAST_TILE;
+
+        for (int b = 0; b < FAST_TILE; b += KNN_BATCH) {
+            float mrun[Q];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) mrun[j] = CUDART_INF_F;
+#pragma unroll
+            for (int c = 0; c < KNN_BATCH; c += 2) {
+                float2 ca[DP / 2], cb[DP / 2];
+                load_row<DP>(tile + (b + c) * DP, ca);
+                load_row<DP>(tile + (b + c + 1) * DP, cb);
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    const float ma = cheb32<DP>(q[j], ca);
+                    const float mb = cheb32<DP>(q[j], cb);
+                    mrun[j] = fminf(fminf(mrun[j], ma), mb);
+                }
+            }
+            bool hit = false;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) hit = hit || (mrun[j] < thr[j]);
+            if (hit) {
+                // rare: walk the batch again, candidate by candidate, and insert
+                for (int c = 0; c < KNN_BATCH; ++c) {
+                    float2 cc[DP / 2];
+                    load_row<DP>(tile + (b + c) * DP, cc);
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        const float m = cheb32<DP>(q[j], cc);
+                        if (m < thr[j]) {
+                            const int col = j * FAST_THREADS + tid;
+                            int r = kcap - 1;
+                            while (r > 0 && lst_d[(size_t)(r - 1) * QB + col] > m) {
+                                lst_d[(size_t)r * QB + col] = lst_d[(size_t)(r - 1) * QB + col];
+                                lst_i[(size_t)r * QB + col] = lst_i[(size_t)(r - 1) * QB + col];
+                                --r;
+                            }
+                            lst_d[(size_t)r * QB + col] = m;
+                            lst_i[(size_t)r * QB + col] = (int32_t)(tile_base + b + c);
+                            thr[j] = lst_d[(size_t)(kcap - 1) * QB + col];
+                        }
+                    }
+                }
+            }
+        }
+
+        // window pruning: may a side stop?  (block-uniform; also the "tile consumed" barrier)
+        int keep_left = 0, keep_right = 0;
+        if (windowed) {
+            if (walk.right_open && walk.hi < n_tiles) {
+                const float edge = __ldg(shadow + (walk.hi * FAST_TILE) * DP + primary);  // min of next right tile
+#pragma unroll
+                for (int j = 0; j < Q; ++j)
+                    if (live[j]) keep_right |= !((edge - qp[j]) > thr[j] + (band.c0 + band.c1 * thr[j]));
+            }
+            if (walk.left_open && walk.lo >= 0) {
+                const float edge = __ldg(shadow + ((walk.lo + 1) * FAST_TILE - 1) * DP + primary);  // max of next left tile
+#pragma unroll
+                for (int j = 0; j < Q; ++j)
+                    if (live[j]) keep_left |= !((qp[j] - edge) > thr[j] + (band.c0 + band.c1 * thr[j]));
+            }
+            const int votes = __syncthreads_or((keep_left ? 1 : 0) | (keep_right ? 2 : 0));
+            if (!(votes & 1)) walk.left_open = false;
+            if (!(votes & 2)) walk.right_open = false;
+        } else {
+            __syncthreads();
+        }
+
+        head = (head + 1) % STAGES;
+        --count;
+        const int64_t tn = walk.next();
+        if (tn >= 0) {
+            pend_tile[slot] = tn;
+            issue(slot, tn);
+            ++count;
+        }
+    }
+
+    if (tid == 0 && tile_counter) atomicAdd(tile_counter, (unsigned long long)tiles_done);
+
+    // emit the lists (ascending), one per split
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const int64_t qi = qb0 + j * FAST_THREADS + tid;
+        if (qi < nq) {
+            const int col = j * FAST_THREADS + tid;
+            for (int r = 0; r < kcap; ++r) {
+                const int64_t o = ((int64_t)blockIdx.y * kcap + r) * nq + qi;
+                part_d32[o] = lst_d[(size_t)r * QB + col];
+                part_idx[o] = lst_i[(size_t)r * QB + col];
+            }
+        }
+    }
+}
+
+// Exact refine: see the file header.  flags[qi] = 1 marks a query for the fp64 fallback.
+constexpr int REFINE_CAP = 96;  // union entries examined per query
+
+static __global__ void __launch_bounds__(128)
+knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict__ part_idx, int kcap, int splits,
+                  int kp, const double* __restrict__ sorted, int64_t ld, int dim, int64_t n, int64_t q_begin,
+                  int64_t nq, const double* __restrict__ maxabs, double* __restrict__ eps_out,
+                  int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    double mmax = 0.0;
+    for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
+
+    // k'-th smallest fp32 distance over the union of the split lists
+    float best[KSG_MAX_KPRIME];
+    int have = 0;
+    for (int s = 0; s < splits; ++s)
+        for (int r = 0; r < kcap; ++r) {
+            const float v = part_d32[((int64_t)s * kcap + r) * nq + qi];
+            if (have == kp && !(v < best[kp - 1])) break;
+            int pos = have < kp ? have : kp - 1;
+            while (pos > 0 && best[pos - 1] > v) { best[pos] = best[pos - 1]; --pos; }
+            best[pos] = v;
+            if (have < kp) ++have;
+        }
+    const double r32 = (have == kp) ? (double)best[kp - 1] : CUDART_INF;
+    if (!(r32 < CUDART_INF)) {  // fewer than k' points exist (k+1 > n): cKDTree pads with inf
+        eps_out[qi] = CUDART_INF;
+        flags[qi] = 0;
+        return;
+    }
+    const double delta = band_f64(mmax, 2.0 * r32);
+    const double T = r32 + 2.0 * delta;
+
+    bool overflow = false;
+    double exact[KSG_MAX_KPRIME];
+    int got = 0, examined = 0;
+    double qc[KSG_MAX_DIM];
+    for (int d = 0; d < dim; ++d) qc[d] = sorted[(int64_t)d * ld + q_begin + qi];
+    for (int s = 0; s < splits && !overflow; ++s) {
+        // a full list whose tail is still inside the band may have dropped in-band candidates
+        const float tail = part_d32[((int64_t)s * kcap + (kcap - 1)) * nq + qi];
+        if ((double)tail <= T) { overflow = true; break; }
+        for (int r = 0; r < kcap; ++r) {
+            const int64_t o = ((int64_t)s * kcap + r) * nq + qi;
+            const float v = part_d32[o];
+            if (!((double)v <= T)) break;
+            if (++examined > REFINE_CAP) { overflow = true; break; }
+            const int64_t j = part_idx[o];
+            double m = 0.0;
+            for (int d = 0; d < dim; ++d) m = fmax(m, fabs(qc[d] - sorted[(int64_t)d * ld + j]));
+            int pos = got < kp ? got : kp - 1;
+            if (got == kp && !(m < exact[kp - 1])) continue;
+            while (pos > 0 && exact[pos - 1] > m) { exact[pos] = exact[pos - 1]; --pos; }
+            exact[pos] = m;
+            if (got < kp) ++got;
+        }
+    }
+    if (overflow || got < kp) {
+        flags[qi] = 1;
+        atomicAdd(n_flagged, 1);
+        eps_out[qi] = CUDART_NAN;
+    } else {
+        flags[qi] = 0;
+        eps_out[qi] = exact[kp - 1];
+    }
+}
+
+}  // namespace ksg

@@ -1,0 +1,50 @@
+// Host-side launchers of the fast (fp32-filtered) kernels; each family of template
+// instantiations lives in its own translation unit so the library builds in parallel.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ksg_b200.h"
+
+namespace ksg {
+
+struct KnnF32Args {
+    const float* shadow;
+    int64_t n_tiles;
+    int primary;
+    int64_t q_begin, nq;
+    int kcap, splits, windowed;
+    const double* maxabs;
+    int dim;
+    float* part_d32;
+    int32_t* part_idx;
+    unsigned long long* tile_counter;
+    cudaStream_t st;
+};
+int knn_f32_queries_per_block(int dim_padded);
+int launch_knn_f32(int dim_padded, const KnnF32Args& a);  // KSG_EUNSUPPORTED if dim_padded not in {2,4,6,8}
+
+struct CountF32Args {
+    const float* shadow;
+    int64_t n_tiles;
+    int primary;
+    int64_t q_begin, nq;
+    const float* thresholds;
+    int windowed;
+    uint32_t masks[4];  // only for the masked (generic) kernel
+    int n_sub;
+    int32_t* counts;    // [n_sub][nq], added to
+    int splits;
+    unsigned long long* tile_counter;
+    cudaStream_t st;
+};
+int count_f32_queries_per_block(int dim_padded);
+int launch_count_pair(int dx, int dy, const CountF32Args& a);          // subspaces x, y
+int launch_count_cmi(int dx, int dy, int dz, const CountF32Args& a);   // subspaces z, xz, yz
+int launch_count_loo(int d, const CountF32Args& a);                    // all leave-one-out subspaces
+int launch_count_masked(int dim_padded, const CountF32Args& a);        // <= 4 run-time masks
+
+void note_launch();  // launch counter (ksg_launch_count)
+
+}  // namespace ksg

@@ -1,0 +1,121 @@
+// Prepared point set: everything the fast (fp32-filtered, exact) kernels need, built
+// once per estimator call on the device.
+//
+//   * the points sorted by one "primary" coordinate (radix sort) -- neighbouring
+//     queries then see neighbouring candidates, which keeps the k-NN thresholds tight
+//     from the first tile on and makes window pruning possible;
+//   * an fp32 AoS shadow copy, centred per dimension so that its rounding error is
+//     2^-24 * |x - centre| instead of 2^-24 * |x|, padded with +inf rows to a whole
+//     number of tiles (padded candidates can never be a neighbour or be counted);
+//   * every coordinate sorted on its own (values + position in the primary order):
+//     1-D marginal counts become two binary searches with the exact fp64 predicate,
+//     and the fp32 count kernel's boundary band is resolved by looking at the handful
+//     of candidates whose coordinate difference is within the band of the radius.
+#pragma once
+
+#include "common.cuh"
+
+namespace ksg {
+
+constexpr int FAST_TILE = 512;       // candidates per shared-memory tile (fast kernels)
+constexpr int STATS_BLOCKS = 64;     // partial min/max blocks per dimension
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// (layout computation lives in fast_abi.cu: it needs CUB's temp-storage size)
+struct PreparedLayout {
+    int64_t ld;        // row stride of the fp64 arrays
+    int64_t n_padded;  // shadow rows
+    int dim_padded;
+    size_t off_perm, off_sorted, off_shadow, off_axis_vals, off_axis_pos, off_center, off_maxabs, off_flags;
+    size_t off_stats, off_iota, off_keys_tmp, off_cub;
+    size_t cub_bytes;
+    size_t total;
+};
+
+// ---- per-dimension min / max (two stages) + non-finite flag
+static __global__ void __launch_bounds__(256)
+stats_stage1_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, double* __restrict__ partial,
+                    int32_t* __restrict__ flags) {
+    const int d = blockIdx.y;
+    const double* row = pts + (int64_t)d * ld;
+    double lo = CUDART_INF, hi = -CUDART_INF;
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double v = row[i];
+        bad |= !isfinite(v);
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    __shared__ double slo[256], shi[256];
+    slo[threadIdx.x] = lo;
+    shi[threadIdx.x] = hi;
+    const int anybad = __syncthreads_or(bad);
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            slo[threadIdx.x] = fmin(slo[threadIdx.x], slo[threadIdx.x + off]);
+            shi[threadIdx.x] = fmax(shi[threadIdx.x], shi[threadIdx.x + off]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[((int64_t)d * STATS_BLOCKS + blockIdx.x) * 2 + 0] = slo[0];
+        partial[((int64_t)d * STATS_BLOCKS + blockIdx.x) * 2 + 1] = shi[0];
+        if (anybad) atomicExch(&flags[0], 1);
+    }
+}
+
+static __global__ void stats_stage2_kernel(const double* __restrict__ partial, int dim, double* __restrict__ center,
+                                    double* __restrict__ maxabs) {
+    const int d = threadIdx.x;
+    if (d >= dim) return;
+    double lo = CUDART_INF, hi = -CUDART_INF;
+    for (int b = 0; b < STATS_BLOCKS; ++b) {
+        lo = fmin(lo, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 0]);
+        hi = fmax(hi, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 1]);
+    }
+    if (!(isfinite(lo) && isfinite(hi))) { lo = 0.0; hi = 0.0; }  // flagged elsewhere; keep the math finite
+    const double c = 0.5 * lo + 0.5 * hi;
+    center[d] = c;
+    // max |x - c| over the data, rounded up generously (the band only has to be an upper bound)
+    maxabs[d] = fmax(hi - c, c - lo) * (1.0 + 1e-12) + 1e-300;
+}
+
+static __global__ void iota_kernel(int32_t* __restrict__ p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+
+// sorted_f64[d][i] = pts[d][perm[i]];  shadow[i][d] = fp32(sorted - centre);  +inf padding rows
+static __global__ void __launch_bounds__(256)
+gather_sorted_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, int dim, int dim_padded,
+                     const int32_t* __restrict__ perm, const double* __restrict__ center,
+                     double* __restrict__ sorted, int64_t ld, float* __restrict__ shadow, int64_t n_padded) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_padded) return;
+    const bool real = i < n;
+    const int64_t src = real ? perm[i] : 0;
+    for (int d = 0; d < dim_padded; ++d) {
+        float s;
+        if (d < dim) {
+            if (real) {
+                const double v = pts[(int64_t)d * ld_in + src];
+                sorted[(int64_t)d * ld + i] = v;
+                s = __double2float_rn(__dsub_rn(v, center[d]));
+            } else {
+                s = CUDART_INF_F;
+            }
+        } else {
+            s = 0.0f;
+        }
+        shadow[i * dim_padded + d] = s;
+    }
+}
+
+static __global__ void copy_axis_kernel(const double* __restrict__ src, double* __restrict__ vals,
+                                 int32_t* __restrict__ pos, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { vals[i] = src[i]; pos[i] = (int32_t)i; }
+}
+
+}  // namespace ksg

@@ -20,7 +20,7 @@ RTOL = 1e-12
 
 
 @pytest.fixture(scope="module")
-def knn():
+def knn(E):
     import torch
 
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
@@ -29,11 +29,16 @@ def knn():
     return mod
 
 
-@pytest.fixture(scope="module")
-def E():
+@pytest.fixture(scope="module", params=["windowed", "dense", "exact"])
+def E(request):
+    """Every test runs under each engine: the fp32-filtered kernels with and without
+    window pruning, and the float64 dense kernels.  All three must give the same bits."""
     from syntropy_b200 import _engine
 
-    return _engine
+    old = _engine.config.engine
+    _engine.config.engine = request.param
+    yield _engine
+    _engine.config.engine = old
 
 
 def close(a, b):
@@ -52,10 +57,21 @@ def radius_and_counts(E, rows, k, subspaces, strict=True):
     import torch
 
     pts = E.to_device_points(rows)
-    n = pts.shape[1]
-    eps = E.knn_radius(pts, k + 1, 0, n)
+    dim, n = pts.shape
     masks = [E.mask_of(s) for s in subspaces]
-    counts = E.count_subspaces(pts, masks, eps, 0, n, strict=strict)
+    if E.config.engine == "exact" or dim > 8:
+        eps = E.knn_radius(pts, k + 1, 0, n)
+        counts = E.count_subspaces(pts, masks, eps, 0, n, strict=strict)
+    else:
+        windowed = E.config.engine == "windowed"
+        prep = E.PreparedSet(pts, 0)
+        eps_s = E.fast_knn(prep, k + 1, 0, n, windowed)
+        counts_s = E.fast_counts(prep, masks, eps_s, 0, n, windowed, strict=strict)
+        perm = prep.perm.long()
+        eps = torch.empty_like(eps_s)
+        eps[perm] = eps_s
+        counts = torch.empty_like(counts_s)
+        counts[:, perm] = counts_s
     torch.cuda.synchronize()
     return eps.cpu().numpy(), counts.cpu().numpy().astype(np.int64)
 
@@ -311,26 +327,45 @@ def test_deterministic_sum(E):
 
 
 # ------------------------------------------------------------------ full-size properties (C2)
-def test_c2_full_size_query_subset(E, knn):
+def test_c2_full_size(E, knn):
     """n = 1e6 (the metric's configuration): oracle on a random query subset against the
     full point set, plus size-independent properties of the counts."""
     data, call = workloads.c2_mi_1m()
     n = data.shape[1]
-    pts = E.to_device_points(data)
+    eps, counts = radius_and_counts(E, data, 5, [(0,), (1,), (0, 1)])
     sub = np.sort(np.random.default_rng(1).choice(n, size=768, replace=False))
-    lo, hi = 400_000, 400_000 + 4096
-    eps = E.knn_radius(pts, 6, lo, hi).cpu().numpy()
-    ref = orc.knn_radius(data, 6, queries=data[:, lo:lo + 512])  # k' = 6 = k+1, self included
-    assert np.array_equal(eps[:512], ref)
-    import torch
-    eps_d = torch.from_numpy(eps).cuda()
-    counts = E.count_subspaces(pts, [1, 2, 3], eps_d, lo, hi).cpu().numpy()
+    ref = orc.knn_radius(data, 6, queries=data[:, sub])  # k' = 6 = k+1, self included
+    assert np.array_equal(eps[sub], ref)
     for row, s in enumerate(((0,), (1,))):
-        want = orc.count_within(data[list(s), :], ref, queries=data[list(s), lo:lo + 512])
-        assert np.array_equal(counts[row, :512], want)
-    # property: in the joint space exactly k points other than the query lie strictly
+        want = orc.count_within(data[list(s), :], ref, queries=data[list(s), :][:, sub])
+        assert np.array_equal(counts[row, sub], want)
+    # property: in the joint space exactly k-1 points other than the query lie strictly
     # inside the (k+1)-th-neighbour radius unless distances tie (continuous data: never)
     assert (counts[2] == 4).all()
     # property: marginal counts dominate the joint count
     assert (counts[0] >= counts[2]).all() and (counts[1] >= counts[2]).all()
-    del sub
+    ptw, avg = knn.mutual_information((0,), (1,), 5, data)
+    assert avg == pytest.approx(0.8044789267532502, rel=1e-12)  # SURVEY.md 8c anchor (reference, n=1e6)
+
+
+def test_engines_agree_bitwise_on_random_configs():
+    """exact fp64, dense fp32-filter and windowed fp32-filter give identical radii / counts."""
+    from syntropy_b200 import _engine as E
+
+    rng = np.random.default_rng(77)
+    old = E.config.engine
+    try:
+        for dim, n, k in ((2, 30_000, 5), (4, 20_000, 3), (6, 12_000, 4), (7, 9_000, 2), (8, 10_000, 4)):
+            rows = rng.standard_normal((dim, n)) + 0.3 * rng.standard_normal((1, n))
+            subs = [(d,) for d in range(dim)] + [tuple(j for j in range(dim) if j != d) for d in range(dim)]
+            if dim >= 4:
+                subs += [tuple(range(dim // 2)), tuple(range(dim // 2, dim)), (0, dim - 1)]
+            got = {}
+            for engine in ("exact", "dense", "windowed"):
+                E.config.engine = engine
+                got[engine] = radius_and_counts(E, rows, k, subs)
+            for engine in ("dense", "windowed"):
+                assert np.array_equal(got[engine][0], got["exact"][0]), (dim, engine, "eps")
+                assert np.array_equal(got[engine][1], got["exact"][1]), (dim, engine, "counts")
+    finally:
+        E.config.engine = old
