@@ -15,7 +15,7 @@ static int launch_count_spec(const CountF32Args& a) {
     constexpr int Q = FastGeom<Spec::DP>::Q, ST = FastGeom<Spec::DP>::STAGES;
     auto kern = count_f32_kernel<Spec, Q, ST, MASKED>;
     const size_t smem = (size_t)ST * FAST_TILE * Spec::DP * sizeof(float);
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {  // static shared (mbarriers) counts against the 48 KB default too
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     }

@@ -11,7 +11,7 @@ static int launch_knn_dp(const KnnF32Args& a) {
     constexpr int Q = FastGeom<DP>::Q, ST = FastGeom<DP>::STAGES;
     auto kern = knn_f32_kernel<DP, Q, ST>;
     const size_t smem = (size_t)ST * FAST_TILE * DP * sizeof(float) + (size_t)a.kcap * FAST_THREADS * Q * 8;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {  // static shared (mbarriers) counts against the 48 KB default too
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     }

@@ -283,9 +283,9 @@ knn_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary, i
                 for (int j = 0; j < Q; ++j)
                     if (live[j]) keep_left |= !((qp[j] - edge) > thr[j] + (band.c0 + band.c1 * thr[j]));
             }
-            const int votes = __syncthreads_or((keep_left ? 1 : 0) | (keep_right ? 2 : 0));
-            if (!(votes & 1)) walk.left_open = false;
-            if (!(votes & 2)) walk.right_open = false;
+            // __syncthreads_or is a boolean OR over the block: one vote per side
+            if (!__syncthreads_or(keep_left)) walk.left_open = false;
+            if (!__syncthreads_or(keep_right)) walk.right_open = false;
         } else {
             __syncthreads();
         }

@@ -48,7 +48,7 @@ void note_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 template <typename K>
 static int allow_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024)
+    if (bytes > 32 * 1024)
         KSG_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return KSG_OK;
 }
