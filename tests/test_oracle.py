@@ -202,3 +202,23 @@ def test_golden_edge_cases(golden):
     with np.errstate(all="ignore"):
         ptw, avg = orc.total_correlation(i32, 3)
     assert same(ptw, g["i32_tc_ptw"]) and same(avg, g["i32_tc_avg"])
+
+
+def test_c_restatement_matches_numpy_oracle():
+    """oracle/ksg_oracle.c (gcc, OpenMP) == oracle/ksg_oracle.py on radii, counts and pair counts."""
+    from oracle import ksg_oracle_c as oc
+
+    rng = np.random.default_rng(8)
+    rows = rng.standard_normal((5, 1500))
+    eps = orc.knn_radius(rows, 4)
+    assert same(oc.knn_radius(rows, 5), eps)
+    assert same(oc.knn_radius(rows, 3, queries=rows[:, :100] + 0.01), orc.knn_radius(rows, 3, queries=rows[:, :100] + 0.01))
+    for sub in ((0,), (1, 3), (0, 1, 2, 3, 4)):
+        assert same(oc.count_within(rows[sub, :], eps), orc.count_within(rows[sub, :], eps))
+        assert same(oc.count_within(rows[sub, :], eps, strict=False), orc.count_within(rows[sub, :], eps, strict=False))
+    x, y = rng.standard_normal(800), rng.standard_normal(800)
+    for m in (1, 2, 3):
+        nt = x.size - m
+        small = orc.pair_count(orc._embed(x, m, nt), orc._embed(y, m, nt), 0.4)
+        big = orc.pair_count(orc._embed(x, m + 1, nt), orc._embed(y, m + 1, nt), 0.4)
+        assert oc.pair_counts(x, y, m, 0.4) == (small, big)
