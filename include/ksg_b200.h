@@ -216,7 +216,7 @@ typedef struct {
     int64_t n;           /* points */
     int32_t dim;         /* joint dimensionality D */
     int32_t dim_padded;  /* D rounded up to even: row length of shadow_f32 */
-    int32_t primary;     /* coordinate the set is sorted by */
+    int32_t primary;     /* coordinate the set is sorted by, or -1: Morton order of the per-coordinate ranks */
     int32_t reserved;
     int64_t ld;          /* row stride (elements) of the [dim][ld] arrays */
     int64_t n_padded;    /* rows of shadow_f32: n rounded up to the tile length, +inf padded */
@@ -227,6 +227,7 @@ typedef struct {
     int32_t* axis_pos;   /* [dim][ld]  sorted position (primary order) of each axis_vals entry */
     double* center;      /* [dim]      per-coordinate centre of the fp32 copy */
     double* maxabs;      /* [dim]      max |x - centre| (bounds the fp32 rounding error) */
+    float* tile_box;     /* [n_padded/512][dim_padded][2] min / max of shadow_f32 over each 512-row tile */
     int32_t* flags;      /* 64 bytes: int32 [0] = 1 if the input held a NaN or an infinity;
                             uint64 at byte 16 / 24 = candidate tiles visited so far by the
                             k-NN / count filter kernels (x 512 candidates x queries per CTA =
@@ -234,8 +235,10 @@ typedef struct {
 } ksg_prepared;
 
 /*
- * Sort the n points of d_points ([dim][ld] float64) by coordinate `primary`
- * (0 <= primary < dim) and build the views above inside d_buffer
+ * Order the n points of d_points ([dim][ld] float64) -- by coordinate `primary` when
+ * 0 <= primary < dim, by the Morton (Z-order) code of their per-coordinate ranks when
+ * primary == -1 (spatially compact 512-point tiles in every coordinate) -- and build the
+ * views above inside d_buffer
  * (ksg_prepare_workspace(n, dim) bytes).  *h_out is filled on the host; the device
  * work is only enqueued.  Replaces the cKDTree constructions of the path
  * (syntropy/knn/utils.py:29 and every per-marginal tree: shannon.py:190,336;

@@ -41,6 +41,7 @@ class Prepared(C.Structure):
         ("axis_pos", C.c_void_p),
         ("center", C.c_void_p),
         ("maxabs", C.c_void_p),
+        ("tile_box", C.c_void_p),
         ("flags", C.c_void_p),
     ]
 

@@ -214,12 +214,12 @@ def device_sum(values: torch.Tensor) -> torch.Tensor:
 class Config:
     """Engine selection.  ``engine``:
       "windowed" (default) fp32 tile filter + exact fp64 resolution, candidate tiles pruned
-                           by the sort coordinate;
+                           by their bounding boxes;
       "dense"              the same kernels scanning every tile (the brute-force roofline case);
       "exact"              the float64 dense kernels (anchor / fallback; also used for > 8 dims).
     All three give identical radii and counts."""
     engine = "windowed"
-    primary = 0
+    primary = -1  # -1: Morton order of the per-coordinate ranks; d >= 0: sort by coordinate d
 
 
 config = Config()

@@ -38,9 +38,14 @@ static inline PreparedLayout prepared_layout(int64_t n, int dim) {
     L.off_center = take((size_t)KSG_MAX_DIM * 8);
     L.off_maxabs = take((size_t)KSG_MAX_DIM * 8);
     L.off_flags = take(64);
+    L.off_tile_box = take((size_t)(L.n_padded / FAST_TILE) * L.dim_padded * 2 * 4);
     L.off_stats = take((size_t)dim * STATS_BLOCKS * 2 * 8);
     L.off_iota = take((size_t)L.ld * 4);
     L.off_keys_tmp = take((size_t)L.ld * 8);
+    L.off_ranks = take((size_t)dim * L.ld * 4);
+    L.off_mkeys = take((size_t)L.ld * 8);
+    L.off_mkeys_out = take((size_t)L.ld * 8);
+    L.off_invperm = take((size_t)L.ld * 4);
     L.cub_bytes = cub_sort_bytes(n);
     L.off_cub = take(L.cub_bytes);
     L.total = o;
@@ -101,7 +106,7 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
     KSG_REQUIRE(d_points && d_buffer && h_out, "ksg_prepare: null pointer");
     KSG_REQUIRE(n > 0 && n < (1ll << 31) - 1024 && ld >= n, "ksg_prepare: need 0 < n < 2^31 and ld >= n");
     KSG_REQUIRE(dim >= 1 && dim <= KSG_MAX_DIM, "ksg_prepare: dim out of range");
-    KSG_REQUIRE(primary >= 0 && primary < dim, "ksg_prepare: primary coordinate out of range");
+    KSG_REQUIRE(primary >= -1 && primary < dim, "ksg_prepare: primary must be -1 (Morton order) or a coordinate");
     const PreparedLayout L = prepared_layout(n, dim);
     if (buffer_bytes < L.total) {
         set_error("ksg_prepare: buffer of %zu bytes needed, %zu given", L.total, buffer_bytes);
@@ -121,7 +126,7 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
     P.flags = (int32_t*)(base + L.off_flags);
     double* stats = (double*)(base + L.off_stats);
     int32_t* iota = (int32_t*)(base + L.off_iota);
-    double* keys_tmp = (double*)(base + L.off_keys_tmp);
+    (void)L.off_keys_tmp;
     void* cub_tmp = base + L.off_cub;
     cudaStream_t st = as_stream2(stream);
 
@@ -132,24 +137,53 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
     KSG_LAUNCHED2();
     iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
     KSG_LAUNCHED2();
-    // primary sort: keys = the primary coordinate, values = original index -> perm
-    int rc = sort_pairs(cub_tmp, L.cub_bytes, d_points + (int64_t)primary * ld, keys_tmp, iota, P.perm, n, st);
-    if (rc) return rc;
+    const unsigned nb = (unsigned)ceil_div(n, 256);
+    int rc;
+    // every coordinate sorted on its own: values + ORIGINAL sample index (remapped below)
+    for (int d = 0; d < dim; ++d) {
+        rc = sort_pairs(cub_tmp, L.cub_bytes, d_points + (int64_t)d * ld, P.axis_vals + (int64_t)d * L.ld, iota,
+                        P.axis_pos + (int64_t)d * L.ld, n, st);
+        if (rc) return rc;
+    }
+    if (primary >= 0) {
+        // order = one coordinate's sorted order
+        KSG_CUDA_TRY(cudaMemcpyAsync(P.perm, P.axis_pos + (int64_t)primary * L.ld, (size_t)n * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+    } else {
+        // order = Morton code of the per-coordinate ranks
+        int32_t* ranks = (int32_t*)(base + L.off_ranks);
+        unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
+        unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
+        for (int d = 0; d < dim; ++d) {
+            rank_scatter_kernel<<<nb, 256, 0, st>>>(P.axis_pos + (int64_t)d * L.ld, n, ranks + (int64_t)d * L.ld);
+            KSG_LAUNCHED2();
+        }
+        int rank_bits = 1;
+        while ((1ll << rank_bits) < n) ++rank_bits;
+        int bits = 63 / dim;
+        if (bits > rank_bits) bits = rank_bits;
+        morton_key_kernel<<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys);
+        KSG_LAUNCHED2();
+        size_t need = L.cub_bytes;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, iota, P.perm, (int)n, 0,
+                                                        bits * dim, st);
+        if (e != cudaSuccess) { set_error("cub SortPairs (morton): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+        note_launch();
+    }
     gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
         d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
     KSG_LAUNCHED2();
-    // every coordinate sorted on its own, remembering the primary-order position
+    // axis_pos: original sample index -> position in the final order
+    int32_t* invperm = (int32_t*)(base + L.off_invperm);
+    invert_perm_kernel<<<nb, 256, 0, st>>>(P.perm, n, invperm);
+    KSG_LAUNCHED2();
     for (int d = 0; d < dim; ++d) {
-        double* vals = P.axis_vals + (int64_t)d * L.ld;
-        int32_t* pos = P.axis_pos + (int64_t)d * L.ld;
-        if (d == primary) {
-            copy_axis_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(P.sorted_f64 + (int64_t)d * L.ld, vals, pos, n);
-            KSG_LAUNCHED2();
-        } else {
-            rc = sort_pairs(cub_tmp, L.cub_bytes, P.sorted_f64 + (int64_t)d * L.ld, vals, iota, pos, n, st);
-            if (rc) return rc;
-        }
+        remap_axis_kernel<<<nb, 256, 0, st>>>(P.axis_pos + (int64_t)d * L.ld, n, invperm);
+        KSG_LAUNCHED2();
     }
+    P.tile_box = (float*)(base + L.off_tile_box);
+    tile_box_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 128, 0, st>>>(P.shadow_f32, L.dim_padded, P.tile_box);
+    KSG_LAUNCHED2();
     *h_out = P;
     return KSG_OK;
 }
@@ -181,7 +215,7 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, int kpri
     }
     cudaStream_t st = as_stream2(stream);
     KnnF32Args a;
-    a.shadow = P->shadow_f32; a.n_tiles = P->n_padded / FAST_TILE; a.primary = P->primary;
+    a.shadow = P->shadow_f32; a.tile_box = P->tile_box; a.n_tiles = P->n_padded / FAST_TILE;
     a.q_begin = q_begin; a.nq = nq; a.kcap = p.kcap; a.splits = p.splits; a.windowed = windowed ? 1 : 0;
     a.maxabs = P->maxabs; a.dim = P->dim;
     a.part_d32 = (float*)d_workspace;
@@ -235,9 +269,10 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
 
     CountF32Args a;
     memset(&a, 0, sizeof(a));
-    a.shadow = P->shadow_f32; a.n_tiles = P->n_padded / FAST_TILE; a.primary = P->primary;
+    a.shadow = P->shadow_f32; a.tile_box = P->tile_box; a.n_tiles = P->n_padded / FAST_TILE;
     a.q_begin = q_begin; a.nq = nq; a.thresholds = thresholds;
-    a.windowed = (windowed && all_have_primary) ? 1 : 0;
+    (void)all_have_primary;  // box pruning works for any subspace family
+    a.windowed = windowed ? 1 : 0;
     a.n_sub = n_subspaces; a.counts = d_counts; a.st = st;
     a.tile_counter = (unsigned long long*)((char*)P->flags + 24);
     const int64_t qblocks = ceil_div(nq, count_f32_queries_per_block(P->dim_padded));

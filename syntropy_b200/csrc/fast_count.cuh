@@ -140,72 +140,83 @@ struct MaskQuad {
 // counts32[s][nq] (int32) are ADDED to (atomicAdd when the candidate range is split).
 template <class Spec, int Q, int STAGES, bool MASKED>
 static __global__ void __launch_bounds__(FAST_THREADS)
-count_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary, int64_t q_begin, int64_t nq,
-                 const float* __restrict__ thresholds, int windowed, MaskQuad masks, int n_sub,
-                 int32_t* __restrict__ counts, unsigned long long* __restrict__ tile_counter) {
+count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
+                 int64_t q_begin, int64_t nq, const float* __restrict__ thresholds, int windowed, MaskQuad masks,
+                 int n_sub, int32_t* __restrict__ counts, unsigned long long* __restrict__ tile_counter) {
     constexpr int DP = Spec::DP, S = Spec::S, SP = (S + 1) / 2;
     constexpr int QB = FAST_THREADS * Q;
     constexpr int TILE_FLOATS = FAST_TILE * DP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ TileQueueShared sh;
 
     const int tid = threadIdx.x;
     const int64_t qb0 = (int64_t)blockIdx.x * QB;
     const int splits = gridDim.y;
 
     float2 q[Q][DP / 2];
-    float qp[Q], T[Q];
-    bool live[Q];
+    float T[Q];
     int cnt[Q][S];
+    float blo[DP], bhi[DP];
+    float tmax = -CUDART_INF_F;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) { blo[d] = CUDART_INF_F; bhi[d] = -CUDART_INF_F; }
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
         const int64_t qi = qb0 + j * FAST_THREADS + tid;
-        live[j] = qi < nq;
-        const int64_t row = q_begin + (live[j] ? qi : 0);
+        const bool live = qi < nq;
+        const int64_t row = q_begin + (live ? qi : 0);
         load_row<DP>(shadow + row * DP, q[j]);
-        qp[j] = shadow[row * DP + primary];
-        T[j] = live[j] ? thresholds[qi] : -1.0f;
+        T[j] = live ? thresholds[qi] : -1.0f;
 #pragma unroll
         for (int s = 0; s < S; ++s) cnt[j][s] = 0;
+        if (live) {
+            tmax = fmaxf(tmax, T[j]);
+#pragma unroll
+            for (int h = 0; h < DP / 2; ++h) {
+                blo[2 * h] = fminf(blo[2 * h], q[j][h].x);         bhi[2 * h] = fmaxf(bhi[2 * h], q[j][h].x);
+                blo[2 * h + 1] = fminf(blo[2 * h + 1], q[j][h].y); bhi[2 * h + 1] = fmaxf(bhi[2 * h + 1], q[j][h].y);
+            }
+        }
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    block_query_box<DP>(blo, bhi, sh);
+    const float Tmax = block_max(tmax, sh);  // a tile is needed iff some subspace's box gap is < Tmax
 
-    const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
-    TileWalk walk(mid / FAST_TILE, n_tiles, blockIdx.y, splits);
-    int64_t pend_tile[STAGES];
-    int head = 0, count = 0;
-    uint32_t phase_bits = 0;
-    auto issue = [&](int slot, int64_t t) {
-        if (tid == 0) {
-            mbar_expect_tx(&full_bar[slot], TILE_FLOATS * 4);
-            bulk_g2s(tiles + (size_t)slot * TILE_FLOATS, shadow + t * TILE_FLOATS, TILE_FLOATS * 4, &full_bar[slot]);
+    auto subspace_maxima = [&](const float* a, float* m) {
+        if constexpr (MASKED) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                float v = 0.0f;
+#pragma unroll
+                for (int d = 0; d < DP; ++d)
+                    if ((masks.m[s] >> d) & 1u) v = fmaxf(v, a[d]);
+                m[s] = masks.m[s] ? v : CUDART_INF_F;  // unused slot: never inside
+            }
+        } else {
+            Spec::eval(a, m);
         }
     };
+    auto test = [&](int64_t t) -> bool {
+        float gap[DP], m[S];
+        box_gaps<DP>(tile_box, t, sh, gap);
+        subspace_maxima(gap, m);
+        bool need = false;
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
-        const int64_t t = walk.next();
-        if (t >= 0) { pend_tile[s] = t; issue(s, t); ++count; }
-    }
-
-    int tiles_done = 0;
-    while (count > 0) {
-        ++tiles_done;
-        const int slot = head;
-        mbar_wait(&full_bar[slot], (phase_bits >> slot) & 1u);
-        phase_bits ^= 1u << slot;
-        const float* tile = tiles + (size_t)slot * TILE_FLOATS;
-
+        for (int s = 0; s < S; ++s) need = need || (s < n_sub && m[s] < Tmax);
+        return need;
+    };
+    auto refresh = [&]() {};
+    auto compute = [&](const float* tile, int64_t) {
         float2 acc[Q][SP];
 #pragma unroll
         for (int j = 0; j < Q; ++j)
 #pragma unroll
             for (int h = 0; h < SP; ++h) acc[j][h] = make_float2(0.0f, 0.0f);
-
 #pragma unroll 2
         for (int c = 0; c < FAST_TILE; ++c) {
             float2 cc[DP / 2];
@@ -220,18 +231,7 @@ count_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary,
                     a[2 * h + 1] = fabsf(d.y);
                 }
                 float m[S];
-                if constexpr (MASKED) {
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        float v = 0.0f;
-#pragma unroll
-                        for (int d = 0; d < DP; ++d)
-                            if ((masks.m[s] >> d) & 1u) v = fmaxf(v, a[d]);
-                        m[s] = masks.m[s] ? v : CUDART_INF_F;  // unused slot: never inside
-                    }
-                } else {
-                    Spec::eval(a, m);
-                }
+                subspace_maxima(a, m);
                 float ind[2 * SP];
 #pragma unroll
                 for (int s = 0; s < S; ++s) ind[s] = (m[s] < T[j]) ? 1.0f : 0.0f;
@@ -245,35 +245,11 @@ count_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary,
         for (int j = 0; j < Q; ++j)
 #pragma unroll
             for (int s = 0; s < S; ++s) cnt[j][s] += (int)((s & 1) ? acc[j][s / 2].y : acc[j][s / 2].x);
+    };
 
-        int keep_left = 0, keep_right = 0;
-        if (windowed) {
-            // a candidate whose primary-coordinate difference is >= T is outside every
-            // subspace of this launch (all of them contain the primary coordinate)
-            if (walk.right_open && walk.hi < n_tiles) {
-                const float edge = __ldg(shadow + (walk.hi * FAST_TILE) * DP + primary);
-#pragma unroll
-                for (int j = 0; j < Q; ++j)
-                    if (live[j]) keep_right |= ((edge - qp[j]) < T[j]);
-            }
-            if (walk.left_open && walk.lo >= 0) {
-                const float edge = __ldg(shadow + ((walk.lo + 1) * FAST_TILE - 1) * DP + primary);
-#pragma unroll
-                for (int j = 0; j < Q; ++j)
-                    if (live[j]) keep_left |= ((qp[j] - edge) < T[j]);
-            }
-            // __syncthreads_or is a boolean OR over the block: one vote per side
-            if (!__syncthreads_or(keep_left)) walk.left_open = false;
-            if (!__syncthreads_or(keep_right)) walk.right_open = false;
-        } else {
-            __syncthreads();
-        }
-        head = (head + 1) % STAGES;
-        --count;
-        const int64_t tn = walk.next();
-        if (tn >= 0) { pend_tile[slot] = tn; issue(slot, tn); ++count; }
-    }
-
+    const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
+    const int tiles_done = run_tile_queue<DP, STAGES>(shadow, tiles, full_bar, sh, mid / FAST_TILE, n_tiles,
+                                                      (int)blockIdx.y, splits, windowed != 0, test, compute, refresh);
     if (tid == 0 && tile_counter) atomicAdd(tile_counter, (unsigned long long)tiles_done);
 #pragma unroll
     for (int j = 0; j < Q; ++j) {

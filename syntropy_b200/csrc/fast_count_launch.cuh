@@ -22,7 +22,7 @@ static int launch_count_spec(const CountF32Args& a) {
     MaskQuad mq;
     for (int i = 0; i < 4; ++i) mq.m[i] = a.masks[i];
     dim3 grid((unsigned)ceil_div(a.nq, FAST_THREADS * Q), (unsigned)a.splits, 1);
-    kern<<<grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.n_tiles, a.primary, a.q_begin, a.nq, a.thresholds,
+    kern<<<grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.thresholds,
                                               a.windowed, mq, a.n_sub, a.counts, a.tile_counter);
     note_launch();
     cudaError_t e = cudaGetLastError();

@@ -24,10 +24,10 @@
 
 #include "common.cuh"
 #include "prepare.cuh"
+#include "tile_queue.cuh"
 
 namespace ksg {
 
-constexpr int FAST_THREADS = 128;
 constexpr int KNN_BATCH = 16;   // candidates between threshold checks
 constexpr int KNN_MARGIN = 3;   // list entries kept beyond k'
 
@@ -90,66 +90,11 @@ __device__ __forceinline__ void load_row(const float* __restrict__ row, float2 (
     }
 }
 
-// ---- mbarrier / bulk-copy primitives (shared::cta addresses)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{ .reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p; }"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// Outward tile walk shared by the filter kernels: own tile, then alternately the next
-// tile to the right and to the left; a side can be closed (window pruning).  `split`
-// keeps every splits-th element of the walk.
-struct TileWalk {
-    int64_t lo, hi, n_tiles;
-    bool left_open, right_open, turn_right;
-    int counter, split, splits;
-    __device__ TileWalk(int64_t own, int64_t n_tiles_, int split_, int splits_)
-        : lo(own - 1), hi(own), n_tiles(n_tiles_), left_open(true), right_open(true), turn_right(true),
-          counter(0), split(split_), splits(splits_) {}
-    // next tile of the full walk, or -1 when exhausted
-    __device__ int64_t next_any() {
-        const bool can_r = right_open && hi < n_tiles;
-        const bool can_l = left_open && lo >= 0;
-        if (!can_r && !can_l) return -1;
-        bool go_right = turn_right ? can_r : !can_l;
-        turn_right = !turn_right;
-        return go_right ? hi++ : lo--;
-    }
-    __device__ int64_t next() {
-        for (;;) {
-            const int64_t t = next_any();
-            if (t < 0) return -1;
-            if ((counter++ % splits) == split) return t;
-        }
-    }
-};
-
 // part_d32 / part_idx: [split][rank][nq]
 template <int DP, int Q, int STAGES>
 static __global__ void __launch_bounds__(FAST_THREADS)
-knn_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary, int64_t q_begin, int64_t nq,
-               int kcap, int windowed, const double* __restrict__ maxabs, int dim,
+knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
+               int64_t q_begin, int64_t nq, int kcap, int windowed, const double* __restrict__ maxabs, int dim,
                float* __restrict__ part_d32, int32_t* __restrict__ part_idx,
                unsigned long long* __restrict__ tile_counter) {
     constexpr int QB = FAST_THREADS * Q;
@@ -159,25 +104,33 @@ knn_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary, i
     float* lst_d = tiles + STAGES * TILE_FLOATS;                             // kcap * QB
     int32_t* lst_i = reinterpret_cast<int32_t*>(lst_d + (size_t)kcap * QB);  // kcap * QB
     __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ TileQueueShared sh;
 
     const int tid = threadIdx.x;
     const int64_t qb0 = (int64_t)blockIdx.x * QB;  // first query of the block (relative to q_begin)
-    const int splits = gridDim.y;
     const Band band = make_band(maxabs, dim);
 
     // queries: slot j of thread t is query qb0 + j*THREADS + t
     float2 q[Q][DP / 2];
-    float qp[Q];      // primary coordinate (window test)
     float thr[Q];     // kcap-th smallest so far
     bool live[Q];
+    float blo[DP], bhi[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) { blo[d] = CUDART_INF_F; bhi[d] = -CUDART_INF_F; }
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
         const int64_t qi = qb0 + j * FAST_THREADS + tid;
         live[j] = qi < nq;
         const int64_t row = q_begin + (live[j] ? qi : 0);
         load_row<DP>(shadow + row * DP, q[j]);
-        qp[j] = shadow[row * DP + primary];
         thr[j] = live[j] ? CUDART_INF_F : -1.0f;  // dead slots never insert
+        if (live[j]) {
+#pragma unroll
+            for (int h = 0; h < DP / 2; ++h) {
+                blo[2 * h] = fminf(blo[2 * h], q[j][h].x);         bhi[2 * h] = fmaxf(bhi[2 * h], q[j][h].x);
+                blo[2 * h + 1] = fminf(blo[2 * h + 1], q[j][h].y); bhi[2 * h + 1] = fmaxf(bhi[2 * h + 1], q[j][h].y);
+            }
+        }
     }
     for (int r = 0; r < kcap; ++r)
 #pragma unroll
@@ -189,41 +142,26 @@ knn_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary, i
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    block_query_box<DP>(blo, bhi, sh);  // (barriers inside: also publishes the mbarrier init)
 
-    // the block's own tile: the one holding its middle query
-    const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
-    TileWalk walk(mid / FAST_TILE, n_tiles, blockIdx.y, splits);
-
-    int64_t pend_tile[STAGES];
-    int head = 0, count = 0;     // ring of issued tiles: slot = (head + i) % STAGES
-    uint32_t phase_bits = 0;     // per-slot parity
-    auto issue = [&](int slot, int64_t t) {
-        if (tid == 0) {
-            mbar_expect_tx(&full_bar[slot], TILE_FLOATS * 4);
-            bulk_g2s(tiles + (size_t)slot * TILE_FLOATS, shadow + t * TILE_FLOATS, TILE_FLOATS * 4, &full_bar[slot]);
-        }
-    };
+    float R = CUDART_INF_F;  // CTA pruning radius: max over its queries of threshold + band
+    auto test = [&](int64_t t) -> bool {
+        float gap[DP];
+        box_gaps<DP>(tile_box, t, sh, gap);
+        float dist = gap[0];
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
-        const int64_t t = walk.next();
-        if (t >= 0) {
-            pend_tile[s] = t;
-            issue(s, t);
-            ++count;
-        }
-    }
-
-    int tiles_done = 0;
-    while (count > 0) {
-        ++tiles_done;
-        const int slot = head;
-        const int64_t t = pend_tile[slot];
-        mbar_wait(&full_bar[slot], (phase_bits >> slot) & 1u);
-        phase_bits ^= 1u << slot;
-        const float* tile = tiles + (size_t)slot * TILE_FLOATS;
+        for (int d = 1; d < DP; ++d) dist = fmaxf(dist, gap[d]);
+        return !(dist > R);
+    };
+    auto refresh = [&]() {
+        float v = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+            if (live[j]) v = fmaxf(v, thr[j] + (band.c0 + band.c1 * thr[j]));
+        R = block_max(v, sh);
+    };
+    auto compute = [&](const float* tile, int64_t t) {
         const int64_t tile_base = t * FAST_TILE;
-
         for (int b = 0; b < FAST_TILE; b += KNN_BATCH) {
             float mrun[Q];
 #pragma unroll
@@ -267,39 +205,13 @@ knn_f32_kernel(const float* __restrict__ shadow, int64_t n_tiles, int primary, i
                 }
             }
         }
+    };
 
-        // window pruning: may a side stop?  (block-uniform; also the "tile consumed" barrier)
-        int keep_left = 0, keep_right = 0;
-        if (windowed) {
-            if (walk.right_open && walk.hi < n_tiles) {
-                const float edge = __ldg(shadow + (walk.hi * FAST_TILE) * DP + primary);  // min of next right tile
-#pragma unroll
-                for (int j = 0; j < Q; ++j)
-                    if (live[j]) keep_right |= !((edge - qp[j]) > thr[j] + (band.c0 + band.c1 * thr[j]));
-            }
-            if (walk.left_open && walk.lo >= 0) {
-                const float edge = __ldg(shadow + ((walk.lo + 1) * FAST_TILE - 1) * DP + primary);  // max of next left tile
-#pragma unroll
-                for (int j = 0; j < Q; ++j)
-                    if (live[j]) keep_left |= !((qp[j] - edge) > thr[j] + (band.c0 + band.c1 * thr[j]));
-            }
-            // __syncthreads_or is a boolean OR over the block: one vote per side
-            if (!__syncthreads_or(keep_left)) walk.left_open = false;
-            if (!__syncthreads_or(keep_right)) walk.right_open = false;
-        } else {
-            __syncthreads();
-        }
-
-        head = (head + 1) % STAGES;
-        --count;
-        const int64_t tn = walk.next();
-        if (tn >= 0) {
-            pend_tile[slot] = tn;
-            issue(slot, tn);
-            ++count;
-        }
-    }
-
+    // the block's own tile: the one holding its middle query
+    const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
+    const int tiles_done = run_tile_queue<DP, STAGES>(shadow, tiles, full_bar, sh, mid / FAST_TILE, n_tiles,
+                                                      (int)blockIdx.y, (int)gridDim.y, windowed != 0, test, compute,
+                                                      refresh);
     if (tid == 0 && tile_counter) atomicAdd(tile_counter, (unsigned long long)tiles_done);
 
     // emit the lists (ascending), one per split

@@ -11,8 +11,8 @@ namespace ksg {
 
 struct KnnF32Args {
     const float* shadow;
+    const float* tile_box;
     int64_t n_tiles;
-    int primary;
     int64_t q_begin, nq;
     int kcap, splits, windowed;
     const double* maxabs;
@@ -27,8 +27,8 @@ int launch_knn_f32(int dim_padded, const KnnF32Args& a);  // KSG_EUNSUPPORTED if
 
 struct CountF32Args {
     const float* shadow;
+    const float* tile_box;
     int64_t n_tiles;
-    int primary;
     int64_t q_begin, nq;
     const float* thresholds;
     int windowed;

@@ -28,7 +28,8 @@ struct PreparedLayout {
     int64_t n_padded;  // shadow rows
     int dim_padded;
     size_t off_perm, off_sorted, off_shadow, off_axis_vals, off_axis_pos, off_center, off_maxabs, off_flags;
-    size_t off_stats, off_iota, off_keys_tmp, off_cub;
+    size_t off_tile_box;
+    size_t off_stats, off_iota, off_keys_tmp, off_ranks, off_mkeys, off_mkeys_out, off_invperm, off_cub;
     size_t cub_bytes;
     size_t total;
 };
@@ -109,6 +110,67 @@ gather_sorted_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, i
             s = 0.0f;
         }
         shadow[i * dim_padded + d] = s;
+    }
+}
+
+// ---- Morton order on per-coordinate RANKS (rank-uniform, so cells hold ~equal point counts)
+// rank[d][orig] = position of sample `orig` in coordinate d's sorted order
+static __global__ void rank_scatter_kernel(const int32_t* __restrict__ sorted_orig, int64_t n,
+                                           int32_t* __restrict__ rank_row) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rank_row[sorted_orig[i]] = (int32_t)i;
+}
+
+// key = bit-interleave of the top `bits` bits of every coordinate's rank (level-major, MSB first)
+static __global__ void morton_key_kernel(const int32_t* __restrict__ ranks, int64_t ld, int64_t n, int dim,
+                                         int rank_bits, int bits, unsigned long long* __restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long key = 0ull;
+    for (int level = 0; level < bits; ++level)
+        for (int d = 0; d < dim; ++d) {
+            const unsigned int r = (unsigned int)ranks[(int64_t)d * ld + i];
+            key = (key << 1) | ((r >> (rank_bits - 1 - level)) & 1u);
+        }
+    keys[i] = key;
+}
+
+static __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = (int32_t)i;
+}
+
+// axis_pos[i] (an original sample index) -> its position in the final order
+static __global__ void remap_axis_kernel(int32_t* __restrict__ pos, int64_t n, const int32_t* __restrict__ inv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] = inv[pos[i]];
+}
+
+// tile_box[(t * dim_padded + d) * 2 + {0,1}] = min / max of the fp32 shadow over tile t
+static __global__ void __launch_bounds__(128)
+tile_box_kernel(const float* __restrict__ shadow, int dim_padded, float* __restrict__ tile_box) {
+    const int64_t t = blockIdx.x;
+    const float* rows = shadow + t * FAST_TILE * dim_padded;
+    __shared__ float slo[4][KSG_MAX_DIM], shi[4][KSG_MAX_DIM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = 0; d < dim_padded; ++d) {
+        float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+        for (int r = threadIdx.x; r < FAST_TILE; r += 128) {
+            const float v = rows[r * dim_padded + d];
+            lo = fminf(lo, v);
+            hi = fmaxf(hi, v);
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        }
+        if (lane == 0) { slo[warp][d] = lo; shi[warp][d] = hi; }
+    }
+    __syncthreads();
+    if (threadIdx.x < dim_padded) {
+        const int d = threadIdx.x;
+        tile_box[(t * dim_padded + d) * 2 + 0] = fminf(fminf(slo[0][d], slo[1][d]), fminf(slo[2][d], slo[3][d]));
+        tile_box[(t * dim_padded + d) * 2 + 1] = fmaxf(fmaxf(shi[0][d], shi[1][d]), fmaxf(shi[2][d], shi[3][d]));
     }
 }
 

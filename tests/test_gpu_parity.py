@@ -64,7 +64,7 @@ def radius_and_counts(E, rows, k, subspaces, strict=True):
         counts = E.count_subspaces(pts, masks, eps, 0, n, strict=strict)
     else:
         windowed = E.config.engine == "windowed"
-        prep = E.PreparedSet(pts, 0)
+        prep = E.PreparedSet(pts, E.config.primary)
         eps_s = E.fast_knn(prep, k + 1, 0, n, windowed)
         counts_s = E.fast_counts(prep, masks, eps_s, 0, n, windowed, strict=strict)
         perm = prep.perm.long()
@@ -349,11 +349,12 @@ def test_c2_full_size(E, knn):
 
 
 def test_engines_agree_bitwise_on_random_configs():
-    """exact fp64, dense fp32-filter and windowed fp32-filter give identical radii / counts."""
+    """exact fp64, dense fp32-filter and windowed fp32-filter (Morton order and single-coordinate
+    order) give identical radii / counts."""
     from syntropy_b200 import _engine as E
 
     rng = np.random.default_rng(77)
-    old = E.config.engine
+    old, old_primary = E.config.engine, E.config.primary
     try:
         for dim, n, k in ((2, 30_000, 5), (4, 20_000, 3), (6, 12_000, 4), (7, 9_000, 2), (8, 10_000, 4)):
             rows = rng.standard_normal((dim, n)) + 0.3 * rng.standard_normal((1, n))
@@ -361,11 +362,11 @@ def test_engines_agree_bitwise_on_random_configs():
             if dim >= 4:
                 subs += [tuple(range(dim // 2)), tuple(range(dim // 2, dim)), (0, dim - 1)]
             got = {}
-            for engine in ("exact", "dense", "windowed"):
-                E.config.engine = engine
-                got[engine] = radius_and_counts(E, rows, k, subs)
-            for engine in ("dense", "windowed"):
-                assert np.array_equal(got[engine][0], got["exact"][0]), (dim, engine, "eps")
-                assert np.array_equal(got[engine][1], got["exact"][1]), (dim, engine, "counts")
+            for engine, primary in (("exact", -1), ("dense", -1), ("windowed", -1), ("windowed", dim - 1)):
+                E.config.engine, E.config.primary = engine, primary
+                got[(engine, primary)] = radius_and_counts(E, rows, k, subs)
+            for key in got:
+                assert np.array_equal(got[key][0], got[("exact", -1)][0]), (dim, key, "eps")
+                assert np.array_equal(got[key][1], got[("exact", -1)][1]), (dim, key, "counts")
     finally:
-        E.config.engine = old
+        E.config.engine, E.config.primary = old, old_primary

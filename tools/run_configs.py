@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Runs the five BASELINE configurations (or scaled versions) on the GPU: parity of radii and
+counts against the CPU oracle on a random query subset (full point set), plus device timing of
+every stage.  Prints one JSON line per configuration.
+
+    python tools/run_configs.py --configs c1,c2,c3,c4 [--engine windowed] [--scale 1.0] [--check 512]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from syntropy_b200 import _engine as E  # noqa: E402
+from syntropy_b200 import knn, workloads  # noqa: E402
+
+# algorithmic lane-ops per pair (radius pass, count pass)
+OPS = {"c1": (4, 4), "c2": (4, 4), "c3": (12, 14), "c4": (16, 42), "c5": (16, 16)}
+SIZES = {"c1": 5_000, "c2": 1_000_000, "c3": 1_000_000, "c4": 250_000, "c5": 4_000_000}
+
+
+def subspaces_of(name, call, dim):
+    if name in ("c1", "c2", "c5"):
+        dx = len(call["idxs_x"])
+        return [tuple(range(dx)), tuple(range(dx, dim))]
+    if name == "c3":
+        return [(4, 5), (0, 1, 4, 5), (2, 3, 4, 5)]
+    subs = []
+    for d in range(dim):
+        subs.append(tuple(j for j in range(dim) if j != d))
+        subs.append((d,))
+    return subs
+
+
+def api_call(name, call, data):
+    if name in ("c1", "c2", "c5"):
+        return knn.mutual_information(call["idxs_x"], call["idxs_y"], call["k"], data)
+    if name == "c3":
+        return knn.conditional_mutual_information(call["idxs_x"], call["idxs_y"], call["idxs_z"], call["k"], data)
+    return knn.o_information(data, call["k"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c1,c2,c3,c4")
+    ap.add_argument("--engine", default="windowed")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--check", type=int, default=512, help="queries checked against the CPU oracle")
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    E.config.engine = args.engine
+    from oracle import ksg_oracle_c as oc
+
+    for name in args.configs.split(","):
+        n = max(64, int(SIZES[name] * args.scale))
+        data, call = workloads.CONFIGS[name](n=n, seed=0)
+        dim, k = data.shape[0], call["k"]
+        if name in ("c1", "c2", "c5"):
+            rows = data[call["idxs_x"] + call["idxs_y"], :]
+        elif name == "c3":
+            rows = data[call["idxs_x"] + call["idxs_y"] + call["idxs_z"], :]
+        else:
+            rows = data
+        subs = subspaces_of(name, call, dim)
+        masks = [E.mask_of(s) for s in subs]
+        pts = E.to_device_points(rows)
+        out = {"config": name, "n": n, "dim": dim, "k": k, "engine": args.engine}
+        best = None
+        for rep in range(args.reps + 1):
+            E.timer.enabled = True
+            E.timer.reset()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if args.engine == "exact":
+                eps = E.knn_radius(pts, k + 1, 0, n)
+                counts = E.count_subspaces(pts, masks, eps, 0, n)
+                prep = None
+            else:
+                prep = E.PreparedSet(pts, E.config.primary)
+                eps = E.fast_knn(prep, k + 1, 0, n, args.engine == "windowed")
+                counts = E.fast_counts(prep, masks, eps, 0, n, args.engine == "windowed")
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            ms = {kname: float(np.sum(v)) for kname, v in E.timer.totals_ms().items()}
+            E.timer.enabled = False
+            if rep > 0 and (best is None or wall < best[0]):
+                best = (wall, ms, prep.tiles_visited() if prep is not None else None)
+        wall, ms, tiles = best
+        out["stage_ms"] = ms
+        out["radius_plus_counts_ms"] = 1e3 * wall
+        a1, a2 = OPS[name]
+        peak = 148 * 128 * 1.965e9
+        if tiles is not None:
+            qb = 512 if ((dim + 1) & ~1) <= 4 else 256
+            p1, p2 = tiles[0] * 512.0 * qb, tiles[1] * 512.0 * qb
+            out["executed_pairs"] = {"knn": p1, "count": p2, "dense": float(n) * n}
+            if ms.get("fast_knn"):
+                out["frac_fp_pipe_knn"] = a1 * p1 / (ms["fast_knn"] * 1e-3) / peak
+            if ms.get("fast_count"):
+                out["frac_fp_pipe_count"] = a2 * p2 / (ms["fast_count"] * 1e-3) / peak
+        else:
+            out["frac_fp_pipe_knn"] = a1 * float(n) * n / (ms["knn_radius"] * 1e-3) / peak
+            out["frac_fp_pipe_count"] = a2 * float(n) * n / (ms["count_subspaces"] * 1e-3) / peak
+        # ---- parity on a query subset against the C oracle (brute force, float64)
+        if prep is not None:
+            perm = prep.perm.long()
+            eps_o = torch.empty_like(eps); eps_o[perm] = eps
+            cnt_o = torch.empty_like(counts); cnt_o[:, perm] = counts
+        else:
+            eps_o, cnt_o = eps, counts
+        eps_h, cnt_h = eps_o.cpu().numpy(), cnt_o.cpu().numpy()
+        sel = np.sort(np.random.default_rng(1).choice(n, size=min(args.check, n), replace=False))
+        t0 = time.perf_counter()
+        ref_eps = oc.knn_radius(rows, k + 1, queries=rows[:, sel])
+        ok_eps = bool(np.array_equal(eps_h[sel], ref_eps))
+        ok_cnt = True
+        for row, s in enumerate(subs):
+            want = oc.count_within(rows[list(s), :], ref_eps, queries=rows[list(s), :][:, sel])
+            ok_cnt = ok_cnt and bool(np.array_equal(cnt_h[row, sel], want))
+        out["oracle_s"] = time.perf_counter() - t0
+        out["parity"] = {"queries_checked": int(sel.size), "radii_bit_exact": ok_eps, "counts_bit_exact": ok_cnt}
+        # ---- public API, end to end on host arrays
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ptw, avg = api_call(name, call, data)
+        out["api_e2e_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["avg_nats"] = float(avg)
+        out["samples_per_s_api"] = n / (out["api_e2e_ms"] * 1e-3)
+        out["fallback_queries"] = dict(E.stats)
+        print(json.dumps(out), flush=True)
+        del pts, prep, eps, counts
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
