@@ -252,14 +252,19 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
 /*
  * K1 on the prepared set: d_eps_out[i - q_begin] = exact kprime-th smallest Chebyshev
  * distance (self included) of the point at SORTED position i, i in [q_begin, q_end).
- * windowed != 0 prunes candidate tiles by the primary coordinate (same result, fewer
- * pairs).  d_flags[i - q_begin] = 1 and *d_n_flagged += 1 for queries the fp32 filter
- * could not decide (tie-saturated neighbourhoods): the caller recomputes those with
- * ksg_knn_radius (queries = the flagged rows of sorted_f64).  d_n_flagged is caller-zeroed.
+ * d_query_index (optional, device int32[q_end - q_begin]): explicit sorted positions of
+ * the queries instead of the contiguous range (q_begin is then ignored; always dense).
+ * windowed != 0 prunes candidate tiles by their bounding boxes (same result, fewer pairs).
+ * Per query, d_flags[i] is 0 (done), 1 (the fp32 filter could not decide -- tie-saturated
+ * neighbourhood: recompute with ksg_knn_radius on that row of sorted_f64) or 2 (an
+ * isolated outlier the windowed pass set aside: recompute with a second ksg_fast_knn call
+ * passing the flagged positions as d_query_index); *d_n_flagged (caller-zeroed) counts
+ * the non-zero flags.
  * Same reference call sites as ksg_knn_radius.
  */
 size_t ksg_fast_knn_workspace(int64_t n, int64_t nq, int dim, int kprime);
-int ksg_fast_knn(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end, int kprime, int windowed,
+int ksg_fast_knn(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end,
+                 const int32_t* d_query_index, int kprime, int windowed,
                  double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged,
                  void* d_workspace, size_t workspace_bytes, void* stream);
 

@@ -262,9 +262,7 @@ class PreparedSet:
         return int(t[2]), int(t[3])
 
 
-def fast_knn(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool) -> torch.Tensor:
-    """Exact k'-th-neighbour radii of sorted positions [q0, q1) (fp32 filter, fp64 refine,
-    dense-fp64 recomputation of the queries the filter could not decide)."""
+def _fast_knn_call(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, q_index=None):
     lib = _cabi.load()
     nq = q1 - q0
     dev = prep.buf.device
@@ -273,16 +271,33 @@ def fast_knn(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool) -
     nflag = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = torch.empty(max(int(lib.ksg_fast_knn_workspace(prep.n, max(nq, 1), prep.dim, kprime)), 1),
                      dtype=torch.uint8, device=dev)
-    with timer.span("fast_knn"):
-        rc = lib.ksg_fast_knn(C.byref(prep.c), q0, q1, kprime, 1 if windowed else 0, _ptr(eps), _ptr(flags),
-                              _ptr(nflag), _ptr(ws), ws.numel(), _stream())
+    with timer.span("fast_knn" if q_index is None else "fast_knn_deferred"):
+        rc = lib.ksg_fast_knn(C.byref(prep.c), q0, q1, _ptr(q_index), kprime, 1 if windowed else 0, _ptr(eps),
+                              _ptr(flags), _ptr(nflag), _ptr(ws), ws.numel(), _stream())
     _cabi.check(rc, "ksg_fast_knn")
+    return eps, flags, nflag
+
+
+def fast_knn(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool) -> torch.Tensor:
+    """Exact k'-th-neighbour radii of sorted positions [q0, q1): fp32 filter + fp64 refine; the
+    outliers the windowed pass sets aside go through a dense launch of the same filter, the
+    queries the filter cannot decide (tie-saturated data) through the dense fp64 kernel."""
+    nq = q1 - q0
+    eps, flags, nflag = _fast_knn_call(prep, kprime, q0, q1, windowed)
     if nq and int(nflag.item()):
-        idx = flags.nonzero().flatten()
-        stats["knn_fallback_queries"] += int(idx.numel())
-        pts = prep.sorted_f64
-        queries = pts[:, q0 + idx].contiguous()
-        eps[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries)
+        deferred = (flags == 2).nonzero().flatten()
+        if deferred.numel():
+            stats["knn_deferred_queries"] += int(deferred.numel())
+            rows = (q0 + deferred).to(torch.int32)
+            eps2, flags2, _ = _fast_knn_call(prep, kprime, 0, int(rows.numel()), False, q_index=rows)
+            eps[deferred] = eps2
+            flags[deferred] = flags2
+        idx = (flags == 1).nonzero().flatten()
+        if idx.numel():
+            stats["knn_fallback_queries"] += int(idx.numel())
+            pts = prep.sorted_f64
+            queries = pts[:, q0 + idx].contiguous()
+            eps[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries)
     return eps
 
 
@@ -334,7 +349,7 @@ def scatter_to_original(values_sorted: torch.Tensor, prep: PreparedSet) -> torch
     return out
 
 
-stats = {"knn_fallback_queries": 0, "count_fallback_queries": 0}
+stats = {"knn_fallback_queries": 0, "count_fallback_queries": 0, "knn_deferred_queries": 0}
 
 
 def _use_fast(dim: int) -> bool:

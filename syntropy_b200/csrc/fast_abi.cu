@@ -195,12 +195,13 @@ size_t ksg_fast_knn_workspace(int64_t n, int64_t nq, int dim, int kprime) {
     return p.d32_bytes + p.idx_bytes + 256;
 }
 
-int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, int kprime, int windowed,
-                 double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged, void* d_workspace,
+int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const int32_t* d_query_index, int kprime,
+                 int windowed, double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged, void* d_workspace,
                  size_t workspace_bytes, void* stream) {
     KSG_REQUIRE(P && d_eps_out && d_flags && d_n_flagged && d_workspace, "ksg_fast_knn: null pointer");
-    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_fast_knn: bad query range");
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && (d_query_index || q_end <= P->n), "ksg_fast_knn: bad query range");
     KSG_REQUIRE(kprime >= 1 && kprime + KNN_MARGIN <= KSG_MAX_KPRIME, "ksg_fast_knn: kprime out of range");
+    if (d_query_index) windowed = 0;  // an explicit query list has no spatial coherence to prune with
     if (P->dim_padded > 8) {
         set_error("ksg_fast_knn: the fp32 filter is instantiated for up to 8 dimensions (got %d); use ksg_knn_radius",
                   P->dim);
@@ -216,7 +217,8 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, int kpri
     cudaStream_t st = as_stream2(stream);
     KnnF32Args a;
     a.shadow = P->shadow_f32; a.tile_box = P->tile_box; a.n_tiles = P->n_padded / FAST_TILE;
-    a.q_begin = q_begin; a.nq = nq; a.kcap = p.kcap; a.splits = p.splits; a.windowed = windowed ? 1 : 0;
+    a.q_begin = q_begin; a.nq = nq; a.q_index = d_query_index; a.kcap = p.kcap; a.splits = p.splits;
+    a.windowed = windowed ? 1 : 0;
     a.maxabs = P->maxabs; a.dim = P->dim;
     a.part_d32 = (float*)d_workspace;
     a.part_idx = (int32_t*)((char*)d_workspace + p.d32_bytes);
@@ -226,7 +228,8 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, int kpri
     if (rc) return rc;
     knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, p.splits, kprime,
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
-                                                                   P->maxabs, d_eps_out, d_flags, d_n_flagged);
+                                                                   d_query_index, P->maxabs, d_eps_out, d_flags,
+                                                                   d_n_flagged);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

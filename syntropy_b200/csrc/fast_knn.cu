@@ -16,7 +16,7 @@ static int launch_knn_dp(const KnnF32Args& a) {
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     }
     dim3 grid((unsigned)ceil_div(a.nq, FAST_THREADS * Q), (unsigned)a.splits, 1);
-    kern<<<grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.windowed,
+    kern<<<grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.q_index, a.kcap, a.windowed,
                                               a.maxabs, a.dim, a.part_d32, a.part_idx, a.tile_counter);
     note_launch();
     cudaError_t e = cudaGetLastError();

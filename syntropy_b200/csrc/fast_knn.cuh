@@ -30,6 +30,9 @@ namespace ksg {
 
 constexpr int KNN_BATCH = 16;   // candidates between threshold checks
 constexpr int KNN_MARGIN = 3;   // list entries kept beyond k'
+constexpr int KNN_SEED_W = 24;  // rows on each side of a query used to seed its threshold
+constexpr float KNN_DEFER_CUT = 4.0f;   // defer a query whose seeded radius exceeds CUT x the CTA mean
+constexpr float KNN_DEFERRED = -2.0f;   // sentinel distance marking a deferred query's list
 
 // ---- fp32 error band of the shadow copy (see DESIGN.md "Exactness")
 // |d32 - d64| <= 2^-24 * (2*M + |d|) * (1 + tiny) per dimension; kept as a pair of
@@ -94,9 +97,9 @@ __device__ __forceinline__ void load_row(const float* __restrict__ row, float2 (
 template <int DP, int Q, int STAGES>
 static __global__ void __launch_bounds__(FAST_THREADS)
 knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
-               int64_t q_begin, int64_t nq, int kcap, int windowed, const double* __restrict__ maxabs, int dim,
-               float* __restrict__ part_d32, int32_t* __restrict__ part_idx,
-               unsigned long long* __restrict__ tile_counter) {
+               int64_t q_begin, int64_t nq, const int32_t* __restrict__ q_index, int kcap, int windowed,
+               const double* __restrict__ maxabs, int dim, float* __restrict__ part_d32,
+               int32_t* __restrict__ part_idx, unsigned long long* __restrict__ tile_counter) {
     constexpr int QB = FAST_THREADS * Q;
     constexpr int TILE_FLOATS = FAST_TILE * DP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -114,6 +117,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
     float2 q[Q][DP / 2];
     float thr[Q];     // kcap-th smallest so far
     bool live[Q];
+    int64_t qrow[Q];  // row of the query in the prepared order
     float blo[DP], bhi[DP];
 #pragma unroll
     for (int d = 0; d < DP; ++d) { blo[d] = CUDART_INF_F; bhi[d] = -CUDART_INF_F; }
@@ -121,7 +125,8 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
     for (int j = 0; j < Q; ++j) {
         const int64_t qi = qb0 + j * FAST_THREADS + tid;
         live[j] = qi < nq;
-        const int64_t row = q_begin + (live[j] ? qi : 0);
+        const int64_t row = q_index ? (int64_t)q_index[live[j] ? qi : 0] : q_begin + (live[j] ? qi : 0);
+        qrow[j] = row;
         load_row<DP>(shadow + row * DP, q[j]);
         thr[j] = live[j] ? CUDART_INF_F : -1.0f;  // dead slots never insert
         if (live[j]) {
@@ -132,12 +137,57 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
             }
         }
     }
-    for (int r = 0; r < kcap; ++r)
+    auto reset_lists = [&]() {
+        for (int r = 0; r < kcap; ++r)
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            lst_d[(size_t)r * QB + j * FAST_THREADS + tid] = CUDART_INF_F;
-            lst_i[(size_t)r * QB + j * FAST_THREADS + tid] = -1;
+            for (int j = 0; j < Q; ++j) {
+                lst_d[(size_t)r * QB + j * FAST_THREADS + tid] = CUDART_INF_F;
+                lst_i[(size_t)r * QB + j * FAST_THREADS + tid] = -1;
+            }
+    };
+    // sorted insertion of (m, idx) into slot j's list; returns the new kcap-th value
+    auto insert = [&](int j, float m, int32_t idx) -> float {
+        const int col = j * FAST_THREADS + tid;
+        int r = kcap - 1;
+        while (r > 0 && lst_d[(size_t)(r - 1) * QB + col] > m) {
+            lst_d[(size_t)r * QB + col] = lst_d[(size_t)(r - 1) * QB + col];
+            lst_i[(size_t)r * QB + col] = lst_i[(size_t)(r - 1) * QB + col];
+            --r;
         }
+        lst_d[(size_t)r * QB + col] = m;
+        lst_i[(size_t)r * QB + col] = idx;
+        return lst_d[(size_t)(kcap - 1) * QB + col];
+    };
+    reset_lists();
+
+    // ---- seed the thresholds: the kcap-th smallest fp32 distance among the 2*KNN_SEED_W rows
+    // around each query in the prepared order is an upper bound of its final kcap-th distance.
+    // Starting from it (+ band, so that those very rows re-enter the list when their tile is
+    // scanned) removes the flood of insertions a threshold of +inf causes and gives the tile
+    // queue a finite pruning radius from its first round.
+    {
+        const int64_t n_rows = n_tiles * FAST_TILE;
+#pragma unroll 1
+        for (int off = 1; off <= KNN_SEED_W; ++off) {
+#pragma unroll 1
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    const int64_t row = qrow[j] + sgn * off;
+                    if (live[j] && row >= 0 && row < n_rows) {
+                        float2 cc[DP / 2];
+                        load_row<DP>(shadow + row * DP, cc);
+                        const float m = cheb32<DP>(q[j], cc);
+                        if (m < thr[j]) thr[j] = insert(j, m, 0);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+            if (live[j]) thr[j] = thr[j] + (band.c0 + band.c1 * thr[j]);  // inf stays inf
+        reset_lists();
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,24 +232,16 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
 #pragma unroll
             for (int j = 0; j < Q; ++j) hit = hit || (mrun[j] < thr[j]);
             if (hit) {
-                // rare: walk the batch again, candidate by candidate, and insert
-                for (int c = 0; c < KNN_BATCH; ++c) {
-                    float2 cc[DP / 2];
-                    load_row<DP>(tile + (b + c) * DP, cc);
+                // rare: walk the batch again for the slots that saw a closer candidate, and insert
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        const float m = cheb32<DP>(q[j], cc);
-                        if (m < thr[j]) {
-                            const int col = j * FAST_THREADS + tid;
-                            int r = kcap - 1;
-                            while (r > 0 && lst_d[(size_t)(r - 1) * QB + col] > m) {
-                                lst_d[(size_t)r * QB + col] = lst_d[(size_t)(r - 1) * QB + col];
-                                lst_i[(size_t)r * QB + col] = lst_i[(size_t)(r - 1) * QB + col];
-                                --r;
-                            }
-                            lst_d[(size_t)r * QB + col] = m;
-                            lst_i[(size_t)r * QB + col] = (int32_t)(tile_base + b + c);
-                            thr[j] = lst_d[(size_t)(kcap - 1) * QB + col];
+                for (int j = 0; j < Q; ++j) {
+                    if (mrun[j] < thr[j]) {
+#pragma unroll 1
+                        for (int c = 0; c < KNN_BATCH; ++c) {
+                            float2 cc[DP / 2];
+                            load_row<DP>(tile + (b + c) * DP, cc);
+                            const float m = cheb32<DP>(q[j], cc);
+                            if (m < thr[j]) thr[j] = insert(j, m, (int32_t)(tile_base + b + c));
                         }
                     }
                 }
@@ -207,8 +249,37 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
         }
     };
 
+    // ---- outlier deferral (windowed engine): one isolated query next to a dense region would
+    // blow the CTA's pruning radius up to its own huge neighbour distance and make all 128*Q
+    // queries walk most of the point set.  Queries whose seeded radius is far above the CTA's
+    // mean AND above the CTA's own extent are taken out here (sentinel in the output list) and
+    // recomputed by a dense launch over the compacted list of such queries.
+    bool deferred[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) deferred[j] = false;
+    if (windowed) {
+        float sum = 0.0f, cnt = 0.0f;
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+            if (live[j] && thr[j] < CUDART_INF_F) { sum += thr[j]; cnt += 1.0f; }
+        sum = block_sum(sum, sh);
+        cnt = block_sum(cnt, sh);
+        float extent = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) extent = fmaxf(extent, sh.qhi[d] - sh.qlo[d]);
+        const float cut = fmaxf(KNN_DEFER_CUT * (sum / fmaxf(cnt, 1.0f)), 2.0f * extent);
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+            if (live[j] && thr[j] < CUDART_INF_F && thr[j] > cut) {
+                deferred[j] = true;
+                live[j] = false;   // no longer part of the pruning radius
+                thr[j] = -1.0f;    // never inserts
+            }
+        refresh();  // seeded thresholds -> finite pruning radius from the first round
+    }
+
     // the block's own tile: the one holding its middle query
-    const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
+    const int64_t mid = q_index ? 0 : q_begin + min(qb0 + QB / 2, nq - 1);
     const int tiles_done = run_tile_queue<DP, STAGES>(shadow, tiles, full_bar, sh, mid / FAST_TILE, n_tiles,
                                                       (int)blockIdx.y, (int)gridDim.y, windowed != 0, test, compute,
                                                       refresh);
@@ -222,7 +293,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
             const int col = j * FAST_THREADS + tid;
             for (int r = 0; r < kcap; ++r) {
                 const int64_t o = ((int64_t)blockIdx.y * kcap + r) * nq + qi;
-                part_d32[o] = lst_d[(size_t)r * QB + col];
+                part_d32[o] = deferred[j] ? KNN_DEFERRED : lst_d[(size_t)r * QB + col];
                 part_idx[o] = lst_i[(size_t)r * QB + col];
             }
         }
@@ -235,10 +306,17 @@ constexpr int REFINE_CAP = 96;  // union entries examined per query
 static __global__ void __launch_bounds__(128)
 knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict__ part_idx, int kcap, int splits,
                   int kp, const double* __restrict__ sorted, int64_t ld, int dim, int64_t n, int64_t q_begin,
-                  int64_t nq, const double* __restrict__ maxabs, double* __restrict__ eps_out,
-                  int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
+                  int64_t nq, const int32_t* __restrict__ q_index, const double* __restrict__ maxabs,
+                  double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
+    if (part_d32[qi] == KNN_DEFERRED) {  // taken out by the windowed filter: needs the dense launch
+        flags[qi] = 2;
+        atomicAdd(n_flagged, 1);
+        eps_out[qi] = CUDART_NAN;
+        return;
+    }
+    const int64_t row_q = q_index ? (int64_t)q_index[qi] : q_begin + qi;
     double mmax = 0.0;
     for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
 
@@ -267,7 +345,7 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     double exact[KSG_MAX_KPRIME];
     int got = 0, examined = 0;
     double qc[KSG_MAX_DIM];
-    for (int d = 0; d < dim; ++d) qc[d] = sorted[(int64_t)d * ld + q_begin + qi];
+    for (int d = 0; d < dim; ++d) qc[d] = sorted[(int64_t)d * ld + row_q];
     for (int s = 0; s < splits && !overflow; ++s) {
         // a full list whose tail is still inside the band may have dropped in-band candidates
         const float tail = part_d32[((int64_t)s * kcap + (kcap - 1)) * nq + qi];

@@ -14,6 +14,7 @@ struct KnnF32Args {
     const float* tile_box;
     int64_t n_tiles;
     int64_t q_begin, nq;
+    const int32_t* q_index;  // optional: explicit query rows (then q_begin is ignored)
     int kcap, splits, windowed;
     const double* maxabs;
     int dim;

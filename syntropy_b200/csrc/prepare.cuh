@@ -113,7 +113,7 @@ gather_sorted_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, i
     }
 }
 
-// ---- Morton order on per-coordinate RANKS (rank-uniform, so cells hold ~equal point counts)
+// ---- space-filling-curve order on per-coordinate RANKS (rank-uniform: cells hold ~equal point counts)
 // rank[d][orig] = position of sample `orig` in coordinate d's sorted order
 static __global__ void rank_scatter_kernel(const int32_t* __restrict__ sorted_orig, int64_t n,
                                            int32_t* __restrict__ rank_row) {
@@ -121,17 +121,42 @@ static __global__ void rank_scatter_kernel(const int32_t* __restrict__ sorted_or
     if (i < n) rank_row[sorted_orig[i]] = (int32_t)i;
 }
 
-// key = bit-interleave of the top `bits` bits of every coordinate's rank (level-major, MSB first)
+// key = Hilbert-curve index of the point in rank space: the top `bits` bits of every
+// coordinate's rank are taken as integer axes, converted to the "transposed" Hilbert form
+// with Skilling's axes-to-transpose bit manipulation (J. Skilling, "Programming the Hilbert
+// curve", AIP Conf. Proc. 707, 2004) and bit-interleaved (level-major, MSB first).  Unlike
+// the plain Z-order interleave the Hilbert curve has no jumps: any run of consecutive
+// points is a connected blob, so 512-point tiles and query blocks get tight boxes.
 static __global__ void morton_key_kernel(const int32_t* __restrict__ ranks, int64_t ld, int64_t n, int dim,
                                          int rank_bits, int bits, unsigned long long* __restrict__ keys) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    unsigned int X[KSG_MAX_DIM];
+    for (int d = 0; d < dim; ++d)
+        X[d] = ((unsigned int)ranks[(int64_t)d * ld + i]) >> (rank_bits - bits);
+    if (dim > 1) {
+        const unsigned int M = 1u << (bits - 1);
+        for (unsigned int Q = M; Q > 1u; Q >>= 1) {
+            const unsigned int P = Q - 1u;
+            for (int d = 0; d < dim; ++d) {
+                if (X[d] & Q) {
+                    X[0] ^= P;  // invert the low bits of axis 0
+                } else {
+                    const unsigned int t = (X[0] ^ X[d]) & P;  // exchange low bits of axes 0 and d
+                    X[0] ^= t;
+                    X[d] ^= t;
+                }
+            }
+        }
+        for (int d = 1; d < dim; ++d) X[d] ^= X[d - 1];  // Gray encode
+        unsigned int t = 0u;
+        for (unsigned int Q = M; Q > 1u; Q >>= 1)
+            if (X[dim - 1] & Q) t ^= Q - 1u;
+        for (int d = 0; d < dim; ++d) X[d] ^= t;
+    }
     unsigned long long key = 0ull;
     for (int level = 0; level < bits; ++level)
-        for (int d = 0; d < dim; ++d) {
-            const unsigned int r = (unsigned int)ranks[(int64_t)d * ld + i];
-            key = (key << 1) | ((r >> (rank_bits - 1 - level)) & 1u);
-        }
+        for (int d = 0; d < dim; ++d) key = (key << 1) | ((X[d] >> (bits - 1 - level)) & 1u);
     keys[i] = key;
 }
 

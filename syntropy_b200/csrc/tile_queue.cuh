@@ -79,6 +79,15 @@ __device__ __forceinline__ float block_max(float v, TileQueueShared& sh) {
     return fmaxf(fmaxf(sh.red[0], sh.red[1]), fmaxf(sh.red[2], sh.red[3]));
 }
 
+// block-wide sum of a per-thread value (all threads get it); contains two barriers
+__device__ __forceinline__ float block_sum(float v, TileQueueShared& sh) {
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return (sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]);
+}
+
 // bounding box of the CTA's live queries -> sh.qlo / sh.qhi
 template <int DP>
 __device__ __forceinline__ void block_query_box(const float (&lo)[DP], const float (&hi)[DP], TileQueueShared& sh) {
@@ -125,7 +134,7 @@ __device__ __forceinline__ int run_tile_queue(const float* __restrict__ shadow, 
     int64_t issue_cnt = 0, consume_cnt = 0;  // kernel-lifetime counters: slot = cnt % STAGES
     int tiles_done = 0;
     int64_t pos = 0;
-    int chunk = prune ? 1 : FAST_THREADS;
+    int chunk = prune ? 32 : FAST_THREADS;  // thresholds are seeded: R is finite from the first round
     while (pos < n_tiles) {
         const int c = (int)((n_tiles - pos) < chunk ? (n_tiles - pos) : chunk);
         // ---- test this round's walk positions, one per thread
@@ -173,7 +182,7 @@ __device__ __forceinline__ int run_tile_queue(const float* __restrict__ shadow, 
         pos += c;
         if (prune) {
             refresh();
-            chunk = chunk == 1 ? 8 : (chunk == 8 ? 32 : FAST_THREADS);
+            chunk = FAST_THREADS;
         }
     }
     return tiles_done;
