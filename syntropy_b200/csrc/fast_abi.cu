@@ -76,17 +76,39 @@ static int sort_pairs(void* cub_tmp, size_t cub_bytes, const double* keys_in, do
 
 struct FastKnnPlan {
     int kcap, splits, qb;
+    int64_t qblocks;
     size_t d32_bytes, idx_bytes;
+    // planning pass (windowed engine)
+    size_t seed_bytes, plan_bytes, count_bytes, order_bytes, sort_bytes;
+    size_t total() const {
+        return d32_bytes + idx_bytes + seed_bytes + plan_bytes + 4 * count_bytes + order_bytes + sort_bytes;
+    }
 };
+static size_t cub_sort_i32_bytes(int64_t n) {
+    size_t bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                                              (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+    if (e != cudaSuccess || bytes == 0) {
+        (void)cudaGetLastError();
+        bytes = (size_t)n * 16 + (1u << 20);
+    }
+    return bytes;
+}
 static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int windowed) {
     FastKnnPlan p;
     const int dp = (dim + 1) & ~1;
     p.kcap = kprime + KNN_MARGIN;
     p.qb = knn_f32_queries_per_block(dp);
     const int64_t qblocks = ceil_div(nq, p.qb);
+    p.qblocks = qblocks;
     p.splits = windowed ? 1 : choose_splits(qblocks, n, FAST_TILE);
     p.d32_bytes = align_up((size_t)p.splits * p.kcap * nq * sizeof(float), 256);
     p.idx_bytes = align_up((size_t)p.splits * p.kcap * nq * sizeof(int32_t), 256);
+    p.seed_bytes = align_up((size_t)nq * sizeof(float), 256);
+    p.plan_bytes = align_up((size_t)qblocks * knn_plan_cap() * 8, 256);
+    p.count_bytes = align_up((size_t)qblocks * sizeof(int32_t), 256);
+    p.order_bytes = align_up((size_t)qblocks * sizeof(int32_t), 256);
+    p.sort_bytes = align_up(cub_sort_i32_bytes(qblocks), 256);
     return p;
 }
 
@@ -192,7 +214,7 @@ size_t ksg_fast_knn_workspace(int64_t n, int64_t nq, int dim, int kprime) {
     if (n <= 0 || nq <= 0 || dim < 1 || kprime < 1) return 0;
     // sized for the dense (split) launch; the windowed launch needs less
     FastKnnPlan p = fast_knn_plan(n, nq, dim, kprime, 0);
-    return p.d32_bytes + p.idx_bytes + 256;
+    return p.total() + 256;
 }
 
 int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const int32_t* d_query_index, int kprime,
@@ -210,8 +232,8 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const in
     const int64_t nq = q_end - q_begin;
     if (nq == 0) return KSG_OK;
     FastKnnPlan p = fast_knn_plan(P->n, nq, P->dim, kprime, windowed);
-    if (workspace_bytes < p.d32_bytes + p.idx_bytes) {
-        set_error("ksg_fast_knn: workspace of %zu bytes needed, %zu given", p.d32_bytes + p.idx_bytes, workspace_bytes);
+    if (workspace_bytes < p.total()) {
+        set_error("ksg_fast_knn: workspace of %zu bytes needed, %zu given", p.total(), workspace_bytes);
         return KSG_EWORKSPACE;
     }
     cudaStream_t st = as_stream2(stream);
@@ -224,7 +246,31 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const in
     a.part_idx = (int32_t*)((char*)d_workspace + p.d32_bytes);
     a.tile_counter = (unsigned long long*)((char*)P->flags + 16);
     a.st = st;
-    int rc = launch_knn_f32(P->dim_padded, a);
+    a.seed_thr = nullptr; a.plan = nullptr; a.plan_count = nullptr; a.block_order = nullptr;
+    int rc;
+    if (a.windowed) {
+        // planning pass: seeds, per-block tile lists, then blocks ordered longest list first
+        char* w = (char*)d_workspace + p.d32_bytes + p.idx_bytes;
+        a.seed_thr = (float*)w;                      w += p.seed_bytes;
+        a.plan = w;                                  w += p.plan_bytes;
+        a.plan_count = (int32_t*)w;                  w += p.count_bytes;
+        int32_t* cost = (int32_t*)w;                 w += p.count_bytes;
+        int32_t* cost_sorted = (int32_t*)w;          w += p.count_bytes;
+        int32_t* iota = (int32_t*)w;                 w += p.count_bytes;
+        int32_t* order = (int32_t*)w;                w += p.order_bytes;
+        void* sort_tmp = w;
+        rc = launch_knn_plan(P->dim_padded, a);
+        if (rc) return rc;
+        plan_cost_kernel<<<(unsigned)ceil_div(p.qblocks, 256), 256, 0, st>>>(a.plan_count, p.qblocks, cost, iota);
+        KSG_LAUNCHED2();
+        size_t need = p.sort_bytes;
+        cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(sort_tmp, need, cost, cost_sorted, iota, order,
+                                                                  (int)p.qblocks, 0, 32, st);
+        if (e != cudaSuccess) { set_error("cub SortPairsDescending: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+        note_launch();
+        a.block_order = order;
+    }
+    rc = launch_knn_f32(P->dim_padded, a);
     if (rc) return rc;
     knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, p.splits, kprime,
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,

@@ -17,11 +17,42 @@ static int launch_knn_dp(const KnnF32Args& a) {
     }
     dim3 grid((unsigned)ceil_div(a.nq, FAST_THREADS * Q), (unsigned)a.splits, 1);
     kern<<<grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.q_index, a.kcap, a.windowed,
-                                              a.maxabs, a.dim, a.part_d32, a.part_idx, a.tile_counter);
+                                              a.maxabs, a.dim, a.seed_thr, (const int2*)a.plan, a.plan_count, a.block_order,
+                                              a.part_d32, a.part_idx, a.tile_counter);
     note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_f32_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     return KSG_OK;
+}
+
+template <int DP>
+static int launch_plan_dp(const KnnF32Args& a) {
+    constexpr int Q = FastGeom<DP>::Q;
+    auto kern = knn_plan_kernel<DP, Q>;
+    const size_t smem = (size_t)a.kcap * FAST_THREADS * Q * 4;
+    if (smem > 32 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    }
+    kern<<<(unsigned)ceil_div(a.nq, FAST_THREADS * Q), FAST_THREADS, smem, a.st>>>(
+        a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.maxabs, a.dim, a.seed_thr, (int2*)a.plan,
+        a.plan_count);
+    note_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("knn_plan_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    return KSG_OK;
+}
+
+int knn_plan_cap() { return KNN_PLAN_CAP; }
+
+int launch_knn_plan(int dim_padded, const KnnF32Args& a) {
+    switch (dim_padded) {
+        case 2: return launch_plan_dp<2>(a);
+        case 4: return launch_plan_dp<4>(a);
+        case 6: return launch_plan_dp<6>(a);
+        case 8: return launch_plan_dp<8>(a);
+        default: return KSG_EUNSUPPORTED;
+    }
 }
 
 int launch_knn_f32(int dim_padded, const KnnF32Args& a) {

@@ -33,6 +33,7 @@ constexpr int KNN_MARGIN = 3;   // list entries kept beyond k'
 constexpr int KNN_SEED_W = 24;  // rows on each side of a query used to seed its threshold
 constexpr float KNN_DEFER_CUT = 4.0f;   // defer a query whose seeded radius exceeds CUT x the CTA mean
 constexpr float KNN_DEFERRED = -2.0f;   // sentinel distance marking a deferred query's list
+constexpr int KNN_PLAN_CAP = 1024;      // tile-list entries per query block (more: in-kernel walk)
 
 // ---- fp32 error band of the shadow copy (see DESIGN.md "Exactness")
 // |d32 - d64| <= 2^-24 * (2*M + |d|) * (1 + tiny) per dimension; kept as a pair of
@@ -93,12 +94,115 @@ __device__ __forceinline__ void load_row(const float* __restrict__ row, float2 (
     }
 }
 
+// ---- planning pass of the windowed engine.  One CTA per query block: seeds every query's
+// threshold from its neighbours in the prepared order, derives the block's pruning radius, tests
+// EVERY candidate tile's bounding box against the block's query box and writes the survivors
+// (tile, gap) in walk order.  The filter kernel then streams exactly that list (re-checking each
+// gap against its shrinking radius) with no in-kernel search rounds, and the host side of the ABI
+// launches the blocks longest-list-first so that no heavy block is left for the tail.
+template <int DP, int Q>
+static __global__ void __launch_bounds__(FAST_THREADS)
+knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
+                int64_t q_begin, int64_t nq, int kcap, const double* __restrict__ maxabs, int dim,
+                float* __restrict__ seed_thr, int2* __restrict__ plan, int32_t* __restrict__ plan_count) {
+    constexpr int QB = FAST_THREADS * Q;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* lst_d = reinterpret_cast<float*>(smem_raw);  // kcap * QB (values only)
+    __shared__ TileQueueShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t qb0 = (int64_t)blockIdx.x * QB;
+    const Band band = make_band(maxabs, dim);
+    const int64_t n_rows = n_tiles * FAST_TILE;
+
+    float blo[DP], bhi[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) { blo[d] = CUDART_INF_F; bhi[d] = -CUDART_INF_F; }
+    float rmax = -CUDART_INF_F;
+#pragma unroll 1
+    for (int j = 0; j < Q; ++j) {
+        const int64_t qi = qb0 + j * FAST_THREADS + tid;
+        if (qi >= nq) continue;
+        const int64_t row = q_begin + qi;
+        float2 q[DP / 2];
+        load_row<DP>(shadow + row * DP, q);
+#pragma unroll
+        for (int h = 0; h < DP / 2; ++h) {
+            blo[2 * h] = fminf(blo[2 * h], q[h].x);         bhi[2 * h] = fmaxf(bhi[2 * h], q[h].x);
+            blo[2 * h + 1] = fminf(blo[2 * h + 1], q[h].y); bhi[2 * h + 1] = fmaxf(bhi[2 * h + 1], q[h].y);
+        }
+        const int col = j * FAST_THREADS + tid;
+        for (int r = 0; r < kcap; ++r) lst_d[(size_t)r * QB + col] = CUDART_INF_F;
+        float thr = CUDART_INF_F;
+#pragma unroll 1
+        for (int off = 1; off <= KNN_SEED_W; ++off)
+#pragma unroll 1
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+                const int64_t r2 = row + sgn * off;
+                if (r2 < 0 || r2 >= n_rows) continue;
+                float2 cc[DP / 2];
+                load_row<DP>(shadow + r2 * DP, cc);
+                const float m = cheb32<DP>(q, cc);
+                if (m < thr) {
+                    int r = kcap - 1;
+                    while (r > 0 && lst_d[(size_t)(r - 1) * QB + col] > m) {
+                        lst_d[(size_t)r * QB + col] = lst_d[(size_t)(r - 1) * QB + col];
+                        --r;
+                    }
+                    lst_d[(size_t)r * QB + col] = m;
+                    thr = lst_d[(size_t)(kcap - 1) * QB + col];
+                }
+            }
+        thr = thr + (band.c0 + band.c1 * thr);  // inf stays inf
+        seed_thr[qi] = thr;
+        rmax = fmaxf(rmax, thr);
+    }
+    block_query_box<DP>(blo, bhi, sh);
+    const float R = block_max(rmax, sh);
+
+    const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
+    const int64_t own = mid / FAST_TILE;
+    int2* out = plan + (int64_t)blockIdx.x * KNN_PLAN_CAP;
+    int total = 0;
+    for (int64_t pos = 0; pos < n_tiles; pos += FAST_THREADS) {
+        bool keep = false;
+        int64_t t = 0;
+        float dist = 0.0f;
+        if (pos + tid < n_tiles) {
+            t = walk_tile(pos + tid, own, n_tiles);
+            float gap[DP];
+            box_gaps<DP>(tile_box, t, sh, gap);
+            dist = gap[0];
+#pragma unroll
+            for (int d = 1; d < DP; ++d) dist = fmaxf(dist, gap[d]);
+            keep = !(dist > R);
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();
+        if (lane == 0) sh.warp_count[warp] = __popc(ballot);
+        __syncthreads();
+        int offset = total, round_total = 0;
+#pragma unroll
+        for (int w = 0; w < FAST_THREADS / 32; ++w) {
+            if (w < warp) offset += sh.warp_count[w];
+            round_total += sh.warp_count[w];
+        }
+        if (keep) {
+            const int k = offset + __popc(ballot & ((1u << lane) - 1u));
+            if (k < KNN_PLAN_CAP) out[k] = make_int2((int)t, __float_as_int(dist));
+        }
+        total += round_total;
+    }
+    if (tid == 0) plan_count[blockIdx.x] = total <= KNN_PLAN_CAP ? total : -1;
+}
+
 // part_d32 / part_idx: [split][rank][nq]
 template <int DP, int Q, int STAGES>
 static __global__ void __launch_bounds__(FAST_THREADS)
 knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
                int64_t q_begin, int64_t nq, const int32_t* __restrict__ q_index, int kcap, int windowed,
-               const double* __restrict__ maxabs, int dim, float* __restrict__ part_d32,
+               const double* __restrict__ maxabs, int dim, const float* __restrict__ seed_thr,
+               const int2* __restrict__ plan, const int32_t* __restrict__ plan_count,
+               const int32_t* __restrict__ block_order, float* __restrict__ part_d32,
                int32_t* __restrict__ part_idx, unsigned long long* __restrict__ tile_counter) {
     constexpr int QB = FAST_THREADS * Q;
     constexpr int TILE_FLOATS = FAST_TILE * DP;
@@ -110,7 +214,9 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
     __shared__ TileQueueShared sh;
 
     const int tid = threadIdx.x;
-    const int64_t qb0 = (int64_t)blockIdx.x * QB;  // first query of the block (relative to q_begin)
+    // planned launches run the query blocks longest-tile-list-first
+    const int64_t qblock = block_order ? (int64_t)block_order[blockIdx.x] : (int64_t)blockIdx.x;
+    const int64_t qb0 = qblock * QB;  // first query of the block (relative to q_begin)
     const Band band = make_band(maxabs, dim);
 
     // queries: slot j of thread t is query qb0 + j*THREADS + t
@@ -165,7 +271,11 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
     // Starting from it (+ band, so that those very rows re-enter the list when their tile is
     // scanned) removes the flood of insertions a threshold of +inf causes and gives the tile
     // queue a finite pruning radius from its first round.
-    {
+    if (seed_thr) {
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+            if (live[j]) thr[j] = seed_thr[qb0 + j * FAST_THREADS + tid];  // from the planning pass
+    } else {
         const int64_t n_rows = n_tiles * FAST_TILE;
 #pragma unroll 1
         for (int off = 1; off <= KNN_SEED_W; ++off) {
@@ -278,11 +388,49 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
         refresh();  // seeded thresholds -> finite pruning radius from the first round
     }
 
-    // the block's own tile: the one holding its middle query
-    const int64_t mid = q_index ? 0 : q_begin + min(qb0 + QB / 2, nq - 1);
-    const int tiles_done = run_tile_queue<DP, STAGES>(shadow, tiles, full_bar, sh, mid / FAST_TILE, n_tiles,
-                                                      (int)blockIdx.y, (int)gridDim.y, windowed != 0, test, compute,
-                                                      refresh);
+    int tiles_done = 0;
+    const int planned = (plan && windowed) ? plan_count[qblock] : -1;
+    if (planned >= 0) {
+        // stream the planned tile list; entries whose gap exceeds the current radius are skipped
+        const int2* lst = plan + qblock * KNN_PLAN_CAP;
+        int64_t issue_cnt = 0, consume_cnt = 0;
+        int64_t ring_tile[STAGES];
+        int next = 0;
+        for (;;) {
+            while (issue_cnt - consume_cnt < STAGES && next < planned) {
+                const int2 e = lst[next++];
+                if (__int_as_float(e.y) > R) continue;
+                const int slot = (int)(issue_cnt % STAGES);
+#pragma unroll
+                for (int s = 0; s < STAGES; ++s)
+                    if (s == slot) ring_tile[s] = e.x;
+                if (tid == 0) {
+                    mbar_expect_tx(&full_bar[slot], TILE_FLOATS * 4);
+                    bulk_g2s(tiles + (size_t)slot * TILE_FLOATS, shadow + (int64_t)e.x * TILE_FLOATS, TILE_FLOATS * 4,
+                             &full_bar[slot]);
+                }
+                ++issue_cnt;
+            }
+            if (consume_cnt == issue_cnt) break;
+            const int slot = (int)(consume_cnt % STAGES);
+            int64_t t = 0;
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s)
+                if (s == slot) t = ring_tile[s];
+            mbar_wait(&full_bar[slot], (uint32_t)((consume_cnt / STAGES) & 1));
+            compute(tiles + (size_t)slot * TILE_FLOATS, t);
+            __syncthreads();  // tile consumed: its slot may be refilled
+            ++consume_cnt;
+            ++tiles_done;
+            if ((tiles_done & 3) == 0) refresh();
+        }
+    } else {
+        // the block's own tile: the one holding its middle query
+        const int64_t mid = q_index ? 0 : q_begin + min(qb0 + QB / 2, nq - 1);
+        tiles_done = run_tile_queue<DP, STAGES>(shadow, tiles, full_bar, sh, mid / FAST_TILE, n_tiles,
+                                                (int)blockIdx.y, (int)gridDim.y, windowed != 0, test, compute,
+                                                refresh);
+    }
     if (tid == 0 && tile_counter) atomicAdd(tile_counter, (unsigned long long)tiles_done);
 
     // emit the lists (ascending), one per split
@@ -298,6 +446,16 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
             }
         }
     }
+}
+
+// cost[b] = planned tile count (overflowed lists count as the heaviest); iota[b] = b
+static __global__ void plan_cost_kernel(const int32_t* __restrict__ plan_count, int64_t n_blocks,
+                                        int32_t* __restrict__ cost, int32_t* __restrict__ iota) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const int32_t c = plan_count[b];
+    cost[b] = c < 0 ? 0x7fffffff : c;
+    iota[b] = (int32_t)b;
 }
 
 // Exact refine: see the file header.  flags[qi] = 1 marks a query for the fp64 fallback.

@@ -18,6 +18,11 @@ struct KnnF32Args {
     int kcap, splits, windowed;
     const double* maxabs;
     int dim;
+    // planning pass outputs (windowed engine; all null otherwise)
+    float* seed_thr;
+    void* plan;            // int2[n_query_blocks][KNN_PLAN_CAP]
+    int32_t* plan_count;   // [n_query_blocks]
+    const int32_t* block_order;
     float* part_d32;
     int32_t* part_idx;
     unsigned long long* tile_counter;
@@ -25,6 +30,8 @@ struct KnnF32Args {
 };
 int knn_f32_queries_per_block(int dim_padded);
 int launch_knn_f32(int dim_padded, const KnnF32Args& a);  // KSG_EUNSUPPORTED if dim_padded not in {2,4,6,8}
+int launch_knn_plan(int dim_padded, const KnnF32Args& a);  // fills seed_thr / plan / plan_count
+int knn_plan_cap();
 
 struct CountF32Args {
     const float* shadow;
