@@ -40,8 +40,8 @@ OPS_PER_PAIR = {"c1": (4, 4), "c2": (4, 4)}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000, help="samples (default: the metric's n = 1e6)")
     ap.add_argument("--k", type=int, default=5)
@@ -49,6 +49,8 @@ def parse():
                     help="windowed: fp32 filter + window pruning (default); dense: same kernels over all "
                          "pairs (brute-force roofline case); exact: float64 dense kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense-leg", action="store_true",
+                    help="skip the extra brute-force (dense engine) measurement reported under 'dense_engine'")
     ap.add_argument("--cpu-sample", type=int, default=200_000,
                     help="samples of the C2 generator the in-line CPU baseline runs on")
     return ap.parse_args()
@@ -63,23 +65,80 @@ def workload(n):
 
 # ------------------------------------------------------------------ clocks sampler
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled from
+    a thread every ~2 ms (a step of this path is a few ms, too short for `nvidia-smi -lms`);
+    if NVML cannot be loaded, one `nvidia-smi` query loop is used instead."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.index = index
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.samples = []      # (sm_mhz, reasons bitmask or None, power_w)
+        self.sm_max = None
         self.lines = []
         self.proc = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.source = None
+
+    # ---- NVML
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        if self.uuid:
+            for cand in (f"GPU-{self.uuid}", str(self.uuid)):
+                try:
+                    return pynvml, pynvml.nvmlDeviceGetHandleByUUID(cand)
+                except Exception:
+                    continue
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll_nvml(self, pynvml, h):
+        while not self.stop_flag.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                try:
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((float(sm), int(rs), pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
+            pynvml, h = self._nvml_handle()
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._pynvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, args=(pynvml, h), daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
 
@@ -88,15 +147,29 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.source == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            p = self._pynvml
+            bits = {"hw_slowdown": p.nvmlClocksEventReasonHwSlowdown,
+                    "hw_thermal_slowdown": p.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": p.nvmlClocksEventReasonSwThermalSlowdown,
+                    "sw_power_cap": p.nvmlClocksEventReasonSwPowerCap}
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"], "source": "nvml"}
+            reasons = sorted(name for name, bit in bits.items() if any(rs & bit for _, rs, _ in self.samples))
+            powers = [pw for _, _, pw in self.samples if pw is not None]
+            return {"sm_mhz": statistics.median(sm for sm, _, _ in self.samples), "sm_max_mhz": self.sm_max,
+                    "reasons": reasons, "samples": len(self.samples), "source": "nvml",
+                    "power_w_max": max(powers) if powers else None}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
@@ -105,13 +178,13 @@ class ClockSampler:
                 sm.append(float(parts[0])); mx.append(float(parts[1]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[3:7]):
+            for name, val in zip(self.NAMES, parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": "nvidia-smi"}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------ CPU arms
@@ -230,7 +303,11 @@ def run_b200_arm(args):
     e2e_step()
     barrier()
 
-    sampler = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
         sampler.start()
     E.timer.enabled = True
@@ -239,6 +316,7 @@ def run_b200_arm(args):
     kernel_ms = E.timer.totals_ms()
     E.timer.enabled = False
     clocks = sampler.stop() if rank == 0 else None
+    pairs_done = last["prep"].pairs_evaluated() if last.get("prep") is not None else (0, 0)
 
     # end to end through the public API, host buffers in / host arrays out
     def e2e_wall(steps):
@@ -255,6 +333,22 @@ def run_b200_arm(args):
         return float(t.item()), res
 
     e2e_s, (ptw_host, avg_host) = e2e_wall(args.steps)
+
+    # brute-force leg: the same filter kernels over ALL n x n pairs (engine "dense"), the case
+    # the FP-pipe roofline of BASELINE.json is defined on; reported beside the headline
+    dense_leg = None
+    if args.engine == "windowed" and not args.no_dense_leg:
+        E.config.engine = "dense"
+        device_step()
+        E.timer.enabled = True
+        E.timer.reset()
+        d_steps = 3
+        d_ms, _, _ = timed(device_step, d_steps)
+        d_kernel_ms = E.timer.totals_ms()
+        E.timer.enabled = False
+        d_tiles = last["prep"].pairs_evaluated()[0]
+        E.config.engine = args.engine
+        dense_leg = (d_ms, d_steps, statistics.mean(d_kernel_ms["fast_knn"]), d_tiles)
 
     if rank == 0:
         value = n * args.steps / (ms_total * 1e-3)
@@ -273,10 +367,7 @@ def run_b200_arm(args):
             pairs_knn = pairs_cnt = float(n) * float(nq)
         else:
             knn_name, cnt_name = "fast_knn", "fast_count"
-            tiles_knn, tiles_cnt = last["prep"].tiles_visited()
-            qb = 512 if rows.shape[0] <= 4 else 256          # queries per CTA of the filter kernels
-            pairs_knn = float(tiles_knn) * 512.0 * qb         # executed (query, candidate) pairs, this rank
-            pairs_cnt = float(tiles_cnt) * 512.0 * qb
+            pairs_knn, pairs_cnt = (float(v) for v in pairs_done)  # evaluated (query, candidate) pairs, this rank
         knn_ms = mean_ms.get(knn_name, float("nan"))
         cnt_ms = mean_ms.get(cnt_name, 0.0)
         psi_ms = mean_ms.get("psi_epilogue", float("nan"))
@@ -292,6 +383,13 @@ def run_b200_arm(args):
             except Exception:
                 pass
         psi_bytes = nq * (4 * len(masks) + 8)
+        # dram bytes (read + write) per launch of the dominant kernel, from the committed
+        # `ncu --set full` capture of this same command (profiles/traffic.json says which file)
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -304,7 +402,8 @@ def run_b200_arm(args):
                     "d2h_bytes_per_step": int(8 * n + 16), "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp_pipe", "kernel": dominant, "achieved": ach / 1e12, "peak": peak / 1e12,
-                         "unit": "Tlane-op/s", "frac": ach / peak, "traffic": None,
+                         "unit": "Tlane-op/s", "frac": ach / peak,
+                         "traffic": traffic.get(f"{dominant}_{args.engine}_c2") if world == 1 else None,
                          "peak_basis": f"{sms} SMs x 128 lanes x {sm_max_mhz:.0f} MHz (max clock)",
                          "frac_at_load_clock": (ach / (sms * 128 * sm_load * 1e6)) if sm_load else None,
                          "ops_per_pair": {knn_name: a1, cnt_name: a2},
@@ -314,10 +413,21 @@ def run_b200_arm(args):
                          "frac_" + knn_name: ach_knn / peak, "frac_" + cnt_name: ach_cnt / peak},
             "roofline_hbm": {"bound": "hbm", "kernel": "psi_epilogue", "achieved": psi_bytes / (psi_ms * 1e-3) / 1e9,
                              "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
-                             "frac": psi_bytes / (psi_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+                             "frac": psi_bytes / (psi_ms * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": traffic.get("psi_epilogue_c2")},
             "fallback_queries": dict(E.stats),
             "mi_nats": float(avg_host),
         }
+        if dense_leg is not None:
+            d_ms, d_steps, d_knn_ms, d_tiles = dense_leg
+            d_pairs = float(d_tiles)
+            d_ach = a1 * d_pairs / (d_knn_ms * 1e-3)
+            line["dense_engine"] = {
+                "what": "same step with engine='dense': the fp32 filter scans every candidate tile (brute force)",
+                "value": n * d_steps / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms / d_steps, "steps": d_steps,
+                "roofline": {"bound": "fp_pipe", "kernel": "fast_knn", "achieved": d_ach / 1e12, "peak": peak / 1e12,
+                             "unit": "Tlane-op/s", "frac": d_ach / peak, "pairs_per_launch": d_pairs,
+                             "kernel_ms": d_knn_ms, "traffic": traffic.get("fast_knn_dense_c2")}}
         if not args.no_cpu_baseline and world == 1:
             from oracle import ref_port
 

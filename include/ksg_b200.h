@@ -228,10 +228,11 @@ typedef struct {
     double* center;      /* [dim]      per-coordinate centre of the fp32 copy */
     double* maxabs;      /* [dim]      max |x - centre| (bounds the fp32 rounding error) */
     float* tile_box;     /* [n_padded/512][dim_padded][2] min / max of shadow_f32 over each 512-row tile */
+    float* sub_box;      /* [n_padded/512][16][dim_padded][2] the same over each 32-row sub-tile */
     int32_t* flags;      /* 64 bytes: int32 [0] = 1 if the input held a NaN or an infinity;
-                            uint64 at byte 16 / 24 = candidate tiles visited so far by the
-                            k-NN / count filter kernels (x 512 candidates x queries per CTA =
-                            executed pairs; for the roofline of the windowed engine) */
+                            uint64 at byte 16 / 24 = (query, candidate) pairs evaluated so far by
+                            the k-NN / count filter kernels (for the roofline of the windowed
+                            engine, which skips most of the n x n pairs) */
 } ksg_prepared;
 
 /*

@@ -42,6 +42,7 @@ class Prepared(C.Structure):
         ("center", C.c_void_p),
         ("maxabs", C.c_void_p),
         ("tile_box", C.c_void_p),
+        ("sub_box", C.c_void_p),
         ("flags", C.c_void_p),
     ]
 

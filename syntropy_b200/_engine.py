@@ -256,8 +256,9 @@ class PreparedSet:
     def flags(self) -> torch.Tensor:
         return self._view(self.c.flags, 4, torch.int32)
 
-    def tiles_visited(self):
-        """(k-NN filter tiles, count filter tiles) visited so far (uint64 counters)."""
+    def pairs_evaluated(self):
+        """(query, candidate) pairs evaluated so far by the (k-NN filter, count filter) kernels
+        on this prepared set (uint64 device counters)."""
         t = self._view(self.c.flags, 64, torch.int64).cpu()
         return int(t[2]), int(t[3])
 

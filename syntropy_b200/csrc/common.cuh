@@ -41,10 +41,10 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // sharded case), without making a split shorter than a handful of tiles.
 static inline int choose_splits(int64_t n_query_blocks, int64_t n_candidates, int tile) {
     int64_t want = ceil_div(4 * (int64_t)sm_count(), n_query_blocks > 0 ? n_query_blocks : 1);
-    int64_t max_by_len = n_candidates / (4 * (int64_t)tile);
+    int64_t max_by_len = n_candidates / (2 * (int64_t)tile);
     if (max_by_len < 1) max_by_len = 1;
     if (want > max_by_len) want = max_by_len;
-    if (want > 64) want = 64;
+    if (want > 128) want = 128;
     if (want < 1) want = 1;
     return (int)want;
 }

@@ -39,6 +39,7 @@ static inline PreparedLayout prepared_layout(int64_t n, int dim) {
     L.off_maxabs = take((size_t)KSG_MAX_DIM * 8);
     L.off_flags = take(64);
     L.off_tile_box = take((size_t)(L.n_padded / FAST_TILE) * L.dim_padded * 2 * 4);
+    L.off_sub_box = take((size_t)(L.n_padded / FAST_TILE) * FAST_NSUB * L.dim_padded * 2 * 4);
     L.off_stats = take((size_t)dim * STATS_BLOCKS * 2 * 8);
     L.off_iota = take((size_t)L.ld * 4);
     L.off_keys_tmp = take((size_t)L.ld * 8);
@@ -76,39 +77,42 @@ static int sort_pairs(void* cub_tmp, size_t cub_bytes, const double* keys_in, do
 
 struct FastKnnPlan {
     int kcap, splits, qb;
-    int64_t qblocks;
+    int64_t qblocks, max_units, plan_capacity;
     size_t d32_bytes, idx_bytes;
-    // planning pass (windowed engine)
-    size_t seed_bytes, plan_bytes, count_bytes, order_bytes, sort_bytes;
+    // windowed engine: planning pass + unit table
+    size_t seed_bytes, plan_bytes, count_bytes, first_bytes, ublock_bytes, meta_bytes;
     size_t total() const {
-        return d32_bytes + idx_bytes + seed_bytes + plan_bytes + 4 * count_bytes + order_bytes + sort_bytes;
+        return d32_bytes + idx_bytes + seed_bytes + plan_bytes + count_bytes + first_bytes + ublock_bytes + meta_bytes;
     }
 };
-static size_t cub_sort_i32_bytes(int64_t n) {
-    size_t bytes = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
-                                                              (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
-    if (e != cudaSuccess || bytes == 0) {
-        (void)cudaGetLastError();
-        bytes = (size_t)n * 16 + (1u << 20);
-    }
-    return bytes;
-}
 static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int windowed) {
     FastKnnPlan p;
+    memset(&p, 0, sizeof(p));
     const int dp = (dim + 1) & ~1;
     p.kcap = kprime + KNN_MARGIN;
     p.qb = knn_f32_queries_per_block(dp);
-    const int64_t qblocks = ceil_div(nq, p.qb);
-    p.qblocks = qblocks;
-    p.splits = windowed ? 1 : choose_splits(qblocks, n, FAST_TILE);
-    p.d32_bytes = align_up((size_t)p.splits * p.kcap * nq * sizeof(float), 256);
-    p.idx_bytes = align_up((size_t)p.splits * p.kcap * nq * sizeof(int32_t), 256);
-    p.seed_bytes = align_up((size_t)nq * sizeof(float), 256);
-    p.plan_bytes = align_up((size_t)qblocks * knn_plan_cap() * 8, 256);
-    p.count_bytes = align_up((size_t)qblocks * sizeof(int32_t), 256);
-    p.order_bytes = align_up((size_t)qblocks * sizeof(int32_t), 256);
-    p.sort_bytes = align_up(cub_sort_i32_bytes(qblocks), 256);
+    p.qblocks = ceil_div(nq, p.qb);
+    if (windowed) {
+        // partial lists per work unit: [unit][rank][qb]
+        p.splits = 1;
+        p.max_units = (1 + (int64_t)knn_unit_factor()) * p.qblocks;
+        p.d32_bytes = align_up((size_t)p.max_units * p.kcap * p.qb * sizeof(float), 256);
+        p.idx_bytes = align_up((size_t)p.max_units * p.kcap * p.qb * sizeof(int32_t), 256);
+        p.seed_bytes = align_up((size_t)nq * sizeof(float), 256);
+        const int64_t n_tiles = ceil_div(n, FAST_TILE);
+        p.plan_capacity = p.qblocks * (n_tiles < knn_plan_cap() ? n_tiles : (int64_t)knn_plan_cap());
+        if (p.plan_capacity > 0x7fff0000ll) p.plan_capacity = 0x7fff0000ll;  // int32 list offsets
+        p.plan_bytes = align_up((size_t)p.plan_capacity * 8, 256);
+        p.count_bytes = 2 * align_up((size_t)p.qblocks * sizeof(int32_t), 256);  // list lengths + starts
+        p.first_bytes = align_up((size_t)(p.qblocks + 1) * sizeof(int32_t), 256);
+        p.ublock_bytes = align_up((size_t)p.max_units * sizeof(int32_t), 256);
+        p.meta_bytes = 256;
+    } else {
+        // partial lists per candidate split: [split][rank][nq]
+        p.splits = choose_splits(p.qblocks, n, FAST_TILE);
+        p.d32_bytes = align_up((size_t)p.splits * p.kcap * nq * sizeof(float), 256);
+        p.idx_bytes = align_up((size_t)p.splits * p.kcap * nq * sizeof(int32_t), 256);
+    }
     return p;
 }
 
@@ -204,7 +208,9 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
         KSG_LAUNCHED2();
     }
     P.tile_box = (float*)(base + L.off_tile_box);
-    tile_box_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 128, 0, st>>>(P.shadow_f32, L.dim_padded, P.tile_box);
+    P.sub_box = (float*)(base + L.off_sub_box);
+    tile_box_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 128, 0, st>>>(P.shadow_f32, L.dim_padded, P.tile_box,
+                                                                         P.sub_box);
     KSG_LAUNCHED2();
     *h_out = P;
     return KSG_OK;
@@ -212,9 +218,10 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
 
 size_t ksg_fast_knn_workspace(int64_t n, int64_t nq, int dim, int kprime) {
     if (n <= 0 || nq <= 0 || dim < 1 || kprime < 1) return 0;
-    // sized for the dense (split) launch; the windowed launch needs less
-    FastKnnPlan p = fast_knn_plan(n, nq, dim, kprime, 0);
-    return p.total() + 256;
+    // either engine may be asked for with this workspace
+    const size_t dense = fast_knn_plan(n, nq, dim, kprime, 0).total();
+    const size_t windowed = fast_knn_plan(n, nq, dim, kprime, 1).total();
+    return (dense > windowed ? dense : windowed) + 256;
 }
 
 int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const int32_t* d_query_index, int kprime,
@@ -238,7 +245,7 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const in
     }
     cudaStream_t st = as_stream2(stream);
     KnnF32Args a;
-    a.shadow = P->shadow_f32; a.tile_box = P->tile_box; a.n_tiles = P->n_padded / FAST_TILE;
+    a.shadow = P->shadow_f32; a.tile_box = P->tile_box; a.sub_box = P->sub_box; a.n_tiles = P->n_padded / FAST_TILE;
     a.q_begin = q_begin; a.nq = nq; a.q_index = d_query_index; a.kcap = p.kcap; a.splits = p.splits;
     a.windowed = windowed ? 1 : 0;
     a.maxabs = P->maxabs; a.dim = P->dim;
@@ -246,36 +253,32 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const in
     a.part_idx = (int32_t*)((char*)d_workspace + p.d32_bytes);
     a.tile_counter = (unsigned long long*)((char*)P->flags + 16);
     a.st = st;
-    a.seed_thr = nullptr; a.plan = nullptr; a.plan_count = nullptr; a.block_order = nullptr;
+    a.seed_thr = nullptr; a.plan = nullptr; a.plan_count = nullptr; a.plan_first = nullptr; a.plan_capacity = 0;
+    a.unit_first = nullptr; a.unit_block = nullptr; a.unit_meta = nullptr; a.max_units = 0;
     int rc;
     if (a.windowed) {
-        // planning pass: seeds, per-block tile lists, then blocks ordered longest list first
+        // planning pass (seeds, deferrals, per-block tile lists) -> unit table -> persistent filter
         char* w = (char*)d_workspace + p.d32_bytes + p.idx_bytes;
         a.seed_thr = (float*)w;                      w += p.seed_bytes;
         a.plan = w;                                  w += p.plan_bytes;
-        a.plan_count = (int32_t*)w;                  w += p.count_bytes;
-        int32_t* cost = (int32_t*)w;                 w += p.count_bytes;
-        int32_t* cost_sorted = (int32_t*)w;          w += p.count_bytes;
-        int32_t* iota = (int32_t*)w;                 w += p.count_bytes;
-        int32_t* order = (int32_t*)w;                w += p.order_bytes;
-        void* sort_tmp = w;
+        a.plan_capacity = p.plan_capacity;
+        a.plan_count = (int32_t*)w;                  w += p.count_bytes / 2;
+        a.plan_first = (int32_t*)w;                  w += p.count_bytes / 2;
+        a.unit_first = (int32_t*)w;                  w += p.first_bytes;
+        a.unit_block = (int32_t*)w;                  w += p.ublock_bytes;
+        a.unit_meta = (int32_t*)w;
+        a.max_units = p.max_units;
         rc = launch_knn_plan(P->dim_padded, a);
         if (rc) return rc;
-        plan_cost_kernel<<<(unsigned)ceil_div(p.qblocks, 256), 256, 0, st>>>(a.plan_count, p.qblocks, cost, iota);
-        KSG_LAUNCHED2();
-        size_t need = p.sort_bytes;
-        cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(sort_tmp, need, cost, cost_sorted, iota, order,
-                                                                  (int)p.qblocks, 0, 32, st);
-        if (e != cudaSuccess) { set_error("cub SortPairsDescending: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
-        note_launch();
-        a.block_order = order;
+        rc = launch_knn_units(P->dim_padded, a);
+    } else {
+        rc = launch_knn_f32(P->dim_padded, a);
     }
-    rc = launch_knn_f32(P->dim_padded, a);
     if (rc) return rc;
     knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, p.splits, kprime,
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
-                                                                   d_query_index, P->maxabs, d_eps_out, d_flags,
-                                                                   d_n_flagged);
+                                                                   d_query_index, P->maxabs, a.seed_thr, a.unit_first,
+                                                                   p.qb, d_eps_out, d_flags, d_n_flagged);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

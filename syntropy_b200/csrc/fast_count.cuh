@@ -250,7 +250,7 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
     const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
     const int tiles_done = run_tile_queue<DP, STAGES>(shadow, tiles, full_bar, sh, mid / FAST_TILE, n_tiles,
                                                       (int)blockIdx.y, splits, windowed != 0, test, compute, refresh);
-    if (tid == 0 && tile_counter) atomicAdd(tile_counter, (unsigned long long)tiles_done);
+    if (tid == 0 && tile_counter) atomicAdd(tile_counter, (unsigned long long)tiles_done * (FAST_TILE * QB));
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
         const int64_t qi = qb0 + j * FAST_THREADS + tid;

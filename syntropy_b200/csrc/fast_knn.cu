@@ -16,9 +16,8 @@ static int launch_knn_dp(const KnnF32Args& a) {
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     }
     dim3 grid((unsigned)ceil_div(a.nq, FAST_THREADS * Q), (unsigned)a.splits, 1);
-    kern<<<grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.q_index, a.kcap, a.windowed,
-                                              a.maxabs, a.dim, a.seed_thr, (const int2*)a.plan, a.plan_count, a.block_order,
-                                              a.part_d32, a.part_idx, a.tile_counter);
+    kern<<<grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.q_index, a.kcap,
+                                              a.maxabs, a.dim, a.part_d32, a.part_idx, a.tile_counter);
     note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_f32_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
@@ -34,16 +33,58 @@ static int launch_plan_dp(const KnnF32Args& a) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     }
+    if (cudaMemsetAsync(a.unit_meta, 0, 16, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
     kern<<<(unsigned)ceil_div(a.nq, FAST_THREADS * Q), FAST_THREADS, smem, a.st>>>(
         a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.maxabs, a.dim, a.seed_thr, (int2*)a.plan,
-        a.plan_count);
+        a.plan_capacity, a.plan_count, a.plan_first, a.unit_meta);
     note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_plan_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    knn_unit_table_kernel<<<1, 1024, 0, a.st>>>(a.plan_count, ceil_div(a.nq, FAST_THREADS * Q), a.max_units,
+                                                 a.unit_first, a.unit_block, a.unit_meta);
+    note_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("knn_unit_table_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    return KSG_OK;
+}
+
+template <int DP>
+static int launch_units_dp(const KnnF32Args& a) {
+    constexpr int Q = FastGeom<DP>::Q, ST = FastGeom<DP>::STAGES;
+    auto kern = knn_units_kernel<DP, Q, ST>;
+    const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float) +
+                        (size_t)a.kcap * FAST_THREADS * Q * 8;
+    if (smem > 32 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    }
+    // persistent: as many CTAs as fit on the machine (never more than there can be units)
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FAST_THREADS, smem);
+    if (e != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
+    int64_t grid = (int64_t)per_sm * sm_count();
+    if (grid > a.max_units) grid = a.max_units;
+    kern<<<(unsigned)grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.sub_box, a.q_begin, a.nq, a.kcap, a.maxabs, a.dim, a.seed_thr,
+                                                       (const int2*)a.plan, a.plan_count, a.plan_first, a.unit_first, a.unit_block,
+                                                       a.unit_meta, a.part_d32, a.part_idx, a.tile_counter);
+    note_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("knn_units_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     return KSG_OK;
 }
 
 int knn_plan_cap() { return KNN_PLAN_CAP; }
+int knn_unit_factor() { return KNN_UNIT_FACTOR; }
+
+int launch_knn_units(int dim_padded, const KnnF32Args& a) {
+    switch (dim_padded) {
+        case 2: return launch_units_dp<2>(a);
+        case 4: return launch_units_dp<4>(a);
+        case 6: return launch_units_dp<6>(a);
+        case 8: return launch_units_dp<8>(a);
+        default: return KSG_EUNSUPPORTED;
+    }
+}
 
 int launch_knn_plan(int dim_padded, const KnnF32Args& a) {
     switch (dim_padded) {

@@ -33,7 +33,9 @@ constexpr int KNN_MARGIN = 3;   // list entries kept beyond k'
 constexpr int KNN_SEED_W = 24;  // rows on each side of a query used to seed its threshold
 constexpr float KNN_DEFER_CUT = 4.0f;   // defer a query whose seeded radius exceeds CUT x the CTA mean
 constexpr float KNN_DEFERRED = -2.0f;   // sentinel distance marking a deferred query's list
-constexpr int KNN_PLAN_CAP = 1024;      // tile-list entries per query block (more: in-kernel walk)
+constexpr int KNN_PLAN_CAP = 1024;      // tile-list pool: this many entries per query block ON AVERAGE
+constexpr int KNN_UNIT_MIN_TILES = 16;  // a work unit = one query block x at most `chunk` planned tiles
+constexpr int KNN_UNIT_FACTOR = 2;      // chunk grows so that #units <= (1 + FACTOR) * #blocks
 
 // ---- fp32 error band of the shadow copy (see DESIGN.md "Exactness")
 // |d32 - d64| <= 2^-24 * (2*M + |d|) * (1 + tiny) per dimension; kept as a pair of
@@ -94,6 +96,19 @@ __device__ __forceinline__ void load_row(const float* __restrict__ row, float2 (
     }
 }
 
+// two consecutive rows (for DP = 2 they share one 16-byte load)
+template <int DP>
+__device__ __forceinline__ void load_two_rows(const float* __restrict__ row, float2 (&a)[DP / 2], float2 (&b)[DP / 2]) {
+    if constexpr (DP == 2) {
+        const float4 v = *reinterpret_cast<const float4*>(row);
+        a[0] = make_float2(v.x, v.y);
+        b[0] = make_float2(v.z, v.w);
+    } else {
+        load_row<DP>(row, a);
+        load_row<DP>(row + DP, b);
+    }
+}
+
 // ---- planning pass of the windowed engine.  One CTA per query block: seeds every query's
 // threshold from its neighbours in the prepared order, derives the block's pruning radius, tests
 // EVERY candidate tile's bounding box against the block's query box and writes the survivors
@@ -104,20 +119,23 @@ template <int DP, int Q>
 static __global__ void __launch_bounds__(FAST_THREADS)
 knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
                 int64_t q_begin, int64_t nq, int kcap, const double* __restrict__ maxabs, int dim,
-                float* __restrict__ seed_thr, int2* __restrict__ plan, int32_t* __restrict__ plan_count) {
+                float* __restrict__ seed_thr, int2* __restrict__ plan, int64_t plan_capacity,
+                int32_t* __restrict__ plan_count, int32_t* __restrict__ plan_first, int32_t* __restrict__ meta) {
     constexpr int QB = FAST_THREADS * Q;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* lst_d = reinterpret_cast<float*>(smem_raw);  // kcap * QB (values only)
     __shared__ TileQueueShared sh;
+    __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t qb0 = (int64_t)blockIdx.x * QB;
     const Band band = make_band(maxabs, dim);
     const int64_t n_rows = n_tiles * FAST_TILE;
 
+    // ---- pass 1: seed every query's threshold from its neighbours in the prepared order
     float blo[DP], bhi[DP];
 #pragma unroll
     for (int d = 0; d < DP; ++d) { blo[d] = CUDART_INF_F; bhi[d] = -CUDART_INF_F; }
-    float rmax = -CUDART_INF_F;
+    float sum = 0.0f, cnt = 0.0f;
 #pragma unroll 1
     for (int j = 0; j < Q; ++j) {
         const int64_t qi = qb0 + j * FAST_THREADS + tid;
@@ -154,55 +172,116 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
             }
         thr = thr + (band.c0 + band.c1 * thr);  // inf stays inf
         seed_thr[qi] = thr;
+        if (thr < CUDART_INF_F) { sum += thr; cnt += 1.0f; }
+    }
+    block_query_box<DP>(blo, bhi, sh);
+
+    // ---- outlier deferral: one isolated query next to a dense region would blow the block's
+    // pruning radius up to its own huge neighbour distance and make all 128*Q queries walk most
+    // of the point set.  Queries whose seeded radius is far above the block's mean AND above the
+    // block's own extent are taken out (seed = KNN_DEFERRED) and recomputed by a dense launch
+    // over the compacted list of such queries.
+    sum = block_sum(sum, sh);
+    cnt = block_sum(cnt, sh);
+    float extent = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) extent = fmaxf(extent, sh.qhi[d] - sh.qlo[d]);
+    const float cut = fmaxf(KNN_DEFER_CUT * (sum / fmaxf(cnt, 1.0f)), 2.0f * extent);
+    __syncthreads();  // everyone has read the full box before it is replaced
+
+    // ---- pass 2: box and radius of the queries that stay
+#pragma unroll
+    for (int d = 0; d < DP; ++d) { blo[d] = CUDART_INF_F; bhi[d] = -CUDART_INF_F; }
+    float rmax = -CUDART_INF_F;
+#pragma unroll 1
+    for (int j = 0; j < Q; ++j) {
+        const int64_t qi = qb0 + j * FAST_THREADS + tid;
+        if (qi >= nq) continue;
+        const float thr = seed_thr[qi];
+        if (thr < CUDART_INF_F && thr > cut) { seed_thr[qi] = KNN_DEFERRED; continue; }
+        float2 q[DP / 2];
+        load_row<DP>(shadow + (q_begin + qi) * DP, q);
+#pragma unroll
+        for (int h = 0; h < DP / 2; ++h) {
+            blo[2 * h] = fminf(blo[2 * h], q[h].x);         bhi[2 * h] = fmaxf(bhi[2 * h], q[h].x);
+            blo[2 * h + 1] = fminf(blo[2 * h + 1], q[h].y); bhi[2 * h + 1] = fmaxf(bhi[2 * h + 1], q[h].y);
+        }
         rmax = fmaxf(rmax, thr);
     }
     block_query_box<DP>(blo, bhi, sh);
     const float R = block_max(rmax, sh);
 
+    // ---- every tile whose box is within R of the query box, in walk order (near first).
+    // The lists live in one pool (meta[3] = bump cursor): a first sweep counts the survivors,
+    // the block reserves that many entries, a second sweep writes them.
     const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
     const int64_t own = mid / FAST_TILE;
-    int2* out = plan + (int64_t)blockIdx.x * KNN_PLAN_CAP;
-    int total = 0;
+    auto gap_of = [&](int64_t pos, int64_t& t) -> float {
+        t = walk_tile(pos, own, n_tiles);
+        float gap[DP];
+        box_gaps<DP>(tile_box, t, sh, gap);
+        float dist = gap[0];
+#pragma unroll
+        for (int d = 1; d < DP; ++d) dist = fmaxf(dist, gap[d]);
+        return dist;
+    };
+    int mine = 0;
+    for (int64_t pos = tid; pos < n_tiles; pos += FAST_THREADS) {
+        int64_t t;
+        mine += !(gap_of(pos, t) > R);
+    }
+    const int total = (int)(block_sum((float)mine, sh) + 0.5f);  // exact: < 2^24 tiles
+    if (tid == 0) {
+        int base = -1;
+        if (total > 0) {
+            base = atomicAdd(&meta[3], total);
+            if ((int64_t)base + total > plan_capacity) base = -1;  // pool exhausted
+        }
+        s_base = base;
+    }
+    __syncthreads();
+    const int base = s_base;
+    if (total > 0 && base < 0) {
+        // no room for this block's list: hand all of its queries to the dense launch
+        for (int j = 0; j < Q; ++j) {
+            const int64_t qi = qb0 + j * FAST_THREADS + tid;
+            if (qi < nq) seed_thr[qi] = KNN_DEFERRED;
+        }
+        if (tid == 0) { plan_count[blockIdx.x] = 0; plan_first[blockIdx.x] = 0; }
+        return;
+    }
+    int2* out = plan + base;
+    int done = 0;
     for (int64_t pos = 0; pos < n_tiles; pos += FAST_THREADS) {
         bool keep = false;
         int64_t t = 0;
         float dist = 0.0f;
         if (pos + tid < n_tiles) {
-            t = walk_tile(pos + tid, own, n_tiles);
-            float gap[DP];
-            box_gaps<DP>(tile_box, t, sh, gap);
-            dist = gap[0];
-#pragma unroll
-            for (int d = 1; d < DP; ++d) dist = fmaxf(dist, gap[d]);
+            dist = gap_of(pos + tid, t);
             keep = !(dist > R);
         }
         const unsigned ballot = __ballot_sync(0xffffffffu, keep);
         __syncthreads();
         if (lane == 0) sh.warp_count[warp] = __popc(ballot);
         __syncthreads();
-        int offset = total, round_total = 0;
+        int offset = done, round_total = 0;
 #pragma unroll
         for (int w = 0; w < FAST_THREADS / 32; ++w) {
             if (w < warp) offset += sh.warp_count[w];
             round_total += sh.warp_count[w];
         }
-        if (keep) {
-            const int k = offset + __popc(ballot & ((1u << lane) - 1u));
-            if (k < KNN_PLAN_CAP) out[k] = make_int2((int)t, __float_as_int(dist));
-        }
-        total += round_total;
+        if (keep) out[offset + __popc(ballot & ((1u << lane) - 1u))] = make_int2((int)t, __float_as_int(dist));
+        done += round_total;
     }
-    if (tid == 0) plan_count[blockIdx.x] = total <= KNN_PLAN_CAP ? total : -1;
+    if (tid == 0) { plan_count[blockIdx.x] = total; plan_first[blockIdx.x] = total > 0 ? base : 0; }
 }
 
 // part_d32 / part_idx: [split][rank][nq]
 template <int DP, int Q, int STAGES>
 static __global__ void __launch_bounds__(FAST_THREADS)
 knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
-               int64_t q_begin, int64_t nq, const int32_t* __restrict__ q_index, int kcap, int windowed,
-               const double* __restrict__ maxabs, int dim, const float* __restrict__ seed_thr,
-               const int2* __restrict__ plan, const int32_t* __restrict__ plan_count,
-               const int32_t* __restrict__ block_order, float* __restrict__ part_d32,
+               int64_t q_begin, int64_t nq, const int32_t* __restrict__ q_index, int kcap,
+               const double* __restrict__ maxabs, int dim, float* __restrict__ part_d32,
                int32_t* __restrict__ part_idx, unsigned long long* __restrict__ tile_counter) {
     constexpr int QB = FAST_THREADS * Q;
     constexpr int TILE_FLOATS = FAST_TILE * DP;
@@ -214,9 +293,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
     __shared__ TileQueueShared sh;
 
     const int tid = threadIdx.x;
-    // planned launches run the query blocks longest-tile-list-first
-    const int64_t qblock = block_order ? (int64_t)block_order[blockIdx.x] : (int64_t)blockIdx.x;
-    const int64_t qb0 = qblock * QB;  // first query of the block (relative to q_begin)
+    const int64_t qb0 = (int64_t)blockIdx.x * QB;  // first query of the block (relative to q_begin)
     const Band band = make_band(maxabs, dim);
 
     // queries: slot j of thread t is query qb0 + j*THREADS + t
@@ -271,11 +348,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
     // Starting from it (+ band, so that those very rows re-enter the list when their tile is
     // scanned) removes the flood of insertions a threshold of +inf causes and gives the tile
     // queue a finite pruning radius from its first round.
-    if (seed_thr) {
-#pragma unroll
-        for (int j = 0; j < Q; ++j)
-            if (live[j]) thr[j] = seed_thr[qb0 + j * FAST_THREADS + tid];  // from the planning pass
-    } else {
+    {
         const int64_t n_rows = n_tiles * FAST_TILE;
 #pragma unroll 1
         for (int off = 1; off <= KNN_SEED_W; ++off) {
@@ -359,79 +432,11 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
         }
     };
 
-    // ---- outlier deferral (windowed engine): one isolated query next to a dense region would
-    // blow the CTA's pruning radius up to its own huge neighbour distance and make all 128*Q
-    // queries walk most of the point set.  Queries whose seeded radius is far above the CTA's
-    // mean AND above the CTA's own extent are taken out here (sentinel in the output list) and
-    // recomputed by a dense launch over the compacted list of such queries.
-    bool deferred[Q];
-#pragma unroll
-    for (int j = 0; j < Q; ++j) deferred[j] = false;
-    if (windowed) {
-        float sum = 0.0f, cnt = 0.0f;
-#pragma unroll
-        for (int j = 0; j < Q; ++j)
-            if (live[j] && thr[j] < CUDART_INF_F) { sum += thr[j]; cnt += 1.0f; }
-        sum = block_sum(sum, sh);
-        cnt = block_sum(cnt, sh);
-        float extent = 0.0f;
-#pragma unroll
-        for (int d = 0; d < DP; ++d) extent = fmaxf(extent, sh.qhi[d] - sh.qlo[d]);
-        const float cut = fmaxf(KNN_DEFER_CUT * (sum / fmaxf(cnt, 1.0f)), 2.0f * extent);
-#pragma unroll
-        for (int j = 0; j < Q; ++j)
-            if (live[j] && thr[j] < CUDART_INF_F && thr[j] > cut) {
-                deferred[j] = true;
-                live[j] = false;   // no longer part of the pruning radius
-                thr[j] = -1.0f;    // never inserts
-            }
-        refresh();  // seeded thresholds -> finite pruning radius from the first round
-    }
-
-    int tiles_done = 0;
-    const int planned = (plan && windowed) ? plan_count[qblock] : -1;
-    if (planned >= 0) {
-        // stream the planned tile list; entries whose gap exceeds the current radius are skipped
-        const int2* lst = plan + qblock * KNN_PLAN_CAP;
-        int64_t issue_cnt = 0, consume_cnt = 0;
-        int64_t ring_tile[STAGES];
-        int next = 0;
-        for (;;) {
-            while (issue_cnt - consume_cnt < STAGES && next < planned) {
-                const int2 e = lst[next++];
-                if (__int_as_float(e.y) > R) continue;
-                const int slot = (int)(issue_cnt % STAGES);
-#pragma unroll
-                for (int s = 0; s < STAGES; ++s)
-                    if (s == slot) ring_tile[s] = e.x;
-                if (tid == 0) {
-                    mbar_expect_tx(&full_bar[slot], TILE_FLOATS * 4);
-                    bulk_g2s(tiles + (size_t)slot * TILE_FLOATS, shadow + (int64_t)e.x * TILE_FLOATS, TILE_FLOATS * 4,
-                             &full_bar[slot]);
-                }
-                ++issue_cnt;
-            }
-            if (consume_cnt == issue_cnt) break;
-            const int slot = (int)(consume_cnt % STAGES);
-            int64_t t = 0;
-#pragma unroll
-            for (int s = 0; s < STAGES; ++s)
-                if (s == slot) t = ring_tile[s];
-            mbar_wait(&full_bar[slot], (uint32_t)((consume_cnt / STAGES) & 1));
-            compute(tiles + (size_t)slot * TILE_FLOATS, t);
-            __syncthreads();  // tile consumed: its slot may be refilled
-            ++consume_cnt;
-            ++tiles_done;
-            if ((tiles_done & 3) == 0) refresh();
-        }
-    } else {
-        // the block's own tile: the one holding its middle query
-        const int64_t mid = q_index ? 0 : q_begin + min(qb0 + QB / 2, nq - 1);
-        tiles_done = run_tile_queue<DP, STAGES>(shadow, tiles, full_bar, sh, mid / FAST_TILE, n_tiles,
-                                                (int)blockIdx.y, (int)gridDim.y, windowed != 0, test, compute,
-                                                refresh);
-    }
-    if (tid == 0 && tile_counter) atomicAdd(tile_counter, (unsigned long long)tiles_done);
+    // the block's own tile: the one holding its middle query
+    const int64_t mid = q_index ? 0 : q_begin + min(qb0 + QB / 2, nq - 1);
+    const int tiles_done = run_tile_queue<DP, STAGES>(shadow, tiles, full_bar, sh, mid / FAST_TILE, n_tiles,
+                                                      (int)blockIdx.y, (int)gridDim.y, false, test, compute, refresh);
+    if (tid == 0 && tile_counter) atomicAdd(tile_counter, (unsigned long long)tiles_done * (FAST_TILE * QB));
 
     // emit the lists (ascending), one per split
 #pragma unroll
@@ -441,21 +446,290 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
             const int col = j * FAST_THREADS + tid;
             for (int r = 0; r < kcap; ++r) {
                 const int64_t o = ((int64_t)blockIdx.y * kcap + r) * nq + qi;
-                part_d32[o] = deferred[j] ? KNN_DEFERRED : lst_d[(size_t)r * QB + col];
+                part_d32[o] = lst_d[(size_t)r * QB + col];
                 part_idx[o] = lst_i[(size_t)r * QB + col];
             }
         }
     }
 }
 
-// cost[b] = planned tile count (overflowed lists count as the heaviest); iota[b] = b
-static __global__ void plan_cost_kernel(const int32_t* __restrict__ plan_count, int64_t n_blocks,
-                                        int32_t* __restrict__ cost, int32_t* __restrict__ iota) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_blocks) return;
-    const int32_t c = plan_count[b];
-    cost[b] = c < 0 ? 0x7fffffff : c;
-    iota[b] = (int32_t)b;
+// ---- work units of the windowed engine.  The planned tile lists are very uneven (a block of
+// queries in a sparse region keeps hundreds of tiles, a typical one ten), so a launch with one
+// CTA per block ends in a long tail of a few heavy CTAs.  The lists are therefore cut into
+// units of at most `chunk` tiles; every unit is an independent (block, tile-range) job that
+// starts from the block's seeded thresholds and emits its own partial lists, which the refine
+// kernel merges exactly like the split lists of the dense launch.
+//   meta[0] = number of units, meta[1] = chunk, meta[2] = work-queue cursor (zeroed here),
+//   meta[3] = tile-list pool cursor (zeroed before the planning pass)
+static __global__ void __launch_bounds__(1024)
+knn_unit_table_kernel(const int32_t* __restrict__ plan_count, int64_t n_blocks, int64_t max_units,
+                      int32_t* __restrict__ unit_first, int32_t* __restrict__ unit_block,
+                      int32_t* __restrict__ meta) {
+    __shared__ long long s_red[32];
+    __shared__ int s_scan[1024];
+    __shared__ int s_chunk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t per = (n_blocks + 1023) / 1024;
+    const int64_t b0 = (int64_t)tid * per, b1 = b0 + per < n_blocks ? b0 + per : n_blocks;
+    long long tiles = 0;
+    for (int64_t b = b0; b < b1; ++b) tiles += plan_count[b] > 0 ? plan_count[b] : 0;
+    for (int off = 16; off > 0; off >>= 1) tiles += __shfl_xor_sync(0xffffffffu, tiles, off);
+    if (lane == 0) s_red[warp] = tiles;
+    __syncthreads();
+    if (tid == 0) {
+        long long total = 0;
+        for (int w = 0; w < 32; ++w) total += s_red[w];
+        long long chunk = (total + KNN_UNIT_FACTOR * n_blocks - 1) / (KNN_UNIT_FACTOR * n_blocks);
+        if (chunk < KNN_UNIT_MIN_TILES) chunk = KNN_UNIT_MIN_TILES;
+        s_chunk = (int)chunk;
+    }
+    __syncthreads();
+    const int chunk = s_chunk;
+    int mine = 0;
+    for (int64_t b = b0; b < b1; ++b) {
+        const int c = plan_count[b];
+        mine += c > 0 ? (c + chunk - 1) / chunk : 0;
+    }
+    s_scan[tid] = mine;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // inclusive scan
+        const int v = tid >= off ? s_scan[tid - off] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int u = s_scan[tid] - mine;
+    for (int64_t b = b0; b < b1; ++b) {
+        const int c = plan_count[b];
+        const int nu = c > 0 ? (c + chunk - 1) / chunk : 0;
+        unit_first[b] = u;
+        for (int i = 0; i < nu; ++i)
+            if (u + i < max_units) unit_block[u + i] = (int32_t)b;
+        u += nu;
+    }
+    if (tid == 1023) {
+        unit_first[n_blocks] = s_scan[1023];
+        meta[0] = s_scan[1023] < max_units ? s_scan[1023] : (int32_t)max_units;  // (bound holds by construction)
+        meta[1] = chunk;
+        meta[2] = 0;
+    }
+}
+
+// (mask << 1) | sign(t): one funnel shift appends a candidate's "closer than the threshold" bit
+__device__ __forceinline__ uint32_t push_sign(uint32_t mask, float t) {
+    uint32_t r;
+    asm("shf.l.clamp.b32 %0, %1, %2, 1;" : "=r"(r) : "r"(__float_as_uint(t)), "r"(mask));
+    return r;
+}
+
+// Persistent filter kernel of the windowed engine: CTAs pull units from a global cursor.
+//
+// Inside a unit the pruning goes one level finer than the planned tile list: every warp owns
+// 32*Q CONSECUTIVE queries of the block (a compact blob in the prepared order) and tests the
+// bounding box of every 32-row sub-tile (staged beside the tile by a second bulk copy) against
+// its own query box and its own largest threshold -- a warp-uniform branch, no block barrier.
+// Surviving sub-tiles are scanned with per-candidate hit bits instead of the dense kernel's
+// "running minimum + re-walk" (which pays off only when hits are rare): per (query, candidate)
+//     DP/2 FADD2 + ~DP/2 FMNMX   the distance,
+//     1 FADD (m - thr)           its sign is the hit bit,
+//     1 SHF                      funnel-shifts the bit into the slot's 32-bit mask,
+// then the lanes pop their hit bits in lock step and insert into their sorted lists.
+// part_d32 / part_idx: [unit][rank][QB], QB index = position of the query in its block.
+template <int DP, int Q, int STAGES>
+static __global__ void __launch_bounds__(FAST_THREADS)
+knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub_box, int64_t q_begin, int64_t nq,
+                 int kcap, const double* __restrict__ maxabs, int dim, const float* __restrict__ seed_thr,
+                 const int2* __restrict__ plan, const int32_t* __restrict__ plan_count,
+                 const int32_t* __restrict__ plan_first, const int32_t* __restrict__ unit_first,
+                 const int32_t* __restrict__ unit_block, int32_t* __restrict__ meta, float* __restrict__ part_d32,
+                 int32_t* __restrict__ part_idx, unsigned long long* __restrict__ pair_counter) {
+    constexpr int QB = FAST_THREADS * Q;
+    constexpr int TILE_FLOATS = FAST_TILE * DP;
+    constexpr int BOX_FLOATS = FAST_NSUB * DP * 2;
+    constexpr int SLOT_FLOATS = TILE_FLOATS + BOX_FLOATS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // STAGES * SLOT_FLOATS
+    float* lst_d = tiles + STAGES * SLOT_FLOATS;                             // kcap * QB
+    int32_t* lst_i = reinterpret_cast<int32_t*>(lst_d + (size_t)kcap * QB);  // kcap * QB
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ TileQueueShared sh;
+    __shared__ int s_unit;
+    __shared__ int s_tile[STAGES];  // tile staged in each ring slot
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Band band = make_band(maxabs, dim);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int n_units = meta[0], chunk = meta[1];
+    // bulk-copy ring (kernel lifetime): next slot to fill / to consume, tiles in flight, and the
+    // mbarrier phase parity of every slot
+    int issue_slot = 0, consume_slot = 0, in_flight = 0;
+    uint32_t phase_bits = 0u;
+    unsigned long long subtiles_total = 0;   // (warp, sub-tile) scans of this thread's warp
+
+    for (;;) {
+        if (tid == 0) s_unit = atomicAdd(&meta[2], 1);
+        __syncthreads();
+        const int u = s_unit;
+        __syncthreads();  // s_unit may be overwritten by the next round only after everyone read it
+        if (u >= n_units) break;
+        const int64_t qblock = unit_block[u];
+        const int first = (u - unit_first[qblock]) * chunk;
+        const int count = plan_count[qblock];
+        const int last = first + chunk < count ? first + chunk : count;
+        const int64_t qb0 = qblock * QB;
+
+        // slot j of this thread = query qb0 + warp*32*Q + j*32 + lane
+        float2 q[Q][DP / 2];
+        float thr[Q];
+        float wlo[DP], whi[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { wlo[d] = CUDART_INF_F; whi[d] = -CUDART_INF_F; }
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            const int64_t qi = qb0 + warp * (32 * Q) + j * 32 + lane;
+            const bool in = qi < nq;
+            load_row<DP>(shadow + (q_begin + (in ? qi : 0)) * DP, q[j]);
+            const float s = in ? seed_thr[qi] : -1.0f;
+            thr[j] = s < 0.0f ? -1.0f : s;  // deferred / dead slots never insert
+            if (thr[j] >= 0.0f) {
+#pragma unroll
+                for (int h = 0; h < DP / 2; ++h) {
+                    wlo[2 * h] = fminf(wlo[2 * h], q[j][h].x);         whi[2 * h] = fmaxf(whi[2 * h], q[j][h].x);
+                    wlo[2 * h + 1] = fminf(wlo[2 * h + 1], q[j][h].y); whi[2 * h + 1] = fmaxf(whi[2 * h + 1], q[j][h].y);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < DP; ++d)
+            for (int off = 16; off > 0; off >>= 1) {
+                wlo[d] = fminf(wlo[d], __shfl_xor_sync(0xffffffffu, wlo[d], off));
+                whi[d] = fmaxf(whi[d], __shfl_xor_sync(0xffffffffu, whi[d], off));
+            }
+        for (int r = 0; r < kcap; ++r)
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                lst_d[(size_t)r * QB + j * FAST_THREADS + tid] = CUDART_INF_F;
+                lst_i[(size_t)r * QB + j * FAST_THREADS + tid] = -1;
+            }
+        auto insert = [&](int j, float m, int32_t idx) -> float {
+            const int col = j * FAST_THREADS + tid;
+            int r = kcap - 1;
+            while (r > 0 && lst_d[(size_t)(r - 1) * QB + col] > m) {
+                lst_d[(size_t)r * QB + col] = lst_d[(size_t)(r - 1) * QB + col];
+                lst_i[(size_t)r * QB + col] = lst_i[(size_t)(r - 1) * QB + col];
+                --r;
+            }
+            lst_d[(size_t)r * QB + col] = m;
+            lst_i[(size_t)r * QB + col] = idx;
+            return lst_d[(size_t)(kcap - 1) * QB + col];
+        };
+        // largest threshold of the warp (insertion needs m < thr, and the box gap is a lower
+        // bound of every computed m: a sub-tile with gap >= wthr cannot change any list)
+        float wthr;
+        auto warp_refresh = [&]() {
+            float v = -1.0f;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) v = fmaxf(v, thr[j]);
+            for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+            wthr = v;
+        };
+        warp_refresh();
+        float R;  // block radius: decides which planned tiles are fetched at all
+        auto refresh = [&]() { R = block_max(wthr, sh); };
+        refresh();
+
+        const int2* lst = plan + plan_first[qblock];
+        int next = first, tiles_done = 0;
+        for (;;) {
+            while (in_flight < STAGES && next < last) {
+                const int2 e = lst[next++];
+                if (!(__int_as_float(e.y) < R)) continue;
+                if (tid == 0) {
+                    float* dst = tiles + (size_t)issue_slot * SLOT_FLOATS;
+                    s_tile[issue_slot] = e.x;  // published by the mbarrier (release on arrive, acquire on wait)
+                    mbar_expect_tx(&full_bar[issue_slot], SLOT_FLOATS * 4);
+                    bulk_g2s(dst, shadow + (int64_t)e.x * TILE_FLOATS, TILE_FLOATS * 4, &full_bar[issue_slot]);
+                    bulk_g2s(dst + TILE_FLOATS, sub_box + (int64_t)e.x * BOX_FLOATS, BOX_FLOATS * 4,
+                             &full_bar[issue_slot]);
+                }
+                issue_slot = issue_slot + 1 == STAGES ? 0 : issue_slot + 1;
+                ++in_flight;
+            }
+            if (in_flight == 0) break;
+            const int slot = consume_slot;
+            mbar_wait(&full_bar[slot], (phase_bits >> slot) & 1u);
+            phase_bits ^= 1u << slot;
+            consume_slot = consume_slot + 1 == STAGES ? 0 : consume_slot + 1;
+            const int64_t t = s_tile[slot];
+            const float* tile = tiles + (size_t)slot * SLOT_FLOATS;
+            const float2* boxes = reinterpret_cast<const float2*>(tile + TILE_FLOATS);
+            const int64_t tile_base = t * FAST_TILE;
+#pragma unroll 1
+            for (int sb = 0; sb < FAST_NSUB; ++sb) {
+                float gap = 0.0f;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) {
+                    const float2 bx = boxes[sb * DP + d];
+                    gap = fmaxf(gap, fmaxf(bx.x - whi[d], wlo[d] - bx.y));
+                }
+                if (!(gap < wthr)) continue;  // warp-uniform
+                ++subtiles_total;
+                const float* rows = tile + sb * FAST_SUB * DP;
+                uint32_t mask[Q];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) mask[j] = 0u;
+#pragma unroll 4
+                for (int c = 0; c < FAST_SUB; c += 2) {
+                    float2 ca[DP / 2], cb[DP / 2];
+                    load_two_rows<DP>(rows + c * DP, ca, cb);
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        mask[j] = push_sign(mask[j], cheb32<DP>(q[j], ca) - thr[j]);
+                        mask[j] = push_sign(mask[j], cheb32<DP>(q[j], cb) - thr[j]);
+                    }
+                }
+                // candidate c of the sub-tile sits at bit 31 - c
+                bool changed = false;
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    uint32_t mk = mask[j];
+                    while (mk) {
+                        const int c = __clz(mk);
+                        mk &= ~(0x80000000u >> c);
+                        float2 cc[DP / 2];
+                        load_row<DP>(rows + c * DP, cc);
+                        const float m = cheb32<DP>(q[j], cc);
+                        if (m < thr[j]) thr[j] = insert(j, m, (int32_t)(tile_base + sb * FAST_SUB + c));
+                        changed = true;
+                    }
+                }
+                if (__any_sync(0xffffffffu, changed)) warp_refresh();
+            }
+            __syncthreads();  // tile consumed: its slot may be refilled
+            --in_flight;
+            ++tiles_done;
+            if ((tiles_done & 3) == 0) refresh();
+        }
+
+        // emit this unit's lists (ascending)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            const int col = j * FAST_THREADS + tid;
+            const int lq = warp * (32 * Q) + j * 32 + lane;
+            for (int r = 0; r < kcap; ++r) {
+                const int64_t o = ((int64_t)u * kcap + r) * QB + lq;
+                part_d32[o] = lst_d[(size_t)r * QB + col];
+                part_idx[o] = lst_i[(size_t)r * QB + col];
+            }
+        }
+        __syncthreads();  // lists are reset by the next unit
+    }
+    if (lane == 0 && pair_counter && subtiles_total)
+        atomicAdd(pair_counter, subtiles_total * (unsigned long long)(FAST_SUB * 32 * Q));
 }
 
 // Exact refine: see the file header.  flags[qi] = 1 marks a query for the fp64 fallback.
@@ -465,14 +739,27 @@ static __global__ void __launch_bounds__(128)
 knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict__ part_idx, int kcap, int splits,
                   int kp, const double* __restrict__ sorted, int64_t ld, int dim, int64_t n, int64_t q_begin,
                   int64_t nq, const int32_t* __restrict__ q_index, const double* __restrict__ maxabs,
+                  const float* __restrict__ seed_thr, const int32_t* __restrict__ unit_first, int qb,
                   double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
-    if (part_d32[qi] == KNN_DEFERRED) {  // taken out by the windowed filter: needs the dense launch
+    if (seed_thr && seed_thr[qi] < 0.0f) {  // taken out by the planning pass: needs the dense launch
         flags[qi] = 2;
         atomicAdd(n_flagged, 1);
         eps_out[qi] = CUDART_NAN;
         return;
+    }
+    // list s, rank r of this query sits at ((s * kcap + r) * stride + off):
+    //   dense launch   : s = candidate split,  [split][rank][nq]
+    //   windowed launch: s = work unit of the query's block,  [unit][rank][QB]
+    int s_begin = 0, s_end = splits;
+    int64_t stride = nq, off = qi;
+    if (unit_first) {
+        const int64_t b = qi / qb;
+        s_begin = unit_first[b];
+        s_end = unit_first[b + 1];
+        stride = qb;
+        off = qi - b * qb;
     }
     const int64_t row_q = q_index ? (int64_t)q_index[qi] : q_begin + qi;
     double mmax = 0.0;
@@ -481,9 +768,9 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     // k'-th smallest fp32 distance over the union of the split lists
     float best[KSG_MAX_KPRIME];
     int have = 0;
-    for (int s = 0; s < splits; ++s)
+    for (int s = s_begin; s < s_end; ++s)
         for (int r = 0; r < kcap; ++r) {
-            const float v = part_d32[((int64_t)s * kcap + r) * nq + qi];
+            const float v = part_d32[((int64_t)s * kcap + r) * stride + off];
             if (have == kp && !(v < best[kp - 1])) break;
             int pos = have < kp ? have : kp - 1;
             while (pos > 0 && best[pos - 1] > v) { best[pos] = best[pos - 1]; --pos; }
@@ -504,12 +791,12 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     int got = 0, examined = 0;
     double qc[KSG_MAX_DIM];
     for (int d = 0; d < dim; ++d) qc[d] = sorted[(int64_t)d * ld + row_q];
-    for (int s = 0; s < splits && !overflow; ++s) {
+    for (int s = s_begin; s < s_end && !overflow; ++s) {
         // a full list whose tail is still inside the band may have dropped in-band candidates
-        const float tail = part_d32[((int64_t)s * kcap + (kcap - 1)) * nq + qi];
+        const float tail = part_d32[((int64_t)s * kcap + (kcap - 1)) * stride + off];
         if ((double)tail <= T) { overflow = true; break; }
         for (int r = 0; r < kcap; ++r) {
-            const int64_t o = ((int64_t)s * kcap + r) * nq + qi;
+            const int64_t o = ((int64_t)s * kcap + r) * stride + off;
             const float v = part_d32[o];
             if (!((double)v <= T)) break;
             if (++examined > REFINE_CAP) { overflow = true; break; }

@@ -12,17 +12,23 @@ namespace ksg {
 struct KnnF32Args {
     const float* shadow;
     const float* tile_box;
+    const float* sub_box;
     int64_t n_tiles;
     int64_t q_begin, nq;
     const int32_t* q_index;  // optional: explicit query rows (then q_begin is ignored)
     int kcap, splits, windowed;
     const double* maxabs;
     int dim;
-    // planning pass outputs (windowed engine; all null otherwise)
-    float* seed_thr;
-    void* plan;            // int2[n_query_blocks][KNN_PLAN_CAP]
-    int32_t* plan_count;   // [n_query_blocks]
-    const int32_t* block_order;
+    // windowed engine only (all null otherwise): planning pass outputs and the unit table
+    float* seed_thr;       // [nq] seeded thresholds; < 0: query deferred to the dense launch
+    void* plan;            // int2[plan_capacity] pool of (tile, box gap) lists
+    int64_t plan_capacity;
+    int32_t* plan_count;   // [n_query_blocks] list length
+    int32_t* plan_first;   // [n_query_blocks] list start in the pool
+    int32_t* unit_first;   // [n_query_blocks + 1]
+    int32_t* unit_block;   // [max_units]
+    int32_t* unit_meta;    // [4]: number of units, tiles per unit, work-queue cursor
+    int64_t max_units;
     float* part_d32;
     int32_t* part_idx;
     unsigned long long* tile_counter;
@@ -30,8 +36,10 @@ struct KnnF32Args {
 };
 int knn_f32_queries_per_block(int dim_padded);
 int launch_knn_f32(int dim_padded, const KnnF32Args& a);  // KSG_EUNSUPPORTED if dim_padded not in {2,4,6,8}
-int launch_knn_plan(int dim_padded, const KnnF32Args& a);  // fills seed_thr / plan / plan_count
+int launch_knn_plan(int dim_padded, const KnnF32Args& a);   // fills seed_thr / plan / plan_count / unit table
+int launch_knn_units(int dim_padded, const KnnF32Args& a);  // persistent windowed filter over the work units
 int knn_plan_cap();
+int knn_unit_factor();
 
 struct CountF32Args {
     const float* shadow;

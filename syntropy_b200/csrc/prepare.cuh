@@ -18,6 +18,8 @@
 namespace ksg {
 
 constexpr int FAST_TILE = 512;       // candidates per shared-memory tile (fast kernels)
+constexpr int FAST_SUB = 32;         // rows of a sub-tile (own bounding box: warp-level culling)
+constexpr int FAST_NSUB = FAST_TILE / FAST_SUB;
 constexpr int STATS_BLOCKS = 64;     // partial min/max blocks per dimension
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -28,7 +30,7 @@ struct PreparedLayout {
     int64_t n_padded;  // shadow rows
     int dim_padded;
     size_t off_perm, off_sorted, off_shadow, off_axis_vals, off_axis_pos, off_center, off_maxabs, off_flags;
-    size_t off_tile_box;
+    size_t off_tile_box, off_sub_box;
     size_t off_stats, off_iota, off_keys_tmp, off_ranks, off_mkeys, off_mkeys_out, off_invperm, off_cub;
     size_t cub_bytes;
     size_t total;
@@ -171,25 +173,32 @@ static __global__ void remap_axis_kernel(int32_t* __restrict__ pos, int64_t n, c
     if (i < n) pos[i] = inv[pos[i]];
 }
 
-// tile_box[(t * dim_padded + d) * 2 + {0,1}] = min / max of the fp32 shadow over tile t
+// tile_box[(t * dim_padded + d) * 2 + {0,1}] = min / max of the fp32 shadow over tile t;
+// sub_box[((t * FAST_NSUB + s) * dim_padded + d) * 2 + {0,1}] = the same over sub-tile s of tile t
 static __global__ void __launch_bounds__(128)
-tile_box_kernel(const float* __restrict__ shadow, int dim_padded, float* __restrict__ tile_box) {
+tile_box_kernel(const float* __restrict__ shadow, int dim_padded, float* __restrict__ tile_box,
+                float* __restrict__ sub_box) {
     const int64_t t = blockIdx.x;
     const float* rows = shadow + t * FAST_TILE * dim_padded;
     __shared__ float slo[4][KSG_MAX_DIM], shi[4][KSG_MAX_DIM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int d = 0; d < dim_padded; ++d) {
-        float lo = CUDART_INF_F, hi = -CUDART_INF_F;
-        for (int r = threadIdx.x; r < FAST_TILE; r += 128) {
-            const float v = rows[r * dim_padded + d];
-            lo = fminf(lo, v);
-            hi = fmaxf(hi, v);
+        float tlo = CUDART_INF_F, thi = -CUDART_INF_F;
+        for (int s = warp; s < FAST_NSUB; s += 4) {
+            const float v = rows[(s * FAST_SUB + lane) * dim_padded + d];
+            float lo = v, hi = v;
+            for (int off = 16; off > 0; off >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+            }
+            if (lane == 0) {
+                sub_box[((t * FAST_NSUB + s) * dim_padded + d) * 2 + 0] = lo;
+                sub_box[((t * FAST_NSUB + s) * dim_padded + d) * 2 + 1] = hi;
+            }
+            tlo = fminf(tlo, lo);
+            thi = fmaxf(thi, hi);
         }
-        for (int off = 16; off > 0; off >>= 1) {
-            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
-        }
-        if (lane == 0) { slo[warp][d] = lo; shi[warp][d] = hi; }
+        if (lane == 0) { slo[warp][d] = tlo; shi[warp][d] = thi; }
     }
     __syncthreads();
     if (threadIdx.x < dim_padded) {
