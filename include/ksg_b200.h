@@ -296,6 +296,15 @@ int ksg_axis_count(const ksg_prepared* h_prep, int axis, int64_t q_begin, int64_
 /* d_dst[perm[i]] = d_src[i], i in [0, n): pointwise values back to the caller's sample order. */
 int ksg_scatter_f64(const double* d_src, const int32_t* d_perm, int64_t n, double* d_dst, void* stream);
 
+/* The same for int32 counts, and its inverse d_dst[i] = d_src[perm[i]] for float64 radii: a
+ * multi-dimensional marginal is counted in a prepared set of its OWN coordinates (its own
+ * space-filling order prunes far better than the joint order does for that marginal), so the
+ * joint radii travel into that order and the counts travel back to the caller's sample order.
+ * (The reference builds one cKDTree per marginal for the same reason: shannon.py:190,336;
+ * multivariate_mi.py:251,318-323,399-404.) */
+int ksg_scatter_i32(const int32_t* d_src, const int32_t* d_perm, int64_t n, int32_t* d_dst, void* stream);
+int ksg_gather_f64(const double* d_src, const int32_t* d_perm, int64_t n, double* d_dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,8 @@ SIGNATURES = {
                                  C.c_int32, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),
     "ksg_axis_count": (C.c_int, [_c_prep, C.c_int, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int32, _c_vp, _c_vp]),
     "ksg_scatter_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "ksg_scatter_i32": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "ksg_gather_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
 }
 
 _lib = None

@@ -75,16 +75,108 @@ def psi_host(n: int) -> float:
     return v
 
 
-def to_device_points(rows: np.ndarray) -> torch.Tensor:
-    """(D, n) array of any real dtype -> contiguous float64 SoA tensor on the GPU.
+# ------------------------------------------------------------------ host <-> device staging
+class RowSelection:
+    """``data[idxs, :]`` without the intermediate host copy: the selected rows go straight
+    from the caller's array into the pinned staging buffer (see ``to_device_points``)."""
 
-    cKDTree converts its input to C-contiguous float64 the same way
-    (integer and float32 inputs are legal)."""
+    def __init__(self, data: np.ndarray, idxs):
+        self.data = data
+        self.idxs = tuple(int(i) for i in idxs)
+        if data.ndim != 2:
+            raise ValueError("data must be (n_variables, n_samples)")
+        self.shape = (len(self.idxs), data.shape[1])
+
+    def row(self, r: int) -> np.ndarray:
+        return self.data[self.idxs[r]]
+
+
+def select_rows(data: np.ndarray, idxs) -> RowSelection:
+    return RowSelection(np.asarray(data), idxs)
+
+
+_pinned: dict = {}   # (device index, "in" | "out") -> pinned uint8 tensor, grown geometrically
+_stage_done: dict = {}  # device index -> event recorded after the last H2D copy out of the "in" buffer
+_copy_pool = None
+_COPY_CHUNK = 1 << 18  # elements per host copy task (2 MiB of float64)
+
+
+def _pool():
+    global _copy_pool
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+
+        _copy_pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+    return _copy_pool
+
+
+def _pinned_buffer(dev: torch.device, kind: str, nbytes: int) -> torch.Tensor:
+    key = (dev.index, kind)
+    cur = _pinned.get(key)
+    if cur is None or cur.numel() < nbytes:
+        size = max(int(nbytes), 1 << 20, 0 if cur is None else 2 * cur.numel())
+        cur = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+        _pinned[key] = cur
+    return cur
+
+
+def _host_copy(dst: np.ndarray, src: np.ndarray):
+    """dst[...] = src (1-D, numeric; casts like ``astype(float64)``), split over a few threads:
+    numpy releases the GIL in its copy loops, and one core cannot saturate host memory."""
+    n = dst.shape[0]
+    if n <= 2 * _COPY_CHUNK:
+        np.copyto(dst, src, casting="unsafe")
+        return
+    futs = [_pool().submit(np.copyto, dst[a:a + _COPY_CHUNK], src[a:a + _COPY_CHUNK], "unsafe")
+            for a in range(0, n, _COPY_CHUNK)]
+    for f in futs:
+        f.result()
+
+
+def to_device_points(rows) -> torch.Tensor:
+    """(D, n) array of any real dtype (or a ``RowSelection``) -> contiguous float64 SoA tensor
+    on the GPU.  cKDTree converts its input to C-contiguous float64 the same way (integer and
+    float32 inputs are legal).
+
+    Each row is converted into a pinned staging buffer by a few host threads and sent with
+    its own asynchronous copy, so the DMA of row r overlaps the host conversion of row r+1."""
     dev = require_cuda()
-    arr = np.ascontiguousarray(rows, dtype=np.float64)
-    if arr.ndim != 2:
-        raise ValueError("data must be (n_variables, n_samples)")
-    return torch.from_numpy(arr).to(dev, non_blocking=False)
+    if not isinstance(rows, RowSelection):
+        arr = np.asarray(rows)
+        if arr.ndim != 2:
+            raise ValueError("data must be (n_variables, n_samples)")
+        rows = RowSelection(arr, range(arr.shape[0]))
+    dim, n = rows.shape
+    if rows.data.dtype.kind not in "fiub":
+        raise TypeError(f"data must be real-valued, got dtype {rows.data.dtype}")
+    out = torch.empty((dim, n), dtype=torch.float64, device=dev)
+    if dim == 0 or n == 0:
+        return out
+    prev = _stage_done.get(dev.index)
+    if prev is not None:
+        prev.synchronize()  # the staging buffer is reused: its last copies must have left it
+    stage = _pinned_buffer(dev, "in", dim * n * 8)[: dim * n * 8].view(torch.float64).view(dim, n)
+    stage_np = stage.numpy()
+    for r in range(dim):
+        _host_copy(stage_np[r], rows.row(r))
+        out[r].copy_(stage[r], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    _stage_done[dev.index] = ev
+    return out
+
+
+def to_host(values: torch.Tensor) -> np.ndarray:
+    """Device vector -> fresh numpy array, through the pinned output buffer."""
+    n = values.numel()
+    stage = _pinned_buffer(values.device, "out", n * values.element_size())[: n * values.element_size()]
+    stage = stage.view(values.dtype)
+    stage.copy_(values.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out = np.empty(n, dtype=stage.numpy().dtype)
+    _host_copy(out, stage.numpy())
+    return out
 
 
 @dataclass
@@ -220,6 +312,8 @@ class Config:
     All three give identical radii and counts."""
     engine = "windowed"
     primary = -1  # -1: Morton order of the per-coordinate ranks; d >= 0: sort by coordinate d
+    own_order = True          # windowed engine: low-dimensional marginals in their own order
+    own_order_max_dim = 4     # ... when they have at most this many coordinates
 
 
 config = Config()
@@ -367,30 +461,53 @@ def check_finite(points: torch.Tensor) -> torch.Tensor:
     return flag
 
 
-def finish_device(ptw_slice: torch.Tensor, n_total: int, prep=None):
+class Pointwise:
+    """Device-resident pointwise values of one estimator call on this rank.
+
+    ``full`` False: ``values`` is this rank's query slice -- in the order of ``prep`` (sorted
+    positions) when ``prep`` is given, else in the caller's sample order (exact engine).
+    ``full`` True: ``values`` already holds all n samples in the caller's order on every rank.
+    ``preps`` lists every prepared set the call built (for the pair counters)."""
+
+    def __init__(self, values, prep=None, full=False, preps=()):
+        self.values, self.prep, self.full, self.preps = values, prep, full, list(preps)
+
+    def pairs_evaluated(self):
+        a = b = 0
+        for p in self.preps:
+            x, y = p.pairs_evaluated()
+            a, b = a + x, b + y
+        return a, b
+
+
+def finish_device(pw: Pointwise, n_total: int):
     """All-gather the pointwise slices (NCCL), put them back into the caller's sample order
     if they were computed in sorted order, and reduce the full vector in a fixed order."""
-    ptw_full = _dist.gather_slices(ptw_slice, n_total)
-    if prep is not None:
-        ptw_full = scatter_to_original(ptw_full, prep)
+    if pw.full:
+        ptw_full = pw.values
+    else:
+        ptw_full = _dist.gather_slices(pw.values, n_total)
+        if pw.prep is not None:
+            ptw_full = scatter_to_original(ptw_full, pw.prep)
     return ptw_full, device_sum(ptw_full)
 
 
-def _finish(ptw_slice: torch.Tensor, n_total: int, flag: torch.Tensor, prep=None):
+def _finish(pw: Pointwise, n_total: int, flag: torch.Tensor):
     """Gather the pointwise slices of all ranks, reduce deterministically, copy out."""
-    ptw_full, total = finish_device(ptw_slice, n_total, prep)
-    host = torch.cat([ptw_full, total, flag.to(torch.float64)]).cpu().numpy()
-    if host[-1] != 0.0:
+    ptw_full, total = finish_device(pw, n_total)
+    tail = torch.cat([total, flag.to(torch.float64)])
+    ptw = to_host(ptw_full)
+    tail = tail.cpu().numpy()
+    if tail[1] != 0.0:
         # what scipy's cKDTree constructor raises, reached from knn/utils.py:29
         raise ValueError("data must be finite, check for nan or inf values")
-    ptw = host[:n_total].copy()
     with np.errstate(all="ignore"):
-        avg = np.float64(host[n_total]) / n_total  # ndarray.mean(): sum / N
+        avg = np.float64(tail[0]) / n_total  # ndarray.mean(): sum / N
     return ptw, avg
 
 
 # ------------------------------------------------------------------ estimator drivers
-def ksg1_family(rows: np.ndarray, k: int, masks, prog_builder):
+def ksg1_family(rows, k: int, masks, prog_builder):
     """Joint radius -> strict counts in every subspace -> psi program -> (ptw, avg).
 
     ``rows`` is the (D, n) joint-space selection in the reference's concatenation
@@ -399,25 +516,88 @@ def ksg1_family(rows: np.ndarray, k: int, masks, prog_builder):
     """
     pts = to_device_points(rows)
     flag = check_finite(pts)
-    ptw, prep = ksg1_device(pts, k, masks, prog_builder)
-    return _finish(ptw, pts.shape[1], flag, prep)
+    pw = ksg1_device(pts, k, masks, prog_builder)
+    return _finish(pw, pts.shape[1], flag)
 
 
-def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder):
-    """The device-resident part of ``ksg1_family``: this rank's pointwise slice, plus the
-    prepared set when the slice is in sorted order (``None`` for the exact engine)."""
+def _dims_of(mask: int):
+    return [d for d in range(int(mask).bit_length()) if (int(mask) >> d) & 1]
+
+
+def own_order_subspaces(masks, dim: int):
+    """Indices of the subspaces that are counted in a prepared set of their OWN coordinates.
+
+    A marginal of a few coordinates is pruned far better by a space-filling order of those
+    coordinates than by the joint order (whose tiles are wide in any low-dimensional
+    projection); each such marginal costs one extra ``ksg_prepare`` (a few sorts) and one
+    single-subspace pass.  Marginals that keep most of the joint coordinates (leave-one-out
+    families) stay in the fused joint-order pass, which shares one distance evaluation among
+    all of them; 1-D marginals need no pass at all (binary search)."""
+    if config.engine != "windowed" or not config.own_order:
+        return []
+    out = []
+    for s, m in enumerate(masks):
+        d = bin(int(m)).count("1")
+        if 1 < d <= config.own_order_max_dim and d < dim:
+            out.append(s)
+    return out
+
+
+def radius_and_counts(pts: torch.Tensor, k: int, masks):
+    """Fast engines: joint radii and every subspace's strict counts for ALL n samples, in the
+    caller's sample order, on every rank (each rank computes its slice of every pass; the
+    slices are all-gathered).  Returns ``(eps (n,), counts (S, n) int32, prepared sets)``."""
+    lib = _cabi.load()
     dim, n = pts.shape
-    q0, q1 = _dist.my_slice(n)
-    prog = prog_builder(psi_host(k), psi_host(n))
-    if not _use_fast(dim):
-        eps = knn_radius(pts, k + 1, q0, q1)
-        counts = count_subspaces(pts, masks, eps, q0, q1, strict=True, bias=-1)
-        return psi_epilogue(counts, prog, n), None
     windowed = config.engine == "windowed"
     prep = PreparedSet(pts, min(config.primary, dim - 1))
+    preps = [prep]
+    q0, q1 = _dist.my_slice(n)
     eps = fast_knn(prep, k + 1, q0, q1, windowed)
-    counts = fast_counts(prep, masks, eps, q0, q1, windowed)
-    return psi_epilogue(counts, prog, n), prep
+    own = own_order_subspaces(masks, dim)
+    counts = torch.empty((len(masks), n), dtype=torch.int32, device=pts.device)
+
+    def to_original(slice_sorted, prep_, out_row):
+        full = _dist.gather_slices(slice_sorted, n)
+        _cabi.check(lib.ksg_scatter_i32(_ptr(full), _ptr(prep_.perm), n, _ptr(out_row), _stream()), "ksg_scatter_i32")
+
+    joint = [s for s in range(len(masks)) if s not in own]
+    if joint:
+        c = fast_counts(prep, [masks[s] for s in joint], eps, q0, q1, windowed)
+        for row, s in enumerate(joint):
+            to_original(c[row], prep, counts[s])
+    eps_orig = scatter_to_original(_dist.gather_slices(eps, n), prep)
+    for s in own:
+        dims = _dims_of(masks[s])
+        sub = pts[dims, :].contiguous()
+        prep_s = PreparedSet(sub, -1)
+        preps.append(prep_s)
+        eps_s = torch.empty(n, dtype=torch.float64, device=pts.device)
+        _cabi.check(lib.ksg_gather_f64(_ptr(eps_orig), _ptr(prep_s.perm), n, _ptr(eps_s), _stream()), "ksg_gather_f64")
+        c = fast_counts(prep_s, [(1 << len(dims)) - 1], eps_s[q0:q1].contiguous(), q0, q1, True)
+        to_original(c[0], prep_s, counts[s])
+    return eps_orig, counts, preps
+
+
+def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder) -> Pointwise:
+    """The device-resident part of ``ksg1_family``."""
+    dim, n = pts.shape
+    prog = prog_builder(psi_host(k), psi_host(n))
+    if not _use_fast(dim):
+        q0, q1 = _dist.my_slice(n)
+        eps = knn_radius(pts, k + 1, q0, q1)
+        counts = count_subspaces(pts, masks, eps, q0, q1, strict=True, bias=-1)
+        return Pointwise(psi_epilogue(counts, prog, n))
+    if not own_order_subspaces(masks, dim):
+        # everything is counted in the joint order: keep the slices sorted until the end
+        windowed = config.engine == "windowed"
+        q0, q1 = _dist.my_slice(n)
+        prep = PreparedSet(pts, min(config.primary, dim - 1))
+        eps = fast_knn(prep, k + 1, q0, q1, windowed)
+        counts = fast_counts(prep, masks, eps, q0, q1, windowed)
+        return Pointwise(psi_epilogue(counts, prog, n), prep=prep, preps=[prep])
+    _, counts, preps = radius_and_counts(pts, k, masks)
+    return Pointwise(psi_epilogue(counts, prog, n), full=True, preps=preps)
 
 
 def ksg2_family(rows: np.ndarray, k: int, masks, prog_builder):
@@ -436,7 +616,7 @@ def ksg2_family(rows: np.ndarray, k: int, masks, prog_builder):
     counts = count_subspaces(pts, masks, eps_s, q0, q1, strict=False, bias=-1, per_subspace_eps=True)
     prog = prog_builder(psi_host(k), psi_host(n))
     ptw = psi_epilogue(counts, prog, n)
-    return _finish(ptw, n, flag)
+    return _finish(Pointwise(ptw), n, flag)
 
 
 def kl_entropy(rows: np.ndarray, k: int):
@@ -453,7 +633,7 @@ def kl_entropy(rows: np.ndarray, k: int):
     ptw = torch.empty(q1 - q0, dtype=torch.float64, device=pts.device)
     rc = _cabi.load().ksg_entropy_epilogue(_ptr(eps), q1 - q0, dim, psi_host(k), psi_host(n), _ptr(ptw), _stream())
     _cabi.check(rc, "ksg_entropy_epilogue")
-    return _finish(ptw, n, flag, prep)
+    return _finish(Pointwise(ptw, prep=prep), n, flag)
 
 
 def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
@@ -470,7 +650,7 @@ def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
         log_ratio = float(np.log(m / (n - 1)))
     rc = _cabi.load().ksg_kl_epilogue(_ptr(nu), _ptr(rho), q1 - q0, dim, log_ratio, _ptr(ptw), _stream())
     _cabi.check(rc, "ksg_kl_epilogue")
-    return _finish(ptw, n, flag)
+    return _finish(Pointwise(ptw), n, flag)
 
 
 def pair_counts(x: np.ndarray, y: np.ndarray, m: int, r: float):

@@ -283,9 +283,34 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const in
     return KSG_OK;
 }
 
+struct FastCountPlan {
+    int64_t qblocks, max_units, plan_capacity;
+    size_t thr_bytes, plan_bytes, count_bytes, first_bytes, ublock_bytes, meta_bytes;
+    size_t total() const { return thr_bytes + plan_bytes + count_bytes + first_bytes + ublock_bytes + meta_bytes; }
+};
+static FastCountPlan fast_count_plan(int64_t n, int64_t nq, int dim) {
+    FastCountPlan p;
+    memset(&p, 0, sizeof(p));
+    if (nq < 1) nq = 1;
+    const int dp = (dim + 1) & ~1;
+    p.thr_bytes = align_up((size_t)nq * sizeof(float), 256);
+    p.qblocks = ceil_div(nq, count_f32_queries_per_block(dp));
+    p.max_units = (1 + (int64_t)knn_unit_factor()) * p.qblocks;
+    const int64_t n_tiles = ceil_div(n, FAST_TILE);
+    p.plan_capacity = p.qblocks * (n_tiles < knn_plan_cap() ? n_tiles : (int64_t)knn_plan_cap());
+    if (p.plan_capacity > 0x7fff0000ll) p.plan_capacity = 0x7fff0000ll;
+    p.plan_bytes = align_up((size_t)p.plan_capacity * 8, 256);
+    p.count_bytes = 2 * align_up((size_t)p.qblocks * sizeof(int32_t), 256);
+    p.first_bytes = align_up((size_t)(p.qblocks + 1) * sizeof(int32_t), 256);
+    p.ublock_bytes = align_up((size_t)p.max_units * sizeof(int32_t), 256);
+    p.meta_bytes = 256;
+    return p;
+}
+
 size_t ksg_fast_count_workspace(int64_t n, int64_t nq, int dim, int n_subspaces) {
-    (void)n; (void)dim; (void)n_subspaces;
-    return align_up((size_t)(nq > 0 ? nq : 1) * sizeof(float), 256);
+    (void)n_subspaces;
+    if (n <= 0 || dim < 1) return 0;
+    return fast_count_plan(n, nq, dim).total();
 }
 
 int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const uint32_t* h_masks,
@@ -302,13 +327,15 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
     }
     const int64_t nq = q_end - q_begin;
     if (nq == 0) return KSG_OK;
-    KSG_REQUIRE(workspace_bytes >= (size_t)nq * sizeof(float), "ksg_fast_count: workspace too small");
+    const FastCountPlan cp = fast_count_plan(P->n, nq, P->dim);
+    if (workspace_bytes < cp.total()) {
+        set_error("ksg_fast_count: workspace of %zu bytes needed, %zu given", cp.total(), workspace_bytes);
+        return KSG_EWORKSPACE;
+    }
     const int dim = P->dim;
     const uint32_t all = dim == 32 ? 0xffffffffu : ((1u << dim) - 1u);
-    bool all_have_primary = true;
     for (int s = 0; s < n_subspaces; ++s) {
         KSG_REQUIRE(h_masks[s] != 0 && (h_masks[s] & ~all) == 0, "ksg_fast_count: empty or out-of-range mask");
-        all_have_primary = all_have_primary && ((h_masks[s] >> P->primary) & 1u);
     }
     cudaStream_t st = as_stream2(stream);
     float* thresholds = (float*)d_workspace;
@@ -323,7 +350,6 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
     memset(&a, 0, sizeof(a));
     a.shadow = P->shadow_f32; a.tile_box = P->tile_box; a.n_tiles = P->n_padded / FAST_TILE;
     a.q_begin = q_begin; a.nq = nq; a.thresholds = thresholds;
-    (void)all_have_primary;  // box pruning works for any subspace family
     a.windowed = windowed ? 1 : 0;
     a.n_sub = n_subspaces; a.counts = d_counts; a.st = st;
     a.tile_counter = (unsigned long long*)((char*)P->flags + 24);
@@ -333,7 +359,21 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
     // recognise the fused structures
     int rc = KSG_EUNSUPPORTED;
     auto low = [](int bits) { return bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u); };
-    if (n_subspaces == 2) {
+    if (n_subspaces == 1 && h_masks[0] == all && a.windowed) {
+        // the subspace is the whole space of this prepared set: planned, unit-balanced pass
+        CountUnitsArgs w;
+        char* p = (char*)d_workspace + cp.thr_bytes;
+        w.sub_box = P->sub_box;
+        w.plan = p;                        p += cp.plan_bytes;
+        w.plan_capacity = cp.plan_capacity;
+        w.plan_count = (int32_t*)p;        p += cp.count_bytes / 2;
+        w.plan_first = (int32_t*)p;        p += cp.count_bytes / 2;
+        w.unit_first = (int32_t*)p;        p += cp.first_bytes;
+        w.unit_block = (int32_t*)p;        p += cp.ublock_bytes;
+        w.unit_meta = (int32_t*)p;
+        w.max_units = cp.max_units;
+        rc = launch_count_full(P->dim_padded, a, w);
+    } else if (n_subspaces == 2) {
         const int dx = __builtin_popcount(h_masks[0]), dy = __builtin_popcount(h_masks[1]);
         if (dx + dy == dim && h_masks[0] == low(dx) && h_masks[1] == (low(dy) << dx)) rc = launch_count_pair(dx, dy, a);
     } else if (n_subspaces == 3) {
@@ -390,6 +430,22 @@ int ksg_scatter_f64(const double* d_src, const int32_t* d_perm, int64_t n, doubl
     KSG_REQUIRE(d_src && d_perm && d_dst && n >= 0, "ksg_scatter_f64: bad argument");
     if (n == 0) return KSG_OK;
     scatter_f64_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream2(stream)>>>(d_src, d_perm, n, d_dst);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+int ksg_scatter_i32(const int32_t* d_src, const int32_t* d_perm, int64_t n, int32_t* d_dst, void* stream) {
+    KSG_REQUIRE(d_src && d_perm && d_dst && n >= 0, "ksg_scatter_i32: bad argument");
+    if (n == 0) return KSG_OK;
+    scatter_i32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream2(stream)>>>(d_src, d_perm, n, d_dst);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+int ksg_gather_f64(const double* d_src, const int32_t* d_perm, int64_t n, double* d_dst, void* stream) {
+    KSG_REQUIRE(d_src && d_perm && d_dst && n >= 0, "ksg_gather_f64: bad argument");
+    if (n == 0) return KSG_OK;
+    gather_f64_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream2(stream)>>>(d_src, d_perm, n, d_dst);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

@@ -408,4 +408,15 @@ static __global__ void scatter_f64_kernel(const double* __restrict__ src, const 
     if (i < n) dst[perm[i]] = src[i];
 }
 
+static __global__ void scatter_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ perm, int64_t n,
+                                   int32_t* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[perm[i]] = src[i];
+}
+static __global__ void gather_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ perm, int64_t n,
+                                  double* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[perm[i]];
+}
+
 }  // namespace ksg

@@ -51,7 +51,7 @@ static int launch_plan_dp(const KnnF32Args& a) {
 template <int DP>
 static int launch_units_dp(const KnnF32Args& a) {
     constexpr int Q = FastGeom<DP>::Q, ST = FastGeom<DP>::STAGES;
-    auto kern = knn_units_kernel<DP, Q, ST>;
+    auto kern = knn_units_kernel<DP, Q, ST, (DP <= 4)>;
     const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float) +
                         (size_t)a.kcap * FAST_THREADS * Q * 8;
     if (smem > 32 * 1024) {
@@ -60,11 +60,11 @@ static int launch_units_dp(const KnnF32Args& a) {
     }
     // persistent: as many CTAs as fit on the machine (never more than there can be units)
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FAST_THREADS, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, UNITS_THREADS, smem);
     if (e != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
     int64_t grid = (int64_t)per_sm * sm_count();
     if (grid > a.max_units) grid = a.max_units;
-    kern<<<(unsigned)grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.sub_box, a.q_begin, a.nq, a.kcap, a.maxabs, a.dim, a.seed_thr,
+    kern<<<(unsigned)grid, UNITS_THREADS, smem, a.st>>>(a.shadow, a.sub_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.seed_thr,
                                                        (const int2*)a.plan, a.plan_count, a.plan_first, a.unit_first, a.unit_block,
                                                        a.unit_meta, a.part_d32, a.part_idx, a.tile_counter);
     note_launch();

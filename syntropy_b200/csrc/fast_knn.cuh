@@ -231,9 +231,12 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
         mine += !(gap_of(pos, t) > R);
     }
     const int total = (int)(block_sum((float)mine, sh) + 0.5f);  // exact: < 2^24 tiles
+    // A block that keeps most of the tiles gets no list at all: plan_first = -1 means "every
+    // tile, in walk order" (the warp-level sub-tile culling of the filter kernel still applies).
+    // That also bounds the pool: explicit lists are at most half the tiles long.
     if (tid == 0) {
         int base = -1;
-        if (total > 0) {
+        if (total > 0 && 2 * (int64_t)total <= n_tiles) {
             base = atomicAdd(&meta[3], total);
             if ((int64_t)base + total > plan_capacity) base = -1;  // pool exhausted
         }
@@ -242,12 +245,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
     __syncthreads();
     const int base = s_base;
     if (total > 0 && base < 0) {
-        // no room for this block's list: hand all of its queries to the dense launch
-        for (int j = 0; j < Q; ++j) {
-            const int64_t qi = qb0 + j * FAST_THREADS + tid;
-            if (qi < nq) seed_thr[qi] = KNN_DEFERRED;
-        }
-        if (tid == 0) { plan_count[blockIdx.x] = 0; plan_first[blockIdx.x] = 0; }
+        if (tid == 0) { plan_count[blockIdx.x] = (int32_t)n_tiles; plan_first[blockIdx.x] = -1; }
         return;
     }
     int2* out = plan + base;
@@ -424,7 +422,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
                             float2 cc[DP / 2];
                             load_row<DP>(tile + (b + c) * DP, cc);
                             const float m = cheb32<DP>(q[j], cc);
-                            if (m < thr[j]) thr[j] = insert(j, m, (int32_t)(tile_base + b + c));
+                            if (m < thr[j]) thr[j] = fminf(thr[j], insert(j, m, (int32_t)(tile_base + b + c)));
                         }
                     }
                 }
@@ -521,24 +519,38 @@ __device__ __forceinline__ uint32_t push_sign(uint32_t mask, float t) {
     asm("shf.l.clamp.b32 %0, %1, %2, 1;" : "=r"(r) : "r"(__float_as_uint(t)), "r"(mask));
     return r;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-// Persistent filter kernel of the windowed engine: CTAs pull units from a global cursor.
+constexpr int UNITS_CONSUMERS = FAST_THREADS;            // 4 filter warps
+constexpr int UNITS_THREADS = FAST_THREADS + 32;         // + 1 copy warp
+
+// Persistent filter kernel of the windowed engine: CTAs pull work units from a global cursor.
 //
-// Inside a unit the pruning goes one level finer than the planned tile list: every warp owns
-// 32*Q CONSECUTIVE queries of the block (a compact blob in the prepared order) and tests the
-// bounding box of every 32-row sub-tile (staged beside the tile by a second bulk copy) against
-// its own query box and its own largest threshold -- a warp-uniform branch, no block barrier.
-// Surviving sub-tiles are scanned with per-candidate hit bits instead of the dense kernel's
-// "running minimum + re-walk" (which pays off only when hits are rare): per (query, candidate)
+// Roles.  Warps 0..3 filter; warp 4 only feeds the shared-memory ring (one lane issues the
+// bulk copies).  Ring slots are handed over with a full / empty mbarrier pair, so the filter
+// warps never meet at a block barrier inside a unit and may run up to STAGES tiles apart --
+// they do very different amounts of work per tile, see below.
+//
+// Pruning goes one level finer than the planned tile list: every filter warp owns 32*Q
+// CONSECUTIVE queries of the block (a compact blob in the prepared order) and tests the
+// bounding box of each 32-row sub-tile (staged beside the tile by a second bulk copy) against
+// its own query box and its own largest threshold -- a warp-uniform branch.  Surviving
+// sub-tiles are scanned with per-candidate hit bits instead of the dense kernel's "running
+// minimum + re-walk" (which pays off only when hits are rare).  Per (query, candidate):
 //     DP/2 FADD2 + ~DP/2 FMNMX   the distance,
 //     1 FADD (m - thr)           its sign is the hit bit,
-//     1 SHF                      funnel-shifts the bit into the slot's 32-bit mask,
-// then the lanes pop their hit bits in lock step and insert into their sorted lists.
+//     1 SHF                      funnel-shifts the bit into the slot's 32-bit mask;
+// then the lanes pop their hit bits in lock step.  The per-query lists (shared memory) are
+// UNSORTED: a hit overwrites the current maximum and one sweep over the kcap entries finds the
+// new maximum -- constant cost, whereas a sorted insert shifts most of the list because new
+// hits are usually closer than what the list holds.  Lists are sorted once, when emitted.
 // part_d32 / part_idx: [unit][rank][QB], QB index = position of the query in its block.
-template <int DP, int Q, int STAGES>
-static __global__ void __launch_bounds__(FAST_THREADS)
-knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub_box, int64_t q_begin, int64_t nq,
-                 int kcap, const double* __restrict__ maxabs, int dim, const float* __restrict__ seed_thr,
+template <int DP, int Q, int STAGES, bool HITMASK>
+static __global__ void __launch_bounds__(UNITS_THREADS)
+knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub_box, int64_t n_tiles,
+                 int64_t q_begin, int64_t nq, int kcap, const float* __restrict__ seed_thr,
                  const int2* __restrict__ plan, const int32_t* __restrict__ plan_count,
                  const int32_t* __restrict__ plan_first, const int32_t* __restrict__ unit_first,
                  const int32_t* __restrict__ unit_block, int32_t* __restrict__ meta, float* __restrict__ part_d32,
@@ -551,174 +563,258 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
     float* tiles = reinterpret_cast<float*>(smem_raw);                       // STAGES * SLOT_FLOATS
     float* lst_d = tiles + STAGES * SLOT_FLOATS;                             // kcap * QB
     int32_t* lst_i = reinterpret_cast<int32_t*>(lst_d + (size_t)kcap * QB);  // kcap * QB
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ TileQueueShared sh;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
     __shared__ int s_unit;
-    __shared__ int s_tile[STAGES];  // tile staged in each ring slot
+    __shared__ int s_tile[STAGES];        // tile staged in each ring slot (-1: end of the unit)
+    __shared__ float s_wthr[FAST_THREADS / 32];  // largest threshold of each filter warp
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const Band band = make_band(maxabs, dim);
+    const bool producer = warp == FAST_THREADS / 32;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);                   // the copy lane's arrive (+ transaction bytes)
+            mbar_init(&empty_bar[s], FAST_THREADS / 32);  // one arrive per filter warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int n_units = meta[0], chunk = meta[1];
-    // bulk-copy ring (kernel lifetime): next slot to fill / to consume, tiles in flight, and the
-    // mbarrier phase parity of every slot
-    int issue_slot = 0, consume_slot = 0, in_flight = 0;
-    uint32_t phase_bits = 0u;
-    unsigned long long subtiles_total = 0;   // (warp, sub-tile) scans of this thread's warp
+    // ring state (kernel lifetime, advanced identically by both roles): next slot and the
+    // phase parity to wait for on it.  A fresh mbarrier passes a wait on parity 1, which is
+    // how the copy lane finds every slot free at the start.
+    int slot = 0;
+    uint32_t phase_bits = producer ? 0xffffffffu : 0u;
+    auto advance = [&]() {
+        phase_bits ^= 1u << slot;
+        slot = slot + 1 == STAGES ? 0 : slot + 1;
+    };
+    unsigned long long subtiles_total = 0;  // (warp, sub-tile) scans of this warp
 
     for (;;) {
         if (tid == 0) s_unit = atomicAdd(&meta[2], 1);
-        __syncthreads();
+        __syncthreads();  // (A) the unit is published; the previous one is finished by everybody
         const int u = s_unit;
-        __syncthreads();  // s_unit may be overwritten by the next round only after everyone read it
         if (u >= n_units) break;
         const int64_t qblock = unit_block[u];
         const int first = (u - unit_first[qblock]) * chunk;
         const int count = plan_count[qblock];
         const int last = first + chunk < count ? first + chunk : count;
         const int64_t qb0 = qblock * QB;
+        const int pfirst = plan_first[qblock];
 
+        // ---------------- filter warps: queries, thresholds, warp box, empty lists
         // slot j of this thread = query qb0 + warp*32*Q + j*32 + lane
         float2 q[Q][DP / 2];
-        float thr[Q];
+        float thr[Q];   // insertion threshold: min(seed, current list maximum)
+        float seed[Q];
+        int pmax[Q];    // position of the list's maximum (the entry a hit replaces)
         float wlo[DP], whi[DP];
-#pragma unroll
-        for (int d = 0; d < DP; ++d) { wlo[d] = CUDART_INF_F; whi[d] = -CUDART_INF_F; }
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            const int64_t qi = qb0 + warp * (32 * Q) + j * 32 + lane;
-            const bool in = qi < nq;
-            load_row<DP>(shadow + (q_begin + (in ? qi : 0)) * DP, q[j]);
-            const float s = in ? seed_thr[qi] : -1.0f;
-            thr[j] = s < 0.0f ? -1.0f : s;  // deferred / dead slots never insert
-            if (thr[j] >= 0.0f) {
-#pragma unroll
-                for (int h = 0; h < DP / 2; ++h) {
-                    wlo[2 * h] = fminf(wlo[2 * h], q[j][h].x);         whi[2 * h] = fmaxf(whi[2 * h], q[j][h].x);
-                    wlo[2 * h + 1] = fminf(wlo[2 * h + 1], q[j][h].y); whi[2 * h + 1] = fmaxf(whi[2 * h + 1], q[j][h].y);
-                }
-            }
-        }
-#pragma unroll
-        for (int d = 0; d < DP; ++d)
-            for (int off = 16; off > 0; off >>= 1) {
-                wlo[d] = fminf(wlo[d], __shfl_xor_sync(0xffffffffu, wlo[d], off));
-                whi[d] = fmaxf(whi[d], __shfl_xor_sync(0xffffffffu, whi[d], off));
-            }
-        for (int r = 0; r < kcap; ++r)
-#pragma unroll
-            for (int j = 0; j < Q; ++j) {
-                lst_d[(size_t)r * QB + j * FAST_THREADS + tid] = CUDART_INF_F;
-                lst_i[(size_t)r * QB + j * FAST_THREADS + tid] = -1;
-            }
-        auto insert = [&](int j, float m, int32_t idx) -> float {
-            const int col = j * FAST_THREADS + tid;
-            int r = kcap - 1;
-            while (r > 0 && lst_d[(size_t)(r - 1) * QB + col] > m) {
-                lst_d[(size_t)r * QB + col] = lst_d[(size_t)(r - 1) * QB + col];
-                lst_i[(size_t)r * QB + col] = lst_i[(size_t)(r - 1) * QB + col];
-                --r;
-            }
-            lst_d[(size_t)r * QB + col] = m;
-            lst_i[(size_t)r * QB + col] = idx;
-            return lst_d[(size_t)(kcap - 1) * QB + col];
-        };
-        // largest threshold of the warp (insertion needs m < thr, and the box gap is a lower
-        // bound of every computed m: a sub-tile with gap >= wthr cannot change any list)
-        float wthr;
+        float wthr = -1.0f;
         auto warp_refresh = [&]() {
             float v = -1.0f;
 #pragma unroll
             for (int j = 0; j < Q; ++j) v = fmaxf(v, thr[j]);
             for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
             wthr = v;
+            if (lane == 0) *reinterpret_cast<volatile float*>(&s_wthr[warp]) = v;
         };
-        warp_refresh();
-        float R;  // block radius: decides which planned tiles are fetched at all
-        auto refresh = [&]() { R = block_max(wthr, sh); };
-        refresh();
-
-        const int2* lst = plan + plan_first[qblock];
-        int next = first, tiles_done = 0;
-        for (;;) {
-            while (in_flight < STAGES && next < last) {
-                const int2 e = lst[next++];
-                if (!(__int_as_float(e.y) < R)) continue;
-                if (tid == 0) {
-                    float* dst = tiles + (size_t)issue_slot * SLOT_FLOATS;
-                    s_tile[issue_slot] = e.x;  // published by the mbarrier (release on arrive, acquire on wait)
-                    mbar_expect_tx(&full_bar[issue_slot], SLOT_FLOATS * 4);
-                    bulk_g2s(dst, shadow + (int64_t)e.x * TILE_FLOATS, TILE_FLOATS * 4, &full_bar[issue_slot]);
-                    bulk_g2s(dst + TILE_FLOATS, sub_box + (int64_t)e.x * BOX_FLOATS, BOX_FLOATS * 4,
-                             &full_bar[issue_slot]);
-                }
-                issue_slot = issue_slot + 1 == STAGES ? 0 : issue_slot + 1;
-                ++in_flight;
-            }
-            if (in_flight == 0) break;
-            const int slot = consume_slot;
-            mbar_wait(&full_bar[slot], (phase_bits >> slot) & 1u);
-            phase_bits ^= 1u << slot;
-            consume_slot = consume_slot + 1 == STAGES ? 0 : consume_slot + 1;
-            const int64_t t = s_tile[slot];
-            const float* tile = tiles + (size_t)slot * SLOT_FLOATS;
-            const float2* boxes = reinterpret_cast<const float2*>(tile + TILE_FLOATS);
-            const int64_t tile_base = t * FAST_TILE;
-#pragma unroll 1
-            for (int sb = 0; sb < FAST_NSUB; ++sb) {
-                float gap = 0.0f;
+        if (!producer) {
 #pragma unroll
-                for (int d = 0; d < DP; ++d) {
-                    const float2 bx = boxes[sb * DP + d];
-                    gap = fmaxf(gap, fmaxf(bx.x - whi[d], wlo[d] - bx.y));
-                }
-                if (!(gap < wthr)) continue;  // warp-uniform
-                ++subtiles_total;
-                const float* rows = tile + sb * FAST_SUB * DP;
-                uint32_t mask[Q];
+            for (int d = 0; d < DP; ++d) { wlo[d] = CUDART_INF_F; whi[d] = -CUDART_INF_F; }
 #pragma unroll
-                for (int j = 0; j < Q; ++j) mask[j] = 0u;
-#pragma unroll 4
-                for (int c = 0; c < FAST_SUB; c += 2) {
-                    float2 ca[DP / 2], cb[DP / 2];
-                    load_two_rows<DP>(rows + c * DP, ca, cb);
+            for (int j = 0; j < Q; ++j) {
+                const int64_t qi = qb0 + warp * (32 * Q) + j * 32 + lane;
+                const bool in = qi < nq;
+                load_row<DP>(shadow + (q_begin + (in ? qi : 0)) * DP, q[j]);
+                const float s = in ? seed_thr[qi] : -1.0f;
+                seed[j] = s < 0.0f ? -1.0f : s;  // deferred / dead slots never insert
+                thr[j] = seed[j];
+                pmax[j] = 0;
+                if (thr[j] >= 0.0f) {
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        mask[j] = push_sign(mask[j], cheb32<DP>(q[j], ca) - thr[j]);
-                        mask[j] = push_sign(mask[j], cheb32<DP>(q[j], cb) - thr[j]);
+                    for (int h = 0; h < DP / 2; ++h) {
+                        wlo[2 * h] = fminf(wlo[2 * h], q[j][h].x);         whi[2 * h] = fmaxf(whi[2 * h], q[j][h].x);
+                        wlo[2 * h + 1] = fminf(wlo[2 * h + 1], q[j][h].y); whi[2 * h + 1] = fmaxf(whi[2 * h + 1], q[j][h].y);
                     }
                 }
-                // candidate c of the sub-tile sits at bit 31 - c
-                bool changed = false;
+            }
+#pragma unroll
+            for (int d = 0; d < DP; ++d)
+                for (int off = 16; off > 0; off >>= 1) {
+                    wlo[d] = fminf(wlo[d], __shfl_xor_sync(0xffffffffu, wlo[d], off));
+                    whi[d] = fmaxf(whi[d], __shfl_xor_sync(0xffffffffu, whi[d], off));
+                }
+            for (int r = 0; r < kcap; ++r)
 #pragma unroll
                 for (int j = 0; j < Q; ++j) {
-                    uint32_t mk = mask[j];
-                    while (mk) {
-                        const int c = __clz(mk);
-                        mk &= ~(0x80000000u >> c);
-                        float2 cc[DP / 2];
-                        load_row<DP>(rows + c * DP, cc);
-                        const float m = cheb32<DP>(q[j], cc);
-                        if (m < thr[j]) thr[j] = insert(j, m, (int32_t)(tile_base + sb * FAST_SUB + c));
-                        changed = true;
-                    }
+                    lst_d[(size_t)r * QB + j * FAST_THREADS + tid] = CUDART_INF_F;
+                    lst_i[(size_t)r * QB + j * FAST_THREADS + tid] = -1;
                 }
-                if (__any_sync(0xffffffffu, changed)) warp_refresh();
+            warp_refresh();
+        }
+        __syncthreads();  // (B) s_wthr is set; s_unit has been read by everybody
+
+        if (producer) {
+            // ---------------- copy warp: stream the unit's tiles, then an end marker
+            if (lane == 0) {
+                const int2* lst = plan + (pfirst < 0 ? 0 : pfirst);
+                const int64_t own = (q_begin + min(qb0 + QB / 2, nq - 1)) / FAST_TILE;  // as in the planning pass
+                for (int next = first; next <= last; ++next) {
+                    int tile = -1;
+                    if (next < last) {
+                        if (pfirst < 0) {  // implicit list: every tile, in walk order
+                            tile = (int)walk_tile(next, own, n_tiles);
+                        } else {
+                            const int2 e = lst[next];
+                            float R = -1.0f;  // the block's current radius (thresholds only shrink)
+#pragma unroll
+                            for (int w = 0; w < FAST_THREADS / 32; ++w)
+                                R = fmaxf(R, *reinterpret_cast<volatile float*>(&s_wthr[w]));
+                            if (!(__int_as_float(e.y) < R)) continue;
+                            tile = e.x;
+                        }
+                    }
+                    mbar_wait(&empty_bar[slot], (phase_bits >> slot) & 1u);
+                    *reinterpret_cast<volatile int*>(&s_tile[slot]) = tile;  // published by the mbarrier below
+                    if (tile >= 0) {
+                        float* dst = tiles + (size_t)slot * SLOT_FLOATS;
+                        mbar_expect_tx(&full_bar[slot], SLOT_FLOATS * 4);
+                        bulk_g2s(dst, shadow + (int64_t)tile * TILE_FLOATS, TILE_FLOATS * 4, &full_bar[slot]);
+                        bulk_g2s(dst + TILE_FLOATS, sub_box + (int64_t)tile * BOX_FLOATS, BOX_FLOATS * 4, &full_bar[slot]);
+                    } else {
+                        mbar_arrive(&full_bar[slot]);
+                    }
+                    advance();
+                }
             }
-            __syncthreads();  // tile consumed: its slot may be refilled
-            --in_flight;
-            ++tiles_done;
-            if ((tiles_done & 3) == 0) refresh();
+            // the other lanes carry the same ring state forward
+            {
+                const int s0 = __shfl_sync(0xffffffffu, slot, 0);
+                const uint32_t p0 = __shfl_sync(0xffffffffu, phase_bits, 0);
+                slot = s0;
+                phase_bits = p0;
+            }
+            continue;
         }
 
-        // emit this unit's lists (ascending)
+        // ---------------- filter warps
+        auto insert = [&](int j, float m, int32_t idx) {
+            const int col = j * FAST_THREADS + tid;
+            lst_d[(size_t)pmax[j] * QB + col] = m;
+            lst_i[(size_t)pmax[j] * QB + col] = idx;
+            float mx = -1.0f;
+            int p = 0;
+#pragma unroll 3
+            for (int r = 0; r < kcap; ++r) {
+                const float v = lst_d[(size_t)r * QB + col];
+                if (v > mx) { mx = v; p = r; }
+            }
+            pmax[j] = p;
+            thr[j] = fminf(seed[j], mx);
+        };
+        for (;;) {
+            mbar_wait(&full_bar[slot], (phase_bits >> slot) & 1u);
+            const int t = *reinterpret_cast<volatile int*>(&s_tile[slot]);
+            if (t >= 0) {
+                const float* tile = tiles + (size_t)slot * SLOT_FLOATS;
+                const float2* boxes = reinterpret_cast<const float2*>(tile + TILE_FLOATS);
+                const int64_t tile_base = (int64_t)t * FAST_TILE;
+#pragma unroll 1
+                for (int sb = 0; sb < FAST_NSUB; ++sb) {
+                    float gap = 0.0f;
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) {
+                        const float2 bx = boxes[sb * DP + d];
+                        gap = fmaxf(gap, fmaxf(bx.x - whi[d], wlo[d] - bx.y));
+                    }
+                    // insertion needs m < thr and the box gap is a lower bound of every computed m
+                    if (!(gap < wthr)) continue;  // warp-uniform
+                    ++subtiles_total;
+                    const float* rows = tile + sb * FAST_SUB * DP;
+                    bool changed = false;
+                    if constexpr (HITMASK) {
+                        // few dimensions: the culling is sharp, most scanned sub-tiles hold hits
+                        uint32_t mask[Q];
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) mask[j] = 0u;
+#pragma unroll 4
+                        for (int c = 0; c < FAST_SUB; c += 2) {
+                            float2 ca[DP / 2], cb[DP / 2];
+                            load_two_rows<DP>(rows + c * DP, ca, cb);
+#pragma unroll
+                            for (int j = 0; j < Q; ++j) {
+                                mask[j] = push_sign(mask[j], cheb32<DP>(q[j], ca) - thr[j]);
+                                mask[j] = push_sign(mask[j], cheb32<DP>(q[j], cb) - thr[j]);
+                            }
+                        }
+                        // candidate c of the sub-tile sits at bit 31 - c
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) {
+                            uint32_t mk = mask[j];
+                            while (mk) {
+                                const int c = __clz(mk);
+                                mk &= ~(0x80000000u >> c);
+                                float2 cc[DP / 2];
+                                load_row<DP>(rows + c * DP, cc);
+                                const float m = cheb32<DP>(q[j], cc);
+                                if (m < thr[j]) insert(j, m, (int32_t)(tile_base + sb * FAST_SUB + c));
+                                changed = true;
+                            }
+                        }
+                    } else {
+                        // many dimensions: boxes overlap, hits are rare among the scanned pairs --
+                        // keep only the running minimum (half a FMNMX3 per pair) and walk the
+                        // sub-tile again for the slots that saw something closer
+                        float mrun[Q];
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) mrun[j] = CUDART_INF_F;
+#pragma unroll 4
+                        for (int c = 0; c < FAST_SUB; c += 2) {
+                            float2 ca[DP / 2], cb[DP / 2];
+                            load_two_rows<DP>(rows + c * DP, ca, cb);
+#pragma unroll
+                            for (int j = 0; j < Q; ++j)
+                                mrun[j] = fminf(fminf(mrun[j], cheb32<DP>(q[j], ca)), cheb32<DP>(q[j], cb));
+                        }
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) {
+                            if (mrun[j] < thr[j]) {
+#pragma unroll 1
+                                for (int c = 0; c < FAST_SUB; ++c) {
+                                    float2 cc[DP / 2];
+                                    load_row<DP>(rows + c * DP, cc);
+                                    const float m = cheb32<DP>(q[j], cc);
+                                    if (m < thr[j]) insert(j, m, (int32_t)(tile_base + sb * FAST_SUB + c));
+                                }
+                                changed = true;
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, changed)) warp_refresh();
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);  // this warp is done with the slot
+            advance();
+            if (t < 0) break;
+        }
+
+        // ---------------- sort each list (ascending) and emit it
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const int col = j * FAST_THREADS + tid;
+            for (int a = 1; a < kcap; ++a) {
+                const float d = lst_d[(size_t)a * QB + col];
+                const int32_t i = lst_i[(size_t)a * QB + col];
+                int b = a - 1;
+                while (b >= 0 && lst_d[(size_t)b * QB + col] > d) {
+                    lst_d[(size_t)(b + 1) * QB + col] = lst_d[(size_t)b * QB + col];
+                    lst_i[(size_t)(b + 1) * QB + col] = lst_i[(size_t)b * QB + col];
+                    --b;
+                }
+                lst_d[(size_t)(b + 1) * QB + col] = d;
+                lst_i[(size_t)(b + 1) * QB + col] = i;
+            }
             const int lq = warp * (32 * Q) + j * 32 + lane;
             for (int r = 0; r < kcap; ++r) {
                 const int64_t o = ((int64_t)u * kcap + r) * QB + lq;
@@ -726,9 +822,8 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
                 part_idx[o] = lst_i[(size_t)r * QB + col];
             }
         }
-        __syncthreads();  // lists are reset by the next unit
     }
-    if (lane == 0 && pair_counter && subtiles_total)
+    if (!producer && lane == 0 && pair_counter && subtiles_total)
         atomicAdd(pair_counter, subtiles_total * (unsigned long long)(FAST_SUB * 32 * Q));
 }
 

@@ -55,7 +55,20 @@ struct CountF32Args {
     unsigned long long* tile_counter;
     cudaStream_t st;
 };
+// planning / work-unit buffers of the single-subspace windowed pass (see fast_count_units.cuh)
+struct CountUnitsArgs {
+    const float* sub_box;
+    void* plan;            // int2[plan_capacity]
+    int64_t plan_capacity;
+    int32_t* plan_count;   // [n_query_blocks]
+    int32_t* plan_first;   // [n_query_blocks]
+    int32_t* unit_first;   // [n_query_blocks + 1]
+    int32_t* unit_block;   // [max_units]
+    int32_t* unit_meta;    // [4]
+    int64_t max_units;
+};
 int count_f32_queries_per_block(int dim_padded);
+int launch_count_full(int dim_padded, const CountF32Args& a, const CountUnitsArgs& w);  // one subspace = all coordinates
 int launch_count_pair(int dx, int dy, const CountF32Args& a);          // subspaces x, y
 int launch_count_cmi(int dx, int dy, int dz, const CountF32Args& a);   // subspaces z, xz, yz
 int launch_count_loo(int d, const CountF32Args& a);                    // all leave-one-out subspaces

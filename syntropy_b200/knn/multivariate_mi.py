@@ -25,7 +25,7 @@ def total_correlation_1(data, k, idxs=None):
     data = np.asarray(data)
     idxs_ = check_idxs(idxs, data)
     m = len(idxs_)
-    rows = data[idxs_, :]
+    rows = E.select_rows(data, idxs_)
 
     def program(psi_k, psi_n):
         prog = E.PsiProgram(init=psi_k + (m - 1) * psi_n)
@@ -42,7 +42,7 @@ def total_correlation_2(data, k, idxs=None):
     data = np.asarray(data)
     idxs_ = check_idxs(idxs, data)
     m = len(idxs_)
-    rows = data[idxs_, :]
+    rows = E.select_rows(data, idxs_)
 
     def program(psi_k, psi_n):
         prog = E.PsiProgram(init=psi_k - ((m - 1) / k) + ((m - 1) * psi_n))
@@ -64,7 +64,7 @@ def dual_total_correlation(data, k, idxs=None):
     data = np.asarray(data)
     idxs_ = check_idxs(idxs, data)
     m = len(idxs_)
-    rows = data[idxs_, :]
+    rows = E.select_rows(data, idxs_)
 
     def program(psi_k, psi_n):
         prog = E.PsiProgram(init=psi_k - psi_n, psi_n=psi_n, scale=float(m - 1))
@@ -89,7 +89,7 @@ def _row_slices(data, idxs_):
     """The reference selects the small marginal by the SLICE ``idxs_[d]:idxs_[d]+1`` and the
     big one by fancy index (knn/multivariate_mi.py:317,321,398,402); both pick the same
     rows for non-negative indices, which is what the joint selection below relies on."""
-    return data[idxs_, :]
+    return E.select_rows(data, idxs_)
 
 
 def s_information(data, k, idxs=None):

@@ -57,7 +57,7 @@ def mutual_information_1(idxs_x, idxs_y, k, data, p=np.inf):
     require_chebyshev(p)
     data = np.asarray(data)
     idxs_x, idxs_y = tuple(idxs_x), tuple(idxs_y)
-    rows = data[idxs_x + idxs_y, :]
+    rows = E.select_rows(data, idxs_x + idxs_y)
     ptw, avg = E.ksg1_family(rows, k, _xy_masks(idxs_x, idxs_y), mi1_program)
     return ptw.reshape(1, -1), avg
 
@@ -70,7 +70,7 @@ def mutual_information_2(idxs_x, idxs_y, k, data, p=np.inf):
     require_chebyshev(p)
     data = np.asarray(data)
     idxs_x, idxs_y = tuple(idxs_x), tuple(idxs_y)
-    rows = data[idxs_x + idxs_y, :]
+    rows = E.select_rows(data, idxs_x + idxs_y)
 
     def program(psi_k, psi_n):
         prog = E.PsiProgram(init=psi_k - (1 / k) + psi_n)
@@ -88,7 +88,7 @@ def conditional_mutual_information(idxs_x, idxs_y, idxs_z, k, data, p=np.inf):
     require_chebyshev(p)
     data = np.asarray(data)
     idxs_x, idxs_y, idxs_z = tuple(idxs_x), tuple(idxs_y), tuple(idxs_z)
-    rows = data[idxs_x + idxs_y + idxs_z, :]
+    rows = E.select_rows(data, idxs_x + idxs_y + idxs_z)
     dx, dy, dz = len(idxs_x), len(idxs_y), len(idxs_z)
     x = list(range(dx))
     y = list(range(dx, dx + dy))

@@ -53,7 +53,7 @@ def close(a, b):
     assert ok.all(), f"max abs diff {np.nanmax(np.abs(a - b)[~(both_inf | both_nan)])}"
 
 
-def radius_and_counts(E, rows, k, subspaces, strict=True):
+def radius_and_counts(E, rows, k, subspaces, strict=True, fused=False):
     import torch
 
     pts = E.to_device_points(rows)
@@ -62,6 +62,9 @@ def radius_and_counts(E, rows, k, subspaces, strict=True):
     if E.config.engine == "exact" or dim > 8:
         eps = E.knn_radius(pts, k + 1, 0, n)
         counts = E.count_subspaces(pts, masks, eps, 0, n, strict=strict)
+    elif strict and not fused:
+        # the product path: joint-order passes + low-dimensional marginals in their own order
+        eps, counts, _ = E.radius_and_counts(pts, k, masks)
     else:
         windowed = E.config.engine == "windowed"
         prep = E.PreparedSet(pts, E.config.primary)
@@ -370,3 +373,18 @@ def test_engines_agree_bitwise_on_random_configs():
                 assert np.array_equal(got[key][1], got[("exact", -1)][1]), (dim, key, "counts")
     finally:
         E.config.engine, E.config.primary = old, old_primary
+
+
+def test_own_order_counts_equal_fused_joint_order_counts(E):
+    """Every multi-dimensional marginal counted in a prepared set of its own coordinates gives
+    the counts of the fused joint-order pass (and of the exact engine, tested above)."""
+    for name, n in (("c3", 6000), ("c5", 5000)):
+        data, call = workloads.CONFIGS[name](n=n, seed=5)
+        if name == "c3":
+            subs = [(4, 5), (0, 1, 4, 5), (2, 3, 4, 5)]
+        else:
+            subs = [(0, 1, 2, 3), (4, 5, 6, 7)]
+        eps_a, counts_a = radius_and_counts(E, data, call["k"], subs)
+        eps_b, counts_b = radius_and_counts(E, data, call["k"], subs, fused=True)
+        assert np.array_equal(eps_a, eps_b)
+        assert np.array_equal(counts_a, counts_b)
