@@ -51,6 +51,45 @@ KERNEL_BEGIN(k_fmnmx)
 asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
 KERNEL_END
 
+// 3-input max (FMNMX3)
+KERNEL_BEGIN(k_fmnmx3)
+asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(a[(i + 1) % CH]));
+KERNEL_END
+
+// 2-input max with |.| on both operands
+KERNEL_BEGIN(k_fmnmx_abs)
+asm volatile("{ .reg .f32 x, y; abs.f32 x, %0; abs.f32 y, %1; max.f32 %0, x, y; }" : "+f"(a[i]) : "f"(b));
+KERNEL_END
+
+// FSET alone (1.0 / 0.0)
+KERNEL_BEGIN(k_fset)
+asm volatile("set.lt.f32.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+KERNEL_END
+
+// funnel shift
+KERNEL_BEGIN(k_shf)
+asm volatile("shf.l.clamp.b32 %0, %1, %0, 1;" : "+r"(cnt[i]) : "r"(__float_as_int(b)));
+a[i] += 0.f;
+KERNEL_END
+
+// FADD (FMA pipe) + FMNMX (ALU pipe) interleaved: do they overlap?
+KERNEL_BEGIN(k_fadd_fmnmx)
+asm volatile("add.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+asm volatile("max.f32 %0, %0, %1;" : "+f"(a[(i + 8) % CH]) : "f"(b));
+KERNEL_END
+
+// FMNMX + FSET (both ALU?)
+KERNEL_BEGIN(k_fmnmx_fset)
+asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+asm volatile("set.lt.f32.f32 %0, %0, %1;" : "+f"(a[(i + 8) % CH]) : "f"(b));
+KERNEL_END
+
+// integer add (which pipe?) next to FMNMX
+KERNEL_BEGIN(k_iadd_fmnmx)
+asm volatile("add.s32 %0, %0, %1;" : "+r"(cnt[i]) : "r"(__float_as_int(b)));
+asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+KERNEL_END
+
 // |a - b| then max: expect FADD + FMNMX(|.|)
 KERNEL_BEGIN(k_sub_absmax)
 asm volatile("{ .reg .f32 t; sub.f32 t, %0, %1; abs.f32 t, t; max.f32 %0, %0, t; }" : "+f"(a[i]) : "f"(b));
@@ -198,6 +237,13 @@ int main() {
     cudaMalloc(&out, sizeof(float) * sms * THREADS);
     cudaMalloc(&cyc, sizeof(long long) * sms);
     run("fadd", k_fadd, 1, sms, out, cyc);
+    run("fmnmx3", k_fmnmx3, 1, sms, out, cyc);
+    run("fmnmx |a|,|b|", k_fmnmx_abs, 1, sms, out, cyc);
+    run("fset", k_fset, 1, sms, out, cyc);
+    run("shf", k_shf, 1, sms, out, cyc);
+    run("fadd+fmnmx", k_fadd_fmnmx, 2, sms, out, cyc);
+    run("fmnmx+fset", k_fmnmx_fset, 2, sms, out, cyc);
+    run("iadd+fmnmx", k_iadd_fmnmx, 2, sms, out, cyc);
     run("ffma", k_ffma, 1, sms, out, cyc);
     run("fmnmx", k_fmnmx, 1, sms, out, cyc);
     run("sub+|max|", k_sub_absmax, 2, sms, out, cyc);

@@ -343,7 +343,8 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
     fill_i32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(d_counts, total, bias);
     KSG_LAUNCHED2();
     KSG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)nq * sizeof(int32_t), st));
-    count_thresholds_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(d_eps, nq, P->maxabs, dim, thresholds);
+    count_thresholds_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(d_eps, q_begin, nq, P->shadow_f32,
+                                                                          P->dim_padded, thresholds);
     KSG_LAUNCHED2();
 
     CountF32Args a;

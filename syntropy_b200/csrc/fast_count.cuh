@@ -44,10 +44,24 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     return r;
 }
 
+// fp32 error bound of a (query, candidate) pair of the count pass, PER QUERY.  With centred
+// values q~, c~ (|q~_d| <= Mq) and a candidate within d of the query, |c~_d| <= Mq + d, so
+//     |d32 - d64| <= 2^-24 (|q~| + |c~| + |d32|) <= 2^-24 (2 Mq + 2 d) (1 + tiny).
+// Using the query's own magnitude instead of the data set's keeps the band narrow where the
+// points are dense (near the centre) even when a few outliers stretch the range.
+__host__ __device__ inline double band_query_f64(double mq, double d) {
+    return 5.9604644775390625e-08 * (2.0 * mq + 2.0 * d) * 1.01 + 1e-37;
+}
+// Mq of the query at `row` of the fp32 shadow (upper bound of max_d |x_d - centre_d|)
+__device__ __forceinline__ double query_maxabs(const float* __restrict__ shadow, int64_t row, int dim_padded) {
+    float m = 0.0f;
+    for (int d = 0; d < dim_padded; ++d) m = fmaxf(m, fabsf(shadow[row * dim_padded + d]));
+    return (double)m * (1.0 + 1e-6) + 1e-300;
+}
 // The filter threshold for a query: the smallest fp32 >= eps + delta(eps), one ulp up.
-__device__ __forceinline__ float count_threshold(double eps, double mmax) {
+__device__ __forceinline__ float count_threshold(double eps, double mq) {
     if (!(eps < CUDART_INF)) return CUDART_INF_F;
-    const float t = __double2float_ru(eps + band_f64(mmax, eps));
+    const float t = __double2float_ru(eps + band_query_f64(mq, eps));
     return nextafterf(t, CUDART_INF_F);
 }
 
@@ -266,17 +280,16 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
 }
 
 // thresholds[qi] = count_threshold(eps[qi]);  counts initialised to `bias`
-static __global__ void count_thresholds_kernel(const double* __restrict__ eps, int64_t nq, const double* __restrict__ maxabs,
-                                        int dim, float* __restrict__ thresholds) {
+static __global__ void count_thresholds_kernel(const double* __restrict__ eps, int64_t q_begin, int64_t nq,
+                                        const float* __restrict__ shadow, int dim_padded,
+                                        float* __restrict__ thresholds) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
-    double mmax = 0.0;
-    for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
-    thresholds[qi] = count_threshold(eps[qi], mmax);
+    thresholds[qi] = count_threshold(eps[qi], query_maxabs(shadow, q_begin + qi, dim_padded));
 }
 
 // ---------------------------------------------------------------- exact resolution of the band
-constexpr int FIX_CAP = 48;  // band candidates examined per query and coordinate
+constexpr int FIX_CAP = 512;  // band candidates examined per query, coordinate and side
 
 __device__ __forceinline__ int64_t lower_bound_f64(const double* __restrict__ v, int64_t n, double x) {
     int64_t lo = 0, hi = n;  // first index with v[i] >= x
@@ -311,12 +324,10 @@ count_fix_kernel(const double* __restrict__ sorted, int64_t ld, const float* __r
     const double e = eps[qi];
     if (!(e < CUDART_INF)) return;  // infinite radius: the filter is exact (everything finite is inside)
     const float T = thresholds[qi];
-    double mmax = 0.0;
     uint32_t used = 0;
-    for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
     for (int s = 0; s < n_sub; ++s) used |= masks.m[s];
-    const double w = 4.0 * band_f64(mmax, e);
     const int64_t row_q = q_begin + qi;
+    const double w = 4.0 * band_query_f64(query_maxabs(shadow, row_q, dim_padded), e);
 
     double xq[KSG_MAX_DIM];
     for (int d = 0; d < dim; ++d) xq[d] = sorted[(int64_t)d * ld + row_q];

@@ -93,7 +93,12 @@ def main():
             if rep > 0 and (best is None or wall < best[0]):
                 pairs = None
                 if preps is not None:
-                    pairs = (sum(p.pairs_evaluated()[0] for p in preps), sum(p.pairs_evaluated()[1] for p in preps))
+                    # (pairs of the k-NN filter, pairs of the count filters, algorithmic lane-ops of the
+                    #  count filters: a single-subspace pass in d_s coordinates does 2*d_s per pair)
+                    per = [(p.dim, p.pairs_evaluated()) for p in preps]
+                    own_ops = sum(2 * d * pe[1] for d, pe in per[1:])
+                    pairs = (sum(pe[0] for _, pe in per), sum(pe[1] for _, pe in per),
+                             OPS[name][1] * per[0][1][1] + own_ops)
                 best = (wall, ms, pairs)
         wall, ms, tiles = best
         out["stage_ms"] = ms
@@ -106,7 +111,7 @@ def main():
             if ms.get("fast_knn"):
                 out["frac_fp_pipe_knn"] = a1 * p1 / (ms["fast_knn"] * 1e-3) / peak
             if ms.get("fast_count"):
-                out["frac_fp_pipe_count"] = a2 * p2 / (ms["fast_count"] * 1e-3) / peak
+                out["frac_fp_pipe_count"] = float(tiles[2]) / (ms["fast_count"] * 1e-3) / peak
         else:
             out["frac_fp_pipe_knn"] = a1 * float(n) * n / (ms["knn_radius"] * 1e-3) / peak
             out["frac_fp_pipe_count"] = a2 * float(n) * n / (ms["count_subspaces"] * 1e-3) / peak
