@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Multi-GPU check (run under torchrun, one rank per GPU): every estimator family returns, on
+every rank, exactly what a single rank computes (sharding off) -- pointwise bit for bit.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tools/check_multi_gpu.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as td  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = td.get_rank(), td.get_world_size()
+    from syntropy_b200 import dist, knn, workloads
+
+    cases = []
+    d, c = workloads.c1_readme_mi(n=20_011, seed=1)
+    cases.append(("mi 1D;1D", lambda: knn.mutual_information(c["idxs_x"], c["idxs_y"], c["k"], d)))
+    d3, c3 = workloads.c3_cmi(n=30_007, seed=2)
+    cases.append(("cmi 2D;2D|2D (own-order marginals)", lambda: knn.conditional_mutual_information(
+        c3["idxs_x"], c3["idxs_y"], c3["idxs_z"], c3["k"], d3)))
+    d4, c4 = workloads.c4_oinfo(n=12_345, seed=3)
+    cases.append(("o-information 8 vars", lambda: knn.o_information(d4, c4["k"])))
+    cases.append(("total correlation 8 vars", lambda: knn.total_correlation(d4, c4["k"])))
+    d5, c5 = workloads.c5_info_rate(n=25_000, seed=4)
+    cases.append(("mi 4D;4D (own-order marginals)", lambda: knn.mutual_information(
+        c5["idxs_x"], c5["idxs_y"], c5["k"], d5)))
+    cases.append(("entropy 3D", lambda: knn.differential_entropy(d4, 3, idxs=(0, 1, 2))))
+    series = workloads.c5_series(n=6_000, seed=5)
+    ok = True
+    for name, fn in cases:
+        dist.configure("auto")
+        ptw_s, avg_s = fn()
+        dist.configure("off")
+        ptw_1, avg_1 = fn()
+        same = bool(np.array_equal(ptw_s, ptw_1) and avg_s == avg_1)
+        ok = ok and same
+        if rank == 0:
+            print(f"{name}: sharded x{world} == single rank: {same} (avg {avg_s!r})", flush=True)
+    dist.configure("auto")
+    se_s = knn.sample_entropy((0,), series)
+    dist.configure("off")
+    se_1 = knn.sample_entropy((0,), series)
+    ok = ok and se_s == se_1
+    if rank == 0:
+        print(f"sample_entropy: sharded == single rank: {se_s == se_1} ({se_s!r})", flush=True)
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    td.all_reduce(flag)
+    td.destroy_process_group()
+    if int(flag.item()):
+        raise SystemExit("multi-GPU results differ from single-rank results")
+    if rank == 0:
+        print("MULTI_GPU_OK")
+
+
+if __name__ == "__main__":
+    main()
