@@ -305,6 +305,11 @@ int ksg_scatter_f64(const double* d_src, const int32_t* d_perm, int64_t n, doubl
 int ksg_scatter_i32(const int32_t* d_src, const int32_t* d_perm, int64_t n, int32_t* d_dst, void* stream);
 int ksg_gather_f64(const double* d_src, const int32_t* d_perm, int64_t n, double* d_dst, void* stream);
 
+/* d_out[0] += sum of n int32 counts (integer, order-independent).  With ksg_prepare +
+ * ksg_fast_count(one subspace, strict = 0, constant radius) on the template matrix this is the
+ * windowed form of cKDTree.count_neighbors(self, r) (syntropy/knn/temporal.py:71-72). */
+int ksg_sum_i32(const int32_t* d_values, int64_t n, unsigned long long* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,7 @@ SIGNATURES = {
     "ksg_scatter_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_scatter_i32": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_gather_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "ksg_sum_i32": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_vp]),
 }
 
 _lib = None

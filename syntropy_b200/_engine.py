@@ -653,8 +653,38 @@ def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
     return _finish(Pointwise(ptw), n, flag)
 
 
+def _self_pair_count(templates: torch.Tensor, r: float) -> torch.Tensor:
+    """Ordered pairs (i, j), self pairs included, of the columns of ``templates`` (d, N) within
+    max-norm distance <= r: this rank's share, as a 1-element int64 tensor.  The template matrix
+    is prepared in its own space-filling order and counted by the single-subspace windowed pass
+    (closed ball, exact)."""
+    lib = _cabi.load()
+    d, nt = templates.shape
+    prep = PreparedSet(templates, -1)
+    q0, q1 = _dist.my_slice(nt)
+    out = torch.zeros(1, dtype=torch.int64, device=templates.device)
+    if q1 > q0:
+        eps = torch.full((q1 - q0,), float(r), dtype=torch.float64, device=templates.device)
+        counts = fast_counts(prep, [(1 << d) - 1] if d > 1 else [1], eps, q0, q1, config.engine == "windowed",
+                             strict=False, bias=0)
+        _cabi.check(lib.ksg_sum_i32(_ptr(counts), counts.numel(), _ptr(out), _stream()), "ksg_sum_i32")
+    return out
+
+
+def _templates(series: torch.Tensor, width: int, nt: int) -> torch.Tensor:
+    """(width, nt) matrix of the length-``width`` sliding windows of a device series."""
+    return torch.stack([series[w:w + nt] for w in range(width)]).contiguous()
+
+
 def pair_counts(x: np.ndarray, y: np.ndarray, m: int, r: float):
-    """(small, big) closed-ball ordered pair counts of the m / (m+1) templates."""
+    """(small, big) closed-ball ordered pair counts of the m / (m+1) templates
+    (reference: cKDTree.count_neighbors, knn/temporal.py:71-72,142-143).
+
+    Fast engines, m + 1 <= 8: every count is a self pair count of a prepared template set.  For
+    two different series the cross count follows from three self counts,
+    ``XY = (UU - XX - YY) / 2`` with U the union of both template sets (the predicate is
+    symmetric and all counts are integers, so this is exact).  Otherwise: the dense float64
+    kernel."""
     dev = require_cuda()
     xs = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
     ys = xs if y is x else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).to(dev)
@@ -662,6 +692,30 @@ def pair_counts(x: np.ndarray, y: np.ndarray, m: int, r: float):
     if nt <= 0:
         raise ValueError("series shorter than the template length")
     flag = check_finite(xs) | check_finite(ys)
+    if config.engine != "exact" and m + 1 <= 8 and np.isfinite(r) and r >= 0:
+        if int(flag.item()):
+            raise ValueError("data must be finite, check for nan or inf values")
+        res = []
+        for width in (m, m + 1):
+            tx = _templates(xs, width, nt)
+            if ys is xs:
+                res.append(_self_pair_count(tx, r))
+            else:
+                ty = _templates(ys, width, nt)
+                uu = _self_pair_count(torch.cat([tx, ty], dim=1).contiguous(), r)
+                res.append(uu - _self_pair_count(tx, r) - _self_pair_count(ty, r))
+        out = _dist.sum_counts(torch.cat(res))
+        if ys is not xs:
+            out = out // 2
+        host = torch.cat([out, flag.to(torch.int64)]).cpu().numpy()
+        if host[2] != 0:
+            raise ValueError("data must be finite, check for nan or inf values")
+        return int(host[0]), int(host[1])
+    return _pair_counts_dense(xs, ys, nt, m, r, flag)
+
+
+def _pair_counts_dense(xs, ys, nt, m, r, flag):
+    dev = xs.device
     i0, i1 = _dist.my_slice(nt)
     out = torch.zeros(2, dtype=torch.int64, device=dev)
     rc = _cabi.load().ksg_paircount_fixed_radius(_ptr(xs), _ptr(ys), nt, m, float(r), i0, i1, _ptr(out), _stream())

@@ -443,6 +443,16 @@ int ksg_scatter_i32(const int32_t* d_src, const int32_t* d_perm, int64_t n, int3
     return KSG_OK;
 }
 
+int ksg_sum_i32(const int32_t* d_values, int64_t n, unsigned long long* d_out, void* stream) {
+    KSG_REQUIRE(d_values && d_out && n >= 0, "ksg_sum_i32: bad argument");
+    if (n == 0) return KSG_OK;
+    int64_t blocks = ceil_div(n, 256 * 8);
+    if (blocks > 4096) blocks = 4096;
+    sum_i32_kernel<<<(unsigned)blocks, 256, 0, as_stream2(stream)>>>(d_values, n, d_out);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
 int ksg_gather_f64(const double* d_src, const int32_t* d_perm, int64_t n, double* d_dst, void* stream) {
     KSG_REQUIRE(d_src && d_perm && d_dst && n >= 0, "ksg_gather_f64: bad argument");
     if (n == 0) return KSG_OK;

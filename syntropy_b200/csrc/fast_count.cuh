@@ -419,6 +419,22 @@ static __global__ void scatter_f64_kernel(const double* __restrict__ src, const 
     if (i < n) dst[perm[i]] = src[i];
 }
 
+// out[0] += sum of counts (int64), one atomic per block
+static __global__ void __launch_bounds__(256)
+sum_i32_kernel(const int32_t* __restrict__ v, int64_t n, unsigned long long* __restrict__ out) {
+    long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) acc += v[i];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    __shared__ long long part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        atomicAdd(out, (unsigned long long)t);
+    }
+}
+
 static __global__ void scatter_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ perm, int64_t n,
                                    int32_t* __restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -388,3 +388,23 @@ def test_own_order_counts_equal_fused_joint_order_counts(E):
         eps_b, counts_b = radius_and_counts(E, data, call["k"], subs, fused=True)
         assert np.array_equal(eps_a, eps_b)
         assert np.array_equal(counts_a, counts_b)
+
+
+def test_windowed_pair_counts_equal_dense_fp64_pair_counts(E):
+    """sample-entropy pair counts from prepared template sets (self counts; cross counts as
+    (UU - XX - YY) / 2) equal the dense float64 kernel's, also when many distances hit the
+    radius exactly (quantised series, closed ball)."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    n = 40_000
+    x = np.cumsum(rng.standard_normal(n)) * 0.05 + rng.standard_normal(n)
+    y = 0.5 * x + rng.standard_normal(n)
+    xq = np.round(x * 4) / 4  # multiples of 0.25: distances equal to r = 0.5 are common
+    for a, b, m, r in ((x, x, 2, 0.2 * x.std()), (x, y, 2, 0.3), (xq, xq, 2, 0.5), (xq, np.round(y * 4) / 4, 3, 0.5)):
+        got = E.pair_counts(a, a if b is a else b, m, r)
+        xs = torch.from_numpy(a).cuda()
+        ys = xs if b is a else torch.from_numpy(b).cuda()
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        want = E._pair_counts_dense(xs, ys, n - m, m, r, flag)
+        assert got == want
