@@ -188,7 +188,12 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
         while ((1ll << rank_bits) < n) ++rank_bits;
         int bits = 63 / dim;
         if (bits > rank_bits) bits = rank_bits;
-        morton_key_kernel<<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys);
+        switch (dim) {
+#define KSG_MORTON(D) case D: morton_key_kernel<D><<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys); break;
+            KSG_MORTON(1) KSG_MORTON(2) KSG_MORTON(3) KSG_MORTON(4) KSG_MORTON(5) KSG_MORTON(6) KSG_MORTON(7) KSG_MORTON(8)
+#undef KSG_MORTON
+            default: morton_key_kernel<0><<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys);
+        }
         KSG_LAUNCHED2();
         size_t need = L.cub_bytes;
         cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, iota, P.perm, (int)n, 0,

@@ -163,13 +163,13 @@ count_units_kernel(const float* __restrict__ shadow, const float* __restrict__ s
         __syncthreads();  // s_unit has been read by everybody
 
         if (producer) {
-            if (lane == 0) {
-                const int2* lst = plan + (pfirst < 0 ? 0 : pfirst);
-                const int64_t own = (q_begin + min(qb0 + QB / 2, nq - 1)) / FAST_TILE;
-                for (int next = first; next <= last; ++next) {
-                    int tile = -1;
-                    if (next < last) tile = pfirst < 0 ? (int)walk_tile(next, own, n_tiles) : lst[next].x;
-                    mbar_wait(&empty_bar[slot], (phase_bits >> slot) & 1u);
+            const int2* lst = plan + (pfirst < 0 ? 0 : pfirst);
+            const int64_t own = (q_begin + min(qb0 + QB / 2, nq - 1)) / FAST_TILE;
+            for (int next = first; next <= last; ++next) {  // all 32 lanes together; lane 0 issues
+                int tile = -1;
+                if (next < last) tile = pfirst < 0 ? (int)walk_tile(next, own, n_tiles) : lst[next].x;
+                mbar_wait_relaxed(&empty_bar[slot], (phase_bits >> slot) & 1u);
+                if (lane == 0) {
                     *reinterpret_cast<volatile int*>(&s_tile[slot]) = tile;
                     if (tile >= 0) {
                         float* dst = tiles + (size_t)slot * SLOT_FLOATS;
@@ -179,13 +179,10 @@ count_units_kernel(const float* __restrict__ shadow, const float* __restrict__ s
                     } else {
                         mbar_arrive(&full_bar[slot]);
                     }
-                    advance();
                 }
+                __syncwarp();
+                advance();
             }
-            const int s0 = __shfl_sync(0xffffffffu, slot, 0);
-            const uint32_t p0 = __shfl_sync(0xffffffffu, phase_bits, 0);
-            slot = s0;
-            phase_bits = p0;
             continue;
         }
 

@@ -24,11 +24,11 @@ static int launch_knn_dp(const KnnF32Args& a) {
     return KSG_OK;
 }
 
-template <int DP>
-static int launch_plan_dp(const KnnF32Args& a) {
+template <int DP, int KC>
+static int launch_plan_kc(const KnnF32Args& a) {
     constexpr int Q = FastGeom<DP>::Q;
-    auto kern = knn_plan_kernel<DP, Q>;
-    const size_t smem = (size_t)a.kcap * FAST_THREADS * Q * 4;
+    auto kern = knn_plan_kernel<DP, Q, KC>;
+    const size_t smem = KC > 0 ? 0 : (size_t)a.kcap * FAST_THREADS * Q * 4;
     if (smem > 32 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
@@ -71,6 +71,13 @@ static int launch_units_dp(const KnnF32Args& a) {
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_units_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     return KSG_OK;
+}
+
+template <int DP>
+static int launch_plan_dp(const KnnF32Args& a) {
+    if (a.kcap <= 8) return launch_plan_kc<DP, 8>(a);
+    if (a.kcap <= 12) return launch_plan_kc<DP, 12>(a);
+    return launch_plan_kc<DP, 0>(a);
 }
 
 int knn_plan_cap() { return KNN_PLAN_CAP; }

@@ -115,7 +115,7 @@ __device__ __forceinline__ void load_two_rows(const float* __restrict__ row, flo
 // (tile, gap) in walk order.  The filter kernel then streams exactly that list (re-checking each
 // gap against its shrinking radius) with no in-kernel search rounds, and the host side of the ABI
 // launches the blocks longest-list-first so that no heavy block is left for the tail.
-template <int DP, int Q>
+template <int DP, int Q, int KC>  // KC > 0: seed lists of KC entries in registers (kcap <= KC); 0: in shared memory
 static __global__ void __launch_bounds__(FAST_THREADS)
 knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
                 int64_t q_begin, int64_t nq, int kcap, const double* __restrict__ maxabs, int dim,
@@ -148,28 +148,51 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
             blo[2 * h] = fminf(blo[2 * h], q[h].x);         bhi[2 * h] = fmaxf(bhi[2 * h], q[h].x);
             blo[2 * h + 1] = fminf(blo[2 * h + 1], q[h].y); bhi[2 * h + 1] = fmaxf(bhi[2 * h + 1], q[h].y);
         }
-        const int col = j * FAST_THREADS + tid;
-        for (int r = 0; r < kcap; ++r) lst_d[(size_t)r * QB + col] = CUDART_INF_F;
         float thr = CUDART_INF_F;
-#pragma unroll 1
-        for (int off = 1; off <= KNN_SEED_W; ++off)
-#pragma unroll 1
-            for (int sgn = -1; sgn <= 1; sgn += 2) {
-                const int64_t r2 = row + sgn * off;
-                if (r2 < 0 || r2 >= n_rows) continue;
-                float2 cc[DP / 2];
-                load_row<DP>(shadow + r2 * DP, cc);
-                const float m = cheb32<DP>(q, cc);
-                if (m < thr) {
-                    int r = kcap - 1;
-                    while (r > 0 && lst_d[(size_t)(r - 1) * QB + col] > m) {
-                        lst_d[(size_t)r * QB + col] = lst_d[(size_t)(r - 1) * QB + col];
-                        --r;
-                    }
-                    lst_d[(size_t)r * QB + col] = m;
-                    thr = lst_d[(size_t)(kcap - 1) * QB + col];
+        if constexpr (KC > 0) {
+            // the KC smallest distances, ascending, kept by a branch-free min/max insertion network
+            float dl[KC];
+#pragma unroll
+            for (int r = 0; r < KC; ++r) dl[r] = CUDART_INF_F;
+#pragma unroll 2
+            for (int off = 1; off <= KNN_SEED_W; ++off)
+#pragma unroll
+                for (int sgn = -1; sgn <= 1; sgn += 2) {
+                    const int64_t r2 = row + sgn * off;
+                    const bool inside = r2 >= 0 && r2 < n_rows;
+                    float2 cc[DP / 2];
+                    load_row<DP>(shadow + (inside ? r2 : row) * DP, cc);
+                    const float m = inside ? cheb32<DP>(q, cc) : CUDART_INF_F;
+#pragma unroll
+                    for (int r = KC - 1; r > 0; --r) dl[r] = fminf(dl[r], fmaxf(dl[r - 1], m));
+                    dl[0] = fminf(dl[0], m);
                 }
-            }
+#pragma unroll
+            for (int r = 0; r < KC; ++r)
+                if (r == kcap - 1) thr = dl[r];
+        } else {
+            const int col = j * FAST_THREADS + tid;
+            for (int r = 0; r < kcap; ++r) lst_d[(size_t)r * QB + col] = CUDART_INF_F;
+#pragma unroll 1
+            for (int off = 1; off <= KNN_SEED_W; ++off)
+#pragma unroll 1
+                for (int sgn = -1; sgn <= 1; sgn += 2) {
+                    const int64_t r2 = row + sgn * off;
+                    if (r2 < 0 || r2 >= n_rows) continue;
+                    float2 cc[DP / 2];
+                    load_row<DP>(shadow + r2 * DP, cc);
+                    const float m = cheb32<DP>(q, cc);
+                    if (m < thr) {
+                        int r = kcap - 1;
+                        while (r > 0 && lst_d[(size_t)(r - 1) * QB + col] > m) {
+                            lst_d[(size_t)r * QB + col] = lst_d[(size_t)(r - 1) * QB + col];
+                            --r;
+                        }
+                        lst_d[(size_t)r * QB + col] = m;
+                        thr = lst_d[(size_t)(kcap - 1) * QB + col];
+                    }
+                }
+        }
         thr = thr + (band.c0 + band.c1 * thr);  // inf stays inf
         seed_thr[qi] = thr;
         if (thr < CUDART_INF_F) { sum += thr; cnt += 1.0f; }
@@ -655,26 +678,27 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
         __syncthreads();  // (B) s_wthr is set; s_unit has been read by everybody
 
         if (producer) {
-            // ---------------- copy warp: stream the unit's tiles, then an end marker
-            if (lane == 0) {
-                const int2* lst = plan + (pfirst < 0 ? 0 : pfirst);
-                const int64_t own = (q_begin + min(qb0 + QB / 2, nq - 1)) / FAST_TILE;  // as in the planning pass
-                for (int next = first; next <= last; ++next) {
-                    int tile = -1;
-                    if (next < last) {
-                        if (pfirst < 0) {  // implicit list: every tile, in walk order
-                            tile = (int)walk_tile(next, own, n_tiles);
-                        } else {
-                            const int2 e = lst[next];
-                            float R = -1.0f;  // the block's current radius (thresholds only shrink)
+            // ---------------- copy warp: stream the unit's tiles, then an end marker.  All 32
+            // lanes walk the list together (no divergence, no spinning lanes); lane 0 issues.
+            const int2* lst = plan + (pfirst < 0 ? 0 : pfirst);
+            const int64_t own = (q_begin + min(qb0 + QB / 2, nq - 1)) / FAST_TILE;  // as in the planning pass
+            for (int next = first; next <= last; ++next) {
+                int tile = -1;
+                if (next < last) {
+                    if (pfirst < 0) {  // implicit list: every tile, in walk order
+                        tile = (int)walk_tile(next, own, n_tiles);
+                    } else {
+                        const int2 e = lst[next];
+                        float R = -1.0f;  // the block's current radius (thresholds only shrink)
 #pragma unroll
-                            for (int w = 0; w < FAST_THREADS / 32; ++w)
-                                R = fmaxf(R, *reinterpret_cast<volatile float*>(&s_wthr[w]));
-                            if (!(__int_as_float(e.y) < R)) continue;
-                            tile = e.x;
-                        }
+                        for (int w = 0; w < FAST_THREADS / 32; ++w)
+                            R = fmaxf(R, *reinterpret_cast<volatile float*>(&s_wthr[w]));
+                        if (!(__int_as_float(e.y) < R)) continue;
+                        tile = e.x;
                     }
-                    mbar_wait(&empty_bar[slot], (phase_bits >> slot) & 1u);
+                }
+                mbar_wait_relaxed(&empty_bar[slot], (phase_bits >> slot) & 1u);
+                if (lane == 0) {
                     *reinterpret_cast<volatile int*>(&s_tile[slot]) = tile;  // published by the mbarrier below
                     if (tile >= 0) {
                         float* dst = tiles + (size_t)slot * SLOT_FLOATS;
@@ -684,15 +708,9 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
                     } else {
                         mbar_arrive(&full_bar[slot]);
                     }
-                    advance();
                 }
-            }
-            // the other lanes carry the same ring state forward
-            {
-                const int s0 = __shfl_sync(0xffffffffu, slot, 0);
-                const uint32_t p0 = __shfl_sync(0xffffffffu, phase_bits, 0);
-                slot = s0;
-                phase_bits = p0;
+                __syncwarp();
+                advance();
             }
             continue;
         }

@@ -20,7 +20,7 @@ namespace ksg {
 constexpr int FAST_TILE = 512;       // candidates per shared-memory tile (fast kernels)
 constexpr int FAST_SUB = 32;         // rows of a sub-tile (own bounding box: warp-level culling)
 constexpr int FAST_NSUB = FAST_TILE / FAST_SUB;
-constexpr int STATS_BLOCKS = 64;     // partial min/max blocks per dimension
+constexpr int STATS_BLOCKS = 256;    // partial min/max blocks per dimension
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -129,17 +129,21 @@ static __global__ void rank_scatter_kernel(const int32_t* __restrict__ sorted_or
 // curve", AIP Conf. Proc. 707, 2004) and bit-interleaved (level-major, MSB first).  Unlike
 // the plain Z-order interleave the Hilbert curve has no jumps: any run of consecutive
 // points is a connected blob, so 512-point tiles and query blocks get tight boxes.
-static __global__ void morton_key_kernel(const int32_t* __restrict__ ranks, int64_t ld, int64_t n, int dim,
+template <int DIM>  // DIM > 0: compile-time dimension (coordinates stay in registers); 0: run-time `dim`
+static __global__ void morton_key_kernel(const int32_t* __restrict__ ranks, int64_t ld, int64_t n, int dim_rt,
                                          int rank_bits, int bits, unsigned long long* __restrict__ keys) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    unsigned int X[KSG_MAX_DIM];
+    const int dim = DIM > 0 ? DIM : dim_rt;
+    unsigned int X[DIM > 0 ? DIM : KSG_MAX_DIM];
+#pragma unroll
     for (int d = 0; d < dim; ++d)
         X[d] = ((unsigned int)ranks[(int64_t)d * ld + i]) >> (rank_bits - bits);
     if (dim > 1) {
         const unsigned int M = 1u << (bits - 1);
         for (unsigned int Q = M; Q > 1u; Q >>= 1) {
             const unsigned int P = Q - 1u;
+#pragma unroll
             for (int d = 0; d < dim; ++d) {
                 if (X[d] & Q) {
                     X[0] ^= P;  // invert the low bits of axis 0
@@ -150,14 +154,17 @@ static __global__ void morton_key_kernel(const int32_t* __restrict__ ranks, int6
                 }
             }
         }
+#pragma unroll
         for (int d = 1; d < dim; ++d) X[d] ^= X[d - 1];  // Gray encode
         unsigned int t = 0u;
         for (unsigned int Q = M; Q > 1u; Q >>= 1)
             if (X[dim - 1] & Q) t ^= Q - 1u;
+#pragma unroll
         for (int d = 0; d < dim; ++d) X[d] ^= t;
     }
     unsigned long long key = 0ull;
     for (int level = 0; level < bits; ++level)
+#pragma unroll
         for (int d = 0; d < dim; ++d) key = (key << 1) | ((X[d] >> (bits - 1 - level)) & 1u);
     keys[i] = key;
 }
