@@ -38,7 +38,7 @@ extern "C" {
 #define KSG_EUNSUPPORTED (-4)
 
 #define KSG_MAX_DIM 32        /* joint-space dimensionality limit */
-#define KSG_MAX_KPRIME 64     /* k+1 limit */
+#define KSG_MAX_KPRIME 128    /* k+1 limit */
 #define KSG_MAX_SUBSPACES 64  /* subspaces per count call */
 
 /* ABI version (major*1000 + minor). */

@@ -241,9 +241,16 @@ def launch_count() -> int:
 
 
 # ------------------------------------------------------------------ kernel wrappers
+MAX_KPRIME = 128  # KSG_MAX_KPRIME of include/ksg_b200.h
+
+
 def knn_radius(points: torch.Tensor, kprime: int, q_begin: int, q_end: int,
                queries: torch.Tensor | None = None, want_indices: bool = False):
     lib = _cabi.load()
+    if kprime > MAX_KPRIME:
+        raise NotImplementedError(
+            f"k + 1 = {kprime} exceeds the neighbour-list limit of the CUDA kernels ({MAX_KPRIME}); "
+            "there is no CPU fallback")
     dim, n = points.shape
     nq = q_end - q_begin
     eps = torch.empty(nq, dtype=torch.float64, device=points.device)
@@ -447,10 +454,19 @@ def scatter_to_original(values_sorted: torch.Tensor, prep: PreparedSet) -> torch
 stats = {"knn_fallback_queries": 0, "count_fallback_queries": 0, "knn_deferred_queries": 0}
 
 
-def _use_fast(dim: int) -> bool:
+def _use_fast(dim: int, kprime: int = 1) -> bool:
+    """The fp32-filtered engines serve up to 8 joint dimensions and neighbour lists that fit in
+    shared memory beside the candidate ring; everything else runs on the exact fp64 kernels."""
     if config.engine not in ("windowed", "dense", "exact"):
         raise ValueError("config.engine must be 'windowed', 'dense' or 'exact'")
-    return config.engine != "exact" and dim <= 8
+    if config.engine == "exact" or dim > 8:
+        return False
+    dp = (dim + 1) & ~1
+    queries_per_block = 128 * (4 if dp <= 4 else 2)
+    stages = 3 if dp <= 4 else 2
+    ring = stages * (512 * dp * 4 + 16 * dp * 8)
+    lists = (kprime + 3) * queries_per_block * 8
+    return ring + lists <= 200 * 1024 and kprime + 3 <= 64
 
 
 def check_finite(points: torch.Tensor) -> torch.Tensor:
@@ -583,7 +599,7 @@ def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder) -> Pointwise:
     """The device-resident part of ``ksg1_family``."""
     dim, n = pts.shape
     prog = prog_builder(psi_host(k), psi_host(n))
-    if not _use_fast(dim):
+    if not _use_fast(dim, k + 1):
         q0, q1 = _dist.my_slice(n)
         eps = knn_radius(pts, k + 1, q0, q1)
         counts = count_subspaces(pts, masks, eps, q0, q1, strict=True, bias=-1)
@@ -625,7 +641,7 @@ def kl_entropy(rows: np.ndarray, k: int):
     flag = check_finite(pts)
     q0, q1 = _dist.my_slice(n)
     prep = None
-    if _use_fast(dim):
+    if _use_fast(dim, k + 1):
         prep = PreparedSet(pts, min(config.primary, dim - 1))
         eps = fast_knn(prep, k + 1, q0, q1, config.engine == "windowed")
     else:

@@ -234,7 +234,7 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const in
                  size_t workspace_bytes, void* stream) {
     KSG_REQUIRE(P && d_eps_out && d_flags && d_n_flagged && d_workspace, "ksg_fast_knn: null pointer");
     KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && (d_query_index || q_end <= P->n), "ksg_fast_knn: bad query range");
-    KSG_REQUIRE(kprime >= 1 && kprime + KNN_MARGIN <= KSG_MAX_KPRIME, "ksg_fast_knn: kprime out of range");
+    KSG_REQUIRE(kprime >= 1 && kprime + KNN_MARGIN <= KNN_MAX_KCAP, "ksg_fast_knn: kprime out of range (k' + 3 <= 64)");
     if (d_query_index) windowed = 0;  // an explicit query list has no spatial coherence to prune with
     if (P->dim_padded > 8) {
         set_error("ksg_fast_knn: the fp32 filter is instantiated for up to 8 dimensions (got %d); use ksg_knn_radius",

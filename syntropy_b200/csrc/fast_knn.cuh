@@ -30,6 +30,7 @@ namespace ksg {
 
 constexpr int KNN_BATCH = 16;   // candidates between threshold checks
 constexpr int KNN_MARGIN = 3;   // list entries kept beyond k'
+constexpr int KNN_MAX_KCAP = 64; // longest neighbour list of the fp32 filter (k' + margin)
 constexpr int KNN_SEED_W = 24;  // rows on each side of a query used to seed its threshold
 constexpr float KNN_DEFER_CUT = 4.0f;   // defer a query whose seeded radius exceeds CUT x the CTA mean
 constexpr float KNN_DEFERRED = -2.0f;   // sentinel distance marking a deferred query's list
@@ -879,7 +880,7 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
 
     // k'-th smallest fp32 distance over the union of the split lists
-    float best[KSG_MAX_KPRIME];
+    float best[KNN_MAX_KCAP];
     int have = 0;
     for (int s = s_begin; s < s_end; ++s)
         for (int r = 0; r < kcap; ++r) {
@@ -900,7 +901,7 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     const double T = r32 + 2.0 * delta;
 
     bool overflow = false;
-    double exact[KSG_MAX_KPRIME];
+    double exact[KNN_MAX_KCAP];
     int got = 0, examined = 0;
     double qc[KSG_MAX_DIM];
     for (int d = 0; d < dim; ++d) qc[d] = sorted[(int64_t)d * ld + row_q];

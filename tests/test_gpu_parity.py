@@ -59,7 +59,7 @@ def radius_and_counts(E, rows, k, subspaces, strict=True, fused=False):
     pts = E.to_device_points(rows)
     dim, n = pts.shape
     masks = [E.mask_of(s) for s in subspaces]
-    if E.config.engine == "exact" or dim > 8:
+    if not E._use_fast(dim, k + 1):
         eps = E.knn_radius(pts, k + 1, 0, n)
         counts = E.count_subspaces(pts, masks, eps, 0, n, strict=strict)
     elif strict and not fused:
@@ -260,7 +260,8 @@ def test_errors_mirror_reference(knn):
 
 
 # ------------------------------------------------------------------ oracle at moderate n
-@pytest.mark.parametrize("dim,k,n", [(1, 1, 777), (2, 5, 6000), (3, 3, 4097), (5, 4, 3000), (8, 4, 5000), (11, 2, 1500)])
+@pytest.mark.parametrize("dim,k,n", [(1, 1, 777), (2, 5, 6000), (3, 3, 4097), (5, 4, 3000), (8, 4, 5000), (11, 2, 1500),
+                                     (2, 12, 5000), (3, 20, 4000), (6, 30, 2500), (2, 40, 3000)])
 def test_radius_counts_vs_oracle(E, dim, k, n):
     rng = np.random.default_rng(100 + dim)
     rows = rng.standard_normal((dim, n)) * rng.uniform(0.5, 3.0, size=(dim, 1))
@@ -408,3 +409,19 @@ def test_windowed_pair_counts_equal_dense_fp64_pair_counts(E):
         flag = torch.zeros(1, dtype=torch.int32, device="cuda")
         want = E._pair_counts_dense(xs, ys, n - m, m, r, flag)
         assert got == want
+
+
+@pytest.mark.parametrize("k", [15, 45, 70])
+def test_large_k_through_the_api(knn, k):
+    """k beyond what the shared-memory neighbour lists hold falls back to the float64 kernels
+    (k + 1 > 64 included): same numbers as the oracle either way."""
+    data, _ = workloads.c3_cmi(n=1500, seed=9)
+    ptw, avg = knn.mutual_information((0, 1), (2,), k, data)
+    ref_ptw, ref_avg = orc.mutual_information((0, 1), (2,), k, data)
+    close(ptw, ref_ptw); close(avg, ref_avg)
+
+
+def test_k_beyond_the_kernel_limit_is_refused_loudly(knn):
+    data, _ = workloads.c1_readme_mi(n=600, seed=2)
+    with pytest.raises(NotImplementedError):
+        knn.mutual_information((0,), (1,), 200, data)
