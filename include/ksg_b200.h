@@ -270,6 +270,17 @@ int ksg_fast_knn(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end,
                  void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same with the neighbours' identities (KSG algorithm 2, syntropy/knn/shannon.py:248-259,
+ * multivariate_mi.py:170-183: `indices[:, 1:]` of tree.query): d_idx_out[(i - q_begin) * kprime + r]
+ * = position in the prepared order of the r-th nearest point (r = 0 is the query itself unless
+ * it has exact duplicates), ascending by (exact distance, original sample index).  Queries with
+ * fewer than kprime points are flagged 1.  d_idx_out may be NULL (then identical to ksg_fast_knn).
+ */
+int ksg_fast_knn_idx(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end, const int32_t* d_query_index,
+                     int kprime, int windowed, double* d_eps_out, int64_t* d_idx_out, int32_t* d_flags,
+                     int32_t* d_n_flagged, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
  * K2 on the prepared set, multi-dimensional subspaces: semantics of ksg_count_subspaces
  * with one shared radius vector (d_eps, sorted order, exact float64), queries = sorted
  * positions [q_begin, q_end).  Recognised subspace structures (x|y, z|xz|yz,

@@ -80,6 +80,8 @@ SIGNATURES = {
     "ksg_fast_knn_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int, C.c_int]),
     "ksg_fast_knn": (C.c_int, [_c_prep, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp,
                                C.c_size_t, _c_vp]),
+    "ksg_fast_knn_idx": (C.c_int, [_c_prep, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
+                                   C.c_size_t, _c_vp]),
     "ksg_fast_count_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int, C.c_int]),
     "ksg_fast_count": (C.c_int, [_c_prep, _c_i64, _c_i64, C.POINTER(C.c_uint32), C.c_int, _c_vp, C.c_int,
                                  C.c_int32, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),

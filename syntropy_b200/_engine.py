@@ -364,43 +364,52 @@ class PreparedSet:
         return int(t[2]), int(t[3])
 
 
-def _fast_knn_call(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, q_index=None):
+def _fast_knn_call(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, q_index=None,
+                   want_indices: bool = False):
     lib = _cabi.load()
     nq = q1 - q0
     dev = prep.buf.device
     eps = torch.empty(nq, dtype=torch.float64, device=dev)
+    idx = torch.empty((nq, kprime), dtype=torch.int64, device=dev) if want_indices else None
     flags = torch.empty(nq, dtype=torch.int32, device=dev)
     nflag = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = torch.empty(max(int(lib.ksg_fast_knn_workspace(prep.n, max(nq, 1), prep.dim, kprime)), 1),
                      dtype=torch.uint8, device=dev)
     with timer.span("fast_knn" if q_index is None else "fast_knn_deferred"):
-        rc = lib.ksg_fast_knn(C.byref(prep.c), q0, q1, _ptr(q_index), kprime, 1 if windowed else 0, _ptr(eps),
-                              _ptr(flags), _ptr(nflag), _ptr(ws), ws.numel(), _stream())
-    _cabi.check(rc, "ksg_fast_knn")
-    return eps, flags, nflag
+        rc = lib.ksg_fast_knn_idx(C.byref(prep.c), q0, q1, _ptr(q_index), kprime, 1 if windowed else 0, _ptr(eps),
+                                  _ptr(idx), _ptr(flags), _ptr(nflag), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "ksg_fast_knn_idx")
+    return eps, idx, flags, nflag
 
 
-def fast_knn(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool) -> torch.Tensor:
+def fast_knn(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, want_indices: bool = False):
     """Exact k'-th-neighbour radii of sorted positions [q0, q1): fp32 filter + fp64 refine; the
     outliers the windowed pass sets aside go through a dense launch of the same filter, the
-    queries the filter cannot decide (tie-saturated data) through the dense fp64 kernel."""
+    queries the filter cannot decide (tie-saturated data) through the dense fp64 kernel.
+    ``want_indices``: also the (nq, k') neighbour positions in the prepared order (KSG-2)."""
     nq = q1 - q0
-    eps, flags, nflag = _fast_knn_call(prep, kprime, q0, q1, windowed)
+    eps, nbr, flags, nflag = _fast_knn_call(prep, kprime, q0, q1, windowed, want_indices=want_indices)
     if nq and int(nflag.item()):
         deferred = (flags == 2).nonzero().flatten()
         if deferred.numel():
             stats["knn_deferred_queries"] += int(deferred.numel())
             rows = (q0 + deferred).to(torch.int32)
-            eps2, flags2, _ = _fast_knn_call(prep, kprime, 0, int(rows.numel()), False, q_index=rows)
+            eps2, nbr2, flags2, _ = _fast_knn_call(prep, kprime, 0, int(rows.numel()), False, q_index=rows,
+                                                   want_indices=want_indices)
             eps[deferred] = eps2
             flags[deferred] = flags2
+            if want_indices:
+                nbr[deferred] = nbr2
         idx = (flags == 1).nonzero().flatten()
         if idx.numel():
             stats["knn_fallback_queries"] += int(idx.numel())
             pts = prep.sorted_f64
             queries = pts[:, q0 + idx].contiguous()
-            eps[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries)
-    return eps
+            if want_indices:
+                eps[idx], nbr[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries, want_indices=True)
+            else:
+                eps[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries)
+    return (eps, nbr) if want_indices else eps
 
 
 def fast_counts(prep: PreparedSet, masks, eps: torch.Tensor, q0: int, q1: int, windowed: bool,
@@ -616,23 +625,60 @@ def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder) -> Pointwise:
     return Pointwise(psi_epilogue(counts, prog, n), full=True, preps=preps)
 
 
-def ksg2_family(rows: np.ndarray, k: int, masks, prog_builder):
-    """KSG algorithm 2: per-subspace radii from the k joint neighbours, closed counts."""
+def ksg2_family(rows, k: int, masks, prog_builder):
+    """KSG algorithm 2 (reference: knn/shannon.py:199-265, multivariate_mi.py:118-193): per-subspace
+    radii from the k joint neighbours, closed-ball counts, psi(count) without the +1."""
     lib = _cabi.load()
     pts = to_device_points(rows)
     dim, n = pts.shape
     flag = check_finite(pts)
     q0, q1 = _dist.my_slice(n)
     nq = q1 - q0
-    _, idx = knn_radius(pts, k + 1, q0, q1, want_indices=True)
-    eps_s = torch.empty((len(masks), nq), dtype=torch.float64, device=pts.device)
-    rc = lib.ksg_subspace_radius_from_neighbours(_ptr(pts), pts.stride(0), n, dim, q0, q1, _ptr(idx), k + 1, 1,
-                                                 _masks(masks), len(masks), _ptr(eps_s), _stream())
-    _cabi.check(rc, "ksg_subspace_radius_from_neighbours")
-    counts = count_subspaces(pts, masks, eps_s, q0, q1, strict=False, bias=-1, per_subspace_eps=True)
     prog = prog_builder(psi_host(k), psi_host(n))
-    ptw = psi_epilogue(counts, prog, n)
-    return _finish(Pointwise(ptw), n, flag)
+    eps_s = torch.empty((len(masks), nq), dtype=torch.float64, device=pts.device)
+    if not _use_fast(dim, k + 1):
+        _, idx = knn_radius(pts, k + 1, q0, q1, want_indices=True)
+        rc = lib.ksg_subspace_radius_from_neighbours(_ptr(pts), pts.stride(0), n, dim, q0, q1, _ptr(idx), k + 1, 1,
+                                                     _masks(masks), len(masks), _ptr(eps_s), _stream())
+        _cabi.check(rc, "ksg_subspace_radius_from_neighbours")
+        counts = count_subspaces(pts, masks, eps_s, q0, q1, strict=False, bias=-1, per_subspace_eps=True)
+        return _finish(Pointwise(psi_epilogue(counts, prog, n)), n, flag)
+
+    # fast engines: neighbours from the fp32 filter + exact refine (prepared order); every
+    # subspace has its own radius, so every multi-dimensional one gets its own single-subspace pass
+    windowed = config.engine == "windowed"
+    prep = PreparedSet(pts, min(config.primary, dim - 1))
+    preps = [prep]
+    _, nbr = fast_knn(prep, k + 1, q0, q1, windowed, want_indices=True)
+    rc = lib.ksg_subspace_radius_from_neighbours(C.c_void_p(prep.c.sorted_f64), prep.ld, n, dim, q0, q1, _ptr(nbr),
+                                                 k + 1, 1, _masks(masks), len(masks), _ptr(eps_s), _stream())
+    _cabi.check(rc, "ksg_subspace_radius_from_neighbours")
+    counts = torch.empty((len(masks), n), dtype=torch.int32, device=pts.device)
+
+    def to_original(slice_sorted, prep_, out_row):
+        full = _dist.gather_slices(slice_sorted, n)
+        _cabi.check(lib.ksg_scatter_i32(_ptr(full), _ptr(prep_.perm), n, _ptr(out_row), _stream()), "ksg_scatter_i32")
+
+    all_mask = (1 << dim) - 1
+    for s, m in enumerate(masks):
+        dims = _dims_of(m)
+        e = eps_s[s].contiguous()
+        if len(dims) == 1:
+            c = fast_counts(prep, [m], e, q0, q1, windowed, strict=False, bias=-1)
+            to_original(c[0], prep, counts[s])
+            continue
+        if int(m) == all_mask:
+            prep_s, e_s = prep, e
+        else:
+            e_orig = scatter_to_original(_dist.gather_slices(e, n), prep)
+            prep_s = PreparedSet(pts[dims, :].contiguous(), -1)
+            preps.append(prep_s)
+            e_all = torch.empty(n, dtype=torch.float64, device=pts.device)
+            _cabi.check(lib.ksg_gather_f64(_ptr(e_orig), _ptr(prep_s.perm), n, _ptr(e_all), _stream()), "ksg_gather_f64")
+            e_s = e_all[q0:q1].contiguous()
+        c = fast_counts(prep_s, [(1 << len(dims)) - 1], e_s, q0, q1, windowed, strict=False, bias=-1)
+        to_original(c[0], prep_s, counts[s])
+    return _finish(Pointwise(psi_epilogue(counts, prog, n), full=True, preps=preps), n, flag)
 
 
 def kl_entropy(rows: np.ndarray, k: int):

@@ -232,6 +232,13 @@ size_t ksg_fast_knn_workspace(int64_t n, int64_t nq, int dim, int kprime) {
 int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const int32_t* d_query_index, int kprime,
                  int windowed, double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged, void* d_workspace,
                  size_t workspace_bytes, void* stream) {
+    return ksg_fast_knn_idx(P, q_begin, q_end, d_query_index, kprime, windowed, d_eps_out, nullptr, d_flags,
+                            d_n_flagged, d_workspace, workspace_bytes, stream);
+}
+
+int ksg_fast_knn_idx(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const int32_t* d_query_index, int kprime,
+                     int windowed, double* d_eps_out, int64_t* d_idx_out, int32_t* d_flags, int32_t* d_n_flagged,
+                     void* d_workspace, size_t workspace_bytes, void* stream) {
     KSG_REQUIRE(P && d_eps_out && d_flags && d_n_flagged && d_workspace, "ksg_fast_knn: null pointer");
     KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && (d_query_index || q_end <= P->n), "ksg_fast_knn: bad query range");
     KSG_REQUIRE(kprime >= 1 && kprime + KNN_MARGIN <= KNN_MAX_KCAP, "ksg_fast_knn: kprime out of range (k' + 3 <= 64)");
@@ -283,7 +290,8 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const in
     knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, p.splits, kprime,
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    d_query_index, P->maxabs, a.seed_thr, a.unit_first,
-                                                                   p.qb, d_eps_out, d_flags, d_n_flagged);
+                                                                   p.qb, P->perm, d_idx_out, d_eps_out, d_flags,
+                                                                   d_n_flagged);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

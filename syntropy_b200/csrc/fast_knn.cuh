@@ -854,7 +854,12 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
                   int kp, const double* __restrict__ sorted, int64_t ld, int dim, int64_t n, int64_t q_begin,
                   int64_t nq, const int32_t* __restrict__ q_index, const double* __restrict__ maxabs,
                   const float* __restrict__ seed_thr, const int32_t* __restrict__ unit_first, int qb,
+                  const int32_t* __restrict__ perm, int64_t* __restrict__ idx_out,
                   double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
+    // idx_out (optional, [nq][kp] int64): the k' nearest points as positions in the prepared
+    // order, ascending by (exact distance, original sample index) -- the order the dense float64
+    // kernel's merge produces.  All points tied with the k'-th distance are among the examined
+    // candidates whenever the query is not flagged, so the tie-break is well defined.
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     if (seed_thr && seed_thr[qi] < 0.0f) {  // taken out by the planning pass: needs the dense launch
@@ -894,7 +899,8 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     const double r32 = (have == kp) ? (double)best[kp - 1] : CUDART_INF;
     if (!(r32 < CUDART_INF)) {  // fewer than k' points exist (k+1 > n): cKDTree pads with inf
         eps_out[qi] = CUDART_INF;
-        flags[qi] = 0;
+        flags[qi] = idx_out ? 1 : 0;  // neighbour identities: leave it to the dense float64 kernel
+        if (idx_out) atomicAdd(n_flagged, 1);
         return;
     }
     const double delta = band_f64(mmax, 2.0 * r32);
@@ -902,6 +908,7 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
 
     bool overflow = false;
     double exact[KNN_MAX_KCAP];
+    int32_t exact_j[KNN_MAX_KCAP], exact_o[KNN_MAX_KCAP];  // prepared position / original index (idx_out only)
     int got = 0, examined = 0;
     double qc[KSG_MAX_DIM];
     for (int d = 0; d < dim; ++d) qc[d] = sorted[(int64_t)d * ld + row_q];
@@ -918,9 +925,19 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
             double m = 0.0;
             for (int d = 0; d < dim; ++d) m = fmax(m, fabs(qc[d] - sorted[(int64_t)d * ld + j]));
             int pos = got < kp ? got : kp - 1;
-            if (got == kp && !(m < exact[kp - 1])) continue;
-            while (pos > 0 && exact[pos - 1] > m) { exact[pos] = exact[pos - 1]; --pos; }
-            exact[pos] = m;
+            if (idx_out) {
+                const int32_t o_j = perm[j];
+                if (got == kp && !(m < exact[kp - 1] || (m == exact[kp - 1] && o_j < exact_o[kp - 1]))) continue;
+                while (pos > 0 && (exact[pos - 1] > m || (exact[pos - 1] == m && exact_o[pos - 1] > o_j))) {
+                    exact[pos] = exact[pos - 1]; exact_j[pos] = exact_j[pos - 1]; exact_o[pos] = exact_o[pos - 1];
+                    --pos;
+                }
+                exact[pos] = m; exact_j[pos] = (int32_t)j; exact_o[pos] = o_j;
+            } else {
+                if (got == kp && !(m < exact[kp - 1])) continue;
+                while (pos > 0 && exact[pos - 1] > m) { exact[pos] = exact[pos - 1]; --pos; }
+                exact[pos] = m;
+            }
             if (got < kp) ++got;
         }
     }
@@ -931,6 +948,8 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     } else {
         flags[qi] = 0;
         eps_out[qi] = exact[kp - 1];
+        if (idx_out)
+            for (int r = 0; r < kp; ++r) idx_out[qi * kp + r] = exact_j[r];
     }
 }
 
