@@ -699,20 +699,30 @@ def kl_entropy(rows: np.ndarray, k: int):
 
 
 def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
+    """kNN KL divergence (reference: knn/shannon.py:350-410): rho = (k+1)-th neighbour distance
+    inside the posterior sample (fast path), nu = k-th neighbour distance in the prior sample
+    (cross-set query: dense float64 kernel)."""
     P = to_device_points(post_rows)
     Q = to_device_points(prior_rows)
     dim, n = P.shape
     m = Q.shape[1]
     flag = check_finite(P) | check_finite(Q)
     q0, q1 = _dist.my_slice(n)
-    rho = knn_radius(P, k + 1, q0, q1)
-    nu = knn_radius(Q, k, q0, q1, queries=P)
+    prep = None
+    if _use_fast(dim, k + 1):
+        prep = PreparedSet(P, min(config.primary, dim - 1))
+        rho = fast_knn(prep, k + 1, q0, q1, config.engine == "windowed")
+        queries = prep.sorted_f64[:, q0:q1].contiguous()   # the same rows, in the prepared order
+        nu = knn_radius(Q, k, 0, q1 - q0, queries=queries)
+    else:
+        rho = knn_radius(P, k + 1, q0, q1)
+        nu = knn_radius(Q, k, q0, q1, queries=P)
     ptw = torch.empty(q1 - q0, dtype=torch.float64, device=P.device)
     with np.errstate(all="ignore"):
         log_ratio = float(np.log(m / (n - 1)))
     rc = _cabi.load().ksg_kl_epilogue(_ptr(nu), _ptr(rho), q1 - q0, dim, log_ratio, _ptr(ptw), _stream())
     _cabi.check(rc, "ksg_kl_epilogue")
-    return _finish(Pointwise(ptw), n, flag)
+    return _finish(Pointwise(ptw, prep=prep, preps=[prep] if prep is not None else []), n, flag)
 
 
 def _self_pair_count(templates: torch.Tensor, r: float) -> torch.Tensor:

@@ -59,6 +59,20 @@ def main():
     E.config.engine = args.engine
     from oracle import ksg_oracle_c as oc
 
+    # under torchrun: one rank per GPU, query rows sharded (every rank ends up with all results)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        import torch.distributed as td
+
+        td.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+
+    def sync():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
     for name in args.configs.split(","):
         n = max(64, int(SIZES[name] * args.scale))
         data, call = workloads.CONFIGS[name](n=n, seed=0)
@@ -72,12 +86,12 @@ def main():
         subs = subspaces_of(name, call, dim)
         masks = [E.mask_of(s) for s in subs]
         pts = E.to_device_points(rows)
-        out = {"config": name, "n": n, "dim": dim, "k": k, "engine": args.engine}
+        out = {"config": name, "n": n, "dim": dim, "k": k, "engine": args.engine, "n_gpus": world}
         best = None
         for rep in range(args.reps + 1):
             E.timer.enabled = True
             E.timer.reset()
-            torch.cuda.synchronize()
+            sync()
             t0 = time.perf_counter()
             if args.engine == "exact":
                 eps = E.knn_radius(pts, k + 1, 0, n)
@@ -86,7 +100,7 @@ def main():
             else:
                 # radii and counts of all n samples, in the caller's sample order
                 eps, counts, preps = E.radius_and_counts(pts, k, masks)
-            torch.cuda.synchronize()
+            sync()
             wall = time.perf_counter() - t0
             ms = {kname: float(np.sum(v)) for kname, v in E.timer.totals_ms().items()}
             E.timer.enabled = False
@@ -129,17 +143,23 @@ def main():
         out["oracle_s"] = time.perf_counter() - t0
         out["parity"] = {"queries_checked": int(sel.size), "radii_bit_exact": ok_eps, "counts_bit_exact": ok_cnt}
         # ---- public API, end to end on host arrays
-        torch.cuda.synchronize()
+        sync()
         t0 = time.perf_counter()
         ptw, avg = api_call(name, call, data)
+        sync()
         out["api_e2e_ms"] = 1e3 * (time.perf_counter() - t0)
         out["avg_nats"] = float(avg)
         out["samples_per_s_api"] = n / (out["api_e2e_ms"] * 1e-3)
         out["fallback_queries"] = dict(E.stats)
-        print(json.dumps(out), flush=True)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
         del pts, preps, eps, counts
         torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
     main()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as _td
+
+        _td.destroy_process_group()
