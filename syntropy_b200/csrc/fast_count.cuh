@@ -65,6 +65,35 @@ __device__ __forceinline__ float count_threshold(double eps, double mq) {
     return nextafterf(t, CUDART_INF_F);
 }
 
+// ---- "m < T" as 1.0f / 0.0f on the FMA pipe.  FSET runs on the half-rate ALU pipe, which the
+// subspace maxima (FMNMX / FMNMX3) already saturate (ncu, leave-one-out of 8: ALU 80 % busy,
+// FMA 15 %).  One saturating FMA does the same: with B = 2^e chosen per query so that
+// T*B ~ 2^100,   sat((-m)*B + T*B)   is 1 when m < T (the gap is >= one ulp of T, i.e.
+// >= 2^-24 T, so the scaled difference is >= 2^76), 0 when m >= T (non-positive), 0 for the
+// NaN of inf - inf (padding rows against an infinite radius) -- single rounding, power-of-two
+// scaling, so the sign is exact.  Thresholds below 2^-100 cannot be scaled that far: those
+// queries are flagged for the float64 kernel (count_fix_kernel).
+constexpr float COUNT_MIN_T = 7.8886090522101181e-31f;  // 2^-100
+struct IndScale {
+    float neg_b, tb;  // -B and T*B
+};
+__device__ __forceinline__ IndScale make_ind_scale(float T) {
+    IndScale s;
+    if (!(T > 0.0f)) { s.neg_b = -1.0f; s.tb = -1.0f; return s; }  // dead slot: never counts
+    const int e = (int)((__float_as_uint(T) >> 23) & 0xffu);        // T in [2^(e-127), 2^(e-126))
+    int be = 354 - e;                                               // biased exponent of 2^(100 - (e - 127))
+    be = be > 253 ? 253 : (be < 1 ? 1 : be);
+    const float b = __uint_as_float((unsigned)be << 23);
+    s.neg_b = -b;
+    s.tb = T * b;  // exact (power of two), inf for an infinite radius
+    return s;
+}
+__device__ __forceinline__ float ind_lt(float m, IndScale s) {
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(m), "f"(s.neg_b), "f"(s.tb));
+    return r;
+}
+
 // ---------------------------------------------------------------- subspace specs
 // a[d] = |q_d - c_d| for the DP (even-padded) joint dimensions; m[s] = subspace maxima.
 template <int LO, int HI>
@@ -171,6 +200,7 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
 
     float2 q[Q][DP / 2];
     float T[Q];
+    IndScale sc[Q];
     int cnt[Q][S];
     float blo[DP], bhi[DP];
     float tmax = -CUDART_INF_F;
@@ -183,6 +213,7 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
         const int64_t row = q_begin + (live ? qi : 0);
         load_row<DP>(shadow + row * DP, q[j]);
         T[j] = live ? thresholds[qi] : -1.0f;
+        sc[j] = make_ind_scale(T[j]);
 #pragma unroll
         for (int s = 0; s < S; ++s) cnt[j][s] = 0;
         if (live) {
@@ -248,7 +279,7 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
                 subspace_maxima(a, m);
                 float ind[2 * SP];
 #pragma unroll
-                for (int s = 0; s < S; ++s) ind[s] = (m[s] < T[j]) ? 1.0f : 0.0f;
+                for (int s = 0; s < S; ++s) ind[s] = ind_lt(m[s], sc[j]);
                 if constexpr (S & 1) ind[S] = 0.0f;
 #pragma unroll
                 for (int h = 0; h < SP; ++h) acc[j][h] = add2(acc[j][h], make_float2(ind[2 * h], ind[2 * h + 1]));
@@ -324,6 +355,11 @@ count_fix_kernel(const double* __restrict__ sorted, int64_t ld, const float* __r
     const double e = eps[qi];
     if (!(e < CUDART_INF)) return;  // infinite radius: the filter is exact (everything finite is inside)
     const float T = thresholds[qi];
+    if (T < COUNT_MIN_T) {  // the filter's scaled compare is not exact this far down (see ind_lt)
+        flags[qi] = 1;
+        atomicAdd(n_flagged, 1);
+        return;
+    }
     uint32_t used = 0;
     for (int s = 0; s < n_sub; ++s) used |= masks.m[s];
     const int64_t row_q = q_begin + qi;

@@ -251,6 +251,8 @@ count_units_kernel(const float* __restrict__ shadow, const float* __restrict__ s
                         load_two_rows<DP>(rows + c * DP, ca, cb);
 #pragma unroll
                         for (int j = 0; j < Q; ++j) {
+                            // (FSET here: with one subspace the ALU pipe has room, the FMA pipe
+                            //  -- FADD2 differences + the accumulate -- does not; measured)
                             acc[j] += (cheb32<DP>(q[j], ca) < T[j]) ? 1.0f : 0.0f;
                             acc[j] += (cheb32<DP>(q[j], cb) < T[j]) ? 1.0f : 0.0f;
                         }
