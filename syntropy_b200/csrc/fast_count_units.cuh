@@ -74,8 +74,9 @@ count_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ ti
     if (tid == 0) {
         int base = -1;
         if (total > 0 && 2 * (int64_t)total <= n_tiles) {
-            base = atomicAdd(&meta[3], total);
-            if ((int64_t)base + total > plan_capacity) base = -1;
+            const unsigned long long at = atomicAdd(reinterpret_cast<unsigned long long*>(meta + 4),
+                                                    (unsigned long long)total);
+            base = at + (unsigned long long)total <= (unsigned long long)plan_capacity ? (int)at : -1;
         }
         s_base = base;
     }
@@ -281,7 +282,7 @@ template <int DP>
 static int launch_count_full_dp(const CountF32Args& a, const CountUnitsArgs& w) {
     constexpr int Q = FastGeom<DP>::Q, ST = FastGeom<DP>::STAGES;
     const int64_t qblocks = ceil_div(a.nq, FAST_THREADS * Q);
-    if (cudaMemsetAsync(w.unit_meta, 0, 16, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
+    if (cudaMemsetAsync(w.unit_meta, 0, 32, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
     count_plan_kernel<DP, Q><<<(unsigned)qblocks, FAST_THREADS, 0, a.st>>>(
         a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.thresholds, (int2*)w.plan, w.plan_capacity, w.plan_count,
         w.plan_first, w.unit_meta);

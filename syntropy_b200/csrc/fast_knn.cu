@@ -33,7 +33,7 @@ static int launch_plan_kc(const KnnF32Args& a) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     }
-    if (cudaMemsetAsync(a.unit_meta, 0, 16, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
+    if (cudaMemsetAsync(a.unit_meta, 0, 32, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
     kern<<<(unsigned)ceil_div(a.nq, FAST_THREADS * Q), FAST_THREADS, smem, a.st>>>(
         a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.maxabs, a.dim, a.seed_thr, (int2*)a.plan,
         a.plan_capacity, a.plan_count, a.plan_first, a.unit_meta);

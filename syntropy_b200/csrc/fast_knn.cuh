@@ -236,7 +236,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
     const float R = block_max(rmax, sh);
 
     // ---- every tile whose box is within R of the query box, in walk order (near first).
-    // The lists live in one pool (meta[3] = bump cursor): a first sweep counts the survivors,
+    // The lists live in one pool (meta[4..5] = 64-bit bump cursor): a first sweep counts the survivors,
     // the block reserves that many entries, a second sweep writes them.
     const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
     const int64_t own = mid / FAST_TILE;
@@ -261,8 +261,10 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
     if (tid == 0) {
         int base = -1;
         if (total > 0 && 2 * (int64_t)total <= n_tiles) {
-            base = atomicAdd(&meta[3], total);
-            if ((int64_t)base + total > plan_capacity) base = -1;  // pool exhausted
+            // 64-bit bump cursor at meta[4..5] (zeroed before this kernel)
+            const unsigned long long at = atomicAdd(reinterpret_cast<unsigned long long*>(meta + 4),
+                                                    (unsigned long long)total);
+            base = at + (unsigned long long)total <= (unsigned long long)plan_capacity ? (int)at : -1;  // else: pool exhausted
         }
         s_base = base;
     }
@@ -482,7 +484,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
 // starts from the block's seeded thresholds and emits its own partial lists, which the refine
 // kernel merges exactly like the split lists of the dense launch.
 //   meta[0] = number of units, meta[1] = chunk, meta[2] = work-queue cursor (zeroed here),
-//   meta[3] = tile-list pool cursor (zeroed before the planning pass)
+//   meta[4..5] = tile-list pool cursor, 64 bit (zeroed before the planning pass)
 static __global__ void __launch_bounds__(1024)
 knn_unit_table_kernel(const int32_t* __restrict__ plan_count, int64_t n_blocks, int64_t max_units,
                       int32_t* __restrict__ unit_first, int32_t* __restrict__ unit_block,
