@@ -233,6 +233,8 @@ typedef struct {
                             uint64 at byte 16 / 24 = (query, candidate) pairs evaluated so far by
                             the k-NN / count filter kernels (for the roofline of the windowed
                             engine, which skips most of the n x n pairs) */
+    uint64_t* curve_keys; /* [n] ascending space-filling-curve keys of the rows (primary == -1 only; else NULL):
+                            lets ksg_cross_prepare place foreign query points on the same curve */
 } ksg_prepared;
 
 /*
@@ -279,6 +281,39 @@ int ksg_fast_knn(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end,
 int ksg_fast_knn_idx(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end, const int32_t* d_query_index,
                      int kprime, int windowed, double* d_eps_out, int64_t* d_idx_out, int32_t* d_flags,
                      int32_t* d_n_flagged, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ cross-set k-NN (KL divergence)
+ *
+ * Queries that are NOT points of the prepared (candidate) set: kullback_leibler_divergence asks
+ * for the k-th neighbour of every posterior sample among the prior samples
+ * (syntropy/knn/shannon.py:401-402, `cKDTree(prior).query(posterior, k)`).  ksg_cross_prepare puts
+ * the nq query points (d_queries, [dim][ldq] float64) on the candidate set's curve: rank of every
+ * coordinate among the candidates' (binary search), same Hilbert key, radix sort; it stores them
+ * in that order as float64 SoA and as fp32 rows in the candidate set's centred frame, together
+ * with the candidate row next to each of them on the curve.  Needs primary == -1.
+ */
+typedef struct {
+    int64_t nq;          /* queries */
+    int64_t ld;          /* row stride of sorted_f64 */
+    int32_t* perm;       /* [nq] position in the cross order -> original query index */
+    double* sorted_f64;  /* [dim][ld] the queries in cross order */
+    float* shadow_f32;   /* [nq][dim_padded] fp32(x - candidate centre) */
+    int32_t* home;       /* [nq] candidate row (prepared order) next to the query on the curve */
+    double* maxabs;      /* [dim] max over BOTH sets of |x - centre| (fp32 error bound) */
+} ksg_cross;
+size_t ksg_cross_prepare_workspace(int64_t n_candidates, int64_t nq, int dim);
+int ksg_cross_prepare(const ksg_prepared* h_candidates, const double* d_queries, int64_t ldq, int64_t nq,
+                      void* d_buffer, size_t buffer_bytes, ksg_cross* h_out, void* stream);
+
+/*
+ * d_eps_out[i - q_begin] = exact kprime-th smallest Chebyshev distance from the query at cross
+ * position i to the candidate set (no self: the query is not a candidate), i in [q_begin, q_end).
+ * Always windowed.  Flags as in ksg_fast_knn; flagged queries (1 or 2) are to be recomputed with
+ * ksg_knn_radius (queries = those rows of sorted_f64).  Workspace: ksg_fast_knn_workspace(n, nq, ...).
+ */
+int ksg_fast_knn_cross(const ksg_prepared* h_candidates, const ksg_cross* h_queries, int64_t q_begin,
+                       int64_t q_end, int kprime, double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
  * K2 on the prepared set, multi-dimensional subspaces: semantics of ksg_count_subspaces

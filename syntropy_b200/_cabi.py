@@ -44,10 +44,25 @@ class Prepared(C.Structure):
         ("tile_box", C.c_void_p),
         ("sub_box", C.c_void_p),
         ("flags", C.c_void_p),
+        ("curve_keys", C.c_void_p),
+    ]
+
+
+class Cross(C.Structure):
+    """ksg_cross of include/ksg_b200.h."""
+    _fields_ = [
+        ("nq", C.c_int64),
+        ("ld", C.c_int64),
+        ("perm", C.c_void_p),
+        ("sorted_f64", C.c_void_p),
+        ("shadow_f32", C.c_void_p),
+        ("home", C.c_void_p),
+        ("maxabs", C.c_void_p),
     ]
 
 
 _c_prep = C.POINTER(Prepared)
+_c_cross = C.POINTER(Cross)
 
 # name -> (restype, argtypes); mirrors include/ksg_b200.h one to one
 SIGNATURES = {
@@ -82,6 +97,10 @@ SIGNATURES = {
                                C.c_size_t, _c_vp]),
     "ksg_fast_knn_idx": (C.c_int, [_c_prep, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
                                    C.c_size_t, _c_vp]),
+    "ksg_cross_prepare_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int]),
+    "ksg_cross_prepare": (C.c_int, [_c_prep, _c_vp, _c_i64, _c_i64, _c_vp, C.c_size_t, _c_cross, _c_vp]),
+    "ksg_fast_knn_cross": (C.c_int, [_c_prep, _c_cross, _c_i64, _c_i64, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp,
+                                     C.c_size_t, _c_vp]),
     "ksg_fast_count_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int, C.c_int]),
     "ksg_fast_count": (C.c_int, [_c_prep, _c_i64, _c_i64, C.POINTER(C.c_uint32), C.c_int, _c_vp, C.c_int,
                                  C.c_int32, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),

@@ -698,31 +698,96 @@ def kl_entropy(rows: np.ndarray, k: int):
     return _finish(Pointwise(ptw, prep=prep), n, flag)
 
 
+class CrossSet:
+    """Host handle of a ksg_cross: query points that are not part of the prepared candidate set,
+    placed on the candidates' space-filling curve (``ksg_cross_prepare``)."""
+
+    def __init__(self, cand: PreparedSet, queries: torch.Tensor):
+        lib = _cabi.load()
+        dim, nq = queries.shape
+        assert dim == cand.dim
+        size = int(lib.ksg_cross_prepare_workspace(cand.n, nq, dim))
+        self.buf = torch.empty(size, dtype=torch.uint8, device=queries.device)
+        self.c = _cabi.Cross()
+        with timer.span("cross_prepare"):
+            rc = lib.ksg_cross_prepare(C.byref(cand.c), _ptr(queries), queries.stride(0), nq, _ptr(self.buf), size,
+                                       C.byref(self.c), _stream())
+        _cabi.check(rc, "ksg_cross_prepare")
+        self.cand, self.nq, self.dim, self.ld = cand, nq, dim, int(self.c.ld)
+
+    def _view(self, ptr, nbytes, dtype):
+        off = int(ptr) - self.buf.data_ptr()
+        return self.buf[off:off + nbytes].view(dtype)
+
+    @property
+    def perm(self) -> torch.Tensor:
+        return self._view(self.c.perm, self.nq * 4, torch.int32)
+
+    @property
+    def sorted_f64(self) -> torch.Tensor:
+        return self._view(self.c.sorted_f64, self.dim * self.ld * 8, torch.float64).view(self.dim, self.ld)[:, :self.nq]
+
+
+def fast_knn_cross(cross: CrossSet, kprime: int, q0: int, q1: int) -> torch.Tensor:
+    """Exact kprime-th-neighbour distance from the queries at cross positions [q0, q1) to the
+    candidate set: windowed fp32 filter + fp64 refine; whatever it sets aside or cannot decide is
+    recomputed by the dense float64 kernel."""
+    lib = _cabi.load()
+    cand = cross.cand
+    nq = q1 - q0
+    dev = cross.buf.device
+    eps = torch.empty(nq, dtype=torch.float64, device=dev)
+    flags = torch.empty(nq, dtype=torch.int32, device=dev)
+    nflag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(int(lib.ksg_fast_knn_workspace(cand.n, max(nq, 1), cand.dim, kprime)), 1),
+                     dtype=torch.uint8, device=dev)
+    with timer.span("fast_knn_cross"):
+        rc = lib.ksg_fast_knn_cross(C.byref(cand.c), C.byref(cross.c), q0, q1, kprime, _ptr(eps), _ptr(flags),
+                                    _ptr(nflag), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "ksg_fast_knn_cross")
+    if nq and int(nflag.item()):
+        idx = flags.nonzero().flatten()
+        stats["knn_fallback_queries"] += int(idx.numel())
+        queries = cross.sorted_f64[:, q0 + idx].contiguous()
+        eps[idx] = knn_radius(cand.sorted_f64, kprime, 0, int(idx.numel()), queries=queries)
+    return eps
+
+
 def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
     """kNN KL divergence (reference: knn/shannon.py:350-410): rho = (k+1)-th neighbour distance
-    inside the posterior sample (fast path), nu = k-th neighbour distance in the prior sample
-    (cross-set query: dense float64 kernel)."""
+    inside the posterior sample, nu = k-th neighbour distance of every posterior sample in the
+    prior sample (cross-set search on the prior's prepared set)."""
+    lib = _cabi.load()
     P = to_device_points(post_rows)
     Q = to_device_points(prior_rows)
     dim, n = P.shape
     m = Q.shape[1]
     flag = check_finite(P) | check_finite(Q)
     q0, q1 = _dist.my_slice(n)
-    prep = None
-    if _use_fast(dim, k + 1):
-        prep = PreparedSet(P, min(config.primary, dim - 1))
-        rho = fast_knn(prep, k + 1, q0, q1, config.engine == "windowed")
-        queries = prep.sorted_f64[:, q0:q1].contiguous()   # the same rows, in the prepared order
-        nu = knn_radius(Q, k, 0, q1 - q0, queries=queries)
-    else:
-        rho = knn_radius(P, k + 1, q0, q1)
-        nu = knn_radius(Q, k, q0, q1, queries=P)
-    ptw = torch.empty(q1 - q0, dtype=torch.float64, device=P.device)
     with np.errstate(all="ignore"):
         log_ratio = float(np.log(m / (n - 1)))
-    rc = _cabi.load().ksg_kl_epilogue(_ptr(nu), _ptr(rho), q1 - q0, dim, log_ratio, _ptr(ptw), _stream())
+    if not _use_fast(dim, k + 1):
+        rho = knn_radius(P, k + 1, q0, q1)
+        nu = knn_radius(Q, k, q0, q1, queries=P)
+        ptw = torch.empty(q1 - q0, dtype=torch.float64, device=P.device)
+        rc = lib.ksg_kl_epilogue(_ptr(nu), _ptr(rho), q1 - q0, dim, log_ratio, _ptr(ptw), _stream())
+        _cabi.check(rc, "ksg_kl_epilogue")
+        return _finish(Pointwise(ptw), n, flag)
+    windowed = config.engine == "windowed"
+    prep_p = PreparedSet(P, -1)
+    rho = scatter_to_original(_dist.gather_slices(fast_knn(prep_p, k + 1, q0, q1, windowed), n), prep_p)
+    prep_q = PreparedSet(Q, -1)
+    if windowed:
+        cross = CrossSet(prep_q, P)
+        nu_cross = _dist.gather_slices(fast_knn_cross(cross, k, q0, q1), n)
+        nu = torch.empty_like(nu_cross)
+        _cabi.check(lib.ksg_scatter_f64(_ptr(nu_cross), _ptr(cross.perm), n, _ptr(nu), _stream()), "ksg_scatter_f64")
+    else:
+        nu = _dist.gather_slices(knn_radius(Q, k, q0, q1, queries=P), n)
+    ptw = torch.empty(n, dtype=torch.float64, device=P.device)
+    rc = lib.ksg_kl_epilogue(_ptr(nu), _ptr(rho), n, dim, log_ratio, _ptr(ptw), _stream())
     _cabi.check(rc, "ksg_kl_epilogue")
-    return _finish(Pointwise(ptw, prep=prep, preps=[prep] if prep is not None else []), n, flag)
+    return _finish(Pointwise(ptw, full=True, preps=[prep_p, prep_q]), n, flag)
 
 
 def _self_pair_count(templates: torch.Tensor, r: float) -> torch.Tensor:

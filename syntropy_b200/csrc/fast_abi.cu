@@ -184,10 +184,8 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
             rank_scatter_kernel<<<nb, 256, 0, st>>>(P.axis_pos + (int64_t)d * L.ld, n, ranks + (int64_t)d * L.ld);
             KSG_LAUNCHED2();
         }
-        int rank_bits = 1;
-        while ((1ll << rank_bits) < n) ++rank_bits;
-        int bits = 63 / dim;
-        if (bits > rank_bits) bits = rank_bits;
+        int rank_bits, bits;
+        curve_bits(n, dim, &rank_bits, &bits);
         switch (dim) {
 #define KSG_MORTON(D) case D: morton_key_kernel<D><<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys); break;
             KSG_MORTON(1) KSG_MORTON(2) KSG_MORTON(3) KSG_MORTON(4) KSG_MORTON(5) KSG_MORTON(6) KSG_MORTON(7) KSG_MORTON(8)
@@ -200,6 +198,7 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
                                                         bits * dim, st);
         if (e != cudaSuccess) { set_error("cub SortPairs (morton): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
         note_launch();
+        P.curve_keys = (uint64_t*)mkeys_out;
     }
     gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
         d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
@@ -261,6 +260,7 @@ int ksg_fast_knn_idx(const ksg_prepared* P, int64_t q_begin, int64_t q_end, cons
     a.q_begin = q_begin; a.nq = nq; a.q_index = d_query_index; a.kcap = p.kcap; a.splits = p.splits;
     a.windowed = windowed ? 1 : 0;
     a.maxabs = P->maxabs; a.dim = P->dim;
+    a.qshadow = nullptr; a.qhome = nullptr;
     a.part_d32 = (float*)d_workspace;
     a.part_idx = (int32_t*)((char*)d_workspace + p.d32_bytes);
     a.tile_counter = (unsigned long long*)((char*)P->flags + 16);
@@ -290,8 +290,145 @@ int ksg_fast_knn_idx(const ksg_prepared* P, int64_t q_begin, int64_t q_end, cons
     knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, p.splits, kprime,
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    d_query_index, P->maxabs, a.seed_thr, a.unit_first,
-                                                                   p.qb, P->perm, d_idx_out, d_eps_out, d_flags,
-                                                                   d_n_flagged);
+                                                                   p.qb, P->perm, d_idx_out, nullptr, 0, d_eps_out,
+                                                                   d_flags, d_n_flagged);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+// ---------------------------------------------------------------- cross-set queries
+struct CrossLayout {
+    int64_t ld;
+    size_t off_perm, off_sorted, off_shadow, off_home, off_maxabs, off_keys, off_keys_out, off_iota, off_stats, off_cub;
+    size_t cub_bytes, total;
+};
+static CrossLayout cross_layout(int64_t nq, int dim) {
+    CrossLayout L;
+    L.ld = (int64_t)align_up((size_t)nq, 32);
+    const int dp = (dim + 1) & ~1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    L.off_perm = take((size_t)L.ld * 4);
+    L.off_sorted = take((size_t)dim * L.ld * 8);
+    L.off_shadow = take((size_t)L.ld * dp * 4);
+    L.off_home = take((size_t)L.ld * 4);
+    L.off_maxabs = take((size_t)KSG_MAX_DIM * 8);
+    L.off_keys = take((size_t)L.ld * 8);
+    L.off_keys_out = take((size_t)L.ld * 8);
+    L.off_iota = take((size_t)L.ld * 4);
+    L.off_stats = take((size_t)dim * STATS_BLOCKS * 2 * 8 + 64);
+    L.cub_bytes = cub_sort_bytes(nq);
+    L.off_cub = take(L.cub_bytes);
+    L.total = o;
+    return L;
+}
+
+size_t ksg_cross_prepare_workspace(int64_t n_candidates, int64_t nq, int dim) {
+    (void)n_candidates;
+    if (nq <= 0 || dim < 1 || dim > KSG_MAX_DIM) return 0;
+    return cross_layout(nq, dim).total;
+}
+
+int ksg_cross_prepare(const ksg_prepared* P, const double* d_queries, int64_t ldq, int64_t nq, void* d_buffer,
+                      size_t buffer_bytes, ksg_cross* h_out, void* stream) {
+    KSG_REQUIRE(P && d_queries && d_buffer && h_out, "ksg_cross_prepare: null pointer");
+    KSG_REQUIRE(nq > 0 && nq < (1ll << 31) - 1024 && ldq >= nq, "ksg_cross_prepare: need 0 < nq < 2^31 and ldq >= nq");
+    KSG_REQUIRE(P->primary == -1 && P->curve_keys, "ksg_cross_prepare: the candidate set must be in curve order (primary = -1)");
+    const int dim = P->dim;
+    const CrossLayout L = cross_layout(nq, dim);
+    if (buffer_bytes < L.total) {
+        set_error("ksg_cross_prepare: buffer of %zu bytes needed, %zu given", L.total, buffer_bytes);
+        return KSG_EWORKSPACE;
+    }
+    char* base = (char*)d_buffer;
+    ksg_cross X;
+    memset(&X, 0, sizeof(X));
+    X.nq = nq; X.ld = L.ld;
+    X.perm = (int32_t*)(base + L.off_perm);
+    X.sorted_f64 = (double*)(base + L.off_sorted);
+    X.shadow_f32 = (float*)(base + L.off_shadow);
+    X.home = (int32_t*)(base + L.off_home);
+    X.maxabs = (double*)(base + L.off_maxabs);
+    unsigned long long* keys = (unsigned long long*)(base + L.off_keys);
+    unsigned long long* keys_out = (unsigned long long*)(base + L.off_keys_out);
+    int32_t* iota = (int32_t*)(base + L.off_iota);
+    double* stats = (double*)(base + L.off_stats);
+    int32_t* scratch_flag = (int32_t*)(base + L.off_stats + (size_t)dim * STATS_BLOCKS * 2 * 8);
+    cudaStream_t st = as_stream2(stream);
+    const unsigned nb = (unsigned)ceil_div(nq, 256);
+    int rank_bits, bits;
+    curve_bits(P->n, dim, &rank_bits, &bits);
+    switch (dim) {
+#define KSG_CROSS(D) case D: cross_key_kernel<D><<<nb, 256, 0, st>>>(d_queries, ldq, nq, P->axis_vals, P->ld, P->n, dim, rank_bits, bits, keys, iota); break;
+        KSG_CROSS(1) KSG_CROSS(2) KSG_CROSS(3) KSG_CROSS(4) KSG_CROSS(5) KSG_CROSS(6) KSG_CROSS(7) KSG_CROSS(8)
+#undef KSG_CROSS
+        default: cross_key_kernel<0><<<nb, 256, 0, st>>>(d_queries, ldq, nq, P->axis_vals, P->ld, P->n, dim, rank_bits, bits, keys, iota);
+    }
+    KSG_LAUNCHED2();
+    size_t need = L.cub_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(base + L.off_cub, need, keys, keys_out, iota, X.perm, (int)nq, 0,
+                                                    bits * dim, st);
+    if (e != cudaSuccess) { set_error("cub SortPairs (cross): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    note_launch();
+    cross_gather_kernel<<<nb, 256, 0, st>>>(d_queries, ldq, nq, dim, P->dim_padded, X.perm, keys_out, P->center,
+                                            (const unsigned long long*)P->curve_keys, P->n, X.sorted_f64, L.ld,
+                                            X.shadow_f32, X.home);
+    KSG_LAUNCHED2();
+    KSG_CUDA_TRY(cudaMemsetAsync(scratch_flag, 0, 64, st));
+    stats_stage1_kernel<<<dim3(STATS_BLOCKS, dim), 256, 0, st>>>(d_queries, ldq, nq, stats, scratch_flag);
+    KSG_LAUNCHED2();
+    cross_maxabs_kernel<<<1, KSG_MAX_DIM, 0, st>>>(stats, dim, P->center, P->maxabs, X.maxabs);
+    KSG_LAUNCHED2();
+    *h_out = X;
+    return KSG_OK;
+}
+
+int ksg_fast_knn_cross(const ksg_prepared* P, const ksg_cross* X, int64_t q_begin, int64_t q_end, int kprime,
+                       double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged, void* d_workspace,
+                       size_t workspace_bytes, void* stream) {
+    KSG_REQUIRE(P && X && d_eps_out && d_flags && d_n_flagged && d_workspace, "ksg_fast_knn_cross: null pointer");
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= X->nq, "ksg_fast_knn_cross: bad query range");
+    KSG_REQUIRE(kprime >= 1 && kprime + KNN_MARGIN <= KNN_MAX_KCAP, "ksg_fast_knn_cross: kprime out of range (k' + 3 <= 64)");
+    if (P->dim_padded > 8) {
+        set_error("ksg_fast_knn_cross: the fp32 filter is instantiated for up to 8 dimensions (got %d)", P->dim);
+        return KSG_EUNSUPPORTED;
+    }
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    FastKnnPlan p = fast_knn_plan(P->n, nq, P->dim, kprime, 1);
+    if (workspace_bytes < p.total()) {
+        set_error("ksg_fast_knn_cross: workspace of %zu bytes needed, %zu given", p.total(), workspace_bytes);
+        return KSG_EWORKSPACE;
+    }
+    cudaStream_t st = as_stream2(stream);
+    KnnF32Args a;
+    a.shadow = P->shadow_f32; a.tile_box = P->tile_box; a.sub_box = P->sub_box; a.n_tiles = P->n_padded / FAST_TILE;
+    a.q_begin = q_begin; a.nq = nq; a.q_index = nullptr; a.kcap = p.kcap; a.splits = 1; a.windowed = 1;
+    a.maxabs = X->maxabs; a.dim = P->dim;
+    a.qshadow = X->shadow_f32; a.qhome = X->home;
+    a.part_d32 = (float*)d_workspace;
+    a.part_idx = (int32_t*)((char*)d_workspace + p.d32_bytes);
+    a.tile_counter = (unsigned long long*)((char*)P->flags + 16);
+    a.st = st;
+    char* w = (char*)d_workspace + p.d32_bytes + p.idx_bytes;
+    a.seed_thr = (float*)w;                      w += p.seed_bytes;
+    a.plan = w;                                  w += p.plan_bytes;
+    a.plan_capacity = p.plan_capacity;
+    a.plan_count = (int32_t*)w;                  w += p.count_bytes / 2;
+    a.plan_first = (int32_t*)w;                  w += p.count_bytes / 2;
+    a.unit_first = (int32_t*)w;                  w += p.first_bytes;
+    a.unit_block = (int32_t*)w;                  w += p.ublock_bytes;
+    a.unit_meta = (int32_t*)w;
+    a.max_units = p.max_units;
+    int rc = launch_knn_plan(P->dim_padded, a);
+    if (rc) return rc;
+    rc = launch_knn_units(P->dim_padded, a);
+    if (rc) return rc;
+    knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, 1, kprime,
+                                                                   P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
+                                                                   nullptr, X->maxabs, a.seed_thr, a.unit_first, p.qb,
+                                                                   P->perm, nullptr, X->sorted_f64, X->ld, d_eps_out,
+                                                                   d_flags, d_n_flagged);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

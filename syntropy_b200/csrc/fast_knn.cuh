@@ -120,8 +120,15 @@ template <int DP, int Q, int KC>  // KC > 0: seed lists of KC entries in registe
 static __global__ void __launch_bounds__(FAST_THREADS)
 knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
                 int64_t q_begin, int64_t nq, int kcap, const double* __restrict__ maxabs, int dim,
+                const float* __restrict__ qshadow, const int32_t* __restrict__ qhome,
                 float* __restrict__ seed_thr, int2* __restrict__ plan, int64_t plan_capacity,
                 int32_t* __restrict__ plan_count, int32_t* __restrict__ plan_first, int32_t* __restrict__ meta) {
+    // qshadow / qhome (optional, cross-set search): the queries are rows [q_begin, q_begin + nq) of
+    // qshadow -- foreign points in the candidate set's centred frame, ordered along the candidates'
+    // curve -- and qhome[row] is the candidate row next to each of them on the curve: the seeds come
+    // from the candidates around it (the home row included: it is not the query itself).
+    const float* qrows = qshadow ? qshadow : shadow;
+    const int self_skip = qshadow ? 0 : 1;
     constexpr int QB = FAST_THREADS * Q;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* lst_d = reinterpret_cast<float*>(smem_raw);  // kcap * QB (values only)
@@ -141,9 +148,9 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
     for (int j = 0; j < Q; ++j) {
         const int64_t qi = qb0 + j * FAST_THREADS + tid;
         if (qi >= nq) continue;
-        const int64_t row = q_begin + qi;
         float2 q[DP / 2];
-        load_row<DP>(shadow + row * DP, q);
+        load_row<DP>(qrows + (q_begin + qi) * DP, q);
+        const int64_t row = qhome ? (int64_t)qhome[q_begin + qi] : q_begin + qi;  // seeds: candidates around it
 #pragma unroll
         for (int h = 0; h < DP / 2; ++h) {
             blo[2 * h] = fminf(blo[2 * h], q[h].x);         bhi[2 * h] = fmaxf(bhi[2 * h], q[h].x);
@@ -159,7 +166,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
             for (int off = 1; off <= KNN_SEED_W; ++off)
 #pragma unroll
                 for (int sgn = -1; sgn <= 1; sgn += 2) {
-                    const int64_t r2 = row + sgn * off;
+                    const int64_t r2 = sgn > 0 ? row + off - 1 + self_skip : row - off;
                     const bool inside = r2 >= 0 && r2 < n_rows;
                     float2 cc[DP / 2];
                     load_row<DP>(shadow + (inside ? r2 : row) * DP, cc);
@@ -178,7 +185,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
             for (int off = 1; off <= KNN_SEED_W; ++off)
 #pragma unroll 1
                 for (int sgn = -1; sgn <= 1; sgn += 2) {
-                    const int64_t r2 = row + sgn * off;
+                    const int64_t r2 = sgn > 0 ? row + off - 1 + self_skip : row - off;
                     if (r2 < 0 || r2 >= n_rows) continue;
                     float2 cc[DP / 2];
                     load_row<DP>(shadow + r2 * DP, cc);
@@ -224,7 +231,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
         const float thr = seed_thr[qi];
         if (thr < CUDART_INF_F && thr > cut) { seed_thr[qi] = KNN_DEFERRED; continue; }
         float2 q[DP / 2];
-        load_row<DP>(shadow + (q_begin + qi) * DP, q);
+        load_row<DP>(qrows + (q_begin + qi) * DP, q);
 #pragma unroll
         for (int h = 0; h < DP / 2; ++h) {
             blo[2 * h] = fminf(blo[2 * h], q[h].x);         bhi[2 * h] = fmaxf(bhi[2 * h], q[h].x);
@@ -239,7 +246,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
     // The lists live in one pool (meta[4..5] = 64-bit bump cursor): a first sweep counts the survivors,
     // the block reserves that many entries, a second sweep writes them.
     const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
-    const int64_t own = mid / FAST_TILE;
+    const int64_t own = (qhome ? (int64_t)qhome[mid] : mid) / FAST_TILE;
     auto gap_of = [&](int64_t pos, int64_t& t) -> float {
         t = walk_tile(pos, own, n_tiles);
         float gap[DP];
@@ -576,7 +583,8 @@ constexpr int UNITS_THREADS = FAST_THREADS + 32;         // + 1 copy warp
 template <int DP, int Q, int STAGES, bool HITMASK>
 static __global__ void __launch_bounds__(UNITS_THREADS)
 knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub_box, int64_t n_tiles,
-                 int64_t q_begin, int64_t nq, int kcap, const float* __restrict__ seed_thr,
+                 int64_t q_begin, int64_t nq, int kcap, const float* __restrict__ qshadow,
+                 const int32_t* __restrict__ qhome, const float* __restrict__ seed_thr,
                  const int2* __restrict__ plan, const int32_t* __restrict__ plan_count,
                  const int32_t* __restrict__ plan_first, const int32_t* __restrict__ unit_first,
                  const int32_t* __restrict__ unit_block, int32_t* __restrict__ meta, float* __restrict__ part_d32,
@@ -651,7 +659,7 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
             for (int j = 0; j < Q; ++j) {
                 const int64_t qi = qb0 + warp * (32 * Q) + j * 32 + lane;
                 const bool in = qi < nq;
-                load_row<DP>(shadow + (q_begin + (in ? qi : 0)) * DP, q[j]);
+                load_row<DP>((qshadow ? qshadow : shadow) + (q_begin + (in ? qi : 0)) * DP, q[j]);
                 const float s = in ? seed_thr[qi] : -1.0f;
                 seed[j] = s < 0.0f ? -1.0f : s;  // deferred / dead slots never insert
                 thr[j] = seed[j];
@@ -684,7 +692,8 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
             // ---------------- copy warp: stream the unit's tiles, then an end marker.  All 32
             // lanes walk the list together (no divergence, no spinning lanes); lane 0 issues.
             const int2* lst = plan + (pfirst < 0 ? 0 : pfirst);
-            const int64_t own = (q_begin + min(qb0 + QB / 2, nq - 1)) / FAST_TILE;  // as in the planning pass
+            const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
+            const int64_t own = (qhome ? (int64_t)qhome[mid] : mid) / FAST_TILE;  // as in the planning pass
             for (int next = first; next <= last; ++next) {
                 int tile = -1;
                 if (next < last) {
@@ -857,7 +866,10 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
                   int64_t nq, const int32_t* __restrict__ q_index, const double* __restrict__ maxabs,
                   const float* __restrict__ seed_thr, const int32_t* __restrict__ unit_first, int qb,
                   const int32_t* __restrict__ perm, int64_t* __restrict__ idx_out,
+                  const double* __restrict__ qsorted, int64_t qld,
                   double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
+    // qsorted (optional, cross-set search): the float64 query coordinates come from this [dim][qld]
+    // array (rows q_begin + qi) instead of the candidate set itself.
     // idx_out (optional, [nq][kp] int64): the k' nearest points as positions in the prepared
     // order, ascending by (exact distance, original sample index) -- the order the dense float64
     // kernel's merge produces.  All points tied with the k'-th distance are among the examined
@@ -913,7 +925,7 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     int32_t exact_j[KNN_MAX_KCAP], exact_o[KNN_MAX_KCAP];  // prepared position / original index (idx_out only)
     int got = 0, examined = 0;
     double qc[KSG_MAX_DIM];
-    for (int d = 0; d < dim; ++d) qc[d] = sorted[(int64_t)d * ld + row_q];
+    for (int d = 0; d < dim; ++d) qc[d] = qsorted ? qsorted[(int64_t)d * qld + row_q] : sorted[(int64_t)d * ld + row_q];
     for (int s = s_begin; s < s_end && !overflow; ++s) {
         // a full list whose tail is still inside the band may have dropped in-band candidates
         const float tail = part_d32[((int64_t)s * kcap + (kcap - 1)) * stride + off];

@@ -16,6 +16,9 @@ struct KnnF32Args {
     int64_t n_tiles;
     int64_t q_begin, nq;
     const int32_t* q_index;  // optional: explicit query rows (then q_begin is ignored)
+    // optional, cross-set search (windowed only): queries = rows of qshadow, seeded around qhome
+    const float* qshadow;
+    const int32_t* qhome;
     int kcap, splits, windowed;
     const double* maxabs;
     int dim;

@@ -129,6 +129,59 @@ static __global__ void rank_scatter_kernel(const int32_t* __restrict__ sorted_or
 // curve", AIP Conf. Proc. 707, 2004) and bit-interleaved (level-major, MSB first).  Unlike
 // the plain Z-order interleave the Hilbert curve has no jumps: any run of consecutive
 // points is a connected blob, so 512-point tiles and query blocks get tight boxes.
+// X[0..dim) (the top `bits` bits of every coordinate's rank) -> Hilbert index, see above
+template <int CAP>
+__device__ __forceinline__ unsigned long long hilbert_index(unsigned int (&X)[CAP], int dim, int bits) {
+    if (dim > 1) {
+        const unsigned int M = 1u << (bits - 1);
+        for (unsigned int Q = M; Q > 1u; Q >>= 1) {
+            const unsigned int P = Q - 1u;
+#pragma unroll
+            for (int d = 0; d < CAP; ++d)
+                if (d < dim) {
+                    if (X[d] & Q) {
+                        X[0] ^= P;  // invert the low bits of axis 0
+                    } else {
+                        const unsigned int t = (X[0] ^ X[d]) & P;  // exchange low bits of axes 0 and d
+                        X[0] ^= t;
+                        X[d] ^= t;
+                    }
+                }
+        }
+#pragma unroll
+        for (int d = 1; d < CAP; ++d)
+            if (d < dim) X[d] ^= X[d - 1];  // Gray encode
+        unsigned int t = 0u;
+        for (unsigned int Q = M; Q > 1u; Q >>= 1) {
+            unsigned int last = 0u;
+#pragma unroll
+            for (int d = 0; d < CAP; ++d)
+                if (d == dim - 1) last = X[d];
+            if (last & Q) t ^= Q - 1u;
+        }
+#pragma unroll
+        for (int d = 0; d < CAP; ++d)
+            if (d < dim) X[d] ^= t;
+    }
+    unsigned long long key = 0ull;
+    for (int level = 0; level < bits; ++level)
+#pragma unroll
+        for (int d = 0; d < CAP; ++d)
+            if (d < dim) key = (key << 1) | ((X[d] >> (bits - 1 - level)) & 1u);
+    return key;
+}
+
+// bits per coordinate of the curve for n points in `dim` coordinates (shared by ksg_prepare and
+// ksg_cross_prepare, which must place foreign points on the SAME curve)
+static inline void curve_bits(int64_t n, int dim, int* rank_bits, int* bits) {
+    int rb = 1;
+    while ((1ll << rb) < n) ++rb;
+    int b = 63 / dim;
+    if (b > rb) b = rb;
+    *rank_bits = rb;
+    *bits = b;
+}
+
 template <int DIM>  // DIM > 0: compile-time dimension (coordinates stay in registers); 0: run-time `dim`
 static __global__ void morton_key_kernel(const int32_t* __restrict__ ranks, int64_t ld, int64_t n, int dim_rt,
                                          int rank_bits, int bits, unsigned long long* __restrict__ keys) {
@@ -137,36 +190,81 @@ static __global__ void morton_key_kernel(const int32_t* __restrict__ ranks, int6
     const int dim = DIM > 0 ? DIM : dim_rt;
     unsigned int X[DIM > 0 ? DIM : KSG_MAX_DIM];
 #pragma unroll
-    for (int d = 0; d < dim; ++d)
-        X[d] = ((unsigned int)ranks[(int64_t)d * ld + i]) >> (rank_bits - bits);
-    if (dim > 1) {
-        const unsigned int M = 1u << (bits - 1);
-        for (unsigned int Q = M; Q > 1u; Q >>= 1) {
-            const unsigned int P = Q - 1u;
+    for (int d = 0; d < (DIM > 0 ? DIM : KSG_MAX_DIM); ++d)
+        if (d < dim) X[d] = ((unsigned int)ranks[(int64_t)d * ld + i]) >> (rank_bits - bits);
+    keys[i] = hilbert_index(X, dim, bits);
+}
+
+// ---- cross-set queries (ksg_cross_prepare): foreign points placed on the candidate set's curve.
+// rank of a query coordinate = number of candidate values below it (binary search in the
+// coordinate's sorted array), clamped into the candidates' rank range.
+template <int DIM>
+static __global__ void cross_key_kernel(const double* __restrict__ qry, int64_t ldq, int64_t nq,
+                                        const double* __restrict__ axis_vals, int64_t ld, int64_t n, int dim_rt,
+                                        int rank_bits, int bits, unsigned long long* __restrict__ keys,
+                                        int32_t* __restrict__ iota) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int dim = DIM > 0 ? DIM : dim_rt;
+    unsigned int X[DIM > 0 ? DIM : KSG_MAX_DIM];
 #pragma unroll
-            for (int d = 0; d < dim; ++d) {
-                if (X[d] & Q) {
-                    X[0] ^= P;  // invert the low bits of axis 0
-                } else {
-                    const unsigned int t = (X[0] ^ X[d]) & P;  // exchange low bits of axes 0 and d
-                    X[0] ^= t;
-                    X[d] ^= t;
-                }
+    for (int d = 0; d < (DIM > 0 ? DIM : KSG_MAX_DIM); ++d)
+        if (d < dim) {
+            const double x = qry[(int64_t)d * ldq + i];
+            const double* v = axis_vals + (int64_t)d * ld;
+            int64_t lo = 0, hi = n;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (v[mid] < x) lo = mid + 1; else hi = mid;
             }
+            if (lo > n - 1) lo = n - 1;
+            X[d] = ((unsigned int)lo) >> (rank_bits - bits);
         }
-#pragma unroll
-        for (int d = 1; d < dim; ++d) X[d] ^= X[d - 1];  // Gray encode
-        unsigned int t = 0u;
-        for (unsigned int Q = M; Q > 1u; Q >>= 1)
-            if (X[dim - 1] & Q) t ^= Q - 1u;
-#pragma unroll
-        for (int d = 0; d < dim; ++d) X[d] ^= t;
+    keys[i] = hilbert_index(X, dim, bits);
+    iota[i] = (int32_t)i;
+}
+
+// queries in cross order: float64 SoA copy, fp32 rows centred with the CANDIDATE set's centre
+// (+inf padding rows), and the candidate row next to each query on the curve
+static __global__ void __launch_bounds__(256)
+cross_gather_kernel(const double* __restrict__ qry, int64_t ldq, int64_t nq, int dim, int dim_padded,
+                    const int32_t* __restrict__ perm, const unsigned long long* __restrict__ keys_sorted,
+                    const double* __restrict__ center, const unsigned long long* __restrict__ cand_keys, int64_t n,
+                    double* __restrict__ sorted, int64_t ld, float* __restrict__ shadow, int32_t* __restrict__ home) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= nq) return;
+    const int64_t src = perm[i];
+    for (int d = 0; d < dim_padded; ++d) {
+        float s = 0.0f;
+        if (d < dim) {
+            const double v = qry[(int64_t)d * ldq + src];
+            sorted[(int64_t)d * ld + i] = v;
+            s = __double2float_rn(__dsub_rn(v, center[d]));
+        }
+        shadow[i * dim_padded + d] = s;
     }
-    unsigned long long key = 0ull;
-    for (int level = 0; level < bits; ++level)
-#pragma unroll
-        for (int d = 0; d < dim; ++d) key = (key << 1) | ((X[d] >> (bits - 1 - level)) & 1u);
-    keys[i] = key;
+    const unsigned long long key = keys_sorted[i];
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (cand_keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    home[i] = (int32_t)(lo > n - 1 ? n - 1 : lo);
+}
+
+// maxabs2[d] = max(candidates' maxabs[d], max over the queries of |x - centre|) (rounded up)
+static __global__ void cross_maxabs_kernel(const double* __restrict__ partial, int dim, const double* __restrict__ center,
+                                           const double* __restrict__ maxabs, double* __restrict__ out) {
+    const int d = threadIdx.x;
+    if (d >= dim) return;
+    double lo = CUDART_INF, hi = -CUDART_INF;
+    for (int b = 0; b < STATS_BLOCKS; ++b) {
+        lo = fmin(lo, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 0]);
+        hi = fmax(hi, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 1]);
+    }
+    if (!(isfinite(lo) && isfinite(hi))) { lo = center[d]; hi = center[d]; }
+    const double m = fmax(hi - center[d], center[d] - lo) * (1.0 + 1e-12) + 1e-300;
+    out[d] = fmax(maxabs[d], m);
 }
 
 static __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {

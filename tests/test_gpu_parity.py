@@ -439,3 +439,18 @@ def test_ksg2_vs_oracle_multidimensional_marginals(knn):
     ptw, avg = knn.total_correlation(data[:5], 4, algorithm=2)
     ref_ptw, ref_avg = orc.total_correlation(data[:5], 4, algorithm=2)
     close(ptw, ref_ptw); close(avg, ref_avg)
+
+
+@pytest.mark.parametrize("dim,n,m,k,shift", [(3, 20_000, 15_000, 1, 0.5), (2, 9_000, 30_000, 4, 0.0),
+                                             (5, 6_000, 6_000, 3, 2.0), (1, 5_000, 7_000, 2, 0.3),
+                                             (3, 4_000, 3_000, 1, 25.0)])
+def test_kl_divergence_cross_set_search_vs_oracle(knn, dim, n, m, k, shift):
+    """The prior-sample radii come from a cross-set search (posterior points placed on the prior's
+    curve); different sample sizes, overlapping and far-apart clouds (shift = 25: every query lies
+    outside the prior's bounding box)."""
+    rng = np.random.default_rng(1000 + dim)
+    post = rng.standard_normal((dim, n)) * rng.uniform(0.5, 2.0, size=(dim, 1)) + shift
+    prior = rng.standard_normal((dim, m)) * 1.3
+    ptw, avg = knn.kullback_leibler_divergence(post, prior, k)
+    ref_ptw, ref_avg = orc.kullback_leibler_divergence(post, prior, k)
+    close(ptw, ref_ptw); close(avg, ref_avg)
