@@ -107,7 +107,9 @@ def _pool():
         from concurrent.futures import ThreadPoolExecutor
         import os
 
-        _copy_pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+        # one process per GPU shares the host cores with its siblings (torchrun sets LOCAL_WORLD_SIZE)
+        siblings = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        _copy_pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // (2 * siblings))))
     return _copy_pool
 
 
