@@ -454,3 +454,84 @@ def test_kl_divergence_cross_set_search_vs_oracle(knn, dim, n, m, k, shift):
     ptw, avg = knn.kullback_leibler_divergence(post, prior, k)
     ref_ptw, ref_avg = orc.kullback_leibler_divergence(post, prior, k)
     close(ptw, ref_ptw); close(avg, ref_avg)
+
+
+# ------------------------------------------------------------------ full-size properties (C3, C4, C5)
+@pytest.fixture()
+def windowed():
+    """(engine module, knn module) with the production engine selected: the full BASELINE sizes are
+    run on it only (the dense engines need minutes there; they are compared at moderate n above)."""
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from syntropy_b200 import _engine, knn as mod
+
+    old = _engine.config.engine
+    _engine.config.engine = "windowed"
+    yield _engine, mod
+    _engine.config.engine = old
+
+
+def _subset_parity(E, rows, k, subs, n_check=256, seed=1):
+    """radii / counts of ALL samples from the product path; oracle (C restatement, brute force in
+    float64 against the full point set) on a random query subset."""
+    from oracle import ksg_oracle_c as oc
+
+    n = rows.shape[1]
+    eps, counts = radius_and_counts(E, rows, k, subs)
+    sel = np.sort(np.random.default_rng(seed).choice(n, size=n_check, replace=False))
+    ref = oc.knn_radius(rows, k + 1, queries=rows[:, sel])
+    assert np.array_equal(eps[sel], ref)
+    for row, s in enumerate(subs):
+        want = oc.count_within(rows[list(s), :], ref, queries=rows[list(s), :][:, sel])
+        assert np.array_equal(counts[row, sel], want), s
+    return eps, counts
+
+
+def test_c3_full_size(windowed):
+    """C3: Frenzel-Pompe CMI 2D;2D|2D, n = 1e6, k = 4 (windowed engine)."""
+    E, knn = windowed
+    data, call = workloads.c3_cmi()
+    subs = [(4, 5), (0, 1, 4, 5), (2, 3, 4, 5), (0, 1, 2, 3, 4, 5)]
+    eps, counts = _subset_parity(E, data, call["k"], subs)
+    assert (counts[3] == call["k"] - 1).all()                 # k-1 points strictly inside the k-th radius
+    assert (counts[0] >= counts[1]).all() and (counts[0] >= counts[2]).all()   # z contains xz and yz
+    assert (counts[1] >= counts[3]).all() and (counts[2] >= counts[3]).all()
+    ptw, avg = knn.conditional_mutual_information(call["idxs_x"], call["idxs_y"], call["idxs_z"], call["k"], data)
+    assert ptw.shape == (1, data.shape[1]) and np.isfinite(ptw).all()
+    assert avg == pytest.approx(float(np.mean(ptw)), rel=1e-12)
+    assert 0.5 < avg < 1.0
+
+
+def test_c4_full_size(windowed):
+    """C4: O-information / TC / DTC / S over 8 variables, n = 250 000, k = 4: all 16 marginal count
+    vectors from one joint radius, and the identities O = TC - DTC, S = TC + DTC (pointwise)."""
+    E, knn = windowed
+    data, call = workloads.c4_oinfo()
+    m = data.shape[0]
+    subs = [tuple(j for j in range(m) if j != d) for d in range(m)] + [(d,) for d in range(m)]
+    eps, counts = _subset_parity(E, data, call["k"], subs)
+    for d in range(m):
+        assert (counts[m + d] >= counts[(d + 1) % m]).all()   # a single coordinate contains any superset of it
+    tc_p, tc = knn.total_correlation(data, call["k"])
+    dtc_p, dtc = knn.dual_total_correlation(data, call["k"])
+    o_p, o = knn.o_information(data, call["k"])
+    s_p, s = knn.s_information(data, call["k"])
+    assert np.abs(o_p - (tc_p - dtc_p)).max() < 1e-9 and np.abs(s_p - (tc_p + dtc_p)).max() < 1e-9
+    assert o == pytest.approx(tc - dtc, abs=1e-10) and s == pytest.approx(tc + dtc, abs=1e-10)
+
+
+def test_c5_full_size(windowed):
+    """C5: MI(present; past) of the delay-embedded 4-channel series, n = 4e6, k = 5 (8-D joint,
+    two 4-D marginals counted in their own order), and MI(x; y) = MI(y; x)."""
+    E, knn = windowed
+    data, call = workloads.c5_info_rate()
+    subs = [(0, 1, 2, 3), (4, 5, 6, 7)]
+    eps, counts = _subset_parity(E, data, call["k"], subs, n_check=192)
+    assert (counts >= call["k"] - 1).all()
+    ptw, avg = knn.mutual_information(call["idxs_x"], call["idxs_y"], call["k"], data)
+    ptw2, avg2 = knn.mutual_information(call["idxs_y"], call["idxs_x"], call["k"], data)
+    assert np.isfinite(ptw).all() and 1.0 < avg < 1.7
+    # swapping the groups permutes the joint coordinates: same radii, same counts; the two
+    # psi terms are then subtracted in the other order, which may differ in the last bit
+    assert np.abs(ptw - ptw2).max() < 1e-12 and avg == pytest.approx(avg2, rel=1e-13)
