@@ -159,7 +159,7 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
     KSG_CUDA_TRY(cudaMemsetAsync(P.flags, 0, 64, st));
     stats_stage1_kernel<<<dim3(STATS_BLOCKS, dim), 256, 0, st>>>(d_points, ld, n, stats, P.flags);
     KSG_LAUNCHED2();
-    stats_stage2_kernel<<<1, KSG_MAX_DIM, 0, st>>>(stats, dim, P.center, P.maxabs);
+    stats_stage2_kernel<<<dim, 32, 0, st>>>(stats, dim, P.center, P.maxabs);
     KSG_LAUNCHED2();
     iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
     KSG_LAUNCHED2();

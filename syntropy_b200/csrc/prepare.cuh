@@ -68,15 +68,21 @@ stats_stage1_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, doubl
     }
 }
 
+// one warp per dimension (blockIdx.x = d)
 static __global__ void stats_stage2_kernel(const double* __restrict__ partial, int dim, double* __restrict__ center,
                                     double* __restrict__ maxabs) {
-    const int d = threadIdx.x;
+    const int d = blockIdx.x;
     if (d >= dim) return;
     double lo = CUDART_INF, hi = -CUDART_INF;
-    for (int b = 0; b < STATS_BLOCKS; ++b) {
+    for (int b = threadIdx.x; b < STATS_BLOCKS; b += 32) {
         lo = fmin(lo, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 0]);
         hi = fmax(hi, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 1]);
     }
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if (threadIdx.x != 0) return;
     if (!(isfinite(lo) && isfinite(hi))) { lo = 0.0; hi = 0.0; }  // flagged elsewhere; keep the math finite
     const double c = 0.5 * lo + 0.5 * hi;
     center[d] = c;
