@@ -287,8 +287,8 @@ static int launch_count_full_dp(const CountF32Args& a, const CountUnitsArgs& w) 
         a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.thresholds, (int2*)w.plan, w.plan_capacity, w.plan_count,
         w.plan_first, w.unit_meta);
     note_launch();
-    knn_unit_table_kernel<<<1, 1024, 0, a.st>>>(w.plan_count, qblocks, w.max_units, w.unit_first, w.unit_block,
-                                                 w.unit_meta);
+    knn_unit_table_kernel<<<1, 1024, 0, a.st>>>(w.plan_count, qblocks, w.max_units, COUNT_UNIT_MIN_TILES, w.unit_first,
+                                                 w.unit_block, w.unit_meta);
     note_launch();
     auto kern = count_units_kernel<DP, Q, ST>;
     const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float);

@@ -41,7 +41,7 @@ static int launch_plan_kc(const KnnF32Args& a) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_plan_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     knn_unit_table_kernel<<<1, 1024, 0, a.st>>>(a.plan_count, ceil_div(a.nq, FAST_THREADS * Q), a.max_units,
-                                                 a.unit_first, a.unit_block, a.unit_meta);
+                                                 KNN_UNIT_MIN_TILES, a.unit_first, a.unit_block, a.unit_meta);
     note_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_unit_table_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
@@ -75,7 +75,9 @@ static int launch_units_dp(const KnnF32Args& a) {
 
 template <int DP>
 static int launch_plan_dp(const KnnF32Args& a) {
+    if (a.kcap <= 6) return launch_plan_kc<DP, 6>(a);
     if (a.kcap <= 8) return launch_plan_kc<DP, 8>(a);
+    if (a.kcap <= 10) return launch_plan_kc<DP, 10>(a);
     if (a.kcap <= 12) return launch_plan_kc<DP, 12>(a);
     return launch_plan_kc<DP, 0>(a);
 }

@@ -36,6 +36,8 @@ constexpr float KNN_DEFER_CUT = 4.0f;   // defer a query whose seeded radius exc
 constexpr float KNN_DEFERRED = -2.0f;   // sentinel distance marking a deferred query's list
 constexpr int KNN_PLAN_CAP = 1024;      // tile-list pool: this many entries per query block ON AVERAGE
 constexpr int KNN_UNIT_MIN_TILES = 16;  // a work unit = one query block x at most `chunk` planned tiles
+constexpr int COUNT_UNIT_MIN_TILES = 64;  // count units are cheap per tile (culled / inside sub-tiles): a unit
+                                          // must be long enough to amortise the latency of its first bulk copy
 constexpr int KNN_UNIT_FACTOR = 2;      // chunk grows so that #units <= (1 + FACTOR) * #blocks
 
 // ---- fp32 error band of the shadow copy (see DESIGN.md "Exactness")
@@ -493,7 +495,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
 //   meta[0] = number of units, meta[1] = chunk, meta[2] = work-queue cursor (zeroed here),
 //   meta[4..5] = tile-list pool cursor, 64 bit (zeroed before the planning pass)
 static __global__ void __launch_bounds__(1024)
-knn_unit_table_kernel(const int32_t* __restrict__ plan_count, int64_t n_blocks, int64_t max_units,
+knn_unit_table_kernel(const int32_t* __restrict__ plan_count, int64_t n_blocks, int64_t max_units, int min_tiles,
                       int32_t* __restrict__ unit_first, int32_t* __restrict__ unit_block,
                       int32_t* __restrict__ meta) {
     __shared__ long long s_red[32];
@@ -511,7 +513,7 @@ knn_unit_table_kernel(const int32_t* __restrict__ plan_count, int64_t n_blocks, 
         long long total = 0;
         for (int w = 0; w < 32; ++w) total += s_red[w];
         long long chunk = (total + KNN_UNIT_FACTOR * n_blocks - 1) / (KNN_UNIT_FACTOR * n_blocks);
-        if (chunk < KNN_UNIT_MIN_TILES) chunk = KNN_UNIT_MIN_TILES;
+        if (chunk < min_tiles) chunk = min_tiles;
         s_chunk = (int)chunk;
     }
     __syncthreads();
