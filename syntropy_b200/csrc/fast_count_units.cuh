@@ -27,7 +27,14 @@ static __global__ void __launch_bounds__(FAST_THREADS)
 count_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
                   int64_t q_begin, int64_t nq, const float* __restrict__ thresholds, int2* __restrict__ plan,
                   int64_t plan_capacity, int32_t* __restrict__ plan_count, int32_t* __restrict__ plan_first,
-                  int32_t* __restrict__ meta) {
+                  int32_t* __restrict__ meta, int32_t* __restrict__ counts) {
+    // Tiles are classified against the whole block here: OUTSIDE (nearest box distance >= the
+    // block's largest threshold) -> not listed; INSIDE (farthest box distance < the block's smallest
+    // threshold: every pair of the block with the tile is inside) -> not listed either, its 512
+    // candidates are added to every query's count right here (the padded last tile has an infinite
+    // box and is never inside); the rest is listed for the filter kernel.  With radii that hold
+    // thousands of points (low-dimensional marginals of a high-dimensional joint radius, sample
+    // entropy) most relevant tiles are INSIDE and are never even fetched.
     constexpr int QB = FAST_THREADS * Q;
     __shared__ TileQueueShared sh;
     __shared__ int s_base;
@@ -37,7 +44,7 @@ count_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ ti
     float blo[DP], bhi[DP];
 #pragma unroll
     for (int d = 0; d < DP; ++d) { blo[d] = CUDART_INF_F; bhi[d] = -CUDART_INF_F; }
-    float tmax = -CUDART_INF_F;
+    float tmax = -CUDART_INF_F, tmin = CUDART_INF_F;
 #pragma unroll 1
     for (int j = 0; j < Q; ++j) {
         const int64_t qi = qb0 + j * FAST_THREADS + tid;
@@ -50,27 +57,39 @@ count_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ ti
             blo[2 * h + 1] = fminf(blo[2 * h + 1], q[h].y); bhi[2 * h + 1] = fmaxf(bhi[2 * h + 1], q[h].y);
         }
         tmax = fmaxf(tmax, thresholds[qi]);
+        tmin = fminf(tmin, thresholds[qi]);
     }
     block_query_box<DP>(blo, bhi, sh);
     const float R = block_max(tmax, sh);
+    const float Tmin = -block_max(-tmin, sh);
 
     const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
     const int64_t own = mid / FAST_TILE;
-    auto gap_of = [&](int64_t pos, int64_t& t) -> float {
+    // nearest box distance; `inside` = the farthest one is below every threshold of the block
+    auto gap_of = [&](int64_t pos, int64_t& t, bool& inside) -> float {
         t = walk_tile(pos, own, n_tiles);
-        float gap[DP];
-        box_gaps<DP>(tile_box, t, sh, gap);
-        float dist = gap[0];
+        float near = 0.0f, far = 0.0f;
 #pragma unroll
-        for (int d = 1; d < DP; ++d) dist = fmaxf(dist, gap[d]);
-        return dist;
+        for (int d = 0; d < DP; ++d) {
+            const float2 b = reinterpret_cast<const float2*>(tile_box)[t * DP + d];
+            const float a = b.x - sh.qhi[d], c = sh.qlo[d] - b.y;  // > 0 when the boxes are apart
+            near = fmaxf(near, fmaxf(a, c));
+            far = fmaxf(far, fmaxf(-a, -c));
+        }
+        inside = far < Tmin;
+        return near;
     };
-    int mine = 0;
+    int mine = 0, mine_inside = 0;
     for (int64_t pos = tid; pos < n_tiles; pos += FAST_THREADS) {
         int64_t t;
-        mine += gap_of(pos, t) < R;
+        bool inside;
+        const bool needed = gap_of(pos, t, inside) < R;
+        mine += needed && !inside;
+        mine_inside += needed && inside;
     }
     const int total = (int)(block_sum((float)mine, sh) + 0.5f);
+    const int n_inside = (int)(block_sum((float)mine_inside, sh) + 0.5f);
+
     if (tid == 0) {
         int base = -1;
         if (total > 0 && 2 * (int64_t)total <= n_tiles) {
@@ -83,9 +102,15 @@ count_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ ti
     __syncthreads();
     const int base = s_base;
     if (total > 0 && base < 0) {  // most tiles are needed (or the pool is full): implicit list
+        // (every tile, the INSIDE ones included: the filter kernel classifies them again per warp)
         if (tid == 0) { plan_count[blockIdx.x] = (int32_t)n_tiles; plan_first[blockIdx.x] = -1; }
         return;
     }
+    if (n_inside > 0)
+        for (int j = 0; j < Q; ++j) {
+            const int64_t qi = qb0 + j * FAST_THREADS + tid;
+            if (qi < nq) counts[qi] += n_inside * FAST_TILE;  // (the filter kernel's atomics come later)
+        }
     int2* out = plan + base;
     int done = 0;
     for (int64_t pos = 0; pos < n_tiles; pos += FAST_THREADS) {
@@ -93,8 +118,9 @@ count_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ ti
         int64_t t = 0;
         float dist = 0.0f;
         if (pos + tid < n_tiles) {
-            dist = gap_of(pos + tid, t);
-            keep = dist < R;
+            bool inside;
+            dist = gap_of(pos + tid, t, inside);
+            keep = dist < R && !inside;
         }
         const unsigned ballot = __ballot_sync(0xffffffffu, keep);
         __syncthreads();
@@ -285,7 +311,7 @@ static int launch_count_full_dp(const CountF32Args& a, const CountUnitsArgs& w) 
     if (cudaMemsetAsync(w.unit_meta, 0, 32, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
     count_plan_kernel<DP, Q><<<(unsigned)qblocks, FAST_THREADS, 0, a.st>>>(
         a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.thresholds, (int2*)w.plan, w.plan_capacity, w.plan_count,
-        w.plan_first, w.unit_meta);
+        w.plan_first, w.unit_meta, a.counts);
     note_launch();
     knn_unit_table_kernel<<<1, 1024, 0, a.st>>>(w.plan_count, qblocks, w.max_units, COUNT_UNIT_MIN_TILES, w.unit_first,
                                                  w.unit_block, w.unit_meta);
