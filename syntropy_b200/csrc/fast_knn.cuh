@@ -1,25 +1,30 @@
 // K1 fast path: k-NN radius with an fp32 tile filter and an exact fp64 refine.
 //
-// Filter (knn_f32_kernel).  Works on the prepared set (prepare.cuh): fp32 AoS shadow
-// rows, sorted by the primary coordinate, +inf padded.  One thread owns Q queries whose
-// coordinates live in registers as packed pairs; candidate tiles are bulk-copied
-// (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) into a STAGES-deep ring of
+// Both filters work on the prepared set (prepare.cuh): fp32 AoS shadow rows in space-filling
+// curve order, +inf padded, with a bounding box per 512-row tile and per 32-row sub-tile.  One
+// thread owns Q queries whose coordinates live in registers as packed pairs; candidate tiles are
+// bulk-copied (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) into a ring of
 // shared-memory buffers; all lanes read the same candidate (LDS.128 broadcasts).
-// Per (query, candidate) the hot loop is   DP/2 FADD2 (packed subtract, two dimensions
-// per issue slot) + ~DP/2 FMNMX/FMNMX3 (|.| folded into the operands) + 1/2 FMNMX3
-// (running minimum over two candidates) -- no compare, no branch.  Every BATCH
-// candidates the running minima are tested against the per-query thresholds; only on a
-// hit is the batch re-walked to insert (d32, index) into the query's sorted list in
-// shared memory.  Tiles are visited outward from the query block's own tile, so the
-// thresholds are tight after the first tile; in windowed mode a side is closed as soon
-// as the primary-coordinate gap to its next tile exceeds every threshold (+ band).
 //
-// Refine (knn_refine_kernel).  The list keeps the KCAP = k' + margin smallest fp32
-// distances.  With r32 the k'-th smallest of them and delta the fp32 error bound,
-// every point whose exact distance is <= the exact radius has d32 <= r32 + 2*delta;
-// if the list provably contains all of those (its tail lies above that bound) the exact
-// radius is the k'-th smallest float64 distance among them.  Otherwise the query is
-// flagged and recomputed by the dense fp64 kernel.
+// Dense filter (knn_f32_kernel): every tile.  Per (query, candidate) DP/2 FADD2 (packed
+// subtract, two dimensions per issue slot) + ~DP/2 FMNMX/FMNMX3 (|.| folded into the operands)
+// + 1/2 FMNMX3 (running minimum over two candidates) -- no compare, no branch.  Every BATCH
+// candidates the running minima are tested against the per-query thresholds; only on a hit is
+// the batch re-walked to insert (d32, index) into the query's sorted list in shared memory.
+// This is the brute-force roofline case, and the path of explicit query lists.
+//
+// Windowed filter (knn_plan_kernel -> knn_unit_table_kernel -> knn_units_kernel): same
+// result from ~1e-3 of the pairs.  Planning seeds every query's threshold from its neighbours
+// on the curve and lists, per block of queries, the tiles whose box is within reach; the lists
+// are cut into work units pulled by a persistent kernel (4 filter warps + 1 copy warp per CTA);
+// each filter warp culls 32-row sub-tiles against the box of its own 32*Q consecutive queries.
+// The same kernels serve cross-set searches (queries that are not candidates: qshadow / qhome).
+//
+// Refine (knn_refine_kernel).  The lists keep the KCAP = k' + margin smallest fp32 distances.
+// With r32 the k'-th smallest of them and delta the fp32 error bound, every point whose exact
+// distance is <= the exact radius has d32 <= r32 + 2*delta; if the lists provably contain all
+// of those (their tails lie above that bound) the exact radius is the k'-th smallest float64
+// distance among them.  Otherwise the query is flagged and recomputed by the dense fp64 kernel.
 #pragma once
 
 #include "common.cuh"
