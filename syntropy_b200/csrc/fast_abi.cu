@@ -159,8 +159,6 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
     KSG_CUDA_TRY(cudaMemsetAsync(P.flags, 0, 64, st));
     stats_stage1_kernel<<<dim3(STATS_BLOCKS, dim), 256, 0, st>>>(d_points, ld, n, stats, P.flags);
     KSG_LAUNCHED2();
-    stats_stage2_kernel<<<dim, 32, 0, st>>>(stats, dim, P.center, P.maxabs);
-    KSG_LAUNCHED2();
     iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
     KSG_LAUNCHED2();
     const unsigned nb = (unsigned)ceil_div(n, 256);
@@ -171,6 +169,11 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
                         P.axis_pos + (int64_t)d * L.ld, n, st);
         if (rc) return rc;
     }
+    // centre of the fp32 copy = per-coordinate MEDIAN (the bulk of the points then has small centred
+    // magnitudes, hence small fp32 error bands, even when outliers stretch the range)
+    center_median_kernel<<<1, KSG_MAX_DIM, 0, st>>>(P.axis_vals, L.ld, n, dim, P.center, P.maxabs);
+    KSG_LAUNCHED2();
+    (void)stats;
     if (primary >= 0) {
         // order = one coordinate's sorted order
         KSG_CUDA_TRY(cudaMemcpyAsync(P.perm, P.axis_pos + (int64_t)primary * L.ld, (size_t)n * 4,
@@ -290,8 +293,8 @@ int ksg_fast_knn_idx(const ksg_prepared* P, int64_t q_begin, int64_t q_end, cons
     knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, p.splits, kprime,
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    d_query_index, P->maxabs, a.seed_thr, a.unit_first,
-                                                                   p.qb, P->perm, d_idx_out, nullptr, 0, d_eps_out,
-                                                                   d_flags, d_n_flagged);
+                                                                   p.qb, P->perm, d_idx_out, nullptr, 0, P->center,
+                                                                   d_eps_out, d_flags, d_n_flagged);
     KSG_LAUNCHED2();
     return KSG_OK;
 }
@@ -427,8 +430,8 @@ int ksg_fast_knn_cross(const ksg_prepared* P, const ksg_cross* X, int64_t q_begi
     knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, 1, kprime,
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    nullptr, X->maxabs, a.seed_thr, a.unit_first, p.qb,
-                                                                   P->perm, nullptr, X->sorted_f64, X->ld, d_eps_out,
-                                                                   d_flags, d_n_flagged);
+                                                                   P->perm, nullptr, X->sorted_f64, X->ld, P->center,
+                                                                   d_eps_out, d_flags, d_n_flagged);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

@@ -44,14 +44,6 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     return r;
 }
 
-// fp32 error bound of a (query, candidate) pair of the count pass, PER QUERY.  With centred
-// values q~, c~ (|q~_d| <= Mq) and a candidate within d of the query, |c~_d| <= Mq + d, so
-//     |d32 - d64| <= 2^-24 (|q~| + |c~| + |d32|) <= 2^-24 (2 Mq + 2 d) (1 + tiny).
-// Using the query's own magnitude instead of the data set's keeps the band narrow where the
-// points are dense (near the centre) even when a few outliers stretch the range.
-__host__ __device__ inline double band_query_f64(double mq, double d) {
-    return 5.9604644775390625e-08 * (2.0 * mq + 2.0 * d) * 1.01 + 1e-37;
-}
 // Mq of the query at `row` of the fp32 shadow (upper bound of max_d |x_d - centre_d|)
 __device__ __forceinline__ double query_maxabs(const float* __restrict__ shadow, int64_t row, int dim_padded) {
     float m = 0.0f;

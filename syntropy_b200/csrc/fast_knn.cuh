@@ -63,6 +63,15 @@ __device__ __forceinline__ Band make_band(const double* __restrict__ maxabs, int
 __host__ __device__ inline double band_f64(double maxabs, double t) {
     return 5.9604644775390625e-08 * (2.0 * maxabs + t) * 1.001 + 1e-37;
 }
+// fp32 error bound of a (query, candidate) pair, PER QUERY.  With centred values q~, c~
+// (|q~_d| <= Mq) and a candidate within d of the query, |c~_d| <= Mq + d, so
+//     |d32 - d64| <= 2^-24 (|q~| + |c~| + |d32|) <= 2^-24 (2 Mq + 2 d) (1 + tiny).
+// Using the query's own magnitude instead of the data set's keeps the band narrow where the
+// points are dense (near the centre = the per-coordinate median) even when a few outliers stretch
+// the range by orders of magnitude (heavy-tailed data).
+__host__ __device__ inline double band_query_f64(double mq, double d) {
+    return 5.9604644775390625e-08 * (2.0 * mq + 2.0 * d) * 1.01 + 1e-37;
+}
 
 // ---- packed helpers
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
@@ -143,7 +152,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t qb0 = (int64_t)blockIdx.x * QB;
-    const Band band = make_band(maxabs, dim);
+    (void)maxabs; (void)dim;
     const int64_t n_rows = n_tiles * FAST_TILE;
 
     // ---- pass 1: seed every query's threshold from its neighbours in the prepared order
@@ -208,7 +217,9 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
                     }
                 }
         }
-        thr = thr + (band.c0 + band.c1 * thr);  // inf stays inf
+        // the seed is itself an fp32 distance to a real candidate: one ulp up and that candidate
+        // (and everything tied with it) passes the strict test when its tile is scanned
+        thr = nextafterf(thr, CUDART_INF_F);  // inf stays inf
         seed_thr[qi] = thr;
         if (thr < CUDART_INF_F) { sum += thr; cnt += 1.0f; }
     }
@@ -406,7 +417,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
         }
 #pragma unroll
         for (int j = 0; j < Q; ++j)
-            if (live[j]) thr[j] = thr[j] + (band.c0 + band.c1 * thr[j]);  // inf stays inf
+            if (live[j]) thr[j] = nextafterf(thr[j], CUDART_INF_F);  // inf stays inf
         reset_lists();
     }
     if (tid == 0) {
@@ -873,7 +884,7 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
                   int64_t nq, const int32_t* __restrict__ q_index, const double* __restrict__ maxabs,
                   const float* __restrict__ seed_thr, const int32_t* __restrict__ unit_first, int qb,
                   const int32_t* __restrict__ perm, int64_t* __restrict__ idx_out,
-                  const double* __restrict__ qsorted, int64_t qld,
+                  const double* __restrict__ qsorted, int64_t qld, const double* __restrict__ center,
                   double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
     // qsorted (optional, cross-set search): the float64 query coordinates come from this [dim][qld]
     // array (rows q_begin + qi) instead of the candidate set itself.
@@ -902,8 +913,15 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
         off = qi - b * qb;
     }
     const int64_t row_q = q_index ? (int64_t)q_index[qi] : q_begin + qi;
-    double mmax = 0.0;
-    for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
+    (void)maxabs;
+    // the query's own magnitude in the centred frame bounds the fp32 error of all its near pairs
+    double qc[KSG_MAX_DIM];
+    double mq = 0.0;
+    for (int d = 0; d < dim; ++d) {
+        qc[d] = qsorted ? qsorted[(int64_t)d * qld + row_q] : sorted[(int64_t)d * ld + row_q];
+        mq = fmax(mq, fabs(qc[d] - center[d]));
+    }
+    mq = mq * (1.0 + 1e-6) + 1e-300;
 
     // k'-th smallest fp32 distance over the union of the split lists
     float best[KNN_MAX_KCAP];
@@ -924,15 +942,13 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
         if (idx_out) atomicAdd(n_flagged, 1);
         return;
     }
-    const double delta = band_f64(mmax, 2.0 * r32);
+    const double delta = band_query_f64(mq, 2.0 * r32);
     const double T = r32 + 2.0 * delta;
 
     bool overflow = false;
     double exact[KNN_MAX_KCAP];
     int32_t exact_j[KNN_MAX_KCAP], exact_o[KNN_MAX_KCAP];  // prepared position / original index (idx_out only)
     int got = 0, examined = 0;
-    double qc[KSG_MAX_DIM];
-    for (int d = 0; d < dim; ++d) qc[d] = qsorted ? qsorted[(int64_t)d * qld + row_q] : sorted[(int64_t)d * ld + row_q];
     for (int s = s_begin; s < s_end && !overflow; ++s) {
         // a full list whose tail is still inside the band may have dropped in-band candidates
         const float tail = part_d32[((int64_t)s * kcap + (kcap - 1)) * stride + off];

@@ -90,6 +90,20 @@ static __global__ void stats_stage2_kernel(const double* __restrict__ partial, i
     maxabs[d] = fmax(hi - c, c - lo) * (1.0 + 1e-12) + 1e-300;
 }
 
+// centre[d] = median of coordinate d (middle entry of its sorted array); maxabs[d] = max |x - centre|
+static __global__ void center_median_kernel(const double* __restrict__ axis_vals, int64_t ld, int64_t n, int dim,
+                                            double* __restrict__ center, double* __restrict__ maxabs) {
+    const int d = threadIdx.x;
+    if (d >= dim) return;
+    const double* v = axis_vals + (int64_t)d * ld;
+    double c = v[n / 2], lo = v[0], hi = v[n - 1];
+    if (!isfinite(c)) c = 0.0;  // non-finite input is flagged elsewhere; keep the math finite
+    if (!isfinite(lo)) lo = c;
+    if (!isfinite(hi)) hi = c;
+    center[d] = c;
+    maxabs[d] = fmax(fabs(hi - c), fabs(c - lo)) * (1.0 + 1e-12) + 1e-300;
+}
+
 static __global__ void iota_kernel(int32_t* __restrict__ p, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = (int32_t)i;

@@ -535,3 +535,25 @@ def test_c5_full_size(windowed):
     # swapping the groups permutes the joint coordinates: same radii, same counts; the two
     # psi terms are then subtracted in the other order, which may differ in the last bit
     assert np.abs(ptw - ptw2).max() < 1e-12 and avg == pytest.approx(avg2, rel=1e-13)
+
+
+def test_heavy_tailed_data_stays_on_the_fast_path(E):
+    """Outliers that stretch the range by orders of magnitude (Student-t with 1.2 degrees of
+    freedom, log-normal with sigma = 3) must neither change a bit nor push the bulk of the queries
+    to the float64 fallback: the fp32 copy is centred on the median and the error band is per query."""
+    rng = np.random.default_rng(31)
+    n = 6000
+    t = rng.standard_t(1.2, size=(2, n))
+    t[1] += 0.5 * t[0]
+    ln = rng.lognormal(0.0, 3.0, size=(3, n))
+    ln[2] *= ln[0] ** 0.25
+    for rows, subs in ((t, [(0,), (1,), (0, 1)]), (ln, [(0,), (1, 2), (0, 1, 2)])):
+        for key in E.stats:
+            E.stats[key] = 0
+        eps, counts = radius_and_counts(E, rows, 4, subs)
+        ref = orc.knn_radius(rows, 4)
+        assert np.array_equal(eps, ref)
+        for row, s in enumerate(subs):
+            assert np.array_equal(counts[row], orc.count_within(rows[list(s), :], ref)), s
+        if E.config.engine != "exact":
+            assert E.stats["knn_fallback_queries"] + E.stats["count_fallback_queries"] <= n // 100
