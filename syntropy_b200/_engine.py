@@ -353,12 +353,22 @@ class Config:
       "exact"              the float64 dense kernels (anchor / fallback; also used for > 8 dims).
     All three give identical radii and counts."""
     engine = "windowed"
-    primary = -1  # -1: Morton order of the per-coordinate ranks; d >= 0: sort by coordinate d
+    primary = -1  # -1: Hilbert curve over the per-coordinate ranks; -2: kd order; d >= 0: sort by coordinate d
+    kd_min_dim = 7  # point sets of at least this many coordinates are prepared in kd order (when primary < 0)
     own_order = True          # windowed engine: low-dimensional marginals in their own order
     own_order_max_dim = 4     # ... when they have at most this many coordinates
 
 
 config = Config()
+
+
+def order_for(dim: int) -> int:
+    """The `primary` argument of ksg_prepare for a point set of `dim` coordinates."""
+    if config.primary >= 0:
+        return min(config.primary, dim - 1)
+    if config.primary == -2 or (config.kd_min_dim is not None and dim >= config.kd_min_dim):
+        return -2
+    return -1
 
 
 class PreparedSet:
@@ -610,7 +620,7 @@ def radius_and_counts(pts: torch.Tensor, k: int, masks):
     lib = _cabi.load()
     dim, n = pts.shape
     windowed = config.engine == "windowed"
-    prep = PreparedSet(pts, min(config.primary, dim - 1))
+    prep = PreparedSet(pts, order_for(dim))
     preps = [prep]
     q0, q1 = _dist.my_slice(n)
     eps = fast_knn(prep, k + 1, q0, q1, windowed)
@@ -630,7 +640,7 @@ def radius_and_counts(pts: torch.Tensor, k: int, masks):
     for s in own:
         dims = _dims_of(masks[s])
         sub = pts[dims, :].contiguous()
-        prep_s = PreparedSet(sub, -1)
+        prep_s = PreparedSet(sub, order_for(len(dims)))
         preps.append(prep_s)
         eps_s = torch.empty(n, dtype=torch.float64, device=pts.device)
         _cabi.check(lib.ksg_gather_f64(_ptr(eps_orig), _ptr(prep_s.perm), n, _ptr(eps_s), _stream()), "ksg_gather_f64")
@@ -652,7 +662,7 @@ def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder) -> Pointwise:
         # everything is counted in the joint order: keep the slices sorted until the end
         windowed = config.engine == "windowed"
         q0, q1 = _dist.my_slice(n)
-        prep = PreparedSet(pts, min(config.primary, dim - 1))
+        prep = PreparedSet(pts, order_for(dim))
         eps = fast_knn(prep, k + 1, q0, q1, windowed)
         counts = fast_counts(prep, masks, eps, q0, q1, windowed)
         return Pointwise(psi_epilogue(counts, prog, n), prep=prep, preps=[prep])
@@ -682,7 +692,7 @@ def ksg2_family(rows, k: int, masks, prog_builder):
     # fast engines: neighbours from the fp32 filter + exact refine (prepared order); every
     # subspace has its own radius, so every multi-dimensional one gets its own single-subspace pass
     windowed = config.engine == "windowed"
-    prep = PreparedSet(pts, min(config.primary, dim - 1))
+    prep = PreparedSet(pts, order_for(dim))
     preps = [prep]
     _, nbr = fast_knn(prep, k + 1, q0, q1, windowed, want_indices=True)
     rc = lib.ksg_subspace_radius_from_neighbours(C.c_void_p(prep.c.sorted_f64), prep.ld, n, dim, q0, q1, _ptr(nbr),
@@ -706,7 +716,7 @@ def ksg2_family(rows, k: int, masks, prog_builder):
             prep_s, e_s = prep, e
         else:
             e_orig = scatter_to_original(_dist.gather_slices(e, n), prep)
-            prep_s = PreparedSet(pts[dims, :].contiguous(), -1)
+            prep_s = PreparedSet(pts[dims, :].contiguous(), order_for(len(dims)))
             preps.append(prep_s)
             e_all = torch.empty(n, dtype=torch.float64, device=pts.device)
             _cabi.check(lib.ksg_gather_f64(_ptr(e_orig), _ptr(prep_s.perm), n, _ptr(e_all), _stream()), "ksg_gather_f64")
@@ -723,7 +733,7 @@ def kl_entropy(rows: np.ndarray, k: int):
     q0, q1 = _dist.my_slice(n)
     prep = None
     if _use_fast(dim, k + 1):
-        prep = PreparedSet(pts, min(config.primary, dim - 1))
+        prep = PreparedSet(pts, order_for(dim))
         eps = fast_knn(prep, k + 1, q0, q1, config.engine == "windowed")
     else:
         eps = knn_radius(pts, k + 1, q0, q1)
@@ -809,7 +819,7 @@ def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
         _cabi.check(rc, "ksg_kl_epilogue")
         return _finish(Pointwise(ptw), n, flag)
     windowed = config.engine == "windowed"
-    prep_p = PreparedSet(P, -1)
+    prep_p = PreparedSet(P, order_for(dim))
     rho = scatter_to_original(_dist.gather_slices(fast_knn(prep_p, k + 1, q0, q1, windowed), n), prep_p)
     prep_q = PreparedSet(Q, -1)
     if windowed:

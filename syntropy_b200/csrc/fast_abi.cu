@@ -132,7 +132,7 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
     KSG_REQUIRE(d_points && d_buffer && h_out, "ksg_prepare: null pointer");
     KSG_REQUIRE(n > 0 && n < (1ll << 31) - 1024 && ld >= n, "ksg_prepare: need 0 < n < 2^31 and ld >= n");
     KSG_REQUIRE(dim >= 1 && dim <= KSG_MAX_DIM, "ksg_prepare: dim out of range");
-    KSG_REQUIRE(primary >= -1 && primary < dim, "ksg_prepare: primary must be -1 (Morton order) or a coordinate");
+    KSG_REQUIRE(primary >= -2 && primary < dim, "ksg_prepare: primary must be -2 (kd order), -1 (curve order) or a coordinate");
     const PreparedLayout L = prepared_layout(n, dim);
     if (buffer_bytes < L.total) {
         set_error("ksg_prepare: buffer of %zu bytes needed, %zu given", L.total, buffer_bytes);
@@ -178,8 +178,34 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
         // order = one coordinate's sorted order
         KSG_CUDA_TRY(cudaMemcpyAsync(P.perm, P.axis_pos + (int64_t)primary * L.ld, (size_t)n * 4,
                                      cudaMemcpyDeviceToDevice, st));
+    } else if (primary == -2) {
+        // order = leaves of a balanced kd-tree over the per-coordinate ranks (see kd_key_kernel)
+        int32_t* ranks = (int32_t*)(base + L.off_ranks);
+        unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
+        unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
+        for (int d = 0; d < dim; ++d) {
+            rank_scatter_kernel<<<nb, 256, 0, st>>>(P.axis_pos + (int64_t)d * L.ld, n, ranks + (int64_t)d * L.ld);
+            KSG_LAUNCHED2();
+        }
+        const int64_t n_groups = ceil_div(n, FAST_SUB);
+        int levels = 0;
+        while ((1ll << levels) < n_groups) ++levels;
+        int32_t* pa = iota;    // holds 0..n-1: the identity order
+        int32_t* pb = P.perm;
+        for (int level = 0; level < levels; ++level) {
+            kd_key_kernel<<<nb, 256, 0, st>>>(pa, ranks + (int64_t)(level % dim) * L.ld, n, level, n_groups, mkeys);
+            KSG_LAUNCHED2();
+            size_t need = L.cub_bytes;
+            cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, pa, pb, (int)n, 0,
+                                                            32 + level, st);
+            if (e != cudaSuccess) { set_error("cub SortPairs (kd): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+            note_launch();
+            int32_t* t = pa; pa = pb; pb = t;
+        }
+        if (pa != P.perm)
+            KSG_CUDA_TRY(cudaMemcpyAsync(P.perm, pa, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     } else {
-        // order = Morton code of the per-coordinate ranks
+        // order = Hilbert curve over the per-coordinate ranks
         int32_t* ranks = (int32_t*)(base + L.off_ranks);
         unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
         unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);

@@ -287,6 +287,27 @@ static __global__ void cross_maxabs_kernel(const double* __restrict__ partial, i
     out[d] = fmax(maxabs[d], m);
 }
 
+// ---- kd order (primary = -2): the order of the leaves of a balanced kd-tree.  Level after level,
+// every segment (a contiguous run of positions, boundaries at multiples of 32 rows) is sorted along
+// one coordinate -- by global rank, cycling through the coordinates -- and cut in half at a 32-row
+// boundary, until a segment is one 32-row sub-tile.  Unlike the curve over GLOBAL ranks the splits
+// are CONDITIONAL medians, so the boxes follow the data when coordinates are correlated or the
+// points sit near a low-dimensional manifold: sub-tiles, tiles and query blocks are nodes of the
+// tree with tight, non-overlapping boxes.  key = (segment of the position at this level, rank).
+static __global__ void kd_key_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ rank_row, int64_t n,
+                                     int level, int64_t n_groups, unsigned long long* __restrict__ keys) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int64_t g = p / FAST_SUB;
+    int64_t lo = 0, hi = n_groups;
+    unsigned long long id = 0ull;
+    for (int l = 0; l < level; ++l) {
+        const int64_t mid = lo + ((hi - lo + 1) >> 1);
+        if (g < mid) { hi = mid; id <<= 1; } else { lo = mid; id = (id << 1) | 1ull; }
+    }
+    keys[p] = (id << 32) | (unsigned long long)(unsigned int)rank_row[perm[p]];
+}
+
 static __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) inv[perm[i]] = (int32_t)i;

@@ -353,8 +353,8 @@ def test_c2_full_size(E, knn):
 
 
 def test_engines_agree_bitwise_on_random_configs():
-    """exact fp64, dense fp32-filter and windowed fp32-filter (Morton order and single-coordinate
-    order) give identical radii / counts."""
+    """exact fp64, dense fp32-filter and windowed fp32-filter (curve order, kd order and
+    single-coordinate order of the prepared set) give identical radii / counts."""
     from syntropy_b200 import _engine as E
 
     rng = np.random.default_rng(77)
@@ -366,7 +366,8 @@ def test_engines_agree_bitwise_on_random_configs():
             if dim >= 4:
                 subs += [tuple(range(dim // 2)), tuple(range(dim // 2, dim)), (0, dim - 1)]
             got = {}
-            for engine, primary in (("exact", -1), ("dense", -1), ("windowed", -1), ("windowed", dim - 1)):
+            for engine, primary in (("exact", -1), ("dense", -1), ("windowed", -1), ("windowed", -2), ("dense", -2),
+                                    ("windowed", dim - 1)):
                 E.config.engine, E.config.primary = engine, primary
                 got[(engine, primary)] = radius_and_counts(E, rows, k, subs)
             for key in got:
