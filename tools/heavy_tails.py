@@ -1,5 +1,15 @@
-import sys, time, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""Heavy-tailed inputs (range 1e4 .. 1e6 times the bulk): time of one KSG MI call and how many
+queries left the fp32-filtered path for the float64 fallback (should be none: the fp32 copy is
+centred on the median and the error band is per query)."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from syntropy_b200 import knn, _engine as E
 rng = np.random.default_rng(0)
 n = 300_000
