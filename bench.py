@@ -244,9 +244,8 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: no CUDA device; the KSG path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # rank 0 prints exactly one line on stdout: keep NCCL's version banner off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0 prints exactly one line on stdout: NCCL's version banner and warnings go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
