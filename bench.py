@@ -244,9 +244,19 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: no CUDA device; the KSG path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # rank 0 prints exactly one line on stdout: NCCL's version banner and warnings go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # rank 0 prints exactly one line on stdout: whatever NCCL prints while the communicator
+        # comes up (its version banner) is sent to stderr by pointing fd 1 there meanwhile
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            td.init_process_group("nccl", device_id=torch.device("cuda", local))
+            td.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 

@@ -36,11 +36,12 @@ int sm_count();
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// How many candidate ranges a query block is split into so that the grid has at
-// least ~4 CTAs per SM even when few queries are resident on this GPU (the 8-GPU
-// sharded case), without making a split shorter than a handful of tiles.
+// How many candidate ranges a query block is split into.  The dense kernels keep ~4 CTAs resident
+// per SM; the grid should be several waves of that (here >= 6), or the last, partly filled wave
+// costs a large share of the time when few queries are resident on this GPU (8-GPU sharding:
+// 244 query blocks x 3 splits was 1.24 waves) -- without making a split shorter than two tiles.
 static inline int choose_splits(int64_t n_query_blocks, int64_t n_candidates, int tile) {
-    int64_t want = ceil_div(4 * (int64_t)sm_count(), n_query_blocks > 0 ? n_query_blocks : 1);
+    int64_t want = ceil_div(24 * (int64_t)sm_count(), n_query_blocks > 0 ? n_query_blocks : 1);
     int64_t max_by_len = n_candidates / (2 * (int64_t)tile);
     if (max_by_len < 1) max_by_len = 1;
     if (want > max_by_len) want = max_by_len;
