@@ -534,7 +534,7 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
     a.n_sub = n_subspaces; a.counts = d_counts; a.st = st;
     a.tile_counter = (unsigned long long*)((char*)P->flags + 24);
     const int64_t qblocks = ceil_div(nq, count_f32_queries_per_block(P->dim_padded));
-    a.splits = a.windowed ? 1 : choose_splits(qblocks, P->n, FAST_TILE);
+    a.splits = choose_splits(qblocks, P->n, FAST_TILE);  // (the pruned walk interleaves the splits too)
 
     // recognise the fused structures
     int rc = KSG_EUNSUPPORTED;
