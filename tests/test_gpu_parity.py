@@ -8,6 +8,8 @@ Bars: radii and neighbour counts bit-exact; pointwise / average nats within 1e-1
 relative (the only non-bit-exact ingredient is log() inside digamma for arguments
 above 10, where CUDA's libdevice and the host libm may differ in the last ulp).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -558,3 +560,16 @@ def test_heavy_tailed_data_stays_on_the_fast_path(E):
             assert np.array_equal(counts[row], orc.count_within(rows[list(s), :], ref)), s
         if E.config.engine != "exact":
             assert E.stats["knn_fallback_queries"] + E.stats["count_fallback_queries"] <= n // 100
+
+
+def test_randomised_engine_agreement():
+    """tools/fuzz_engines.py, a short run: random sizes / dimensions / k / subspace families /
+    prepared orders / awkward distributions; windowed and dense engines == exact engine, bit for
+    bit, and the public API agrees between engines (400 cases: profiles/r1ad_fuzz_400_cases.txt)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_engines.py"), "--cases", "30", "--seed", "3"],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0 and "FUZZ_OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
