@@ -599,7 +599,7 @@ int ksg_axis_count(const ksg_prepared* P, int axis, int64_t q_begin, int64_t q_e
     KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_axis_count: bad query range");
     const int64_t nq = q_end - q_begin;
     if (nq == 0) return KSG_OK;
-    axis_count_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, as_stream2(stream)>>>(
+    axis_count_kernel<<<(unsigned)ceil_div(nq, AXIS_THREADS), AXIS_THREADS, 0, as_stream2(stream)>>>(
         P->sorted_f64 + (int64_t)axis * P->ld, P->axis_vals + (int64_t)axis * P->ld, P->n, q_begin, nq, d_eps,
         strict ? 1 : 0, bias, d_counts);
     KSG_LAUNCHED2();

@@ -410,35 +410,52 @@ count_fix_kernel(const double* __restrict__ sorted, int64_t ld, const float* __r
 }
 
 // ---------------------------------------------------------------- 1-D marginals
-// counts[qi] = #{j : |fl64(x_q - v_j)| < eps} + bias   over the coordinate's sorted array.
-static __global__ void __launch_bounds__(128)
+// counts[qi] = #{j : |fl64(x_q - v_j)| < eps} + bias   over the coordinate's sorted array: the
+// length of the run around x_q that satisfies the exact predicate (monotone along the sorted
+// array because IEEE rounding is monotone), found by two binary searches.  The searches are
+// latency-bound chains of dependent loads, so their upper levels run in shared memory: every CTA
+// first samples the array at AXIS_TAB evenly spaced positions (the last element of each chunk),
+// a search picks its chunk there and only bisects inside the chunk in global memory.
+constexpr int AXIS_THREADS = 1024;
+constexpr int AXIS_TAB = 1024;
+
+static __global__ void __launch_bounds__(AXIS_THREADS)
 axis_count_kernel(const double* __restrict__ sorted_row, const double* __restrict__ vals, int64_t n,
                   int64_t q_begin, int64_t nq, const double* __restrict__ eps, int strict, int32_t bias,
                   int32_t* __restrict__ counts) {
+    __shared__ double tab[AXIS_TAB];
+    const int64_t chunk = (n + AXIS_TAB - 1) / AXIS_TAB;          // elements per chunk (>= 1)
+    const int n_chunks = (int)((n + chunk - 1) / chunk);          // <= AXIS_TAB
+    for (int i = threadIdx.x; i < n_chunks; i += AXIS_THREADS) {
+        const int64_t last = ((int64_t)i + 1) * chunk - 1;
+        tab[i] = vals[last < n ? last : n - 1];
+    }
+    __syncthreads();
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     const double x = sorted_row[q_begin + qi];
     const double e = eps[qi];
-    // first index inside on the left: predicate (v > x) || inside(x - v) is monotone in v
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        const double v = vals[mid];
-        const double dl = x - v;
-        const bool p = (v > x) || (strict ? (dl < e) : (dl <= e));
-        if (p) hi = mid; else lo = mid + 1;
-    }
-    const int64_t left = lo;
+    // first index whose value satisfies pred (pred is false ... false true ... true along the array)
+    auto first_true = [&](auto pred) -> int64_t {
+        int lo = 0, hi = n_chunks;  // first chunk whose LAST element satisfies pred
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (pred(tab[mid])) hi = mid; else lo = mid + 1;
+        }
+        if (lo == n_chunks) return n;
+        int64_t a = (int64_t)lo * chunk, b = a + chunk < n ? a + chunk : n;
+        b -= 1;  // the chunk's last element satisfies pred: the answer is in [a, b]
+        while (a < b) {
+            const int64_t mid = (a + b) >> 1;
+            if (pred(vals[mid])) b = mid; else a = mid + 1;
+        }
+        return a;
+    };
+    // first index inside on the left: (v > x) || inside(x - v)
+    const int64_t left = first_true([&](double v) { return (v > x) || (strict ? (x - v < e) : (x - v <= e)); });
     // first index beyond the run on the right: (v > x) && !inside(v - x)
-    lo = left; hi = n;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        const double v = vals[mid];
-        const double dr = v - x;
-        const bool p = (v > x) && !(strict ? (dr < e) : (dr <= e));
-        if (p) hi = mid; else lo = mid + 1;
-    }
-    counts[qi] = (int32_t)(lo - left) + bias;
+    const int64_t right = first_true([&](double v) { return (v > x) && !(strict ? (v - x < e) : (v - x <= e)); });
+    counts[qi] = (int32_t)(right - left) + bias;
 }
 
 static __global__ void scatter_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ perm, int64_t n,
