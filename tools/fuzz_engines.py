@@ -79,12 +79,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=60)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--big", action="store_true", help="sizes 5e4 .. 3e5 instead of 37 .. 2e4")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     bad = 0
     for case in range(args.cases):
         dim = int(rng.integers(1, 9))
-        n = int(rng.choice([37, 200, 511, 513, 1000, 2049, 5000, 9973, 20011]))
+        n = int(rng.choice([50_021, 131_072, 200_003, 300_007] if args.big else
+                           [37, 200, 511, 513, 1000, 2049, 5000, 9973, 20011]))
         k = int(rng.integers(1, min(12, n - 1)))
         kind, rows = make_data(rng, dim, n)
         subs = subspaces(rng, dim)
