@@ -282,6 +282,19 @@ int ksg_fast_knn_idx(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end,
                      int kprime, int windowed, double* d_eps_out, int64_t* d_idx_out, int32_t* d_flags,
                      int32_t* d_n_flagged, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * The same with an explicit list margin: the filter keeps the k' + margin smallest fp32 distances
+ * per query (ksg_fast_knn / ksg_fast_knn_idx use margin = 3).  A query is decided exactly when
+ * fewer than `margin` further candidates lie inside the fp32 error band of its k'-th distance;
+ * quantised data with many exact ties needs a longer list (k' + margin <= 64; the lists live in
+ * shared memory, so large values cost occupancy).  Workspace: ksg_fast_knn_workspace_margin.
+ */
+size_t ksg_fast_knn_workspace_margin(int64_t n, int64_t nq, int dim, int kprime, int margin);
+int ksg_fast_knn_margin(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end, const int32_t* d_query_index,
+                        int kprime, int margin, int windowed, double* d_eps_out, int64_t* d_idx_out,
+                        int32_t* d_flags, int32_t* d_n_flagged, void* d_workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* ------------------------------------------------------------------ cross-set k-NN (KL divergence)
  *
  * Queries that are NOT points of the prepared (candidate) set: kullback_leibler_divergence asks

@@ -97,6 +97,9 @@ SIGNATURES = {
                                C.c_size_t, _c_vp]),
     "ksg_fast_knn_idx": (C.c_int, [_c_prep, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
                                    C.c_size_t, _c_vp]),
+    "ksg_fast_knn_workspace_margin": (C.c_size_t, [_c_i64, _c_i64, C.c_int, C.c_int, C.c_int]),
+    "ksg_fast_knn_margin": (C.c_int, [_c_prep, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int, C.c_int, _c_vp, _c_vp, _c_vp,
+                                      _c_vp, _c_vp, C.c_size_t, _c_vp]),
     "ksg_cross_prepare_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int]),
     "ksg_cross_prepare": (C.c_int, [_c_prep, _c_vp, _c_i64, _c_i64, _c_vp, C.c_size_t, _c_cross, _c_vp]),
     "ksg_fast_knn_cross": (C.c_int, [_c_prep, _c_cross, _c_i64, _c_i64, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp,

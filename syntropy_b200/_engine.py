@@ -409,8 +409,21 @@ class PreparedSet:
         return int(t[2]), int(t[3])
 
 
+KNN_MARGIN = 3          # list entries the filter keeps beyond k' (ksg_fast_knn's default)
+KNN_WIDE_MARGIN = 24    # second pass for tie-saturated (quantised) data
+
+
+def _lists_fit(dim: int, kcap: int) -> bool:
+    """Do neighbour lists of kcap entries fit in shared memory beside the candidate ring?"""
+    dp = (dim + 1) & ~1
+    queries_per_block = 128 * (4 if dp <= 4 else 2)
+    stages = 3 if dp <= 4 else 2
+    ring = stages * (512 * dp * 4 + 16 * dp * 8)
+    return ring + kcap * queries_per_block * 8 <= 200 * 1024 and kcap <= 64
+
+
 def _fast_knn_call(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, q_index=None,
-                   want_indices: bool = False):
+                   want_indices: bool = False, margin: int = KNN_MARGIN):
     lib = _cabi.load()
     nq = q1 - q0
     dev = prep.buf.device
@@ -418,23 +431,32 @@ def _fast_knn_call(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: b
     idx = torch.empty((nq, kprime), dtype=torch.int64, device=dev) if want_indices else None
     flags = torch.empty(nq, dtype=torch.int32, device=dev)
     nflag = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws = torch.empty(max(int(lib.ksg_fast_knn_workspace(prep.n, max(nq, 1), prep.dim, kprime)), 1),
+    ws = torch.empty(max(int(lib.ksg_fast_knn_workspace_margin(prep.n, max(nq, 1), prep.dim, kprime, margin)), 1),
                      dtype=torch.uint8, device=dev)
     with timer.span("fast_knn" if q_index is None else "fast_knn_deferred"):
-        rc = lib.ksg_fast_knn_idx(C.byref(prep.c), q0, q1, _ptr(q_index), kprime, 1 if windowed else 0, _ptr(eps),
-                                  _ptr(idx), _ptr(flags), _ptr(nflag), _ptr(ws), ws.numel(), _stream())
-    _cabi.check(rc, "ksg_fast_knn_idx")
+        rc = lib.ksg_fast_knn_margin(C.byref(prep.c), q0, q1, _ptr(q_index), kprime, margin, 1 if windowed else 0,
+                                     _ptr(eps), _ptr(idx), _ptr(flags), _ptr(nflag), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "ksg_fast_knn_margin")
     return eps, idx, flags, nflag
 
 
 def fast_knn(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, want_indices: bool = False):
-    """Exact k'-th-neighbour radii of sorted positions [q0, q1): fp32 filter + fp64 refine; the
-    outliers the windowed pass sets aside go through a dense launch of the same filter, the
-    queries the filter cannot decide (tie-saturated data) through the dense fp64 kernel.
+    """Exact k'-th-neighbour radii of sorted positions [q0, q1): fp32 filter + fp64 refine.
+    What the first pass cannot settle is escalated: outliers the windowed pass set aside go through
+    a dense launch of the same filter; when many queries tie beyond the list margin (quantised
+    data) the pass is repeated once with a long list; the rest (and tie-saturated neighbourhoods in
+    general) goes to the dense fp64 kernel.
     ``want_indices``: also the (nq, k') neighbour positions in the prepared order (KSG-2)."""
     nq = q1 - q0
     eps, nbr, flags, nflag = _fast_knn_call(prep, kprime, q0, q1, windowed, want_indices=want_indices)
     if nq and int(nflag.item()):
+        n_tied = int((flags == 1).sum().item())
+        # worth it when the dense float64 pass over the tied queries (n_tied x n pairs at ~3e12 pairs/s)
+        # would cost more than a second filter pass over all of them (~70 ns per query, measured)
+        if (windowed and n_tied * prep.n > 4e5 * nq and _lists_fit(prep.dim, kprime + KNN_WIDE_MARGIN)):
+            stats["knn_wide_margin_passes"] += 1
+            eps, nbr, flags, nflag = _fast_knn_call(prep, kprime, q0, q1, windowed, want_indices=want_indices,
+                                                    margin=KNN_WIDE_MARGIN)
         deferred = (flags == 2).nonzero().flatten()
         if deferred.numel():
             stats["knn_deferred_queries"] += int(deferred.numel())
@@ -505,7 +527,8 @@ def scatter_to_original(values_sorted: torch.Tensor, prep: PreparedSet) -> torch
     return out
 
 
-stats = {"knn_fallback_queries": 0, "count_fallback_queries": 0, "knn_deferred_queries": 0}
+stats = {"knn_fallback_queries": 0, "count_fallback_queries": 0, "knn_deferred_queries": 0,
+         "knn_wide_margin_passes": 0}
 
 
 def _use_fast(dim: int, kprime: int = 1) -> bool:

@@ -85,11 +85,11 @@ struct FastKnnPlan {
         return d32_bytes + idx_bytes + seed_bytes + plan_bytes + count_bytes + first_bytes + ublock_bytes + meta_bytes;
     }
 };
-static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int windowed) {
+static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int windowed, int margin = KNN_MARGIN) {
     FastKnnPlan p;
     memset(&p, 0, sizeof(p));
     const int dp = (dim + 1) & ~1;
-    p.kcap = kprime + KNN_MARGIN;
+    p.kcap = kprime + margin;
     p.qb = knn_f32_queries_per_block(dp);
     p.qblocks = ceil_div(nq, p.qb);
     if (windowed) {
@@ -250,10 +250,14 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
 }
 
 size_t ksg_fast_knn_workspace(int64_t n, int64_t nq, int dim, int kprime) {
-    if (n <= 0 || nq <= 0 || dim < 1 || kprime < 1) return 0;
+    return ksg_fast_knn_workspace_margin(n, nq, dim, kprime, KNN_MARGIN);
+}
+
+size_t ksg_fast_knn_workspace_margin(int64_t n, int64_t nq, int dim, int kprime, int margin) {
+    if (n <= 0 || nq <= 0 || dim < 1 || kprime < 1 || margin < 1) return 0;
     // either engine may be asked for with this workspace
-    const size_t dense = fast_knn_plan(n, nq, dim, kprime, 0).total();
-    const size_t windowed = fast_knn_plan(n, nq, dim, kprime, 1).total();
+    const size_t dense = fast_knn_plan(n, nq, dim, kprime, 0, margin).total();
+    const size_t windowed = fast_knn_plan(n, nq, dim, kprime, 1, margin).total();
     return (dense > windowed ? dense : windowed) + 256;
 }
 
@@ -267,9 +271,17 @@ int ksg_fast_knn(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const in
 int ksg_fast_knn_idx(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const int32_t* d_query_index, int kprime,
                      int windowed, double* d_eps_out, int64_t* d_idx_out, int32_t* d_flags, int32_t* d_n_flagged,
                      void* d_workspace, size_t workspace_bytes, void* stream) {
+    return ksg_fast_knn_margin(P, q_begin, q_end, d_query_index, kprime, KNN_MARGIN, windowed, d_eps_out, d_idx_out,
+                               d_flags, d_n_flagged, d_workspace, workspace_bytes, stream);
+}
+
+int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const int32_t* d_query_index, int kprime,
+                        int margin, int windowed, double* d_eps_out, int64_t* d_idx_out, int32_t* d_flags,
+                        int32_t* d_n_flagged, void* d_workspace, size_t workspace_bytes, void* stream) {
     KSG_REQUIRE(P && d_eps_out && d_flags && d_n_flagged && d_workspace, "ksg_fast_knn: null pointer");
     KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && (d_query_index || q_end <= P->n), "ksg_fast_knn: bad query range");
-    KSG_REQUIRE(kprime >= 1 && kprime + KNN_MARGIN <= KNN_MAX_KCAP, "ksg_fast_knn: kprime out of range (k' + 3 <= 64)");
+    KSG_REQUIRE(kprime >= 1 && margin >= 1 && kprime + margin <= KNN_MAX_KCAP,
+                "ksg_fast_knn: k' + margin out of range (1 <= margin, k' + margin <= 64)");
     if (d_query_index) windowed = 0;  // an explicit query list has no spatial coherence to prune with
     if (P->dim_padded > 8) {
         set_error("ksg_fast_knn: the fp32 filter is instantiated for up to 8 dimensions (got %d); use ksg_knn_radius",
@@ -278,7 +290,7 @@ int ksg_fast_knn_idx(const ksg_prepared* P, int64_t q_begin, int64_t q_end, cons
     }
     const int64_t nq = q_end - q_begin;
     if (nq == 0) return KSG_OK;
-    FastKnnPlan p = fast_knn_plan(P->n, nq, P->dim, kprime, windowed);
+    FastKnnPlan p = fast_knn_plan(P->n, nq, P->dim, kprime, windowed, margin);
     if (workspace_bytes < p.total()) {
         set_error("ksg_fast_knn: workspace of %zu bytes needed, %zu given", p.total(), workspace_bytes);
         return KSG_EWORKSPACE;
