@@ -68,3 +68,23 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(base, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+\.*oracle|ksg_oracle|libksg_oracle", text, flags=re.M), \
                     f"{f} reaches into oracle/"
+
+
+def test_c_abi_example_compiles_against_the_header_and_library(tmp_path):
+    """examples/ksg_mi_cabi.cu uses nothing but include/ksg_b200.h, the CUDA runtime and
+    libksg_b200.so (no torch, no Python): it must compile and link for sm_100a."""
+    import shutil
+    import subprocess
+
+    from syntropy_b200 import _build
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    lib = _build.build()
+    out = tmp_path / "ksg_mi_cabi"
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+           "-o", str(out), os.path.join(ROOT, "examples", "ksg_mi_cabi.cu"), "-L", os.path.dirname(lib), "-lksg_b200"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    assert out.exists()
