@@ -45,24 +45,6 @@ constexpr int COUNT_UNIT_MIN_TILES = 64;  // count units are cheap per tile (cul
                                           // must be long enough to amortise the latency of its first bulk copy
 constexpr int KNN_UNIT_FACTOR = 2;      // chunk grows so that #units <= (1 + FACTOR) * #blocks
 
-// ---- fp32 error band of the shadow copy (see DESIGN.md "Exactness")
-// |d32 - d64| <= 2^-24 * (2*M + |d|) * (1 + tiny) per dimension; kept as a pair of
-// coefficients so that band(T) = c0 + c1 * T, evaluated with upward slack.
-struct Band {
-    float c0, c1;
-};
-// band(T) = c0 + c1*T  >=  2 * delta(T), with ~1% upward slack for its own fp32 evaluation
-__device__ __forceinline__ Band make_band(const double* __restrict__ maxabs, int dim) {
-    double mmax = 0.0;
-    for (int d = 0; d < dim; ++d) mmax = fmax(mmax, maxabs[d]);
-    Band b;
-    b.c0 = __double2float_ru(2.0 * 5.9604644775390625e-08 * 2.0 * mmax * 1.02 + 1e-37);
-    b.c1 = __double2float_ru(2.0 * 5.9604644775390625e-08 * 1.02);
-    return b;
-}
-__host__ __device__ inline double band_f64(double maxabs, double t) {
-    return 5.9604644775390625e-08 * (2.0 * maxabs + t) * 1.001 + 1e-37;
-}
 // fp32 error bound of a (query, candidate) pair, PER QUERY.  With centred values q~, c~
 // (|q~_d| <= Mq) and a candidate within d of the query, |c~_d| <= Mq + d, so
 //     |d32 - d64| <= 2^-24 (|q~| + |c~| + |d32|) <= 2^-24 (2 Mq + 2 d) (1 + tiny).
@@ -343,7 +325,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
 
     const int tid = threadIdx.x;
     const int64_t qb0 = (int64_t)blockIdx.x * QB;  // first query of the block (relative to q_begin)
-    const Band band = make_band(maxabs, dim);
+    (void)maxabs; (void)dim;
 
     // queries: slot j of thread t is query qb0 + j*THREADS + t
     float2 q[Q][DP / 2];
@@ -394,7 +376,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
 
     // ---- seed the thresholds: the kcap-th smallest fp32 distance among the 2*KNN_SEED_W rows
     // around each query in the prepared order is an upper bound of its final kcap-th distance.
-    // Starting from it (+ band, so that those very rows re-enter the list when their tile is
+    // Starting from it (one ulp up, so that those very rows re-enter the list when their tile is
     // scanned) removes the flood of insertions a threshold of +inf causes and gives the tile
     // queue a finite pruning radius from its first round.
     {
@@ -426,7 +408,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
     }
     block_query_box<DP>(blo, bhi, sh);  // (barriers inside: also publishes the mbarrier init)
 
-    float R = CUDART_INF_F;  // CTA pruning radius: max over its queries of threshold + band
+    float R = CUDART_INF_F;  // CTA radius: max over its queries' thresholds (unused by the dense walk)
     auto test = [&](int64_t t) -> bool {
         float gap[DP];
         box_gaps<DP>(tile_box, t, sh, gap);
@@ -439,7 +421,7 @@ knn_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_
         float v = -CUDART_INF_F;
 #pragma unroll
         for (int j = 0; j < Q; ++j)
-            if (live[j]) v = fmaxf(v, thr[j] + (band.c0 + band.c1 * thr[j]));
+            if (live[j]) v = fmaxf(v, thr[j]);
         R = block_max(v, sh);
     };
     auto compute = [&](const float* tile, int64_t t) {
@@ -574,8 +556,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int UNITS_CONSUMERS = FAST_THREADS;            // 4 filter warps
-constexpr int UNITS_THREADS = FAST_THREADS + 32;         // + 1 copy warp
+constexpr int UNITS_THREADS = FAST_THREADS + 32;  // 4 filter warps + 1 copy warp
 
 // Persistent filter kernel of the windowed engine: CTAs pull work units from a global cursor.
 //

@@ -36,7 +36,7 @@ struct PreparedLayout {
     size_t total;
 };
 
-// ---- per-dimension min / max (two stages) + non-finite flag
+// ---- non-finite flag (and per-dimension partial min / max, used by the cross-set queries' range)
 static __global__ void __launch_bounds__(256)
 stats_stage1_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, double* __restrict__ partial,
                     int32_t* __restrict__ flags) {
@@ -66,28 +66,6 @@ stats_stage1_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, doubl
         partial[((int64_t)d * STATS_BLOCKS + blockIdx.x) * 2 + 1] = shi[0];
         if (anybad) atomicExch(&flags[0], 1);
     }
-}
-
-// one warp per dimension (blockIdx.x = d)
-static __global__ void stats_stage2_kernel(const double* __restrict__ partial, int dim, double* __restrict__ center,
-                                    double* __restrict__ maxabs) {
-    const int d = blockIdx.x;
-    if (d >= dim) return;
-    double lo = CUDART_INF, hi = -CUDART_INF;
-    for (int b = threadIdx.x; b < STATS_BLOCKS; b += 32) {
-        lo = fmin(lo, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 0]);
-        hi = fmax(hi, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 1]);
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
-    }
-    if (threadIdx.x != 0) return;
-    if (!(isfinite(lo) && isfinite(hi))) { lo = 0.0; hi = 0.0; }  // flagged elsewhere; keep the math finite
-    const double c = 0.5 * lo + 0.5 * hi;
-    center[d] = c;
-    // max |x - c| over the data, rounded up generously (the band only has to be an upper bound)
-    maxabs[d] = fmax(hi - c, c - lo) * (1.0 + 1e-12) + 1e-300;
 }
 
 // centre[d] = median of coordinate d (middle entry of its sorted array); maxabs[d] = max |x - centre|
@@ -352,12 +330,6 @@ tile_box_kernel(const float* __restrict__ shadow, int dim_padded, float* __restr
         tile_box[(t * dim_padded + d) * 2 + 0] = fminf(fminf(slo[0][d], slo[1][d]), fminf(slo[2][d], slo[3][d]));
         tile_box[(t * dim_padded + d) * 2 + 1] = fmaxf(fmaxf(shi[0][d], shi[1][d]), fmaxf(shi[2][d], shi[3][d]));
     }
-}
-
-static __global__ void copy_axis_kernel(const double* __restrict__ src, double* __restrict__ vals,
-                                 int32_t* __restrict__ pos, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { vals[i] = src[i]; pos[i] = (int32_t)i; }
 }
 
 }  // namespace ksg
