@@ -90,7 +90,7 @@ static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int
     memset(&p, 0, sizeof(p));
     const int dp = (dim + 1) & ~1;
     p.kcap = kprime + margin;
-    p.qb = knn_f32_queries_per_block(dp);
+    p.qb = windowed ? knn_units_queries_per_block(dp) : knn_f32_queries_per_block(dp);
     p.qblocks = ceil_div(nq, p.qb);
     if (windowed) {
         // partial lists per work unit: [unit][rank][qb]

@@ -6,6 +6,21 @@ namespace ksg {
 
 int knn_f32_queries_per_block(int dim_padded) { return FAST_THREADS * (dim_padded <= 4 ? 4 : 2); }
 
+// Queries per thread of the WINDOWED kernels (planning + work units): ONE.  The culling is limited by
+// the warp's largest threshold and by its query box, both taken over 32*Q queries, and every scanned
+// sub-tile costs 32*Q pair evaluations per lane group -- measured on C2 (2-D): Q = 4 -> 2 -> 1 evaluates
+// 1058 -> 610 -> 391 million pairs and takes 1.14 -> 0.86 -> 0.82 ms; C5 (8-D): Q = 2 -> 1 halves the
+// pairs (2.47 -> 2.0 s).  The dense kernel keeps Q = 4 / 2: there every pair is evaluated anyway and
+// more queries per thread amortise the shared-memory reads.
+template <int DP>
+struct UnitsQ {
+    static constexpr int Q = UNITS_Q;
+};
+int knn_units_queries_per_block(int dim_padded) {
+    (void)dim_padded;
+    return FAST_THREADS * UNITS_Q;
+}
+
 template <int DP>
 static int launch_knn_dp(const KnnF32Args& a) {
     constexpr int Q = FastGeom<DP>::Q, ST = FastGeom<DP>::STAGES;
@@ -26,7 +41,7 @@ static int launch_knn_dp(const KnnF32Args& a) {
 
 template <int DP, int KC>
 static int launch_plan_kc(const KnnF32Args& a) {
-    constexpr int Q = FastGeom<DP>::Q;
+    constexpr int Q = UnitsQ<DP>::Q;
     auto kern = knn_plan_kernel<DP, Q, KC>;
     const size_t smem = KC > 0 ? 0 : (size_t)a.kcap * FAST_THREADS * Q * 4;
     if (smem > 32 * 1024) {
@@ -50,7 +65,7 @@ static int launch_plan_kc(const KnnF32Args& a) {
 
 template <int DP>
 static int launch_units_dp(const KnnF32Args& a) {
-    constexpr int Q = FastGeom<DP>::Q, ST = FastGeom<DP>::STAGES;
+    constexpr int Q = UnitsQ<DP>::Q, ST = FastGeom<DP>::STAGES;
     auto kern = knn_units_kernel<DP, Q, ST, (DP <= 4)>;
     const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float) +
                         (size_t)a.kcap * FAST_THREADS * Q * 8;

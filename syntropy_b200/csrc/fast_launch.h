@@ -37,7 +37,9 @@ struct KnnF32Args {
     unsigned long long* tile_counter;
     cudaStream_t st;
 };
+constexpr int UNITS_Q = 1;  // queries per thread of the windowed k-NN kernels (see fast_knn.cu)
 int knn_f32_queries_per_block(int dim_padded);
+int knn_units_queries_per_block(int dim_padded);
 int launch_knn_f32(int dim_padded, const KnnF32Args& a);  // KSG_EUNSUPPORTED if dim_padded not in {2,4,6,8}
 int launch_knn_plan(int dim_padded, const KnnF32Args& a);   // fills seed_thr / plan / plan_count / unit table
 int launch_knn_units(int dim_padded, const KnnF32Args& a);  // persistent windowed filter over the work units
