@@ -485,7 +485,8 @@ static FastCountPlan fast_count_plan(int64_t n, int64_t nq, int dim) {
     if (nq < 1) nq = 1;
     const int dp = (dim + 1) & ~1;
     p.thr_bytes = align_up((size_t)nq * sizeof(float), 256);
-    p.qblocks = ceil_div(nq, count_f32_queries_per_block(dp));
+    (void)dp;
+    p.qblocks = ceil_div(nq, (int64_t)FAST_THREADS * COUNT_UNITS_Q);  // (the work-unit path's query blocks)
     p.max_units = (1 + (int64_t)knn_unit_factor()) * p.qblocks;
     const int64_t n_tiles = ceil_div(n, FAST_TILE);
     p.plan_capacity = p.qblocks * (n_tiles < knn_plan_cap() ? n_tiles : (int64_t)knn_plan_cap());

@@ -306,7 +306,7 @@ count_units_kernel(const float* __restrict__ shadow, const float* __restrict__ s
 
 template <int DP>
 static int launch_count_full_dp(const CountF32Args& a, const CountUnitsArgs& w) {
-    constexpr int Q = FastGeom<DP>::Q, ST = FastGeom<DP>::STAGES;
+    constexpr int Q = COUNT_UNITS_Q, ST = FastGeom<DP>::STAGES;
     const int64_t qblocks = ceil_div(a.nq, FAST_THREADS * Q);
     if (cudaMemsetAsync(w.unit_meta, 0, 32, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
     count_plan_kernel<DP, Q><<<(unsigned)qblocks, FAST_THREADS, 0, a.st>>>(

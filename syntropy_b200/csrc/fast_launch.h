@@ -38,6 +38,7 @@ struct KnnF32Args {
     cudaStream_t st;
 };
 constexpr int UNITS_Q = 1;  // queries per thread of the windowed k-NN kernels (see fast_knn.cu)
+constexpr int COUNT_UNITS_Q = 1;  // ... and of the single-subspace windowed count kernels
 int knn_f32_queries_per_block(int dim_padded);
 int knn_units_queries_per_block(int dim_padded);
 int launch_knn_f32(int dim_padded, const KnnF32Args& a);  // KSG_EUNSUPPORTED if dim_padded not in {2,4,6,8}
