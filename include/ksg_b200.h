@@ -216,7 +216,7 @@ typedef struct {
     int64_t n;           /* points */
     int32_t dim;         /* joint dimensionality D */
     int32_t dim_padded;  /* D rounded up to even: row length of shadow_f32 */
-    int32_t primary;     /* coordinate the set is sorted by, or -1: Morton order of the per-coordinate ranks */
+    int32_t primary;     /* coordinate the set is sorted by; -1: Hilbert-curve order of the per-coordinate ranks; -2: kd order */
     int32_t reserved;
     int64_t ld;          /* row stride (elements) of the [dim][ld] arrays */
     int64_t n_padded;    /* rows of shadow_f32: n rounded up to the tile length, +inf padded */
@@ -238,19 +238,30 @@ typedef struct {
 } ksg_prepared;
 
 /*
- * Order the n points of d_points ([dim][ld] float64) -- by coordinate `primary` when
- * 0 <= primary < dim, by the Morton (Z-order) code of their per-coordinate ranks when
- * primary == -1 (spatially compact 512-point tiles in every coordinate) -- and build the
- * views above inside d_buffer
- * (ksg_prepare_workspace(n, dim) bytes).  *h_out is filled on the host; the device
- * work is only enqueued.  Replaces the cKDTree constructions of the path
- * (syntropy/knn/utils.py:29 and every per-marginal tree: shannon.py:190,336;
- * multivariate_mi.py:106,251,318-323,399-404) -- one sorted layout serves the joint
- * space and all marginals.
+ * Order the n points of d_points ([dim][ld] float64) and build the views above inside d_buffer
+ * (ksg_prepare_workspace(n, dim) bytes).  primary >= 0: the order of that coordinate;
+ * primary == -1: the Hilbert curve over the per-coordinate ranks (spatially compact 512-point
+ * tiles and 32-point sub-tiles in every coordinate); primary == -2: the leaf order of a balanced
+ * kd-tree over the ranks (conditional medians: the better order from ~7 coordinates up).
+ * *h_out is filled on the host; the device work is only enqueued (the per-coordinate sorts run
+ * concurrently on helper streams of the library, forked from and joined to `stream`).
+ * Replaces the cKDTree constructions of the path (syntropy/knn/utils.py:29 and every
+ * per-marginal tree: shannon.py:190,336; multivariate_mi.py:106,251,318-323,399-404) -- one
+ * sorted layout serves the joint space and all marginals.
+ *
+ * ksg_prepare_rows: the same, for rows that are still on their way to the device.
+ * h_row_ready (host array of dim cudaEvent_t handles, entries may be NULL) names, per coordinate,
+ * the event after which d_points[d][*] is valid -- typically recorded on a copy stream after the
+ * host-to-device copy of that row.  The sort of coordinate d waits for its own event only, so it
+ * overlaps the transfer of the rows behind it; everything `stream` does after the call is ordered
+ * after all the events.
  */
 size_t ksg_prepare_workspace(int64_t n, int dim);
 int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int primary,
                 void* d_buffer, size_t buffer_bytes, ksg_prepared* h_out, void* stream);
+int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int primary,
+                     void* const* h_row_ready, void* d_buffer, size_t buffer_bytes, ksg_prepared* h_out,
+                     void* stream);
 
 /*
  * K1 on the prepared set: d_eps_out[i - q_begin] = exact kprime-th smallest Chebyshev

@@ -92,6 +92,8 @@ SIGNATURES = {
                                              _c_vp, _c_vp]),
     "ksg_prepare_workspace": (C.c_size_t, [_c_i64, C.c_int]),
     "ksg_prepare": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, C.c_int, _c_vp, C.c_size_t, _c_prep, _c_vp]),
+    "ksg_prepare_rows": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, C.c_int, C.POINTER(C.c_void_p), _c_vp, C.c_size_t,
+                                   _c_prep, _c_vp]),
     "ksg_fast_knn_workspace": (C.c_size_t, [_c_i64, _c_i64, C.c_int, C.c_int]),
     "ksg_fast_knn": (C.c_int, [_c_prep, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp,
                                C.c_size_t, _c_vp]),

@@ -150,13 +150,34 @@ def _rows_are_page_locked(rows: RowSelection, dim: int) -> bool:
     return True
 
 
-def to_device_points(rows) -> torch.Tensor:
+_copy_streams: dict = {}  # device index -> the stream host-to-device row copies are issued on
+
+
+def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
+    s = _copy_streams.get(dev.index)
+    if s is None:
+        s = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def wait_rows(row_ready) -> None:
+    """Order the current stream after the row copies of ``to_device_points(..., row_events=True)``."""
+    for ev in row_ready or ():
+        ev.wait()
+
+
+def to_device_points(rows, row_events: bool = False):
     """(D, n) array of any real dtype (or a ``RowSelection``) -> contiguous float64 SoA tensor
     on the GPU.  cKDTree converts its input to C-contiguous float64 the same way (integer and
     float32 inputs are legal).
 
     Each row is converted into a pinned staging buffer by a few host threads and sent with
-    its own asynchronous copy, so the DMA of row r overlaps the host conversion of row r+1."""
+    its own asynchronous copy, so the DMA of row r overlaps the host conversion of row r+1.
+
+    ``row_events``: the copies are issued on a copy stream and ``(points, events)`` is returned,
+    events[r] recorded after row r's copy: the consumer (``PreparedSet``: ksg_prepare_rows) starts
+    sorting row r while the rows behind it are still in flight.  The caller must order every
+    other use of the tensor after the events (``wait_rows``)."""
     dev = require_cuda()
     if not isinstance(rows, RowSelection):
         arr = np.asarray(rows)
@@ -168,25 +189,42 @@ def to_device_points(rows) -> torch.Tensor:
         raise TypeError(f"data must be real-valued, got dtype {rows.data.dtype}")
     out = torch.empty((dim, n), dtype=torch.float64, device=dev)
     if dim == 0 or n == 0:
-        return out
-    if _rows_are_page_locked(rows, dim):
-        # the caller's array is already page-locked float64 (torch pinned memory, cudaHostRegister):
-        # the DMA reads it in place, no staging copy
-        for r in range(dim):
-            out[r].copy_(torch.from_numpy(rows.row(r)), non_blocking=True)
-        return out
-    prev = _stage_done.get(dev.index)
-    if prev is not None:
-        prev.synchronize()  # the staging buffer is reused: its last copies must have left it
-    stage = _pinned_buffer(dev, "in", dim * n * 8)[: dim * n * 8].view(torch.float64).view(dim, n)
-    stage_np = stage.numpy()
-    for r in range(dim):
-        _host_copy(stage_np[r], rows.row(r))
-        out[r].copy_(stage[r], non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record(torch.cuda.current_stream())
-    _stage_done[dev.index] = ev
-    return out
+        return (out, []) if row_events else out
+    events = []
+    main = torch.cuda.current_stream()
+    if row_events:
+        lane = _copy_stream(dev)
+        lane.wait_stream(main)  # `out` may be a recycled block with work pending on the main stream
+    else:
+        lane = main
+
+    def sent():
+        if row_events:
+            ev = torch.cuda.Event()
+            ev.record(lane)
+            events.append(ev)
+
+    with torch.cuda.stream(lane):
+        if _rows_are_page_locked(rows, dim):
+            # the caller's array is already page-locked float64 (torch pinned memory, cudaHostRegister):
+            # the DMA reads it in place, no staging copy
+            for r in range(dim):
+                out[r].copy_(torch.from_numpy(rows.row(r)), non_blocking=True)
+                sent()
+        else:
+            prev = _stage_done.get(dev.index)
+            if prev is not None:
+                prev.synchronize()  # the staging buffer is reused: its last copies must have left it
+            stage = _pinned_buffer(dev, "in", dim * n * 8)[: dim * n * 8].view(torch.float64).view(dim, n)
+            stage_np = stage.numpy()
+            for r in range(dim):
+                _host_copy(stage_np[r], rows.row(r))
+                out[r].copy_(stage[r], non_blocking=True)
+                sent()
+            ev = torch.cuda.Event()
+            ev.record(lane)
+            _stage_done[dev.index] = ev
+    return (out, events) if row_events else out
 
 
 PINNED_RESULT_MAX_BYTES = 64 << 20
@@ -374,16 +412,22 @@ def order_for(dim: int) -> int:
 class PreparedSet:
     """Host handle of a ksg_prepared: the struct, the owning buffer and typed views."""
 
-    def __init__(self, pts: torch.Tensor, primary: int):
+    def __init__(self, pts: torch.Tensor, primary: int, row_ready=None):
+        """``row_ready``: events of ``to_device_points(..., row_events=True)`` -- row d is sorted as
+        soon as its own copy has landed; the current stream is ordered after all of them on return."""
         lib = _cabi.load()
         dim, n = pts.shape
         size = int(lib.ksg_prepare_workspace(n, dim))
         self.buf = torch.empty(size, dtype=torch.uint8, device=pts.device)
         self.c = _cabi.Prepared()
+        ready = None
+        if row_ready:
+            assert len(row_ready) == dim
+            ready = (C.c_void_p * dim)(*[int(ev.cuda_event) for ev in row_ready])
         with timer.span("prepare"):
-            rc = lib.ksg_prepare(_ptr(pts), pts.stride(0), n, dim, primary, _ptr(self.buf), size,
-                                 C.byref(self.c), _stream())
-        _cabi.check(rc, "ksg_prepare")
+            rc = lib.ksg_prepare_rows(_ptr(pts), pts.stride(0), n, dim, primary, ready, _ptr(self.buf), size,
+                                      C.byref(self.c), _stream())
+        _cabi.check(rc, "ksg_prepare_rows")
         self.n, self.dim, self.ld = n, dim, int(self.c.ld)
 
     def _view(self, ptr, nbytes, dtype):
@@ -588,9 +632,11 @@ def finish_device(pw: Pointwise, n_total: int):
 def _finish(pw: Pointwise, n_total: int, flag: torch.Tensor):
     """Gather the pointwise slices of all ranks, reduce deterministically, copy out."""
     ptw_full, total = finish_device(pw, n_total)
-    tail = torch.cat([total, flag.to(torch.float64)])
-    ptw = to_host(ptw_full)
-    tail = tail.cpu().numpy()
+    tail_dev = torch.cat([total, flag.to(torch.float64)])
+    tail_pinned = torch.empty(2, dtype=torch.float64, pin_memory=True)
+    tail_pinned.copy_(tail_dev, non_blocking=True)
+    ptw = to_host(ptw_full)  # synchronises the stream: the tail has landed too
+    tail = tail_pinned.numpy()
     if tail[1] != 0.0:
         # what scipy's cKDTree constructor raises, reached from knn/utils.py:29
         raise ValueError("data must be finite, check for nan or inf values")
@@ -607,9 +653,9 @@ def ksg1_family(rows, k: int, masks, prog_builder):
     order; ``masks`` are subspace bitmasks over those D rows; ``prog_builder(psi_k,
     psi_N)`` returns the PsiProgram.
     """
-    pts = to_device_points(rows)
+    pts, row_ready = to_device_points(rows, row_events=True)
+    pw = ksg1_device(pts, k, masks, prog_builder, row_ready=row_ready)  # orders the stream after the copies
     flag = check_finite(pts)
-    pw = ksg1_device(pts, k, masks, prog_builder)
     return _finish(pw, pts.shape[1], flag)
 
 
@@ -636,14 +682,14 @@ def own_order_subspaces(masks, dim: int):
     return out
 
 
-def radius_and_counts(pts: torch.Tensor, k: int, masks):
+def radius_and_counts(pts: torch.Tensor, k: int, masks, row_ready=None):
     """Fast engines: joint radii and every subspace's strict counts for ALL n samples, in the
     caller's sample order, on every rank (each rank computes its slice of every pass; the
     slices are all-gathered).  Returns ``(eps (n,), counts (S, n) int32, prepared sets)``."""
     lib = _cabi.load()
     dim, n = pts.shape
     windowed = config.engine == "windowed"
-    prep = PreparedSet(pts, order_for(dim))
+    prep = PreparedSet(pts, order_for(dim), row_ready=row_ready)
     preps = [prep]
     q0, q1 = _dist.my_slice(n)
     eps = fast_knn(prep, k + 1, q0, q1, windowed)
@@ -672,11 +718,13 @@ def radius_and_counts(pts: torch.Tensor, k: int, masks):
     return eps_orig, counts, preps
 
 
-def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder) -> Pointwise:
-    """The device-resident part of ``ksg1_family``."""
+def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder, row_ready=None) -> Pointwise:
+    """The device-resident part of ``ksg1_family``.  ``row_ready``: see ``to_device_points``; the
+    current stream is ordered after those events when this returns."""
     dim, n = pts.shape
     prog = prog_builder(psi_host(k), psi_host(n))
     if not _use_fast(dim, k + 1):
+        wait_rows(row_ready)
         q0, q1 = _dist.my_slice(n)
         eps = knn_radius(pts, k + 1, q0, q1)
         counts = count_subspaces(pts, masks, eps, q0, q1, strict=True, bias=-1)
@@ -685,11 +733,11 @@ def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder) -> Pointwise:
         # everything is counted in the joint order: keep the slices sorted until the end
         windowed = config.engine == "windowed"
         q0, q1 = _dist.my_slice(n)
-        prep = PreparedSet(pts, order_for(dim))
+        prep = PreparedSet(pts, order_for(dim), row_ready=row_ready)
         eps = fast_knn(prep, k + 1, q0, q1, windowed)
         counts = fast_counts(prep, masks, eps, q0, q1, windowed)
         return Pointwise(psi_epilogue(counts, prog, n), prep=prep, preps=[prep])
-    _, counts, preps = radius_and_counts(pts, k, masks)
+    _, counts, preps = radius_and_counts(pts, k, masks, row_ready=row_ready)
     return Pointwise(psi_epilogue(counts, prog, n), full=True, preps=preps)
 
 

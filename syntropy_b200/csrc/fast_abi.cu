@@ -1,6 +1,8 @@
 // extern "C" entry points of the fast path (prepare / fast_knn / fast_count / axis_count).
 #include <string.h>
 
+#include <mutex>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -40,17 +42,43 @@ static inline PreparedLayout prepared_layout(int64_t n, int dim) {
     L.off_flags = take(64);
     L.off_tile_box = take((size_t)(L.n_padded / FAST_TILE) * L.dim_padded * 2 * 4);
     L.off_sub_box = take((size_t)(L.n_padded / FAST_TILE) * FAST_NSUB * L.dim_padded * 2 * 4);
-    L.off_stats = take((size_t)dim * STATS_BLOCKS * 2 * 8);
     L.off_iota = take((size_t)L.ld * 4);
-    L.off_keys_tmp = take((size_t)L.ld * 8);
     L.off_ranks = take((size_t)dim * L.ld * 4);
     L.off_mkeys = take((size_t)L.ld * 8);
     L.off_mkeys_out = take((size_t)L.ld * 8);
     L.off_invperm = take((size_t)L.ld * 4);
-    L.cub_bytes = cub_sort_bytes(n);
-    L.off_cub = take(L.cub_bytes);
+    L.cub_bytes = align_up(cub_sort_bytes(n), 256);
+    L.sort_lanes = dim < SORT_LANES ? dim : SORT_LANES;
+    L.off_cub = take(L.cub_bytes * L.sort_lanes);  // one CUB scratch area per concurrent coordinate sort
     L.total = o;
     return L;
+}
+
+// The per-coordinate sorts of ksg_prepare are independent and, at a million points, latency bound
+// (a one-sweep pass moves 24 MB in ~15 us): they run side by side on up to SORT_LANES streams --
+// lane 0 is the caller's stream, the others are helper streams of this library (one set per
+// device, created on first use) forked from / joined to the caller's stream with events.
+struct SortLanes {
+    cudaStream_t helper[SORT_LANES - 1];
+    cudaEvent_t fork, join[SORT_LANES - 1];
+    bool ready;
+};
+static SortLanes* sort_lanes_for_device() {
+    static SortLanes lanes[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    SortLanes& L = lanes[dev];
+    if (!L.ready) {
+        if (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int i = 0; i < SORT_LANES - 1; ++i) {
+            if (cudaStreamCreateWithFlags(&L.helper[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&L.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        L.ready = true;
+    }
+    return &L;
 }
 
 
@@ -129,6 +157,11 @@ size_t ksg_prepare_workspace(int64_t n, int dim) {
 
 int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int primary, void* d_buffer,
                 size_t buffer_bytes, ksg_prepared* h_out, void* stream) {
+    return ksg_prepare_rows(d_points, ld, n, dim, primary, nullptr, d_buffer, buffer_bytes, h_out, stream);
+}
+
+int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int primary, void* const* h_row_ready,
+                     void* d_buffer, size_t buffer_bytes, ksg_prepared* h_out, void* stream) {
     KSG_REQUIRE(d_points && d_buffer && h_out, "ksg_prepare: null pointer");
     KSG_REQUIRE(n > 0 && n < (1ll << 31) - 1024 && ld >= n, "ksg_prepare: need 0 < n < 2^31 and ld >= n");
     KSG_REQUIRE(dim >= 1 && dim <= KSG_MAX_DIM, "ksg_prepare: dim out of range");
@@ -150,30 +183,42 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
     P.center = (double*)(base + L.off_center);
     P.maxabs = (double*)(base + L.off_maxabs);
     P.flags = (int32_t*)(base + L.off_flags);
-    double* stats = (double*)(base + L.off_stats);
     int32_t* iota = (int32_t*)(base + L.off_iota);
-    (void)L.off_keys_tmp;
-    void* cub_tmp = base + L.off_cub;
+    char* cub_base = base + L.off_cub;
+    void* cub_tmp = cub_base;
     cudaStream_t st = as_stream2(stream);
 
     KSG_CUDA_TRY(cudaMemsetAsync(P.flags, 0, 64, st));
-    stats_stage1_kernel<<<dim3(STATS_BLOCKS, dim), 256, 0, st>>>(d_points, ld, n, stats, P.flags);
-    KSG_LAUNCHED2();
     iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
     KSG_LAUNCHED2();
     const unsigned nb = (unsigned)ceil_div(n, 256);
     int rc;
-    // every coordinate sorted on its own: values + ORIGINAL sample index (remapped below)
+    // every coordinate sorted on its own: values + ORIGINAL sample index (remapped below);
+    // coordinate d runs on lane d % sort_lanes (see SortLanes)
+    SortLanes* lanes = L.sort_lanes > 1 ? sort_lanes_for_device() : nullptr;
+    const int n_lanes = lanes ? L.sort_lanes : 1;
+    if (n_lanes > 1) {
+        KSG_CUDA_TRY(cudaEventRecord(lanes->fork, st));
+        for (int l = 1; l < n_lanes; ++l) KSG_CUDA_TRY(cudaStreamWaitEvent(lanes->helper[l - 1], lanes->fork, 0));
+    }
     for (int d = 0; d < dim; ++d) {
-        rc = sort_pairs(cub_tmp, L.cub_bytes, d_points + (int64_t)d * ld, P.axis_vals + (int64_t)d * L.ld, iota,
-                        P.axis_pos + (int64_t)d * L.ld, n, st);
+        const int lane = d % n_lanes;
+        if (h_row_ready && h_row_ready[d])
+            KSG_CUDA_TRY(cudaStreamWaitEvent(lane == 0 ? st : lanes->helper[lane - 1], (cudaEvent_t)h_row_ready[d], 0));
+        rc = sort_pairs(cub_base + (size_t)lane * L.cub_bytes, L.cub_bytes, d_points + (int64_t)d * ld,
+                        P.axis_vals + (int64_t)d * L.ld, iota, P.axis_pos + (int64_t)d * L.ld, n,
+                        lane == 0 ? st : lanes->helper[lane - 1]);
         if (rc) return rc;
     }
+    for (int l = 1; l < n_lanes; ++l) {
+        KSG_CUDA_TRY(cudaEventRecord(lanes->join[l - 1], lanes->helper[l - 1]));
+        KSG_CUDA_TRY(cudaStreamWaitEvent(st, lanes->join[l - 1], 0));
+    }
     // centre of the fp32 copy = per-coordinate MEDIAN (the bulk of the points then has small centred
-    // magnitudes, hence small fp32 error bands, even when outliers stretch the range)
-    center_median_kernel<<<1, KSG_MAX_DIM, 0, st>>>(P.axis_vals, L.ld, n, dim, P.center, P.maxabs);
+    // magnitudes, hence small fp32 error bands, even when outliers stretch the range); the ends of
+    // the sorted arrays also tell whether the input held a NaN or an infinity (flags[0])
+    center_median_kernel<<<1, KSG_MAX_DIM, 0, st>>>(P.axis_vals, L.ld, n, dim, P.center, P.maxabs, P.flags);
     KSG_LAUNCHED2();
-    (void)stats;
     if (primary >= 0) {
         // order = one coordinate's sorted order
         KSG_CUDA_TRY(cudaMemcpyAsync(P.perm, P.axis_pos + (int64_t)primary * L.ld, (size_t)n * 4,
@@ -183,10 +228,8 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
         int32_t* ranks = (int32_t*)(base + L.off_ranks);
         unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
         unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
-        for (int d = 0; d < dim; ++d) {
-            rank_scatter_kernel<<<nb, 256, 0, st>>>(P.axis_pos + (int64_t)d * L.ld, n, ranks + (int64_t)d * L.ld);
-            KSG_LAUNCHED2();
-        }
+        rank_scatter_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, ranks);
+        KSG_LAUNCHED2();
         const int64_t n_groups = ceil_div(n, FAST_SUB);
         int levels = 0;
         while ((1ll << levels) < n_groups) ++levels;
@@ -209,10 +252,8 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
         int32_t* ranks = (int32_t*)(base + L.off_ranks);
         unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
         unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
-        for (int d = 0; d < dim; ++d) {
-            rank_scatter_kernel<<<nb, 256, 0, st>>>(P.axis_pos + (int64_t)d * L.ld, n, ranks + (int64_t)d * L.ld);
-            KSG_LAUNCHED2();
-        }
+        rank_scatter_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, ranks);
+        KSG_LAUNCHED2();
         int rank_bits, bits;
         curve_bits(n, dim, &rank_bits, &bits);
         switch (dim) {
@@ -236,10 +277,8 @@ int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int prim
     int32_t* invperm = (int32_t*)(base + L.off_invperm);
     invert_perm_kernel<<<nb, 256, 0, st>>>(P.perm, n, invperm);
     KSG_LAUNCHED2();
-    for (int d = 0; d < dim; ++d) {
-        remap_axis_kernel<<<nb, 256, 0, st>>>(P.axis_pos + (int64_t)d * L.ld, n, invperm);
-        KSG_LAUNCHED2();
-    }
+    remap_axis_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, invperm);
+    KSG_LAUNCHED2();
     P.tile_box = (float*)(base + L.off_tile_box);
     P.sub_box = (float*)(base + L.off_sub_box);
     tile_box_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 128, 0, st>>>(P.shadow_f32, L.dim_padded, P.tile_box,

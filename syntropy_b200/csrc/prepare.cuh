@@ -21,6 +21,7 @@ constexpr int FAST_TILE = 512;       // candidates per shared-memory tile (fast 
 constexpr int FAST_SUB = 32;         // rows of a sub-tile (own bounding box: warp-level culling)
 constexpr int FAST_NSUB = FAST_TILE / FAST_SUB;
 constexpr int STATS_BLOCKS = 256;    // partial min/max blocks per dimension
+constexpr int SORT_LANES = 4;        // per-coordinate sorts of ksg_prepare that run concurrently
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -31,8 +32,9 @@ struct PreparedLayout {
     int dim_padded;
     size_t off_perm, off_sorted, off_shadow, off_axis_vals, off_axis_pos, off_center, off_maxabs, off_flags;
     size_t off_tile_box, off_sub_box;
-    size_t off_stats, off_iota, off_keys_tmp, off_ranks, off_mkeys, off_mkeys_out, off_invperm, off_cub;
-    size_t cub_bytes;
+    size_t off_iota, off_ranks, off_mkeys, off_mkeys_out, off_invperm, off_cub;
+    size_t cub_bytes;  // per sort lane
+    int sort_lanes;
     size_t total;
 };
 
@@ -68,13 +70,17 @@ stats_stage1_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, doubl
     }
 }
 
-// centre[d] = median of coordinate d (middle entry of its sorted array); maxabs[d] = max |x - centre|
+// centre[d] = median of coordinate d (middle entry of its sorted array); maxabs[d] = max |x - centre|;
+// flags[0] = 1 if any coordinate holds a NaN or an infinity (the radix order puts -inf and negative
+// NaNs first, +inf and positive NaNs last: the two ends of every sorted array tell)
 static __global__ void center_median_kernel(const double* __restrict__ axis_vals, int64_t ld, int64_t n, int dim,
-                                            double* __restrict__ center, double* __restrict__ maxabs) {
+                                            double* __restrict__ center, double* __restrict__ maxabs,
+                                            int32_t* __restrict__ flags) {
     const int d = threadIdx.x;
     if (d >= dim) return;
     const double* v = axis_vals + (int64_t)d * ld;
     double c = v[n / 2], lo = v[0], hi = v[n - 1];
+    if (!isfinite(lo) || !isfinite(hi)) atomicExch(&flags[0], 1);
     if (!isfinite(c)) c = 0.0;  // non-finite input is flagged elsewhere; keep the math finite
     if (!isfinite(lo)) lo = c;
     if (!isfinite(hi)) hi = c;
@@ -115,10 +121,12 @@ gather_sorted_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, i
 
 // ---- space-filling-curve order on per-coordinate RANKS (rank-uniform: cells hold ~equal point counts)
 // rank[d][orig] = position of sample `orig` in coordinate d's sorted order
-static __global__ void rank_scatter_kernel(const int32_t* __restrict__ sorted_orig, int64_t n,
-                                           int32_t* __restrict__ rank_row) {
+// (grid.y = coordinate; both arrays have row stride ld)
+static __global__ void rank_scatter_kernel(const int32_t* __restrict__ sorted_orig, int64_t ld, int64_t n,
+                                           int32_t* __restrict__ ranks) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) rank_row[sorted_orig[i]] = (int32_t)i;
+    const int64_t row = (int64_t)blockIdx.y * ld;
+    if (i < n) ranks[row + sorted_orig[row + i]] = (int32_t)i;
 }
 
 // key = Hilbert-curve index of the point in rank space: the top `bits` bits of every
@@ -291,10 +299,14 @@ static __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int6
     if (i < n) inv[perm[i]] = (int32_t)i;
 }
 
-// axis_pos[i] (an original sample index) -> its position in the final order
-static __global__ void remap_axis_kernel(int32_t* __restrict__ pos, int64_t n, const int32_t* __restrict__ inv) {
+// axis_pos[d][i] (an original sample index) -> its position in the final order (grid.y = coordinate)
+static __global__ void remap_axis_kernel(int32_t* __restrict__ pos, int64_t ld, int64_t n,
+                                         const int32_t* __restrict__ inv) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pos[i] = inv[pos[i]];
+    if (i < n) {
+        int32_t* p = pos + (int64_t)blockIdx.y * ld + i;
+        *p = inv[*p];
+    }
 }
 
 // tile_box[(t * dim_padded + d) * 2 + {0,1}] = min / max of the fp32 shadow over tile t;

@@ -573,3 +573,37 @@ def test_randomised_engine_agreement():
     proc = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_engines.py"), "--cases", "30", "--seed", "3"],
                           capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0 and "FUZZ_OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
+
+
+def test_rows_in_flight_prepare_equals_resident_prepare(windowed):
+    """ksg_prepare_rows with per-row copy events (the sort of row d overlaps the transfer of the
+    rows behind it) builds the same prepared set as ksg_prepare on resident points, for pageable
+    and page-locked host arrays, and reports non-finite input in flags[0]."""
+    import torch
+
+    E, knn = windowed
+    rng = np.random.default_rng(77)
+    for dim, n in ((2, 200_000), (5, 70_001), (8, 30_000)):
+        host = rng.standard_normal((dim, n))
+        resident = E.to_device_points(host)
+        torch.cuda.synchronize()
+        base = E.PreparedSet(resident, E.order_for(dim))
+        for src in (host, torch.from_numpy(host).pin_memory().numpy()):
+            pts, ready = E.to_device_points(E.select_rows(src, range(dim)), row_events=True)
+            assert len(ready) == dim
+            prep = E.PreparedSet(pts, E.order_for(dim), row_ready=ready)
+            assert torch.equal(prep.perm, base.perm)
+            assert torch.equal(prep.sorted_f64, base.sorted_f64)
+            assert int(prep.flags[0]) == 0
+    bad = rng.standard_normal((3, 5000))
+    for value in (np.nan, -np.nan, np.inf, -np.inf):
+        rows = bad.copy()
+        rows[1, 1234] = value
+        prep = E.PreparedSet(E.to_device_points(rows), -1)
+        assert int(prep.flags[0]) == 1, value
+    a = rng.standard_normal((2, 150_000))
+    a[1] += a[0]
+    pinned = torch.from_numpy(a).pin_memory().numpy()
+    p1, m1 = knn.mutual_information((0,), (1,), 4, a)
+    p2, m2 = knn.mutual_information((0,), (1,), 4, pinned)
+    assert np.array_equal(p1, p2) and m1 == m2
