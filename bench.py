@@ -283,8 +283,12 @@ def run_b200_arm(args):
     last = {}
 
     def device_step():
-        pw = E.ksg1_device(pts, k, masks, mi1_program)
-        full, total = E.finish_device(pw, n)
+        # what knn.mutual_information does after the upload and before the download: the 16-byte
+        # status block is read back (and the step recomputed if the k-NN filter flagged queries)
+        status = E.Status(dev)
+        pw = E.ksg1_device(pts, k, masks, mi1_program, status=status)
+        full, total = E.finish_device(pw, n, out=status.total)
+        pw, full, total = E.settle(pw, n, status, full, total)
         last["pw"] = pw
         return full, total
 

@@ -372,9 +372,10 @@ def psi_epilogue(counts: torch.Tensor, prog: PsiProgram, n_total: int) -> torch.
     return ptw
 
 
-def device_sum(values: torch.Tensor) -> torch.Tensor:
+def device_sum(values: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     lib = _cabi.load()
-    out = torch.empty(1, dtype=torch.float64, device=values.device)
+    if out is None:
+        out = torch.empty(1, dtype=torch.float64, device=values.device)
     ws = torch.empty(int(lib.ksg_sum_workspace(values.numel())), dtype=torch.uint8, device=values.device)
     with timer.span("sum_f64"):
         rc = lib.ksg_sum_f64(_ptr(values), values.numel(), _ptr(out), _ptr(ws), ws.numel(), _stream())
@@ -467,14 +468,17 @@ def _lists_fit(dim: int, kcap: int) -> bool:
 
 
 def _fast_knn_call(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, q_index=None,
-                   want_indices: bool = False, margin: int = KNN_MARGIN):
+                   want_indices: bool = False, margin: int = KNN_MARGIN, nflag: torch.Tensor | None = None):
+    """One ksg_fast_knn_margin launch sequence (nothing is read back).  ``nflag``: a zeroed int32[1]
+    device counter to use instead of a fresh one."""
     lib = _cabi.load()
     nq = q1 - q0
     dev = prep.buf.device
     eps = torch.empty(nq, dtype=torch.float64, device=dev)
     idx = torch.empty((nq, kprime), dtype=torch.int64, device=dev) if want_indices else None
     flags = torch.empty(nq, dtype=torch.int32, device=dev)
-    nflag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if nflag is None:
+        nflag = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = torch.empty(max(int(lib.ksg_fast_knn_workspace_margin(prep.n, max(nq, 1), prep.dim, kprime, margin)), 1),
                      dtype=torch.uint8, device=dev)
     with timer.span("fast_knn" if q_index is None else "fast_knn_deferred"):
@@ -494,33 +498,41 @@ def fast_knn(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, w
     nq = q1 - q0
     eps, nbr, flags, nflag = _fast_knn_call(prep, kprime, q0, q1, windowed, want_indices=want_indices)
     if nq and int(nflag.item()):
-        n_tied = int((flags == 1).sum().item())
-        # worth it when the dense float64 pass over the tied queries (n_tied x n pairs at ~3e12 pairs/s)
-        # would cost more than a second filter pass over all of them (~70 ns per query, measured)
-        if (windowed and n_tied * prep.n > 4e5 * nq and _lists_fit(prep.dim, kprime + KNN_WIDE_MARGIN)):
-            stats["knn_wide_margin_passes"] += 1
-            eps, nbr, flags, nflag = _fast_knn_call(prep, kprime, q0, q1, windowed, want_indices=want_indices,
-                                                    margin=KNN_WIDE_MARGIN)
-        deferred = (flags == 2).nonzero().flatten()
-        if deferred.numel():
-            stats["knn_deferred_queries"] += int(deferred.numel())
-            rows = (q0 + deferred).to(torch.int32)
-            eps2, nbr2, flags2, _ = _fast_knn_call(prep, kprime, 0, int(rows.numel()), False, q_index=rows,
-                                                   want_indices=want_indices)
-            eps[deferred] = eps2
-            flags[deferred] = flags2
-            if want_indices:
-                nbr[deferred] = nbr2
-        idx = (flags == 1).nonzero().flatten()
-        if idx.numel():
-            stats["knn_fallback_queries"] += int(idx.numel())
-            pts = prep.sorted_f64
-            queries = pts[:, q0 + idx].contiguous()
-            if want_indices:
-                eps[idx], nbr[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries, want_indices=True)
-            else:
-                eps[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries)
+        eps, nbr = _fast_knn_escalate(prep, kprime, q0, q1, windowed, want_indices, eps, nbr, flags)
     return (eps, nbr) if want_indices else eps
+
+
+def _fast_knn_escalate(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, want_indices: bool,
+                       eps: torch.Tensor, nbr, flags: torch.Tensor):
+    """The first pass flagged queries (see ``fast_knn``): settle them; returns the final (eps, nbr)."""
+    nq = q1 - q0
+    n_tied = int((flags == 1).sum().item())
+    # worth it when the dense float64 pass over the tied queries (n_tied x n pairs at ~3e12 pairs/s)
+    # would cost more than a second filter pass over all of them (~70 ns per query, measured)
+    if (windowed and n_tied * prep.n > 4e5 * nq and _lists_fit(prep.dim, kprime + KNN_WIDE_MARGIN)):
+        stats["knn_wide_margin_passes"] += 1
+        eps, nbr, flags, _ = _fast_knn_call(prep, kprime, q0, q1, windowed, want_indices=want_indices,
+                                            margin=KNN_WIDE_MARGIN)
+    deferred = (flags == 2).nonzero().flatten()
+    if deferred.numel():
+        stats["knn_deferred_queries"] += int(deferred.numel())
+        rows = (q0 + deferred).to(torch.int32)
+        eps2, nbr2, flags2, _ = _fast_knn_call(prep, kprime, 0, int(rows.numel()), False, q_index=rows,
+                                               want_indices=want_indices)
+        eps[deferred] = eps2
+        flags[deferred] = flags2
+        if want_indices:
+            nbr[deferred] = nbr2
+    idx = (flags == 1).nonzero().flatten()
+    if idx.numel():
+        stats["knn_fallback_queries"] += int(idx.numel())
+        pts = prep.sorted_f64
+        queries = pts[:, q0 + idx].contiguous()
+        if want_indices:
+            eps[idx], nbr[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries, want_indices=True)
+        else:
+            eps[idx] = knn_radius(pts, kprime, 0, int(idx.numel()), queries=queries)
+    return eps, nbr
 
 
 def fast_counts(prep: PreparedSet, masks, eps: torch.Tensor, q0: int, q1: int, windowed: bool,
@@ -590,12 +602,31 @@ def _use_fast(dim: int, kprime: int = 1) -> bool:
     return ring + lists <= 200 * 1024 and kprime + 3 <= 64
 
 
-def check_finite(points: torch.Tensor) -> torch.Tensor:
-    flag = torch.zeros(1, dtype=torch.int32, device=points.device)
+def check_finite(points: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """flag (int32[1], or ``out``: only ever set, never cleared) = 1 if any entry is NaN or infinite."""
+    flag = torch.zeros(1, dtype=torch.int32, device=points.device) if out is None else out
     assert points.is_contiguous()
     rc = _cabi.load().ksg_check_finite(_ptr(points), points.numel(), _ptr(flag), _stream())
     _cabi.check(rc, "ksg_check_finite")
     return flag
+
+
+class Status:
+    """16 device bytes that an estimator call reads back once, at the very end, together with its
+    result: [0:8) the float64 sum of the pointwise values, [8:12) int32 non-finite-input flag,
+    [12:16) int32 number of queries the speculative k-NN pass could not settle (see ``ksg1_device``)."""
+
+    def __init__(self, device):
+        self.buf = torch.zeros(4, dtype=torch.int32, device=device)
+        self.total = self.buf[0:2].view(torch.float64)
+        self.finite = self.buf[2:3]
+        self.nflag = self.buf[3:4]
+
+    def read_async(self) -> np.ndarray:
+        """Enqueue the copy to page-locked host memory; valid after the stream is synchronised."""
+        host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+        host.copy_(self.buf, non_blocking=True)
+        return host.numpy()
 
 
 class Pointwise:
@@ -604,10 +635,13 @@ class Pointwise:
     ``full`` False: ``values`` is this rank's query slice -- in the order of ``prep`` (sorted
     positions) when ``prep`` is given, else in the caller's sample order (exact engine).
     ``full`` True: ``values`` already holds all n samples in the caller's order on every rank.
-    ``preps`` lists every prepared set the call built (for the pair counters)."""
+    ``preps`` lists every prepared set the call built (for the pair counters).
+    ``redo``: set by a speculative run (``ksg1_device``): the values are final only if the
+    ``Status.nflag`` they were computed under reads 0; otherwise ``redo()`` returns the settled
+    Pointwise."""
 
-    def __init__(self, values, prep=None, full=False, preps=()):
-        self.values, self.prep, self.full, self.preps = values, prep, full, list(preps)
+    def __init__(self, values, prep=None, full=False, preps=(), redo=None):
+        self.values, self.prep, self.full, self.preps, self.redo = values, prep, full, list(preps), redo
 
     def pairs_evaluated(self):
         a = b = 0
@@ -617,31 +651,49 @@ class Pointwise:
         return a, b
 
 
-def finish_device(pw: Pointwise, n_total: int):
+def finish_device(pw: Pointwise, n_total: int, out: torch.Tensor | None = None):
     """All-gather the pointwise slices (NCCL), put them back into the caller's sample order
-    if they were computed in sorted order, and reduce the full vector in a fixed order."""
+    if they were computed in sorted order, and reduce the full vector in a fixed order
+    (into ``out``, a float64[1] device view, when given)."""
     if pw.full:
         ptw_full = pw.values
     else:
         ptw_full = _dist.gather_slices(pw.values, n_total)
         if pw.prep is not None:
             ptw_full = scatter_to_original(ptw_full, pw.prep)
-    return ptw_full, device_sum(ptw_full)
+    return ptw_full, device_sum(ptw_full, out=out)
 
 
-def _finish(pw: Pointwise, n_total: int, flag: torch.Tensor):
+def settle(pw: Pointwise, n_total: int, status: Status, ptw_full: torch.Tensor, total: torch.Tensor):
+    """Device-resident callers (bench.py): what ``_finish`` does for a speculative run without the
+    copy of the result -- read the status block and recompute if the k-NN pass had flagged queries.
+    Returns the final ``(pw, ptw_full, total)``."""
+    if pw.redo is None:
+        return pw, ptw_full, total
+    host = status.read_async()
+    torch.cuda.current_stream().synchronize()
+    if int(host[3]) == 0:
+        return pw, ptw_full, total
+    pw = pw.redo()
+    status.nflag.zero_()
+    ptw_full, total = finish_device(pw, n_total, out=status.total)
+    return pw, ptw_full, total
+
+
+def _finish(pw: Pointwise, n_total: int, status: Status):
     """Gather the pointwise slices of all ranks, reduce deterministically, copy out."""
-    ptw_full, total = finish_device(pw, n_total)
-    tail_dev = torch.cat([total, flag.to(torch.float64)])
-    tail_pinned = torch.empty(2, dtype=torch.float64, pin_memory=True)
-    tail_pinned.copy_(tail_dev, non_blocking=True)
-    ptw = to_host(ptw_full)  # synchronises the stream: the tail has landed too
-    tail = tail_pinned.numpy()
-    if tail[1] != 0.0:
+    ptw_full, _ = finish_device(pw, n_total, out=status.total)
+    host = status.read_async()
+    ptw = to_host(ptw_full)  # synchronises the stream: the status block has landed too
+    if int(host[2]) != 0:
         # what scipy's cKDTree constructor raises, reached from knn/utils.py:29
         raise ValueError("data must be finite, check for nan or inf values")
+    if pw.redo is not None and int(host[3]) != 0:
+        settled = pw.redo()
+        status.nflag.zero_()
+        return _finish(settled, n_total, status)
     with np.errstate(all="ignore"):
-        avg = np.float64(tail[0]) / n_total  # ndarray.mean(): sum / N
+        avg = host[0:2].view(np.float64)[0] / n_total  # ndarray.mean(): sum / N
     return ptw, avg
 
 
@@ -654,9 +706,11 @@ def ksg1_family(rows, k: int, masks, prog_builder):
     psi_N)`` returns the PsiProgram.
     """
     pts, row_ready = to_device_points(rows, row_events=True)
-    pw = ksg1_device(pts, k, masks, prog_builder, row_ready=row_ready)  # orders the stream after the copies
-    flag = check_finite(pts)
-    return _finish(pw, pts.shape[1], flag)
+    status = Status(pts.device)
+    # (orders the stream after the row copies)
+    pw = ksg1_device(pts, k, masks, prog_builder, row_ready=row_ready, status=status)
+    check_finite(pts, out=status.finite)
+    return _finish(pw, pts.shape[1], status)
 
 
 def _dims_of(mask: int):
@@ -718,9 +772,18 @@ def radius_and_counts(pts: torch.Tensor, k: int, masks, row_ready=None):
     return eps_orig, counts, preps
 
 
-def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder, row_ready=None) -> Pointwise:
+def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder, row_ready=None,
+                status: Status | None = None) -> Pointwise:
     """The device-resident part of ``ksg1_family``.  ``row_ready``: see ``to_device_points``; the
-    current stream is ordered after those events when this returns."""
+    current stream is ordered after those events when this returns.
+
+    ``status`` (single rank, 1-D marginals only -- the MI of two scalar series): the run is
+    SPECULATIVE.  The k-NN filter's count of unsettled queries goes to ``status.nflag`` and is not
+    read here; the binary-search counts and the psi pass are enqueued right behind the k-NN
+    kernels, so the device never waits for the host in mid-call.  The caller reads the status
+    block with the result (``_finish`` / ``settle``) and, in the rare flagged case (tie-saturated
+    neighbourhoods, set-aside outliers), calls ``Pointwise.redo``: escalation of the flagged
+    queries, then the cheap stages again."""
     dim, n = pts.shape
     prog = prog_builder(psi_host(k), psi_host(n))
     if not _use_fast(dim, k + 1):
@@ -734,6 +797,18 @@ def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder, row_ready=None) 
         windowed = config.engine == "windowed"
         q0, q1 = _dist.my_slice(n)
         prep = PreparedSet(pts, order_for(dim), row_ready=row_ready)
+        speculative = (status is not None and q1 - q0 == n and n > 0
+                       and all(bin(int(m)).count("1") == 1 for m in masks))
+        if speculative:
+            eps, _, flags, _ = _fast_knn_call(prep, k + 1, q0, q1, windowed, nflag=status.nflag)
+            counts = fast_counts(prep, masks, eps, q0, q1, windowed)
+
+            def redo():
+                eps2, _ = _fast_knn_escalate(prep, k + 1, q0, q1, windowed, False, eps, None, flags)
+                counts2 = fast_counts(prep, masks, eps2, q0, q1, windowed)
+                return Pointwise(psi_epilogue(counts2, prog, n), prep=prep, preps=[prep])
+
+            return Pointwise(psi_epilogue(counts, prog, n), prep=prep, preps=[prep], redo=redo)
         eps = fast_knn(prep, k + 1, q0, q1, windowed)
         counts = fast_counts(prep, masks, eps, q0, q1, windowed)
         return Pointwise(psi_epilogue(counts, prog, n), prep=prep, preps=[prep])
@@ -747,7 +822,8 @@ def ksg2_family(rows, k: int, masks, prog_builder):
     lib = _cabi.load()
     pts = to_device_points(rows)
     dim, n = pts.shape
-    flag = check_finite(pts)
+    status = Status(pts.device)
+    check_finite(pts, out=status.finite)
     q0, q1 = _dist.my_slice(n)
     nq = q1 - q0
     prog = prog_builder(psi_host(k), psi_host(n))
@@ -758,7 +834,7 @@ def ksg2_family(rows, k: int, masks, prog_builder):
                                                      _masks(masks), len(masks), _ptr(eps_s), _stream())
         _cabi.check(rc, "ksg_subspace_radius_from_neighbours")
         counts = count_subspaces(pts, masks, eps_s, q0, q1, strict=False, bias=-1, per_subspace_eps=True)
-        return _finish(Pointwise(psi_epilogue(counts, prog, n)), n, flag)
+        return _finish(Pointwise(psi_epilogue(counts, prog, n)), n, status)
 
     # fast engines: neighbours from the fp32 filter + exact refine (prepared order); every
     # subspace has its own radius, so every multi-dimensional one gets its own single-subspace pass
@@ -794,13 +870,14 @@ def ksg2_family(rows, k: int, masks, prog_builder):
             e_s = e_all[q0:q1].contiguous()
         c = fast_counts(prep_s, [(1 << len(dims)) - 1], e_s, q0, q1, windowed, strict=False, bias=-1)
         to_original(c[0], prep_s, counts[s])
-    return _finish(Pointwise(psi_epilogue(counts, prog, n), full=True, preps=preps), n, flag)
+    return _finish(Pointwise(psi_epilogue(counts, prog, n), full=True, preps=preps), n, status)
 
 
 def kl_entropy(rows: np.ndarray, k: int):
     pts = to_device_points(rows)
     dim, n = pts.shape
-    flag = check_finite(pts)
+    status = Status(pts.device)
+    check_finite(pts, out=status.finite)
     q0, q1 = _dist.my_slice(n)
     prep = None
     if _use_fast(dim, k + 1):
@@ -811,7 +888,7 @@ def kl_entropy(rows: np.ndarray, k: int):
     ptw = torch.empty(q1 - q0, dtype=torch.float64, device=pts.device)
     rc = _cabi.load().ksg_entropy_epilogue(_ptr(eps), q1 - q0, dim, psi_host(k), psi_host(n), _ptr(ptw), _stream())
     _cabi.check(rc, "ksg_entropy_epilogue")
-    return _finish(Pointwise(ptw, prep=prep), n, flag)
+    return _finish(Pointwise(ptw, prep=prep), n, status)
 
 
 class CrossSet:
@@ -878,7 +955,9 @@ def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
     Q = to_device_points(prior_rows)
     dim, n = P.shape
     m = Q.shape[1]
-    flag = check_finite(P) | check_finite(Q)
+    status = Status(P.device)
+    check_finite(P, out=status.finite)
+    check_finite(Q, out=status.finite)
     q0, q1 = _dist.my_slice(n)
     with np.errstate(all="ignore"):
         log_ratio = float(np.log(m / (n - 1)))
@@ -888,7 +967,7 @@ def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
         ptw = torch.empty(q1 - q0, dtype=torch.float64, device=P.device)
         rc = lib.ksg_kl_epilogue(_ptr(nu), _ptr(rho), q1 - q0, dim, log_ratio, _ptr(ptw), _stream())
         _cabi.check(rc, "ksg_kl_epilogue")
-        return _finish(Pointwise(ptw), n, flag)
+        return _finish(Pointwise(ptw), n, status)
     windowed = config.engine == "windowed"
     prep_p = PreparedSet(P, order_for(dim))
     rho = scatter_to_original(_dist.gather_slices(fast_knn(prep_p, k + 1, q0, q1, windowed), n), prep_p)
@@ -903,7 +982,7 @@ def kl_divergence(post_rows: np.ndarray, prior_rows: np.ndarray, k: int):
     ptw = torch.empty(n, dtype=torch.float64, device=P.device)
     rc = lib.ksg_kl_epilogue(_ptr(nu), _ptr(rho), n, dim, log_ratio, _ptr(ptw), _stream())
     _cabi.check(rc, "ksg_kl_epilogue")
-    return _finish(Pointwise(ptw, full=True, preps=[prep_p, prep_q]), n, flag)
+    return _finish(Pointwise(ptw, full=True, preps=[prep_p, prep_q]), n, status)
 
 
 def _self_pair_count(templates: torch.Tensor, r: float) -> torch.Tensor:

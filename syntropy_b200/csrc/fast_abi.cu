@@ -1,7 +1,9 @@
 // extern "C" entry points of the fast path (prepare / fast_knn / fast_count / axis_count).
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -14,7 +16,7 @@
 
 namespace ksg {
 
-static inline size_t cub_sort_bytes(int64_t n) {
+static inline size_t cub_sort_bytes_query(int64_t n) {
     size_t bytes = 0;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const double*)nullptr, (double*)nullptr,
                                                     (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
@@ -22,6 +24,26 @@ static inline size_t cub_sort_bytes(int64_t n) {
         (void)cudaGetLastError();
         bytes = (size_t)n * 16 + (16u << 20);  // no device visible: conservative estimate
     }
+    return bytes;
+}
+
+// (the size query walks CUB's whole dispatch on the host: remember the last few answers)
+static inline size_t cub_sort_bytes(int64_t n) {
+    static std::mutex mu;
+    static int64_t seen_n[8];
+    static size_t seen_bytes[8];
+    static int used = 0, next = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (int i = 0; i < used; ++i)
+            if (seen_n[i] == n) return seen_bytes[i];
+    }
+    const size_t bytes = cub_sort_bytes_query(n);
+    std::lock_guard<std::mutex> lock(mu);
+    seen_n[next] = n;
+    seen_bytes[next] = bytes;
+    next = (next + 1) % 8;
+    if (used < 8) ++used;
     return bytes;
 }
 
@@ -81,6 +103,144 @@ static SortLanes* sort_lanes_for_device() {
     return &L;
 }
 
+
+// ---- launch-sequence cache.  ksg_prepare is ~60 short launches (three radix sorts of 5-8 passes
+// each, every pass a memset + a ~17 us kernel): at a million points the host cannot enqueue two
+// concurrent sorts as fast as the device retires them, and every launch leaves a 2-3 us gap.  A
+// sequence that is requested again with the SAME arguments (pointers, sizes, options -- what an
+// estimator called in a loop, or an allocator that recycles its blocks, produces) is captured once
+// into a CUDA graph and replayed with one launch from then on.  First sighting: direct launches
+// (a one-off call never pays for a capture); second sighting: capture + instantiate + launch;
+// later: replay.  KSG_B200_GRAPHS=0 switches the cache off.
+struct GraphKey {
+    int32_t dev, kind;
+    const void* ptr[5];
+    int64_t i64[3];
+    int32_t i32[4];
+};
+enum { GRAPH_AXIS_SORT = 1, GRAPH_PREPARE_TAIL = 2 };
+constexpr size_t GRAPH_CACHE_ENTRIES = 32;
+
+class GraphCache {
+    struct Entry {
+        GraphKey key;
+        cudaGraphExec_t exec;
+        unsigned long long launches;
+        uint64_t stamp;
+    };
+    std::mutex mu_;
+    std::vector<Entry> entries_;
+    uint64_t clock_ = 0;
+    bool disabled_;
+    cudaStream_t capture_stream_[64] = {};
+
+    cudaStream_t capture_stream(int dev) {
+        if (dev < 0 || dev >= 64) return nullptr;
+        if (!capture_stream_[dev] &&
+            cudaStreamCreateWithFlags(&capture_stream_[dev], cudaStreamNonBlocking) != cudaSuccess) {
+            (void)cudaGetLastError();
+            capture_stream_[dev] = nullptr;
+        }
+        return capture_stream_[dev];
+    }
+
+    template <class Body>
+    bool capture(Entry& e, Body& body) {
+        cudaStream_t cap = capture_stream(e.key.dev);
+        if (!cap) return false;
+        if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        const unsigned long long l0 = ksg_launch_count();
+        const int rc = body(cap);
+        const unsigned long long l1 = ksg_launch_count();
+        cudaGraph_t graph = nullptr;
+        cudaError_t err = cudaStreamEndCapture(cap, &graph);
+        cudaGraphExec_t exec = nullptr;
+        if (rc == KSG_OK && err == cudaSuccess && graph) err = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) (void)cudaGraphDestroy(graph);
+        if (rc != KSG_OK || err != cudaSuccess || !exec) {
+            (void)cudaGetLastError();
+            note_launches(-(long long)(l1 - l0));  // nothing was launched
+            return false;
+        }
+        e.exec = exec;
+        e.launches = l1 - l0;  // (counted once by the capture pass itself)
+        return true;
+    }
+
+public:
+    GraphCache() {
+        const char* env = getenv("KSG_B200_GRAPHS");
+        disabled_ = env && env[0] == '0';
+    }
+
+    // Enqueue body(stream)'s launches on `st`: directly, or as the replay of their captured graph.
+    template <class Body>
+    int run(const GraphKey& key, cudaStream_t st, Body&& body) {
+        if (disabled_) return body(st);
+        cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &status) != cudaSuccess || status != cudaStreamCaptureStatusNone) {
+            (void)cudaGetLastError();
+            return body(st);  // the caller is capturing: stay part of ITS graph
+        }
+        std::unique_lock<std::mutex> lock(mu_);
+        Entry* hit = nullptr;
+        for (Entry& e : entries_)
+            if (memcmp(&e.key, &key, sizeof(GraphKey)) == 0) { hit = &e; break; }
+        if (!hit) {
+            if (entries_.size() >= GRAPH_CACHE_ENTRIES) {
+                size_t lru = 0;
+                for (size_t i = 1; i < entries_.size(); ++i)
+                    if (entries_[i].stamp < entries_[lru].stamp) lru = i;
+                if (entries_[lru].exec) (void)cudaGraphExecDestroy(entries_[lru].exec);
+                entries_.erase(entries_.begin() + (long)lru);
+            }
+            entries_.push_back(Entry{key, nullptr, 0ull, ++clock_});
+            lock.unlock();
+            return body(st);
+        }
+        hit->stamp = ++clock_;
+        bool counted = false;
+        if (!hit->exec) {
+            if (!capture(*hit, body)) {
+                disabled_ = true;  // capture is not possible here: direct launches from now on
+                lock.unlock();
+                return body(st);
+            }
+            counted = true;
+        }
+        const cudaError_t err = cudaGraphLaunch(hit->exec, st);
+        if (err != cudaSuccess) {
+            set_error("cudaGraphLaunch: %s", cudaGetErrorString(err));
+            (void)cudaGetLastError();
+            return KSG_ECUDA;
+        }
+        if (!counted) note_launches((long long)hit->launches);
+        return KSG_OK;
+    }
+};
+static GraphCache& graph_cache() {
+    static GraphCache cache;
+    return cache;
+}
+static inline GraphKey graph_key(int kind, std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> i64,
+                                 std::initializer_list<int32_t> i32) {
+    GraphKey k;
+    memset(&k, 0, sizeof(k));
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = -1; }
+    k.dev = dev;
+    k.kind = kind;
+    int i = 0;
+    for (const void* p : ptrs) k.ptr[i++] = p;
+    i = 0;
+    for (int64_t v : i64) k.i64[i++] = v;
+    i = 0;
+    for (int32_t v : i32) k.i32[i++] = v;
+    return k;
+}
 
 #define KSG_LAUNCHED2()                   \
     do {                                  \
@@ -205,15 +365,25 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
         const int lane = d % n_lanes;
         if (h_row_ready && h_row_ready[d])
             KSG_CUDA_TRY(cudaStreamWaitEvent(lane == 0 ? st : lanes->helper[lane - 1], (cudaEvent_t)h_row_ready[d], 0));
-        rc = sort_pairs(cub_base + (size_t)lane * L.cub_bytes, L.cub_bytes, d_points + (int64_t)d * ld,
-                        P.axis_vals + (int64_t)d * L.ld, iota, P.axis_pos + (int64_t)d * L.ld, n,
-                        lane == 0 ? st : lanes->helper[lane - 1]);
+        void* lane_tmp = cub_base + (size_t)lane * L.cub_bytes;
+        const double* keys_in = d_points + (int64_t)d * ld;
+        double* keys_out = P.axis_vals + (int64_t)d * L.ld;
+        int32_t* pos_out = P.axis_pos + (int64_t)d * L.ld;
+        rc = graph_cache().run(graph_key(GRAPH_AXIS_SORT, {keys_in, keys_out, iota, pos_out, lane_tmp}, {n}, {}),
+                               lane == 0 ? st : lanes->helper[lane - 1], [&](cudaStream_t s) {
+                                   return sort_pairs(lane_tmp, L.cub_bytes, keys_in, keys_out, iota, pos_out, n, s);
+                               });
         if (rc) return rc;
     }
     for (int l = 1; l < n_lanes; ++l) {
         KSG_CUDA_TRY(cudaEventRecord(lanes->join[l - 1], lanes->helper[l - 1]));
         KSG_CUDA_TRY(cudaStreamWaitEvent(st, lanes->join[l - 1], 0));
     }
+    P.tile_box = (float*)(base + L.off_tile_box);
+    P.sub_box = (float*)(base + L.off_sub_box);
+    if (primary == -1) P.curve_keys = (uint64_t*)(base + L.off_mkeys_out);
+    // everything behind the coordinate sorts, as one cached launch sequence
+    auto tail = [&](cudaStream_t st) -> int {
     // centre of the fp32 copy = per-coordinate MEDIAN (the bulk of the points then has small centred
     // magnitudes, hence small fp32 error bands, even when outliers stretch the range); the ends of
     // the sorted arrays also tell whether the input held a NaN or an infinity (flags[0])
@@ -268,7 +438,6 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                                                         bits * dim, st);
         if (e != cudaSuccess) { set_error("cub SortPairs (morton): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
         note_launch();
-        P.curve_keys = (uint64_t*)mkeys_out;
     }
     gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
         d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
@@ -279,11 +448,13 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     KSG_LAUNCHED2();
     remap_axis_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, invperm);
     KSG_LAUNCHED2();
-    P.tile_box = (float*)(base + L.off_tile_box);
-    P.sub_box = (float*)(base + L.off_sub_box);
     tile_box_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 128, 0, st>>>(P.shadow_f32, L.dim_padded, P.tile_box,
                                                                          P.sub_box);
     KSG_LAUNCHED2();
+    return KSG_OK;
+    };
+    rc = graph_cache().run(graph_key(GRAPH_PREPARE_TAIL, {d_points, d_buffer}, {n, ld}, {dim, primary}), st, tail);
+    if (rc) return rc;
     *h_out = P;
     return KSG_OK;
 }

@@ -108,6 +108,8 @@ __device__ __forceinline__ void load_two_rows(const float* __restrict__ row, flo
     }
 }
 
+constexpr int PLAN_MASK_WORDS = 1024;  // survivor bitmask of the planning pass: up to 32768 tiles (16.7 M points)
+
 // ---- planning pass of the windowed engine.  One CTA per query block: seeds every query's
 // threshold from its neighbours in the prepared order, derives the block's pruning radius, tests
 // EVERY candidate tile's bounding box against the block's query box and writes the survivors
@@ -256,12 +258,30 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
         for (int d = 1; d < DP; ++d) dist = fmaxf(dist, gap[d]);
         return dist;
     };
+    // (up to PLAN_MASK_WORDS * 32 tiles the first sweep leaves a survivor bitmask in shared memory --
+    // word i = walk positions [32 i, 32 i + 32) -- and the second one only visits the set bits)
+    __shared__ unsigned s_mask[PLAN_MASK_WORDS];
+    const bool masked = n_tiles <= (int64_t)PLAN_MASK_WORDS * 32;
+    const int n_words = (int)((n_tiles + 31) / 32);
     int mine = 0;
-    for (int64_t pos = tid; pos < n_tiles; pos += FAST_THREADS) {
-        int64_t t;
-        mine += !(gap_of(pos, t) > R);
+    if (masked) {
+        for (int wi = warp; wi < n_words; wi += FAST_THREADS / 32) {
+            const int64_t pos = (int64_t)wi * 32 + lane;
+            int64_t t;
+            const bool keep = pos < n_tiles && !(gap_of(pos, t) > R);
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) {
+                s_mask[wi] = ballot;
+                mine += __popc(ballot);
+            }
+        }
+    } else {
+        for (int64_t pos = tid; pos < n_tiles; pos += FAST_THREADS) {
+            int64_t t;
+            mine += !(gap_of(pos, t) > R);
+        }
     }
-    const int total = (int)(block_sum((float)mine, sh) + 0.5f);  // exact: < 2^24 tiles
+    const int total = (int)(block_sum((float)mine, sh) + 0.5f);  // exact: < 2^24 tiles (and publishes s_mask)
     // A block that keeps most of the tiles gets no list at all: plan_first = -1 means "every
     // tile, in walk order" (the warp-level sub-tile culling of the filter kernel still applies).
     // That also bounds the pool: explicit lists are at most half the tiles long.
@@ -282,6 +302,37 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
         return;
     }
     int2* out = plan + base;
+    if (masked) {
+        // thread t owns the words [t W, (t + 1) W): block-wide exclusive scan of their bit counts,
+        // then one (tile, gap) entry per set bit, in walk order
+        const int W = (n_words + FAST_THREADS - 1) / FAST_THREADS;
+        const int w0 = min(tid * W, n_words), w1 = min(w0 + W, n_words);
+        int cnt = 0;
+        for (int wi = w0; wi < w1; ++wi) cnt += __popc(s_mask[wi]);
+        int incl = cnt;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) sh.warp_count[warp] = incl;
+        __syncthreads();
+        int offset = incl - cnt;
+#pragma unroll
+        for (int w = 0; w < FAST_THREADS / 32; ++w)
+            if (w < warp) offset += sh.warp_count[w];
+        for (int wi = w0; wi < w1; ++wi) {
+            unsigned bits = s_mask[wi];
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                int64_t t;
+                const float dist = gap_of((int64_t)wi * 32 + b, t);
+                out[offset++] = make_int2((int)t, __float_as_int(dist));
+            }
+        }
+        if (tid == 0) { plan_count[blockIdx.x] = total; plan_first[blockIdx.x] = total > 0 ? base : 0; }
+        return;
+    }
     int done = 0;
     for (int64_t pos = 0; pos < n_tiles; pos += FAST_THREADS) {
         bool keep = false;

@@ -81,5 +81,6 @@ int launch_count_loo(int d, const CountF32Args& a);                    // all le
 int launch_count_masked(int dim_padded, const CountF32Args& a);        // <= 4 run-time masks
 
 void note_launch();  // launch counter (ksg_launch_count)
+void note_launches(long long delta);  // ... for a replayed launch sequence (CUDA graph)
 
 }  // namespace ksg

@@ -45,6 +45,7 @@ static unsigned long long g_launches = 0;
     } while (0)
 
 void note_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+void note_launches(long long delta) { __atomic_add_fetch(&g_launches, (unsigned long long)delta, __ATOMIC_RELAXED); }
 
 template <typename K>
 static int allow_smem(K kernel, size_t bytes) {

@@ -179,11 +179,16 @@ __device__ __forceinline__ unsigned long long hilbert_index(unsigned int (&X)[CA
 
 // bits per coordinate of the curve for n points in `dim` coordinates (shared by ksg_prepare and
 // ksg_cross_prepare, which must place foreign points on the SAME curve)
+// The curve only has to resolve the points down to a sub-tile: with b = rank_bits - 4 bits per
+// coordinate a rank slice holds <= 16 points, so even when the coordinates are functions of each
+// other (all points of a slice in ONE cell) a cell is smaller than a 32-row sub-tile; everything
+// finer would only lengthen the key sort (one radix pass per 8 bits of dim * b).
 static inline void curve_bits(int64_t n, int dim, int* rank_bits, int* bits) {
     int rb = 1;
     while ((1ll << rb) < n) ++rb;
     int b = 63 / dim;
-    if (b > rb) b = rb;
+    const int need = rb > 5 ? rb - 4 : 1;
+    if (b > need) b = need;
     *rank_bits = rb;
     *bits = b;
 }

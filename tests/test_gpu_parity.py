@@ -607,3 +607,39 @@ def test_rows_in_flight_prepare_equals_resident_prepare(windowed):
     p1, m1 = knn.mutual_information((0,), (1,), 4, a)
     p2, m2 = knn.mutual_information((0,), (1,), 4, pinned)
     assert np.array_equal(p1, p2) and m1 == m2
+
+
+def test_speculative_run_recomputes_when_the_filter_flags_queries(windowed):
+    """MI of two scalar series runs speculatively (counts and psi enqueued behind the k-NN pass,
+    its flag count read with the result).  On tie-heavy data the filter flags queries: the settled
+    result must equal the oracle's pointwise values; on continuous data nothing is flagged and the
+    speculative values stand."""
+    E, knn = windowed
+    rng = np.random.default_rng(12)
+    n = 6000
+    x = rng.standard_normal(n)
+    y = 0.6 * x + 0.8 * rng.standard_normal(n)
+    for rows, expect_escalation in ((np.round(np.vstack([x, y]) * 32) / 32, True), (np.vstack([x, y]), False)):
+        for key in E.stats:
+            E.stats[key] = 0
+        with np.errstate(all="ignore"):
+            ptw, avg = knn.mutual_information((0,), (1,), 4, rows)
+            ref_ptw, ref_avg = orc.mutual_information((0,), (1,), 4, rows)
+        close(ptw, ref_ptw)
+        close(avg, ref_avg)
+        escalated = (E.stats["knn_fallback_queries"] + E.stats["knn_deferred_queries"]
+                     + E.stats["knn_wide_margin_passes"]) > 0
+        assert escalated == expect_escalation
+        # the device-resident entry points (bench.py's step) settle the same way
+        import torch
+
+        from syntropy_b200.knn.shannon import _xy_masks, mi1_program
+
+        pts = E.to_device_points(rows)
+        status = E.Status(pts.device)
+        pw = E.ksg1_device(pts, 4, _xy_masks((0,), (1,)), mi1_program, status=status)
+        assert pw.redo is not None
+        full, total = E.finish_device(pw, n, out=status.total)
+        pw, full, total = E.settle(pw, n, status, full, total)
+        torch.cuda.synchronize()
+        close(full.cpu().numpy(), np.asarray(ref_ptw).reshape(-1))
