@@ -909,6 +909,7 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
 
 // Exact refine: see the file header.  flags[qi] = 1 marks a query for the fp64 fallback.
 constexpr int REFINE_CAP = 96;  // union entries examined per query
+constexpr int REFINE_BATCH = 8;  // list heads / tails fetched together
 
 static __global__ void __launch_bounds__(128)
 knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict__ part_idx, int kcap, int splits,
@@ -956,17 +957,31 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     mq = mq * (1.0 + 1e-6) + 1e-300;
 
     // k'-th smallest fp32 distance over the union of the split lists
+    // (a block in a sparse region can own a hundred work units, most of whose lists hold nothing
+    // below the running k'-th value: the list heads are fetched REFINE_BATCH at a time, so those
+    // lists cost one overlapped load each instead of one dependent L2 round trip each)
     float best[KNN_MAX_KCAP];
     int have = 0;
-    for (int s = s_begin; s < s_end; ++s)
-        for (int r = 0; r < kcap; ++r) {
-            const float v = part_d32[((int64_t)s * kcap + r) * stride + off];
-            if (have == kp && !(v < best[kp - 1])) break;
-            int pos = have < kp ? have : kp - 1;
-            while (pos > 0 && best[pos - 1] > v) { best[pos] = best[pos - 1]; --pos; }
-            best[pos] = v;
-            if (have < kp) ++have;
+    for (int s0 = s_begin; s0 < s_end; s0 += REFINE_BATCH) {
+        float head[REFINE_BATCH];
+#pragma unroll
+        for (int u = 0; u < REFINE_BATCH; ++u)
+            head[u] = s0 + u < s_end ? part_d32[((int64_t)(s0 + u) * kcap) * stride + off] : CUDART_INF_F;
+#pragma unroll
+        for (int u = 0; u < REFINE_BATCH; ++u) {
+            const int s = s0 + u;
+            if (s >= s_end) break;
+            if (have == kp && !(head[u] < best[kp - 1])) continue;  // ascending list: nothing in it counts
+            for (int r = 0; r < kcap; ++r) {
+                const float v = r == 0 ? head[u] : part_d32[((int64_t)s * kcap + r) * stride + off];
+                if (have == kp && !(v < best[kp - 1])) break;
+                int pos = have < kp ? have : kp - 1;
+                while (pos > 0 && best[pos - 1] > v) { best[pos] = best[pos - 1]; --pos; }
+                best[pos] = v;
+                if (have < kp) ++have;
+            }
         }
+    }
     const double r32 = (have == kp) ? (double)best[kp - 1] : CUDART_INF;
     if (!(r32 < CUDART_INF)) {  // fewer than k' points exist (k+1 > n): cKDTree pads with inf
         eps_out[qi] = CUDART_INF;
@@ -981,13 +996,24 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     double exact[KNN_MAX_KCAP];
     int32_t exact_j[KNN_MAX_KCAP], exact_o[KNN_MAX_KCAP];  // prepared position / original index (idx_out only)
     int got = 0, examined = 0;
-    for (int s = s_begin; s < s_end && !overflow; ++s) {
+    for (int s0 = s_begin; s0 < s_end && !overflow; s0 += REFINE_BATCH) {
+      float head[REFINE_BATCH], tails[REFINE_BATCH];
+#pragma unroll
+      for (int u = 0; u < REFINE_BATCH; ++u) {
+          const bool in = s0 + u < s_end;
+          head[u] = in ? part_d32[((int64_t)(s0 + u) * kcap) * stride + off] : CUDART_INF_F;
+          tails[u] = in ? part_d32[((int64_t)(s0 + u) * kcap + (kcap - 1)) * stride + off] : CUDART_INF_F;
+      }
+#pragma unroll
+      for (int u = 0; u < REFINE_BATCH; ++u) {
+        const int s = s0 + u;
+        if (s >= s_end || overflow) break;
         // a full list whose tail is still inside the band may have dropped in-band candidates
-        const float tail = part_d32[((int64_t)s * kcap + (kcap - 1)) * stride + off];
-        if ((double)tail <= T) { overflow = true; break; }
+        if ((double)tails[u] <= T) { overflow = true; break; }
+        if (!((double)head[u] <= T)) continue;  // ascending list: nothing of it is inside the band
         for (int r = 0; r < kcap; ++r) {
             const int64_t o = ((int64_t)s * kcap + r) * stride + off;
-            const float v = part_d32[o];
+            const float v = r == 0 ? head[u] : part_d32[o];
             if (!((double)v <= T)) break;
             if (++examined > REFINE_CAP) { overflow = true; break; }
             const int64_t j = part_idx[o];
@@ -1009,6 +1035,7 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
             }
             if (got < kp) ++got;
         }
+      }
     }
     if (overflow || got < kp) {
         flags[qi] = 1;
