@@ -429,3 +429,66 @@ def cross_sample_entropy(idx_x, idx_y, data, m=2, r=0.2, norm=np.inf):
     if A == 0:
         return np.inf
     return -np.log(A / B)
+
+
+# ------------------------------------------------------------------ syntropy.mixed, knn branch
+# (the caller of differential_entropy per discrete class.  Only
+# ``continuous_estimator="knn"`` is on the path; the Gaussian branch belongs to syntropy.gaussian.)
+def _mixed_classes(discrete_vars):
+    """mixed/shannon.py:53-56,63-65: the distinct columns (np.unique, axis=1: lexicographic
+    order), their probabilities and one boolean mask per class."""
+    discrete_vars = np.asarray(discrete_vars)
+    unq, counts = np.unique(discrete_vars, axis=1, return_counts=True)
+    probs = counts / counts.sum()
+    masks = [np.all(discrete_vars == unq[:, [i]], axis=0) for i in range(unq.shape[1])]
+    return probs, masks
+
+
+def mixed_shannon_entropy(discrete_vars, continuous_vars, k=5):
+    """mixed/shannon.py:7-90 with continuous_estimator="knn": H(X,Y) = H(X) + H(Y|X)."""
+    discrete_vars, continuous_vars = np.asarray(discrete_vars), np.asarray(continuous_vars)
+    assert discrete_vars.shape[1] == continuous_vars.shape[1]
+    probs, masks = _mixed_classes(discrete_vars)
+    avg = -np.sum(probs * np.log(probs))
+    ptw = np.zeros((1, continuous_vars.shape[1]))
+    conditional = 0.0
+    for i, mask in enumerate(masks):
+        ptw[:, mask] -= np.log(probs[i])
+        ptw_c, avg_c = differential_entropy(continuous_vars[:, mask], k=k)
+        ptw[:, mask] += ptw_c
+        conditional += probs[i] * avg_c
+    avg += conditional
+    return ptw, avg
+
+
+def mixed_conditional_entropy(discrete_vars, continuous_vars, conditional="discrete", k=5):
+    """mixed/shannon.py:93-181 with continuous_estimator="knn": joint minus the marginal of the
+    conditioning variable."""
+    discrete_vars, continuous_vars = np.asarray(discrete_vars), np.asarray(continuous_vars)
+    assert discrete_vars.shape[1] == continuous_vars.shape[1]
+    assert conditional in {"discrete", "continuous"}
+    ptw_joint, avg_joint = mixed_shannon_entropy(discrete_vars, continuous_vars, k=k)
+    if conditional == "continuous":
+        ptw_marginal, avg_marginal = differential_entropy(continuous_vars, k)
+    else:
+        probs, masks = _mixed_classes(discrete_vars)
+        ptw_marginal = np.zeros((1, discrete_vars.shape[1]))
+        avg_marginal = -np.sum(probs * np.log(probs))
+        for i, mask in enumerate(masks):
+            ptw_marginal[:, mask] = -np.log(probs[i])
+    return ptw_joint - ptw_marginal, avg_joint - avg_marginal
+
+
+def mixed_mutual_information(discrete_vars, continuous_vars, k=5):
+    """mixed/shannon.py:184-275 with continuous_estimator="knn": I(D;C) = H(C) - H(C|D)."""
+    discrete_vars, continuous_vars = np.asarray(discrete_vars), np.asarray(continuous_vars)
+    assert discrete_vars.shape[1] == continuous_vars.shape[1]
+    ptw, avg = differential_entropy(continuous_vars, k=k)
+    probs, masks = _mixed_classes(discrete_vars)
+    conditional = 0.0
+    for i, mask in enumerate(masks):
+        local_c, avg_c = differential_entropy(continuous_vars[:, mask], k=k)
+        conditional += probs[i] * avg_c
+        ptw[:, mask] -= local_c
+    avg -= conditional
+    return ptw, avg

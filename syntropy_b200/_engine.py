@@ -887,11 +887,10 @@ def ksg2_family(rows, k: int, masks, prog_builder):
     return _finish(Pointwise(psi_epilogue(counts, prog, n), full=True, preps=preps), n, status)
 
 
-def kl_entropy(rows: np.ndarray, k: int):
-    pts = to_device_points(rows)
+def _kl_entropy_device(pts: torch.Tensor, k: int) -> Pointwise:
+    """Kozachenko-Leonenko pointwise entropies of a device-resident (D, n) point set
+    (reference: knn/shannon.py:81-87): radius pass + ``ksg_entropy_epilogue``."""
     dim, n = pts.shape
-    status = Status(pts.device)
-    check_finite(pts, out=status.finite)
     q0, q1 = _dist.my_slice(n)
     prep = None
     if _use_fast(dim, k + 1):
@@ -902,7 +901,58 @@ def kl_entropy(rows: np.ndarray, k: int):
     ptw = torch.empty(q1 - q0, dtype=torch.float64, device=pts.device)
     rc = _cabi.load().ksg_entropy_epilogue(_ptr(eps), q1 - q0, dim, psi_host(k), psi_host(n), _ptr(ptw), _stream())
     _cabi.check(rc, "ksg_entropy_epilogue")
-    return _finish(Pointwise(ptw, prep=prep), n, status)
+    return Pointwise(ptw, prep=prep, preps=[prep] if prep is not None else [])
+
+
+def kl_entropy(rows: np.ndarray, k: int):
+    pts = to_device_points(rows)
+    status = Status(pts.device)
+    check_finite(pts, out=status.finite)
+    return _finish(_kl_entropy_device(pts, k), pts.shape[1], status)
+
+
+def kl_entropy_classes(rows: np.ndarray, order: np.ndarray, bounds, k: int, pooled: bool):
+    """``knn.differential_entropy`` of every class of a partition of the samples of one (D, n)
+    array, and optionally of the pooled sample -- the calling pattern of ``syntropy.mixed`` (one
+    call per discrete class on ``continuous_vars[:, mask]``, reference: mixed/shannon.py:82,162,
+    241,266).  ``order`` (int64[n]) lists the sample indices class after class, ascending inside a
+    class; class g is ``order[bounds[g]:bounds[g + 1]]``.
+
+    The array and ``order`` go to the GPU once; every class is gathered on the device, runs the
+    same prepared-set / k-NN / epilogue pipeline as ``kl_entropy`` and is reduced in a fixed order;
+    the class results are scattered back into sample order on the device; one download at the end.
+
+    Returns ``(by_sample, pooled_ptw, sums)``: ``by_sample[i]`` the pointwise entropy of sample i
+    within its own class, ``pooled_ptw`` the pointwise entropies of the pooled sample (or None),
+    ``sums[g]`` the float64 sum over class g (``sums[-1]``: over the pooled sample, if asked)."""
+    pts = to_device_points(rows)
+    dim, n = pts.shape
+    status = Status(pts.device)
+    check_finite(pts, out=status.finite)
+    n_classes = len(bounds) - 1
+    order_dev = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int64)).to(pts.device)
+    packed = torch.empty(max(n, 1), dtype=torch.float64, device=pts.device)
+    sums = torch.zeros(n_classes + 1, dtype=torch.float64, device=pts.device)
+    for g in range(n_classes):
+        b0, b1 = int(bounds[g]), int(bounds[g + 1])
+        if b1 == b0:
+            continue
+        sub = pts.index_select(1, order_dev[b0:b1])
+        full, _ = finish_device(_kl_entropy_device(sub, k), b1 - b0, out=sums[g:g + 1])
+        packed[b0:b1].copy_(full)
+    by_sample = torch.empty(n, dtype=torch.float64, device=pts.device)
+    if n:
+        by_sample.index_copy_(0, order_dev, packed[:n])
+    pooled_ptw = None
+    if pooled:
+        pooled_ptw, _ = finish_device(_kl_entropy_device(pts, k), n, out=sums[n_classes:n_classes + 1])
+    host_status = status.read_async()
+    sums_host = to_host(sums)
+    by_sample_host = to_host(by_sample) if n else np.empty(0)
+    pooled_host = to_host(pooled_ptw) if pooled_ptw is not None else None
+    if int(host_status[2]) != 0:
+        raise ValueError("data must be finite, check for nan or inf values")
+    return by_sample_host, pooled_host, sums_host
 
 
 class CrossSet:

@@ -88,3 +88,29 @@ CONFIGS = {
     "c4": c4_oinfo,
     "c5": c5_info_rate,
 }
+
+
+def mixed_cases():
+    """Discrete x continuous fixtures for the ``syntropy.mixed`` knn branch:
+    ``name -> (discrete (vars, n) int64, continuous (vars, n) float64, k)``.
+    "shift": balanced binary class, 1-D Gaussian with a class-dependent mean (the generator style of
+    the reference's tests/test_mixed.py); "grid": two discrete variables (3 x 2 states, unbalanced),
+    2-D continuous with class-dependent mean and scale; "small": one class has fewer than k + 1
+    samples (its radii are inf, as cKDTree pads missing neighbours)."""
+    rng = np.random.default_rng(21)
+    cases = {}
+    n = 3000
+    d = rng.integers(0, 2, size=(1, n))
+    c = rng.standard_normal((1, n)) + 1.5 * d
+    cases["shift"] = (d.astype(np.int64), c, 5)
+    n = 2500
+    d = np.vstack([rng.choice(3, size=n, p=[0.5, 0.3, 0.2]), rng.integers(0, 2, size=n)])
+    c = rng.standard_normal((2, n)) * (1.0 + 0.5 * d[1]) + np.vstack([d[0], -d[0]])
+    cases["grid"] = (d.astype(np.int64), c, 3)
+    n = 400
+    d = np.zeros((1, n), dtype=np.int64)
+    d[0, :3] = 7
+    d[0, 3:150] = 2
+    c = rng.standard_normal((3, n)) + 0.1 * d
+    cases["small"] = (d, c, 4)
+    return cases

@@ -52,7 +52,29 @@ def radius_and_counts(utils, data, joint, subspaces, k):
     return out
 
 
+def make_mixed():
+    """tests/golden/mixed_knn.npz: the reference's syntropy.mixed functions with
+    continuous_estimator="knn" on ``workloads.mixed_cases()``."""
+    load_reference_knn()
+    mixed = importlib.import_module("syntropy.mixed.shannon")
+    out = {}
+    with np.errstate(all="ignore"):
+        for name, (d, c, k) in workloads.mixed_cases().items():
+            ptw, avg = mixed.shannon_entropy(d, c, continuous_estimator="knn", k=k)
+            out[f"{name}_h_ptw"], out[f"{name}_h_avg"] = ptw, avg
+            for cond in ("discrete", "continuous"):
+                ptw, avg = mixed.conditional_entropy(d, c, conditional=cond, continuous_estimator="knn", k=k)
+                out[f"{name}_ce_{cond}_ptw"], out[f"{name}_ce_{cond}_avg"] = ptw, avg
+            ptw, avg = mixed.mutual_information(d, c, continuous_estimator="knn", k=k)
+            out[f"{name}_mi_ptw"], out[f"{name}_mi_avg"] = ptw, avg
+    np.savez_compressed(os.path.join(HERE, "mixed_knn.npz"), **out)
+    print("mixed_knn.npz", os.path.getsize(os.path.join(HERE, "mixed_knn.npz")))
+
+
 def main():
+    if "--only-mixed" in sys.argv:
+        make_mixed()
+        return
     knn, utils = load_reference_knn()
     os.makedirs(HERE, exist_ok=True)
 
@@ -172,6 +194,7 @@ def main():
     with np.errstate(all="ignore"):
         np.savez_compressed(os.path.join(HERE, "digamma.npz"), args=args, psi=digamma(args))
 
+    make_mixed()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -643,3 +643,52 @@ def test_speculative_run_recomputes_when_the_filter_flags_queries(windowed):
         pw, full, total = E.settle(pw, n, status, full, total)
         torch.cuda.synchronize()
         close(full.cpu().numpy(), np.asarray(ref_ptw).reshape(-1))
+
+
+# ------------------------------------------------------------------ syntropy.mixed, knn branch
+def test_mixed_knn_branch_vs_reference_golden(E, golden):
+    """shannon_entropy / conditional_entropy / mutual_information with continuous_estimator="knn"
+    against the unmodified reference's outputs (tests/golden/mixed_knn.npz): per-class radii are
+    exact, so the pointwise arrays agree to 1e-12 (psi / log ulps), averages likewise."""
+    from syntropy_b200 import mixed
+
+    g = golden("mixed_knn")
+    with np.errstate(all="ignore"):
+        for name, (d, c, k) in workloads.mixed_cases().items():
+            ptw, avg = mixed.shannon_entropy(d, c, continuous_estimator="knn", k=k)
+            close(ptw, g[f"{name}_h_ptw"]); close(avg, g[f"{name}_h_avg"])
+            for cond in ("discrete", "continuous"):
+                ptw, avg = mixed.conditional_entropy(d, c, conditional=cond, continuous_estimator="knn", k=k)
+                close(ptw, g[f"{name}_ce_{cond}_ptw"]); close(avg, g[f"{name}_ce_{cond}_avg"])
+            ptw, avg = mixed.mutual_information(d, c, continuous_estimator="knn", k=k)
+            assert ptw.shape == (1, d.shape[1])
+            close(ptw, g[f"{name}_mi_ptw"]); close(avg, g[f"{name}_mi_avg"])
+
+
+def test_mixed_knn_properties_at_the_reference_test_size(windowed):
+    """The reference's own statistical checks (tests/test_mixed.py:279-324, n = 50 000, k = 5,
+    tolerance 2e-2): well-separated classes saturate I(D;C) at ln 2, independent C gives 0, the
+    pointwise mean equals the average; plus the chain rule H(D,C) = H(D) + H(C|D) exactly."""
+    from syntropy_b200 import mixed
+
+    rng = np.random.default_rng(0)
+    n = 50_000
+    d = rng.integers(0, 2, size=(1, n))
+    c = rng.standard_normal((1, n)) + 5.0 * d
+    ptw, mi = mixed.mutual_information(d, c, continuous_estimator="knn", k=5)
+    assert mi == pytest.approx(np.log(2.0), abs=2e-2)
+    assert ptw.mean() == pytest.approx(mi, abs=1e-9)
+    c_ind = rng.standard_normal((1, n))
+    assert mixed.mutual_information(d, c_ind, continuous_estimator="knn", k=5)[1] == pytest.approx(0.0, abs=2e-2)
+    _, joint = mixed.shannon_entropy(d, c, continuous_estimator="knn", k=5)
+    _, h_c_given_d = mixed.conditional_entropy(d, c, conditional="discrete", continuous_estimator="knn", k=5)
+    p = np.bincount(d[0]) / n
+    assert joint == pytest.approx(-(p * np.log(p)).sum() + h_c_given_d, abs=1e-12)
+    # the per-class calls are knn.differential_entropy on the class's columns
+    from syntropy_b200 import knn
+
+    ptw_h, _ = mixed.shannon_entropy(d, c, continuous_estimator="knn", k=5)
+    for state in (0, 1):
+        mask = d[0] == state
+        ptw_c, _ = knn.differential_entropy(c[:, mask], k=5)
+        assert np.array_equal(ptw_h[0, mask], (0.0 - np.log(p[state])) + ptw_c[0])

@@ -131,3 +131,45 @@ def test_int32_counts_gather_like_float64_slices():
         assert dist.gather_slices(v, 10) is v and dist.my_slice(10) == (0, 10)
     finally:
         dist.configure("auto")
+
+
+def test_mixed_class_partition_equals_the_reference_masks():
+    """syntropy_b200.mixed groups samples by a counted mixed-radix key (or np.unique's inverse); the
+    reference builds one boolean mask per distinct column (mixed/shannon.py:53-65): same classes,
+    same order, same members -- for small-range integers (fast path), negative values, several
+    discrete variables, wide-range integers and floats (general path)."""
+    from syntropy_b200 import workloads
+    from syntropy_b200.mixed.shannon import _classes
+
+    rng = np.random.default_rng(8)
+    cases = {name: d for name, (d, _, _) in workloads.mixed_cases().items()}
+    cases["negative"] = rng.integers(-3, 2, size=(2, 500))
+    cases["three vars, int8"] = rng.integers(0, 3, size=(3, 700)).astype(np.int8)
+    cases["bool"] = rng.integers(0, 2, size=(2, 300)).astype(bool)
+    cases["wide range"] = rng.choice(np.array([-2**40, 5, 2**50]), size=(2, 400))
+    cases["float labels"] = rng.choice(np.array([0.5, 1.5, -2.0]), size=(1, 300))
+    cases["one class"] = np.full((1, 50), 3)
+    for name, d in cases.items():
+        probs, class_id, order, bounds = _classes(d)
+        unq, counts = np.unique(d, axis=1, return_counts=True)
+        assert np.array_equal(probs, counts / counts.sum()), name
+        assert bounds.shape[0] == unq.shape[1] + 1 and bounds[-1] == d.shape[1]
+        for i in range(unq.shape[1]):
+            mask = np.all(d == unq[:, [i]], axis=0)
+            assert np.array_equal(order[bounds[i]:bounds[i + 1]], np.flatnonzero(mask)), (name, i)
+            assert np.all(class_id[mask] == i), (name, i)
+
+
+def test_mixed_rejects_what_it_does_not_implement():
+    from syntropy_b200 import mixed
+
+    d = np.zeros((1, 10), dtype=np.int64)
+    c = np.zeros((1, 10))
+    with pytest.raises(NotImplementedError):
+        mixed.mutual_information(d, c)  # default estimator is the Gaussian plug-in
+    with pytest.raises(AssertionError):
+        mixed.shannon_entropy(d, c, continuous_estimator="kde")
+    with pytest.raises(AssertionError):
+        mixed.conditional_entropy(d, c[:, :5], continuous_estimator="knn")
+    with pytest.raises(AssertionError):
+        mixed.conditional_entropy(d, c, conditional="both", continuous_estimator="knn")
