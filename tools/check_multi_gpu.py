@@ -36,6 +36,13 @@ def main():
     cases.append(("mi 4D;4D (own-order marginals)", lambda: knn.mutual_information(
         c5["idxs_x"], c5["idxs_y"], c5["k"], d5)))
     cases.append(("entropy 3D", lambda: knn.differential_entropy(d4, 3, idxs=(0, 1, 2))))
+    from syntropy_b200 import mixed
+
+    rng = np.random.default_rng(6)
+    dm = rng.integers(0, 3, size=(1, 30_011))
+    cm = rng.standard_normal((2, 30_011)) * (1.0 + 0.3 * dm) + dm
+    cases.append(("mixed mi, 3 classes (per-class entropies)", lambda: mixed.mutual_information(dm, cm, "knn", 4)))
+    cases.append(("mixed H(D|C)", lambda: mixed.conditional_entropy(dm, cm, "continuous", "knn", 4)))
     series = workloads.c5_series(n=6_000, seed=5)
     ok = True
     for name, fn in cases:
