@@ -473,7 +473,9 @@ KNN_WIDE_MARGIN = 24    # second pass for tie-saturated (quantised) data
 
 
 def _lists_fit(dim: int, kcap: int) -> bool:
-    """Do neighbour lists of kcap entries fit in shared memory beside the candidate ring?"""
+    """Do neighbour lists of kcap entries fit in shared memory beside the candidate ring?
+    (Geometry of the dense filter kernel -- 4 / 2 queries per thread -- which also serves the
+    windowed engine's deferred queries; the windowed kernels, one query per thread, need less.)"""
     dp = (dim + 1) & ~1
     queries_per_block = 128 * (4 if dp <= 4 else 2)
     stages = 3 if dp <= 4 else 2

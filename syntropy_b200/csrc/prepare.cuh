@@ -1,9 +1,11 @@
 // Prepared point set: everything the fast (fp32-filtered, exact) kernels need, built
 // once per estimator call on the device.
 //
-//   * the points sorted by one "primary" coordinate (radix sort) -- neighbouring
-//     queries then see neighbouring candidates, which keeps the k-NN thresholds tight
-//     from the first tile on and makes window pruning possible;
+//   * the points in a space-filling order -- the Hilbert curve over the per-coordinate ranks
+//     (primary = -1), the leaf order of a balanced kd-tree (primary = -2) or one coordinate's
+//     sorted order (primary >= 0): neighbouring queries then see neighbouring candidates, which
+//     keeps the k-NN thresholds tight from the first tile on and gives 512-row tiles and 32-row
+//     sub-tiles tight bounding boxes (the windowed engine's pruning);
 //   * an fp32 AoS shadow copy, centred per dimension so that its rounding error is
 //     2^-24 * |x - centre| instead of 2^-24 * |x|, padded with +inf rows to a whole
 //     number of tiles (padded candidates can never be a neighbour or be counted);
