@@ -324,7 +324,8 @@ def run_b200_arm(args):
     # warm-up (also builds the psi table and pays first-launch costs)
     for _ in range(max(args.warmup, 3)):
         device_step()
-    e2e_step()
+    for _ in range(max(args.warmup, 3)):  # (the second call with the same buffers captures the prepare graphs)
+        e2e_step()
     barrier()
 
     try:
