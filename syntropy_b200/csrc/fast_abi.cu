@@ -384,74 +384,74 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     if (primary == -1) P.curve_keys = (uint64_t*)(base + L.off_mkeys_out);
     // everything behind the coordinate sorts, as one cached launch sequence
     auto tail = [&](cudaStream_t st) -> int {
-    // centre of the fp32 copy = per-coordinate MEDIAN (the bulk of the points then has small centred
-    // magnitudes, hence small fp32 error bands, even when outliers stretch the range); the ends of
-    // the sorted arrays also tell whether the input held a NaN or an infinity (flags[0])
-    center_median_kernel<<<1, KSG_MAX_DIM, 0, st>>>(P.axis_vals, L.ld, n, dim, P.center, P.maxabs, P.flags);
-    KSG_LAUNCHED2();
-    if (primary >= 0) {
-        // order = one coordinate's sorted order
-        KSG_CUDA_TRY(cudaMemcpyAsync(P.perm, P.axis_pos + (int64_t)primary * L.ld, (size_t)n * 4,
-                                     cudaMemcpyDeviceToDevice, st));
-    } else if (primary == -2) {
-        // order = leaves of a balanced kd-tree over the per-coordinate ranks (see kd_key_kernel)
-        int32_t* ranks = (int32_t*)(base + L.off_ranks);
-        unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
-        unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
-        rank_scatter_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, ranks);
+        // centre of the fp32 copy = per-coordinate MEDIAN (the bulk of the points then has small centred
+        // magnitudes, hence small fp32 error bands, even when outliers stretch the range); the ends of
+        // the sorted arrays also tell whether the input held a NaN or an infinity (flags[0])
+        center_median_kernel<<<1, KSG_MAX_DIM, 0, st>>>(P.axis_vals, L.ld, n, dim, P.center, P.maxabs, P.flags);
         KSG_LAUNCHED2();
-        const int64_t n_groups = ceil_div(n, FAST_SUB);
-        int levels = 0;
-        while ((1ll << levels) < n_groups) ++levels;
-        int32_t* pa = iota;    // holds 0..n-1: the identity order
-        int32_t* pb = P.perm;
-        for (int level = 0; level < levels; ++level) {
-            kd_key_kernel<<<nb, 256, 0, st>>>(pa, ranks + (int64_t)(level % dim) * L.ld, n, level, n_groups, mkeys);
+        if (primary >= 0) {
+            // order = one coordinate's sorted order
+            KSG_CUDA_TRY(cudaMemcpyAsync(P.perm, P.axis_pos + (int64_t)primary * L.ld, (size_t)n * 4,
+                                         cudaMemcpyDeviceToDevice, st));
+        } else if (primary == -2) {
+            // order = leaves of a balanced kd-tree over the per-coordinate ranks (see kd_key_kernel)
+            int32_t* ranks = (int32_t*)(base + L.off_ranks);
+            unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
+            unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
+            rank_scatter_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, ranks);
+            KSG_LAUNCHED2();
+            const int64_t n_groups = ceil_div(n, FAST_SUB);
+            int levels = 0;
+            while ((1ll << levels) < n_groups) ++levels;
+            int32_t* pa = iota;    // holds 0..n-1: the identity order
+            int32_t* pb = P.perm;
+            for (int level = 0; level < levels; ++level) {
+                kd_key_kernel<<<nb, 256, 0, st>>>(pa, ranks + (int64_t)(level % dim) * L.ld, n, level, n_groups, mkeys);
+                KSG_LAUNCHED2();
+                size_t need = L.cub_bytes;
+                cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, pa, pb, (int)n, 0,
+                                                                32 + level, st);
+                if (e != cudaSuccess) { set_error("cub SortPairs (kd): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+                note_launch();
+                int32_t* t = pa; pa = pb; pb = t;
+            }
+            if (pa != P.perm)
+                KSG_CUDA_TRY(cudaMemcpyAsync(P.perm, pa, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        } else {
+            // order = Hilbert curve over the per-coordinate ranks
+            int32_t* ranks = (int32_t*)(base + L.off_ranks);
+            unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
+            unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
+            rank_scatter_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, ranks);
+            KSG_LAUNCHED2();
+            int rank_bits, bits;
+            curve_bits(n, dim, &rank_bits, &bits);
+            switch (dim) {
+#define KSG_MORTON(D) case D: morton_key_kernel<D><<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys); break;
+                KSG_MORTON(1) KSG_MORTON(2) KSG_MORTON(3) KSG_MORTON(4) KSG_MORTON(5) KSG_MORTON(6) KSG_MORTON(7) KSG_MORTON(8)
+#undef KSG_MORTON
+                default: morton_key_kernel<0><<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys);
+            }
             KSG_LAUNCHED2();
             size_t need = L.cub_bytes;
-            cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, pa, pb, (int)n, 0,
-                                                            32 + level, st);
-            if (e != cudaSuccess) { set_error("cub SortPairs (kd): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+            cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, iota, P.perm, (int)n, 0,
+                                                            bits * dim, st);
+            if (e != cudaSuccess) { set_error("cub SortPairs (morton): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
             note_launch();
-            int32_t* t = pa; pa = pb; pb = t;
         }
-        if (pa != P.perm)
-            KSG_CUDA_TRY(cudaMemcpyAsync(P.perm, pa, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-    } else {
-        // order = Hilbert curve over the per-coordinate ranks
-        int32_t* ranks = (int32_t*)(base + L.off_ranks);
-        unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
-        unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
-        rank_scatter_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, ranks);
+        gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
+            d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
         KSG_LAUNCHED2();
-        int rank_bits, bits;
-        curve_bits(n, dim, &rank_bits, &bits);
-        switch (dim) {
-#define KSG_MORTON(D) case D: morton_key_kernel<D><<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys); break;
-            KSG_MORTON(1) KSG_MORTON(2) KSG_MORTON(3) KSG_MORTON(4) KSG_MORTON(5) KSG_MORTON(6) KSG_MORTON(7) KSG_MORTON(8)
-#undef KSG_MORTON
-            default: morton_key_kernel<0><<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys);
-        }
+        // axis_pos: original sample index -> position in the final order
+        int32_t* invperm = (int32_t*)(base + L.off_invperm);
+        invert_perm_kernel<<<nb, 256, 0, st>>>(P.perm, n, invperm);
         KSG_LAUNCHED2();
-        size_t need = L.cub_bytes;
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, iota, P.perm, (int)n, 0,
-                                                        bits * dim, st);
-        if (e != cudaSuccess) { set_error("cub SortPairs (morton): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
-        note_launch();
-    }
-    gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
-        d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
-    KSG_LAUNCHED2();
-    // axis_pos: original sample index -> position in the final order
-    int32_t* invperm = (int32_t*)(base + L.off_invperm);
-    invert_perm_kernel<<<nb, 256, 0, st>>>(P.perm, n, invperm);
-    KSG_LAUNCHED2();
-    remap_axis_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, invperm);
-    KSG_LAUNCHED2();
-    tile_box_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 128, 0, st>>>(P.shadow_f32, L.dim_padded, P.tile_box,
-                                                                         P.sub_box);
-    KSG_LAUNCHED2();
-    return KSG_OK;
+        remap_axis_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, invperm);
+        KSG_LAUNCHED2();
+        tile_box_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 128, 0, st>>>(P.shadow_f32, L.dim_padded, P.tile_box,
+                                                                             P.sub_box);
+        KSG_LAUNCHED2();
+        return KSG_OK;
     };
     rc = graph_cache().run(graph_key(GRAPH_PREPARE_TAIL, {d_points, d_buffer}, {n, ld}, {dim, primary}), st, tail);
     if (rc) return rc;
