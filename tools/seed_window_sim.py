@@ -75,10 +75,15 @@ def run(name, data, k, n):
         r = np.array(ratios)
         print(f"  W={W:4d}: median seed/true = {np.median(r):.3f}, mean volume factor (ratio^dim) = {np.mean(r**dim):.1f}, median {np.median(r**dim):.1f}")
 
-n = 200_000
-d3, c3 = workloads.c3_cmi(n=n, seed=0)
-run("C3 joint 6-D", d3, c3["k"], n)
-d5, c5 = workloads.c5_info_rate(n=n, seed=0)
-run("C5 joint 8-D", d5, c5["k"], n)
-d2, c2 = workloads.c2_mi_1m(n=n, seed=0)
-run("C2 joint 2-D", d2, c2["k"], n)
+def main():
+    n = 200_000
+    d3, c3 = workloads.c3_cmi(n=n, seed=0)
+    run("C3 joint 6-D", d3, c3["k"], n)
+    d5, c5 = workloads.c5_info_rate(n=n, seed=0)
+    run("C5 joint 8-D", d5, c5["k"], n)
+    d2, c2 = workloads.c2_mi_1m(n=n, seed=0)
+    run("C2 joint 2-D", d2, c2["k"], n)
+
+
+if __name__ == "__main__":
+    main()
