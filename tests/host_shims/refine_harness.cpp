@@ -1,0 +1,140 @@
+// Host-side harness for knn_refine_kernel (tests/test_refine_host.py): the kernel's CUDA source is
+// plain C++ apart from a few keywords, so it is compiled here for the CPU -- one call per "thread" --
+// and checked against brute force in float64.  The filter's partial lists are emulated: the
+// candidate set is cut into disjoint chunks (work units / splits), every chunk keeps the kcap
+// smallest fp32 distances to the query, ascending, exactly what the filter kernels emit.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
+#include <random>
+#include <vector>
+#define __global__
+#define __device__
+#define __host__
+#define __restrict__
+#define __launch_bounds__(x)
+#define __forceinline__ inline
+#define CUDART_INF (std::numeric_limits<double>::infinity())
+#define CUDART_INF_F (std::numeric_limits<float>::infinity())
+#define CUDART_NAN (std::numeric_limits<double>::quiet_NaN())
+struct Dim3 { unsigned x; };
+static Dim3 blockIdx{0}, blockDim{128}, threadIdx{0};
+static inline int atomicAdd(int32_t* p, int v) { int o = *p; *p += v; return o; }
+using std::fabs;
+using std::fmax;
+constexpr int KSG_MAX_DIM = 16;
+constexpr int KNN_MAX_KCAP = 64;
+#include "refine_kernel.inc"  // band_query_f64 + constants + knn_refine_kernel, cut out of csrc/fast_knn.cuh
+
+int main(int argc, char** argv) {
+    const int trials = argc > 1 ? atoi(argv[1]) : 400;
+    std::mt19937_64 rng(2024);
+    long checked = 0, wrong = 0, flagged_continuous = 0, flagged_tied = 0, decided_tied = 0;
+    for (int trial = 0; trial < trials; ++trial) {
+        const int dim = 1 + (int)(rng() % 8);
+        const int kp = 1 + (int)(rng() % 10);
+        const int kcap = kp + ((rng() % 4 == 0) ? 24 : 3);
+        const int qb = 128;
+        const int64_t n = 600 + (int64_t)(rng() % 900);
+        const int64_t nq = std::min<int64_t>(n, 128 + (int64_t)(rng() % 200));
+        const bool windowed = rng() % 3 != 0;
+        const bool want_idx = rng() % 2 == 0;
+        const bool tied = rng() % 4 == 0;  // quantised coordinates: exact ties, saturated lists
+        std::vector<double> pts((size_t)dim * n), center(dim);
+        std::normal_distribution<double> nd(0.0, 1.0);
+        for (int d = 0; d < dim; ++d) {
+            const double shift = (rng() % 3 == 0) ? 1e3 : 0.0;  // off-centre data: the band must use centred magnitudes
+            center[d] = shift;
+            for (int64_t i = 0; i < n; ++i) {
+                double v = nd(rng);
+                if (tied) v = std::round(v * 4) / 4;
+                pts[(size_t)d * n + i] = v + shift;
+            }
+        }
+        std::vector<int32_t> perm(n);
+        for (int64_t i = 0; i < n; ++i) perm[i] = (int32_t)i;
+        std::shuffle(perm.begin(), perm.end(), rng);
+        const int nblocks = (int)((nq + qb - 1) / qb);
+        // chunks of the candidate set per query block (windowed) or for everybody (dense)
+        std::vector<int32_t> unit_first(nblocks + 1, 0);
+        const int splits = 1 + (int)(rng() % 6);
+        int total_units = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            unit_first[b] = total_units;
+            total_units += 1 + (int)(rng() % 4 == 0 ? rng() % 30 : rng() % 3);
+        }
+        unit_first[nblocks] = total_units;
+        const int n_lists = windowed ? total_units : splits;
+        const int64_t stride = windowed ? qb : nq;
+        std::vector<float> d32((size_t)n_lists * kcap * stride, CUDART_INF_F);
+        std::vector<int32_t> idx((size_t)n_lists * kcap * stride, -1);
+        auto dist64 = [&](int64_t a, int64_t b) {
+            double m = 0.0;
+            for (int d = 0; d < dim; ++d) m = fmax(m, fabs(pts[(size_t)d * n + a] - pts[(size_t)d * n + b]));
+            return m;
+        };
+        auto dist32 = [&](int64_t a, int64_t b) {  // the filter's arithmetic: centred fp32 rows
+            float m = 0.0f;
+            for (int d = 0; d < dim; ++d) {
+                const float x = (float)(pts[(size_t)d * n + a] - center[d]), y = (float)(pts[(size_t)d * n + b] - center[d]);
+                m = std::max(m, std::fabs(x - y));
+            }
+            return m;
+        };
+        for (int64_t qi = 0; qi < nq; ++qi) {
+            int s_begin = 0, s_end = splits;
+            int64_t off = qi;
+            if (windowed) { const int64_t b = qi / qb; s_begin = unit_first[b]; s_end = unit_first[b + 1]; off = qi - b * qb; }
+            const int ns = s_end - s_begin;
+            std::vector<std::vector<std::pair<float, int32_t>>> chunk(ns);
+            for (int64_t j = 0; j < n; ++j) chunk[(size_t)((j * 2654435761ull + qi) % ns)].push_back({dist32(qi, j), (int32_t)j});
+            for (int s = 0; s < ns; ++s) {
+                std::sort(chunk[s].begin(), chunk[s].end());
+                for (int r = 0; r < kcap && r < (int)chunk[s].size(); ++r) {
+                    d32[((size_t)(s_begin + s) * kcap + r) * stride + off] = chunk[s][r].first;
+                    idx[((size_t)(s_begin + s) * kcap + r) * stride + off] = chunk[s][r].second;
+                }
+            }
+        }
+        std::vector<double> eps(nq, -7.0);
+        std::vector<int32_t> flags(nq, -7);
+        std::vector<int64_t> nbr((size_t)nq * kp, -7);
+        int32_t n_flagged = 0;
+        for (int64_t qi = 0; qi < nq; ++qi) {
+            blockIdx.x = (unsigned)(qi / 128);
+            threadIdx.x = (unsigned)(qi % 128);
+            knn_refine_kernel(d32.data(), idx.data(), kcap, splits, kp, pts.data(), n, dim, n, 0, nq, nullptr, nullptr,
+                              nullptr, windowed ? unit_first.data() : nullptr, qb, perm.data(),
+                              want_idx ? nbr.data() : nullptr, nullptr, 0, center.data(), eps.data(), flags.data(), &n_flagged);
+        }
+        int counted = 0;
+        for (int64_t qi = 0; qi < nq; ++qi) {
+            if (flags[qi] != 0) {
+                ++counted;
+                (tied ? flagged_tied : flagged_continuous)++;
+                continue;
+            }
+            if (tied) ++decided_tied;
+            ++checked;
+            std::vector<std::pair<double, int32_t>> all(n);  // (exact distance, original index) of every point
+            std::vector<int64_t> pos(n);
+            for (int64_t j = 0; j < n; ++j) all[j] = {dist64(qi, j), perm[j]};
+            std::vector<int64_t> order(n);
+            for (int64_t j = 0; j < n; ++j) order[j] = j;
+            std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return all[a] < all[b]; });
+            bool ok = eps[qi] == all[order[kp - 1]].first;
+            if (ok && want_idx)
+                for (int r = 0; r < kp; ++r) ok = ok && nbr[(size_t)qi * kp + r] == order[r];
+            if (!ok && ++wrong < 10)
+                printf("WRONG trial %d qi %ld: eps %.17g want %.17g (dim %d kp %d kcap %d windowed %d tied %d)\n", trial,
+                       (long)qi, eps[qi], all[order[kp - 1]].first, dim, kp, kcap, (int)windowed, (int)tied);
+        }
+        if (counted != n_flagged) { ++wrong; printf("WRONG trial %d: n_flagged %d, flags say %d\n", trial, n_flagged, counted); }
+    }
+    printf("checked %ld wrong %ld flagged_continuous %ld flagged_tied %ld decided_tied %ld\n", checked, wrong,
+           flagged_continuous, flagged_tied, decided_tied);
+    return wrong ? 1 : 0;
+}
