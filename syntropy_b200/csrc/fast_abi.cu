@@ -263,6 +263,36 @@ static int sort_pairs(void* cub_tmp, size_t cub_bytes, const double* keys_in, do
     return KSG_OK;
 }
 
+// Experiment switches of the windowed k-NN stage (read once): KSG_B200_TIGHT_SEED=0 restores the
+// legacy kcap-th-distance seeds, KSG_B200_FUSED_REFINE=0 the separate refine launch for every block.
+static bool env_flag(const char* name, bool dflt) {
+    const char* e = getenv(name);
+    return e && e[0] ? e[0] != '0' : dflt;
+}
+static bool tight_seeds() { static const bool v = env_flag("KSG_B200_TIGHT_SEED", true); return v; }
+static bool fused_refine() { static const bool v = env_flag("KSG_B200_FUSED_REFINE", true); return v; }
+
+static void fill_refine_args(KnnF32Args& a, const ksg_prepared* P, int kprime, const double* qsorted, int64_t qld,
+                             int64_t* d_idx_out, double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged) {
+    // the window excludes the query itself when it is a member of the candidate set: the (k' - 1)-th
+    // smallest distance to the OTHER rows bounds the k'-th smallest with self (0) included
+    const int kseed = qsorted ? kprime : (kprime > 1 ? kprime - 1 : 1);
+    a.kseed = tight_seeds() && kseed < a.kcap ? kseed : a.kcap;
+    a.ra.fused = fused_refine() ? 1 : 0;
+    a.ra.kp = kprime;
+    a.ra.dim = P->dim;
+    a.ra.sorted = P->sorted_f64;
+    a.ra.ld = P->ld;
+    a.ra.qsorted = qsorted;
+    a.ra.qld = qld;
+    a.ra.center = P->center;
+    a.ra.perm = P->perm;
+    a.ra.idx_out = d_idx_out;
+    a.ra.eps_out = d_eps_out;
+    a.ra.flags = d_flags;
+    a.ra.n_flagged = d_n_flagged;
+}
+
 struct FastKnnPlan {
     int kcap, splits, qb;
     int64_t qblocks, max_units, plan_capacity;
@@ -518,6 +548,7 @@ int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, c
     a.st = st;
     a.seed_thr = nullptr; a.plan = nullptr; a.plan_count = nullptr; a.plan_first = nullptr; a.plan_capacity = 0;
     a.unit_first = nullptr; a.unit_block = nullptr; a.unit_meta = nullptr; a.max_units = 0;
+    fill_refine_args(a, P, kprime, nullptr, 0, d_idx_out, d_eps_out, d_flags, d_n_flagged);
     int rc;
     if (a.windowed) {
         // planning pass (seeds, deferrals, per-block tile lists) -> unit table -> persistent filter
@@ -542,7 +573,8 @@ int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, c
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    d_query_index, P->maxabs, a.seed_thr, a.unit_first,
                                                                    p.qb, P->perm, d_idx_out, nullptr, 0, P->center,
-                                                                   d_eps_out, d_flags, d_n_flagged);
+                                                                   d_eps_out, d_flags, d_n_flagged,
+                                                                   a.windowed && a.ra.fused);
     KSG_LAUNCHED2();
     return KSG_OK;
 }
@@ -671,6 +703,7 @@ int ksg_fast_knn_cross(const ksg_prepared* P, const ksg_cross* X, int64_t q_begi
     a.unit_block = (int32_t*)w;                  w += p.ublock_bytes;
     a.unit_meta = (int32_t*)w;
     a.max_units = p.max_units;
+    fill_refine_args(a, P, kprime, X->sorted_f64, X->ld, nullptr, d_eps_out, d_flags, d_n_flagged);
     int rc = launch_knn_plan(P->dim_padded, a);
     if (rc) return rc;
     rc = launch_knn_units(P->dim_padded, a);
@@ -679,7 +712,7 @@ int ksg_fast_knn_cross(const ksg_prepared* P, const ksg_cross* X, int64_t q_begi
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    nullptr, X->maxabs, a.seed_thr, a.unit_first, p.qb,
                                                                    P->perm, nullptr, X->sorted_f64, X->ld, P->center,
-                                                                   d_eps_out, d_flags, d_n_flagged);
+                                                                   d_eps_out, d_flags, d_n_flagged, a.ra.fused);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

@@ -43,14 +43,14 @@ template <int DP, int KC>
 static int launch_plan_kc(const KnnF32Args& a) {
     constexpr int Q = UnitsQ<DP>::Q;
     auto kern = knn_plan_kernel<DP, Q, KC>;
-    const size_t smem = KC > 0 ? 0 : (size_t)a.kcap * FAST_THREADS * Q * 4;
+    const size_t smem = KC > 0 ? 0 : (size_t)a.kseed * FAST_THREADS * Q * 4;
     if (smem > 32 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     }
     if (cudaMemsetAsync(a.unit_meta, 0, 32, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
     kern<<<(unsigned)ceil_div(a.nq, FAST_THREADS * Q), FAST_THREADS, smem, a.st>>>(
-        a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.maxabs, a.dim, a.qshadow, a.qhome, a.seed_thr, (int2*)a.plan,
+        a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.kseed, a.maxabs, a.dim, a.qshadow, a.qhome, a.seed_thr, (int2*)a.plan,
         a.plan_capacity, a.plan_count, a.plan_first, a.unit_meta);
     note_launch();
     cudaError_t e = cudaGetLastError();
@@ -81,7 +81,7 @@ static int launch_units_dp(const KnnF32Args& a) {
     if (grid > a.max_units) grid = a.max_units;
     kern<<<(unsigned)grid, UNITS_THREADS, smem, a.st>>>(a.shadow, a.sub_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.qshadow, a.qhome, a.seed_thr,
                                                        (const int2*)a.plan, a.plan_count, a.plan_first, a.unit_first, a.unit_block,
-                                                       a.unit_meta, a.part_d32, a.part_idx, a.tile_counter);
+                                                       a.unit_meta, a.part_d32, a.part_idx, a.tile_counter, a.ra);
     note_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_units_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
@@ -90,10 +90,11 @@ static int launch_units_dp(const KnnF32Args& a) {
 
 template <int DP>
 static int launch_plan_dp(const KnnF32Args& a) {
-    if (a.kcap <= 6) return launch_plan_kc<DP, 6>(a);
-    if (a.kcap <= 8) return launch_plan_kc<DP, 8>(a);
-    if (a.kcap <= 10) return launch_plan_kc<DP, 10>(a);
-    if (a.kcap <= 12) return launch_plan_kc<DP, 12>(a);
+    // (the register-resident seed network holds kseed entries)
+    if (a.kseed <= 6) return launch_plan_kc<DP, 6>(a);
+    if (a.kseed <= 8) return launch_plan_kc<DP, 8>(a);
+    if (a.kseed <= 10) return launch_plan_kc<DP, 10>(a);
+    if (a.kseed <= 12) return launch_plan_kc<DP, 12>(a);
     return launch_plan_kc<DP, 0>(a);
 }
 

@@ -28,6 +28,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "fast_launch.h"
 #include "prepare.cuh"
 #include "tile_queue.cuh"
 
@@ -53,6 +54,17 @@ constexpr int KNN_UNIT_FACTOR = 2;      // chunk grows so that #units <= (1 + FA
 // the range by orders of magnitude (heavy-tailed data).
 __host__ __device__ inline double band_query_f64(double mq, double d) {
     return 5.9604644775390625e-08 * (2.0 * mq + 2.0 * d) * 1.01 + 1e-37;
+}
+
+// Tight seed of the windowed filter: s = the k'-th smallest fp32 distance of the seed window (an upper
+// bound of the final r32), mq = max_d |q~_d| of the fp32 row.  The refine examines every candidate
+// with d32 <= T = r32 + 2 * band_query_f64(mq64, 2 * r32) = r32 + 2^-23 (2 mq64 + 4 r32) * 1.01 (+2e-37),
+// mq64 <= mq (1 + 2e-6).  The value returned here exceeds that for every r32 <= s (factor 1.024
+// against 1.01, every operation rounded up), so "inserted iff d32 < seed" captures them all; the
+// refine still verifies T < seed and flags the query otherwise.
+__device__ __forceinline__ float tight_seed(float s, float mq) {
+    const float w = __fmul_ru(1.2207031e-07f, __fadd_ru(__fadd_ru(mq, mq), __fmul_ru(4.0f, s)));  // 1.024 * 2^-23 (2 mq + 4 s)
+    return __fadd_ru(s, __fadd_ru(w, 1e-36f));  // inf stays inf
 }
 
 // ---- packed helpers
@@ -119,10 +131,16 @@ constexpr int PLAN_MASK_WORDS = 1024;  // survivor bitmask of the planning pass:
 template <int DP, int Q, int KC>  // KC > 0: seed lists of KC entries in registers (kcap <= KC); 0: in shared memory
 static __global__ void __launch_bounds__(FAST_THREADS)
 knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
-                int64_t q_begin, int64_t nq, int kcap, const double* __restrict__ maxabs, int dim,
+                int64_t q_begin, int64_t nq, int kcap, int kseed, const double* __restrict__ maxabs, int dim,
                 const float* __restrict__ qshadow, const int32_t* __restrict__ qhome,
                 float* __restrict__ seed_thr, int2* __restrict__ plan, int64_t plan_capacity,
                 int32_t* __restrict__ plan_count, int32_t* __restrict__ plan_first, int32_t* __restrict__ meta) {
+    // kseed: rank of the seed distance.  kseed == kcap (legacy): the seed is the kcap-th smallest
+    // distance of the window, one ulp up -- the window's own rows fill the list.  kseed == k' <
+    // kcap (tight): the seed is the k'-th smallest window distance s plus the width of the refine
+    // kernel's error band at s (tight_seed below), so the filter keeps exactly the candidates the
+    // refine needs -- ~k' insertions per query instead of ~kcap-and-replacements, and a block
+    // radius that is the k'-th, not the kcap-th, neighbour distance.
     // qshadow / qhome (optional, cross-set search): the queries are rows [q_begin, q_begin + nq) of
     // qshadow -- foreign points in the candidate set's centred frame, ordered along the candidates'
     // curve -- and qhome[row] is the candidate row next to each of them on the curve: the seeds come
@@ -177,10 +195,10 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
                 }
 #pragma unroll
             for (int r = 0; r < KC; ++r)
-                if (r == kcap - 1) thr = dl[r];
+                if (r == kseed - 1) thr = dl[r];
         } else {
             const int col = j * FAST_THREADS + tid;
-            for (int r = 0; r < kcap; ++r) lst_d[(size_t)r * QB + col] = CUDART_INF_F;
+            for (int r = 0; r < kseed; ++r) lst_d[(size_t)r * QB + col] = CUDART_INF_F;
 #pragma unroll 1
             for (int off = 1; off <= KNN_SEED_W; ++off)
 #pragma unroll 1
@@ -191,15 +209,21 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
                     load_row<DP>(shadow + r2 * DP, cc);
                     const float m = cheb32<DP>(q, cc);
                     if (m < thr) {
-                        int r = kcap - 1;
+                        int r = kseed - 1;
                         while (r > 0 && lst_d[(size_t)(r - 1) * QB + col] > m) {
                             lst_d[(size_t)r * QB + col] = lst_d[(size_t)(r - 1) * QB + col];
                             --r;
                         }
                         lst_d[(size_t)r * QB + col] = m;
-                        thr = lst_d[(size_t)(kcap - 1) * QB + col];
+                        thr = lst_d[(size_t)(kseed - 1) * QB + col];
                     }
                 }
+        }
+        if (kseed < kcap) {
+            float mq = 0.0f;
+#pragma unroll
+            for (int h = 0; h < DP / 2; ++h) mq = fmaxf(mq, fmaxf(fabsf(q[h].x), fabsf(q[h].y)));
+            thr = tight_seed(thr, mq);
         }
         // the seed is itself an fp32 distance to a real candidate: one ulp up and that candidate
         // (and everything tied with it) passes the strict test when its tile is scanned
@@ -609,6 +633,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 constexpr int UNITS_THREADS = FAST_THREADS + 32;  // 4 filter warps + 1 copy warp
 
+static __device__ void refine_single_list(const float* col_d, const int32_t* col_i, int stride, int kcap, float seed,
+                                   int64_t row_q, int64_t qi, const RefineArgs& ra);
+
 // Persistent filter kernel of the windowed engine: CTAs pull work units from a global cursor.
 //
 // Roles.  Warps 0..3 filter; warp 4 only feeds the shared-memory ring (one lane issues the
@@ -630,15 +657,20 @@ constexpr int UNITS_THREADS = FAST_THREADS + 32;  // 4 filter warps + 1 copy war
 // new maximum -- constant cost, whereas a sorted insert shifts most of the list because new
 // hits are usually closer than what the list holds.  Lists are sorted once, when emitted.
 // part_d32 / part_idx: [unit][rank][QB], QB index = position of the query in its block.
+// Register cap = what the filter loop alone needs (so many CTAs fit beside its shared memory); the
+// fused refine epilogue (a noinline call, once per query) spills instead of costing residency.
+constexpr int units_min_blocks(int dp) { return dp <= 2 ? 9 : dp <= 6 ? 6 : 5; }
+
 template <int DP, int Q, int STAGES, bool HITMASK>
-static __global__ void __launch_bounds__(UNITS_THREADS)
+static __global__ void __launch_bounds__(UNITS_THREADS, units_min_blocks(DP))
 knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub_box, int64_t n_tiles,
                  int64_t q_begin, int64_t nq, int kcap, const float* __restrict__ qshadow,
                  const int32_t* __restrict__ qhome, const float* __restrict__ seed_thr,
                  const int2* __restrict__ plan, const int32_t* __restrict__ plan_count,
                  const int32_t* __restrict__ plan_first, const int32_t* __restrict__ unit_first,
                  const int32_t* __restrict__ unit_block, int32_t* __restrict__ meta, float* __restrict__ part_d32,
-                 int32_t* __restrict__ part_idx, unsigned long long* __restrict__ pair_counter) {
+                 int32_t* __restrict__ part_idx, unsigned long long* __restrict__ pair_counter,
+                 const __grid_constant__ RefineArgs ra) {
     constexpr int QB = FAST_THREADS * Q;
     constexpr int TILE_FLOATS = FAST_TILE * DP;
     constexpr int BOX_FLOATS = FAST_NSUB * DP * 2;
@@ -685,6 +717,8 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
         const int last = first + chunk < count ? first + chunk : count;
         const int64_t qb0 = qblock * QB;
         const int pfirst = plan_first[qblock];
+        // a block whose whole tile list is this one unit is refined right here, from shared memory
+        const bool refine_here = ra.fused && unit_first[qblock + 1] - unit_first[qblock] == 1;
 
         // ---------------- filter warps: queries, thresholds, warp box, empty lists
         // slot j of this thread = query qb0 + warp*32*Q + j*32 + lane
@@ -692,6 +726,8 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
         float thr[Q];   // insertion threshold: min(seed, current list maximum)
         float seed[Q];
         int pmax[Q];    // position of the list's maximum (the entry a hit replaces)
+        int nfill[Q];   // entries written so far (kcap: the list is full)
+        bool alive[Q];  // the slot holds a query of this launch
         float wlo[DP], whi[DP];
         float wthr = -1.0f;
         auto warp_refresh = [&]() {
@@ -714,6 +750,8 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
                 seed[j] = s < 0.0f ? -1.0f : s;  // deferred / dead slots never insert
                 thr[j] = seed[j];
                 pmax[j] = 0;
+                nfill[j] = 0;
+                alive[j] = in;
                 if (thr[j] >= 0.0f) {
 #pragma unroll
                     for (int h = 0; h < DP / 2; ++h) {
@@ -778,10 +816,17 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
         }
 
         // ---------------- filter warps
-        auto insert = [&](int j, float m, int32_t idx) {
+        auto insert = [&](int j, float m, int32_t idx) -> bool {
             const int col = j * FAST_THREADS + tid;
             lst_d[(size_t)pmax[j] * QB + col] = m;
             lst_i[(size_t)pmax[j] * QB + col] = idx;
+            // while the list still has free (+inf) slots the entry to replace is simply the next free
+            // one and the threshold stays at the seed: no sweep (it would find just that)
+            if (nfill[j] + 1 < kcap) {
+                pmax[j] = ++nfill[j];
+                return false;
+            }
+            nfill[j] = kcap;
             float mx = -1.0f;
             int p = 0;
 #pragma unroll 3
@@ -791,6 +836,7 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
             }
             pmax[j] = p;
             thr[j] = fminf(seed[j], mx);
+            return true;  // the threshold may have shrunk
         };
         for (;;) {
             mbar_wait(&full_bar[slot], (phase_bits >> slot) & 1u);
@@ -799,14 +845,25 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
                 const float* tile = tiles + (size_t)slot * SLOT_FLOATS;
                 const float2* boxes = reinterpret_cast<const float2*>(tile + TILE_FLOATS);
                 const int64_t tile_base = (int64_t)t * FAST_TILE;
-#pragma unroll 1
-                for (int sb = 0; sb < FAST_NSUB; ++sb) {
-                    float gap = 0.0f;
+                // lane s (mod 16) tests sub-tile s: one round of box arithmetic per tile instead of
+                // sixteen warp-uniform ones; a survivor's gap is re-read by shuffle and tested again
+                // against the (shrinking) warp threshold when its turn comes
+                static_assert(FAST_NSUB == 16, "lane-parallel sub-tile test assumes 16 sub-tiles per tile");
+                float my_gap = 0.0f;
+                {
+                    const int sbl = lane & (FAST_NSUB - 1);
 #pragma unroll
                     for (int d = 0; d < DP; ++d) {
-                        const float2 bx = boxes[sb * DP + d];
-                        gap = fmaxf(gap, fmaxf(bx.x - whi[d], wlo[d] - bx.y));
+                        const float2 bx = boxes[sbl * DP + d];
+                        my_gap = fmaxf(my_gap, fmaxf(bx.x - whi[d], wlo[d] - bx.y));
                     }
+                }
+                uint32_t live = __ballot_sync(0xffffffffu, my_gap < wthr) & ((1u << FAST_NSUB) - 1u);
+#pragma unroll 1
+                while (live) {
+                    const int sb = __ffs(live) - 1;
+                    live &= live - 1u;
+                    const float gap = __shfl_sync(0xffffffffu, my_gap, sb);
                     // insertion needs m < thr and the box gap is a lower bound of every computed m
                     if (!(gap < wthr)) continue;  // warp-uniform
                     ++subtiles_total;
@@ -837,8 +894,7 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
                                 float2 cc[DP / 2];
                                 load_row<DP>(rows + c * DP, cc);
                                 const float m = cheb32<DP>(q[j], cc);
-                                if (m < thr[j]) insert(j, m, (int32_t)(tile_base + sb * FAST_SUB + c));
-                                changed = true;
+                                if (m < thr[j]) changed |= insert(j, m, (int32_t)(tile_base + sb * FAST_SUB + c));
                             }
                         }
                     } else {
@@ -864,9 +920,8 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
                                     float2 cc[DP / 2];
                                     load_row<DP>(rows + c * DP, cc);
                                     const float m = cheb32<DP>(q[j], cc);
-                                    if (m < thr[j]) insert(j, m, (int32_t)(tile_base + sb * FAST_SUB + c));
+                                    if (m < thr[j]) changed |= insert(j, m, (int32_t)(tile_base + sb * FAST_SUB + c));
                                 }
-                                changed = true;
                             }
                         }
                     }
@@ -879,11 +934,12 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
             if (t < 0) break;
         }
 
-        // ---------------- sort each list (ascending) and emit it
+        // ---------------- sort each list (ascending); refine it here or emit it
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const int col = j * FAST_THREADS + tid;
-            for (int a = 1; a < kcap; ++a) {
+            const int filled = nfill[j];  // the rest of the column is +inf / -1
+            for (int a = 1; a < filled; ++a) {
                 const float d = lst_d[(size_t)a * QB + col];
                 const int32_t i = lst_i[(size_t)a * QB + col];
                 int b = a - 1;
@@ -896,6 +952,11 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
                 lst_i[(size_t)(b + 1) * QB + col] = i;
             }
             const int lq = warp * (32 * Q) + j * 32 + lane;
+            if (refine_here) {
+                if (alive[j])
+                    refine_single_list(lst_d + col, lst_i + col, QB, kcap, seed[j], q_begin + qb0 + lq, qb0 + lq, ra);
+                continue;
+            }
             for (int r = 0; r < kcap; ++r) {
                 const int64_t o = ((int64_t)u * kcap + r) * QB + lq;
                 part_d32[o] = lst_d[(size_t)r * QB + col];
@@ -918,7 +979,10 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
                   const float* __restrict__ seed_thr, const int32_t* __restrict__ unit_first, int qb,
                   const int32_t* __restrict__ perm, int64_t* __restrict__ idx_out,
                   const double* __restrict__ qsorted, int64_t qld, const double* __restrict__ center,
-                  double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
+                  double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged,
+                  int skip_single) {
+    // skip_single: blocks that own exactly one work unit were already refined inside
+    // knn_units_kernel (RefineArgs::fused); only the multi-unit blocks are merged here.
     // qsorted (optional, cross-set search): the float64 query coordinates come from this [dim][qld]
     // array (rows q_begin + qi) instead of the candidate set itself.
     // idx_out (optional, [nq][kp] int64): the k' nearest points as positions in the prepared
@@ -927,6 +991,10 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     // candidates whenever the query is not flagged, so the tie-break is well defined.
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
+    if (skip_single && unit_first) {
+        const int64_t b = qi / qb;
+        if (unit_first[b + 1] - unit_first[b] == 1) return;
+    }
     if (seed_thr && seed_thr[qi] < 0.0f) {  // taken out by the planning pass: needs the dense launch
         flags[qi] = 2;
         atomicAdd(n_flagged, 1);
@@ -992,7 +1060,8 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     const double delta = band_query_f64(mq, 2.0 * r32);
     const double T = r32 + 2.0 * delta;
 
-    bool overflow = false;
+    // a list that is not full holds everything below the seeded threshold -- and nothing above it
+    bool overflow = seed_thr && !(T < (double)seed_thr[qi]);
     double exact[KNN_MAX_KCAP];
     int32_t exact_j[KNN_MAX_KCAP], exact_o[KNN_MAX_KCAP];  // prepared position / original index (idx_out only)
     int got = 0, examined = 0;
@@ -1047,6 +1116,80 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
         if (idx_out)
             for (int r = 0; r < kp; ++r) idx_out[qi * kp + r] = exact_j[r];
     }
+}
+
+// The refine of ONE ascending list that still sits in shared memory (called by knn_units_kernel for
+// blocks whose tile list is a single work unit -- nearly all of them): same decision rule as
+// knn_refine_kernel, without the merge.  col_d / col_i: the query's column (entry r at r * stride;
+// unused entries +inf / -1); seed: the threshold the list was filled under (< 0: the planning pass
+// set the query aside).  All in-band float64 rows are fetched as one batch of independent loads.
+static __device__ __noinline__ void refine_single_list(const float* col_d, const int32_t* col_i, int stride, int kcap,
+                                                float seed, int64_t row_q, int64_t qi, const RefineArgs& ra) {
+    if (seed < 0.0f) {
+        ra.flags[qi] = 2;
+        atomicAdd(ra.n_flagged, 1);
+        ra.eps_out[qi] = CUDART_NAN;
+        return;
+    }
+    const int kp = ra.kp, dim = ra.dim;
+    const float v_kp = col_d[(size_t)(kp - 1) * stride];
+    if (!(v_kp < CUDART_INF_F)) {  // fewer than k' points exist (k+1 > n): cKDTree pads with inf
+        ra.eps_out[qi] = CUDART_INF;
+        ra.flags[qi] = ra.idx_out ? 1 : 0;
+        if (ra.idx_out) atomicAdd(ra.n_flagged, 1);
+        return;
+    }
+    double qc[KSG_MAX_DIM];
+    double mq = 0.0;
+    for (int d = 0; d < dim; ++d) {
+        qc[d] = ra.qsorted ? ra.qsorted[(int64_t)d * ra.qld + row_q] : ra.sorted[(int64_t)d * ra.ld + row_q];
+        mq = fmax(mq, fabs(qc[d] - ra.center[d]));
+    }
+    mq = mq * (1.0 + 1e-6) + 1e-300;
+    const double r32 = (double)v_kp;
+    const double T = r32 + 2.0 * band_query_f64(mq, 2.0 * r32);
+    const double tail = (double)col_d[(size_t)(kcap - 1) * stride];
+    // full list with its tail inside the band, or a band that reaches the seeded threshold:
+    // in-band candidates may be missing
+    bool undecided = tail <= T || !(T < (double)seed);
+    double m[KNN_MAX_KCAP];
+    int32_t mj[KNN_MAX_KCAP], mo[KNN_MAX_KCAP];
+    int nb = 0;
+    if (!undecided) {
+        while (nb < kcap && (double)col_d[(size_t)nb * stride] <= T) ++nb;  // >= k' entries
+        for (int r = 0; r < nb; ++r) mj[r] = col_i[(size_t)r * stride];
+        for (int r = 0; r < nb; ++r) {
+            double v = 0.0;
+            for (int d = 0; d < dim; ++d) v = fmax(v, fabs(qc[d] - ra.sorted[(int64_t)d * ra.ld + mj[r]]));
+            m[r] = v;
+        }
+        if (ra.idx_out)
+            for (int r = 0; r < nb; ++r) mo[r] = ra.perm[mj[r]];
+        // ascending by (exact distance, original sample index): insertion sort of <= kcap entries
+        for (int a = 1; a < nb; ++a) {
+            const double v = m[a];
+            const int32_t j = mj[a], o = ra.idx_out ? mo[a] : 0;
+            int b = a - 1;
+            while (b >= 0 && (m[b] > v || (ra.idx_out && m[b] == v && mo[b] > o))) {
+                m[b + 1] = m[b]; mj[b + 1] = mj[b];
+                if (ra.idx_out) mo[b + 1] = mo[b];
+                --b;
+            }
+            m[b + 1] = v; mj[b + 1] = j;
+            if (ra.idx_out) mo[b + 1] = o;
+        }
+        undecided = nb < kp;
+    }
+    if (undecided) {
+        ra.flags[qi] = 1;
+        atomicAdd(ra.n_flagged, 1);
+        ra.eps_out[qi] = CUDART_NAN;
+        return;
+    }
+    ra.flags[qi] = 0;
+    ra.eps_out[qi] = m[kp - 1];
+    if (ra.idx_out)
+        for (int r = 0; r < kp; ++r) ra.idx_out[qi * kp + r] = mj[r];
 }
 
 }  // namespace ksg

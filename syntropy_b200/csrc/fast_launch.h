@@ -9,6 +9,23 @@
 
 namespace ksg {
 
+// What the exact refine needs besides the fp32 lists (see knn_refine_kernel / refine_single_list).
+struct RefineArgs {
+    int fused;                 // 1: blocks that own a single work unit are refined inside knn_units_kernel
+    int kp;                    // k'
+    int dim;
+    const double* sorted;      // candidate coordinates, float64 SoA [dim][ld], prepared order
+    int64_t ld;
+    const double* qsorted;     // cross-set search: query coordinates [dim][qld] (else null)
+    int64_t qld;
+    const double* center;
+    const int32_t* perm;
+    int64_t* idx_out;          // optional [nq][kp]
+    double* eps_out;           // [nq]
+    int32_t* flags;            // [nq]
+    int32_t* n_flagged;
+};
+
 struct KnnF32Args {
     const float* shadow;
     const float* tile_box;
@@ -36,6 +53,10 @@ struct KnnF32Args {
     int32_t* part_idx;
     unsigned long long* tile_counter;
     cudaStream_t st;
+    // windowed engine: rank of the seed distance (kcap: legacy seeds; < kcap: tight seeds, see
+    // knn_plan_kernel) and the exact refine's arguments (fused into the units kernel when ra.fused)
+    int kseed;
+    RefineArgs ra;
 };
 constexpr int UNITS_Q = 1;  // queries per thread of the windowed k-NN kernels (see fast_knn.cu)
 constexpr int COUNT_UNITS_Q = 1;  // ... and of the single-subspace windowed count kernels

@@ -16,6 +16,7 @@
 #define __host__
 #define __restrict__
 #define __launch_bounds__(x)
+#define __noinline__
 #define __forceinline__ inline
 #define CUDART_INF (std::numeric_limits<double>::infinity())
 #define CUDART_INF_F (std::numeric_limits<float>::infinity())
@@ -27,7 +28,108 @@ using std::fabs;
 using std::fmax;
 constexpr int KSG_MAX_DIM = 16;
 constexpr int KNN_MAX_KCAP = 64;
-#include "refine_kernel.inc"  // band_query_f64 + constants + knn_refine_kernel, cut out of csrc/fast_knn.cuh
+// round-up float arithmetic of tight_seed(), emulated through double (exact for + and * of two floats
+// up to the final rounding, which is then pushed up)
+static inline float round_up(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return f;
+}
+static inline float __fmul_ru(float a, float b) { return round_up((double)a * (double)b); }
+static inline float __fadd_ru(float a, float b) { return round_up((double)a + (double)b); }
+// RefineArgs (csrc/fast_launch.h) + band_query_f64 + tight_seed + constants + knn_refine_kernel +
+// refine_single_list, cut out of csrc/fast_knn.cuh
+#include "refine_kernel.inc"
+
+// refine_single_list on the list the windowed filter leaves in shared memory for a block with ONE
+// work unit: every candidate with d32 < seed, the kcap smallest of them, ascending.  The seed is
+// tight_seed(s, mq) with s an upper bound of the k'-th smallest d32 (k'-th .. (k'+2)-th smallest).
+static int single_list_trials(int trials, long* checked_out, long* flagged_cont_out, long* flagged_tied_out) {
+    std::mt19937_64 rng(77);
+    long checked = 0, wrong = 0, flagged_cont = 0, flagged_tied = 0;
+    for (int trial = 0; trial < trials; ++trial) {
+        const int dim = 1 + (int)(rng() % 8);
+        const int kp = 1 + (int)(rng() % 10);
+        const int kcap = kp + ((rng() % 4 == 0) ? 24 : 3);
+        const int64_t n = 300 + (int64_t)(rng() % 600);
+        const int64_t nq = std::min<int64_t>(n, 64 + (int64_t)(rng() % 100));
+        const bool want_idx = rng() % 2 == 0;
+        const bool tied = rng() % 4 == 0;
+        const bool cross = rng() % 5 == 0;  // queries that are not members of the candidate set
+        const double scale = (rng() % 3 == 0) ? 1e-9 : 1.0;
+        std::vector<double> pts((size_t)dim * n), qry((size_t)dim * nq), center(dim);
+        std::normal_distribution<double> nd(0.0, 1.0);
+        for (int d = 0; d < dim; ++d) {
+            const double shift = (rng() % 3 == 0) ? 1e3 * scale : 0.0;
+            center[d] = shift;
+            for (int64_t i = 0; i < n; ++i) {
+                double v = nd(rng);
+                if (tied) v = std::round(v * 4) / 4;
+                pts[(size_t)d * n + i] = v * scale + shift;
+            }
+            for (int64_t i = 0; i < nq; ++i) {
+                double v = nd(rng);
+                if (tied) v = std::round(v * 4) / 4;
+                qry[(size_t)d * nq + i] = cross ? v * scale + shift : pts[(size_t)d * n + i];
+            }
+        }
+        std::vector<int32_t> perm(n);
+        for (int64_t i = 0; i < n; ++i) perm[i] = (int32_t)i;
+        std::shuffle(perm.begin(), perm.end(), rng);
+        std::vector<double> eps(nq, -7.0);
+        std::vector<int32_t> flags(nq, -7);
+        std::vector<int64_t> nbr((size_t)nq * kp, -7);
+        int32_t n_flagged = 0;
+        RefineArgs ra;
+        ra.fused = 1; ra.kp = kp; ra.dim = dim; ra.sorted = pts.data(); ra.ld = n;
+        ra.qsorted = cross ? qry.data() : nullptr; ra.qld = nq; ra.center = center.data(); ra.perm = perm.data();
+        ra.idx_out = want_idx ? nbr.data() : nullptr; ra.eps_out = eps.data(); ra.flags = flags.data();
+        ra.n_flagged = &n_flagged;
+        int counted = 0;
+        for (int64_t qi = 0; qi < nq; ++qi) {
+            std::vector<std::pair<float, int32_t>> all32(n);
+            std::vector<std::pair<double, int32_t>> all64(n);
+            float mq = 0.0f;
+            for (int d = 0; d < dim; ++d) mq = std::max(mq, std::fabs((float)(qry[(size_t)d * nq + qi] - center[d])));
+            for (int64_t j = 0; j < n; ++j) {
+                float m32 = 0.0f;
+                double m64 = 0.0;
+                for (int d = 0; d < dim; ++d) {
+                    const float x = (float)(qry[(size_t)d * nq + qi] - center[d]), y = (float)(pts[(size_t)d * n + j] - center[d]);
+                    m32 = std::max(m32, std::fabs(x - y));
+                    m64 = fmax(m64, fabs(qry[(size_t)d * nq + qi] - pts[(size_t)d * n + j]));
+                }
+                all32[j] = {m32, (int32_t)j};
+                all64[j] = {m64, perm[j]};
+            }
+            std::vector<std::pair<float, int32_t>> s32 = all32;
+            std::sort(s32.begin(), s32.end());
+            const int loose = kp - 1 + (int)(rng() % 3);
+            const float s = s32[std::min<int64_t>(loose, n - 1)].first;
+            const float seed = std::nextafterf(tight_seed(s, mq), CUDART_INF_F);
+            std::vector<float> col_d(kcap, CUDART_INF_F);
+            std::vector<int32_t> col_i(kcap, -1);
+            int fill = 0;
+            for (int64_t j = 0; j < n && fill < kcap; ++j)
+                if (s32[j].first < seed) { col_d[fill] = s32[j].first; col_i[fill] = s32[j].second; ++fill; }
+            refine_single_list(col_d.data(), col_i.data(), 1, kcap, seed, qi, qi, ra);
+            if (flags[qi] != 0) { ++counted; (tied ? flagged_tied : flagged_cont)++; continue; }
+            ++checked;
+            std::vector<int64_t> order(n);
+            for (int64_t j = 0; j < n; ++j) order[j] = j;
+            std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return all64[a] < all64[b]; });
+            bool ok = eps[qi] == all64[order[kp - 1]].first;
+            if (ok && want_idx)
+                for (int r = 0; r < kp; ++r) ok = ok && nbr[(size_t)qi * kp + r] == order[r];
+            if (!ok && ++wrong < 10)
+                printf("WRONG single-list trial %d qi %ld: eps %.17g want %.17g (dim %d kp %d kcap %d tied %d cross %d)\n",
+                       trial, (long)qi, eps[qi], all64[order[kp - 1]].first, dim, kp, kcap, (int)tied, (int)cross);
+        }
+        if (counted != n_flagged) { ++wrong; printf("WRONG single-list trial %d: n_flagged %d, flags say %d\n", trial, n_flagged, counted); }
+    }
+    *checked_out = checked; *flagged_cont_out = flagged_cont; *flagged_tied_out = flagged_tied;
+    return (int)wrong;
+}
 
 int main(int argc, char** argv) {
     const int trials = argc > 1 ? atoi(argv[1]) : 400;
@@ -108,7 +210,8 @@ int main(int argc, char** argv) {
             threadIdx.x = (unsigned)(qi % 128);
             knn_refine_kernel(d32.data(), idx.data(), kcap, splits, kp, pts.data(), n, dim, n, 0, nq, nullptr, nullptr,
                               nullptr, windowed ? unit_first.data() : nullptr, qb, perm.data(),
-                              want_idx ? nbr.data() : nullptr, nullptr, 0, center.data(), eps.data(), flags.data(), &n_flagged);
+                              want_idx ? nbr.data() : nullptr, nullptr, 0, center.data(), eps.data(), flags.data(), &n_flagged,
+                              0);
         }
         int counted = 0;
         for (int64_t qi = 0; qi < nq; ++qi) {
@@ -134,7 +237,10 @@ int main(int argc, char** argv) {
         }
         if (counted != n_flagged) { ++wrong; printf("WRONG trial %d: n_flagged %d, flags say %d\n", trial, n_flagged, counted); }
     }
-    printf("checked %ld wrong %ld flagged_continuous %ld flagged_tied %ld decided_tied %ld\n", checked, wrong,
-           flagged_continuous, flagged_tied, decided_tied);
+    long s_checked = 0, s_flagged_cont = 0, s_flagged_tied = 0;
+    wrong += single_list_trials(trials, &s_checked, &s_flagged_cont, &s_flagged_tied);
+    printf("checked %ld wrong %ld flagged_continuous %ld flagged_tied %ld decided_tied %ld single_checked %ld "
+           "single_flagged_continuous %ld single_flagged_tied %ld\n", checked, wrong,
+           flagged_continuous, flagged_tied, decided_tied, s_checked, s_flagged_cont, s_flagged_tied);
     return wrong ? 1 : 0;
 }

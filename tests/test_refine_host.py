@@ -17,12 +17,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def cut_refine_kernel():
     src = open(os.path.join(ROOT, "syntropy_b200", "csrc", "fast_knn.cuh")).read()
+    launch = open(os.path.join(ROOT, "syntropy_b200", "csrc", "fast_launch.h")).read()
+    args0 = launch.index("struct RefineArgs {")
+    args = launch[args0:launch.index("};", args0) + 2]
     band0 = src.index("__host__ __device__ inline double band_query_f64")
     band = src[band0:src.index("}", band0) + 1]
+    seed0 = src.index("__device__ __forceinline__ float tight_seed")
+    seed = src[seed0:src.index("}", seed0) + 1]
     start = src.index("// Exact refine: see the file header.")
     kernel = src[start:src.index("}  // namespace ksg", start)]
-    assert re.search(r"\bknn_refine_kernel\(", kernel)
-    return band + "\n\n" + kernel
+    assert re.search(r"\bknn_refine_kernel\(", kernel) and re.search(r"\brefine_single_list\(", kernel)
+    return args + "\n\n" + band + "\n\n" + seed + "\n\n" + kernel
 
 
 def test_refine_kernel_logic_on_the_host(tmp_path):
@@ -42,3 +47,6 @@ def test_refine_kernel_logic_on_the_host(tmp_path):
     assert stats["checked"] > 30_000
     assert stats["flagged_continuous"] == 0       # the k' + 3 margin always suffices without ties
     assert stats["flagged_tied"] > 0 and stats["decided_tied"] > 0   # both outcomes were exercised
+    # the fused refine of single-unit blocks (refine_single_list) under tight seeds
+    assert stats["single_checked"] > 15_000
+    assert stats["single_flagged_continuous"] == 0
