@@ -34,7 +34,8 @@ METRIC = "KSG MI query samples/sec at n=1M,k=5"
 UNIT = "samples/s"
 # algorithmic FP-pipe lane-ops per (query, candidate) pair, SURVEY.md 8(d):
 # pass 1 (radius) = D FADD + (D-1) FMNMX + 1 FSETP = 2D; pass 2 (counts) = D FADD + M FMNMX + S FSETP
-OPS_PER_PAIR = {"c1": (4, 4), "c2": (4, 4)}
+OPS_PER_PAIR = {"c1": (4, 4), "c2": (4, 4), "c3": (12, 14), "c4": (16, 42), "c5": (16, 16)}
+CONFIG_SIZES = {"c1": 5_000, "c3": 1_000_000, "c4": 250_000, "c5": 4_000_000}
 
 
 def parse():
@@ -51,9 +52,25 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense-leg", action="store_true",
                     help="skip the extra brute-force (dense engine) measurement reported under 'dense_engine'")
-    ap.add_argument("--cpu-sample", type=int, default=200_000,
-                    help="samples of the C2 generator the in-line CPU baseline runs on")
-    return ap.parse_args()
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000,
+                    help="samples of the C2 generator the in-line CPU baseline runs on (default: the full n)")
+    ap.add_argument("--configs", default="c1,c3,c4,c5",
+                    help="other BASELINE configurations measured + parity-checked into the line's 'configs' block "
+                         "('' or 'none': skip)")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="scale the sizes of the 'configs' block")
+    ap.add_argument("--parity-queries", type=int, default=256)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)  # timing rule: at least three untimed steps (both arms)
+    return args
+
+
+def config_dict(n, k, gpus, engine="windowed"):
+    """The `config` object of the JSON line -- the same for both arms (the driver compares them)."""
+    return {"workload": f"C2: KSG-1 MI 1D;1D n={n} k={k}, x vs x^2+noise (BASELINE configs[1])",
+            "parallelism": f"b200 arm: query rows sharded x{gpus}, full point set per GPU; "
+                           "reference arm: host threads on rank 0 (scipy cKDTree workers=-1)",
+            "l2": "b200 arm: flushed between timed steps (256 MiB write); reference arm: CPU, not applicable",
+            "engine": f"b200 arm: {engine}; reference arm: the reference's algorithm on CPU (oracle/ref_port.py)"}
 
 
 def workload(n):
@@ -208,8 +225,8 @@ def run_reference_arm(args):
 
     data, call = workload(args.n)
     mode = "fast"
-    for _ in range(min(args.warmup, 1)):
-        cpu_port_run(data[:, :50_000], call, mode)
+    for _ in range(args.warmup):
+        cpu_port_run(data, call, mode)
     times = []
     for _ in range(args.steps):
         dt, avg = cpu_port_run(data, call, mode)
@@ -218,18 +235,188 @@ def run_reference_arm(args):
     value = args.n * args.steps / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"C2: KSG-1 MI 1D;1D n={args.n} k={args.k}, x vs x^2+noise (BASELINE configs[1])",
-                   "parallelism": "host threads (scipy cKDTree workers=-1), rank 0 only",
-                   "engine": "reference algorithm on CPU (oracle/ref_port.py)"},
+        "config": config_dict(args.n, args.k, args.gpus, args.engine),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref_port.cores_used(mode), "kind": "port",
                          "sample": f"full workload per step (n={args.n}); scipy cKDTree, workers=-1, vectorised counts"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "mi_nats": avg,
     }
     print(json.dumps(line), flush=True)
+
+
+
+# ------------------------------------------------------------------ the other BASELINE configurations
+def _config_plan(name, data, call):
+    """(joint rows, [(estimator label, masks, psi program)], parity subspaces, public call)."""
+    from syntropy_b200 import _engine as E
+    from syntropy_b200 import knn
+    from syntropy_b200.knn import multivariate_mi as mv
+    from syntropy_b200.knn.shannon import _xy_masks, cmi_spec, mi1_program
+
+    dim = data.shape[0]
+    if name in ("c1", "c5"):
+        rows = data[call["idxs_x"] + call["idxs_y"], :]
+        masks = _xy_masks(call["idxs_x"], call["idxs_y"])
+        ests = [("mutual_information", masks, mi1_program)]
+        api = lambda: knn.mutual_information(call["idxs_x"], call["idxs_y"], call["k"], data)  # noqa: E731
+    elif name == "c3":
+        rows = data[call["idxs_x"] + call["idxs_y"] + call["idxs_z"], :]
+        masks, prog = cmi_spec(len(call["idxs_x"]), len(call["idxs_y"]), len(call["idxs_z"]))
+        ests = [("conditional_mutual_information", masks, prog)]
+        api = lambda: knn.conditional_mutual_information(call["idxs_x"], call["idxs_y"], call["idxs_z"],  # noqa: E731
+                                                         call["k"], data)
+    else:
+        rows = data
+        ests = [(fn,) + mv.spec(fn, dim) for fn in ("o_information", "total_correlation",
+                                                    "dual_total_correlation", "s_information")]
+        api = lambda: knn.o_information(data, call["k"])  # noqa: E731
+    parity_masks = ests[0][1]  # (C4: the 16 big / small marginals of the O-information)
+    subs = [tuple(d for d in range(rows.shape[0]) if (m >> d) & 1) for m in parity_masks]
+    return np.ascontiguousarray(rows), ests, parity_masks, subs, api
+
+
+def run_config_block(args, world, rank, dev, barrier):
+    """C1, C3, C4 (O / TC / DTC / S) and C5 at their BASELINE sizes on the same ranks as the headline:
+    device time of every estimator step with the point set resident (CUDA events, max over ranks),
+    one end-to-end public call on host arrays, executed pairs and FP-pipe fraction of the radius +
+    count passes, and a parity verdict -- radii and EVERY count vector of a random query subset
+    bit-exact against the C oracle run on the full point set, the average against the committed
+    full-size golden value (tests/golden/full_size.json) at 1e-12 relative."""
+    import torch
+    import torch.distributed as td
+
+    from syntropy_b200 import _engine as E
+    from syntropy_b200 import workloads
+
+    names = [c for c in args.configs.split(",") if c and c != "none"]
+    if not names:
+        return None
+    golden = {}
+    try:
+        golden = json.load(open(os.path.join(ROOT, "tests", "golden", "full_size.json")))
+    except Exception:
+        pass
+    oc = None
+    if rank == 0:
+        from oracle import ksg_oracle_c as oc
+
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        oracle_threads = oc.set_threads(max(1, (os.cpu_count() or 1) // (2 if local_world > 1 else 1)))
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    out = {}
+    for name in names:
+        n = max(64, int(CONFIG_SIZES[name] * args.config_scale))
+        t_gen = time.perf_counter()
+        data, call = workloads.CONFIGS[name](n=n, seed=0)
+        t_gen = time.perf_counter() - t_gen
+        k = call["k"]
+        rows, ests, parity_masks, subs, api = _config_plan(name, data, call)
+        pts = E.to_device_points(rows)
+        rec = {"n": n, "dim": int(rows.shape[0]), "k": k, "estimators": {}}
+
+        def step(masks, prog):
+            status = E.Status(dev)
+            pw = E.ksg1_device(pts, k, masks, prog, status=status)
+            full, total = E.finish_device(pw, n, out=status.total)
+            pw, full, total = E.settle(pw, n, status, full, total)
+            return full, total
+
+        reps = 1 if name == "c5" else 2
+        for label, masks, prog in ests:
+            step(masks, prog)  # warm-up (graphs, psi table)
+            barrier()
+            a = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+            b = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+            for i in range(reps):
+                a[i].record()
+                full, total = step(masks, prog)
+                b[i].record()
+            barrier()
+            t = torch.tensor([min(x.elapsed_time(y) for x, y in zip(a, b))], dtype=torch.float64, device=dev)
+            if world > 1:
+                td.all_reduce(t, op=td.ReduceOp.MAX)
+            ms = float(t.item())
+            avg = float(total.item()) / n
+            est = {"ms": ms, "samples_per_s": n / (ms * 1e-3), "avg_nats": avg}
+            g = golden.get(name, {}).get({"mutual_information": "mi", "conditional_mutual_information": "cmi"}.get(label, label))
+            if g and golden[name].get("n") == n:
+                est["golden_avg"] = g["avg"]
+                est["avg_rel_err"] = abs(avg - g["avg"]) / max(abs(g["avg"]), g["mean_abs_ptw"])
+                est["avg_matches_golden_1e-12"] = bool(est["avg_rel_err"] <= 1e-12)
+            rec["estimators"][label] = est
+        first = rec["estimators"][ests[0][0]]
+        rec["ms"], rec["samples_per_s"] = first["ms"], first["samples_per_s"]
+
+        # ---- radii + every count vector once more through the stage-level entry (per-stage timers,
+        # executed pairs) and the parity check of a query subset on rank 0
+        if E._use_fast(rows.shape[0], k + 1):
+            E.timer.enabled = True
+            E.timer.reset()
+            barrier()
+            eps, counts, preps = E.radius_and_counts(pts, k, parity_masks)
+            barrier()
+            stage_ms = {kn: float(np.sum(v)) for kn, v in E.timer.totals_ms().items()}
+            E.timer.enabled = False
+            per = [(p_.dim, p_.pairs_evaluated()) for p_ in preps]
+            p_knn = float(sum(pe[0] for _, pe in per))
+            p_cnt = float(sum(pe[1] for _, pe in per))
+            a1, a2 = OPS_PER_PAIR[name]
+            cnt_ops = a2 * float(per[0][1][1]) + float(sum(2 * d * pe[1] for d, pe in per[1:]))
+            peak = sms * 128 * 1.965e9
+            rec["stage_ms"] = stage_ms
+            rec["executed_pairs"] = {"knn": p_knn, "count": p_cnt, "dense_per_pass": float(n) * n / world}
+            if stage_ms.get("fast_knn"):
+                rec["frac"] = a1 * p_knn / (stage_ms["fast_knn"] * 1e-3) / peak
+            if stage_ms.get("fast_count"):
+                rec["frac_count"] = cnt_ops / (stage_ms["fast_count"] * 1e-3) / peak
+        else:
+            q0, q1 = 0, n
+            eps = E.knn_radius(pts, k + 1, 0, n)
+            counts = E.count_subspaces(pts, parity_masks, eps, 0, n)
+        if rank == 0:
+            t0 = time.perf_counter()
+            eps_h, cnt_h = eps.cpu().numpy(), counts.cpu().numpy()
+            sel = np.sort(np.random.default_rng(1).choice(n, size=min(args.parity_queries, n), replace=False))
+            ref_eps = oc.knn_radius(rows, k + 1, queries=rows[:, sel])
+            ok_eps = bool(np.array_equal(eps_h[sel], ref_eps))
+            ok_cnt = True
+            for row, sub in enumerate(subs):
+                want = oc.count_within(rows[list(sub), :], ref_eps, queries=rows[list(sub), :][:, sel])
+                ok_cnt = ok_cnt and bool(np.array_equal(cnt_h[row, sel], want))
+            golden_ok = [e_["avg_matches_golden_1e-12"] for e_ in rec["estimators"].values()
+                         if "avg_matches_golden_1e-12" in e_]
+            rec["parity"] = bool(ok_eps and ok_cnt and all(golden_ok))
+            rec["parity_detail"] = {"queries": int(sel.size), "radii_bit_exact": ok_eps, "counts_bit_exact": ok_cnt,
+                                    "count_vectors": len(subs), "averages_vs_golden": golden_ok or None,
+                                    "oracle": f"oracle/ksg_oracle.c brute force fp64 on the full point set, "
+                                              f"{oracle_threads} threads", "oracle_s": time.perf_counter() - t0}
+            if name == "c5" and n == CONFIG_SIZES["c5"]:
+                # pointwise values of the committed 50 000-query subset (fast oracle on the full set)
+                try:
+                    g5 = np.load(os.path.join(ROOT, "tests", "golden", "full_size_c5.npz"))
+                    sel5 = g5["sel"].astype(np.int64)
+                    ok5 = bool(np.array_equal(eps_h[sel5], g5["eps"]) and np.array_equal(cnt_h[:, sel5], g5["counts"]))
+                    rec["parity_detail"]["golden_subset_50k_bit_exact"] = ok5
+                    rec["parity"] = bool(rec["parity"] and ok5)
+                except Exception as exc:  # fixture missing: say so, do not fail the bench
+                    rec["parity_detail"]["golden_subset_50k_bit_exact"] = f"unavailable: {exc}"
+        # ---- public API, host arrays in / host arrays out
+        barrier()
+        t0 = time.perf_counter()
+        _, avg_api = api()
+        torch.cuda.synchronize()
+        rec["e2e_ms"] = 1e3 * (time.perf_counter() - t0)
+        rec["e2e_avg_nats"] = float(avg_api)
+        rec["host_generate_s"] = t_gen
+        rec["fallback_queries"] = dict(E.stats)
+        out[name] = rec
+        del pts, eps, counts
+        torch.cuda.empty_cache()
+        barrier()
+    return out
 
 
 # ------------------------------------------------------------------ B200 arm
@@ -322,9 +509,9 @@ def run_b200_arm(args):
         return float(t.item()), launches, out
 
     # warm-up (also builds the psi table and pays first-launch costs)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup):
         device_step()
-    for _ in range(max(args.warmup, 3)):  # (the second call with the same buffers captures the prepare graphs)
+    for _ in range(args.warmup):  # (the second call with the same buffers captures the prepare graphs)
         e2e_step()
     barrier()
 
@@ -375,6 +562,9 @@ def run_b200_arm(args):
         E.config.engine = args.engine
         dense_leg = (d_ms, d_steps, statistics.mean(d_kernel_ms["fast_knn"]), d_tiles)
 
+    stats_c2 = dict(E.stats)
+    configs_block = run_config_block(args, world, rank, dev, barrier) if args.engine == "windowed" else None
+
     if rank == 0:
         value = n * args.steps / (ms_total * 1e-3)
         e2e_value = n * args.steps / e2e_s
@@ -417,11 +607,9 @@ def run_b200_arm(args):
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2: KSG-1 MI 1D;1D n={n} k={k}, x vs x^2+noise (BASELINE configs[1])",
-                       "parallelism": f"query-sharded x{world}", "l2": "flushed between timed steps (256 MiB write)",
-                       "engine": args.engine},
+            "config": config_dict(n, k, args.gpus, args.engine),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rows.nbytes),
                     "d2h_bytes_per_step": int(8 * n + 16), "ms_per_step": 1e3 * e2e_s / args.steps,
@@ -448,9 +636,11 @@ def run_b200_arm(args):
                              "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
                              "frac": psi_bytes / (psi_ms * 1e-3) / 1e9 / hbm_peak,
                              "traffic": traffic.get("psi_epilogue_c2")},
-            "fallback_queries": dict(E.stats),
+            "fallback_queries": stats_c2,
             "mi_nats": float(avg_host),
         }
+        if configs_block is not None:
+            line["configs"] = configs_block
         if dense_leg is not None:
             d_ms, d_steps, d_knn_ms, d_tiles = dense_leg
             d_pairs = float(d_tiles)
@@ -465,12 +655,14 @@ def run_b200_arm(args):
             from oracle import ref_port
 
             ns = min(args.cpu_sample, n)
-            dt, _ = cpu_port_run(data[:, :ns], call, "faithful")
+            dt, cpu_avg = cpu_port_run(data[:, :ns], call, "faithful")
             line["cpu_baseline"] = {
                 "value": ns / dt, "unit": UNIT, "cores": ref_port.cores_used("faithful"), "kind": "port",
-                "sample": f"first {ns} samples of the same generator, one pass ({dt:.1f} s); the reference's own "
-                          f"scipy call sequence incl. its per-sample Python loop (single-threaded, as the reference is); "
-                          f"host has {os.cpu_count()} cores"}
+                "sample": (f"the full workload, n={ns}, one pass ({dt:.1f} s)" if ns == n else
+                           f"first {ns} samples of the same generator, one pass ({dt:.1f} s)") +
+                          "; the reference's own scipy call sequence incl. its per-sample Python loop "
+                          f"(single-threaded, as the reference is); host has {os.cpu_count()} cores",
+                "mi_nats": cpu_avg}
         print(json.dumps(line), flush=True)
     if world > 1:
         td.destroy_process_group()

@@ -11,6 +11,21 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* threads of the brute-force loops (0: leave the OpenMP default); returns the count in effect.
+ * torchrun exports OMP_NUM_THREADS=1 to every rank: callers that want the host's cores say so. */
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 static double cheb(const double* pts, int64_t ld, int dim, int64_t j, const double* q) {
     double m = 0.0;

@@ -23,6 +23,11 @@ def load():
     return _lib
 
 
+def set_threads(n: int = 0) -> int:
+    """Use ``n`` OpenMP threads from now on (0: keep the default); returns the count in effect."""
+    return int(load().oracle_set_threads(C.c_int(int(n))))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -273,7 +273,7 @@ static bool tight_seeds() { static const bool v = env_flag("KSG_B200_TIGHT_SEED"
 static bool fused_refine() { static const bool v = env_flag("KSG_B200_FUSED_REFINE", true); return v; }
 
 static void fill_refine_args(KnnF32Args& a, const ksg_prepared* P, int kprime, const double* qsorted, int64_t qld,
-                             int64_t* d_idx_out, double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged) {
+                             const double* maxabs, int64_t* d_idx_out, double* d_eps_out, int32_t* d_flags, int32_t* d_n_flagged) {
     // the window excludes the query itself when it is a member of the candidate set: the (k' - 1)-th
     // smallest distance to the OTHER rows bounds the k'-th smallest with self (0) included
     const int kseed = qsorted ? kprime : (kprime > 1 ? kprime - 1 : 1);
@@ -286,6 +286,7 @@ static void fill_refine_args(KnnF32Args& a, const ksg_prepared* P, int kprime, c
     a.ra.qsorted = qsorted;
     a.ra.qld = qld;
     a.ra.center = P->center;
+    a.ra.maxabs = maxabs;
     a.ra.perm = P->perm;
     a.ra.idx_out = d_idx_out;
     a.ra.eps_out = d_eps_out;
@@ -548,7 +549,7 @@ int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, c
     a.st = st;
     a.seed_thr = nullptr; a.plan = nullptr; a.plan_count = nullptr; a.plan_first = nullptr; a.plan_capacity = 0;
     a.unit_first = nullptr; a.unit_block = nullptr; a.unit_meta = nullptr; a.max_units = 0;
-    fill_refine_args(a, P, kprime, nullptr, 0, d_idx_out, d_eps_out, d_flags, d_n_flagged);
+    fill_refine_args(a, P, kprime, nullptr, 0, P->maxabs, d_idx_out, d_eps_out, d_flags, d_n_flagged);
     int rc;
     if (a.windowed) {
         // planning pass (seeds, deferrals, per-block tile lists) -> unit table -> persistent filter
@@ -703,7 +704,7 @@ int ksg_fast_knn_cross(const ksg_prepared* P, const ksg_cross* X, int64_t q_begi
     a.unit_block = (int32_t*)w;                  w += p.ublock_bytes;
     a.unit_meta = (int32_t*)w;
     a.max_units = p.max_units;
-    fill_refine_args(a, P, kprime, X->sorted_f64, X->ld, nullptr, d_eps_out, d_flags, d_n_flagged);
+    fill_refine_args(a, P, kprime, X->sorted_f64, X->ld, X->maxabs, nullptr, d_eps_out, d_flags, d_n_flagged);
     int rc = launch_knn_plan(P->dim_padded, a);
     if (rc) return rc;
     rc = launch_knn_units(P->dim_padded, a);

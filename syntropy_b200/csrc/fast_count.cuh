@@ -347,7 +347,8 @@ count_fix_kernel(const double* __restrict__ sorted, int64_t ld, const float* __r
     const double e = eps[qi];
     if (!(e < CUDART_INF)) return;  // infinite radius: the filter is exact (everything finite is inside)
     const float T = thresholds[qi];
-    if (T < COUNT_MIN_T) {  // the filter's scaled compare is not exact this far down (see ind_lt)
+    // (also: shadow rows beyond the fp32 range look like padding to the filter, see fp32_range_ok)
+    if (T < COUNT_MIN_T || !fp32_range_ok(maxabs, dim)) {  // the filter's scaled compare is not exact this far down (see ind_lt)
         flags[qi] = 1;
         atomicAdd(n_flagged, 1);
         return;

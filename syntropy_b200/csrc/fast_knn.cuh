@@ -56,6 +56,16 @@ __host__ __device__ inline double band_query_f64(double mq, double d) {
     return 5.9604644775390625e-08 * (2.0 * mq + 2.0 * d) * 1.01 + 1e-37;
 }
 
+// The fp32 shadow holds x - centre: finite float64 input farther than FLT_MAX from the median would
+// turn into +-inf rows that look like padding.  maxabs[d] = max |x_d - centre_d| of the prepared set
+// (candidates and, for cross-set searches, queries): when it leaves the fp32 range every query is
+// handed to the float64 kernels instead (cKDTree handles such input; so must we).
+__host__ __device__ inline bool fp32_range_ok(const double* maxabs, int dim) {
+    bool ok = true;
+    for (int d = 0; d < dim; ++d) ok = ok && maxabs[d] < 3.0e38;
+    return ok;
+}
+
 // Tight seed of the windowed filter: s = the k'-th smallest fp32 distance of the seed window (an upper
 // bound of the final r32), mq = max_d |q~_d| of the fp32 row.  The refine examines every candidate
 // with d32 <= T = r32 + 2 * band_query_f64(mq64, 2 * r32) = r32 + 2^-23 (2 mq64 + 4 r32) * 1.01 (+2e-37),
@@ -1014,7 +1024,12 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
         off = qi - b * qb;
     }
     const int64_t row_q = q_index ? (int64_t)q_index[qi] : q_begin + qi;
-    (void)maxabs;
+    if (maxabs && !fp32_range_ok(maxabs, dim)) {  // shadow rows may have overflowed: float64 kernels
+        flags[qi] = 1;
+        atomicAdd(n_flagged, 1);
+        eps_out[qi] = CUDART_NAN;
+        return;
+    }
     // the query's own magnitude in the centred frame bounds the fp32 error of all its near pairs
     double qc[KSG_MAX_DIM];
     double mq = 0.0;
@@ -1132,6 +1147,12 @@ static __device__ __noinline__ void refine_single_list(const float* col_d, const
         return;
     }
     const int kp = ra.kp, dim = ra.dim;
+    if (!fp32_range_ok(ra.maxabs, dim)) {  // shadow rows may have overflowed: float64 kernels
+        ra.flags[qi] = 1;
+        atomicAdd(ra.n_flagged, 1);
+        ra.eps_out[qi] = CUDART_NAN;
+        return;
+    }
     const float v_kp = col_d[(size_t)(kp - 1) * stride];
     if (!(v_kp < CUDART_INF_F)) {  // fewer than k' points exist (k+1 > n): cKDTree pads with inf
         ra.eps_out[qi] = CUDART_INF;

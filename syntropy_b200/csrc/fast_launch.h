@@ -19,6 +19,7 @@ struct RefineArgs {
     const double* qsorted;     // cross-set search: query coordinates [dim][qld] (else null)
     int64_t qld;
     const double* center;
+    const double* maxabs;      // [dim] max |x - centre| of candidates (and cross-set queries)
     const int32_t* perm;
     int64_t* idx_out;          // optional [nq][kp]
     double* eps_out;           // [nq]

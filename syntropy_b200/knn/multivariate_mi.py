@@ -26,14 +26,8 @@ def total_correlation_1(data, k, idxs=None):
     idxs_ = check_idxs(idxs, data)
     m = len(idxs_)
     rows = E.select_rows(data, idxs_)
-
-    def program(psi_k, psi_n):
-        prog = E.PsiProgram(init=psi_k + (m - 1) * psi_n)
-        for d in range(m):
-            prog.add(d, -1)
-        return prog
-
-    ptw, avg = E.ksg1_family(rows, k, [1 << d for d in range(m)], program)
+    masks, program = spec("total_correlation", m)
+    ptw, avg = E.ksg1_family(rows, k, masks, program)
     return ptw.reshape(1, -1), avg
 
 
@@ -65,15 +59,9 @@ def dual_total_correlation(data, k, idxs=None):
     idxs_ = check_idxs(idxs, data)
     m = len(idxs_)
     rows = E.select_rows(data, idxs_)
-
-    def program(psi_k, psi_n):
-        prog = E.PsiProgram(init=psi_k - psi_n, psi_n=psi_n, scale=float(m - 1))
-        for i in range(m):
-            prog.add(i, -1, centered=True, divisor=m - 1)
-        return prog
-
+    masks, program = spec("dual_total_correlation", m)
     with np.errstate(all="ignore"):
-        ptw, avg = E.ksg1_family(rows, k, [_leave_one_out(m, i) for i in range(m)], program)
+        ptw, avg = E.ksg1_family(rows, k, masks, program)
     return ptw.reshape(1, -1), avg
 
 
@@ -85,11 +73,41 @@ def _big_small_masks(m):
     return masks
 
 
-def _row_slices(data, idxs_):
-    """The reference selects the small marginal by the SLICE ``idxs_[d]:idxs_[d]+1`` and the
-    big one by fancy index (knn/multivariate_mi.py:317,321,398,402); both pick the same
-    rows for non-negative indices, which is what the joint selection below relies on."""
-    return E.select_rows(data, idxs_)
+def spec(name, m):
+    """(subspace masks over the m selected rows, psi program) of a multivariate estimator; the
+    programs replay the reference's float64 update order (knn/multivariate_mi.py:100-113,
+    241-258, 311-333, 394-413)."""
+    if name == "total_correlation":
+        def program(psi_k, psi_n):
+            prog = E.PsiProgram(init=psi_k + (m - 1) * psi_n)
+            for d in range(m):
+                prog.add(d, -1)
+            return prog
+        return [1 << d for d in range(m)], program
+    if name == "dual_total_correlation":
+        def program(psi_k, psi_n):
+            prog = E.PsiProgram(init=psi_k - psi_n, psi_n=psi_n, scale=float(m - 1))
+            for i in range(m):
+                prog.add(i, -1, centered=True, divisor=m - 1)
+            return prog
+        return [_leave_one_out(m, i) for i in range(m)], program
+    if name == "s_information":
+        def program(psi_k, psi_n):
+            prog = E.PsiProgram(init=psi_k - psi_n, psi_n=psi_n, scale=float(m))
+            for d in range(m):
+                prog.add(2 * d, -1, centered=True, divisor=m)
+                prog.add(2 * d + 1, -1, centered=True, divisor=m)
+            return prog
+        return _big_small_masks(m), program
+    if name == "o_information":
+        def program(psi_k, psi_n):
+            prog = E.PsiProgram(init=psi_k - psi_n, psi_n=psi_n, scale=float(2 - m))
+            for d in range(m):
+                prog.add(2 * d, -1, centered=True, divisor=m - 2)
+                prog.add(2 * d + 1, +1, centered=True, divisor=m - 2)
+            return prog
+        return _big_small_masks(m), program
+    raise ValueError(name)
 
 
 def s_information(data, k, idxs=None):
@@ -97,16 +115,11 @@ def s_information(data, k, idxs=None):
     data = np.asarray(data)
     idxs_ = check_idxs(idxs, data)
     m = len(idxs_)
-    rows = _row_slices(data, idxs_)
-
-    def program(psi_k, psi_n):
-        prog = E.PsiProgram(init=psi_k - psi_n, psi_n=psi_n, scale=float(m))
-        for d in range(m):
-            prog.add(2 * d, -1, centered=True, divisor=m)
-            prog.add(2 * d + 1, -1, centered=True, divisor=m)
-        return prog
-
-    ptw, avg = E.ksg1_family(rows, k, _big_small_masks(m), program)
+    # (the reference selects the small marginal by the SLICE ``idxs_[d]:idxs_[d]+1`` and the big one by
+    #  fancy index, knn/multivariate_mi.py:317,321,398,402: the same rows for non-negative indices)
+    rows = E.select_rows(data, idxs_)
+    masks, program = spec("s_information", m)
+    ptw, avg = E.ksg1_family(rows, k, masks, program)
     return ptw.reshape(1, -1), avg
 
 
@@ -119,15 +132,8 @@ def o_information(data, k, idxs=None):
     m = len(idxs_)
     if m == 2:
         return np.zeros(N), 0.0
-    rows = _row_slices(data, idxs_)
-
-    def program(psi_k, psi_n):
-        prog = E.PsiProgram(init=psi_k - psi_n, psi_n=psi_n, scale=float(2 - m))
-        for d in range(m):
-            prog.add(2 * d, -1, centered=True, divisor=m - 2)
-            prog.add(2 * d + 1, +1, centered=True, divisor=m - 2)
-        return prog
-
+    rows = E.select_rows(data, idxs_)
+    masks, program = spec("o_information", m)
     with np.errstate(all="ignore"):
-        ptw, avg = E.ksg1_family(rows, k, _big_small_masks(m), program)
+        ptw, avg = E.ksg1_family(rows, k, masks, program)
     return ptw.reshape(1, -1), avg

@@ -89,7 +89,13 @@ def conditional_mutual_information(idxs_x, idxs_y, idxs_z, k, data, p=np.inf):
     data = np.asarray(data)
     idxs_x, idxs_y, idxs_z = tuple(idxs_x), tuple(idxs_y), tuple(idxs_z)
     rows = E.select_rows(data, idxs_x + idxs_y + idxs_z)
-    dx, dy, dz = len(idxs_x), len(idxs_y), len(idxs_z)
+    masks, program = cmi_spec(len(idxs_x), len(idxs_y), len(idxs_z))
+    ptw, avg = E.ksg1_family(rows, k, masks, program)
+    return ptw.reshape(1, -1), avg
+
+
+def cmi_spec(dx, dy, dz):
+    """(subspace masks z | xz | yz over the x,y,z-concatenated rows, psi program) of the CMI."""
     x = list(range(dx))
     y = list(range(dx, dx + dy))
     z = list(range(dx + dy, dx + dy + dz))
@@ -102,8 +108,7 @@ def conditional_mutual_information(idxs_x, idxs_y, idxs_z, k, data, p=np.inf):
         prog.add(2, -1)
         return prog
 
-    ptw, avg = E.ksg1_family(rows, k, masks, program)
-    return ptw.reshape(1, -1), avg
+    return masks, program
 
 
 def kullback_leibler_divergence(posterior_data, prior_data, k, p=np.inf):

@@ -83,6 +83,8 @@ static int single_list_trials(int trials, long* checked_out, long* flagged_cont_
         RefineArgs ra;
         ra.fused = 1; ra.kp = kp; ra.dim = dim; ra.sorted = pts.data(); ra.ld = n;
         ra.qsorted = cross ? qry.data() : nullptr; ra.qld = nq; ra.center = center.data(); ra.perm = perm.data();
+        std::vector<double> maxabs(dim, 1e6);
+        ra.maxabs = maxabs.data();
         ra.idx_out = want_idx ? nbr.data() : nullptr; ra.eps_out = eps.data(); ra.flags = flags.data();
         ra.n_flagged = &n_flagged;
         int counted = 0;

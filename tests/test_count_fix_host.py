@@ -16,6 +16,8 @@ def cut_count_fix_kernel():
     knn = open(os.path.join(ROOT, "syntropy_b200", "csrc", "fast_knn.cuh")).read()
     b0 = knn.index("__host__ __device__ inline double band_query_f64")
     band = knn[b0:knn.index("}", b0) + 1]
+    r0 = knn.index("__host__ __device__ inline bool fp32_range_ok")
+    band += "\n" + knn[r0:knn.index("\n}\n", r0) + 3]
     src = open(os.path.join(ROOT, "syntropy_b200", "csrc", "fast_count.cuh")).read()
     q0 = src.index("// Mq of the query at `row` of the fp32 shadow")
     helpers = src[q0:src.index("// ---- \"m < T\" as 1.0f / 0.0f on the FMA pipe.")]

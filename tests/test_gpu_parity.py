@@ -43,16 +43,33 @@ def E(request):
     _engine.config.engine = old
 
 
-def close(a, b):
-    """|a-b| <= 1e-12 * max(|b|, 1): relative 1e-12, with an absolute floor for pointwise
-    values that cancel to ~0 (every psi term is O(1..20))."""
+def ptw_floor(ref_ptw):
+    """mean |ptw_ref| over the finite entries: the floor SURVEY.md 8(d) allows under the 1e-12
+    relative bar (pointwise values are sums of psi terms of this size that may cancel to ~0)."""
+    b = np.asarray(ref_ptw, dtype=np.float64).reshape(-1)
+    b = b[np.isfinite(b)]
+    return float(np.mean(np.abs(b))) if b.size else 0.0
+
+
+def close(a, b, floor=None):
+    """|a-b| <= 1e-12 * max(|b|, floor).  ``floor`` defaults to mean |b| for an array and to 0
+    (purely relative) for a scalar; an average is compared with the floor of its own pointwise
+    reference (``close_pair``)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, (a.shape, b.shape)
+    if floor is None:
+        floor = ptw_floor(b) if b.size > 1 else 0.0
     both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
     both_nan = np.isnan(a) & np.isnan(b)
-    ok = both_inf | both_nan | (np.abs(a - b) <= RTOL * np.maximum(np.abs(b), 1.0))
-    assert ok.all(), f"max abs diff {np.nanmax(np.abs(a - b)[~(both_inf | both_nan)])}"
+    ok = both_inf | both_nan | (np.abs(a - b) <= RTOL * np.maximum(np.abs(b), floor))
+    assert ok.all(), f"max abs diff {np.nanmax(np.abs(a - b)[~(both_inf | both_nan)])}, floor {floor}"
+
+
+def close_pair(ptw, ref_ptw, avg, ref_avg):
+    """Pointwise array and average of one estimator call against the reference's."""
+    close(ptw, ref_ptw)
+    close(avg, ref_avg, floor=ptw_floor(ref_ptw))
 
 
 def radius_and_counts(E, rows, k, subspaces, strict=True, fused=False):
@@ -100,20 +117,20 @@ def test_golden_tie_fixture(knn, E, golden):
     data = workloads.tie_fixture()
     for k in (1, 4):
         ptw, avg = knn.differential_entropy(data=data, idxs=(0,), k=k)
-        close(ptw, g[f"entropy_k{k}_ptw"]); close(avg, g[f"entropy_k{k}_avg"])
+        close_pair(ptw, g[f"entropy_k{k}_ptw"], avg, g[f"entropy_k{k}_avg"])
     ptw, avg = knn.mutual_information((0,), (1,), k=1, data=data, algorithm=1)
-    close(ptw, g["mi1_ptw"]); close(avg, g["mi1_avg"])
+    close_pair(ptw, g["mi1_ptw"], avg, g["mi1_avg"])
     assert avg == pytest.approx(5.177377517639623, 1e-6)   # tests/test_knn.py:44 (JIDT)
     mi2 = knn.mutual_information((0,), (1,), k=1, data=data, algorithm=2)[1]
     assert mi2 == pytest.approx(2.2173775176396227, 1e-6)  # tests/test_knn.py:50 (JIDT)
     ptw, avg = knn.conditional_mutual_information((0,), (1,), (2,), k=1, data=data)
-    close(ptw, g["cmi_ptw"]); close(avg, g["cmi_avg"])
+    close_pair(ptw, g["cmi_ptw"], avg, g["cmi_avg"])
     assert avg == pytest.approx(4.479205338329424, 1e-6)   # tests/test_knn.py:57
     known = {"total_correlation": 5.875549696949821, "dual_total_correlation": 5.1773775176396235,
              "o_information": 0.6981721793101983, "s_information": 11.052927214589442}
     for name, val in known.items():
         ptw, avg = getattr(knn, name)(data=data, k=1)
-        close(ptw, g[name + "_ptw"]); close(avg, g[name + "_avg"])
+        close_pair(ptw, g[name + "_ptw"], avg, g[name + "_avg"])
         assert avg == pytest.approx(val, 1e-6)               # tests/test_knn.py:60-75
     subs = {"x": (0,), "y": (1,), "z": (2,), "xy": (0, 1), "yz": (1, 2)}
     eps, counts = radius_and_counts(E, data, 1, list(subs.values()))
@@ -131,10 +148,10 @@ def test_golden_c1_readme_case(knn, E, golden):
     assert np.array_equal(counts[1], g["counts_y"])
     ptw, avg = knn.mutual_information((0,), (1,), k=5, data=data)
     assert ptw.shape == (1, 5000) and isinstance(avg, np.float64)
-    close(ptw, g["ptw"]); close(avg, g["avg"])
+    close_pair(ptw, g["ptw"], avg, g["avg"])
     assert avg == pytest.approx(0.780399359365535, rel=1e-12)
     ptw, avg = knn.mutual_information((0,), (1,), k=5, data=data, algorithm=2)
-    close(ptw, g["ptw_alg2"]); close(avg, g["avg_alg2"])
+    close_pair(ptw, g["ptw_alg2"], avg, g["avg_alg2"])
 
 
 def test_golden_c3_cmi(knn, E, golden):
@@ -145,7 +162,7 @@ def test_golden_c3_cmi(knn, E, golden):
     for row, name in enumerate(("z", "xz", "yz")):
         assert np.array_equal(counts[row], g["counts_" + name]), name
     ptw, avg = knn.conditional_mutual_information((0, 1), (2, 3), (4, 5), k=4, data=data)
-    close(ptw, g["ptw"]); close(avg, g["avg"])
+    close_pair(ptw, g["ptw"], avg, g["avg"])
 
 
 def test_golden_c4_multivariate(knn, E, golden):
@@ -159,16 +176,16 @@ def test_golden_c4_multivariate(knn, E, golden):
         assert np.array_equal(counts[8 + d], g[f"counts_big{d}"])
     for name in ("total_correlation", "dual_total_correlation", "o_information", "s_information"):
         ptw, avg = getattr(knn, name)(data=data, k=4)
-        close(ptw, g[name + "_ptw"]); close(avg, g[name + "_avg"])
+        close_pair(ptw, g[name + "_ptw"], avg, g[name + "_avg"])
         ptw, avg = getattr(knn, name)(data=data, k=3, idxs=(5, 1, 6, 2))
-        close(ptw, g[name + "_sel_ptw"]); close(avg, g[name + "_sel_avg"])
+        close_pair(ptw, g[name + "_sel_ptw"], avg, g[name + "_sel_avg"])
     ptw, avg = knn.total_correlation(data=data, k=4, algorithm=2)
-    close(ptw, g["total_correlation2_ptw"]); close(avg, g["total_correlation2_avg"])
+    close_pair(ptw, g["total_correlation2_ptw"], avg, g["total_correlation2_avg"])
     for k in (1, 4):
         ptw, avg = knn.differential_entropy(data=data, k=k, idxs=(0, 3, 7))
-        close(ptw, g[f"entropy_k{k}_ptw"]); close(avg, g[f"entropy_k{k}_avg"])
+        close_pair(ptw, g[f"entropy_k{k}_ptw"], avg, g[f"entropy_k{k}_avg"])
     ptw, avg = knn.differential_entropy(data=data, k=3, noise_level=0.05, seed=7)
-    close(ptw, g["entropy_noise_ptw"]); close(avg, g["entropy_noise_avg"])
+    close_pair(ptw, g["entropy_noise_ptw"], avg, g["entropy_noise_avg"])
     # identities O = TC - DTC, S = TC + DTC hold on the outputs
     tc = knn.total_correlation(data, 4)[1]; dtc = knn.dual_total_correlation(data, 4)[1]
     assert knn.o_information(data, 4)[1] == pytest.approx(tc - dtc, abs=1e-9)
@@ -183,7 +200,7 @@ def test_golden_c5_and_temporal(knn, E, golden):
     assert np.array_equal(eps, g["eps"])
     assert np.array_equal(counts[0], g["counts_x"]) and np.array_equal(counts[1], g["counts_y"])
     ptw, avg = knn.mutual_information((0, 1, 2, 3), (4, 5, 6, 7), k=5, data=data)
-    close(ptw, g["ptw"]); close(avg, g["avg"])
+    close_pair(ptw, g["ptw"], avg, g["avg"])
     series = workloads.c5_series(n=n, seed=0)
     # pair counts are integers: the entropies are bit-exact up to the host log
     assert [knn.sample_entropy((c,), series) for c in range(4)] == list(g["sampen"])
@@ -201,7 +218,7 @@ def test_golden_kl_divergence(knn, golden):
     for k in (1, 3):
         ptw, avg = knn.kullback_leibler_divergence(post, prior, k=k)
         assert ptw.shape == (2000,)
-        close(ptw, g[f"k{k}_ptw"]); close(avg, g[f"k{k}_avg"])
+        close_pair(ptw, g[f"k{k}_ptw"], avg, g[f"k{k}_avg"])
 
 
 def test_golden_edge_cases(knn, E, golden):
@@ -214,18 +231,18 @@ def test_golden_edge_cases(knn, E, golden):
     assert np.array_equal(counts[0], g["dup_counts_x"]) and counts[0].min() == -1
     assert np.array_equal(counts[1], g["dup_counts_y"])
     ptw, avg = knn.mutual_information((0,), (1,), k=2, data=dup)
-    close(ptw, g["dup_mi_ptw"]); close(avg, g["dup_mi_avg"])     # +inf entries from psi(0)
+    close_pair(ptw, g["dup_mi_ptw"], avg, g["dup_mi_avg"])     # +inf entries from psi(0)
     tiny = rng.standard_normal((2, 4))
     eps, counts = radius_and_counts(E, tiny, 5, [(0,), (1,)])     # k+1 > n -> eps = inf
     assert np.isinf(eps).all() and np.array_equal(counts[0], g["tiny_counts_x"])
     ptw, avg = knn.mutual_information((0,), (1,), k=5, data=tiny)
-    close(ptw, g["tiny_mi_ptw"]); close(avg, g["tiny_mi_avg"])
+    close_pair(ptw, g["tiny_mi_ptw"], avg, g["tiny_mi_avg"])
     f32 = rng.standard_normal((3, 500)).astype(np.float32)
     ptw, avg = knn.conditional_mutual_information((0,), (1,), (2,), k=3, data=f32)
-    close(ptw, g["f32_cmi_ptw"]); close(avg, g["f32_cmi_avg"])
+    close_pair(ptw, g["f32_cmi_ptw"], avg, g["f32_cmi_avg"])
     i32 = rng.integers(-50, 50, size=(3, 400)).astype(np.int32)
     ptw, avg = knn.total_correlation(data=i32, k=3)
-    close(ptw, g["i32_tc_ptw"]); close(avg, g["i32_tc_avg"])
+    close_pair(ptw, g["i32_tc_ptw"], avg, g["i32_tc_avg"])
 
 
 # ------------------------------------------------------------------ reference-test semantics
@@ -352,6 +369,7 @@ def test_c2_full_size(E, knn):
     assert (counts[0] >= counts[2]).all() and (counts[1] >= counts[2]).all()
     ptw, avg = knn.mutual_information((0,), (1,), 5, data)
     assert avg == pytest.approx(0.8044789267532502, rel=1e-12)  # SURVEY.md 8c anchor (reference, n=1e6)
+    check_full_size(ptw, avg, _full_size_golden()["c2"]["mi"])
 
 
 def test_engines_agree_bitwise_on_random_configs():
@@ -421,7 +439,7 @@ def test_large_k_through_the_api(knn, k):
     data, _ = workloads.c3_cmi(n=1500, seed=9)
     ptw, avg = knn.mutual_information((0, 1), (2,), k, data)
     ref_ptw, ref_avg = orc.mutual_information((0, 1), (2,), k, data)
-    close(ptw, ref_ptw); close(avg, ref_avg)
+    close_pair(ptw, ref_ptw, avg, ref_avg)
 
 
 def test_k_beyond_the_kernel_limit_is_refused_loudly(knn):
@@ -438,10 +456,10 @@ def test_ksg2_vs_oracle_multidimensional_marginals(knn):
     for ix, iy, k in (((0, 1), (2, 3), 4), ((4,), (0, 2, 5), 3)):
         ptw, avg = knn.mutual_information(ix, iy, k, data, algorithm=2)
         ref_ptw, ref_avg = orc.mutual_information(ix, iy, k, data, algorithm=2)
-        close(ptw, ref_ptw); close(avg, ref_avg)
+        close_pair(ptw, ref_ptw, avg, ref_avg)
     ptw, avg = knn.total_correlation(data[:5], 4, algorithm=2)
     ref_ptw, ref_avg = orc.total_correlation(data[:5], 4, algorithm=2)
-    close(ptw, ref_ptw); close(avg, ref_avg)
+    close_pair(ptw, ref_ptw, avg, ref_avg)
 
 
 @pytest.mark.parametrize("dim,n,m,k,shift", [(3, 20_000, 15_000, 1, 0.5), (2, 9_000, 30_000, 4, 0.0),
@@ -456,7 +474,7 @@ def test_kl_divergence_cross_set_search_vs_oracle(knn, dim, n, m, k, shift):
     prior = rng.standard_normal((dim, m)) * 1.3
     ptw, avg = knn.kullback_leibler_divergence(post, prior, k)
     ref_ptw, ref_avg = orc.kullback_leibler_divergence(post, prior, k)
-    close(ptw, ref_ptw); close(avg, ref_avg)
+    close_pair(ptw, ref_ptw, avg, ref_avg)
 
 
 # ------------------------------------------------------------------ full-size properties (C3, C4, C5)
@@ -491,6 +509,21 @@ def _subset_parity(E, rows, k, subs, n_check=256, seed=1):
     return eps, counts
 
 
+def _full_size_golden():
+    import json
+
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_size.json")))
+
+
+def check_full_size(ptw, avg, g):
+    """Average and 64 probed pointwise values against tests/golden/full_size.json (fast oracle on
+    the FULL configuration, tests/golden/make_full_size.py): 1e-12 relative, floor mean |ptw_ref|."""
+    flat = np.asarray(ptw).reshape(-1)
+    floor = g["mean_abs_ptw"]
+    assert abs(avg - g["avg"]) <= RTOL * max(abs(g["avg"]), floor), (avg, g["avg"])
+    close(flat[np.asarray(g["probe_idx"])], np.asarray(g["probe_ptw"]), floor=floor)
+
+
 def test_c3_full_size(windowed):
     """C3: Frenzel-Pompe CMI 2D;2D|2D, n = 1e6, k = 4 (windowed engine)."""
     E, knn = windowed
@@ -503,7 +536,7 @@ def test_c3_full_size(windowed):
     ptw, avg = knn.conditional_mutual_information(call["idxs_x"], call["idxs_y"], call["idxs_z"], call["k"], data)
     assert ptw.shape == (1, data.shape[1]) and np.isfinite(ptw).all()
     assert avg == pytest.approx(float(np.mean(ptw)), rel=1e-12)
-    assert 0.5 < avg < 1.0
+    check_full_size(ptw, avg, _full_size_golden()["c3"]["cmi"])
 
 
 def test_c4_full_size(windowed):
@@ -522,6 +555,10 @@ def test_c4_full_size(windowed):
     s_p, s = knn.s_information(data, call["k"])
     assert np.abs(o_p - (tc_p - dtc_p)).max() < 1e-9 and np.abs(s_p - (tc_p + dtc_p)).max() < 1e-9
     assert o == pytest.approx(tc - dtc, abs=1e-10) and s == pytest.approx(tc + dtc, abs=1e-10)
+    g = _full_size_golden()["c4"]
+    for name, (ptw, avg) in {"total_correlation": (tc_p, tc), "dual_total_correlation": (dtc_p, dtc),
+                             "o_information": (o_p, o), "s_information": (s_p, s)}.items():
+        check_full_size(ptw, avg, g[name])
 
 
 def test_c5_full_size(windowed):
@@ -535,6 +572,14 @@ def test_c5_full_size(windowed):
     ptw, avg = knn.mutual_information(call["idxs_x"], call["idxs_y"], call["k"], data)
     ptw2, avg2 = knn.mutual_information(call["idxs_y"], call["idxs_x"], call["k"], data)
     assert np.isfinite(ptw).all() and 1.0 < avg < 1.7
+    # the committed 50 000-query subset (fast oracle against the full 4e6-point set): radii and both
+    # marginal count vectors bit-exact, pointwise values at 1e-12 relative
+    g5 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_size_c5.npz"))
+    sel = g5["sel"].astype(np.int64)
+    assert np.array_equal(eps[sel], g5["eps"])
+    assert np.array_equal(counts[:, sel], g5["counts"].astype(np.int64))
+    close(ptw.reshape(-1)[sel], g5["ptw"])
+    assert float(np.mean(ptw.reshape(-1)[sel])) == pytest.approx(_full_size_golden()["c5"]["subset_mean"], rel=1e-12)
     # swapping the groups permutes the joint coordinates: same radii, same counts; the two
     # psi terms are then subtracted in the other order, which may differ in the last bit
     assert np.abs(ptw - ptw2).max() < 1e-12 and avg == pytest.approx(avg2, rel=1e-13)
@@ -560,6 +605,22 @@ def test_heavy_tailed_data_stays_on_the_fast_path(E):
             assert np.array_equal(counts[row], orc.count_within(rows[list(s), :], ref)), s
         if E.config.engine != "exact":
             assert E.stats["knn_fallback_queries"] + E.stats["count_fallback_queries"] <= n // 100
+
+
+def test_coordinates_beyond_the_fp32_range(E):
+    """Finite float64 input farther than FLT_MAX from the median: the centred fp32 copy
+    would overflow to +-inf and look like padding.  The prepared set notices (maxabs) and every query
+    goes to the float64 kernels: radii and counts still equal the oracle's."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    rows = rng.standard_normal((2, n))
+    rows[0, ::7] *= 1e39       # a seventh of the points lie ~1e39 away from the median
+    rows[1, 5] = -3e200
+    eps, counts = radius_and_counts(E, rows, 4, [(0,), (1,), (0, 1)])
+    ref = orc.knn_radius(rows, 4)
+    assert np.array_equal(eps, ref)
+    for row, s in enumerate([(0,), (1,), (0, 1)]):
+        assert np.array_equal(counts[row], orc.count_within(rows[list(s), :], ref)), s
 
 
 def test_randomised_engine_agreement():
@@ -625,8 +686,7 @@ def test_speculative_run_recomputes_when_the_filter_flags_queries(windowed):
         with np.errstate(all="ignore"):
             ptw, avg = knn.mutual_information((0,), (1,), 4, rows)
             ref_ptw, ref_avg = orc.mutual_information((0,), (1,), 4, rows)
-        close(ptw, ref_ptw)
-        close(avg, ref_avg)
+        close_pair(ptw, ref_ptw, avg, ref_avg)
         escalated = (E.stats["knn_fallback_queries"] + E.stats["knn_deferred_queries"]
                      + E.stats["knn_wide_margin_passes"]) > 0
         assert escalated == expect_escalation
@@ -656,13 +716,13 @@ def test_mixed_knn_branch_vs_reference_golden(E, golden):
     with np.errstate(all="ignore"):
         for name, (d, c, k) in workloads.mixed_cases().items():
             ptw, avg = mixed.shannon_entropy(d, c, continuous_estimator="knn", k=k)
-            close(ptw, g[f"{name}_h_ptw"]); close(avg, g[f"{name}_h_avg"])
+            close_pair(ptw, g[f"{name}_h_ptw"], avg, g[f"{name}_h_avg"])
             for cond in ("discrete", "continuous"):
                 ptw, avg = mixed.conditional_entropy(d, c, conditional=cond, continuous_estimator="knn", k=k)
-                close(ptw, g[f"{name}_ce_{cond}_ptw"]); close(avg, g[f"{name}_ce_{cond}_avg"])
+                close_pair(ptw, g[f"{name}_ce_{cond}_ptw"], avg, g[f"{name}_ce_{cond}_avg"])
             ptw, avg = mixed.mutual_information(d, c, continuous_estimator="knn", k=k)
             assert ptw.shape == (1, d.shape[1])
-            close(ptw, g[f"{name}_mi_ptw"]); close(avg, g[f"{name}_mi_avg"])
+            close_pair(ptw, g[f"{name}_mi_ptw"], avg, g[f"{name}_mi_avg"])
 
 
 def test_mixed_knn_properties_at_the_reference_test_size(windowed):

@@ -22,6 +22,8 @@ def cut_refine_kernel():
     args = launch[args0:launch.index("};", args0) + 2]
     band0 = src.index("__host__ __device__ inline double band_query_f64")
     band = src[band0:src.index("}", band0) + 1]
+    r0 = src.index("__host__ __device__ inline bool fp32_range_ok")
+    band += "\n" + src[r0:src.index("\n}\n", r0) + 3]
     seed0 = src.index("__device__ __forceinline__ float tight_seed")
     seed = src[seed0:src.index("}", seed0) + 1]
     start = src.index("// Exact refine: see the file header.")
