@@ -104,6 +104,130 @@ def _cheb_block(q, pts):
     return dist
 
 
+# ---- Minkowski p-norms other than the maximum norm.  cKDTree works in
+# "p-th power space" (scipy/spatial/ckdtree/src/distance_base.h, distance.h -- not vendored in the
+# reference; the published algorithm, pinned below against the installed scipy):
+#   p = 1    s = sum_d |x_d - y_d|                          sequential over d; distance = s
+#   p = 2    s = sum_d (x_d - y_d)^2                        four partial sums over d = 0,4,8.. / 1,5,.. /
+#                                                           2,6,.. / 3,7,.., added as ((a0+a1)+a2)+a3, then
+#                                                           the d % 4 remainder sequentially; distance = sqrt(s)
+#   other p  s = sum_d pow(|x_d - y_d|, p)                  sequential; distance = pow(s, 1/p)
+# and a ball query of radius r keeps s <= r (p = 1), s <= r*r (p = 2), s <= pow(r, p) (other p).
+def _is_inf(p):
+    return p == np.inf
+
+
+def _pow_dist_block(q, pts, p):
+    """(nq, n) matrix of the p-th-power-space distances, operation order as above."""
+    D = q.shape[0]
+    diff = [q[d][:, None] - pts[d][None, :] for d in range(D)]
+    if p == 1:
+        s = np.abs(diff[0])
+        for d in range(1, D):
+            s = s + np.abs(diff[d])
+        return s
+    if p == 2:
+        full = D - D % 4
+        if full:
+            acc = [np.zeros_like(diff[0]) for _ in range(4)]
+            for d in range(0, full, 4):
+                for u in range(4):
+                    acc[u] = acc[u] + diff[d + u] * diff[d + u]
+            s = ((acc[0] + acc[1]) + acc[2]) + acc[3]
+        else:
+            s = np.zeros_like(diff[0])
+        for d in range(full, D):
+            s = s + diff[d] * diff[d]
+        return s
+    s = np.power(np.abs(diff[0]), p)
+    for d in range(1, D):
+        s = s + np.power(np.abs(diff[d]), p)
+    return s
+
+
+def _root_p(s, p):
+    if p == 1:
+        return s
+    if p == 2:
+        return np.sqrt(s)
+    with np.errstate(all="ignore"):
+        return np.power(s, 1.0 / p)
+
+
+def _bound_p(r, p):
+    r = np.asarray(r, dtype=np.float64)
+    if p == 1:
+        return r
+    if p == 2:
+        return r * r
+    with np.errstate(all="ignore"):
+        return np.power(r, p)
+
+
+def _check_p(p):
+    if not (p >= 1):
+        raise ValueError("Only p-norms with 1<=p<=infinity permitted")  # what cKDTree raises
+
+
+def knn_radius_p(points, k, p, queries=None, block=256, return_indices=False):
+    """``knn_radius`` under the Minkowski p-norm (1 <= p < inf), cKDTree's arithmetic."""
+    _check_p(p)
+    pts = _as_f64(points)
+    n = pts.shape[1]
+    if queries is None:
+        qs, kp = pts, k + 1
+    else:
+        qs, kp = _as_f64(queries), k
+    if p not in (1, 2):
+        # numpy's vectorised power is not the libm pow() scipy's C++ calls: the C restatement is
+        from . import ksg_oracle_c as oc
+        return oc.knn_radius_p(pts, kp, p, queries=qs, return_indices=return_indices)
+    nq = qs.shape[1]
+    eps = np.full(nq, np.inf)
+    idx = np.full((nq, kp), n, dtype=np.int64)
+    for b in range(0, nq, block):
+        s = _pow_dist_block(qs[:, b:b + block], pts, p)
+        if kp <= n:
+            order = np.argsort(s, axis=1, kind="stable")[:, :kp]
+            idx[b:b + block] = order
+            eps[b:b + block] = _root_p(np.take_along_axis(s, order[:, -1:], axis=1)[:, 0], p)
+    return (eps, idx) if return_indices else eps
+
+
+def count_within_p(points, eps, p, strict=True, queries=None, block=256):
+    """``count_within`` under the Minkowski p-norm: ``#{j : s_ij <= bound(r_i)} - 1`` with
+    ``r = nextafter(eps, -inf)`` when strict (knn/utils.py:75-84 with ``p`` forwarded)."""
+    _check_p(p)
+    pts = _as_f64(points)
+    qs = pts if queries is None else _as_f64(queries)
+    eps = np.asarray(eps, dtype=np.float64)
+    if p not in (1, 2):
+        from . import ksg_oracle_c as oc
+        return oc.count_within_p(pts, eps, p, strict=strict, queries=qs)
+    r = np.nextafter(eps, -np.inf) if strict else eps
+    ub = _bound_p(r, p)
+    nq = qs.shape[1]
+    out = np.empty(nq, dtype=np.int64)
+    for b in range(0, nq, block):
+        s = _pow_dist_block(qs[:, b:b + block], pts, p)
+        out[b:b + block] = (s <= ub[b:b + block][:, None]).sum(axis=1) - 1
+    return out
+
+
+def pair_count_p(u, v, r, p, block=512):
+    """``pair_count`` under the Minkowski p-norm (cKDTree.count_neighbors(.., r, p))."""
+    _check_p(p)
+    u, v = _as_f64(u), _as_f64(v)
+    if p not in (1, 2):
+        from . import ksg_oracle_c as oc
+        return oc.pair_count_p(u, v, r, p)
+    ub = float(_bound_p(r, p))
+    total = 0
+    for b in range(0, u.shape[1], block):
+        total += int((_pow_dist_block(u[:, b:b + block], v, p) <= ub).sum())
+    return total
+
+
 def knn_radius(points, k, queries=None, block=256, return_indices=False):
     """k'-th smallest Chebyshev distance from each query to the point set.
 
@@ -197,7 +321,7 @@ def differential_entropy(data, k, idxs=None, p=np.inf, noise_level=0.0, seed=0):
         # (knn/shannon.py:80); an integer copy would raise there, as it does here.
         rng = np.random.default_rng(seed)
         sub += rng.standard_normal(sub.shape) * noise_level
-    eps = knn_radius(sub, k)
+    eps = knn_radius(sub, k) if _is_inf(p) else knn_radius_p(sub, k, p)   # knn/shannon.py:82
     ptw = np.zeros((1, N))
     with np.errstate(divide="ignore"):
         ptw[0, :] += -psi_k + psi_N + d * np.log(2 * eps)
@@ -208,12 +332,13 @@ def mutual_information(idxs_x, idxs_y, k, data, algorithm=1, p=np.inf):
     """knn/shannon.py:90-134 dispatcher."""
     assert algorithm in {1, 2}, "Algorithm must be 1 or 2."
     if algorithm == 1:
-        return mutual_information_1(idxs_x, idxs_y, k, data)
-    return mutual_information_2(idxs_x, idxs_y, k, data)
+        return mutual_information_1(idxs_x, idxs_y, k, data, p=p)
+    return mutual_information_2(idxs_x, idxs_y, k, data, p=p)
 
 
-def mutual_information_1(idxs_x, idxs_y, k, data):
-    """knn/shannon.py:137-196 (KSG-1)."""
+def mutual_information_1(idxs_x, idxs_y, k, data, p=np.inf):
+    """knn/shannon.py:137-196 (KSG-1).  ``p`` reaches the marginal counts only: the joint query is
+    issued without it (:186, maximum norm), the counts forward it (:192)."""
     data = np.asarray(data)
     idxs_xy = tuple(idxs_x) + tuple(idxs_y)
     N = data.shape[1]
@@ -222,22 +347,24 @@ def mutual_information_1(idxs_x, idxs_y, k, data):
     eps = knn_radius(_rows(data, idxs_xy), k)
     ptw = np.full((1, N), psi_k + psi_N)
     for idxs in (idxs_x, idxs_y):
-        counts = count_within(_rows(data, idxs), eps)
+        counts = count_within(_rows(data, idxs), eps) if _is_inf(p) else count_within_p(_rows(data, idxs), eps, p)
         ptw[0, :] -= psi_int(counts + 1)
     return ptw, ptw.mean()
 
 
-def _ksg2_subspace_radius(sub, neighbours):
-    """eps_s = max_j<=k dist_s(i, nbr_j)  (knn/shannon.py:253-259)."""
+def _ksg2_subspace_radius(sub, neighbours, p=np.inf):
+    """eps_s = max_j<=k ||x_i - x_nbr_j||_p in the subspace, ``np.linalg.norm(.., ord=p, axis=1)``
+    (knn/shannon.py:253-259): |.|.max() for inf, sum |.| for 1, sqrt(sum .^2) for 2 (left-to-right
+    over the < 8 coordinates), (sum |.|^p)^(1/p) otherwise."""
     N = sub.shape[1]
     eps = np.full(N, -np.inf)
     for j in range(neighbours.shape[1]):
-        nb = sub[:, neighbours[:, j]]
-        eps = np.maximum(np.abs(sub - nb).max(axis=0), eps)
+        diff = (sub - sub[:, neighbours[:, j]]).T        # (N, d), as the reference forms it
+        eps = np.maximum(np.linalg.norm(diff, ord=p, axis=1), eps)
     return eps
 
 
-def mutual_information_2(idxs_x, idxs_y, k, data):
+def mutual_information_2(idxs_x, idxs_y, k, data, p=np.inf):
     """knn/shannon.py:199-265 (KSG-2).  Neighbour identity among exact distance
     ties is cKDTree-internal; this restatement breaks ties by index."""
     data = np.asarray(data)
@@ -245,13 +372,16 @@ def mutual_information_2(idxs_x, idxs_y, k, data):
     N = data.shape[1]
     psi_k = float(psi_int(k))
     psi_N = float(psi_int(N))
-    _, indices = knn_radius(_rows(data, idxs_xy), k, return_indices=True)
+    if _is_inf(p):
+        _, indices = knn_radius(_rows(data, idxs_xy), k, return_indices=True)
+    else:
+        _, indices = knn_radius_p(_rows(data, idxs_xy), k, p, return_indices=True)
     neighbours = indices[:, 1:]
     ptw = np.full((1, N), psi_k - (1 / k) + psi_N)
     for idxs in (idxs_x, idxs_y):
         sub = _as_f64(_rows(data, idxs))
-        eps = _ksg2_subspace_radius(sub, neighbours)
-        counts = count_within(sub, eps, strict=False)
+        eps = _ksg2_subspace_radius(sub, neighbours, p)
+        counts = count_within(sub, eps, strict=False) if _is_inf(p) else count_within_p(sub, eps, p, strict=False)
         ptw[0, :] -= psi_int(counts)
     return ptw, ptw.mean()
 
@@ -263,9 +393,10 @@ def conditional_mutual_information(idxs_x, idxs_y, idxs_z, k, data, p=np.inf):
     psi_k = float(psi_int(k))
     idxs_x, idxs_y, idxs_z = tuple(idxs_x), tuple(idxs_y), tuple(idxs_z)
     ptw = np.full((1, N), psi_k)
-    eps = knn_radius(_rows(data, idxs_x + idxs_y + idxs_z), k)
+    joint = _rows(data, idxs_x + idxs_y + idxs_z)
+    eps = knn_radius(joint, k) if _is_inf(p) else knn_radius_p(joint, k, p)   # :332, p forwarded
     for c, idxs in enumerate((idxs_z, idxs_x + idxs_z, idxs_y + idxs_z)):
-        counts = count_within(_rows(data, idxs), eps)
+        counts = count_within(_rows(data, idxs), eps) if _is_inf(p) else count_within_p(_rows(data, idxs), eps, p)
         if c == 0:
             ptw[0, :] += psi_int(counts + 1)
         else:
@@ -280,8 +411,12 @@ def kullback_leibler_divergence(posterior_data, prior_data, k, p=np.inf):
     assert P.shape[0] == Q.shape[0], "The data must have the same number of dimensions."
     d, n = P.shape
     m = Q.shape[1]
-    rho = knn_radius(P, k)
-    nu = knn_radius(Q, k, queries=P)
+    if _is_inf(p):
+        rho = knn_radius(P, k)
+        nu = knn_radius(Q, k, queries=P)
+    else:
+        rho = knn_radius_p(P, k, p)                # :401
+        nu = knn_radius_p(Q, k, p, queries=P)      # :402
     ptw = d * np.log(nu / rho) + np.log(m / (n - 1))
     return ptw, np.mean(ptw)
 
@@ -405,8 +540,9 @@ def sample_entropy(idx, data, m=2, r=0.2, normalize_r=True, norm=np.inf):
     big = _embed(series, m + 1, N)
     if normalize_r:
         r = r * np.std(series)
-    counts_small = pair_count(small, small, r) - N
-    counts_big = pair_count(big, big, r) - N
+    pc = pair_count if _is_inf(norm) else (lambda u, v, rr: pair_count_p(u, v, rr, norm))   # :71-72
+    counts_small = pc(small, small, r) - N
+    counts_big = pc(big, big, r) - N
     if counts_big == 0:
         return np.inf
     return -np.log(counts_big / counts_small)
@@ -424,8 +560,9 @@ def cross_sample_entropy(idx_x, idx_y, data, m=2, r=0.2, norm=np.inf):
     N = data.shape[1] - m
     sx = zscore(data[idx_x[0], :])
     sy = zscore(data[idx_y[0], :])
-    B = pair_count(_embed(sx, m, N), _embed(sy, m, N), r)
-    A = pair_count(_embed(sx, m + 1, N), _embed(sy, m + 1, N), r)
+    pc = pair_count if _is_inf(norm) else (lambda u, v, rr: pair_count_p(u, v, rr, norm))   # :142-143
+    B = pc(_embed(sx, m, N), _embed(sy, m, N), r)
+    A = pc(_embed(sx, m + 1, N), _embed(sy, m + 1, N), r)
     if A == 0:
         return np.inf
     return -np.log(A / B)

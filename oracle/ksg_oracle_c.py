@@ -63,3 +63,39 @@ def pair_counts(x, y, m, r):
     out = np.zeros(2, dtype=np.int64)
     load().oracle_pair_count(_p(x), _p(y), C.c_int64(nt), C.c_int(m), C.c_double(r), _p(out))
     return int(out[0]), int(out[1])
+
+
+def knn_radius_p(points, kprime, p, queries=None, return_indices=False):
+    """kprime-th smallest Minkowski-p distance (1 <= p < inf) of each query to the points."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    qs = pts if queries is None else np.ascontiguousarray(queries, dtype=np.float64)
+    dim, n = pts.shape
+    nq = qs.shape[1]
+    out = np.empty(nq)
+    idx = np.empty((nq, kprime), dtype=np.int64) if return_indices else None
+    load().oracle_knn_radius_p(_p(pts), C.c_int64(n), C.c_int64(n), C.c_int(dim), _p(qs), C.c_int64(nq),
+                               C.c_int64(nq), C.c_int(kprime), C.c_double(float(p)), _p(out),
+                               _p(idx) if return_indices else None)
+    return (out, idx) if return_indices else out
+
+
+def count_within_p(points, eps, p, strict=True, queries=None, bias=-1):
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    qs = pts if queries is None else np.ascontiguousarray(queries, dtype=np.float64)
+    eps = np.ascontiguousarray(eps, dtype=np.float64)
+    dim, n = pts.shape
+    nq = qs.shape[1]
+    out = np.empty(nq, dtype=np.int64)
+    load().oracle_count_within_p(_p(pts), C.c_int64(n), C.c_int64(n), C.c_int(dim), _p(qs), C.c_int64(nq),
+                                 C.c_int64(nq), _p(eps), C.c_int(1 if strict else 0), C.c_int64(bias),
+                                 C.c_double(float(p)), _p(out))
+    return out
+
+
+def pair_count_p(u, v, r, p):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    fn = load().oracle_pair_count_p
+    fn.restype = C.c_int64
+    return int(fn(_p(u), C.c_int64(u.shape[1]), C.c_int64(u.shape[1]), _p(v), C.c_int64(v.shape[1]),
+                  C.c_int64(v.shape[1]), C.c_int(u.shape[0]), C.c_double(float(r)), C.c_double(float(p))))

@@ -7,11 +7,15 @@
    container (tests/golden/make_golden.py): radii and counts bit-exact, pointwise
    values bit-exact (same fp64 op order), averages to 1e-13.
 """
+import os
+
 import numpy as np
 import pytest
 
 from oracle import ksg_oracle as orc
 from syntropy_b200 import workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 REL = 1e-6  # the reference's own tolerance (tests/test_knn.py:18)
 
@@ -240,3 +244,48 @@ def test_mixed_knn_branch_vs_reference_golden(golden):
             ptw, avg = orc.mixed_mutual_information(d, c, k)
             assert same(ptw, g[f"{name}_mi_ptw"])
             assert avg == pytest.approx(g[f"{name}_mi_avg"], rel=1e-13) or same(avg, g[f"{name}_mi_avg"])
+
+
+# ------------------------------------------------------------------ Minkowski p
+def _minkowski_inputs():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.minkowski_cases()
+
+
+def test_oracle_minkowski_p_vs_reference_golden(golden):
+    """p = 1 and p = 2 (cKDTree's p-th-power-space arithmetic incl. the four-way unrolled sum of
+    squares) and p = 3 (libm pow through the C restatement) reproduce the unmodified reference bit
+    for bit: radii, strict / closed counts, every estimator that takes ``p`` / ``norm``, tied data."""
+    g = golden("minkowski")
+    cont, tied, post, prior, series = _minkowski_inputs()
+    with np.errstate(all="ignore"):
+        for p in (1, 2, 3):
+            t = f"p{p}"
+            eps = orc.knn_radius_p(cont[(0, 1, 2), :], 4, p)
+            assert np.array_equal(eps, g[f"{t}_eps"])
+            assert np.array_equal(orc.count_within_p(cont[(0, 1), :], eps, p), g[f"{t}_counts_strict"])
+            assert np.array_equal(orc.count_within_p(cont[(0, 1), :], eps, p, strict=False), g[f"{t}_counts_closed"])
+            ptw, avg = orc.differential_entropy(cont, 4, idxs=(0, 2, 5), p=p)
+            assert np.array_equal(ptw, g[f"{t}_entropy_ptw"]) and avg == g[f"{t}_entropy_avg"]
+            for alg in (1, 2):
+                ptw, avg = orc.mutual_information((0, 1), (2, 3), 4, cont, algorithm=alg, p=p)
+                assert np.array_equal(ptw, g[f"{t}_mi{alg}_ptw"]), (p, alg)
+                assert avg == g[f"{t}_mi{alg}_avg"]
+            ptw, avg = orc.mutual_information((0,), (1,), 3, cont, algorithm=1, p=p)
+            assert np.array_equal(ptw, g[f"{t}_mi1_1d_ptw"])
+            ptw, avg = orc.conditional_mutual_information((0, 1), (2,), (3, 4), 3, cont, p=p)
+            assert np.array_equal(ptw, g[f"{t}_cmi_ptw"]) and avg == g[f"{t}_cmi_avg"]
+            ptw, avg = orc.kullback_leibler_divergence(post, prior, 3, p=p)
+            assert np.array_equal(ptw, g[f"{t}_kl_ptw"]) and avg == g[f"{t}_kl_avg"]
+            se = np.array([orc.sample_entropy((c,), series, m=2, r=0.3, norm=p) for c in range(2)])
+            assert np.array_equal(se, g[f"{t}_sampen"])
+            assert orc.cross_sample_entropy((0,), (1,), series, m=2, r=0.35, norm=p) == g[f"{t}_cross_sampen"]
+            if p != 3:
+                ptw, avg = orc.mutual_information((0, 1), (2,), 3, tied, algorithm=1, p=p)
+                assert np.array_equal(ptw, g[f"{t}_tied_mi1_ptw"], equal_nan=True)
+                ptw, avg = orc.conditional_mutual_information((0,), (1,), (2, 3), 2, tied, p=p)
+                assert np.array_equal(ptw, g[f"{t}_tied_cmi_ptw"], equal_nan=True)   # (psi(0) - psi(0) = nan)
