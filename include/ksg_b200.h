@@ -380,6 +380,15 @@ int ksg_gather_f64(const double* d_src, const int32_t* d_perm, int64_t n, double
  * windowed form of cKDTree.count_neighbors(self, r) (syntropy/knn/temporal.py:71-72). */
 int ksg_sum_i32(const int32_t* d_values, int64_t n, unsigned long long* d_out, void* stream);
 
+/* The key sort ksg_prepare is built on (argsort of one coordinate; reference: the ordering work
+ * cKDTree's constructor does at syntropy/knn/utils.py:29): d_keys_out = the n float64 keys ascending,
+ * d_index_out = their positions in d_keys_in, ties in position order (a stable sort).
+ * n <= 2^21: five-launch sample sort (csrc/sample_sort.cuh); above, or with algorithm = 1:
+ * cub::DeviceRadixSort.  algorithm: 0 = default, 1 = radix sort.  Workspace: ksg_sort_workspace(n). */
+size_t ksg_sort_workspace(int64_t n);
+int ksg_sort_f64(const double* d_keys_in, int64_t n, double* d_keys_out, int32_t* d_index_out, int algorithm,
+                 void* d_workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

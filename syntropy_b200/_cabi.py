@@ -114,6 +114,8 @@ SIGNATURES = {
     "ksg_scatter_i32": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_gather_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_sum_i32": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_vp]),
+    "ksg_sort_workspace": (C.c_size_t, [_c_i64]),
+    "ksg_sort_f64": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, C.c_int, _c_vp, C.c_size_t, _c_vp]),
 }
 
 _lib = None

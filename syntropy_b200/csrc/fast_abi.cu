@@ -13,6 +13,7 @@
 #include "fast_knn.cuh"
 #include "fast_launch.h"
 #include "prepare.cuh"
+#include "sample_sort.cuh"
 
 namespace ksg {
 
@@ -28,7 +29,13 @@ static inline size_t cub_sort_bytes_query(int64_t n) {
 }
 
 // (the size query walks CUB's whole dispatch on the host: remember the last few answers)
+static inline size_t cub_sort_bytes_cached(int64_t n);
+// scratch of one key sort: whichever of the two implementations runs (sample_sort.cuh / CUB)
 static inline size_t cub_sort_bytes(int64_t n) {
+    const size_t a = cub_sort_bytes_cached(n), b = n <= SS_MAX_N ? ss_layout(n).total : 0;
+    return a > b ? a : b;
+}
+static inline size_t cub_sort_bytes_cached(int64_t n) {
     static std::mutex mu;
     static int64_t seen_n[8];
     static size_t seen_bytes[8];
@@ -250,8 +257,33 @@ static inline GraphKey graph_key(int kind, std::initializer_list<const void*> pt
 
 static inline cudaStream_t as_stream2(void* s) { return (cudaStream_t)s; }
 
+// KSG_B200_SORT=cub keeps every key sort on cub::DeviceRadixSort (A/B measurements, cross-checks)
+static bool use_sample_sort(int64_t n) {
+    static const bool off = [] {
+        const char* e = getenv("KSG_B200_SORT");
+        return e && e[0] == 'c';
+    }();
+    return !off && n <= SS_MAX_N;
+}
+
+// (key, position) pairs by sample sort; `tmp` holds cub_sort_bytes(n)
+template <class KeyT>
+static int sample_sort_launch(void* tmp, const KeyT* keys_in, KeyT* keys_out, int32_t* idx_out, int64_t n,
+                              cudaStream_t st) {
+    int launches = 0;
+    const cudaError_t e = sample_sort_pairs<KeyT>(tmp, keys_in, keys_out, idx_out, n, st, &launches);
+    note_launches(launches);
+    if (e != cudaSuccess) {
+        set_error("sample sort: %s", cudaGetErrorString(e));
+        return KSG_ECUDA;
+    }
+    return KSG_OK;
+}
+
+// keys + the positions 0..n-1 (`vals_in` = iota) by key, stable
 static int sort_pairs(void* cub_tmp, size_t cub_bytes, const double* keys_in, double* keys_out,
                       const int32_t* vals_in, int32_t* vals_out, int64_t n, cudaStream_t st) {
+    if (use_sample_sort(n)) return sample_sort_launch<double>(cub_tmp, keys_in, keys_out, vals_out, n, st);
     size_t need = cub_bytes;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, keys_in, keys_out, vals_in, vals_out, (int)n, 0,
                                                     64, st);
@@ -464,11 +496,16 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 default: morton_key_kernel<0><<<nb, 256, 0, st>>>(ranks, L.ld, n, dim, rank_bits, bits, mkeys);
             }
             KSG_LAUNCHED2();
-            size_t need = L.cub_bytes;
-            cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, iota, P.perm, (int)n, 0,
-                                                            bits * dim, st);
-            if (e != cudaSuccess) { set_error("cub SortPairs (morton): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
-            note_launch();
+            if (use_sample_sort(n)) {
+                const int rc2 = sample_sort_launch<unsigned long long>(cub_tmp, mkeys, mkeys_out, P.perm, n, st);
+                if (rc2) return rc2;
+            } else {
+                size_t need = L.cub_bytes;
+                cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, iota, P.perm, (int)n, 0,
+                                                                bits * dim, st);
+                if (e != cudaSuccess) { set_error("cub SortPairs (morton): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+                note_launch();
+            }
         }
         gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
             d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
@@ -649,11 +686,16 @@ int ksg_cross_prepare(const ksg_prepared* P, const double* d_queries, int64_t ld
         default: cross_key_kernel<0><<<nb, 256, 0, st>>>(d_queries, ldq, nq, P->axis_vals, P->ld, P->n, dim, rank_bits, bits, keys, iota);
     }
     KSG_LAUNCHED2();
-    size_t need = L.cub_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(base + L.off_cub, need, keys, keys_out, iota, X.perm, (int)nq, 0,
-                                                    bits * dim, st);
-    if (e != cudaSuccess) { set_error("cub SortPairs (cross): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
-    note_launch();
+    if (use_sample_sort(nq)) {
+        const int rc2 = sample_sort_launch<unsigned long long>(base + L.off_cub, keys, keys_out, X.perm, nq, st);
+        if (rc2) return rc2;
+    } else {
+        size_t need = L.cub_bytes;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(base + L.off_cub, need, keys, keys_out, iota, X.perm, (int)nq, 0,
+                                                        bits * dim, st);
+        if (e != cudaSuccess) { set_error("cub SortPairs (cross): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+        note_launch();
+    }
     cross_gather_kernel<<<nb, 256, 0, st>>>(d_queries, ldq, nq, dim, P->dim_padded, X.perm, keys_out, P->center,
                                             (const unsigned long long*)P->curve_keys, P->n, X.sorted_f64, L.ld,
                                             X.shadow_f32, X.home);
@@ -886,6 +928,38 @@ int ksg_sum_i32(const int32_t* d_values, int64_t n, unsigned long long* d_out, v
     if (blocks > 4096) blocks = 4096;
     sum_i32_kernel<<<(unsigned)blocks, 256, 0, as_stream2(stream)>>>(d_values, n, d_out);
     KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+size_t ksg_sort_workspace(int64_t n) {
+    if (n <= 0) return 0;
+    return align_up(cub_sort_bytes(n), 256) + align_up((size_t)n * 4, 256);
+}
+
+int ksg_sort_f64(const double* d_keys_in, int64_t n, double* d_keys_out, int32_t* d_index_out, int algorithm,
+                 void* d_workspace, size_t workspace_bytes, void* stream) {
+    KSG_REQUIRE(d_keys_in && d_keys_out && d_index_out && d_workspace, "ksg_sort_f64: null pointer");
+    KSG_REQUIRE(n > 0 && n < (1ll << 31) - 1024, "ksg_sort_f64: need 0 < n < 2^31");
+    KSG_REQUIRE(algorithm == 0 || algorithm == 1, "ksg_sort_f64: algorithm must be 0 (default) or 1 (radix sort)");
+    if (workspace_bytes < ksg_sort_workspace(n)) {
+        set_error("ksg_sort_f64: workspace of %zu bytes needed, %zu given", ksg_sort_workspace(n), workspace_bytes);
+        return KSG_EWORKSPACE;
+    }
+    cudaStream_t st = as_stream2(stream);
+    const size_t sort_bytes = align_up(cub_sort_bytes(n), 256);
+    if (algorithm == 0 && use_sample_sort(n))
+        return sample_sort_launch<double>(d_workspace, d_keys_in, d_keys_out, d_index_out, n, st);
+    int32_t* iota = (int32_t*)((char*)d_workspace + sort_bytes);
+    iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
+    KSG_LAUNCHED2();
+    size_t need = sort_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(d_workspace, need, d_keys_in, d_keys_out, iota, d_index_out, (int)n,
+                                                    0, 64, st);
+    if (e != cudaSuccess) {
+        set_error("cub::DeviceRadixSort::SortPairs: %s", cudaGetErrorString(e));
+        return KSG_ECUDA;
+    }
+    note_launch();
     return KSG_OK;
 }
 
