@@ -331,9 +331,10 @@ struct FastKnnPlan {
     int64_t qblocks, max_units, plan_capacity;
     size_t d32_bytes, idx_bytes;
     // windowed engine: planning pass + unit table
-    size_t seed_bytes, plan_bytes, count_bytes, first_bytes, ublock_bytes, meta_bytes;
+    size_t seed_bytes, plan_bytes, count_bytes, first_bytes, ublock_bytes, meta_bytes, done_bytes;
     size_t total() const {
-        return d32_bytes + idx_bytes + seed_bytes + plan_bytes + count_bytes + first_bytes + ublock_bytes + meta_bytes;
+        return d32_bytes + idx_bytes + seed_bytes + plan_bytes + count_bytes + first_bytes + ublock_bytes + meta_bytes +
+               done_bytes;
     }
 };
 static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int windowed, int margin = KNN_MARGIN) {
@@ -358,6 +359,7 @@ static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int
         p.first_bytes = align_up((size_t)(p.qblocks + 1) * sizeof(int32_t), 256);
         p.ublock_bytes = align_up((size_t)p.max_units * sizeof(int32_t), 256);
         p.meta_bytes = 256;
+        p.done_bytes = align_up((size_t)p.qblocks * sizeof(int32_t), 256);
     } else {
         // partial lists per candidate split: [split][rank][nq]
         p.splits = choose_splits(p.qblocks, n, FAST_TILE);
@@ -585,7 +587,7 @@ int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, c
     a.tile_counter = (unsigned long long*)((char*)P->flags + 16);
     a.st = st;
     a.seed_thr = nullptr; a.plan = nullptr; a.plan_count = nullptr; a.plan_first = nullptr; a.plan_capacity = 0;
-    a.unit_first = nullptr; a.unit_block = nullptr; a.unit_meta = nullptr; a.max_units = 0;
+    a.unit_first = nullptr; a.unit_block = nullptr; a.unit_meta = nullptr; a.unit_done = nullptr; a.max_units = 0;
     fill_refine_args(a, P, kprime, nullptr, 0, P->maxabs, d_idx_out, d_eps_out, d_flags, d_n_flagged);
     int rc;
     if (a.windowed) {
@@ -598,11 +600,13 @@ int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, c
         a.plan_first = (int32_t*)w;                  w += p.count_bytes / 2;
         a.unit_first = (int32_t*)w;                  w += p.first_bytes;
         a.unit_block = (int32_t*)w;                  w += p.ublock_bytes;
-        a.unit_meta = (int32_t*)w;
+        a.unit_meta = (int32_t*)w;                   w += p.meta_bytes;
+        a.unit_done = (int32_t*)w;
         a.max_units = p.max_units;
         rc = launch_knn_plan(P->dim_padded, a);
         if (rc) return rc;
         rc = launch_knn_units(P->dim_padded, a);
+        if (rc || a.ra.fused) return rc;  // fused: every block was refined inside the units kernel
     } else {
         rc = launch_knn_f32(P->dim_padded, a);
     }
@@ -611,8 +615,7 @@ int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, c
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    d_query_index, P->maxabs, a.seed_thr, a.unit_first,
                                                                    p.qb, P->perm, d_idx_out, nullptr, 0, P->center,
-                                                                   d_eps_out, d_flags, d_n_flagged,
-                                                                   a.windowed && a.ra.fused);
+                                                                   d_eps_out, d_flags, d_n_flagged);
     KSG_LAUNCHED2();
     return KSG_OK;
 }
@@ -744,18 +747,19 @@ int ksg_fast_knn_cross(const ksg_prepared* P, const ksg_cross* X, int64_t q_begi
     a.plan_first = (int32_t*)w;                  w += p.count_bytes / 2;
     a.unit_first = (int32_t*)w;                  w += p.first_bytes;
     a.unit_block = (int32_t*)w;                  w += p.ublock_bytes;
-    a.unit_meta = (int32_t*)w;
+    a.unit_meta = (int32_t*)w;                   w += p.meta_bytes;
+    a.unit_done = (int32_t*)w;
     a.max_units = p.max_units;
     fill_refine_args(a, P, kprime, X->sorted_f64, X->ld, X->maxabs, nullptr, d_eps_out, d_flags, d_n_flagged);
     int rc = launch_knn_plan(P->dim_padded, a);
     if (rc) return rc;
     rc = launch_knn_units(P->dim_padded, a);
-    if (rc) return rc;
+    if (rc || a.ra.fused) return rc;
     knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, 1, kprime,
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    nullptr, X->maxabs, a.seed_thr, a.unit_first, p.qb,
                                                                    P->perm, nullptr, X->sorted_f64, X->ld, P->center,
-                                                                   d_eps_out, d_flags, d_n_flagged, a.ra.fused);
+                                                                   d_eps_out, d_flags, d_n_flagged);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

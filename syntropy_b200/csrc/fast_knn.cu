@@ -51,7 +51,7 @@ static int launch_plan_kc(const KnnF32Args& a) {
     if (cudaMemsetAsync(a.unit_meta, 0, 32, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
     kern<<<(unsigned)ceil_div(a.nq, FAST_THREADS * Q), FAST_THREADS, smem, a.st>>>(
         a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.kseed, a.maxabs, a.dim, a.qshadow, a.qhome, a.seed_thr, (int2*)a.plan,
-        a.plan_capacity, a.plan_count, a.plan_first, a.unit_meta);
+        a.plan_capacity, a.plan_count, a.plan_first, a.unit_meta, a.unit_done);
     note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_plan_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
@@ -81,7 +81,7 @@ static int launch_units_dp(const KnnF32Args& a) {
     if (grid > a.max_units) grid = a.max_units;
     kern<<<(unsigned)grid, UNITS_THREADS, smem, a.st>>>(a.shadow, a.sub_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.qshadow, a.qhome, a.seed_thr,
                                                        (const int2*)a.plan, a.plan_count, a.plan_first, a.unit_first, a.unit_block,
-                                                       a.unit_meta, a.part_d32, a.part_idx, a.tile_counter, a.ra);
+                                                       a.unit_meta, a.part_d32, a.part_idx, a.tile_counter, a.unit_done, a.ra);
     note_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_units_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }

@@ -144,7 +144,8 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
                 int64_t q_begin, int64_t nq, int kcap, int kseed, const double* __restrict__ maxabs, int dim,
                 const float* __restrict__ qshadow, const int32_t* __restrict__ qhome,
                 float* __restrict__ seed_thr, int2* __restrict__ plan, int64_t plan_capacity,
-                int32_t* __restrict__ plan_count, int32_t* __restrict__ plan_first, int32_t* __restrict__ meta) {
+                int32_t* __restrict__ plan_count, int32_t* __restrict__ plan_first, int32_t* __restrict__ meta,
+                int32_t* __restrict__ unit_done) {
     // kseed: rank of the seed distance.  kseed == kcap (legacy): the seed is the kcap-th smallest
     // distance of the window, one ulp up -- the window's own rows fill the list.  kseed == k' <
     // kcap (tight): the seed is the k'-th smallest window distance s plus the width of the refine
@@ -166,15 +167,35 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
     const int64_t qb0 = (int64_t)blockIdx.x * QB;
     (void)maxabs; (void)dim;
     const int64_t n_rows = n_tiles * FAST_TILE;
+    if (tid == 0 && unit_done) unit_done[blockIdx.x] = 0;  // finished work units of this block (knn_units_kernel)
 
     // ---- pass 1: seed every query's threshold from its neighbours in the prepared order
     float blo[DP], bhi[DP];
 #pragma unroll
     for (int d = 0; d < DP; ++d) { blo[d] = CUDART_INF_F; bhi[d] = -CUDART_INF_F; }
     float sum = 0.0f, cnt = 0.0f;
+    // Within-set searches with register-resident seed lists read their window from shared memory: the
+    // rows [first query - W, last query + W] of the block are staged by one coalesced sweep, and the
+    // 2 W candidate rows of every query come from there instead of 2 W dependent L1 / L2 round trips.
+    constexpr int WIN_ROWS = FAST_THREADS + 2 * KNN_SEED_W;
+    __shared__ __align__(16) float s_win[KC > 0 ? WIN_ROWS * DP : 1];
+    const bool staged = KC > 0 && !qhome && !qshadow;
 #pragma unroll 1
     for (int j = 0; j < Q; ++j) {
         const int64_t qi = qb0 + j * FAST_THREADS + tid;
+        if constexpr (KC > 0) {
+            if (staged) {
+                if (j > 0) __syncthreads();  // the previous slot's reads are done
+                const int64_t base_row = q_begin + qb0 + (int64_t)j * FAST_THREADS - KNN_SEED_W;
+                for (int i = tid; i < WIN_ROWS * (DP / 2); i += FAST_THREADS) {
+                    const int64_t r2 = base_row + i / (DP / 2);
+                    float2 v = make_float2(CUDART_INF_F, CUDART_INF_F);  // rows that do not exist: never a seed
+                    if (r2 >= 0 && r2 < n_rows) v = reinterpret_cast<const float2*>(shadow)[r2 * (DP / 2) + i % (DP / 2)];
+                    reinterpret_cast<float2*>(s_win)[i] = v;
+                }
+                __syncthreads();
+            }
+        }
         if (qi >= nq) continue;
         float2 q[DP / 2];
         load_row<DP>(qrows + (q_begin + qi) * DP, q);
@@ -190,6 +211,20 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
             float dl[KC];
 #pragma unroll
             for (int r = 0; r < KC; ++r) dl[r] = CUDART_INF_F;
+            if (staged) {
+                const float* mine = s_win + (tid + KNN_SEED_W) * DP;  // this query's own row
+#pragma unroll 4
+                for (int off = 1; off <= KNN_SEED_W; ++off)
+#pragma unroll
+                    for (int sgn = -1; sgn <= 1; sgn += 2) {
+                        float2 cc[DP / 2];
+                        load_row<DP>(mine + sgn * off * DP, cc);
+                        const float m = cheb32<DP>(q, cc);  // +inf for the rows that do not exist
+#pragma unroll
+                        for (int r = KC - 1; r > 0; --r) dl[r] = fminf(dl[r], fmaxf(dl[r - 1], m));
+                        dl[0] = fminf(dl[0], m);
+                    }
+            } else {
 #pragma unroll 2
             for (int off = 1; off <= KNN_SEED_W; ++off)
 #pragma unroll
@@ -203,6 +238,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
                     for (int r = KC - 1; r > 0; --r) dl[r] = fminf(dl[r], fmaxf(dl[r - 1], m));
                     dl[0] = fminf(dl[0], m);
                 }
+            }
 #pragma unroll
             for (int r = 0; r < KC; ++r)
                 if (r == kseed - 1) thr = dl[r];
@@ -645,6 +681,12 @@ constexpr int UNITS_THREADS = FAST_THREADS + 32;  // 4 filter warps + 1 copy war
 
 static __device__ void refine_single_list(const float* col_d, const int32_t* col_i, int stride, int kcap, float seed,
                                    int64_t row_q, int64_t qi, const RefineArgs& ra);
+static __device__ void refine_merge_lists(const float* part_d32, const int32_t* part_idx, int kcap, int s_begin,
+                                          int s_end, int64_t stride, int64_t off, bool has_seed, float seed,
+                                          int64_t row_q, int64_t qi, const RefineArgs& ra);
+__device__ __forceinline__ void filter_warps_barrier() {  // the four filter warps only (the copy warp is elsewhere)
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
 
 // Persistent filter kernel of the windowed engine: CTAs pull work units from a global cursor.
 //
@@ -680,7 +722,8 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
                  const int32_t* __restrict__ plan_first, const int32_t* __restrict__ unit_first,
                  const int32_t* __restrict__ unit_block, int32_t* __restrict__ meta, float* __restrict__ part_d32,
                  int32_t* __restrict__ part_idx, unsigned long long* __restrict__ pair_counter,
-                 const __grid_constant__ RefineArgs ra) {
+                 int32_t* __restrict__ unit_done, const __grid_constant__ RefineArgs ra) {
+    static_assert(FAST_THREADS == 128, "filter_warps_barrier() counts 128 threads");
     constexpr int QB = FAST_THREADS * Q;
     constexpr int TILE_FLOATS = FAST_TILE * DP;
     constexpr int BOX_FLOATS = FAST_NSUB * DP * 2;
@@ -691,6 +734,7 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
     int32_t* lst_i = reinterpret_cast<int32_t*>(lst_d + (size_t)kcap * QB);  // kcap * QB
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
     __shared__ int s_unit;
+    __shared__ int s_last;                // this CTA finished the last open unit of its block
     __shared__ int s_tile[STAGES];        // tile staged in each ring slot (-1: end of the unit)
     __shared__ float s_wthr[FAST_THREADS / 32];  // largest threshold of each filter warp
 
@@ -727,8 +771,11 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
         const int last = first + chunk < count ? first + chunk : count;
         const int64_t qb0 = qblock * QB;
         const int pfirst = plan_first[qblock];
-        // a block whose whole tile list is this one unit is refined right here, from shared memory
-        const bool refine_here = ra.fused && unit_first[qblock + 1] - unit_first[qblock] == 1;
+        // a block whose whole tile list is this one unit is refined right here, from shared memory;
+        // the units of a longer list emit partial lists, and whoever finishes the LAST of them merges
+        const int ufirst = unit_first[qblock];
+        const int nunits = unit_first[qblock + 1] - ufirst;
+        const bool refine_here = ra.fused && nunits == 1;
 
         // ---------------- filter warps: queries, thresholds, warp box, empty lists
         // slot j of this thread = query qb0 + warp*32*Q + j*32 + lane
@@ -973,6 +1020,25 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
                 part_idx[o] = lst_i[(size_t)r * QB + col];
             }
         }
+        if (ra.fused && !refine_here) {
+            // last-unit-done merge: the lists above are published (fence), the block's counter is
+            // bumped once per unit, and the CTA that brings it to nunits reads everybody's lists
+            __threadfence();
+            filter_warps_barrier();
+            if (tid == 0) s_last = atomicAdd(&unit_done[qblock], 1) == nunits - 1;
+            filter_warps_barrier();
+            if (s_last) {
+                __threadfence();
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    const int lq = warp * (32 * Q) + j * 32 + lane;
+                    if (alive[j])
+                        refine_merge_lists(part_d32, part_idx, kcap, ufirst, ufirst + nunits, QB, lq, true,
+                                           seed[j] < 0.0f ? -1.0f : seed_thr[qb0 + lq], q_begin + qb0 + lq,
+                                           qb0 + lq, ra);
+                }
+            }
+        }
     }
     if (!producer && lane == 0 && pair_counter && subtiles_total)
         atomicAdd(pair_counter, subtiles_total * (unsigned long long)(FAST_SUB * 32 * Q));
@@ -982,60 +1048,42 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
 constexpr int REFINE_CAP = 96;  // union entries examined per query
 constexpr int REFINE_BATCH = 8;  // list heads / tails fetched together
 
-static __global__ void __launch_bounds__(128)
-knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict__ part_idx, int kcap, int splits,
-                  int kp, const double* __restrict__ sorted, int64_t ld, int dim, int64_t n, int64_t q_begin,
-                  int64_t nq, const int32_t* __restrict__ q_index, const double* __restrict__ maxabs,
-                  const float* __restrict__ seed_thr, const int32_t* __restrict__ unit_first, int qb,
-                  const int32_t* __restrict__ perm, int64_t* __restrict__ idx_out,
-                  const double* __restrict__ qsorted, int64_t qld, const double* __restrict__ center,
-                  double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged,
-                  int skip_single) {
-    // skip_single: blocks that own exactly one work unit were already refined inside
-    // knn_units_kernel (RefineArgs::fused); only the multi-unit blocks are merged here.
-    // qsorted (optional, cross-set search): the float64 query coordinates come from this [dim][qld]
-    // array (rows q_begin + qi) instead of the candidate set itself.
-    // idx_out (optional, [nq][kp] int64): the k' nearest points as positions in the prepared
-    // order, ascending by (exact distance, original sample index) -- the order the dense float64
-    // kernel's merge produces.  All points tied with the k'-th distance are among the examined
-    // candidates whenever the query is not flagged, so the tie-break is well defined.
-    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= nq) return;
-    if (skip_single && unit_first) {
-        const int64_t b = qi / qb;
-        if (unit_first[b + 1] - unit_first[b] == 1) return;
-    }
-    if (seed_thr && seed_thr[qi] < 0.0f) {  // taken out by the planning pass: needs the dense launch
-        flags[qi] = 2;
-        atomicAdd(n_flagged, 1);
-        eps_out[qi] = CUDART_NAN;
+// loads of the partial lists: L2 only.  Inside knn_units_kernel they were written by OTHER CTAs of
+// the same launch (last-unit-done merge), which the per-SM L1 knows nothing about.
+#ifdef __CUDA_ARCH__
+#define KSG_LD_PART(ptr) __ldcg(ptr)
+#else
+#define KSG_LD_PART(ptr) (*(ptr))
+#endif
+
+// Merge the ascending lists [s_begin, s_end) of one query (entry (s, r) at ((s * kcap + r) * stride +
+// off)) and decide its exact radius; see the file header.  has_seed: `seed` is the threshold the
+// windowed filter ran under (< 0: the planning pass set the query aside).
+static __device__ __noinline__ void refine_merge_lists(const float* part_d32, const int32_t* part_idx, int kcap,
+                                                       int s_begin, int s_end, int64_t stride, int64_t off,
+                                                       bool has_seed, float seed, int64_t row_q, int64_t qi,
+                                                       const RefineArgs& ra) {
+    const int kp = ra.kp, dim = ra.dim;
+    const double* sorted = ra.sorted;
+    const int64_t ld = ra.ld;
+    if (has_seed && seed < 0.0f) {  // taken out by the planning pass: needs the dense launch
+        ra.flags[qi] = 2;
+        atomicAdd(ra.n_flagged, 1);
+        ra.eps_out[qi] = CUDART_NAN;
         return;
     }
-    // list s, rank r of this query sits at ((s * kcap + r) * stride + off):
-    //   dense launch   : s = candidate split,  [split][rank][nq]
-    //   windowed launch: s = work unit of the query's block,  [unit][rank][QB]
-    int s_begin = 0, s_end = splits;
-    int64_t stride = nq, off = qi;
-    if (unit_first) {
-        const int64_t b = qi / qb;
-        s_begin = unit_first[b];
-        s_end = unit_first[b + 1];
-        stride = qb;
-        off = qi - b * qb;
-    }
-    const int64_t row_q = q_index ? (int64_t)q_index[qi] : q_begin + qi;
-    if (maxabs && !fp32_range_ok(maxabs, dim)) {  // shadow rows may have overflowed: float64 kernels
-        flags[qi] = 1;
-        atomicAdd(n_flagged, 1);
-        eps_out[qi] = CUDART_NAN;
+    if (ra.maxabs && !fp32_range_ok(ra.maxabs, dim)) {  // shadow rows may have overflowed: float64 kernels
+        ra.flags[qi] = 1;
+        atomicAdd(ra.n_flagged, 1);
+        ra.eps_out[qi] = CUDART_NAN;
         return;
     }
     // the query's own magnitude in the centred frame bounds the fp32 error of all its near pairs
     double qc[KSG_MAX_DIM];
     double mq = 0.0;
     for (int d = 0; d < dim; ++d) {
-        qc[d] = qsorted ? qsorted[(int64_t)d * qld + row_q] : sorted[(int64_t)d * ld + row_q];
-        mq = fmax(mq, fabs(qc[d] - center[d]));
+        qc[d] = ra.qsorted ? ra.qsorted[(int64_t)d * ra.qld + row_q] : sorted[(int64_t)d * ld + row_q];
+        mq = fmax(mq, fabs(qc[d] - ra.center[d]));
     }
     mq = mq * (1.0 + 1e-6) + 1e-300;
 
@@ -1049,14 +1097,14 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
         float head[REFINE_BATCH];
 #pragma unroll
         for (int u = 0; u < REFINE_BATCH; ++u)
-            head[u] = s0 + u < s_end ? part_d32[((int64_t)(s0 + u) * kcap) * stride + off] : CUDART_INF_F;
+            head[u] = s0 + u < s_end ? KSG_LD_PART(&part_d32[((int64_t)(s0 + u) * kcap) * stride + off]) : CUDART_INF_F;
 #pragma unroll
         for (int u = 0; u < REFINE_BATCH; ++u) {
             const int s = s0 + u;
             if (s >= s_end) break;
             if (have == kp && !(head[u] < best[kp - 1])) continue;  // ascending list: nothing in it counts
             for (int r = 0; r < kcap; ++r) {
-                const float v = r == 0 ? head[u] : part_d32[((int64_t)s * kcap + r) * stride + off];
+                const float v = r == 0 ? head[u] : KSG_LD_PART(&part_d32[((int64_t)s * kcap + r) * stride + off]);
                 if (have == kp && !(v < best[kp - 1])) break;
                 int pos = have < kp ? have : kp - 1;
                 while (pos > 0 && best[pos - 1] > v) { best[pos] = best[pos - 1]; --pos; }
@@ -1067,16 +1115,16 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     }
     const double r32 = (have == kp) ? (double)best[kp - 1] : CUDART_INF;
     if (!(r32 < CUDART_INF)) {  // fewer than k' points exist (k+1 > n): cKDTree pads with inf
-        eps_out[qi] = CUDART_INF;
-        flags[qi] = idx_out ? 1 : 0;  // neighbour identities: leave it to the dense float64 kernel
-        if (idx_out) atomicAdd(n_flagged, 1);
+        ra.eps_out[qi] = CUDART_INF;
+        ra.flags[qi] = ra.idx_out ? 1 : 0;  // neighbour identities: leave it to the dense float64 kernel
+        if (ra.idx_out) atomicAdd(ra.n_flagged, 1);
         return;
     }
     const double delta = band_query_f64(mq, 2.0 * r32);
     const double T = r32 + 2.0 * delta;
 
     // a list that is not full holds everything below the seeded threshold -- and nothing above it
-    bool overflow = seed_thr && !(T < (double)seed_thr[qi]);
+    bool overflow = has_seed && !(T < (double)seed);
     double exact[KNN_MAX_KCAP];
     int32_t exact_j[KNN_MAX_KCAP], exact_o[KNN_MAX_KCAP];  // prepared position / original index (idx_out only)
     int got = 0, examined = 0;
@@ -1085,8 +1133,8 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
 #pragma unroll
       for (int u = 0; u < REFINE_BATCH; ++u) {
           const bool in = s0 + u < s_end;
-          head[u] = in ? part_d32[((int64_t)(s0 + u) * kcap) * stride + off] : CUDART_INF_F;
-          tails[u] = in ? part_d32[((int64_t)(s0 + u) * kcap + (kcap - 1)) * stride + off] : CUDART_INF_F;
+          head[u] = in ? KSG_LD_PART(&part_d32[((int64_t)(s0 + u) * kcap) * stride + off]) : CUDART_INF_F;
+          tails[u] = in ? KSG_LD_PART(&part_d32[((int64_t)(s0 + u) * kcap + (kcap - 1)) * stride + off]) : CUDART_INF_F;
       }
 #pragma unroll
       for (int u = 0; u < REFINE_BATCH; ++u) {
@@ -1097,15 +1145,15 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
         if (!((double)head[u] <= T)) continue;  // ascending list: nothing of it is inside the band
         for (int r = 0; r < kcap; ++r) {
             const int64_t o = ((int64_t)s * kcap + r) * stride + off;
-            const float v = r == 0 ? head[u] : part_d32[o];
+            const float v = r == 0 ? head[u] : KSG_LD_PART(&part_d32[o]);
             if (!((double)v <= T)) break;
             if (++examined > REFINE_CAP) { overflow = true; break; }
-            const int64_t j = part_idx[o];
+            const int64_t j = KSG_LD_PART(&part_idx[o]);
             double m = 0.0;
             for (int d = 0; d < dim; ++d) m = fmax(m, fabs(qc[d] - sorted[(int64_t)d * ld + j]));
             int pos = got < kp ? got : kp - 1;
-            if (idx_out) {
-                const int32_t o_j = perm[j];
+            if (ra.idx_out) {
+                const int32_t o_j = ra.perm[j];
                 if (got == kp && !(m < exact[kp - 1] || (m == exact[kp - 1] && o_j < exact_o[kp - 1]))) continue;
                 while (pos > 0 && (exact[pos - 1] > m || (exact[pos - 1] == m && exact_o[pos - 1] > o_j))) {
                     exact[pos] = exact[pos - 1]; exact_j[pos] = exact_j[pos - 1]; exact_o[pos] = exact_o[pos - 1];
@@ -1122,15 +1170,54 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
       }
     }
     if (overflow || got < kp) {
-        flags[qi] = 1;
-        atomicAdd(n_flagged, 1);
-        eps_out[qi] = CUDART_NAN;
+        ra.flags[qi] = 1;
+        atomicAdd(ra.n_flagged, 1);
+        ra.eps_out[qi] = CUDART_NAN;
     } else {
-        flags[qi] = 0;
-        eps_out[qi] = exact[kp - 1];
-        if (idx_out)
-            for (int r = 0; r < kp; ++r) idx_out[qi * kp + r] = exact_j[r];
+        ra.flags[qi] = 0;
+        ra.eps_out[qi] = exact[kp - 1];
+        if (ra.idx_out)
+            for (int r = 0; r < kp; ++r) ra.idx_out[qi * kp + r] = exact_j[r];
     }
+}
+
+// The refine as a launch of its own: the dense filter's split lists, and the windowed filter's unit
+// lists when the in-kernel refine is switched off (RefineArgs::fused == 0).
+static __global__ void __launch_bounds__(128)
+knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict__ part_idx, int kcap, int splits,
+                  int kp, const double* __restrict__ sorted, int64_t ld, int dim, int64_t n, int64_t q_begin,
+                  int64_t nq, const int32_t* __restrict__ q_index, const double* __restrict__ maxabs,
+                  const float* __restrict__ seed_thr, const int32_t* __restrict__ unit_first, int qb,
+                  const int32_t* __restrict__ perm, int64_t* __restrict__ idx_out,
+                  const double* __restrict__ qsorted, int64_t qld, const double* __restrict__ center,
+                  double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
+    // qsorted (optional, cross-set search): the float64 query coordinates come from this [dim][qld]
+    // array (rows q_begin + qi) instead of the candidate set itself.
+    // idx_out (optional, [nq][kp] int64): the k' nearest points as positions in the prepared
+    // order, ascending by (exact distance, original sample index) -- the order the dense float64
+    // kernel's merge produces.  All points tied with the k'-th distance are among the examined
+    // candidates whenever the query is not flagged, so the tie-break is well defined.
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    (void)n;
+    // list s, rank r of this query sits at ((s * kcap + r) * stride + off):
+    //   dense launch   : s = candidate split,  [split][rank][nq]
+    //   windowed launch: s = work unit of the query's block,  [unit][rank][QB]
+    int s_begin = 0, s_end = splits;
+    int64_t stride = nq, off = qi;
+    if (unit_first) {
+        const int64_t b = qi / qb;
+        s_begin = unit_first[b];
+        s_end = unit_first[b + 1];
+        stride = qb;
+        off = qi - b * qb;
+    }
+    RefineArgs ra;
+    ra.fused = 0; ra.kp = kp; ra.dim = dim; ra.sorted = sorted; ra.ld = ld; ra.qsorted = qsorted; ra.qld = qld;
+    ra.center = center; ra.maxabs = maxabs; ra.perm = perm; ra.idx_out = idx_out; ra.eps_out = eps_out;
+    ra.flags = flags; ra.n_flagged = n_flagged;
+    refine_merge_lists(part_d32, part_idx, kcap, s_begin, s_end, stride, off, seed_thr != nullptr,
+                       seed_thr ? seed_thr[qi] : 0.0f, q_index ? (int64_t)q_index[qi] : q_begin + qi, qi, ra);
 }
 
 // The refine of ONE ascending list that still sits in shared memory (called by knn_units_kernel for

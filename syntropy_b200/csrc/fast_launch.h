@@ -49,6 +49,7 @@ struct KnnF32Args {
     int32_t* unit_first;   // [n_query_blocks + 1]
     int32_t* unit_block;   // [max_units]
     int32_t* unit_meta;    // [4]: number of units, tiles per unit, work-queue cursor
+    int32_t* unit_done;    // [n_query_blocks] finished units per block (last-unit-done merge)
     int64_t max_units;
     float* part_d32;
     int32_t* part_idx;

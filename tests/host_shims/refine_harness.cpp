@@ -17,6 +17,7 @@
 #define __restrict__
 #define __launch_bounds__(x)
 #define __noinline__
+#define __ldcg(p) (*(p))
 #define __forceinline__ inline
 #define CUDART_INF (std::numeric_limits<double>::infinity())
 #define CUDART_INF_F (std::numeric_limits<float>::infinity())
@@ -212,8 +213,7 @@ int main(int argc, char** argv) {
             threadIdx.x = (unsigned)(qi % 128);
             knn_refine_kernel(d32.data(), idx.data(), kcap, splits, kp, pts.data(), n, dim, n, 0, nq, nullptr, nullptr,
                               nullptr, windowed ? unit_first.data() : nullptr, qb, perm.data(),
-                              want_idx ? nbr.data() : nullptr, nullptr, 0, center.data(), eps.data(), flags.data(), &n_flagged,
-                              0);
+                              want_idx ? nbr.data() : nullptr, nullptr, 0, center.data(), eps.data(), flags.data(), &n_flagged);
         }
         int counted = 0;
         for (int64_t qi = 0; qi < nq; ++qi) {
