@@ -380,11 +380,34 @@ int ksg_gather_f64(const double* d_src, const int32_t* d_perm, int64_t n, double
  * windowed form of cKDTree.count_neighbors(self, r) (syntropy/knn/temporal.py:71-72). */
 int ksg_sum_i32(const int32_t* d_values, int64_t n, unsigned long long* d_out, void* stream);
 
+/* ---- Minkowski p-norms, 1 <= p < inf (the `p` / `norm` arguments of syntropy.knn: knn/shannon.py:15,96,274,354;
+ * knn/temporal.py:16,85).  Same contracts as ksg_knn_radius / ksg_count_subspaces /
+ * ksg_subspace_radius_from_neighbours / ksg_paircount_fixed_radius with the distance of scipy's cKDTree for
+ * that p (p-th-power space: sum |d|, sum d^2 with its four-way partial sums, sum pow(|d|, p); a ball of radius r
+ * holds s <= r, r*r, pow(r, p); strict = the radius nudged down with nextafter first, knn/utils.py:75-76).
+ * Exact float64, dense; bit-exact for p = 1 and p = 2, device pow() for other p.  p = inf is rejected here
+ * (use the functions above).  ksg_knn_radius_p takes the workspace of ksg_knn_radius_workspace. */
+int ksg_knn_radius_p(const double* d_points, int64_t ld, int64_t n, int dim, const double* d_queries, int64_t ldq,
+                     int64_t q_begin, int64_t q_end, int kprime, double p, double* d_eps_out, int64_t* d_idx_out,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+int ksg_count_subspaces_p(const double* d_points, int64_t ld, int64_t n, int dim, const double* d_queries,
+                          int64_t ldq, int64_t q_begin, int64_t q_end, const uint32_t* h_masks, int n_subspaces,
+                          const double* d_eps, int64_t eps_stride, int strict, int32_t bias, double p,
+                          int32_t* d_counts, void* stream);
+int ksg_subspace_radius_from_neighbours_p(const double* d_points, int64_t ld, int64_t n, int dim, int64_t q_begin,
+                                          int64_t q_end, const int64_t* d_idx, int kprime, int skip_first,
+                                          const uint32_t* h_masks, int n_subspaces, double p, double* d_eps_out,
+                                          void* stream);
+int ksg_paircount_fixed_radius_p(const double* d_x, const double* d_y, int64_t n_templates, int m, double r, double p,
+                                 int64_t i_begin, int64_t i_end, unsigned long long* d_counts, void* stream);
+
 /* The key sort ksg_prepare is built on (argsort of one coordinate; reference: the ordering work
  * cKDTree's constructor does at syntropy/knn/utils.py:29): d_keys_out = the n float64 keys ascending,
  * d_index_out = their positions in d_keys_in, ties in position order (a stable sort).
- * n <= 2^21: five-launch sample sort (csrc/sample_sort.cuh); above, or with algorithm = 1:
- * cub::DeviceRadixSort.  algorithm: 0 = default, 1 = radix sort.  Workspace: ksg_sort_workspace(n). */
+ * algorithm 1: cub::DeviceRadixSort -- what ksg_prepare uses (eight latency-bound passes per float64
+ * coordinate).  algorithm 0: the five-launch sample sort of csrc/sample_sort.cuh for n <= 2^21 (radix sort
+ * above); measured slower on B200 at n = 1e6 (profiles/r2b_*), kept as an independent cross-check of the
+ * order.  Workspace: ksg_sort_workspace(n). */
 size_t ksg_sort_workspace(int64_t n);
 int ksg_sort_f64(const double* d_keys_in, int64_t n, double* d_keys_out, int32_t* d_index_out, int algorithm,
                  void* d_workspace, size_t workspace_bytes, void* stream);

@@ -114,6 +114,16 @@ SIGNATURES = {
     "ksg_scatter_i32": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_gather_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_sum_i32": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_vp]),
+    "ksg_knn_radius_p": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, _c_vp, _c_i64, _c_i64, _c_i64, C.c_int, C.c_double,
+                                   _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),
+    "ksg_count_subspaces_p": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, _c_vp, _c_i64, _c_i64, _c_i64,
+                                        C.POINTER(C.c_uint32), C.c_int, _c_vp, _c_i64, C.c_int, C.c_int32, C.c_double,
+                                        _c_vp, _c_vp]),
+    "ksg_subspace_radius_from_neighbours_p": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, _c_i64, _c_i64, _c_vp,
+                                                        C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int, C.c_double,
+                                                        _c_vp, _c_vp]),
+    "ksg_paircount_fixed_radius_p": (C.c_int, [_c_vp, _c_vp, _c_i64, C.c_int, C.c_double, C.c_double, _c_i64, _c_i64,
+                                               _c_vp, _c_vp]),
     "ksg_sort_workspace": (C.c_size_t, [_c_i64]),
     "ksg_sort_f64": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, C.c_int, _c_vp, C.c_size_t, _c_vp]),
 }

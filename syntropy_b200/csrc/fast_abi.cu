@@ -257,13 +257,16 @@ static inline GraphKey graph_key(int kind, std::initializer_list<const void*> pt
 
 static inline cudaStream_t as_stream2(void* s) { return (cudaStream_t)s; }
 
-// KSG_B200_SORT=cub keeps every key sort on cub::DeviceRadixSort (A/B measurements, cross-checks)
+// KSG_B200_SORT=sample moves the key sorts of ksg_prepare to the sample sort of sample_sort.cuh.
+// Measured on C2 (profiles/r2b_*): its single-CTA splitter sort and its shared-memory bitonic bucket
+// sorts make it SLOWER than eight latency-bound onesweep passes (prepare 1.12 ms against 0.38 ms), so
+// cub::DeviceRadixSort stays the default; the code is kept for ksg_sort_f64(algorithm 0) cross-checks.
 static bool use_sample_sort(int64_t n) {
-    static const bool off = [] {
+    static const bool on = [] {
         const char* e = getenv("KSG_B200_SORT");
-        return e && e[0] == 'c';
+        return e && e[0] == 's';
     }();
-    return !off && n <= SS_MAX_N;
+    return on && n <= SS_MAX_N;
 }
 
 // (key, position) pairs by sample sort; `tmp` holds cub_sort_bytes(n)
@@ -356,7 +359,7 @@ static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int
         if (p.plan_capacity > 0x7fff0000ll) p.plan_capacity = 0x7fff0000ll;  // int32 list offsets
         p.plan_bytes = align_up((size_t)p.plan_capacity * 8, 256);
         p.count_bytes = 2 * align_up((size_t)p.qblocks * sizeof(int32_t), 256);  // list lengths + starts
-        p.first_bytes = align_up((size_t)(p.qblocks + 1) * sizeof(int32_t), 256);
+        p.first_bytes = align_up((size_t)2 * (p.qblocks + 1) * sizeof(int32_t), 256);  // starts + counts
         p.ublock_bytes = align_up((size_t)p.max_units * sizeof(int32_t), 256);
         p.meta_bytes = 256;
         p.done_bytes = align_up((size_t)p.qblocks * sizeof(int32_t), 256);
@@ -783,7 +786,7 @@ static FastCountPlan fast_count_plan(int64_t n, int64_t nq, int dim) {
     if (p.plan_capacity > 0x7fff0000ll) p.plan_capacity = 0x7fff0000ll;
     p.plan_bytes = align_up((size_t)p.plan_capacity * 8, 256);
     p.count_bytes = 2 * align_up((size_t)p.qblocks * sizeof(int32_t), 256);
-    p.first_bytes = align_up((size_t)(p.qblocks + 1) * sizeof(int32_t), 256);
+    p.first_bytes = align_up((size_t)2 * (p.qblocks + 1) * sizeof(int32_t), 256);  // starts + counts
     p.ublock_bytes = align_up((size_t)p.max_units * sizeof(int32_t), 256);
     p.meta_bytes = 256;
     return p;
@@ -951,7 +954,7 @@ int ksg_sort_f64(const double* d_keys_in, int64_t n, double* d_keys_out, int32_t
     }
     cudaStream_t st = as_stream2(stream);
     const size_t sort_bytes = align_up(cub_sort_bytes(n), 256);
-    if (algorithm == 0 && use_sample_sort(n))
+    if (algorithm == 0 && n <= SS_MAX_N)
         return sample_sort_launch<double>(d_workspace, d_keys_in, d_keys_out, d_index_out, n, st);
     int32_t* iota = (int32_t*)((char*)d_workspace + sort_bytes);
     iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);

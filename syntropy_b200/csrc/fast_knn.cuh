@@ -618,7 +618,6 @@ knn_unit_table_kernel(const int32_t* __restrict__ plan_count, int64_t n_blocks, 
                       int32_t* __restrict__ unit_first, int32_t* __restrict__ unit_block,
                       int32_t* __restrict__ meta) {
     __shared__ long long s_red[32];
-    __shared__ int s_scan[1024];
     __shared__ int s_chunk;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t per = (n_blocks + 1023) / 1024;
@@ -637,31 +636,45 @@ knn_unit_table_kernel(const int32_t* __restrict__ plan_count, int64_t n_blocks, 
     }
     __syncthreads();
     const int chunk = s_chunk;
-    int mine = 0;
-    for (int64_t b = b0; b < b1; ++b) {
-        const int c = plan_count[b];
-        mine += c > 0 ? (c + chunk - 1) / chunk : 0;
-    }
-    s_scan[tid] = mine;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // inclusive scan
-        const int v = tid >= off ? s_scan[tid - off] : 0;
-        __syncthreads();
-        s_scan[tid] += v;
-        __syncthreads();
-    }
-    int u = s_scan[tid] - mine;
+    // Units of the blocks that need SEVERAL come first in the queue: their partial lists are merged by
+    // whoever finishes the block's last unit, and that merge must not be the tail of the launch
+    // (longest work first).  unit_first[b] = first unit of block b, unit_first[n_blocks + 1 + b] = how many.
+    int32_t* unit_count = unit_first + (n_blocks + 1);
+    int mine_multi = 0, mine_single = 0;
     for (int64_t b = b0; b < b1; ++b) {
         const int c = plan_count[b];
         const int nu = c > 0 ? (c + chunk - 1) / chunk : 0;
+        if (nu > 1) mine_multi += nu; else mine_single += nu;
+    }
+    // one scan over (multi, single) packed into 64 bits (each < 2^31)
+    __shared__ unsigned long long s_scan2[1024];
+    unsigned long long mine2 = ((unsigned long long)mine_multi << 32) | (unsigned long long)mine_single;
+    s_scan2[tid] = mine2;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // inclusive scan
+        const unsigned long long v = tid >= off ? s_scan2[tid - off] : 0ull;
+        __syncthreads();
+        s_scan2[tid] += v;
+        __syncthreads();
+    }
+    const unsigned long long incl = s_scan2[tid], total2 = s_scan2[1023];
+    const int total_multi = (int)(total2 >> 32), total_single = (int)(total2 & 0xffffffffull);
+    int um = (int)(incl >> 32) - mine_multi;                                   // next multi-unit slot
+    int us = total_multi + (int)(incl & 0xffffffffull) - mine_single;          // next single-unit slot
+    for (int64_t b = b0; b < b1; ++b) {
+        const int c = plan_count[b];
+        const int nu = c > 0 ? (c + chunk - 1) / chunk : 0;
+        int& u = nu > 1 ? um : us;
         unit_first[b] = u;
+        unit_count[b] = nu;
         for (int i = 0; i < nu; ++i)
             if (u + i < max_units) unit_block[u + i] = (int32_t)b;
         u += nu;
     }
     if (tid == 1023) {
-        unit_first[n_blocks] = s_scan[1023];
-        meta[0] = s_scan[1023] < max_units ? s_scan[1023] : (int32_t)max_units;  // (bound holds by construction)
+        const int total = total_multi + total_single;
+        unit_first[n_blocks] = total;
+        meta[0] = total < max_units ? total : (int32_t)max_units;  // (bound holds by construction)
         meta[1] = chunk;
         meta[2] = 0;
     }
@@ -749,6 +762,7 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
     }
     __syncthreads();
     const int n_units = meta[0], chunk = meta[1];
+    const int32_t* unit_count = unit_first + ((nq + QB - 1) / QB + 1);  // (see knn_unit_table_kernel)
     // ring state (kernel lifetime, advanced identically by both roles): next slot and the
     // phase parity to wait for on it.  A fresh mbarrier passes a wait on parity 1, which is
     // how the copy lane finds every slot free at the start.
@@ -774,7 +788,7 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
         // a block whose whole tile list is this one unit is refined right here, from shared memory;
         // the units of a longer list emit partial lists, and whoever finishes the LAST of them merges
         const int ufirst = unit_first[qblock];
-        const int nunits = unit_first[qblock + 1] - ufirst;
+        const int nunits = unit_count[qblock];
         const bool refine_here = ra.fused && nunits == 1;
 
         // ---------------- filter warps: queries, thresholds, warp box, empty lists
@@ -1208,7 +1222,7 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     if (unit_first) {
         const int64_t b = qi / qb;
         s_begin = unit_first[b];
-        s_end = unit_first[b + 1];
+        s_end = s_begin + unit_first[(nq + qb - 1) / qb + 1 + b];  // (counts sit behind the starts)
         stride = qb;
         off = qi - b * qb;
     }
@@ -1260,6 +1274,49 @@ static __device__ __noinline__ void refine_single_list(const float* col_d, const
     // full list with its tail inside the band, or a band that reaches the seeded threshold:
     // in-band candidates may be missing
     bool undecided = tail <= T || !(T < (double)seed);
+    if (!undecided && !ra.idx_out) {
+        // Radius only.  With |d64 - d32| <= delta the exact radius r64 lies in [r32 - delta, r32 + delta]:
+        // an entry with d32 < r32 - 2 delta is strictly below r64, one with d32 > r32 + 2 delta strictly
+        // above.  So r64 is the (k' - a)-th smallest EXACT distance among the entries inside
+        // [r32 - 2 delta, r32 + 2 delta], a = the number of entries below that band -- on continuous
+        // data the band holds the k'-th entry alone and the refine is ONE float64 distance.
+        const double lo = r32 - 2.0 * band_query_f64(mq, 2.0 * r32);  // (the band's 1 % slack covers the rounding)
+        int a = 0;
+        while (a < kp - 1 && (double)col_d[(size_t)a * stride] < lo) ++a;
+        int e = kp;  // entry k' - 1 (= r32) is inside
+        while (e < kcap && (double)col_d[(size_t)e * stride] <= T) ++e;
+        const int b = e - a, want = kp - a;  // 1 <= want <= b
+        constexpr int BAND_REGS = 4;
+        if (b <= BAND_REGS) {
+            double mb[BAND_REGS];
+#pragma unroll
+            for (int r = 0; r < BAND_REGS; ++r) {
+                mb[r] = CUDART_INF;
+                if (r < b) {
+                    const int64_t j = col_i[(size_t)(a + r) * stride];
+                    double v = 0.0;
+                    for (int d = 0; d < dim; ++d) v = fmax(v, fabs(qc[d] - ra.sorted[(int64_t)d * ra.ld + j]));
+                    mb[r] = v;
+                }
+            }
+            // the want-th smallest of mb[0..b): the value with fewer than `want` values below it and at
+            // least `want` values not above it
+            double ans = mb[0];
+#pragma unroll
+            for (int r = 0; r < BAND_REGS; ++r) {
+                int less = 0, le = 0;
+#pragma unroll
+                for (int t = 0; t < BAND_REGS; ++t) {
+                    less += (t < b && mb[t] < mb[r]) ? 1 : 0;
+                    le += (t < b && mb[t] <= mb[r]) ? 1 : 0;
+                }
+                if (r < b && less < want && want <= le) ans = mb[r];
+            }
+            ra.flags[qi] = 0;
+            ra.eps_out[qi] = ans;
+            return;
+        }
+    }
     double m[KNN_MAX_KCAP];
     int32_t mj[KNN_MAX_KCAP], mo[KNN_MAX_KCAP];
     int nb = 0;

@@ -8,6 +8,7 @@
 #include "epilogue.cuh"
 #include "exact_f64.cuh"
 #include "fast_launch.h"
+#include "minkowski_f64.cuh"
 
 namespace ksg {
 
@@ -385,6 +386,185 @@ int ksg_paircount_fixed_radius(const double* d_x, const double* d_y, int64_t n_t
             return launch_paircount<0>(d_x, d_y, n_templates, m, r, i_begin, ni, d_counts, st);
     }
 #undef KSG_CASE
+}
+
+// ------------------------------------------------------------------ Minkowski p
+}  // extern "C"
+
+namespace ksg {
+
+static int norm_of(double p) { return p == 1.0 ? NORM_1 : (p == 2.0 ? NORM_2 : NORM_P); }
+
+static int sub_dims_of(const uint32_t* h_masks, int n_subspaces, int dim, SubDims* out, const char* who) {
+    memset(out, 0, sizeof(*out));
+    const uint32_t all = dim == 32 ? 0xffffffffu : ((1u << dim) - 1u);
+    for (int s = 0; s < n_subspaces; ++s) {
+        if (h_masks[s] == 0 || (h_masks[s] & ~all) != 0) {
+            set_error("invalid argument: %s: empty or out-of-range mask", who);
+            return KSG_EINVAL;
+        }
+        int nd = 0;
+        for (int d = 0; d < dim; ++d)
+            if ((h_masks[s] >> d) & 1u) out->d[s][nd++] = (int8_t)d;
+        out->n[s] = (int8_t)nd;
+    }
+    return KSG_OK;
+}
+
+template <int NORM, bool WITH_IDX>
+static int launch_knn_pow(const double* pts, int64_t ld, int64_t n, int dim, const double* qry, int64_t ldq,
+                          int64_t q_begin, int64_t nq, int kp, double p, const KnnPlan& plan, double* part_dist,
+                          int64_t* part_idx, cudaStream_t st) {
+    size_t smem = (size_t)dim * F64_TILE * sizeof(double) + (size_t)kp * F64_THREADS * sizeof(double) +
+                  (WITH_IDX ? (size_t)kp * F64_THREADS * sizeof(int64_t) : 0);
+    int rc = allow_smem(knn_pow_kernel<NORM, WITH_IDX>, smem);
+    if (rc) return rc;
+    dim3 grid((unsigned)plan.qblocks, (unsigned)plan.splits, 1);
+    knn_pow_kernel<NORM, WITH_IDX><<<grid, F64_THREADS, smem, st>>>(pts, ld, n, qry, ldq, q_begin, nq, dim, kp, p,
+                                                                    plan.cand_per_split, part_dist, part_idx);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+template <int NORM>
+static int launch_count_pow(const double* pts, int64_t ld, int64_t n, int dim, const double* qry, int64_t ldq,
+                            int64_t q_begin, int64_t nq, const SubDims& subs, int n_sub, const double* eps,
+                            int64_t eps_stride, int strict, double p, int32_t* counts, cudaStream_t st) {
+    const int64_t qblocks = ceil_div(nq, F64_THREADS);
+    int splits = choose_splits(qblocks * n_sub, n, F64_TILE);
+    const int64_t per = ceil_div(ceil_div(n, splits), F64_TILE) * F64_TILE;
+    splits = (int)ceil_div(n, per);
+    if (splits < 1) splits = 1;
+    const size_t smem = (size_t)dim * F64_TILE * sizeof(double);
+    int rc = allow_smem(count_pow_kernel<NORM>, smem);
+    if (rc) return rc;
+    dim3 grid((unsigned)qblocks, (unsigned)splits, (unsigned)n_sub);
+    count_pow_kernel<NORM><<<grid, F64_THREADS, smem, st>>>(pts, ld, n, qry, ldq, q_begin, nq, dim, subs, n_sub, eps,
+                                                            eps_stride, strict, p, per, counts);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+}  // namespace ksg
+
+extern "C" {
+
+#define KSG_NORM_SWITCH(p, CALL)                            switch (norm_of(p)) {                                       case NORM_1: { constexpr int NORM = NORM_1; CALL; } break;         case NORM_2: { constexpr int NORM = NORM_2; CALL; } break;         default: { constexpr int NORM = NORM_P; CALL; } break;         }
+
+int ksg_knn_radius_p(const double* d_points, int64_t ld, int64_t n, int dim, const double* d_queries, int64_t ldq,
+                     int64_t q_begin, int64_t q_end, int kprime, double p, double* d_eps_out, int64_t* d_idx_out,
+                     void* d_workspace, size_t workspace_bytes, void* stream) {
+    KSG_REQUIRE(d_points && d_eps_out, "ksg_knn_radius_p: null pointer");
+    KSG_REQUIRE(n > 0 && ld >= n, "ksg_knn_radius_p: need n > 0 and ld >= n");
+    KSG_REQUIRE(dim >= 1 && dim <= KSG_MAX_DIM, "ksg_knn_radius_p: dim out of range");
+    KSG_REQUIRE(kprime >= 1 && kprime <= KSG_MAX_KPRIME, "ksg_knn_radius_p: kprime out of range");
+    KSG_REQUIRE(p >= 1.0 && p <= 1.7976931348623157e308, "ksg_knn_radius_p: need 1 <= p < inf (p = inf: ksg_knn_radius)");
+    if (!d_queries) {
+        d_queries = d_points;
+        ldq = ld;
+        KSG_REQUIRE(q_end <= n, "ksg_knn_radius_p: query range exceeds the point set");
+    }
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && ldq >= q_end, "ksg_knn_radius_p: bad query range");
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    KnnPlan plan = knn_plan(n, nq, kprime);
+    if (workspace_bytes < plan.dist_bytes + plan.idx_bytes || !d_workspace) {
+        set_error("ksg_knn_radius_p: workspace of %zu bytes needed, %zu given", plan.dist_bytes + plan.idx_bytes,
+                  workspace_bytes);
+        return KSG_EWORKSPACE;
+    }
+    double* part_dist = (double*)d_workspace;
+    int64_t* part_idx = (int64_t*)((char*)d_workspace + plan.dist_bytes);
+    cudaStream_t st = as_stream(stream);
+    int rc = KSG_OK;
+    if (d_idx_out) {
+        KSG_NORM_SWITCH(p, (rc = launch_knn_pow<NORM, true>(d_points, ld, n, dim, d_queries, ldq, q_begin, nq, kprime, p,
+                                                            plan, part_dist, part_idx, st)))
+    } else {
+        KSG_NORM_SWITCH(p, (rc = launch_knn_pow<NORM, false>(d_points, ld, n, dim, d_queries, ldq, q_begin, nq, kprime, p,
+                                                             plan, part_dist, part_idx, st)))
+    }
+    if (rc) return rc;
+    const unsigned mb = (unsigned)ceil_div(nq, 128);
+    if (d_idx_out)
+        knn_merge_kernel<true><<<mb, 128, 0, st>>>(part_dist, part_idx, nq, kprime, plan.splits, d_eps_out, d_idx_out);
+    else
+        knn_merge_kernel<false><<<mb, 128, 0, st>>>(part_dist, part_idx, nq, kprime, plan.splits, d_eps_out, nullptr);
+    KSG_LAUNCHED();
+    KSG_NORM_SWITCH(p, (pow_root_kernel<NORM><<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(d_eps_out, nq, p)))
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_count_subspaces_p(const double* d_points, int64_t ld, int64_t n, int dim, const double* d_queries,
+                          int64_t ldq, int64_t q_begin, int64_t q_end, const uint32_t* h_masks, int n_subspaces,
+                          const double* d_eps, int64_t eps_stride, int strict, int32_t bias, double p,
+                          int32_t* d_counts, void* stream) {
+    KSG_REQUIRE(d_points && h_masks && d_eps && d_counts, "ksg_count_subspaces_p: null pointer");
+    KSG_REQUIRE(n > 0 && ld >= n, "ksg_count_subspaces_p: need n > 0 and ld >= n");
+    KSG_REQUIRE(dim >= 1 && dim <= KSG_MAX_DIM, "ksg_count_subspaces_p: dim out of range");
+    KSG_REQUIRE(n_subspaces >= 1 && n_subspaces <= KSG_MAX_SUBSPACES, "ksg_count_subspaces_p: subspace count");
+    KSG_REQUIRE(p >= 1.0 && p <= 1.7976931348623157e308, "ksg_count_subspaces_p: need 1 <= p < inf (p = inf: ksg_count_subspaces)");
+    if (!d_queries) {
+        d_queries = d_points;
+        ldq = ld;
+        KSG_REQUIRE(q_end <= n, "ksg_count_subspaces_p: query range exceeds the point set");
+    }
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && ldq >= q_end, "ksg_count_subspaces_p: bad query range");
+    const int64_t nq = q_end - q_begin;
+    KSG_REQUIRE(eps_stride == 0 || eps_stride >= nq, "ksg_count_subspaces_p: eps_stride must be 0 or >= nq");
+    if (nq == 0) return KSG_OK;
+    SubDims subs;
+    int rc = sub_dims_of(h_masks, n_subspaces, dim, &subs, "ksg_count_subspaces_p");
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int64_t total = (int64_t)n_subspaces * nq;
+    fill_i32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(d_counts, total, bias);
+    KSG_LAUNCHED();
+    KSG_NORM_SWITCH(p, (rc = launch_count_pow<NORM>(d_points, ld, n, dim, d_queries, ldq, q_begin, nq, subs, n_subspaces,
+                                                    d_eps, eps_stride, strict, p, d_counts, st)))
+    return rc;
+}
+
+int ksg_subspace_radius_from_neighbours_p(const double* d_points, int64_t ld, int64_t n, int dim, int64_t q_begin,
+                                          int64_t q_end, const int64_t* d_idx, int kprime, int skip_first,
+                                          const uint32_t* h_masks, int n_subspaces, double p, double* d_eps_out,
+                                          void* stream) {
+    KSG_REQUIRE(d_points && d_idx && h_masks && d_eps_out, "ksg_subspace_radius_from_neighbours_p: null pointer");
+    KSG_REQUIRE(n > 0 && ld >= n && dim >= 1 && dim <= KSG_MAX_DIM, "ksg_subspace_radius_from_neighbours_p: sizes");
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= n, "ksg_subspace_radius_from_neighbours_p: query range");
+    KSG_REQUIRE(n_subspaces >= 1 && n_subspaces <= KSG_MAX_SUBSPACES, "ksg_subspace_radius_from_neighbours_p: subspaces");
+    KSG_REQUIRE(kprime >= 1 && kprime <= KSG_MAX_KPRIME, "ksg_subspace_radius_from_neighbours_p: kprime");
+    KSG_REQUIRE(p >= 1.0 && p <= 1.7976931348623157e308, "ksg_subspace_radius_from_neighbours_p: need 1 <= p < inf");
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    SubDims subs;
+    int rc = sub_dims_of(h_masks, n_subspaces, dim, &subs, "ksg_subspace_radius_from_neighbours_p");
+    if (rc) return rc;
+    KSG_NORM_SWITCH(p, (subspace_radius_pow_kernel<NORM><<<(unsigned)ceil_div(nq, 128), 128, 0, as_stream(stream)>>>(
+                           d_points, ld, q_begin, nq, n, d_idx, kprime, skip_first, subs, n_subspaces, p, d_eps_out)))
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_paircount_fixed_radius_p(const double* d_x, const double* d_y, int64_t n_templates, int m, double r, double p,
+                                 int64_t i_begin, int64_t i_end, unsigned long long* d_counts, void* stream) {
+    KSG_REQUIRE(d_x && d_y && d_counts, "ksg_paircount_fixed_radius_p: null pointer");
+    KSG_REQUIRE(n_templates > 0 && m >= 1 && m < KSG_MAX_DIM, "ksg_paircount_fixed_radius_p: sizes");
+    KSG_REQUIRE(i_begin >= 0 && i_end >= i_begin && i_end <= n_templates, "ksg_paircount_fixed_radius_p: range");
+    KSG_REQUIRE(p >= 1.0 && p <= 1.7976931348623157e308, "ksg_paircount_fixed_radius_p: need 1 <= p < inf");
+    const int64_t ni = i_end - i_begin;
+    if (ni == 0) return KSG_OK;
+    const int64_t iblocks = ceil_div(ni, PC_THREADS);
+    int splits = choose_splits(iblocks, n_templates, PC_TILE);
+    const int64_t per = ceil_div(ceil_div(n_templates, splits), PC_TILE) * PC_TILE;
+    splits = (int)ceil_div(n_templates, per);
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)iblocks, (unsigned)splits, 1);
+    KSG_NORM_SWITCH(p, (paircount_pow_kernel<NORM><<<grid, PC_THREADS, 0, as_stream(stream)>>>(
+                           d_x, d_y, n_templates, m, r, p, i_begin, ni, per, d_counts)))
+    KSG_LAUNCHED();
+    return KSG_OK;
 }
 
 }  // extern "C"

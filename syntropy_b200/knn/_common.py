@@ -10,9 +10,8 @@ def check_idxs(idxs, data):
     return tuple(idxs)
 
 
-def require_chebyshev(p):
-    if not (p == np.inf):
-        raise NotImplementedError(
-            "syntropy_b200 implements the Chebyshev (p=inf) KSG path only; "
-            f"p={p!r} is not supported and there is no CPU fallback"
-        )
+def is_chebyshev(p) -> bool:
+    """p = inf: the maximum norm, the path BASELINE.json names (fp32-filtered engines).  Any other
+    p >= 1 runs on the exact float64 Minkowski kernels (``syntropy_b200._minkowski``); p < 1 raises
+    the ValueError cKDTree raises."""
+    return p == np.inf

@@ -1,16 +1,18 @@
 """Drop-in for ``syntropy.knn.shannon`` (reference: syntropy/knn/shannon.py).
 
 Same signatures, argument meaning, return tuples and assertion behaviour; the work is
-done by the sm_100a kernels behind ``include/ksg_b200.h``.  Only the Chebyshev norm
-(``p = inf``) -- the path BASELINE.json names -- is implemented; any other ``p`` raises
-``NotImplementedError`` (there is no CPU fallback).
+done by the sm_100a kernels behind ``include/ksg_b200.h``.  ``p = inf`` (the maximum norm, the
+path BASELINE.json names) runs on the fp32-filtered engines; any other ``p >= 1`` runs on the
+exact float64 Minkowski kernels and reproduces the reference's forwarding of ``p`` function by
+function (ignored by the joint query of algorithm 1, knn/shannon.py:186 vs :192).
 """
 from __future__ import annotations
 
 import numpy as np
 
 from .. import _engine as E
-from ._common import check_idxs, require_chebyshev
+from .. import _minkowski as M
+from ._common import check_idxs, is_chebyshev
 
 
 def differential_entropy(data, k, idxs=None, p=np.inf, noise_level=0.0, seed=0):
@@ -19,7 +21,6 @@ def differential_entropy(data, k, idxs=None, p=np.inf, noise_level=0.0, seed=0):
     Returns ``(ptw (1, N) float64, average)`` with
     ``ptw = -psi(k) + psi(N) + d*log(2*eps)``.
     """
-    require_chebyshev(p)
     data = np.asarray(data)
     idxs_ = check_idxs(idxs, data)
     rows = data[idxs_, :]
@@ -27,7 +28,7 @@ def differential_entropy(data, k, idxs=None, p=np.inf, noise_level=0.0, seed=0):
         # the reference jitters its fancy-index copy in place (:78-80)
         rng = np.random.default_rng(seed)
         rows += rng.standard_normal(rows.shape) * noise_level
-    ptw, avg = E.kl_entropy(rows, k)
+    ptw, avg = E.kl_entropy(rows, k) if is_chebyshev(p) else M.entropy(rows, k, p)
     return ptw.reshape(1, -1), avg
 
 
@@ -54,9 +55,12 @@ def mi1_program(psi_k, psi_n):
 
 def mutual_information_1(idxs_x, idxs_y, k, data, p=np.inf):
     """KSG-1: ``(psi(k)+psi(N)) - psi(n_x+1) - psi(n_y+1)`` (reference: knn/shannon.py:137-196)."""
-    require_chebyshev(p)
     data = np.asarray(data)
     idxs_x, idxs_y = tuple(idxs_x), tuple(idxs_y)
+    if not is_chebyshev(p):
+        # the joint radius stays a maximum-norm radius (:186), only the counts see p (:192)
+        ptw, avg = M.ksg1(data[idxs_x + idxs_y, :], k, _xy_masks(idxs_x, idxs_y), mi1_program, p, joint_chebyshev=True)
+        return ptw.reshape(1, -1), avg
     rows = E.select_rows(data, idxs_x + idxs_y)
     ptw, avg = E.ksg1_family(rows, k, _xy_masks(idxs_x, idxs_y), mi1_program)
     return ptw.reshape(1, -1), avg
@@ -67,10 +71,8 @@ def mutual_information_2(idxs_x, idxs_y, k, data, p=np.inf):
     ``psi(k) - 1/k + psi(N) - psi(n_x) - psi(n_y)`` (reference: knn/shannon.py:199-265).
     Neighbour identity among exactly tied distances is cKDTree-internal in the reference;
     here ties are broken by index, so bit parity holds on tie-free data."""
-    require_chebyshev(p)
     data = np.asarray(data)
     idxs_x, idxs_y = tuple(idxs_x), tuple(idxs_y)
-    rows = E.select_rows(data, idxs_x + idxs_y)
 
     def program(psi_k, psi_n):
         prog = E.PsiProgram(init=psi_k - (1 / k) + psi_n)
@@ -78,6 +80,10 @@ def mutual_information_2(idxs_x, idxs_y, k, data, p=np.inf):
         prog.add(1, -1, count_offset=0)
         return prog
 
+    if not is_chebyshev(p):
+        ptw, avg = M.ksg2(data[idxs_x + idxs_y, :], k, _xy_masks(idxs_x, idxs_y), program, p)
+        return ptw.reshape(1, -1), avg
+    rows = E.select_rows(data, idxs_x + idxs_y)
     ptw, avg = E.ksg2_family(rows, k, _xy_masks(idxs_x, idxs_y), program)
     return ptw.reshape(1, -1), avg
 
@@ -85,11 +91,13 @@ def mutual_information_2(idxs_x, idxs_y, k, data, p=np.inf):
 def conditional_mutual_information(idxs_x, idxs_y, idxs_z, k, data, p=np.inf):
     """Frenzel-Pompe CMI: ``psi(k) + psi(n_z+1) - psi(n_xz+1) - psi(n_yz+1)``
     (reference: knn/shannon.py:268-347)."""
-    require_chebyshev(p)
     data = np.asarray(data)
     idxs_x, idxs_y, idxs_z = tuple(idxs_x), tuple(idxs_y), tuple(idxs_z)
-    rows = E.select_rows(data, idxs_x + idxs_y + idxs_z)
     masks, program = cmi_spec(len(idxs_x), len(idxs_y), len(idxs_z))
+    if not is_chebyshev(p):
+        ptw, avg = M.ksg1(data[idxs_x + idxs_y + idxs_z, :], k, masks, program, p, joint_chebyshev=False)  # :332,338
+        return ptw.reshape(1, -1), avg
+    rows = E.select_rows(data, idxs_x + idxs_y + idxs_z)
     ptw, avg = E.ksg1_family(rows, k, masks, program)
     return ptw.reshape(1, -1), avg
 
@@ -119,6 +127,7 @@ def kullback_leibler_divergence(posterior_data, prior_data, k, p=np.inf):
     assert posterior_data.shape[0] == prior_data.shape[0], (
         "The data must have the same number of dimensions."
     )
-    require_chebyshev(p)
+    if not is_chebyshev(p):
+        return M.kl_divergence(posterior_data, prior_data, k, p)
     ptw, avg = E.kl_divergence(posterior_data, prior_data, k)
     return ptw, avg

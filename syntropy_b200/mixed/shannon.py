@@ -7,8 +7,11 @@ pooled set where the estimator needs H(C) -- runs the KSG radius pipeline on a d
 its columns (``_engine.kl_entropy_groups``).  The class bookkeeping (np.unique, probabilities,
 ``-log p`` terms) stays on the host in the reference's float64 operation order.
 
-``continuous_estimator="gaussian"`` is ``syntropy.gaussian``'s closed form, not part of the KSG
-path: it raises ``NotImplementedError`` here (there is nothing to accelerate and no CPU fallback).
+``continuous_estimator="gaussian"`` -- the reference's DEFAULT -- is ``syntropy.gaussian``'s closed
+form, not part of the KSG path and with nothing to accelerate: such calls are handed to the installed
+reference (``syntropy.mixed``) unchanged, so default-argument calls keep working where syntropy is
+installed; without it they raise ``NotImplementedError`` that says so.  The knn branch never falls
+back to anything.
 """
 from __future__ import annotations
 
@@ -19,13 +22,25 @@ from .. import _engine as E
 _ESTIMATORS = {"gaussian", "knn"}
 
 
+def _gaussian_branch(name, *args, **kwargs):
+    """The Gaussian plug-in is not on the KSG path: delegate to the reference if it is installed."""
+    try:
+        import importlib
+
+        ref = importlib.import_module("syntropy.mixed")
+    except Exception as exc:
+        raise NotImplementedError(
+            "syntropy_b200.mixed accelerates continuous_estimator='knn' (the KSG path); "
+            "continuous_estimator='gaussian' (the default) is syntropy.gaussian's closed form and is "
+            "delegated to the reference package, which is not importable here (%s). "
+            "Pass continuous_estimator='knn' or install syntropy." % exc
+        ) from exc
+    return getattr(ref, name)(*args, **kwargs)
+
+
 def _require_knn(continuous_estimator):
     assert continuous_estimator in _ESTIMATORS, "Continuous estimator options are 'gaussian' or 'knn'."
-    if continuous_estimator != "knn":
-        raise NotImplementedError(
-            "syntropy_b200.mixed implements continuous_estimator='knn' only (the KSG path); "
-            "the Gaussian plug-in is syntropy.gaussian's closed form and has no GPU path here"
-        )
+    return continuous_estimator == "knn"
 
 
 _DENSE_KEY_LIMIT = 1 << 20  # integer class keys up to this many distinct codes are counted, not sorted
@@ -109,7 +124,8 @@ def _joint(probs, class_id, by_sample, avgs):
 def shannon_entropy(discrete_vars, continuous_vars, continuous_estimator="gaussian", k=5):
     """H(X, Y) = H(X) + H(Y | X) for discrete X, continuous Y (reference: mixed/shannon.py:7-90)."""
     discrete_vars, continuous_vars = _check_shapes(discrete_vars, continuous_vars)
-    _require_knn(continuous_estimator)
+    if not _require_knn(continuous_estimator):
+        return _gaussian_branch("shannon_entropy", discrete_vars, continuous_vars, continuous_estimator=continuous_estimator, k=k)
     probs, class_id, order, bounds = _classes(discrete_vars)
     by_sample, _, avgs, _ = _class_entropies(continuous_vars, order, bounds, k)
     return _joint(probs, class_id, by_sample, avgs)
@@ -121,7 +137,9 @@ def conditional_entropy(discrete_vars, continuous_vars, conditional="discrete", 
     assert conditional in {"discrete", "continuous"}, (
         "Please specify whether the conditioning variable is discrete or continuous."
     )
-    _require_knn(continuous_estimator)
+    if not _require_knn(continuous_estimator):
+        return _gaussian_branch("conditional_entropy", discrete_vars, continuous_vars, conditional=conditional,
+                                continuous_estimator=continuous_estimator, k=k)
     probs, class_id, order, bounds = _classes(discrete_vars)
     pooled = conditional == "continuous"
     by_sample, pooled_ptw, avgs, pooled_avg = _class_entropies(continuous_vars, order, bounds, k, pooled=pooled)
@@ -138,7 +156,8 @@ def conditional_entropy(discrete_vars, continuous_vars, conditional="discrete", 
 def mutual_information(discrete_vars, continuous_vars, continuous_estimator="gaussian", k=5):
     """I(D; C) = H(C) - H(C | D) (reference: mixed/shannon.py:184-275)."""
     discrete_vars, continuous_vars = _check_shapes(discrete_vars, continuous_vars)
-    _require_knn(continuous_estimator)
+    if not _require_knn(continuous_estimator):
+        return _gaussian_branch("mutual_information", discrete_vars, continuous_vars, continuous_estimator=continuous_estimator, k=k)
     probs, class_id, order, bounds = _classes(discrete_vars)
     by_sample, pooled_ptw, avgs, avg = _class_entropies(continuous_vars, order, bounds, k, pooled=True)
     with np.errstate(all="ignore"):

@@ -164,7 +164,7 @@ int main(int argc, char** argv) {
         std::shuffle(perm.begin(), perm.end(), rng);
         const int nblocks = (int)((nq + qb - 1) / qb);
         // chunks of the candidate set per query block (windowed) or for everybody (dense)
-        std::vector<int32_t> unit_first(nblocks + 1, 0);
+        std::vector<int32_t> unit_first(2 * (nblocks + 1), 0);  // starts, then counts (knn_unit_table_kernel)
         const int splits = 1 + (int)(rng() % 6);
         int total_units = 0;
         for (int b = 0; b < nblocks; ++b) {
@@ -172,6 +172,7 @@ int main(int argc, char** argv) {
             total_units += 1 + (int)(rng() % 4 == 0 ? rng() % 30 : rng() % 3);
         }
         unit_first[nblocks] = total_units;
+        for (int b = 0; b < nblocks; ++b) unit_first[nblocks + 1 + b] = unit_first[b + 1] - unit_first[b];
         const int n_lists = windowed ? total_units : splits;
         const int64_t stride = windowed ? qb : nq;
         std::vector<float> d32((size_t)n_lists * kcap * stride, CUDART_INF_F);

@@ -272,8 +272,8 @@ def test_errors_mirror_reference(knn):
     bad = data.copy(); bad[1, 5] = np.nan
     with pytest.raises(ValueError):
         knn.mutual_information((0,), (1,), 3, bad)
-    with pytest.raises(NotImplementedError):
-        knn.mutual_information((0,), (1,), 3, data, p=2)
+    with pytest.raises(ValueError):
+        knn.mutual_information((0,), (1,), 3, data, p=0.5)  # cKDTree: only p-norms with 1 <= p <= inf
     ptw, avg = knn.o_information(data[:2], 3)
     assert ptw.shape == (64,) and avg == 0.0 and not ptw.any()
 

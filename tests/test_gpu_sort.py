@@ -1,5 +1,6 @@
-"""The key sort of ksg_prepare (csrc/sample_sort.cuh) on the GPU: ksg_sort_f64 against numpy's stable
-argsort, against the radix-sort path it replaces, and prepared sets that are identical under both."""
+"""The key sorts behind ksg_prepare on the GPU: ksg_sort_f64 (sample sort, csrc/sample_sort.cuh)
+against numpy's stable argsort and against the radix sort ksg_prepare uses, and prepared sets that
+are identical under both."""
 import ctypes as C
 import hashlib
 import os
@@ -81,7 +82,7 @@ def _prepared_digest():
     h = hashlib.sha1()
     rng = np.random.default_rng(9)
     sets = [workloads.c2_mi_1m(n=300_000)[0], workloads.c3_cmi(n=60_000)[0], rng.standard_normal((3, 5_000)),
-            np.round(rng.standard_normal((2, 80_000)) * 8) / 8]
+            np.round(rng.standard_normal((2, 80_000)) * 8) / 8 + 0.0]   # (+ 0.0: no negative zeros, whose order is free)
     for rows in sets:
         pts = E.to_device_points(rows)
         prep = E.PreparedSet(pts, -1)
@@ -99,7 +100,7 @@ def _prepared_digest():
 def test_prepared_sets_identical_under_both_sorts():
     mine = _prepared_digest()
     code = "import sys; sys.path.insert(0, %r); from tests.test_gpu_sort import _prepared_digest; print(_prepared_digest())" % ROOT
-    env = dict(os.environ, KSG_B200_SORT="cub")
+    env = dict(os.environ, KSG_B200_SORT="sample")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip().splitlines()[-1] == mine
