@@ -36,6 +36,12 @@ def main():
     cases.append(("mi 4D;4D (own-order marginals)", lambda: knn.mutual_information(
         c5["idxs_x"], c5["idxs_y"], c5["k"], d5)))
     cases.append(("entropy 3D", lambda: knn.differential_entropy(d4, 3, idxs=(0, 1, 2))))
+    rk = np.random.default_rng(8)
+    post, prior = rk.standard_normal((3, 20_003)), 1.2 * rk.standard_normal((3, 17_001)) + 0.1
+    cases.append(("KL divergence 3D (cross-set search)", lambda: knn.kullback_leibler_divergence(post, prior, 2)))
+    cases.append(("mi 1D;1D, KSG-2", lambda: knn.mutual_information(c["idxs_x"], c["idxs_y"], c["k"], d[:, :6_001], algorithm=2)))
+    cases.append(("cmi, p = 2 (Minkowski kernels)", lambda: knn.conditional_mutual_information(
+        c3["idxs_x"], c3["idxs_y"], c3["idxs_z"], c3["k"], d3[:, :5_003], p=2)))
     from syntropy_b200 import mixed
 
     rng = np.random.default_rng(6)
