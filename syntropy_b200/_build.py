@@ -92,7 +92,52 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+# ------------------------------------------------------------------ the torch extension (host C++ only)
+TORCH_EXT_SRC = os.path.join(PKG, "csrc_torch", "ksg_torch.cpp")
+TORCH_EXT = os.path.join(LIBDIR, "ksg_torch_ext.so")
+
+
+def torch_ext_is_stale() -> bool:
+    if not os.path.exists(TORCH_EXT):
+        return True
+    t = os.path.getmtime(TORCH_EXT)
+    return any(os.path.getmtime(d) > t for d in (TORCH_EXT_SRC, os.path.join(ROOT, "include", "ksg_b200.h")))
+
+
+def build_torch_ext(force: bool = False) -> str:
+    """Compile syntropy_b200/csrc_torch/ksg_torch.cpp into lib/ksg_torch_ext.so next to libksg_b200.so
+    (g++ only: the extension holds no device code; it links the C ABI library through an $ORIGIN rpath)."""
+    if not force and not torch_ext_is_stale():
+        return TORCH_EXT
+    build()  # the library it links against
+    import sysconfig
+
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if cxx is None:
+        raise RuntimeError("g++ not found; ksg_torch_ext.so cannot be built")
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    inc = []
+    for d in ce.include_paths(device_type="cuda") + [sysconfig.get_paths()["include"], os.path.join(ROOT, "include")]:
+        inc += ["-isystem", d]
+    abi = int(getattr(torch._C, "_GLIBCXX_USE_CXX11_ABI", True))
+    tmp = TORCH_EXT + ".tmp%d" % os.getpid()
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=ksg_torch_ext",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", f"-D_GLIBCXX_USE_CXX11_ABI={abi}", *inc, TORCH_EXT_SRC, "-o", tmp,
+           "-L", LIBDIR, "-lksg_b200", "-L", torch_lib, "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
+           "-ltorch_python", "-L", "/usr/local/cuda/lib64", "-lcudart",
+           "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + torch_lib, "-Wl,--no-as-needed"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("torch extension build failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr[-4000:])
+    os.replace(tmp, TORCH_EXT)
+    return TORCH_EXT
+
+
 if __name__ == "__main__":
     import sys
 
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_torch_ext(force="--force" in sys.argv))

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import _cabi
+from . import _text
 from . import dist as _dist
 
 
@@ -241,6 +242,31 @@ def to_device_points(rows, row_events: bool = False):
     return (out, events) if row_events else out
 
 
+def to_device_points_sharded(rows):
+    """``to_device_points`` for several ranks: every rank sends only ITS slice of every row over PCIe
+    (n / G samples instead of n) and the full rows are assembled by one NVLink all-gather per row --
+    the ranks share the host's PCIe / memory bandwidth, NVLink is not shared with anything.
+    Returns a (D, n) view (row stride G * ceil(n / G)) of the assembled tensor."""
+    dev = require_cuda()
+    if not isinstance(rows, RowSelection):
+        arr = np.asarray(rows)
+        rows = RowSelection(arr, range(arr.shape[0]))
+    dim, n = rows.shape
+    rank, ws = _dist.world()
+    c = _dist.chunk_len(n, ws)
+    q0, q1 = _dist.slice_of(n, rank, ws)
+    local_rows = RowSelection(rows.data[:, q0:q1], rows.idxs) if q1 > q0 else None
+    local = torch.zeros((dim, c), dtype=torch.float64, device=dev)
+    if local_rows is not None:
+        local[:, : q1 - q0].copy_(to_device_points(local_rows))
+    full = torch.empty((dim, ws * c), dtype=torch.float64, device=dev)
+    for d in range(dim):
+        _dist.all_gather_into(full[d], local[d])
+    return full[:, :n]
+
+
+SHARDED_UPLOAD_MIN = 1 << 16  # samples; below, the collectives cost more than the copies they save
+
 PINNED_RESULT_MAX_BYTES = 64 << 20
 
 
@@ -285,11 +311,23 @@ class KernelTimer:
     roofline; it is off (zero overhead) otherwise."""
 
     def __init__(self):
-        self.enabled = False
+        self._enabled = False
         self.records = []  # (name, start_event, end_event)
+
+    @property
+    def enabled(self):
+        return self._enabled
+
+    @enabled.setter
+    def enabled(self, on):
+        self._enabled = bool(on)
+        if _text.enabled() and (on or _text._ext is not None):
+            _text.load().set_timing(bool(on))  # the fused steps of the torch extension record their own spans
 
     def reset(self):
         self.records = []
+        if _text.enabled() and _text._ext is not None:
+            _text._ext.collect_spans()
 
     def span(self, name):
         return _Span(self, name)
@@ -299,6 +337,9 @@ class KernelTimer:
         out = {}
         for name, a, b in self.records:
             out.setdefault(name, []).append(a.elapsed_time(b))
+        if _text.enabled() and _text._ext is not None:
+            for name, values in _text._ext.collect_spans().items():
+                out.setdefault(name, []).extend(values)
         return out
 
 
@@ -444,6 +485,16 @@ class PreparedSet:
                                       C.byref(self.c), _stream())
         _cabi.check(rc, "ksg_prepare_rows")
         self.n, self.dim, self.ld = n, dim, int(self.c.ld)
+
+    @classmethod
+    def from_raw(cls, buf: torch.Tensor, struct_bytes: torch.Tensor) -> "PreparedSet":
+        """Wrap a prepared set built by the torch extension (owning buffer + the ksg_prepared bytes)."""
+        self = cls.__new__(cls)
+        self.buf = buf
+        self.c = _cabi.Prepared.from_buffer_copy(struct_bytes.numpy().tobytes())
+        self.n, self.dim, self.ld = int(self.c.n), int(self.c.dim), int(self.c.ld)
+        self.struct_bytes = struct_bytes
+        return self
 
     def _view(self, ptr, nbytes, dtype):
         off = int(ptr) - self.buf.data_ptr()
@@ -676,6 +727,8 @@ def finish_device(pw: Pointwise, n_total: int, out: torch.Tensor | None = None):
     else:
         ptw_full = _dist.gather_slices(pw.values, n_total)
         if pw.prep is not None:
+            if out is not None and _text.enabled() and getattr(pw.prep, "struct_bytes", None) is not None:
+                return _text.load().finish_step(ptw_full, pw.prep.struct_bytes, out), out  # scatter + sum, one call
             ptw_full = scatter_to_original(ptw_full, pw.prep)
     return ptw_full, device_sum(ptw_full, out=out)
 
@@ -686,6 +739,7 @@ def settle(pw: Pointwise, n_total: int, status: Status, ptw_full: torch.Tensor, 
     Returns the final ``(pw, ptw_full, total)``."""
     if pw.redo is None:
         return pw, ptw_full, total
+    _dist.sum_counts(status.nflag)  # unsettled queries of ALL ranks: every rank takes the same branch
     host = status.read_async()
     torch.cuda.current_stream().synchronize()
     if int(host[3]) == 0:
@@ -699,6 +753,8 @@ def settle(pw: Pointwise, n_total: int, status: Status, ptw_full: torch.Tensor, 
 def _finish(pw: Pointwise, n_total: int, status: Status):
     """Gather the pointwise slices of all ranks, reduce deterministically, copy out."""
     ptw_full, _ = finish_device(pw, n_total, out=status.total)
+    if pw.redo is not None:
+        _dist.sum_counts(status.nflag)  # unsettled queries of ALL ranks: every rank takes the same branch
     host = status.read_async()
     ptw = to_host(ptw_full)  # synchronises the stream: the status block has landed too
     if int(host[2]) != 0:
@@ -721,7 +777,11 @@ def ksg1_family(rows, k: int, masks, prog_builder):
     order; ``masks`` are subspace bitmasks over those D rows; ``prog_builder(psi_k,
     psi_N)`` returns the PsiProgram.
     """
-    pts, row_ready = to_device_points(rows, row_events=True)
+    n_samples = rows.shape[1] if isinstance(rows, RowSelection) else np.asarray(rows).shape[1]
+    if _dist.world()[1] > 1 and n_samples >= SHARDED_UPLOAD_MIN:
+        pts, row_ready = to_device_points_sharded(rows), None
+    else:
+        pts, row_ready = to_device_points(rows, row_events=True)
     status = Status(pts.device)
     # (orders the stream after the row copies)
     pw = ksg1_device(pts, k, masks, prog_builder, row_ready=row_ready, status=status)
@@ -812,9 +872,12 @@ def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder, row_ready=None,
         # everything is counted in the joint order: keep the slices sorted until the end
         windowed = config.engine == "windowed"
         q0, q1 = _dist.my_slice(n)
+        # (several ranks: each runs its slice speculatively; the flag counters are summed over the
+        #  ranks before anybody looks at them, so all ranks take the same branch -- see settle / _finish)
+        speculative = (status is not None and n > 0 and all(bin(int(m)).count("1") == 1 for m in masks))
+        if speculative and _text.enabled():
+            return _ksg1_step_ext(pts, k, masks, prog, n, q0, q1, windowed, row_ready, status)
         prep = PreparedSet(pts, order_for(dim), row_ready=row_ready)
-        speculative = (status is not None and q1 - q0 == n and n > 0
-                       and all(bin(int(m)).count("1") == 1 for m in masks))
         if speculative:
             eps, _, flags, _ = _fast_knn_call(prep, k + 1, q0, q1, windowed, nflag=status.nflag)
             counts = fast_counts(prep, masks, eps, q0, q1, windowed)
@@ -830,6 +893,30 @@ def ksg1_device(pts: torch.Tensor, k: int, masks, prog_builder, row_ready=None,
         return Pointwise(psi_epilogue(counts, prog, n), prep=prep, preps=[prep])
     _, counts, preps = radius_and_counts(pts, k, masks, row_ready=row_ready)
     return Pointwise(psi_epilogue(counts, prog, n), full=True, preps=preps)
+
+
+def _ksg1_step_ext(pts, k, masks, prog: PsiProgram, n, q0, q1, windowed, row_ready, status: Status) -> Pointwise:
+    """The speculative 1-D-marginal step as ONE call into the torch extension (ksg_torch.cpp:ksg1_step):
+    prepared set, k-NN radii, one binary-search count per marginal and the psi program are enqueued
+    by C++ without coming back to Python in between."""
+    ext = _text.load()
+    dim = pts.shape[0]
+    axes = [int(m).bit_length() - 1 for m in masks]
+    table = psi_table(n + 2)
+    steps = prog.steps
+    ready = [int(ev.cuda_event) for ev in row_ready] if row_ready else []
+    ptw, prep_buf, prep_struct, eps, flags, _counts = ext.ksg1_step(
+        pts, k, axes, prog.init, prog.psi_n, prog.scale is not None, 0.0 if prog.scale is None else prog.scale,
+        [st[0] for st in steps], [st[1] for st in steps], [st[2] for st in steps], [st[3] for st in steps],
+        [st[4] for st in steps], table, q0, q1, windowed, order_for(dim), KNN_MARGIN, status.nflag, ready)
+    prep = PreparedSet.from_raw(prep_buf, prep_struct)
+
+    def redo():
+        eps2, _ = _fast_knn_escalate(prep, k + 1, q0, q1, windowed, False, eps, None, flags)
+        counts2 = fast_counts(prep, masks, eps2, q0, q1, windowed)
+        return Pointwise(psi_epilogue(counts2, prog, n), prep=prep, preps=[prep])
+
+    return Pointwise(ptw, prep=prep, preps=[prep], redo=redo)
 
 
 def ksg2_family(rows, k: int, masks, prog_builder):

@@ -76,3 +76,24 @@ def sum_counts(local: torch.Tensor) -> torch.Tensor:
         return local
     td.all_reduce(local, op=td.ReduceOp.SUM, group=_group)
     return local
+
+
+def all_gather_into(out: torch.Tensor, local: torch.Tensor) -> None:
+    """``out`` (contiguous, world_size * local.numel() elements) = the ranks' ``local`` chunks in rank order."""
+    _, ws = world()
+    if ws == 1:
+        out.copy_(local)
+        return
+    if td.get_backend(_group) == "nccl":
+        td.all_gather_into_tensor(out, local.contiguous(), group=_group)
+    else:
+        c = local.numel()
+        td.all_gather([out[i * c:(i + 1) * c] for i in range(ws)], local.contiguous(), group=_group)
+
+
+def any_flag(flag: torch.Tensor) -> torch.Tensor:
+    """In-place OR (as a max) of an integer flag over the ranks."""
+    _, ws = world()
+    if ws > 1:
+        td.all_reduce(flag, op=td.ReduceOp.MAX, group=_group)
+    return flag
