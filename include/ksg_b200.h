@@ -235,6 +235,15 @@ typedef struct {
                             engine, which skips most of the n x n pairs) */
     uint64_t* curve_keys; /* [n] ascending space-filling-curve keys of the rows (primary == -1 only; else NULL):
                             lets ksg_cross_prepare place foreign query points on the same curve */
+    double* curve_table;  /* [dim][1026] (primary == -1, early order; else NULL): per coordinate [min, sorted
+                            sample of 1024 values, max] -- the monotone map behind the curve coordinates */
+    void* axes_ready;     /* cudaEvent_t or NULL.  Early order (primary == -1): the curve is built from the
+                            table above, and the EXACT coordinate sorts behind axis_vals / axis_pos run on
+                            side streams of the library underneath whatever the caller enqueues next
+                            (the k-NN stage).  Every entry point that reads them (ksg_axis_count,
+                            ksg_fast_count) and ksg_fast_knn* order the caller's stream after this event
+                            themselves; a caller that frees or reuses the buffer without having called any
+                            of them calls ksg_prepare_join first. */
 } ksg_prepared;
 
 /*
@@ -257,6 +266,8 @@ typedef struct {
  * after all the events.
  */
 size_t ksg_prepare_workspace(int64_t n, int dim);
+/* Order `stream` after every piece of library-side work on the prepared set (see axes_ready). */
+int ksg_prepare_join(const ksg_prepared* h_prep, void* stream);
 int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int primary,
                 void* d_buffer, size_t buffer_bytes, ksg_prepared* h_out, void* stream);
 int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int primary,

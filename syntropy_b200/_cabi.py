@@ -45,6 +45,8 @@ class Prepared(C.Structure):
         ("sub_box", C.c_void_p),
         ("flags", C.c_void_p),
         ("curve_keys", C.c_void_p),
+        ("curve_table", C.c_void_p),
+        ("axes_ready", C.c_void_p),
     ]
 
 
@@ -91,6 +93,7 @@ SIGNATURES = {
     "ksg_paircount_fixed_radius": (C.c_int, [_c_vp, _c_vp, _c_i64, C.c_int, C.c_double, _c_i64, _c_i64,
                                              _c_vp, _c_vp]),
     "ksg_prepare_workspace": (C.c_size_t, [_c_i64, C.c_int]),
+    "ksg_prepare_join": (C.c_int, [_c_prep, _c_vp]),
     "ksg_prepare": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, C.c_int, _c_vp, C.c_size_t, _c_prep, _c_vp]),
     "ksg_prepare_rows": (C.c_int, [_c_vp, _c_i64, _c_i64, C.c_int, C.c_int, C.POINTER(C.c_void_p), _c_vp, C.c_size_t,
                                    _c_prep, _c_vp]),

@@ -486,6 +486,15 @@ class PreparedSet:
         _cabi.check(rc, "ksg_prepare_rows")
         self.n, self.dim, self.ld = n, dim, int(self.c.ld)
 
+    def __del__(self):
+        # the exact coordinate sorts of an early-order set run on side streams of the library: order
+        # the current stream after them BEFORE the buffer goes back to the caching allocator
+        try:
+            if getattr(self, "c", None) is not None and self.c.axes_ready and _cuda_ready:
+                _cabi.load().ksg_prepare_join(C.byref(self.c), _stream())
+        except Exception:
+            pass
+
     @classmethod
     def from_raw(cls, buf: torch.Tensor, struct_bytes: torch.Tensor) -> "PreparedSet":
         """Wrap a prepared set built by the torch extension (owning buffer + the ksg_prepared bytes)."""
@@ -519,7 +528,11 @@ class PreparedSet:
         return int(t[2]), int(t[3])
 
 
-KNN_MARGIN = 3          # list entries the filter keeps beyond k' (ksg_fast_knn's default)
+KNN_MARGIN = 3          # list entries the filter keeps beyond k' (ksg_fast_knn's default; dense engine)
+KNN_MARGIN_WINDOWED = 6  # windowed engine: under tight seeds a query meets ~k' + 2 candidates below its
+#                          seed; with k' + 3 slots every other list filled up and paid a replace-the-
+#                          maximum sweep per further hit (14 % of the units kernel's instructions,
+#                          profiles/r2c_*), with k' + 6 the fill phase (append, no sweep) nearly always suffices
 KNN_WIDE_MARGIN = 24    # second pass for tie-saturated (quantised) data
 
 
@@ -534,12 +547,22 @@ def _lists_fit(dim: int, kcap: int) -> bool:
     return ring + kcap * queries_per_block * 8 <= 200 * 1024 and kcap <= 64
 
 
+def default_margin(windowed: bool, kprime: int, dim: int) -> int:
+    # (from 5 coordinates up the seeds are loose -- ball volume x10 and more -- and every list fills
+    #  whatever its length: longer lists would only cost shared memory and longer sweeps there)
+    if windowed and dim <= 4 and kprime + KNN_MARGIN_WINDOWED <= 64 and _lists_fit(dim, kprime + KNN_MARGIN_WINDOWED):
+        return KNN_MARGIN_WINDOWED
+    return KNN_MARGIN
+
+
 def _fast_knn_call(prep: PreparedSet, kprime: int, q0: int, q1: int, windowed: bool, q_index=None,
-                   want_indices: bool = False, margin: int = KNN_MARGIN, nflag: torch.Tensor | None = None):
+                   want_indices: bool = False, margin: int | None = None, nflag: torch.Tensor | None = None):
     """One ksg_fast_knn_margin launch sequence (nothing is read back).  ``nflag``: a zeroed int32[1]
     device counter to use instead of a fresh one."""
     lib = _cabi.load()
     nq = q1 - q0
+    if margin is None:
+        margin = default_margin(windowed and q_index is None, kprime, prep.dim)
     dev = prep.buf.device
     eps = torch.empty(nq, dtype=torch.float64, device=dev)
     idx = torch.empty((nq, kprime), dtype=torch.int64, device=dev) if want_indices else None
@@ -908,7 +931,8 @@ def _ksg1_step_ext(pts, k, masks, prog: PsiProgram, n, q0, q1, windowed, row_rea
     ptw, prep_buf, prep_struct, eps, flags, _counts = ext.ksg1_step(
         pts, k, axes, prog.init, prog.psi_n, prog.scale is not None, 0.0 if prog.scale is None else prog.scale,
         [st[0] for st in steps], [st[1] for st in steps], [st[2] for st in steps], [st[3] for st in steps],
-        [st[4] for st in steps], table, q0, q1, windowed, order_for(dim), KNN_MARGIN, status.nflag, ready)
+        [st[4] for st in steps], table, q0, q1, windowed, order_for(dim), default_margin(windowed, k + 1, dim),
+        status.nflag, ready)
     prep = PreparedSet.from_raw(prep_buf, prep_struct)
 
     def redo():

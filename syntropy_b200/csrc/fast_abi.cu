@@ -76,9 +76,13 @@ static inline PreparedLayout prepared_layout(int64_t n, int dim) {
     L.off_mkeys = take((size_t)L.ld * 8);
     L.off_mkeys_out = take((size_t)L.ld * 8);
     L.off_invperm = take((size_t)L.ld * 4);
+    L.off_curve_table = take((size_t)KSG_MAX_DIM * CURVE_TABLE * 8);
+    L.off_stats = take((size_t)KSG_MAX_DIM * STATS_BLOCKS * 2 * 8);
     L.cub_bytes = align_up(cub_sort_bytes(n), 256);
     L.sort_lanes = dim < SORT_LANES ? dim : SORT_LANES;
-    L.off_cub = take(L.cub_bytes * L.sort_lanes);  // one CUB scratch area per concurrent coordinate sort
+    // one CUB scratch area per concurrent coordinate sort (early order: area 0 = the key sort on the
+    // caller's stream, areas 1.. = the coordinate sorts on the side streams)
+    L.off_cub = take(L.cub_bytes * SORT_LANES);
     L.total = o;
     return L;
 }
@@ -87,9 +91,13 @@ static inline PreparedLayout prepared_layout(int64_t n, int dim) {
 // (a one-sweep pass moves 24 MB in ~15 us): they run side by side on up to SORT_LANES streams --
 // lane 0 is the caller's stream, the others are helper streams of this library (one set per
 // device, created on first use) forked from / joined to the caller's stream with events.
+constexpr int AXES_EVENTS = 256;  // ring of "exact coordinate sorts of this prepared set are done" events
 struct SortLanes {
     cudaStream_t helper[SORT_LANES - 1];
     cudaEvent_t fork, join[SORT_LANES - 1];
+    cudaEvent_t perm_ready;               // early order: the curve permutation exists (main stream)
+    cudaEvent_t axes_ready[AXES_EVENTS];  // early order: axis_vals / axis_pos are final (side stream)
+    unsigned next_axes;
     bool ready;
 };
 static SortLanes* sort_lanes_for_device() {
@@ -105,6 +113,10 @@ static SortLanes* sort_lanes_for_device() {
             if (cudaStreamCreateWithFlags(&L.helper[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
             if (cudaEventCreateWithFlags(&L.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
+        if (cudaEventCreateWithFlags(&L.perm_ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int i = 0; i < AXES_EVENTS; ++i)
+            if (cudaEventCreateWithFlags(&L.axes_ready[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        L.next_axes = 0;
         L.ready = true;
     }
     return &L;
@@ -125,7 +137,22 @@ struct GraphKey {
     int64_t i64[3];
     int32_t i32[4];
 };
-enum { GRAPH_AXIS_SORT = 1, GRAPH_PREPARE_TAIL = 2 };
+enum { GRAPH_AXIS_SORT = 1, GRAPH_PREPARE_TAIL = 2, GRAPH_PREPARE_EARLY = 3 };
+
+// KSG_B200_EARLY_ORDER=0: the curve waits for the exact coordinate sorts again (A/B measurements)
+static bool early_order() {
+    static const bool v = [] {
+        const char* e = getenv("KSG_B200_EARLY_ORDER");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+
+// Order `st` after the side-stream work of an early-order prepared set (no-op otherwise).
+static int wait_axes(const ksg_prepared* P, cudaStream_t st) {
+    if (P->axes_ready) KSG_CUDA_TRY(cudaStreamWaitEvent(st, (cudaEvent_t)P->axes_ready, 0));
+    return KSG_OK;
+}
 constexpr size_t GRAPH_CACHE_ENTRIES = 32;
 
 class GraphCache {
@@ -383,6 +410,11 @@ size_t ksg_prepare_workspace(int64_t n, int dim) {
     return prepared_layout(n, dim).total;
 }
 
+int ksg_prepare_join(const ksg_prepared* P, void* stream) {
+    KSG_REQUIRE(P, "ksg_prepare_join: null pointer");
+    return wait_axes(P, as_stream2(stream));
+}
+
 int ksg_prepare(const double* d_points, int64_t ld, int64_t n, int dim, int primary, void* d_buffer,
                 size_t buffer_bytes, ksg_prepared* h_out, void* stream) {
     return ksg_prepare_rows(d_points, ld, n, dim, primary, nullptr, d_buffer, buffer_bytes, h_out, stream);
@@ -421,9 +453,108 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     KSG_LAUNCHED2();
     const unsigned nb = (unsigned)ceil_div(n, 256);
     int rc;
+    P.tile_box = (float*)(base + L.off_tile_box);
+    P.sub_box = (float*)(base + L.off_sub_box);
+    if (primary == -1) P.curve_keys = (uint64_t*)(base + L.off_mkeys_out);
+    SortLanes* lanes = sort_lanes_for_device();
+
+    if (primary == -1 && early_order() && lanes) {
+        // ================= early order: the curve from approximate ranks on `st`, the exact coordinate
+        // sorts (+ their remap into the prepared order) on the side streams, joined by P.axes_ready
+        P.curve_table = (double*)(base + L.off_curve_table);
+        double* stats = (double*)(base + L.off_stats);
+        unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
+        unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
+        int32_t* invperm = (int32_t*)(base + L.off_invperm);
+        const int n_side = SORT_LANES - 1;
+        KSG_CUDA_TRY(cudaEventRecord(lanes->fork, st));  // (iota exists: the sorts' payload)
+        for (int l = 0; l < n_side && l < dim; ++l) KSG_CUDA_TRY(cudaStreamWaitEvent(lanes->helper[l], lanes->fork, 0));
+        for (int d = 0; d < dim; ++d) {
+            cudaStream_t ls = lanes->helper[d % n_side];
+            if (h_row_ready && h_row_ready[d]) KSG_CUDA_TRY(cudaStreamWaitEvent(ls, (cudaEvent_t)h_row_ready[d], 0));
+            void* lane_tmp = cub_base + (size_t)(1 + d % n_side) * L.cub_bytes;  // (area 0: the key sort on `st`)
+            const double* keys_in = d_points + (int64_t)d * ld;
+            double* keys_out = P.axis_vals + (int64_t)d * L.ld;
+            int32_t* pos_out = P.axis_pos + (int64_t)d * L.ld;
+            rc = graph_cache().run(graph_key(GRAPH_AXIS_SORT, {keys_in, keys_out, iota, pos_out, lane_tmp}, {n}, {}), ls,
+                                   [&](cudaStream_t s2) {
+                                       return sort_pairs(lane_tmp, L.cub_bytes, keys_in, keys_out, iota, pos_out, n, s2);
+                                   });
+            if (rc) return rc;
+        }
+        if (h_row_ready)
+            for (int d = 0; d < dim; ++d)
+                if (h_row_ready[d]) KSG_CUDA_TRY(cudaStreamWaitEvent(st, (cudaEvent_t)h_row_ready[d], 0));
+        int rank_bits, bits;
+        curve_bits(n, dim, &rank_bits, &bits);
+        if ((size_t)dim * CURVE_TABLE * sizeof(double) > 48 * 1024) {  // (outside any capture)
+            const int bytes = (int)((size_t)dim * CURVE_TABLE * sizeof(double));
+            cudaError_t e = cudaSuccess;
+            switch (dim) {
+                case 6: e = cudaFuncSetAttribute(curve_key_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); break;
+                case 7: e = cudaFuncSetAttribute(curve_key_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); break;
+                case 8: e = cudaFuncSetAttribute(curve_key_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); break;
+                default: e = cudaFuncSetAttribute(curve_key_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            }
+            KSG_CUDA_TRY(e);
+        }
+        auto early = [&](cudaStream_t st) -> int {
+            stats_stage1_kernel<<<dim3(STATS_BLOCKS, dim), 256, 0, st>>>(d_points, ld, n, stats, P.flags);
+            KSG_LAUNCHED2();
+            curve_table_kernel<<<dim, 512, 0, st>>>(d_points, ld, n, stats, P.curve_table, P.center, P.maxabs);
+            KSG_LAUNCHED2();
+            const size_t tsmem = (size_t)dim * CURVE_TABLE * sizeof(double);
+            switch (dim) {
+#define KSG_CKEY(D) case D: curve_key_kernel<D><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, bits, mkeys, nullptr); break;
+                KSG_CKEY(1) KSG_CKEY(2) KSG_CKEY(3) KSG_CKEY(4) KSG_CKEY(5) KSG_CKEY(6) KSG_CKEY(7) KSG_CKEY(8)
+#undef KSG_CKEY
+                default: curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, bits, mkeys, nullptr);
+            }
+            KSG_LAUNCHED2();
+            if (use_sample_sort(n)) {
+                const int rc2 = sample_sort_launch<unsigned long long>(cub_tmp, mkeys, mkeys_out, P.perm, n, st);
+                if (rc2) return rc2;
+            } else {
+                size_t need = L.cub_bytes;
+                cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, mkeys, mkeys_out, iota, P.perm, (int)n, 0,
+                                                                bits * dim, st);
+                if (e != cudaSuccess) { set_error("cub SortPairs (curve): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+                note_launch();
+            }
+            gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
+                d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
+            KSG_LAUNCHED2();
+            invert_perm_kernel<<<nb, 256, 0, st>>>(P.perm, n, invperm);
+            KSG_LAUNCHED2();
+            tile_box_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 128, 0, st>>>(P.shadow_f32, L.dim_padded, P.tile_box,
+                                                                                 P.sub_box);
+            KSG_LAUNCHED2();
+            return KSG_OK;
+        };
+        rc = graph_cache().run(graph_key(GRAPH_PREPARE_EARLY, {d_points, d_buffer}, {n, ld}, {dim, primary}), st, early);
+        if (rc) return rc;
+        KSG_CUDA_TRY(cudaEventRecord(lanes->perm_ready, st));
+        // side lane 0 collects the other lanes and the permutation, then remaps axis_pos
+        cudaStream_t s0 = lanes->helper[0];
+        for (int l = 1; l < n_side && l < dim; ++l) {
+            KSG_CUDA_TRY(cudaEventRecord(lanes->join[l], lanes->helper[l]));
+            KSG_CUDA_TRY(cudaStreamWaitEvent(s0, lanes->join[l], 0));
+        }
+        KSG_CUDA_TRY(cudaStreamWaitEvent(s0, lanes->perm_ready, 0));
+        remap_axis_kernel<<<dim3(nb, dim), 256, 0, s0>>>(P.axis_pos, L.ld, n, invperm);
+        KSG_LAUNCHED2();
+        cudaEvent_t done = lanes->axes_ready[lanes->next_axes++ % AXES_EVENTS];
+        KSG_CUDA_TRY(cudaEventRecord(done, s0));
+        P.axes_ready = (void*)done;
+        *h_out = P;
+        return KSG_OK;
+    }
+
+    // ================= exact order: every coordinate sorted first (kd order, single-coordinate order,
+    // KSG_B200_EARLY_ORDER=0)
     // every coordinate sorted on its own: values + ORIGINAL sample index (remapped below);
     // coordinate d runs on lane d % sort_lanes (see SortLanes)
-    SortLanes* lanes = L.sort_lanes > 1 ? sort_lanes_for_device() : nullptr;
+    if (L.sort_lanes <= 1) lanes = nullptr;
     const int n_lanes = lanes ? L.sort_lanes : 1;
     if (n_lanes > 1) {
         KSG_CUDA_TRY(cudaEventRecord(lanes->fork, st));
@@ -447,9 +578,6 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
         KSG_CUDA_TRY(cudaEventRecord(lanes->join[l - 1], lanes->helper[l - 1]));
         KSG_CUDA_TRY(cudaStreamWaitEvent(st, lanes->join[l - 1], 0));
     }
-    P.tile_box = (float*)(base + L.off_tile_box);
-    P.sub_box = (float*)(base + L.off_sub_box);
-    if (primary == -1) P.curve_keys = (uint64_t*)(base + L.off_mkeys_out);
     // everything behind the coordinate sorts, as one cached launch sequence
     auto tail = [&](cudaStream_t st) -> int {
         // centre of the fp32 copy = per-coordinate MEDIAN (the bulk of the points then has small centred
@@ -609,7 +737,8 @@ int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, c
         rc = launch_knn_plan(P->dim_padded, a);
         if (rc) return rc;
         rc = launch_knn_units(P->dim_padded, a);
-        if (rc || a.ra.fused) return rc;  // fused: every block was refined inside the units kernel
+        if (rc) return rc;
+        if (a.ra.fused) return wait_axes(P, st);  // fused: every block was refined inside the units kernel
     } else {
         rc = launch_knn_f32(P->dim_padded, a);
     }
@@ -620,7 +749,9 @@ int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, c
                                                                    p.qb, P->perm, d_idx_out, nullptr, 0, P->center,
                                                                    d_eps_out, d_flags, d_n_flagged);
     KSG_LAUNCHED2();
-    return KSG_OK;
+    // from here on the caller's stream is also behind the side-stream work of the prepared set (the
+    // exact coordinate sorts ran underneath the kernels above)
+    return wait_axes(P, st);
 }
 
 // ---------------------------------------------------------------- cross-set queries
@@ -685,6 +816,12 @@ int ksg_cross_prepare(const ksg_prepared* P, const double* d_queries, int64_t ld
     const unsigned nb = (unsigned)ceil_div(nq, 256);
     int rank_bits, bits;
     curve_bits(P->n, dim, &rank_bits, &bits);
+    if (P->curve_table) {
+        // the candidates' curve was built from their coordinate table: place the queries with the same map
+        const size_t tsmem = (size_t)dim * CURVE_TABLE * sizeof(double);
+        if (tsmem > 48 * 1024) KSG_CUDA_TRY(cudaFuncSetAttribute(curve_key_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_queries, ldq, nq, dim, P->curve_table, bits, keys, iota);
+    } else
     switch (dim) {
 #define KSG_CROSS(D) case D: cross_key_kernel<D><<<nb, 256, 0, st>>>(d_queries, ldq, nq, P->axis_vals, P->ld, P->n, dim, rank_bits, bits, keys, iota); break;
         KSG_CROSS(1) KSG_CROSS(2) KSG_CROSS(3) KSG_CROSS(4) KSG_CROSS(5) KSG_CROSS(6) KSG_CROSS(7) KSG_CROSS(8)
@@ -757,14 +894,15 @@ int ksg_fast_knn_cross(const ksg_prepared* P, const ksg_cross* X, int64_t q_begi
     int rc = launch_knn_plan(P->dim_padded, a);
     if (rc) return rc;
     rc = launch_knn_units(P->dim_padded, a);
-    if (rc || a.ra.fused) return rc;
+    if (rc) return rc;
+    if (a.ra.fused) return wait_axes(P, st);
     knn_refine_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(a.part_d32, a.part_idx, p.kcap, 1, kprime,
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    nullptr, X->maxabs, a.seed_thr, a.unit_first, p.qb,
                                                                    P->perm, nullptr, X->sorted_f64, X->ld, P->center,
                                                                    d_eps_out, d_flags, d_n_flagged);
     KSG_LAUNCHED2();
-    return KSG_OK;
+    return wait_axes(P, st);
 }
 
 struct FastCountPlan {
@@ -823,6 +961,10 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
         KSG_REQUIRE(h_masks[s] != 0 && (h_masks[s] & ~all) == 0, "ksg_fast_count: empty or out-of-range mask");
     }
     cudaStream_t st = as_stream2(stream);
+    {
+        const int rc0 = wait_axes(P, st);  // (the band resolution reads axis_vals / axis_pos)
+        if (rc0) return rc0;
+    }
     float* thresholds = (float*)d_workspace;
     const int64_t total = (int64_t)n_subspaces * nq;
     fill_i32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(d_counts, total, bias);
@@ -905,6 +1047,10 @@ int ksg_axis_count(const ksg_prepared* P, int axis, int64_t q_begin, int64_t q_e
     KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_axis_count: bad query range");
     const int64_t nq = q_end - q_begin;
     if (nq == 0) return KSG_OK;
+    {
+        const int rc0 = wait_axes(P, as_stream2(stream));
+        if (rc0) return rc0;
+    }
     axis_count_kernel<<<(unsigned)ceil_div(nq, AXIS_THREADS), AXIS_THREADS, 0, as_stream2(stream)>>>(
         P->sorted_f64 + (int64_t)axis * P->ld, P->axis_vals + (int64_t)axis * P->ld, P->n, q_begin, nq, d_eps,
         strict ? 1 : 0, bias, d_counts);

@@ -16,6 +16,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "sample_sort.cuh"
 
 namespace ksg {
 
@@ -34,7 +35,7 @@ struct PreparedLayout {
     int dim_padded;
     size_t off_perm, off_sorted, off_shadow, off_axis_vals, off_axis_pos, off_center, off_maxabs, off_flags;
     size_t off_tile_box, off_sub_box;
-    size_t off_iota, off_ranks, off_mkeys, off_mkeys_out, off_invperm, off_cub;
+    size_t off_iota, off_ranks, off_mkeys, off_mkeys_out, off_invperm, off_cub, off_curve_table, off_stats;
     size_t cub_bytes;  // per sort lane
     int sort_lanes;
     size_t total;
@@ -177,6 +178,107 @@ __device__ __forceinline__ unsigned long long hilbert_index(unsigned int (&X)[CA
         for (int d = 0; d < CAP; ++d)
             if (d < dim) key = (key << 1) | ((X[d] >> (bits - 1 - level)) & 1u);
     return key;
+}
+
+// ---- approximate ranks for the curve (primary = -1, "early order").  The Hilbert order only needs a
+// monotone, roughly rank-uniform map of every coordinate -- not its exact ranks -- so the curve keys
+// need not wait for the exact coordinate sorts (eight radix passes each): a stratified sample of
+// CURVE_SAMPLES values per coordinate is sorted by one CTA, and a value's curve coordinate is its
+// position among [min, sample..., max] refined by linear interpolation inside its gap.  The exact sorts
+// (needed by the 1-D counts and the band look-ups, i.e. AFTER the k-NN stage) then run on the
+// library's side streams underneath the k-NN kernels.  Any monotone map gives a valid, spatially
+// coherent order; results never depend on it.
+constexpr int CURVE_SAMPLES = 1024;
+constexpr int CURVE_TABLE = CURVE_SAMPLES + 2;  // [min, sorted sample, max]
+
+// grid = dim CTAs of 512 threads.  partial: the (min, max) pairs of stats_stage1_kernel.
+static __global__ void __launch_bounds__(512)
+curve_table_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, const double* __restrict__ partial,
+                   double* __restrict__ table, double* __restrict__ center, double* __restrict__ maxabs) {
+    __shared__ uint64_t sk[CURVE_SAMPLES];
+    __shared__ uint32_t si[CURVE_SAMPLES];
+    __shared__ double s_lo[512], s_hi[512];
+    const int d = blockIdx.x, tid = threadIdx.x;
+    const double* row = pts + (int64_t)d * ld;
+    for (int s = tid; s < CURVE_SAMPLES; s += 512) {
+        const uint64_t lo = (uint64_t)s * (uint64_t)n / CURVE_SAMPLES, hi = (uint64_t)(s + 1) * (uint64_t)n / CURVE_SAMPLES;
+        uint64_t e = lo + (hi > lo ? ss_hash((uint32_t)s * 2654435761u + 977u * (uint32_t)d) % (hi - lo) : 0);
+        if (e >= (uint64_t)n) e = (uint64_t)n - 1;
+        sk[s] = ss_key_of(row[e]);
+        si[s] = (uint32_t)s;
+    }
+    double lo = CUDART_INF, hi = -CUDART_INF;
+    for (int b = tid; b < STATS_BLOCKS; b += 512) {
+        lo = fmin(lo, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 0]);
+        hi = fmax(hi, partial[((int64_t)d * STATS_BLOCKS + b) * 2 + 1]);
+    }
+    s_lo[tid] = lo;
+    s_hi[tid] = hi;
+    __syncthreads();
+    ss_bitonic(sk, si, CURVE_SAMPLES, tid, 512);
+    for (int off = 256; off > 0; off >>= 1) {
+        if (tid < off) {
+            s_lo[tid] = fmin(s_lo[tid], s_lo[tid + off]);
+            s_hi[tid] = fmax(s_hi[tid], s_hi[tid + off]);
+        }
+        __syncthreads();
+    }
+    double* out = table + (int64_t)d * CURVE_TABLE;
+    for (int s = tid; s < CURVE_SAMPLES; s += 512) ss_store_key(&out[1 + s], sk[s]);
+    if (tid == 0) {
+        double c;
+        ss_store_key(&c, sk[CURVE_SAMPLES / 2]);  // sample median: the centre of the fp32 copy
+        double mn = s_lo[0], mx = s_hi[0];
+        if (!isfinite(c)) c = 0.0;  // non-finite input is flagged (stats_stage1_kernel); keep the math finite
+        if (!isfinite(mn)) mn = c;
+        if (!isfinite(mx)) mx = c;
+        out[0] = mn;
+        out[CURVE_TABLE - 1] = mx;
+        center[d] = c;
+        maxabs[d] = fmax(fabs(mx - c), fabs(c - mn)) * (1.0 + 1e-12) + 1e-300;
+    }
+}
+
+// curve coordinate of x in [0, 2^bits): monotone in x (tb: CURVE_TABLE ascending values)
+__device__ __forceinline__ unsigned int curve_coord(double x, const double* __restrict__ tb, int bits) {
+    int lo = 0, hi = CURVE_TABLE;  // number of table entries <= x
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tb[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    double pos = 0.0;  // in [0, CURVE_TABLE - 1]
+    if (lo >= CURVE_TABLE) {
+        pos = (double)(CURVE_TABLE - 1);
+    } else if (lo > 0) {
+        const double a = tb[lo - 1], b = tb[lo];
+        double f = b > a ? (x - a) / (b - a) : 0.0;
+        if (!(f >= 0.0)) f = 0.0;
+        if (f > 1.0) f = 1.0;
+        pos = (double)(lo - 1) + f;
+    }
+    const double scaled = pos * ((double)(1u << bits) / (double)(CURVE_TABLE - 1));
+    unsigned int c = (unsigned int)scaled;
+    const unsigned int top = (1u << bits) - 1u;
+    return c > top ? top : c;
+}
+
+// keys[i] = Hilbert index of point i's curve coordinates.  Dynamic shared memory: dim * CURVE_TABLE doubles.
+template <int DIM>
+static __global__ void __launch_bounds__(256)
+curve_key_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, int dim_rt, const double* __restrict__ table,
+                 int bits, unsigned long long* __restrict__ keys, int32_t* __restrict__ iota) {
+    extern __shared__ double s_table[];
+    const int dim = DIM > 0 ? DIM : dim_rt;
+    for (int i = threadIdx.x; i < dim * CURVE_TABLE; i += 256) s_table[i] = table[i];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    unsigned int X[DIM > 0 ? DIM : KSG_MAX_DIM];
+#pragma unroll
+    for (int d = 0; d < (DIM > 0 ? DIM : KSG_MAX_DIM); ++d)
+        if (d < dim) X[d] = curve_coord(pts[(int64_t)d * ld + i], s_table + d * CURVE_TABLE, bits);
+    keys[i] = hilbert_index(X, dim, bits);
+    if (iota) iota[i] = (int32_t)i;
 }
 
 // bits per coordinate of the curve for n points in `dim` coordinates (shared by ksg_prepare and

@@ -97,7 +97,7 @@ def test_ctypes_structs_mirror_the_header():
     assert [f[0] for f in _cabi.Prepared._fields_] == _header_struct_fields("ksg_prepared")
     assert [f[0] for f in _cabi.Cross._fields_] == _header_struct_fields("ksg_cross")
     # all-pointer tails and 8-byte scalars: no padding surprises
-    assert C.sizeof(_cabi.Prepared) == 8 + 4 * 4 + 8 * 2 + 8 * 11
+    assert C.sizeof(_cabi.Prepared) == 8 + 4 * 4 + 8 * 2 + 8 * 13
     assert C.sizeof(_cabi.Cross) == 8 * 7
 
 
