@@ -78,6 +78,7 @@ static inline PreparedLayout prepared_layout(int64_t n, int dim) {
     L.off_invperm = take((size_t)L.ld * 4);
     L.off_curve_table = take((size_t)KSG_MAX_DIM * CURVE_TABLE * 8);
     L.off_stats = take((size_t)KSG_MAX_DIM * STATS_BLOCKS * 2 * 8);
+    L.off_exact = take((size_t)EXACT_INFO_INTS * 4);
     L.cub_bytes = align_up(cub_sort_bytes(n), 256);
     L.sort_lanes = dim < SORT_LANES ? dim : SORT_LANES;
     // one CUB scratch area per concurrent coordinate sort (early order: area 0 = the key sort on the
@@ -349,6 +350,7 @@ static void fill_refine_args(KnnF32Args& a, const ksg_prepared* P, int kprime, c
     a.ra.qld = qld;
     a.ra.center = P->center;
     a.ra.maxabs = maxabs;
+    a.ra.exact32 = qsorted ? nullptr : P->flags + 8;  // (foreign queries: their shadows were never analysed)
     a.ra.perm = P->perm;
     a.ra.idx_out = d_idx_out;
     a.ra.eps_out = d_eps_out;
@@ -444,9 +446,19 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     P.maxabs = (double*)(base + L.off_maxabs);
     P.flags = (int32_t*)(base + L.off_flags);
     int32_t* iota = (int32_t*)(base + L.off_iota);
+    int32_t* exact_info = (int32_t*)(base + L.off_exact);
     char* cub_base = base + L.off_cub;
     void* cub_tmp = cub_base;
     cudaStream_t st = as_stream2(stream);
+    // byte patterns: exact_info[0] = 0, then (min -> 0x7f7f7f7f, max -> 0x80808080) per coordinate
+    auto exact_setup = [&](int32_t* info, cudaStream_t s2) -> int {
+        static const bool off = [] { const char* e = getenv("KSG_B200_EXACT32"); return e && e[0] == '0'; }();
+        if (cudaMemsetAsync(info, 0x7f, (size_t)EXACT_INFO_INTS * 4, s2) != cudaSuccess) return 1;
+        if (cudaMemsetAsync(info, off ? 0x01 : 0x00, 4, s2) != cudaSuccess) return 1;  // (switch: "inexact" from the start)
+        for (int d = 0; d < dim; ++d)
+            if (cudaMemsetAsync(info + 2 + 2 * d, 0x80, 4, s2) != cudaSuccess) return 1;
+        return 0;
+    };
 
     KSG_CUDA_TRY(cudaMemsetAsync(P.flags, 0, 64, st));
     iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
@@ -521,8 +533,12 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 if (e != cudaSuccess) { set_error("cub SortPairs (curve): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
                 note_launch();
             }
+            if (exact_setup(exact_info, st)) return KSG_ECUDA;
             gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
-                d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
+                d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded,
+                exact_info);
+            KSG_LAUNCHED2();
+            exact_flag_kernel<<<1, 32, 0, st>>>(exact_info, dim, P.flags);
             KSG_LAUNCHED2();
             invert_perm_kernel<<<nb, 256, 0, st>>>(P.perm, n, invperm);
             KSG_LAUNCHED2();
@@ -640,8 +656,12 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 note_launch();
             }
         }
+        if (exact_setup(exact_info, st)) return KSG_ECUDA;
         gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
-            d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded);
+            d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded,
+            exact_info);
+        KSG_LAUNCHED2();
+        exact_flag_kernel<<<1, 32, 0, st>>>(exact_info, dim, P.flags);
         KSG_LAUNCHED2();
         // axis_pos: original sample index -> position in the final order
         int32_t* invperm = (int32_t*)(base + L.off_invperm);
@@ -747,7 +767,7 @@ int ksg_fast_knn_margin(const ksg_prepared* P, int64_t q_begin, int64_t q_end, c
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    d_query_index, P->maxabs, a.seed_thr, a.unit_first,
                                                                    p.qb, P->perm, d_idx_out, nullptr, 0, P->center,
-                                                                   d_eps_out, d_flags, d_n_flagged);
+                                                                   d_eps_out, d_flags, d_n_flagged, a.ra.exact32);
     KSG_LAUNCHED2();
     // from here on the caller's stream is also behind the side-stream work of the prepared set (the
     // exact coordinate sorts ran underneath the kernels above)
@@ -900,7 +920,7 @@ int ksg_fast_knn_cross(const ksg_prepared* P, const ksg_cross* X, int64_t q_begi
                                                                    P->sorted_f64, P->ld, P->dim, P->n, q_begin, nq,
                                                                    nullptr, X->maxabs, a.seed_thr, a.unit_first, p.qb,
                                                                    P->perm, nullptr, X->sorted_f64, X->ld, P->center,
-                                                                   d_eps_out, d_flags, d_n_flagged);
+                                                                   d_eps_out, d_flags, d_n_flagged, nullptr);
     KSG_LAUNCHED2();
     return wait_axes(P, st);
 }
@@ -971,7 +991,8 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
     KSG_LAUNCHED2();
     KSG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)nq * sizeof(int32_t), st));
     count_thresholds_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(d_eps, q_begin, nq, P->shadow_f32,
-                                                                          P->dim_padded, thresholds);
+                                                                          P->dim_padded, strict ? 1 : 0, P->flags + 8,
+                                                                          thresholds);
     KSG_LAUNCHED2();
 
     CountF32Args a;
@@ -1035,7 +1056,7 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
     for (int s = 0; s < n_subspaces; ++s) mt.m[s] = h_masks[s];
     count_fix_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(
         P->sorted_f64, P->ld, P->shadow_f32, dim, P->dim_padded, P->n, P->axis_vals, P->axis_pos, P->maxabs, q_begin,
-        nq, d_eps, thresholds, mt, n_subspaces, strict ? 1 : 0, d_counts, d_flags, d_n_flagged);
+        nq, d_eps, thresholds, mt, n_subspaces, strict ? 1 : 0, d_counts, d_flags, d_n_flagged, P->flags + 8);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

@@ -303,12 +303,20 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
 }
 
 // thresholds[qi] = count_threshold(eps[qi]);  counts initialised to `bias`
+// exact32 (prepared flags[8]): the fp32 distances are the float64 distances themselves, so the filter's
+// "m < T" is made the exact predicate -- strict: d < eps  <=>  d < ceil32(eps); closed: d <= eps  <=>
+// d < nextup(floor32(eps)) -- and count_fix_kernel has nothing to correct.
 static __global__ void count_thresholds_kernel(const double* __restrict__ eps, int64_t q_begin, int64_t nq,
-                                        const float* __restrict__ shadow, int dim_padded,
-                                        float* __restrict__ thresholds) {
+                                        const float* __restrict__ shadow, int dim_padded, int strict,
+                                        const int32_t* __restrict__ exact32, float* __restrict__ thresholds) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
-    thresholds[qi] = count_threshold(eps[qi], query_maxabs(shadow, q_begin + qi, dim_padded));
+    const double e = eps[qi];
+    if (exact32 && *exact32 && e < CUDART_INF && e >= 0.0) {
+        thresholds[qi] = strict ? __double2float_ru(e) : nextafterf(__double2float_rd(e), CUDART_INF_F);
+        return;
+    }
+    thresholds[qi] = count_threshold(e, query_maxabs(shadow, q_begin + qi, dim_padded));
 }
 
 // ---------------------------------------------------------------- exact resolution of the band
@@ -341,12 +349,21 @@ count_fix_kernel(const double* __restrict__ sorted, int64_t ld, const float* __r
                  const int32_t* __restrict__ axis_pos, const double* __restrict__ maxabs, int64_t q_begin,
                  int64_t nq, const double* __restrict__ eps, const float* __restrict__ thresholds,
                  MaskTable64 masks, int n_sub, int strict, int32_t* __restrict__ counts,
-                 int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
+                 int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged, const int32_t* __restrict__ exact32) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     const double e = eps[qi];
     if (!(e < CUDART_INF)) return;  // infinite radius: the filter is exact (everything finite is inside)
     const float T = thresholds[qi];
+    if (exact32 && *exact32 && e >= 0.0 && fp32_range_ok(maxabs, dim)) {
+        // exact fp32 copy: the filter already counted with the exact predicate (count_thresholds_kernel);
+        // only thresholds the scaled compare cannot represent go to the float64 kernel
+        if (T > 0.0f && T < COUNT_MIN_T) {
+            flags[qi] = 1;
+            atomicAdd(n_flagged, 1);
+        }
+        return;
+    }
     // (also: shadow rows beyond the fp32 range look like padding to the filter, see fp32_range_ok)
     if (T < COUNT_MIN_T || !fp32_range_ok(maxabs, dim)) {  // the filter's scaled compare is not exact this far down (see ind_lt)
         flags[qi] = 1;

@@ -1134,6 +1134,11 @@ static __device__ __noinline__ void refine_merge_lists(const float* part_d32, co
         if (ra.idx_out) atomicAdd(ra.n_flagged, 1);
         return;
     }
+    if (ra.exact32 && *ra.exact32 && !ra.idx_out) {  // exact fp32 copy: see refine_single_list
+        ra.flags[qi] = 0;
+        ra.eps_out[qi] = r32;
+        return;
+    }
     const double delta = band_query_f64(mq, 2.0 * r32);
     const double T = r32 + 2.0 * delta;
 
@@ -1204,7 +1209,8 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
                   const float* __restrict__ seed_thr, const int32_t* __restrict__ unit_first, int qb,
                   const int32_t* __restrict__ perm, int64_t* __restrict__ idx_out,
                   const double* __restrict__ qsorted, int64_t qld, const double* __restrict__ center,
-                  double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged) {
+                  double* __restrict__ eps_out, int32_t* __restrict__ flags, int32_t* __restrict__ n_flagged,
+                  const int32_t* __restrict__ exact32) {
     // qsorted (optional, cross-set search): the float64 query coordinates come from this [dim][qld]
     // array (rows q_begin + qi) instead of the candidate set itself.
     // idx_out (optional, [nq][kp] int64): the k' nearest points as positions in the prepared
@@ -1229,7 +1235,7 @@ knn_refine_kernel(const float* __restrict__ part_d32, const int32_t* __restrict_
     RefineArgs ra;
     ra.fused = 0; ra.kp = kp; ra.dim = dim; ra.sorted = sorted; ra.ld = ld; ra.qsorted = qsorted; ra.qld = qld;
     ra.center = center; ra.maxabs = maxabs; ra.perm = perm; ra.idx_out = idx_out; ra.eps_out = eps_out;
-    ra.flags = flags; ra.n_flagged = n_flagged;
+    ra.flags = flags; ra.n_flagged = n_flagged; ra.exact32 = exact32;
     refine_merge_lists(part_d32, part_idx, kcap, s_begin, s_end, stride, off, seed_thr != nullptr,
                        seed_thr ? seed_thr[qi] : 0.0f, q_index ? (int64_t)q_index[qi] : q_begin + qi, qi, ra);
 }
@@ -1259,6 +1265,13 @@ static __device__ __noinline__ void refine_single_list(const float* col_d, const
         ra.eps_out[qi] = CUDART_INF;
         ra.flags[qi] = ra.idx_out ? 1 : 0;
         if (ra.idx_out) atomicAdd(ra.n_flagged, 1);
+        return;
+    }
+    if (ra.exact32 && *ra.exact32 && !ra.idx_out) {
+        // quantised / integer data: every fp32 distance is the float64 distance itself (prepare.cuh,
+        // exact_flag_kernel) -- the k'-th smallest of the list is the exact radius, ties and all
+        ra.flags[qi] = 0;
+        ra.eps_out[qi] = (double)v_kp;
         return;
     }
     double qc[KSG_MAX_DIM];

@@ -20,6 +20,7 @@ struct RefineArgs {
     int64_t qld;
     const double* center;
     const double* maxabs;      // [dim] max |x - centre| of candidates (and cross-set queries)
+    const int32_t* exact32;    // device flag "the fp32 copy is exact" (prepared flags[8]) or null (cross-set search)
     const int32_t* perm;
     int64_t* idx_out;          // optional [nq][kp]
     double* eps_out;           // [nq]

@@ -35,7 +35,7 @@ struct PreparedLayout {
     int dim_padded;
     size_t off_perm, off_sorted, off_shadow, off_axis_vals, off_axis_pos, off_center, off_maxabs, off_flags;
     size_t off_tile_box, off_sub_box;
-    size_t off_iota, off_ranks, off_mkeys, off_mkeys_out, off_invperm, off_cub, off_curve_table, off_stats;
+    size_t off_iota, off_ranks, off_mkeys, off_mkeys_out, off_invperm, off_cub, off_curve_table, off_stats, off_exact;
     size_t cub_bytes;  // per sort lane
     int sort_lanes;
     size_t total;
@@ -96,30 +96,77 @@ static __global__ void iota_kernel(int32_t* __restrict__ p, int64_t n) {
     if (i < n) p[i] = (int32_t)i;
 }
 
+// ---- "the fp32 copy is EXACT" (quantised / integer data).  If every centred coordinate x - centre is
+// a multiple of one power of two q_d and smaller than 2^23 q_d, then the subtraction x - centre, its
+// conversion to fp32 and every difference of two shadow values are exact: the fp32 filter computes
+// the float64 distances themselves, the k'-th smallest fp32 distance IS the exact radius (ties need
+// no identities), the fp32 counts are the exact counts, and nothing needs a recheck or a fallback.
+// exact_info: [0] = any inexact step seen, [1 + 2 d] = min exponent of the lowest set bit of
+// coordinate d's shadow values, [2 + 2 d] = max exponent of their highest bit.
+constexpr int EXACT_INFO_INTS = 2 * KSG_MAX_DIM + 2;
+
+__device__ __forceinline__ void shadow_bit_range(float s, int& low, int& high) {
+    const unsigned int b = __float_as_uint(s) & 0x7fffffffu;
+    const int e = (int)(b >> 23);
+    const unsigned int mant = (b & 0x7fffffu) | (e ? 0x800000u : 0u);
+    const int base = (e ? e : 1) - 150;  // value = mant * 2^base
+    low = base + (__ffs((int)mant) - 1);
+    high = base + (31 - __clz((int)mant));
+}
+
 // sorted_f64[d][i] = pts[d][perm[i]];  shadow[i][d] = fp32(sorted - centre);  +inf padding rows
 static __global__ void __launch_bounds__(256)
 gather_sorted_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, int dim, int dim_padded,
                      const int32_t* __restrict__ perm, const double* __restrict__ center,
-                     double* __restrict__ sorted, int64_t ld, float* __restrict__ shadow, int64_t n_padded) {
+                     double* __restrict__ sorted, int64_t ld, float* __restrict__ shadow, int64_t n_padded,
+                     int32_t* __restrict__ exact_info) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_padded) return;
+    const bool in_range = i < n_padded;
     const bool real = i < n;
     const int64_t src = real ? perm[i] : 0;
+    int inexact = 0;
     for (int d = 0; d < dim_padded; ++d) {
         float s;
+        int low = 0x7fffffff, high = -0x7fffffff;
         if (d < dim) {
             if (real) {
-                const double v = pts[(int64_t)d * ld_in + src];
+                const double v = pts[(int64_t)d * ld_in + src], c = center[d];
                 sorted[(int64_t)d * ld + i] = v;
-                s = __double2float_rn(__dsub_rn(v, center[d]));
+                const double t = __dsub_rn(v, c);
+                s = __double2float_rn(t);
+                // error-free transformation of v - c (TwoSum) and of the conversion
+                const double bb = __dsub_rn(t, v);
+                const double err = __dadd_rn(__dsub_rn(v, __dsub_rn(t, bb)), __dsub_rn(-c, bb));
+                inexact |= !(err == 0.0) || !((double)s == t);
+                if (s != 0.0f && isfinite(s)) shadow_bit_range(s, low, high);
             } else {
                 s = CUDART_INF_F;
             }
         } else {
             s = 0.0f;
         }
-        shadow[i * dim_padded + d] = s;
+        if (in_range) shadow[i * dim_padded + d] = s;
+        if (exact_info && d < dim) {
+            low = __reduce_min_sync(0xffffffffu, low);
+            high = __reduce_max_sync(0xffffffffu, high);
+            if ((threadIdx.x & 31) == 0) {
+                if (low != 0x7fffffff) atomicMin(&exact_info[1 + 2 * d], low);
+                if (high != -0x7fffffff) atomicMax(&exact_info[2 + 2 * d], high);
+            }
+        }
     }
+    if (exact_info && __any_sync(0xffffffffu, inexact) && (threadIdx.x & 31) == 0) atomicOr(&exact_info[0], 1);
+}
+
+// flags[8] = 1 when the fp32 copy is exact (see above)
+static __global__ void exact_flag_kernel(const int32_t* __restrict__ exact_info, int dim, int32_t* __restrict__ flags) {
+    if (threadIdx.x != 0) return;
+    int ok = exact_info[0] == 0;
+    for (int d = 0; d < dim; ++d) {
+        const int low = exact_info[1 + 2 * d], high = exact_info[2 + 2 * d];
+        if (low != 0x7f7f7f7f && high - low > 22) ok = 0;  // (all-zero coordinate: the initial pattern is still there)
+    }
+    flags[8] = ok;
 }
 
 // ---- space-filling-curve order on per-coordinate RANKS (rank-uniform: cells hold ~equal point counts)

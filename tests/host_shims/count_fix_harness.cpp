@@ -119,7 +119,7 @@ int main(int argc, char** argv) {
             blockIdx.x = (unsigned)(q / 128);
             threadIdx.x = (unsigned)(q % 128);
             count_fix_kernel(pts.data(), n, shadow.data(), dim, dp, n, axis_vals.data(), axis_pos.data(), maxabs.data(), 0, n,
-                             eps.data(), thresholds.data(), masks, n_sub, strict, counts.data(), flags.data(), &n_flagged);
+                             eps.data(), thresholds.data(), masks, n_sub, strict, counts.data(), flags.data(), &n_flagged, nullptr);
         }
         for (int64_t q = 0; q < n; ++q) {
             if (flags[q]) { ++flagged; continue; }

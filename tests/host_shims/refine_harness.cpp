@@ -86,6 +86,7 @@ static int single_list_trials(int trials, long* checked_out, long* flagged_cont_
         ra.qsorted = cross ? qry.data() : nullptr; ra.qld = nq; ra.center = center.data(); ra.perm = perm.data();
         std::vector<double> maxabs(dim, 1e6);
         ra.maxabs = maxabs.data();
+        ra.exact32 = nullptr;
         ra.idx_out = want_idx ? nbr.data() : nullptr; ra.eps_out = eps.data(); ra.flags = flags.data();
         ra.n_flagged = &n_flagged;
         int counted = 0;
@@ -214,7 +215,8 @@ int main(int argc, char** argv) {
             threadIdx.x = (unsigned)(qi % 128);
             knn_refine_kernel(d32.data(), idx.data(), kcap, splits, kp, pts.data(), n, dim, n, 0, nq, nullptr, nullptr,
                               nullptr, windowed ? unit_first.data() : nullptr, qb, perm.data(),
-                              want_idx ? nbr.data() : nullptr, nullptr, 0, center.data(), eps.data(), flags.data(), &n_flagged);
+                              want_idx ? nbr.data() : nullptr, nullptr, 0, center.data(), eps.data(), flags.data(), &n_flagged,
+                              nullptr);
         }
         int counted = 0;
         for (int64_t qi = 0; qi < nq; ++qi) {

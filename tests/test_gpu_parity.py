@@ -607,6 +607,45 @@ def test_heavy_tailed_data_stays_on_the_fast_path(E):
             assert E.stats["knn_fallback_queries"] + E.stats["count_fallback_queries"] <= n // 100
 
 
+def test_quantised_data_needs_no_fallback(E):
+    """Dyadic-quantised / integer data (exact distance ties everywhere): the prepared set proves that
+    its fp32 copy is exact, so radii and counts come straight from the fp32 filter -- bit-exact, with
+    no query handed to the float64 kernels (the round-1 cliff: 86 % of the queries of 8-bit data)."""
+    from oracle import ksg_oracle_c as oc
+
+    rng = np.random.default_rng(17)
+    n = 120_000
+    x = rng.standard_normal(n)
+    cases = {"8-bit": 8.0 / (1 << 8), "12-bit": 8.0 / (1 << 12)}
+    for name, q in cases.items():
+        rows = np.vstack([np.round(x / q) * q, np.round((0.6 * x + 0.8 * rng.standard_normal(n)) / q) * q,
+                          np.round(rng.standard_normal(n) / q) * q])
+        for key in E.stats:
+            E.stats[key] = 0
+        subs = [(0,), (1,), (0, 1), (1, 2), (0, 1, 2)]
+        eps, counts = radius_and_counts(E, rows, 5, subs)
+        sel = np.sort(rng.choice(n, size=300, replace=False))
+        ref = oc.knn_radius(rows, 6, queries=rows[:, sel])
+        assert np.array_equal(eps[sel], ref), name
+        for row, sub in enumerate(subs):
+            want = oc.count_within(rows[list(sub), :], ref, queries=rows[list(sub), :][:, sel])
+            assert np.array_equal(counts[row, sel], want), (name, sub)
+        if E.config.engine != "exact":
+            assert E.stats["knn_fallback_queries"] == 0 and E.stats["count_fallback_queries"] == 0, (name, dict(E.stats))
+    # the reference's own integer fixture (tests/test_knn.py:20-24), tiled with integer offsets
+    tie = workloads.tie_fixture().astype(np.float64)
+    big = np.concatenate([tie + 1000 * i for i in range(300)], axis=1)
+    for key in E.stats:
+        E.stats[key] = 0
+    eps, counts = radius_and_counts(E, big, 1, [(0,), (1,), (2,), (0, 1)])
+    ref = orc.knn_radius(big, 1)
+    assert np.array_equal(eps, ref)
+    for row, sub in enumerate([(0,), (1,), (2,), (0, 1)]):
+        assert np.array_equal(counts[row], orc.count_within(big[list(sub), :], ref)), sub
+    if E.config.engine != "exact":
+        assert E.stats["knn_fallback_queries"] == 0 and E.stats["count_fallback_queries"] == 0, dict(E.stats)
+
+
 def test_coordinates_beyond_the_fp32_range(E):
     """Finite float64 input farther than FLT_MAX from the median: the centred fp32 copy
     would overflow to +-inf and look like padding.  The prepared set notices (maxabs) and every query
