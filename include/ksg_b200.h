@@ -235,8 +235,8 @@ typedef struct {
                             engine, which skips most of the n x n pairs) */
     uint64_t* curve_keys; /* [n] ascending space-filling-curve keys of the rows (primary == -1 only; else NULL):
                             lets ksg_cross_prepare place foreign query points on the same curve */
-    double* curve_table;  /* [dim][1026] (primary == -1, early order; else NULL): per coordinate [min, sorted
-                            sample of 1024 values, max] -- the monotone map behind the curve coordinates */
+    float* curve_table;   /* [dim][1026] (primary == -1, early order; else NULL): per coordinate the centred fp32
+                            [min, sorted sample of 1024 values, max] -- the monotone map behind the curve coordinates */
     void* axes_ready;     /* cudaEvent_t or NULL.  Early order (primary == -1): the curve is built from the
                             table above, and the EXACT coordinate sorts behind axis_vals / axis_pos run on
                             side streams of the library underneath whatever the caller enqueues next

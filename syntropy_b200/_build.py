@@ -66,13 +66,27 @@ def _compile_one(args):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the library if it is missing or older than its sources; return its path.
-    One object per translation unit, compiled in parallel, then linked."""
+    One object per translation unit, compiled in parallel, then linked.  Serialised across
+    processes by a file lock (several torchrun ranks may find a stale library at once)."""
     if not force and not is_stale():
         return LIB
-    from concurrent.futures import ThreadPoolExecutor
-
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
+    import fcntl
+
+    with open(os.path.join(LIBDIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # a sibling built it while we waited
+                return LIB
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
+    from concurrent.futures import ThreadPoolExecutor
+
     jobs = []
     objs = []
     newest_header = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
@@ -85,10 +99,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         logs = list(pool.map(_compile_one, jobs))
     if verbose:
         print("\n".join(logs))
-    cmd = [nvcc_path(), *LINK_FLAGS, "-o", LIB, *objs]
+    # link under a temporary name and move it into place: another process (a sibling torchrun rank, a
+    # snapshot of the tree) never sees a half-written library
+    tmp = LIB + ".tmp%d" % os.getpid()
+    cmd = [nvcc_path(), *LINK_FLAGS, "-o", tmp, *objs]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, LIB)
     return LIB
 
 

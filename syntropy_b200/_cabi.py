@@ -157,6 +157,10 @@ def load():
                     "libksg_b200.so is missing and could not be built; the KSG path has no "
                     "CPU fallback (%s)" % exc
                 ) from exc
+            import warnings
+
+            warnings.warn("libksg_b200.so is older than its sources and could not be rebuilt (%s): loading the "
+                          "existing binary; header / ABI changes since then are NOT in it" % exc, RuntimeWarning)
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header and library out of sync

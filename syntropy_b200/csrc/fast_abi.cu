@@ -76,9 +76,9 @@ static inline PreparedLayout prepared_layout(int64_t n, int dim) {
     L.off_mkeys = take((size_t)L.ld * 8);
     L.off_mkeys_out = take((size_t)L.ld * 8);
     L.off_invperm = take((size_t)L.ld * 4);
-    L.off_curve_table = take((size_t)KSG_MAX_DIM * CURVE_TABLE * 8);
+    L.off_curve_table = take((size_t)KSG_MAX_DIM * CURVE_TABLE * 4);
     L.off_stats = take((size_t)KSG_MAX_DIM * STATS_BLOCKS * 2 * 8);
-    L.off_exact = take((size_t)EXACT_INFO_INTS * 4);
+    L.off_exact = take((size_t)(L.n_padded / 256 + 1) * EXACT_INFO_INTS * 4);  // one record per gather block
     L.cub_bytes = align_up(cub_sort_bytes(n), 256);
     L.sort_lanes = dim < SORT_LANES ? dim : SORT_LANES;
     // one CUB scratch area per concurrent coordinate sort (early order: area 0 = the key sort on the
@@ -450,15 +450,9 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     char* cub_base = base + L.off_cub;
     void* cub_tmp = cub_base;
     cudaStream_t st = as_stream2(stream);
-    // byte patterns: exact_info[0] = 0, then (min -> 0x7f7f7f7f, max -> 0x80808080) per coordinate
-    auto exact_setup = [&](int32_t* info, cudaStream_t s2) -> int {
-        static const bool off = [] { const char* e = getenv("KSG_B200_EXACT32"); return e && e[0] == '0'; }();
-        if (cudaMemsetAsync(info, 0x7f, (size_t)EXACT_INFO_INTS * 4, s2) != cudaSuccess) return 1;
-        if (cudaMemsetAsync(info, off ? 0x01 : 0x00, 4, s2) != cudaSuccess) return 1;  // (switch: "inexact" from the start)
-        for (int d = 0; d < dim; ++d)
-            if (cudaMemsetAsync(info + 2 + 2 * d, 0x80, 4, s2) != cudaSuccess) return 1;
-        return 0;
-    };
+    // KSG_B200_EXACT32=0: never declare the fp32 copy exact (A/B of the quantised-data path)
+    static const int exact_off = [] { const char* e = getenv("KSG_B200_EXACT32"); return e && e[0] == '0' ? 1 : 0; }();
+    const int64_t gather_blocks = ceil_div(L.n_padded, 256);
 
     KSG_CUDA_TRY(cudaMemsetAsync(P.flags, 0, 64, st));
     iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
@@ -473,54 +467,31 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     if (primary == -1 && early_order() && lanes) {
         // ================= early order: the curve from approximate ranks on `st`, the exact coordinate
         // sorts (+ their remap into the prepared order) on the side streams, joined by P.axes_ready
-        P.curve_table = (double*)(base + L.off_curve_table);
+        P.curve_table = (float*)(base + L.off_curve_table);
         double* stats = (double*)(base + L.off_stats);
         unsigned long long* mkeys = (unsigned long long*)(base + L.off_mkeys);
         unsigned long long* mkeys_out = (unsigned long long*)(base + L.off_mkeys_out);
         int32_t* invperm = (int32_t*)(base + L.off_invperm);
         const int n_side = SORT_LANES - 1;
-        KSG_CUDA_TRY(cudaEventRecord(lanes->fork, st));  // (iota exists: the sorts' payload)
-        for (int l = 0; l < n_side && l < dim; ++l) KSG_CUDA_TRY(cudaStreamWaitEvent(lanes->helper[l], lanes->fork, 0));
-        for (int d = 0; d < dim; ++d) {
-            cudaStream_t ls = lanes->helper[d % n_side];
-            if (h_row_ready && h_row_ready[d]) KSG_CUDA_TRY(cudaStreamWaitEvent(ls, (cudaEvent_t)h_row_ready[d], 0));
-            void* lane_tmp = cub_base + (size_t)(1 + d % n_side) * L.cub_bytes;  // (area 0: the key sort on `st`)
-            const double* keys_in = d_points + (int64_t)d * ld;
-            double* keys_out = P.axis_vals + (int64_t)d * L.ld;
-            int32_t* pos_out = P.axis_pos + (int64_t)d * L.ld;
-            rc = graph_cache().run(graph_key(GRAPH_AXIS_SORT, {keys_in, keys_out, iota, pos_out, lane_tmp}, {n}, {}), ls,
-                                   [&](cudaStream_t s2) {
-                                       return sort_pairs(lane_tmp, L.cub_bytes, keys_in, keys_out, iota, pos_out, n, s2);
-                                   });
-            if (rc) return rc;
-        }
         if (h_row_ready)
             for (int d = 0; d < dim; ++d)
                 if (h_row_ready[d]) KSG_CUDA_TRY(cudaStreamWaitEvent(st, (cudaEvent_t)h_row_ready[d], 0));
         int rank_bits, bits;
         curve_bits(n, dim, &rank_bits, &bits);
-        if ((size_t)dim * CURVE_TABLE * sizeof(double) > 48 * 1024) {  // (outside any capture)
-            const int bytes = (int)((size_t)dim * CURVE_TABLE * sizeof(double));
-            cudaError_t e = cudaSuccess;
-            switch (dim) {
-                case 6: e = cudaFuncSetAttribute(curve_key_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); break;
-                case 7: e = cudaFuncSetAttribute(curve_key_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); break;
-                case 8: e = cudaFuncSetAttribute(curve_key_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); break;
-                default: e = cudaFuncSetAttribute(curve_key_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            }
-            KSG_CUDA_TRY(e);
-        }
+        if ((size_t)dim * CURVE_TABLE * sizeof(float) > 48 * 1024)  // (dim > 11: the run-time-dimension kernel; outside any capture)
+            KSG_CUDA_TRY(cudaFuncSetAttribute(curve_key_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)((size_t)dim * CURVE_TABLE * sizeof(float))));
         auto early = [&](cudaStream_t st) -> int {
             stats_stage1_kernel<<<dim3(STATS_BLOCKS, dim), 256, 0, st>>>(d_points, ld, n, stats, P.flags);
             KSG_LAUNCHED2();
             curve_table_kernel<<<dim, 512, 0, st>>>(d_points, ld, n, stats, P.curve_table, P.center, P.maxabs);
             KSG_LAUNCHED2();
-            const size_t tsmem = (size_t)dim * CURVE_TABLE * sizeof(double);
+            const size_t tsmem = (size_t)dim * CURVE_TABLE * sizeof(float);
             switch (dim) {
-#define KSG_CKEY(D) case D: curve_key_kernel<D><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, bits, mkeys, nullptr); break;
+#define KSG_CKEY(D) case D: curve_key_kernel<D><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, nullptr); break;
                 KSG_CKEY(1) KSG_CKEY(2) KSG_CKEY(3) KSG_CKEY(4) KSG_CKEY(5) KSG_CKEY(6) KSG_CKEY(7) KSG_CKEY(8)
 #undef KSG_CKEY
-                default: curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, bits, mkeys, nullptr);
+                default: curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, nullptr);
             }
             KSG_LAUNCHED2();
             if (use_sample_sort(n)) {
@@ -533,12 +504,11 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 if (e != cudaSuccess) { set_error("cub SortPairs (curve): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
                 note_launch();
             }
-            if (exact_setup(exact_info, st)) return KSG_ECUDA;
-            gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
+            gather_sorted_kernel<<<(unsigned)gather_blocks, 256, 0, st>>>(
                 d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded,
                 exact_info);
             KSG_LAUNCHED2();
-            exact_flag_kernel<<<1, 32, 0, st>>>(exact_info, dim, P.flags);
+            exact_flag_kernel<<<1, 256, 0, st>>>(exact_info, gather_blocks, dim, exact_off, P.flags);
             KSG_LAUNCHED2();
             invert_perm_kernel<<<nb, 256, 0, st>>>(P.perm, n, invperm);
             KSG_LAUNCHED2();
@@ -550,13 +520,28 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
         rc = graph_cache().run(graph_key(GRAPH_PREPARE_EARLY, {d_points, d_buffer}, {n, ld}, {dim, primary}), st, early);
         if (rc) return rc;
         KSG_CUDA_TRY(cudaEventRecord(lanes->perm_ready, st));
-        // side lane 0 collects the other lanes and the permutation, then remaps axis_pos
+        // The exact coordinate sorts start HERE, behind the curve path: three radix sorts side by side
+        // slow each other down (every pass is latency bound and they share the SMs: measured, the curve
+        // path took 2.5x as long with the coordinate sorts running beside it), whereas the k-NN kernels
+        // the caller enqueues next leave issue slots free.  Side lane 0 then remaps axis_pos.
+        for (int l = 0; l < n_side && l < dim; ++l) KSG_CUDA_TRY(cudaStreamWaitEvent(lanes->helper[l], lanes->perm_ready, 0));
+        for (int d = 0; d < dim; ++d) {
+            cudaStream_t ls = lanes->helper[d % n_side];
+            void* lane_tmp = cub_base + (size_t)(1 + d % n_side) * L.cub_bytes;  // (area 0: the key sort on `st`)
+            const double* keys_in = d_points + (int64_t)d * ld;
+            double* keys_out = P.axis_vals + (int64_t)d * L.ld;
+            int32_t* pos_out = P.axis_pos + (int64_t)d * L.ld;
+            rc = graph_cache().run(graph_key(GRAPH_AXIS_SORT, {keys_in, keys_out, iota, pos_out, lane_tmp}, {n}, {}), ls,
+                                   [&](cudaStream_t s2) {
+                                       return sort_pairs(lane_tmp, L.cub_bytes, keys_in, keys_out, iota, pos_out, n, s2);
+                                   });
+            if (rc) return rc;
+        }
         cudaStream_t s0 = lanes->helper[0];
         for (int l = 1; l < n_side && l < dim; ++l) {
             KSG_CUDA_TRY(cudaEventRecord(lanes->join[l], lanes->helper[l]));
             KSG_CUDA_TRY(cudaStreamWaitEvent(s0, lanes->join[l], 0));
         }
-        KSG_CUDA_TRY(cudaStreamWaitEvent(s0, lanes->perm_ready, 0));
         remap_axis_kernel<<<dim3(nb, dim), 256, 0, s0>>>(P.axis_pos, L.ld, n, invperm);
         KSG_LAUNCHED2();
         cudaEvent_t done = lanes->axes_ready[lanes->next_axes++ % AXES_EVENTS];
@@ -656,12 +641,11 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 note_launch();
             }
         }
-        if (exact_setup(exact_info, st)) return KSG_ECUDA;
-        gather_sorted_kernel<<<(unsigned)ceil_div(L.n_padded, 256), 256, 0, st>>>(
+        gather_sorted_kernel<<<(unsigned)gather_blocks, 256, 0, st>>>(
             d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded,
             exact_info);
         KSG_LAUNCHED2();
-        exact_flag_kernel<<<1, 32, 0, st>>>(exact_info, dim, P.flags);
+        exact_flag_kernel<<<1, 256, 0, st>>>(exact_info, gather_blocks, dim, exact_off, P.flags);
         KSG_LAUNCHED2();
         // axis_pos: original sample index -> position in the final order
         int32_t* invperm = (int32_t*)(base + L.off_invperm);
@@ -838,9 +822,9 @@ int ksg_cross_prepare(const ksg_prepared* P, const double* d_queries, int64_t ld
     curve_bits(P->n, dim, &rank_bits, &bits);
     if (P->curve_table) {
         // the candidates' curve was built from their coordinate table: place the queries with the same map
-        const size_t tsmem = (size_t)dim * CURVE_TABLE * sizeof(double);
+        const size_t tsmem = (size_t)dim * CURVE_TABLE * sizeof(float);
         if (tsmem > 48 * 1024) KSG_CUDA_TRY(cudaFuncSetAttribute(curve_key_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-        curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_queries, ldq, nq, dim, P->curve_table, bits, keys, iota);
+        curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_queries, ldq, nq, dim, P->curve_table, P->center, bits, keys, iota);
     } else
     switch (dim) {
 #define KSG_CROSS(D) case D: cross_key_kernel<D><<<nb, 256, 0, st>>>(d_queries, ldq, nq, P->axis_vals, P->ld, P->n, dim, rank_bits, bits, keys, iota); break;

@@ -1,5 +1,7 @@
 // k-NN filter instantiations (DP = 2, 4, 6, 8) and their launcher.
 #include "fast_count_launch.cuh"
+#include <stdlib.h>
+
 #include "fast_knn.cuh"
 
 namespace ksg {
@@ -39,6 +41,17 @@ static int launch_knn_dp(const KnnF32Args& a) {
     return KSG_OK;
 }
 
+// Rows on each side of a query that seed its threshold in the planning pass (see knn_plan_kernel).
+// KSG_B200_SEED_W overrides (experiments).
+static int plan_seed_width(int dp) {
+    static const int forced = [] {
+        const char* e = getenv("KSG_B200_SEED_W");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced > 0) return forced;
+    return dp <= 4 ? KNN_SEED_W : 4 * KNN_SEED_W;
+}
+
 template <int DP, int KC>
 static int launch_plan_kc(const KnnF32Args& a) {
     constexpr int Q = UnitsQ<DP>::Q;
@@ -50,7 +63,7 @@ static int launch_plan_kc(const KnnF32Args& a) {
     }
     if (cudaMemsetAsync(a.unit_meta, 0, 32, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
     kern<<<(unsigned)ceil_div(a.nq, FAST_THREADS * Q), FAST_THREADS, smem, a.st>>>(
-        a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.kseed, a.maxabs, a.dim, a.qshadow, a.qhome, a.seed_thr, (int2*)a.plan,
+        a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.kseed, plan_seed_width(DP), a.maxabs, a.dim, a.qshadow, a.qhome, a.seed_thr, (int2*)a.plan,
         a.plan_capacity, a.plan_count, a.plan_first, a.unit_meta, a.unit_done);
     note_launch();
     cudaError_t e = cudaGetLastError();

@@ -141,7 +141,7 @@ constexpr int PLAN_MASK_WORDS = 1024;  // survivor bitmask of the planning pass:
 template <int DP, int Q, int KC>  // KC > 0: seed lists of KC entries in registers (kcap <= KC); 0: in shared memory
 static __global__ void __launch_bounds__(FAST_THREADS)
 knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box, int64_t n_tiles,
-                int64_t q_begin, int64_t nq, int kcap, int kseed, const double* __restrict__ maxabs, int dim,
+                int64_t q_begin, int64_t nq, int kcap, int kseed, int seed_w, const double* __restrict__ maxabs, int dim,
                 const float* __restrict__ qshadow, const int32_t* __restrict__ qhome,
                 float* __restrict__ seed_thr, int2* __restrict__ plan, int64_t plan_capacity,
                 int32_t* __restrict__ plan_count, int32_t* __restrict__ plan_first, int32_t* __restrict__ meta,
@@ -179,7 +179,11 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
     // 2 W candidate rows of every query come from there instead of 2 W dependent L1 / L2 round trips.
     constexpr int WIN_ROWS = FAST_THREADS + 2 * KNN_SEED_W;
     __shared__ __align__(16) float s_win[KC > 0 ? WIN_ROWS * DP : 1];
-    const bool staged = KC > 0 && !qhome && !qshadow;
+    // seed_w: rows on each side of a query that seed its threshold.  Any width gives a valid upper
+    // bound; from ~5 coordinates up consecutive rows of the curve are a poor sample of a query's
+    // neighbourhood (seed / true radius 1.5 at +-24 rows in 6-D and 8-D, 1.2 at +-384:
+    // profiles/r1aj_seed_window_simulation.txt), so those sets use a wider window (global loads).
+    const bool staged = KC > 0 && !qhome && !qshadow && seed_w == KNN_SEED_W;
 #pragma unroll 1
     for (int j = 0; j < Q; ++j) {
         const int64_t qi = qb0 + j * FAST_THREADS + tid;
@@ -226,7 +230,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
                     }
             } else {
 #pragma unroll 2
-            for (int off = 1; off <= KNN_SEED_W; ++off)
+            for (int off = 1; off <= seed_w; ++off)
 #pragma unroll
                 for (int sgn = -1; sgn <= 1; sgn += 2) {
                     const int64_t r2 = sgn > 0 ? row + off - 1 + self_skip : row - off;
@@ -246,7 +250,7 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
             const int col = j * FAST_THREADS + tid;
             for (int r = 0; r < kseed; ++r) lst_d[(size_t)r * QB + col] = CUDART_INF_F;
 #pragma unroll 1
-            for (int off = 1; off <= KNN_SEED_W; ++off)
+            for (int off = 1; off <= seed_w; ++off)
 #pragma unroll 1
                 for (int sgn = -1; sgn <= 1; sgn += 2) {
                     const int64_t r2 = sgn > 0 ? row + off - 1 + self_skip : row - off;

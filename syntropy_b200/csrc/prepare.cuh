@@ -101,9 +101,11 @@ static __global__ void iota_kernel(int32_t* __restrict__ p, int64_t n) {
 // conversion to fp32 and every difference of two shadow values are exact: the fp32 filter computes
 // the float64 distances themselves, the k'-th smallest fp32 distance IS the exact radius (ties need
 // no identities), the fp32 counts are the exact counts, and nothing needs a recheck or a fallback.
-// exact_info: [0] = any inexact step seen, [1 + 2 d] = min exponent of the lowest set bit of
-// coordinate d's shadow values, [2 + 2 d] = max exponent of their highest bit.
-constexpr int EXACT_INFO_INTS = 2 * KSG_MAX_DIM + 2;
+// exact_info (per block of 256 rows, no atomics): [b][0] = an inexact step was seen, [b][1 + 2 d] =
+// min exponent of the lowest set bit of coordinate d's shadow values, [b][2 + 2 d] = max exponent of
+// their highest bit; exact_flag_kernel folds the blocks.
+constexpr int EXACT_INFO_INTS = 2 * 8 + 2;  // the fp32 filters serve up to 8 coordinates
+constexpr int EXACT_NONE_LOW = 0x7fffffff, EXACT_NONE_HIGH = -0x7fffffff;
 
 __device__ __forceinline__ void shadow_bit_range(float s, int& low, int& high) {
     const unsigned int b = __float_as_uint(s) & 0x7fffffffu;
@@ -120,25 +122,30 @@ gather_sorted_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, i
                      const int32_t* __restrict__ perm, const double* __restrict__ center,
                      double* __restrict__ sorted, int64_t ld, float* __restrict__ shadow, int64_t n_padded,
                      int32_t* __restrict__ exact_info) {
+    __shared__ int s_low[8][8], s_high[8][8], s_bad[8];
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool in_range = i < n_padded;
     const bool real = i < n;
     const int64_t src = real ? perm[i] : 0;
+    const bool analyse = exact_info != nullptr && dim <= 8;
     int inexact = 0;
     for (int d = 0; d < dim_padded; ++d) {
         float s;
-        int low = 0x7fffffff, high = -0x7fffffff;
+        int low = EXACT_NONE_LOW, high = EXACT_NONE_HIGH;
         if (d < dim) {
             if (real) {
                 const double v = pts[(int64_t)d * ld_in + src], c = center[d];
                 sorted[(int64_t)d * ld + i] = v;
                 const double t = __dsub_rn(v, c);
                 s = __double2float_rn(t);
-                // error-free transformation of v - c (TwoSum) and of the conversion
-                const double bb = __dsub_rn(t, v);
-                const double err = __dadd_rn(__dsub_rn(v, __dsub_rn(t, bb)), __dsub_rn(-c, bb));
-                inexact |= !(err == 0.0) || !((double)s == t);
-                if (s != 0.0f && isfinite(s)) shadow_bit_range(s, low, high);
+                if (analyse) {
+                    // error-free transformation of v - c (TwoSum) and of the conversion
+                    const double bb = __dsub_rn(t, v);
+                    const double err = __dadd_rn(__dsub_rn(v, __dsub_rn(t, bb)), __dsub_rn(-c, bb));
+                    inexact |= !(err == 0.0) || !((double)s == t);
+                    if (s != 0.0f && isfinite(s)) shadow_bit_range(s, low, high);
+                }
             } else {
                 s = CUDART_INF_F;
             }
@@ -146,27 +153,64 @@ gather_sorted_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, i
             s = 0.0f;
         }
         if (in_range) shadow[i * dim_padded + d] = s;
-        if (exact_info && d < dim) {
+        if (analyse && d < dim) {
             low = __reduce_min_sync(0xffffffffu, low);
             high = __reduce_max_sync(0xffffffffu, high);
-            if ((threadIdx.x & 31) == 0) {
-                if (low != 0x7fffffff) atomicMin(&exact_info[1 + 2 * d], low);
-                if (high != -0x7fffffff) atomicMax(&exact_info[2 + 2 * d], high);
-            }
+            if (lane == 0) { s_low[warp][d] = low; s_high[warp][d] = high; }
         }
     }
-    if (exact_info && __any_sync(0xffffffffu, inexact) && (threadIdx.x & 31) == 0) atomicOr(&exact_info[0], 1);
+    if (!analyse) return;
+    inexact = __any_sync(0xffffffffu, inexact);
+    if (lane == 0) s_bad[warp] = inexact;
+    __syncthreads();
+    int32_t* out = exact_info + (int64_t)blockIdx.x * EXACT_INFO_INTS;
+    if (threadIdx.x < dim) {
+        const int d = threadIdx.x;
+        int low = EXACT_NONE_LOW, high = EXACT_NONE_HIGH;
+        for (int w = 0; w < 8; ++w) { low = min(low, s_low[w][d]); high = max(high, s_high[w][d]); }
+        out[1 + 2 * d] = low;
+        out[2 + 2 * d] = high;
+    }
+    if (threadIdx.x == 0) {
+        int bad = 0;
+        for (int w = 0; w < 8; ++w) bad |= s_bad[w];
+        out[0] = bad;
+    }
 }
 
-// flags[8] = 1 when the fp32 copy is exact (see above)
-static __global__ void exact_flag_kernel(const int32_t* __restrict__ exact_info, int dim, int32_t* __restrict__ flags) {
-    if (threadIdx.x != 0) return;
-    int ok = exact_info[0] == 0;
+// flags[8] = 1 when the fp32 copy is exact (see above); one CTA of 256 threads folds the block records
+static __global__ void __launch_bounds__(256)
+exact_flag_kernel(const int32_t* __restrict__ exact_info, int64_t n_blocks, int dim, int force_off,
+                  int32_t* __restrict__ flags) {
+    __shared__ int s_low[256], s_high[256], s_ok;
+    if (threadIdx.x == 0) s_ok = (dim <= 8 && !force_off) ? 1 : 0;
+    __syncthreads();
+    if (dim > 8 || force_off) { if (threadIdx.x == 0) flags[8] = 0; return; }
+    int bad = 0;
+    for (int64_t b = threadIdx.x; b < n_blocks; b += 256) bad |= exact_info[b * EXACT_INFO_INTS];
+    if (bad) s_ok = 0;
     for (int d = 0; d < dim; ++d) {
-        const int low = exact_info[1 + 2 * d], high = exact_info[2 + 2 * d];
-        if (low != 0x7f7f7f7f && high - low > 22) ok = 0;  // (all-zero coordinate: the initial pattern is still there)
+        int low = EXACT_NONE_LOW, high = EXACT_NONE_HIGH;
+        for (int64_t b = threadIdx.x; b < n_blocks; b += 256) {
+            low = min(low, exact_info[b * EXACT_INFO_INTS + 1 + 2 * d]);
+            high = max(high, exact_info[b * EXACT_INFO_INTS + 2 + 2 * d]);
+        }
+        s_low[threadIdx.x] = low;
+        s_high[threadIdx.x] = high;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            if (threadIdx.x < off) {
+                s_low[threadIdx.x] = min(s_low[threadIdx.x], s_low[threadIdx.x + off]);
+                s_high[threadIdx.x] = max(s_high[threadIdx.x], s_high[threadIdx.x + off]);
+            }
+            __syncthreads();
+        }
+        // (a coordinate that is all zeros has no bits at all: fine)
+        if (threadIdx.x == 0 && s_low[0] != EXACT_NONE_LOW && s_high[0] - s_low[0] > 22) s_ok = 0;
+        __syncthreads();
     }
-    flags[8] = ok;
+    __syncthreads();
+    if (threadIdx.x == 0) flags[8] = s_ok;
 }
 
 // ---- space-filling-curve order on per-coordinate RANKS (rank-uniform: cells hold ~equal point counts)
@@ -239,12 +283,15 @@ constexpr int CURVE_SAMPLES = 1024;
 constexpr int CURVE_TABLE = CURVE_SAMPLES + 2;  // [min, sorted sample, max]
 
 // grid = dim CTAs of 512 threads.  partial: the (min, max) pairs of stats_stage1_kernel.
+// table[d] = fp32 [min - c, sorted sample - c, max - c] with c = center[d] = the sample median (centred
+// like the shadow copy, so data at a large offset keep their resolution; fp32 rounding is monotone).
 static __global__ void __launch_bounds__(512)
 curve_table_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, const double* __restrict__ partial,
-                   double* __restrict__ table, double* __restrict__ center, double* __restrict__ maxabs) {
+                   float* __restrict__ table, double* __restrict__ center, double* __restrict__ maxabs) {
     __shared__ uint64_t sk[CURVE_SAMPLES];
     __shared__ uint32_t si[CURVE_SAMPLES];
     __shared__ double s_lo[512], s_hi[512];
+    __shared__ double s_center;
     const int d = blockIdx.x, tid = threadIdx.x;
     const double* row = pts + (int64_t)d * ld;
     for (int s = tid; s < CURVE_SAMPLES; s += 512) {
@@ -270,8 +317,7 @@ curve_table_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, const 
         }
         __syncthreads();
     }
-    double* out = table + (int64_t)d * CURVE_TABLE;
-    for (int s = tid; s < CURVE_SAMPLES; s += 512) ss_store_key(&out[1 + s], sk[s]);
+    float* out = table + (int64_t)d * CURVE_TABLE;
     if (tid == 0) {
         double c;
         ss_store_key(&c, sk[CURVE_SAMPLES / 2]);  // sample median: the centre of the fp32 copy
@@ -279,42 +325,51 @@ curve_table_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, const 
         if (!isfinite(c)) c = 0.0;  // non-finite input is flagged (stats_stage1_kernel); keep the math finite
         if (!isfinite(mn)) mn = c;
         if (!isfinite(mx)) mx = c;
-        out[0] = mn;
-        out[CURVE_TABLE - 1] = mx;
+        out[0] = __double2float_rn(mn - c);
+        out[CURVE_TABLE - 1] = __double2float_rn(mx - c);
         center[d] = c;
         maxabs[d] = fmax(fabs(mx - c), fabs(c - mn)) * (1.0 + 1e-12) + 1e-300;
+        s_center = c;
+    }
+    __syncthreads();
+    const double c = s_center;
+    for (int s = tid; s < CURVE_SAMPLES; s += 512) {
+        double v;
+        ss_store_key(&v, sk[s]);
+        out[1 + s] = __double2float_rn(v - c);
     }
 }
 
-// curve coordinate of x in [0, 2^bits): monotone in x (tb: CURVE_TABLE ascending values)
-__device__ __forceinline__ unsigned int curve_coord(double x, const double* __restrict__ tb, int bits) {
+// curve coordinate of the centred value x in [0, 2^bits): monotone in x (tb: CURVE_TABLE ascending values)
+__device__ __forceinline__ unsigned int curve_coord(float x, const float* __restrict__ tb, int bits) {
     int lo = 0, hi = CURVE_TABLE;  // number of table entries <= x
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (tb[mid] <= x) lo = mid + 1; else hi = mid;
     }
-    double pos = 0.0;  // in [0, CURVE_TABLE - 1]
+    float pos = 0.0f;  // in [0, CURVE_TABLE - 1]
     if (lo >= CURVE_TABLE) {
-        pos = (double)(CURVE_TABLE - 1);
+        pos = (float)(CURVE_TABLE - 1);
     } else if (lo > 0) {
-        const double a = tb[lo - 1], b = tb[lo];
-        double f = b > a ? (x - a) / (b - a) : 0.0;
-        if (!(f >= 0.0)) f = 0.0;
-        if (f > 1.0) f = 1.0;
-        pos = (double)(lo - 1) + f;
+        const float a = tb[lo - 1], b = tb[lo];
+        float f = b > a ? __fdividef(x - a, b - a) : 0.0f;
+        if (!(f >= 0.0f)) f = 0.0f;
+        if (f > 1.0f) f = 1.0f;
+        pos = (float)(lo - 1) + f;
     }
-    const double scaled = pos * ((double)(1u << bits) / (double)(CURVE_TABLE - 1));
+    const float scaled = pos * ((float)(1u << bits) / (float)(CURVE_TABLE - 1));
     unsigned int c = (unsigned int)scaled;
     const unsigned int top = (1u << bits) - 1u;
     return c > top ? top : c;
 }
 
-// keys[i] = Hilbert index of point i's curve coordinates.  Dynamic shared memory: dim * CURVE_TABLE doubles.
+// keys[i] = Hilbert index of point i's curve coordinates.  Dynamic shared memory: dim * CURVE_TABLE floats.
 template <int DIM>
 static __global__ void __launch_bounds__(256)
-curve_key_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, int dim_rt, const double* __restrict__ table,
-                 int bits, unsigned long long* __restrict__ keys, int32_t* __restrict__ iota) {
-    extern __shared__ double s_table[];
+curve_key_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, int dim_rt, const float* __restrict__ table,
+                 const double* __restrict__ center, int bits, unsigned long long* __restrict__ keys,
+                 int32_t* __restrict__ iota) {
+    extern __shared__ float s_table[];
     const int dim = DIM > 0 ? DIM : dim_rt;
     for (int i = threadIdx.x; i < dim * CURVE_TABLE; i += 256) s_table[i] = table[i];
     __syncthreads();
@@ -323,7 +378,8 @@ curve_key_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, int dim_
     unsigned int X[DIM > 0 ? DIM : KSG_MAX_DIM];
 #pragma unroll
     for (int d = 0; d < (DIM > 0 ? DIM : KSG_MAX_DIM); ++d)
-        if (d < dim) X[d] = curve_coord(pts[(int64_t)d * ld + i], s_table + d * CURVE_TABLE, bits);
+        if (d < dim)
+            X[d] = curve_coord(__double2float_rn(pts[(int64_t)d * ld + i] - center[d]), s_table + d * CURVE_TABLE, bits);
     keys[i] = hilbert_index(X, dim, bits);
     if (iota) iota[i] = (int32_t)i;
 }
