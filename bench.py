@@ -562,6 +562,20 @@ def run_b200_arm(args):
         E.config.engine = args.engine
         dense_leg = (d_ms, d_steps, statistics.mean(d_kernel_ms["fast_knn"]), d_tiles)
 
+    # host time to ENQUEUE one resident step (no synchronisation inside): what the binding costs
+    def enqueue_only():
+        status = E.Status(dev)
+        pw = E.ksg1_device(pts, k, masks, mi1_program, status=status)
+        return E.finish_device(pw, n, out=status.total)
+
+    host_us = []
+    for _ in range(10):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        enqueue_only()
+        host_us.append(1e6 * (time.perf_counter() - t0))
+        torch.cuda.synchronize()
+    host_enqueue_us = statistics.median(host_us)
     stats_c2 = dict(E.stats)
     configs_block = run_config_block(args, world, rank, dev, barrier) if args.engine == "windowed" else None
 
@@ -638,6 +652,9 @@ def run_b200_arm(args):
                              "traffic": traffic.get("psi_epilogue_c2")},
             "fallback_queries": stats_c2,
             "mi_nats": float(avg_host),
+            "host_enqueue_us_per_step": host_enqueue_us,
+            "binding": os.environ.get("KSG_B200_BINDING", "torch") + " (torch C++ extension over the C ABI)"
+                       if os.environ.get("KSG_B200_BINDING", "torch") != "ctypes" else "ctypes over the C ABI",
         }
         if configs_block is not None:
             line["configs"] = configs_block

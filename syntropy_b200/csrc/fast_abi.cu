@@ -1056,9 +1056,19 @@ int ksg_axis_count(const ksg_prepared* P, int axis, int64_t q_begin, int64_t q_e
         const int rc0 = wait_axes(P, as_stream2(stream));
         if (rc0) return rc0;
     }
-    axis_count_kernel<<<(unsigned)ceil_div(nq, AXIS_THREADS), AXIS_THREADS, 0, as_stream2(stream)>>>(
-        P->sorted_f64 + (int64_t)axis * P->ld, P->axis_vals + (int64_t)axis * P->ld, P->n, q_begin, nq, d_eps,
-        strict ? 1 : 0, bias, d_counts);
+    // KSG_B200_AXIS_ORDER=prepared selects the thread-per-query kernel (A/B measurements)
+    static const bool by_value = [] {
+        const char* e = getenv("KSG_B200_AXIS_ORDER");
+        return !(e && e[0] == 'p');
+    }();
+    if (by_value)
+        axis_count_sorted_kernel<<<(unsigned)ceil_div(P->n, 256), 256, 0, as_stream2(stream)>>>(
+            P->axis_vals + (int64_t)axis * P->ld, P->axis_pos + (int64_t)axis * P->ld, P->n, q_begin, nq, d_eps,
+            strict ? 1 : 0, bias, d_counts);
+    else
+        axis_count_kernel<<<(unsigned)ceil_div(nq, AXIS_THREADS), AXIS_THREADS, 0, as_stream2(stream)>>>(
+            P->sorted_f64 + (int64_t)axis * P->ld, P->axis_vals + (int64_t)axis * P->ld, P->n, q_begin, nq, d_eps,
+            strict ? 1 : 0, bias, d_counts);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

@@ -476,6 +476,50 @@ axis_count_kernel(const double* __restrict__ sorted_row, const double* __restric
     counts[qi] = (int32_t)(right - left) + bias;
 }
 
+// The same counts with the threads in the order of the COORDINATE: thread i owns the i-th smallest
+// value x = vals[i] (pos[i] = its row in the prepared order, where its radius lives and its count
+// goes).  Both ends of its run lie near i, so they are found by galloping outwards from i (1, 2, 4, ...
+// steps, then a bisection of the last step): ~2 log2(count) loads instead of 2 log2(n), and the runs of
+// neighbouring threads nearly coincide, so a warp touches one or two cache lines per step instead of 32.
+// Rows outside the query slice [q_begin, q_begin + nq) are skipped (several ranks).
+static __global__ void __launch_bounds__(256)
+axis_count_sorted_kernel(const double* __restrict__ vals, const int32_t* __restrict__ pos, int64_t n,
+                         int64_t q_begin, int64_t nq, const double* __restrict__ eps, int strict, int32_t bias,
+                         int32_t* __restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t qi = (int64_t)pos[i] - q_begin;
+    if (qi < 0 || qi >= nq) return;
+    const double x = vals[i];
+    const double e = eps[qi];
+    // first index at which a monotone predicate (false ... false true ... true) holds; pred(n) = true
+    auto first_true_from = [&](auto pred) -> int64_t {
+        if (pred(x)) {
+            // true at i: gallop to the left for the last false
+            int64_t hi = i, lo = i - 1, step = 1;
+            while (lo >= 0 && pred(vals[lo])) { hi = lo; lo -= step; step <<= 1; }
+            if (lo < -1) lo = -1;
+            while (hi - lo > 1) {
+                const int64_t mid = lo + ((hi - lo) >> 1);
+                if (pred(vals[mid])) hi = mid; else lo = mid;
+            }
+            return hi;
+        }
+        // false at i: gallop to the right for the first true
+        int64_t lo = i, hi = i + 1, step = 1;
+        while (hi < n && !pred(vals[hi])) { lo = hi; hi += step; step <<= 1; }
+        if (hi > n) hi = n;
+        while (hi - lo > 1) {
+            const int64_t mid = lo + ((hi - lo) >> 1);
+            if (pred(vals[mid])) hi = mid; else lo = mid;
+        }
+        return hi;
+    };
+    const int64_t left = first_true_from([&](double v) { return (v > x) || (strict ? (x - v < e) : (x - v <= e)); });
+    const int64_t right = first_true_from([&](double v) { return (v > x) && !(strict ? (v - x < e) : (v - x <= e)); });
+    counts[qi] = (int32_t)(right - left) + bias;
+}
+
 static __global__ void scatter_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ perm, int64_t n,
                                    double* __restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

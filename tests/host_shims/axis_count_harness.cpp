@@ -14,6 +14,7 @@
 #include <vector>
 #define __global__
 #define __device__
+#define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(x)
 #define __shared__ static
@@ -49,7 +50,15 @@ int main(int argc, char** argv) {
             e = pick == 0 ? 0.0 : pick == 1 ? std::numeric_limits<double>::infinity() : pick == 2 ? 0.25
                 : pick == 3 ? 1e-300 : std::fabs(nd(rng)) * (pick < 7 ? 0.01 : 1.0);
         }
-        std::vector<int32_t> counts(nq, -12345);
+        // position of every sorted value in the prepared order (ties: any consistent assignment)
+        std::vector<int32_t> pos(n);
+        {
+            std::vector<int32_t> order(n);
+            for (int64_t i = 0; i < n; ++i) order[i] = (int32_t)i;
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return row[a] < row[b]; });
+            for (int64_t i = 0; i < n; ++i) pos[i] = order[i];
+        }
+        std::vector<int32_t> counts(nq, -12345), counts_by_value(nq, -12345);
         const unsigned blocks = (unsigned)((nq + 1023) / 1024);
         for (unsigned b = 0; b < blocks; ++b)
             for (int pass = 0; pass < 2; ++pass)
@@ -58,6 +67,20 @@ int main(int argc, char** argv) {
                     threadIdx.x = t;
                     axis_count_kernel(row.data(), vals.data(), n, q_begin, nq, eps.data(), strict, bias, counts.data());
                 }
+#ifdef HAVE_SORTED_KERNEL
+        const unsigned blocks_n = (unsigned)((n + 1023) / 1024);
+        for (unsigned b = 0; b < blocks_n; ++b)
+            for (int pass = 0; pass < 2; ++pass)
+                for (unsigned t = 0; t < 1024; ++t) {
+                    blockIdx.x = b;
+                    threadIdx.x = t;
+                    axis_count_sorted_kernel(vals.data(), pos.data(), n, q_begin, nq, eps.data(), strict, bias,
+                                             counts_by_value.data());
+                }
+        for (int64_t qi = 0; qi < nq; ++qi)
+            if (counts_by_value[qi] != counts[qi] && ++wrong < 10)
+                printf("WRONG (by value) trial %d qi %ld: %d vs %d\n", trial, (long)qi, counts_by_value[qi], counts[qi]);
+#endif
         for (int64_t qi = 0; qi < nq; ++qi) {
             const double x = row[q_begin + qi], e = eps[qi];
             int32_t want = bias;

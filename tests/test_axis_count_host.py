@@ -25,7 +25,8 @@ def test_axis_count_kernel_against_brute_force_on_the_host(tmp_path):
     (tmp_path / "axis_count_kernel.inc").write_text(cut_axis_count_kernel())
     shutil.copy(os.path.join(ROOT, "tests", "host_shims", "axis_count_harness.cpp"), tmp_path / "axis_count_harness.cpp")
     exe = tmp_path / "axis_count_harness"
-    proc = subprocess.run([gxx, "-O1", "-std=c++17", "-o", str(exe), "axis_count_harness.cpp"], cwd=tmp_path,
+    flags = ["-DHAVE_SORTED_KERNEL"] if "axis_count_sorted_kernel" in cut_axis_count_kernel() else []
+    proc = subprocess.run([gxx, "-O1", "-std=c++17", *flags, "-o", str(exe), "axis_count_harness.cpp"], cwd=tmp_path,
                           capture_output=True, text=True)
     assert proc.returncode == 0, proc.stderr[-3000:]
     run = subprocess.run([str(exe), "300"], capture_output=True, text=True, timeout=900)
