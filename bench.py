@@ -531,12 +531,16 @@ def run_b200_arm(args):
     pairs_done = last["pw"].pairs_evaluated() if last.get("pw") is not None else (0, 0)
 
     # end to end through the public API, host buffers in / host arrays out
+    e2e_each = []
+
     def e2e_wall(steps):
         barrier()
         t0 = time.perf_counter()
         res = None
         for _ in range(steps):
-            res = e2e_step()
+            t1 = time.perf_counter()
+            res = e2e_step()   # (returns host arrays: the call has synchronised)
+            e2e_each.append(1e3 * (time.perf_counter() - t1))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -628,7 +632,8 @@ def run_b200_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rows.nbytes),
                     "d2h_bytes_per_step": int(8 * n + 16), "ms_per_step": 1e3 * e2e_s / args.steps,
                     "what": "knn.mutual_information(idxs_x, idxs_y, k, data) on a page-locked host array; "
-                            "returns host arrays"},
+                            "returns host arrays",
+                    "ms_each_call": [round(v, 3) for v in e2e_each]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp_pipe", "kernel": dominant, "achieved": ach / 1e12, "peak": peak / 1e12,
                          "unit": "Tlane-op/s", "frac": ach / peak,
