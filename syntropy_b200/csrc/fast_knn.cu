@@ -87,9 +87,20 @@ static int launch_units_dp(const KnnF32Args& a) {
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     }
     // persistent: as many CTAs as fit on the machine (never more than there can be units)
+    // (the occupancy query costs ~10 us of host time: remember the last answer per instantiation)
+    static int cached_dev = -1, cached_per_sm = 0;
+    static size_t cached_smem = 0;
+    int dev = 0;
+    (void)cudaGetDevice(&dev);
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, UNITS_THREADS, smem);
-    if (e != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
+    cudaError_t e = cudaSuccess;
+    if (dev == cached_dev && smem == cached_smem && cached_per_sm > 0) {
+        per_sm = cached_per_sm;
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, UNITS_THREADS, smem);
+        if (e != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
+        cached_dev = dev; cached_smem = smem; cached_per_sm = per_sm;
+    }
     int64_t grid = (int64_t)per_sm * sm_count();
     if (grid > a.max_units) grid = a.max_units;
     kern<<<(unsigned)grid, UNITS_THREADS, smem, a.st>>>(a.shadow, a.sub_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.qshadow, a.qhome, a.seed_thr,
