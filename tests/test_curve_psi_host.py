@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def cut_device_functions():
     prep = open(os.path.join(ROOT, "syntropy_b200", "csrc", "prepare.cuh")).read()
     h0 = prep.index("template <int CAP>\n__device__ __forceinline__ unsigned long long hilbert_index")
-    hilbert = prep[h0:prep.index("// bits per coordinate of the curve", h0)]
+    hilbert = prep[h0:prep.index("\n}\n", h0) + 3]  # the function body only (kernels follow it)
     epi = open(os.path.join(ROOT, "syntropy_b200", "csrc", "epilogue.cuh")).read()
     p0 = epi.index("__device__ inline double psi_of_int")
     psi = epi[p0:epi.index("static __global__ void psi_table_kernel")]
