@@ -374,6 +374,31 @@ int ksg_fast_count(const ksg_prepared* h_prep, int64_t q_begin, int64_t q_end,
 int ksg_axis_count(const ksg_prepared* h_prep, int axis, int64_t q_begin, int64_t q_end,
                    const double* d_eps, int strict, int32_t bias, int32_t* d_counts, void* stream);
 
+/* Several ONE-dimensional subspaces in one launch (the searches are latency-bound: two coordinates side
+ * by side cost little more than one): d_counts[s * nq + (i - q_begin)] for coordinate h_axes[s], nq =
+ * q_end - q_begin.  Both marginals of mutual_information (shannon.py:190-194), every single of
+ * total_correlation / o_information (multivariate_mi.py:106-113,399-404). */
+int ksg_axis_count_multi(const ksg_prepared* h_prep, const int32_t* h_axes, int n_axes, int64_t q_begin,
+                         int64_t q_end, const double* d_eps, int strict, int32_t bias, int32_t* d_counts,
+                         void* stream);
+
+/* The tail of an estimator step in ONE launch, for values of ALL n samples in the prepared order:
+ *   ksg_psi_finish      v_i = the psi program of ksg_psi_epilogue over d_counts[s * n + i],
+ *   ksg_scatter_sum_f64 v_i = d_values_sorted[i] (e.g. all-gathered slices of several ranks),
+ * then d_out[perm[i]] = v_i (the caller's sample order: the `ptw` the reference returns) and
+ * d_total[0] = the deterministic float64 sum of all v_i (ptw.mean() = d_total / n; a fixed tree over
+ * the prepared order, independent of launch geometry and of the number of ranks).  d_ticket: one
+ * int32 that is 0 on entry and 0 again on exit (the block that finishes last folds the partial sums).
+ * Workspace: ksg_finish_workspace(n) bytes. */
+size_t ksg_finish_workspace(int64_t n);
+int ksg_psi_finish(const int32_t* d_counts, int64_t n, int n_subspaces, const ksg_psi_step* h_steps, int n_steps,
+                   double init, double psi_n, int apply_scale, double scale, const double* d_psi_table,
+                   int64_t table_entries, const int32_t* d_perm, double* d_out, double* d_total,
+                   int32_t* d_ticket, void* d_workspace, size_t workspace_bytes, void* stream);
+int ksg_scatter_sum_f64(const double* d_values_sorted, const int32_t* d_perm, int64_t n, double* d_out,
+                        double* d_total, int32_t* d_ticket, void* d_workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* d_dst[perm[i]] = d_src[i], i in [0, n): pointwise values back to the caller's sample order. */
 int ksg_scatter_f64(const double* d_src, const int32_t* d_perm, int64_t n, double* d_dst, void* stream);
 

@@ -113,6 +113,12 @@ SIGNATURES = {
     "ksg_fast_count": (C.c_int, [_c_prep, _c_i64, _c_i64, C.POINTER(C.c_uint32), C.c_int, _c_vp, C.c_int,
                                  C.c_int32, C.c_int, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),
     "ksg_axis_count": (C.c_int, [_c_prep, C.c_int, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int32, _c_vp, _c_vp]),
+    "ksg_axis_count_multi": (C.c_int, [_c_prep, C.POINTER(C.c_int32), C.c_int, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int32,
+                                       _c_vp, _c_vp]),
+    "ksg_finish_workspace": (C.c_size_t, [_c_i64]),
+    "ksg_psi_finish": (C.c_int, [_c_vp, _c_i64, C.c_int, C.POINTER(PsiStep), C.c_int, C.c_double, C.c_double, C.c_int,
+                                 C.c_double, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),
+    "ksg_scatter_sum_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),
     "ksg_scatter_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_scatter_i32": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_gather_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),

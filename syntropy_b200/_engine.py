@@ -451,6 +451,7 @@ class Config:
     kd_min_dim = 7  # point sets of at least this many coordinates are prepared in kd order (when primary < 0)
     own_order = True          # windowed engine: low-dimensional marginals in their own order
     own_order_max_dim = 4     # ... when they have at most this many coordinates
+    fused_tail = True         # single rank: psi program + sample order + sum in one launch (ksg_psi_finish)
 
 
 config = Config()
@@ -657,12 +658,17 @@ def fast_counts(prep: PreparedSet, masks, eps: torch.Tensor, q0: int, q1: int, w
         if out is not counts:
             for row, s in enumerate(multi):
                 counts[s] = out[row]
-    for s in single:
-        axis = int(masks[s]).bit_length() - 1
+    if single and nq:
+        # all 1-D subspaces in one launch (ksg_axis_count_multi writes consecutive rows)
+        axes = (C.c_int32 * len(single))(*[int(masks[s]).bit_length() - 1 for s in single])
+        out1 = counts if len(single) == len(masks) else torch.empty((len(single), nq), dtype=torch.int32, device=dev)
         with timer.span("axis_count"):
-            rc = lib.ksg_axis_count(C.byref(prep.c), axis, q0, q1, _ptr(eps), 1 if strict else 0, bias,
-                                    _ptr(counts[s]), _stream())
-        _cabi.check(rc, "ksg_axis_count")
+            rc = lib.ksg_axis_count_multi(C.byref(prep.c), axes, len(single), q0, q1, _ptr(eps), 1 if strict else 0, bias,
+                                          _ptr(out1), _stream())
+        _cabi.check(rc, "ksg_axis_count_multi")
+        if out1 is not counts:
+            for row, s in enumerate(single):
+                counts[s] = out1[row]
     return counts
 
 
@@ -707,10 +713,11 @@ class Status:
     [12:16) int32 number of queries the speculative k-NN pass could not settle (see ``ksg1_device``)."""
 
     def __init__(self, device):
-        self.buf = torch.zeros(4, dtype=torch.int32, device=device)
+        self.buf = torch.zeros(8, dtype=torch.int32, device=device)
         self.total = self.buf[0:2].view(torch.float64)
         self.finite = self.buf[2:3]
         self.nflag = self.buf[3:4]
+        self.ticket = self.buf[4:5]  # ksg_psi_finish / ksg_scatter_sum_f64: 0 on entry, 0 again on exit
 
     def read_async(self) -> np.ndarray:
         """Enqueue the copy to page-locked host memory; valid after the stream is synchronised."""
@@ -730,8 +737,9 @@ class Pointwise:
     ``Status.nflag`` they were computed under reads 0; otherwise ``redo()`` returns the settled
     Pointwise."""
 
-    def __init__(self, values, prep=None, full=False, preps=(), redo=None):
+    def __init__(self, values, prep=None, full=False, preps=(), redo=None, summed=False):
         self.values, self.prep, self.full, self.preps, self.redo = values, prep, full, list(preps), redo
+        self.summed = summed  # full values whose sum already sits in the Status block (fused tail launch)
 
     def pairs_evaluated(self):
         a = b = 0
@@ -741,17 +749,24 @@ class Pointwise:
         return a, b
 
 
-def finish_device(pw: Pointwise, n_total: int, out: torch.Tensor | None = None):
+def finish_device(pw: Pointwise, n_total: int, out: torch.Tensor | None = None, status: "Status | None" = None):
     """All-gather the pointwise slices (NCCL), put them back into the caller's sample order
     if they were computed in sorted order, and reduce the full vector in a fixed order
-    (into ``out``, a float64[1] device view, when given)."""
+    (into ``out``, a float64[1] device view, when given; ``status``: into its ``total``, with its
+    ticket -- scatter and sum are then one launch)."""
+    ticket = None
+    if status is not None:
+        out, ticket = status.total, status.ticket
     if pw.full:
+        if pw.summed and status is not None:
+            return pw.values, out
         ptw_full = pw.values
     else:
         ptw_full = _dist.gather_slices(pw.values, n_total)
         if pw.prep is not None:
             if out is not None and _text.enabled() and getattr(pw.prep, "struct_bytes", None) is not None:
-                return _text.load().finish_step(ptw_full, pw.prep.struct_bytes, out), out  # scatter + sum, one call
+                # scatter + sum, one call (one launch with a ticket)
+                return _text.load().finish_step(ptw_full, pw.prep.struct_bytes, out, ticket), out
             ptw_full = scatter_to_original(ptw_full, pw.prep)
     return ptw_full, device_sum(ptw_full, out=out)
 
@@ -769,13 +784,13 @@ def settle(pw: Pointwise, n_total: int, status: Status, ptw_full: torch.Tensor, 
         return pw, ptw_full, total
     pw = pw.redo()
     status.nflag.zero_()
-    ptw_full, total = finish_device(pw, n_total, out=status.total)
+    ptw_full, total = finish_device(pw, n_total, status=status)
     return pw, ptw_full, total
 
 
 def _finish(pw: Pointwise, n_total: int, status: Status):
     """Gather the pointwise slices of all ranks, reduce deterministically, copy out."""
-    ptw_full, _ = finish_device(pw, n_total, out=status.total)
+    ptw_full, _ = finish_device(pw, n_total, status=status)
     if pw.redo is not None:
         _dist.sum_counts(status.nflag)  # unsettled queries of ALL ranks: every rank takes the same branch
     host = status.read_async()
@@ -928,11 +943,13 @@ def _ksg1_step_ext(pts, k, masks, prog: PsiProgram, n, q0, q1, windowed, row_rea
     table = psi_table(n + 2)
     steps = prog.steps
     ready = [int(ev.cuda_event) for ev in row_ready] if row_ready else []
+    # one rank owns every query: psi program, sample order and the sum are ONE launch (ksg_psi_finish)
+    fused_tail = q0 == 0 and q1 == n and n > 0 and config.fused_tail
     ptw, prep_buf, prep_struct, eps, flags, _counts = ext.ksg1_step(
         pts, k, axes, prog.init, prog.psi_n, prog.scale is not None, 0.0 if prog.scale is None else prog.scale,
         [st[0] for st in steps], [st[1] for st in steps], [st[2] for st in steps], [st[3] for st in steps],
         [st[4] for st in steps], table, q0, q1, windowed, order_for(dim), default_margin(windowed, k + 1, dim),
-        status.nflag, ready)
+        status.nflag, ready, status.total if fused_tail else None, status.ticket if fused_tail else None)
     prep = PreparedSet.from_raw(prep_buf, prep_struct)
 
     def redo():
@@ -940,6 +957,8 @@ def _ksg1_step_ext(pts, k, masks, prog: PsiProgram, n, q0, q1, windowed, row_rea
         counts2 = fast_counts(prep, masks, eps2, q0, q1, windowed)
         return Pointwise(psi_epilogue(counts2, prog, n), prep=prep, preps=[prep])
 
+    if fused_tail:
+        return Pointwise(ptw, full=True, preps=[prep], redo=redo, summed=True)
     return Pointwise(ptw, prep=prep, preps=[prep], redo=redo)
 
 

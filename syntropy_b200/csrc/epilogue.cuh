@@ -51,6 +51,22 @@ struct PsiProgram {
     double divisor[MAX_PSI_STEPS];
 };
 
+// one sample's value of the psi program (the reference's float64 operation order)
+__device__ __forceinline__ double psi_program_value(const int32_t* __restrict__ counts, int64_t nq,
+                                                    const PsiProgram& prog, const double* __restrict__ table,
+                                                    int64_t entries, int64_t qi) {
+    double v = prog.init;
+    for (int t = 0; t < prog.n_steps; ++t) {
+        int64_t c = (int64_t)counts[(int64_t)prog.subspace[t] * nq + qi] + prog.offset[t];
+        c = c < 0 ? 0 : (c >= entries ? entries - 1 : c);
+        double term = table[c];
+        if (prog.centered[t]) term = __ddiv_rn(__dsub_rn(term, prog.psi_n), prog.divisor[t]);
+        v = prog.sign[t] > 0 ? __dadd_rn(v, term) : __dsub_rn(v, term);
+    }
+    if (prog.apply_scale) v = __dmul_rn(v, prog.scale);
+    return v;
+}
+
 static __global__ void psi_epilogue_kernel(const int32_t* __restrict__ counts, int64_t nq,
                                     const __grid_constant__ PsiProgram prog,
                                     const double* __restrict__ table, int64_t entries,
@@ -128,6 +144,48 @@ sum_stage2_kernel(const double* __restrict__ partial, double* __restrict__ out) 
     for (int i = threadIdx.x; i < SUM_BLOCKS; i += SUM_THREADS) acc = __dadd_rn(acc, partial[i]);
     const double total = block_tree_sum(acc);
     if (threadIdx.x == 0) out[0] = total;
+}
+
+// The tail of an estimator step in ONE launch: pointwise values of ALL n samples in the prepared order
+// (PSI: the psi program over the count rows; else: given values) -> the caller's sample order
+// (out[perm[i]]) + the deterministic sum.  Same fixed tree as sum_stage1/2 (SUM_BLOCKS chunks of the
+// PREPARED order), the second stage run by whichever block finishes last (ticket: 0 on entry, 0 again
+// on exit).  The tree depends only on n and on the prepared order, never on the launch geometry or the
+// number of ranks.
+template <bool PSI>
+static __global__ void __launch_bounds__(SUM_THREADS)
+finish_kernel(const int32_t* __restrict__ counts, const double* __restrict__ values, int64_t n,
+              const __grid_constant__ PsiProgram prog, const double* __restrict__ table, int64_t entries,
+              const int32_t* __restrict__ perm, double* __restrict__ out, double* __restrict__ partial,
+              int32_t* __restrict__ ticket, double* __restrict__ total) {
+    const int64_t chunk = (n + SUM_BLOCKS - 1) / SUM_BLOCKS;
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = min(n, lo + chunk);
+    double acc = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += SUM_THREADS) {
+        double v;
+        if constexpr (PSI) v = psi_program_value(counts, n, prog, table, entries, i);
+        else v = values[i];
+        out[perm[i]] = v;
+        acc = __dadd_rn(acc, v);
+    }
+    const double block_total = block_tree_sum(acc);
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = block_total;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double acc2 = 0.0;
+    for (int i = threadIdx.x; i < SUM_BLOCKS; i += SUM_THREADS) acc2 = __dadd_rn(acc2, __ldcg(&partial[i]));
+    const double t = block_tree_sum(acc2);
+    if (threadIdx.x == 0) {
+        total[0] = t;
+        *ticket = 0;
+    }
 }
 
 }  // namespace ksg

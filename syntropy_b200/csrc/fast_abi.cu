@@ -407,6 +407,12 @@ using namespace ksg;
 
 extern "C" {
 
+// KSG_B200_FUSED_GATHER=0: the four separate kernels behind the key sort (A/B runs)
+static bool fused_gather() {
+    static const bool on = [] { const char* e = getenv("KSG_B200_FUSED_GATHER"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 size_t ksg_prepare_workspace(int64_t n, int dim) {
     if (n <= 0 || dim < 1 || dim > KSG_MAX_DIM) return 0;
     return prepared_layout(n, dim).total;
@@ -503,6 +509,13 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                                                                 bits * dim, st);
                 if (e != cudaSuccess) { set_error("cub SortPairs (curve): %s", cudaGetErrorString(e)); return KSG_ECUDA; }
                 note_launch();
+            }
+            if (fused_gather()) {
+                gather_tile_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 256, 0, st>>>(
+                    d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, invperm,
+                    P.tile_box, P.sub_box, exact_info, exact_off, P.flags);
+                KSG_LAUNCHED2();
+                return KSG_OK;
             }
             gather_sorted_kernel<<<(unsigned)gather_blocks, 256, 0, st>>>(
                 d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded,
@@ -641,14 +654,23 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 note_launch();
             }
         }
+        // axis_pos: original sample index -> position in the final order
+        int32_t* invperm = (int32_t*)(base + L.off_invperm);
+        if (fused_gather()) {
+            gather_tile_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 256, 0, st>>>(
+                d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, invperm,
+                P.tile_box, P.sub_box, exact_info, exact_off, P.flags);
+            KSG_LAUNCHED2();
+            remap_axis_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, invperm);
+            KSG_LAUNCHED2();
+            return KSG_OK;
+        }
         gather_sorted_kernel<<<(unsigned)gather_blocks, 256, 0, st>>>(
             d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded,
             exact_info);
         KSG_LAUNCHED2();
         exact_flag_kernel<<<1, 256, 0, st>>>(exact_info, gather_blocks, dim, exact_off, P.flags);
         KSG_LAUNCHED2();
-        // axis_pos: original sample index -> position in the final order
-        int32_t* invperm = (int32_t*)(base + L.off_invperm);
         invert_perm_kernel<<<nb, 256, 0, st>>>(P.perm, n, invperm);
         KSG_LAUNCHED2();
         remap_axis_kernel<<<dim3(nb, dim), 256, 0, st>>>(P.axis_pos, L.ld, n, invperm);
@@ -1069,6 +1091,26 @@ int ksg_axis_count(const ksg_prepared* P, int axis, int64_t q_begin, int64_t q_e
         axis_count_kernel<<<(unsigned)ceil_div(nq, AXIS_THREADS), AXIS_THREADS, 0, as_stream2(stream)>>>(
             P->sorted_f64 + (int64_t)axis * P->ld, P->axis_vals + (int64_t)axis * P->ld, P->n, q_begin, nq, d_eps,
             strict ? 1 : 0, bias, d_counts);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+int ksg_axis_count_multi(const ksg_prepared* P, const int32_t* h_axes, int n_axes, int64_t q_begin, int64_t q_end,
+                         const double* d_eps, int strict, int32_t bias, int32_t* d_counts, void* stream) {
+    KSG_REQUIRE(P && h_axes && d_eps && d_counts, "ksg_axis_count_multi: null pointer");
+    KSG_REQUIRE(n_axes >= 1 && n_axes <= KSG_MAX_DIM, "ksg_axis_count_multi: 1 <= n_axes <= KSG_MAX_DIM");
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_axis_count_multi: bad query range");
+    AxisList axes;
+    for (int a = 0; a < n_axes; ++a) {
+        KSG_REQUIRE(h_axes[a] >= 0 && h_axes[a] < P->dim, "ksg_axis_count_multi: axis out of range");
+        axes.axis[a] = h_axes[a];
+    }
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    const int rc0 = wait_axes(P, as_stream2(stream));
+    if (rc0) return rc0;
+    axis_count_sorted_multi_kernel<<<dim3((unsigned)ceil_div(P->n, 256), (unsigned)n_axes), 256, 0, as_stream2(stream)>>>(
+        P->axis_vals, P->axis_pos, P->ld, axes, P->n, q_begin, nq, d_eps, strict ? 1 : 0, bias, d_counts);
     KSG_LAUNCHED2();
     return KSG_OK;
 }

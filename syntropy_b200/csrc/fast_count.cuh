@@ -482,11 +482,10 @@ axis_count_kernel(const double* __restrict__ sorted_row, const double* __restric
 // steps, then a bisection of the last step): ~2 log2(count) loads instead of 2 log2(n), and the runs of
 // neighbouring threads nearly coincide, so a warp touches one or two cache lines per step instead of 32.
 // Rows outside the query slice [q_begin, q_begin + nq) are skipped (several ranks).
-static __global__ void __launch_bounds__(256)
-axis_count_sorted_kernel(const double* __restrict__ vals, const int32_t* __restrict__ pos, int64_t n,
-                         int64_t q_begin, int64_t nq, const double* __restrict__ eps, int strict, int32_t bias,
-                         int32_t* __restrict__ counts) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void axis_count_sorted_one(const double* __restrict__ vals, const int32_t* __restrict__ pos,
+                                                      int64_t n, int64_t q_begin, int64_t nq,
+                                                      const double* __restrict__ eps, int strict, int32_t bias,
+                                                      int32_t* __restrict__ counts, int64_t i) {
     if (i >= n) return;
     const int64_t qi = (int64_t)pos[i] - q_begin;
     if (qi < 0 || qi >= nq) return;
@@ -520,6 +519,14 @@ axis_count_sorted_kernel(const double* __restrict__ vals, const int32_t* __restr
     counts[qi] = (int32_t)(right - left) + bias;
 }
 
+static __global__ void __launch_bounds__(256)
+axis_count_sorted_kernel(const double* __restrict__ vals, const int32_t* __restrict__ pos, int64_t n,
+                         int64_t q_begin, int64_t nq, const double* __restrict__ eps, int strict, int32_t bias,
+                         int32_t* __restrict__ counts) {
+    axis_count_sorted_one(vals, pos, n, q_begin, nq, eps, strict, bias, counts,
+                          (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 static __global__ void scatter_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ perm, int64_t n,
                                    double* __restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -551,6 +558,20 @@ static __global__ void gather_f64_kernel(const double* __restrict__ src, const i
                                   double* __restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[perm[i]];
+}
+
+// Several 1-D marginals in ONE launch (blockIdx.y = which): the searches are latency-bound, two
+// coordinates side by side cost little more than one.  counts: [n_axes][nq].
+struct AxisList {
+    int32_t axis[KSG_MAX_DIM];
+};
+static __global__ void __launch_bounds__(256)
+axis_count_sorted_multi_kernel(const double* __restrict__ axis_vals, const int32_t* __restrict__ axis_pos, int64_t ld,
+                               const AxisList axes, int64_t n, int64_t q_begin, int64_t nq,
+                               const double* __restrict__ eps, int strict, int32_t bias, int32_t* __restrict__ counts) {
+    const int64_t a = axes.axis[blockIdx.y];
+    axis_count_sorted_one(axis_vals + a * ld, axis_pos + a * ld, n, q_begin, nq, eps, strict, bias,
+                          counts + (int64_t)blockIdx.y * nq, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 }  // namespace ksg

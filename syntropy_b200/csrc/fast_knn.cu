@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include "fast_knn.cuh"
+#include "fast_knn_warp.cuh"
 
 namespace ksg {
 
@@ -76,8 +77,65 @@ static int launch_plan_kc(const KnnF32Args& a) {
     return KSG_OK;
 }
 
+// Few dimensions: every warp its own worker (fast_knn_warp.cuh).  KSG_B200_UNITS=cta keeps the CTA-level
+// kernel with the shared tile ring (experiments, A/B runs).
+static bool warp_units_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KSG_B200_UNITS");
+        return !(e && e[0] == 'c');
+    }();
+    return on;
+}
+
+template <int DP, int KC>
+static int launch_wunits_kc(const KnnF32Args& a) {
+    auto kern = knn_wunits_kernel<DP, KC>;
+    const size_t smem = (FAST_THREADS / 32) * wunits_smem_per_warp(KC, DP);
+    if (smem > 32 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    }
+    // persistent: as many CTAs as fit on the machine (four work items per unit, one per warp)
+    static int cached_dev = -1, cached_per_sm = 0;
+    static size_t cached_smem = 0;
+    int dev = 0;
+    (void)cudaGetDevice(&dev);
+    int per_sm = 0;
+    cudaError_t e = cudaSuccess;
+    if (dev == cached_dev && smem == cached_smem && cached_per_sm > 0) {
+        per_sm = cached_per_sm;
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FAST_THREADS, smem);
+        if (e != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
+        cached_dev = dev; cached_smem = smem; cached_per_sm = per_sm;
+    }
+    int64_t grid = (int64_t)per_sm * sm_count();
+    if (grid > a.max_units) grid = a.max_units;
+    kern<<<(unsigned)grid, FAST_THREADS, smem, a.st>>>(a.shadow, a.sub_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.qshadow, a.qhome,
+                                                      a.seed_thr, (const int2*)a.plan, a.plan_count, a.plan_first, a.unit_first,
+                                                      a.unit_block, a.unit_meta, a.part_d32, a.part_idx, a.tile_counter,
+                                                      a.unit_done, a.ra);
+    note_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("knn_wunits_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    return KSG_OK;
+}
+
+template <int DP>
+static int launch_wunits_dp(const KnnF32Args& a) {
+    switch (wunits_list_capacity(a.kcap)) {
+        case 8: return launch_wunits_kc<DP, 8>(a);
+        case 12: return launch_wunits_kc<DP, 12>(a);
+        case 16: return launch_wunits_kc<DP, 16>(a);
+        default: return launch_wunits_kc<DP, WU_MAX_KC>(a);
+    }
+}
+
 template <int DP>
 static int launch_units_dp(const KnnF32Args& a) {
+    if constexpr (DP <= 4 && UNITS_Q == 1) {
+        if (warp_units_enabled() && a.kcap <= WU_MAX_KC) return launch_wunits_dp<DP>(a);
+    }
     constexpr int Q = UnitsQ<DP>::Q, ST = FastGeom<DP>::STAGES;
     auto kern = knn_units_kernel<DP, Q, ST, (DP <= 4)>;
     const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float) +

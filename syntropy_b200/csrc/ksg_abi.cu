@@ -308,6 +308,70 @@ int ksg_psi_epilogue(const int32_t* d_counts, int64_t nq, int n_subspaces, const
     return KSG_OK;
 }
 
+static int fill_psi_program(PsiProgram& prog, int n_subspaces, const ksg_psi_step* h_steps, int n_steps, double init,
+                            double psi_n, int apply_scale, double scale) {
+    KSG_REQUIRE(n_steps >= 0 && n_steps <= MAX_PSI_STEPS, "psi program: too many steps");
+    memset(&prog, 0, sizeof(prog));
+    prog.n_steps = n_steps;
+    prog.apply_scale = apply_scale;
+    prog.init = init;
+    prog.psi_n = psi_n;
+    prog.scale = scale;
+    for (int t = 0; t < n_steps; ++t) {
+        KSG_REQUIRE(h_steps[t].subspace >= 0 && h_steps[t].subspace < n_subspaces,
+                    "psi program: step refers to a missing subspace");
+        KSG_REQUIRE(h_steps[t].count_offset >= -100 && h_steps[t].count_offset <= 100,
+                    "psi program: count_offset out of range");
+        prog.subspace[t] = (int16_t)h_steps[t].subspace;
+        prog.offset[t] = (int8_t)h_steps[t].count_offset;
+        prog.sign[t] = (int8_t)(h_steps[t].sign >= 0 ? 1 : -1);
+        prog.centered[t] = (int8_t)(h_steps[t].centered != 0);
+        prog.divisor[t] = h_steps[t].divisor;
+    }
+    return KSG_OK;
+}
+
+size_t ksg_finish_workspace(int64_t n) {
+    (void)n;
+    return SUM_BLOCKS * sizeof(double);
+}
+
+int ksg_psi_finish(const int32_t* d_counts, int64_t n, int n_subspaces, const ksg_psi_step* h_steps, int n_steps,
+                   double init, double psi_n, int apply_scale, double scale, const double* d_psi_table,
+                   int64_t table_entries, const int32_t* d_perm, double* d_out, double* d_total, int32_t* d_ticket,
+                   void* d_workspace, size_t workspace_bytes, void* stream) {
+    KSG_REQUIRE(d_counts && h_steps && d_psi_table && d_perm && d_out && d_total && d_ticket, "ksg_psi_finish: null pointer");
+    KSG_REQUIRE(table_entries >= 1 && n >= 0, "ksg_psi_finish: bad sizes");
+    if (!d_workspace || workspace_bytes < SUM_BLOCKS * sizeof(double)) {
+        set_error("ksg_psi_finish: workspace of %zu bytes needed", SUM_BLOCKS * sizeof(double));
+        return KSG_EWORKSPACE;
+    }
+    PsiProgram prog;
+    const int rc = fill_psi_program(prog, n_subspaces, h_steps, n_steps, init, psi_n, apply_scale, scale);
+    if (rc) return rc;
+    finish_kernel<true><<<SUM_BLOCKS, SUM_THREADS, 0, as_stream(stream)>>>(d_counts, nullptr, n, prog, d_psi_table,
+                                                                          table_entries, d_perm, d_out,
+                                                                          (double*)d_workspace, d_ticket, d_total);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_scatter_sum_f64(const double* d_values_sorted, const int32_t* d_perm, int64_t n, double* d_out, double* d_total,
+                        int32_t* d_ticket, void* d_workspace, size_t workspace_bytes, void* stream) {
+    KSG_REQUIRE(d_values_sorted && d_perm && d_out && d_total && d_ticket && n >= 0, "ksg_scatter_sum_f64: bad argument");
+    if (!d_workspace || workspace_bytes < SUM_BLOCKS * sizeof(double)) {
+        set_error("ksg_scatter_sum_f64: workspace of %zu bytes needed", SUM_BLOCKS * sizeof(double));
+        return KSG_EWORKSPACE;
+    }
+    PsiProgram prog;
+    memset(&prog, 0, sizeof(prog));
+    finish_kernel<false><<<SUM_BLOCKS, SUM_THREADS, 0, as_stream(stream)>>>(nullptr, d_values_sorted, n, prog, nullptr, 0,
+                                                                           d_perm, d_out, (double*)d_workspace,
+                                                                           d_ticket, d_total);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
 int ksg_entropy_epilogue(const double* d_eps, int64_t nq, int dim, double psi_k, double psi_n, double* d_ptw,
                          void* stream) {
     KSG_REQUIRE(d_eps && d_ptw && nq >= 0 && dim >= 1, "ksg_entropy_epilogue: bad argument");

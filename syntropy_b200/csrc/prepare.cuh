@@ -213,6 +213,150 @@ exact_flag_kernel(const int32_t* __restrict__ exact_info, int64_t n_blocks, int 
     if (threadIdx.x == 0) flags[8] = s_ok;
 }
 
+// gather_sorted_kernel + invert_perm_kernel + tile_box_kernel + exact_flag_kernel as ONE launch, one CTA
+// per 512-row tile (two passes of 256 rows; warp w of pass p owns sub-tile 8 p + w, so the sub-tile
+// boxes are warp reductions of values still in registers).  The CTA that finishes last (ticket =
+// flags[9], zeroed with the flag block at the start of ksg_prepare) folds the per-tile exactness
+// records into flags[8].  Same outputs, bit for bit, as the four kernels.
+static __global__ void __launch_bounds__(256)
+gather_tile_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, int dim, int dim_padded,
+                   const int32_t* __restrict__ perm, const double* __restrict__ center,
+                   double* __restrict__ sorted, int64_t ld, float* __restrict__ shadow,
+                   int32_t* __restrict__ invperm, float* __restrict__ tile_box, float* __restrict__ sub_box,
+                   int32_t* __restrict__ exact_info, int force_off, int32_t* __restrict__ flags) {
+    static_assert(FAST_TILE == 512 && FAST_SUB == 32, "two passes of 256 rows, one sub-tile per warp and pass");
+    __shared__ float slo[8][KSG_MAX_DIM], shi[8][KSG_MAX_DIM];
+    __shared__ int s_low[8][8], s_high[8][8], s_bad[8], s_last;
+    const int64_t t = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool analyse = dim <= 8;
+    int inexact = 0;
+    int alow[8], ahigh[8];  // (dim <= 8 only) per coordinate, this thread's two rows
+#pragma unroll
+    for (int d = 0; d < 8; ++d) { alow[d] = EXACT_NONE_LOW; ahigh[d] = EXACT_NONE_HIGH; }
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {
+        const int64_t i = t * FAST_TILE + p * 256 + threadIdx.x;
+        const bool real = i < n;
+        const int64_t src = real ? perm[i] : 0;
+        if (real && invperm) invperm[src] = (int32_t)i;
+        const int sub = p * 8 + warp;
+        for (int d = 0; d < dim_padded; ++d) {
+            float s;
+            if (d < dim) {
+                if (real) {
+                    const double v = pts[(int64_t)d * ld_in + src], c = center[d];
+                    sorted[(int64_t)d * ld + i] = v;
+                    const double tt = __dsub_rn(v, c);
+                    s = __double2float_rn(tt);
+                    if (analyse) {
+                        // error-free transformation of v - c (TwoSum) and of the conversion
+                        const double bb = __dsub_rn(tt, v);
+                        const double err = __dadd_rn(__dsub_rn(v, __dsub_rn(tt, bb)), __dsub_rn(-c, bb));
+                        inexact |= !(err == 0.0) || !((double)s == tt);
+                        if (s != 0.0f && isfinite(s)) {
+                            int low, high;
+                            shadow_bit_range(s, low, high);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (e == d) { alow[e] = min(alow[e], low); ahigh[e] = max(ahigh[e], high); }
+                        }
+                    }
+                } else {
+                    s = CUDART_INF_F;
+                }
+            } else {
+                s = 0.0f;
+            }
+            shadow[i * dim_padded + d] = s;  // (n_padded is a multiple of the tile: every row exists)
+            float lo = s, hi = s;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+            }
+            if (lane == 0) {
+                sub_box[((t * FAST_NSUB + sub) * dim_padded + d) * 2 + 0] = lo;
+                sub_box[((t * FAST_NSUB + sub) * dim_padded + d) * 2 + 1] = hi;
+                slo[warp][d] = p == 0 ? lo : fminf(slo[warp][d], lo);
+                shi[warp][d] = p == 0 ? hi : fmaxf(shi[warp][d], hi);
+            }
+        }
+    }
+    if (analyse) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+            if (d < dim) {
+                const int low = __reduce_min_sync(0xffffffffu, alow[d]);
+                const int high = __reduce_max_sync(0xffffffffu, ahigh[d]);
+                if (lane == 0) { s_low[warp][d] = low; s_high[warp][d] = high; }
+            }
+        inexact = __any_sync(0xffffffffu, inexact);
+        if (lane == 0) s_bad[warp] = inexact;
+    }
+    __syncthreads();
+    if (threadIdx.x < dim_padded) {
+        const int d = threadIdx.x;
+        float lo = slo[0][d], hi = shi[0][d];
+        for (int w = 1; w < 8; ++w) { lo = fminf(lo, slo[w][d]); hi = fmaxf(hi, shi[w][d]); }
+        tile_box[(t * dim_padded + d) * 2 + 0] = lo;
+        tile_box[(t * dim_padded + d) * 2 + 1] = hi;
+    }
+    if (!analyse || force_off) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[8] = 0;
+        return;
+    }
+    int32_t* rec = exact_info + t * EXACT_INFO_INTS;
+    if (threadIdx.x < dim) {
+        const int d = threadIdx.x;
+        int low = EXACT_NONE_LOW, high = EXACT_NONE_HIGH;
+        for (int w = 0; w < 8; ++w) { low = min(low, s_low[w][d]); high = max(high, s_high[w][d]); }
+        rec[1 + 2 * d] = low;
+        rec[2 + 2 * d] = high;
+    }
+    if (threadIdx.x == 0) {
+        int bad = 0;
+        for (int w = 0; w < 8; ++w) bad |= s_bad[w];
+        rec[0] = bad;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&flags[9], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    // ---- the last CTA folds every tile's record (exact_flag_kernel)
+    __threadfence();
+    __shared__ int f_low[256], f_high[256], f_ok;
+    if (threadIdx.x == 0) f_ok = 1;
+    __syncthreads();
+    const int64_t n_rec = gridDim.x;
+    int bad = 0;
+    for (int64_t b = threadIdx.x; b < n_rec; b += 256) bad |= __ldcg(&exact_info[b * EXACT_INFO_INTS]);
+    if (bad) f_ok = 0;
+    for (int d = 0; d < dim; ++d) {
+        int low = EXACT_NONE_LOW, high = EXACT_NONE_HIGH;
+        for (int64_t b = threadIdx.x; b < n_rec; b += 256) {
+            low = min(low, __ldcg(&exact_info[b * EXACT_INFO_INTS + 1 + 2 * d]));
+            high = max(high, __ldcg(&exact_info[b * EXACT_INFO_INTS + 2 + 2 * d]));
+        }
+        f_low[threadIdx.x] = low;
+        f_high[threadIdx.x] = high;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            if (threadIdx.x < off) {
+                f_low[threadIdx.x] = min(f_low[threadIdx.x], f_low[threadIdx.x + off]);
+                f_high[threadIdx.x] = max(f_high[threadIdx.x], f_high[threadIdx.x + off]);
+            }
+            __syncthreads();
+        }
+        // (a coordinate that is all zeros has no bits at all: fine)
+        if (threadIdx.x == 0 && f_low[0] != EXACT_NONE_LOW && f_high[0] - f_low[0] > 22) f_ok = 0;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) flags[8] = f_ok;
+}
+
 // ---- space-filling-curve order on per-coordinate RANKS (rank-uniform: cells hold ~equal point counts)
 // rank[d][orig] = position of sample `orig` in coordinate d's sorted order
 // (grid.y = coordinate; both arrays have row stride ld)

@@ -96,7 +96,8 @@ std::vector<at::Tensor> ksg1_step(at::Tensor pts, int64_t k, std::vector<int64_t
                                   std::vector<int64_t> step_off, std::vector<int64_t> step_sign,
                                   std::vector<int64_t> step_centered, std::vector<double> step_div,
                                   at::Tensor psi_table, int64_t q0, int64_t q1, bool windowed, int64_t primary,
-                                  int64_t margin, at::Tensor nflag, std::vector<int64_t> row_ready) {
+                                  int64_t margin, at::Tensor nflag, std::vector<int64_t> row_ready,
+                                  c10::optional<at::Tensor> total, c10::optional<at::Tensor> ticket) {
     TORCH_CHECK(pts.is_cuda() && pts.scalar_type() == at::kDouble && pts.dim() == 2 && pts.stride(1) == 1,
                 "pts must be a (D, n) float64 CUDA tensor with unit column stride");
     c10::cuda::CUDAGuard guard(pts.device());
@@ -136,12 +137,13 @@ std::vector<at::Tensor> ksg1_step(at::Tensor pts, int64_t k, std::vector<int64_t
                                       ws_bytes, st),
                   "ksg_fast_knn_margin");
         }
-        // ---- one exact 1-D count per marginal
-        for (size_t s_i = 0; s_i < axes.size(); ++s_i) {
+        // ---- the exact 1-D counts of all marginals, one launch
+        {
+            std::vector<int32_t> ax(axes.begin(), axes.end());
             Scope s("axis_count", st);
-            check(ksg_axis_count(&P, (int)axes[s_i], q0, q1, eps.data_ptr<double>(), 1, -1,
-                                 counts.data_ptr<int32_t>() + (int64_t)s_i * nq, st),
-                  "ksg_axis_count");
+            check(ksg_axis_count_multi(&P, ax.data(), (int)ax.size(), q0, q1, eps.data_ptr<double>(), 1, -1,
+                                       counts.data_ptr<int32_t>(), st),
+                  "ksg_axis_count_multi");
         }
         // ---- psi program
         std::vector<ksg_psi_step> steps(step_sub.size() ? step_sub.size() : 1);
@@ -151,6 +153,19 @@ std::vector<at::Tensor> ksg1_step(at::Tensor pts, int64_t k, std::vector<int64_t
             steps[t].sign = (int32_t)step_sign[t];
             steps[t].centered = (int32_t)step_centered[t];
             steps[t].divisor = step_div[t];
+        }
+        if (total.has_value() && ticket.has_value() && q0 == 0 && q1 == n) {
+            // one rank owns every query: psi program + sample order + deterministic sum in ONE launch
+            // (ptw then holds all n values in the CALLER's order and *total their sum)
+            const size_t fin_bytes = ksg_finish_workspace(n);
+            at::Tensor fin_ws = bytes(fin_bytes, pts);
+            Scope s("psi_finish", st);
+            check(ksg_psi_finish(counts.data_ptr<int32_t>(), n, (int)axes.size(), steps.data(), (int)step_sub.size(), init,
+                                 psi_n, apply_scale ? 1 : 0, scale, psi_table.data_ptr<double>(), psi_table.numel(), P.perm,
+                                 ptw.data_ptr<double>(), total->data_ptr<double>(), ticket->data_ptr<int32_t>(),
+                                 fin_ws.data_ptr(), fin_bytes, st),
+                  "ksg_psi_finish");
+            return {ptw, prep_buf, prep_struct, eps, flags, counts};
         }
         Scope s("psi_epilogue", st);
         check(ksg_psi_epilogue(counts.data_ptr<int32_t>(), nq, (int)axes.size(), steps.data(), (int)step_sub.size(), init,
@@ -162,13 +177,23 @@ std::vector<at::Tensor> ksg1_step(at::Tensor pts, int64_t k, std::vector<int64_t
 }
 
 // full pointwise vector (prepared order) -> caller's sample order + fixed-order sum into `total`
-at::Tensor finish_step(at::Tensor values_sorted, at::Tensor prep_struct, at::Tensor total) {
+at::Tensor finish_step(at::Tensor values_sorted, at::Tensor prep_struct, at::Tensor total,
+                       c10::optional<at::Tensor> ticket) {
     c10::cuda::CUDAGuard guard(values_sorted.device());
     ksg_prepared P;
     std::memcpy(&P, prep_struct.data_ptr(), sizeof(P));
     const int64_t n = values_sorted.numel();
     void* st = stream_of(values_sorted);
     at::Tensor out = at::empty_like(values_sorted);
+    if (ticket.has_value()) {  // scatter + both stages of the sum in one launch
+        const size_t fin_bytes = ksg_finish_workspace(n);
+        at::Tensor fin_ws = bytes(fin_bytes, values_sorted);
+        Scope s("scatter_sum", st);
+        check(ksg_scatter_sum_f64(values_sorted.data_ptr<double>(), P.perm, n, out.data_ptr<double>(),
+                                  total.data_ptr<double>(), ticket->data_ptr<int32_t>(), fin_ws.data_ptr(), fin_bytes, st),
+              "ksg_scatter_sum_f64");
+        return out;
+    }
     check(ksg_scatter_f64(values_sorted.data_ptr<double>(), P.perm, n, out.data_ptr<double>(), st), "ksg_scatter_f64");
     const size_t ws_bytes = ksg_sum_workspace(n);
     at::Tensor ws = bytes(ws_bytes, values_sorted);

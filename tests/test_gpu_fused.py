@@ -1,0 +1,220 @@
+"""GPU checks of the round-2 launch fusions and of the warp-level k-NN kernel against the kernels they
+replace (all through the C ABI):
+
+* ``gather_tile_kernel`` (gather + shadow + inverse permutation + boxes + exactness flag, one launch) builds
+  prepared sets identical, byte for byte, to the four separate kernels (``KSG_B200_FUSED_GATHER=0``);
+* ``knn_wunits_kernel`` (every warp its own worker, unsorted lists) returns the radii, flags and neighbour
+  lists of ``knn_units_kernel`` (``KSG_B200_UNITS=cta``) -- continuous, quantised, heavy-tailed data, 1 to 4
+  coordinates, short and long lists, cross-set queries;
+* ``ksg_axis_count_multi`` == one ``ksg_axis_count`` per coordinate;
+* ``ksg_psi_finish`` / ``ksg_scatter_sum_f64`` == ``ksg_psi_epilogue`` + ``ksg_scatter_f64`` (+ ``ksg_sum_f64``
+  up to the summation order; the ticket comes back to 0).
+"""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sets():
+    from syntropy_b200 import workloads
+
+    rng = np.random.default_rng(19)
+    heavy = rng.standard_t(1.3, size=(2, 60_000))
+    return [("c2", workloads.c2_mi_1m(n=300_000)[0]),
+            ("c3", workloads.c3_cmi(n=40_000)[0]),
+            ("3d", rng.standard_normal((3, 5_000))),
+            ("1d", rng.standard_normal((1, 7_001))),
+            ("4d", rng.standard_normal((4, 33_000)) + 1e3),
+            ("quantised", np.round(rng.standard_normal((2, 80_000)) * 8) / 8 + 0.0),
+            ("integers", rng.integers(-50, 50, size=(3, 20_000)).astype(np.float64)),
+            ("heavy", heavy),
+            ("8d", rng.standard_normal((8, 9_000))),
+            ("tiny", rng.standard_normal((2, 37)))]
+
+
+def _prepared_digest():
+    """sha1 over everything ksg_prepare writes (orders, both copies, boxes, flags) for a few point sets."""
+    import torch
+
+    from syntropy_b200 import _engine as E
+
+    out = []
+    for name, rows in _sets():
+        pts = E.to_device_points(rows)
+        prep = E.PreparedSet(pts, E.order_for(rows.shape[0]))
+        E._cabi.check(E._cabi.load().ksg_prepare_join(C.byref(prep.c), E._stream()), "ksg_prepare_join")
+        torch.cuda.synchronize()
+        h = hashlib.sha1()
+        dim, n, ld, dp, npad = prep.dim, prep.n, prep.ld, int(prep.c.dim_padded), int(prep.c.n_padded)
+        tiles = npad // 512
+        h.update(prep.perm.cpu().numpy().tobytes())
+        h.update(prep.sorted_f64.cpu().numpy().tobytes())
+        h.update(prep._view(prep.c.shadow_f32, npad * dp * 4, torch.float32).cpu().numpy().tobytes())
+        h.update(prep._view(prep.c.tile_box, tiles * dp * 2 * 4, torch.float32).cpu().numpy().tobytes())
+        h.update(prep._view(prep.c.sub_box, tiles * 16 * dp * 2 * 4, torch.float32).cpu().numpy().tobytes())
+        h.update(prep._view(prep.c.axis_vals, dim * ld * 8, torch.float64).view(dim, ld)[:, :n].cpu().numpy().tobytes())
+        h.update(prep._view(prep.c.axis_pos, dim * ld * 4, torch.int32).view(dim, ld)[:, :n].cpu().numpy().tobytes())
+        flags = prep._view(prep.c.flags, 64, torch.int32).cpu().numpy()
+        h.update(flags[[0, 8]].tobytes())  # non-finite input, "the fp32 copy is exact"
+        out.append("%s:%s:exact32=%d" % (name, h.hexdigest(), int(flags[8])))
+    return "|".join(out)
+
+
+def _knn_digest():
+    """sha1 over radii / flags / neighbour lists of the windowed k-NN stage (first pass, nothing escalated)."""
+    import torch
+
+    from syntropy_b200 import _engine as E
+
+    out = []
+    rng = np.random.default_rng(23)
+    for name, rows in _sets():
+        dim = rows.shape[0]
+        if dim > 4:
+            continue
+        pts = E.to_device_points(rows)
+        prep = E.PreparedSet(pts, -1)
+        n = prep.n
+        # (k' + margin = 8, 12, 16, 24: the list capacities of the warp-level kernel, so that both kernels keep
+        #  lists of the same length and flag the same tie-saturated queries; 44 and 36: too long for it)
+        for kprime, margin, want_idx in ((2, 6, False), (6, 6, False), (6, 6, True), (9, 7, False), (12, 12, False),
+                                         (20, 24, False), (30, 6, False)):
+            if kprime >= n:
+                continue
+            eps, idx, flags, nflag = E._fast_knn_call(prep, kprime, 0, n, True, want_indices=want_idx, margin=margin)
+            torch.cuda.synchronize()
+            h = hashlib.sha1()
+            f = flags.cpu().numpy()
+            e = eps.cpu().numpy()
+            h.update(f.tobytes())
+            h.update(e[f == 0].tobytes())
+            if want_idx:
+                h.update(idx.cpu().numpy()[f == 0].tobytes())
+            out.append("%s/k%d/m%d:%s:flagged=%d" % (name, kprime, margin, h.hexdigest(), int(nflag.item())))
+        # a query slice that starts inside a block, and a cross-set search
+        q0, q1 = n // 3 + 5, n // 3 + 5 + min(n // 2, 4_321)
+        eps, _, flags, _ = E._fast_knn_call(prep, 4, q0, q1, True)
+        out.append("%s/slice:%s" % (name, hashlib.sha1(eps.cpu().numpy().tobytes() + flags.cpu().numpy().tobytes()).hexdigest()))
+        if dim >= 2 and n >= 1000:
+            other = torch.from_numpy(np.ascontiguousarray(rows[:, ::-1] * 1.05 + 0.01 * rng.standard_normal(rows.shape))).cuda()
+            cross = E.CrossSet(prep, other)
+            r = E.fast_knn_cross(cross, 3, 0, other.shape[1])
+            out.append("%s/cross:%s" % (name, hashlib.sha1(r.cpu().numpy().tobytes()).hexdigest()))
+    return "|".join(out)
+
+
+def _in_subprocess(fn_name, **env):
+    code = ("import sys; sys.path.insert(0, %r); from tests import test_gpu_fused as t; print(t.%s())" % (ROOT, fn_name))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **env),
+                         timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return out.stdout.strip().splitlines()[-1]
+
+
+def _diff(a, b):
+    return [x + "  !=  " + y for x, y in zip(a.split("|"), b.split("|")) if x != y]
+
+
+def test_fused_gather_builds_identical_prepared_sets():
+    mine = _prepared_digest()
+    assert "quantised:" in mine and "exact32=1" in mine and "exact32=0" in mine  # both outcomes of the exactness fold
+    ref = _in_subprocess("_prepared_digest", KSG_B200_FUSED_GATHER="0")
+    assert mine == ref, _diff(mine, ref)
+
+
+def test_warp_level_knn_equals_the_cta_level_kernel():
+    mine = _knn_digest()
+    ref = _in_subprocess("_knn_digest", KSG_B200_UNITS="cta")
+    assert mine == ref, _diff(mine, ref)
+
+
+def test_axis_count_multi_equals_single_launches():
+    import torch
+
+    from syntropy_b200 import _engine as E
+
+    lib = E._cabi.load()
+    rng = np.random.default_rng(5)
+    for rows, k in ((rng.standard_normal((3, 50_000)), 4), (np.round(rng.standard_normal((2, 20_000)) * 4) / 4, 3)):
+        pts = E.to_device_points(rows)
+        prep = E.PreparedSet(pts, -1)
+        n, dim = prep.n, prep.dim
+        eps = E.fast_knn(prep, k + 1, 0, n, True)
+        for q0, q1 in ((0, n), (n // 4 + 3, n // 2 + 11)):
+            nq = q1 - q0
+            e = eps[q0:q1].contiguous()
+            axes = list(range(dim))[::-1]
+            multi = torch.empty((dim, nq), dtype=torch.int32, device=pts.device)
+            arr = (C.c_int32 * dim)(*axes)
+            E._cabi.check(lib.ksg_axis_count_multi(C.byref(prep.c), arr, dim, q0, q1, E._ptr(e), 1, -1, E._ptr(multi),
+                                                   E._stream()), "ksg_axis_count_multi")
+            for row, axis in enumerate(axes):
+                one = torch.empty(nq, dtype=torch.int32, device=pts.device)
+                E._cabi.check(lib.ksg_axis_count(C.byref(prep.c), axis, q0, q1, E._ptr(e), 1, -1, E._ptr(one), E._stream()),
+                              "ksg_axis_count")
+                assert torch.equal(multi[row], one)
+
+
+def test_fused_tail_equals_epilogue_scatter_sum():
+    import torch
+
+    from syntropy_b200 import _engine as E
+
+    lib = E._cabi.load()
+    rng = np.random.default_rng(6)
+    for n in (1, 37, 1000, 300_001):
+        dev = torch.device("cuda")
+        counts = torch.from_numpy(rng.integers(0, max(n - 1, 1), size=(3, n)).astype(np.int32)).to(dev)
+        perm = torch.from_numpy(rng.permutation(n).astype(np.int32)).to(dev)
+        prog = E.PsiProgram(init=0.25, psi_n=E.psi_host(n), scale=0.5)
+        prog.add(0, -1)
+        prog.add(1, -1, count_offset=0)
+        prog.add(2, +1, centered=True, divisor=3.0)
+        ptw = E.psi_epilogue(counts, prog, n)
+        ref = torch.empty_like(ptw)
+        E._cabi.check(lib.ksg_scatter_f64(E._ptr(ptw), E._ptr(perm), n, E._ptr(ref), E._stream()), "ksg_scatter_f64")
+        ref_sum = float(E.device_sum(ref).item())
+        table = E.psi_table(n + 2)
+        steps = (E._cabi.PsiStep * len(prog.steps))(*[E._cabi.PsiStep(*st) for st in prog.steps])
+        ws = torch.empty(int(lib.ksg_finish_workspace(n)), dtype=torch.uint8, device=dev)
+        status = E.Status(dev)
+        for _ in range(2):  # the ticket must come back to 0: the second call works like the first
+            out = torch.full((n,), -7.0, dtype=torch.float64, device=dev)
+            E._cabi.check(lib.ksg_psi_finish(E._ptr(counts), n, 3, steps, len(prog.steps), prog.init, prog.psi_n, 1, prog.scale,
+                                             E._ptr(table), table.numel(), E._ptr(perm), E._ptr(out), E._ptr(status.total),
+                                             E._ptr(status.ticket), E._ptr(ws), ws.numel(), E._stream()), "ksg_psi_finish")
+            assert torch.equal(out, ref)
+            got = float(status.total.item())
+            assert abs(got - ref_sum) <= 1e-12 * max(abs(ref_sum), float(ref.abs().sum().item()) * 1e-3 + 1e-300)
+            assert int(status.ticket.item()) == 0
+        out2 = torch.full((n,), -7.0, dtype=torch.float64, device=dev)
+        total2 = torch.zeros(1, dtype=torch.float64, device=dev)
+        E._cabi.check(lib.ksg_scatter_sum_f64(E._ptr(ptw), E._ptr(perm), n, E._ptr(out2), E._ptr(total2), E._ptr(status.ticket),
+                                              E._ptr(ws), ws.numel(), E._stream()), "ksg_scatter_sum_f64")
+        assert torch.equal(out2, ref)
+        assert float(total2.item()) == got  # the same tree over the same prepared order
+        assert int(status.ticket.item()) == 0
+
+
+def test_public_call_is_the_same_with_and_without_the_fused_tail():
+    from syntropy_b200 import _engine as E
+    from syntropy_b200 import knn, workloads
+
+    data, call = workloads.c2_mi_1m(n=200_000)
+    ptw1, avg1 = knn.mutual_information(call["idxs_x"], call["idxs_y"], call["k"], data)
+    E.config.fused_tail = False
+    try:
+        ptw0, avg0 = knn.mutual_information(call["idxs_x"], call["idxs_y"], call["k"], data)
+    finally:
+        E.config.fused_tail = True
+    assert np.array_equal(ptw1, ptw0)
+    assert abs(avg1 - avg0) <= 1e-13 * abs(avg0)

@@ -742,7 +742,7 @@ def test_speculative_run_recomputes_when_the_filter_flags_queries(windowed):
         status = E.Status(pts.device)
         pw = E.ksg1_device(pts, 4, _xy_masks((0,), (1,)), mi1_program, status=status)
         assert pw.redo is not None
-        full, total = E.finish_device(pw, n, out=status.total)
+        full, total = E.finish_device(pw, n, status=status)
         pw, full, total = E.settle(pw, n, status, full, total)
         torch.cuda.synchronize()
         close(full.cpu().numpy(), np.asarray(ref_ptw).reshape(-1))

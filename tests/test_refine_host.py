@@ -29,7 +29,15 @@ def cut_refine_kernel():
     start = src.index("// Exact refine: see the file header.")
     kernel = src[start:src.index("}  // namespace ksg", start)]
     assert re.search(r"\bknn_refine_kernel\(", kernel) and re.search(r"\brefine_single_list\(", kernel)
-    return args + "\n\n" + band + "\n\n" + seed + "\n\n" + kernel
+    warp = open(os.path.join(ROOT, "syntropy_b200", "csrc", "fast_knn_warp.cuh")).read()
+    c0 = warp.index("constexpr int WU_MAX_KC")
+    consts = warp[c0:warp.index("\n", warp.index("constexpr int WU_BAND_REGS")) + 1]
+    cap0 = warp.index("constexpr int wunits_list_capacity")
+    consts += warp[cap0:warp.index("\n", cap0) + 1]
+    u0 = warp.index("template <int DP, int KC, int KPR>")
+    unsorted = warp[u0:warp.index("\n}\n", u0) + 3]
+    assert "refine_unsorted_list" in unsorted
+    return args + "\n\n" + band + "\n\n" + seed + "\n\n" + kernel + "\n\n" + consts + "\n" + unsorted
 
 
 def test_refine_kernel_logic_on_the_host(tmp_path):
@@ -39,7 +47,7 @@ def test_refine_kernel_logic_on_the_host(tmp_path):
     (tmp_path / "refine_kernel.inc").write_text(cut_refine_kernel())
     shutil.copy(os.path.join(ROOT, "tests", "host_shims", "refine_harness.cpp"), tmp_path / "refine_harness.cpp")
     exe = tmp_path / "refine_harness"
-    proc = subprocess.run([gxx, "-O1", "-std=c++17", "-o", str(exe), "refine_harness.cpp"], cwd=tmp_path,
+    proc = subprocess.run([gxx, "-O1", "-std=c++17", "-DHAVE_UNSORTED", "-o", str(exe), "refine_harness.cpp"], cwd=tmp_path,
                           capture_output=True, text=True)
     assert proc.returncode == 0, proc.stderr[-3000:]
     run = subprocess.run([str(exe), "250"], capture_output=True, text=True, timeout=600)
@@ -52,3 +60,8 @@ def test_refine_kernel_logic_on_the_host(tmp_path):
     # the fused refine of single-unit blocks (refine_single_list) under tight seeds
     assert stats["single_checked"] > 15_000
     assert stats["single_flagged_continuous"] == 0
+    # the unsorted-list refine of the warp-level kernel (refine_unsorted_list): equal to the sorted path and to
+    # brute force whenever it answers; continuous data practically never needs the general path
+    assert stats["unsorted_checked"] > 15_000
+    assert stats["unsorted_fallback_continuous"] <= stats["unsorted_checked"] // 50
+    assert stats["unsorted_fallback_tied"] > 0

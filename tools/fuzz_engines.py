@@ -116,13 +116,19 @@ def main():
             if n >= 200:
                 out.append((np.array([knn.sample_entropy((0,), rows, m=2, r=0.3)]), 0.0))
             api[engine] = out
-        for a, b in zip(api["exact"], api["windowed"]):
+        for which, (a, b) in enumerate(zip(api["exact"], api["windowed"])):
             with np.errstate(all="ignore"):
                 same = np.array_equal(np.asarray(a[0]), np.asarray(b[0]), equal_nan=True)
                 close = np.allclose(np.asarray(a[0]), np.asarray(b[0]), rtol=1e-12, atol=1e-12, equal_nan=True)
             if not (same or close):
                 bad += 1
-                print(f"API MISMATCH case {case}: {kind} dim={dim} n={n} k={k}", flush=True)
+                aa, bb = np.atleast_1d(np.asarray(a[0], dtype=np.float64)), np.atleast_1d(np.asarray(b[0], dtype=np.float64))
+                with np.errstate(all="ignore"):
+                    worst = int(np.nanargmax(np.abs(aa - bb))) if aa.shape == bb.shape and aa.size else -1
+                print(f"API MISMATCH case {case}: {kind} dim={dim} n={n} k={k} output#{which} "
+                      f"n_diff={int((aa != bb).sum()) if aa.shape == bb.shape else -1} worst_at={worst} "
+                      f"exact={aa[worst] if worst >= 0 else None!r} windowed={bb[worst] if worst >= 0 else None!r} "
+                      f"avg_exact={a[1]!r} avg_windowed={b[1]!r}", flush=True)
         print(f"case {case}: {kind} dim={dim} n={n} k={k} subs={len(subs)} ok", flush=True)
     print("FUZZ_OK" if bad == 0 else f"FUZZ_FAILED {bad}")
     sys.exit(1 if bad else 0)

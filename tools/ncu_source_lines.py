@@ -19,17 +19,20 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = None
     per = {}
+    fname = ""
     for row in rows:
+        if row and row[0] == "File Path":
+            fname = row[1].rsplit("/", 1)[-1] if len(row) > 1 else ""
+            continue
         if row and row[0] == "Line No":
-            if hdr is not None:
-                break  # the next function of the report
+            # one section per source file that contributed lines to the kernel (inlined headers)
             hdr = row
             i_inst, i_samp = hdr.index("Instructions Executed"), hdr.index("# Samples")
             stall_cols = [(h, i) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
             continue
         if hdr is None or len(row) < len(hdr) - 2 or not row[0].strip().isdigit():
             continue  # (rows without a line number are the SASS instructions under a CUDA line)
-        key = (row[0].strip(), row[1].strip())
+        key = (fname + ":" + row[0].strip(), row[1].strip())
         ent = per.setdefault(key, [0, 0, {}])
         try:
             ent[0] += int(row[i_inst] or 0)
@@ -49,7 +52,7 @@ def main():
         if pi < min_pct and ps < min_pct:
             continue
         top = ",".join(f"{k[6:]}={v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:3])
-        print(f"{pi:6.1f} {ps:6.1f}  {line:>6}  {top:40s} | {src[:110]}")
+        print(f"{pi:6.1f} {ps:6.1f}  {line:>24}  {top:40s} | {src[:110]}")
 
 
 if __name__ == "__main__":

@@ -48,7 +48,7 @@ def main():
             return knn.mutual_information(call["idxs_x"], call["idxs_y"], k, pinned.numpy())
         status = E.Status(pts.device)
         pw = E.ksg1_device(pts, k, masks, mi1_program, status=status)
-        full, total = E.finish_device(pw, n, out=status.total)
+        full, total = E.finish_device(pw, n, status=status)
         return E.settle(pw, n, status, full, total)
 
     for _ in range(5):
