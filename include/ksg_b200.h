@@ -217,7 +217,11 @@ typedef struct {
     int32_t dim;         /* joint dimensionality D */
     int32_t dim_padded;  /* D rounded up to even: row length of shadow_f32 */
     int32_t primary;     /* coordinate the set is sorted by; -1: Hilbert-curve order of the per-coordinate ranks; -2: kd order */
-    int32_t reserved;
+    int32_t axes_mode;   /* 0: axis_vals / axis_pos are the exact per-coordinate sorts.  b > 0 ("lazy axes", built with
+                            primary == -3): no coordinate was sorted; axis_vals[d] holds coordinate d's values GROUPED
+                            into 2^b value buckets (any order inside a bucket) and axis_pos[d] the buckets' prefix sums
+                            (2^b + 1 entries) -- what ksg_axis_count_buckets reads; ksg_prepare_axes turns the set into
+                            an ordinary one (axes_mode 0) when the sorted arrays are needed after all */
     int64_t ld;          /* row stride (elements) of the [dim][ld] arrays */
     int64_t n_padded;    /* rows of shadow_f32: n rounded up to the tile length, +inf padded */
     int32_t* perm;       /* [n]        sorted position -> original sample index */
@@ -251,7 +255,10 @@ typedef struct {
  * (ksg_prepare_workspace(n, dim) bytes).  primary >= 0: the order of that coordinate;
  * primary == -1: the Hilbert curve over the per-coordinate ranks (spatially compact 512-point
  * tiles and 32-point sub-tiles in every coordinate); primary == -2: the leaf order of a balanced
- * kd-tree over the ranks (conditional medians: the better order from ~7 coordinates up).
+ * kd-tree over the ranks (conditional medians: the better order from ~7 coordinates up);
+ * primary == -3: the curve order with LAZY axes (ksg_prepared::axes_mode): no coordinate is sorted, the values
+ * are grouped into value buckets instead -- enough for ksg_fast_knn* and ksg_axis_count_buckets, i.e. for the
+ * mutual information of scalar series; everything else needs ksg_prepare_axes first.
  * *h_out is filled on the host; the device work is only enqueued (the per-coordinate sorts run
  * concurrently on helper streams of the library, forked from and joined to `stream`).
  * Replaces the cKDTree constructions of the path (syntropy/knn/utils.py:29 and every
@@ -381,6 +388,19 @@ int ksg_axis_count(const ksg_prepared* h_prep, int axis, int64_t q_begin, int64_
 int ksg_axis_count_multi(const ksg_prepared* h_prep, const int32_t* h_axes, int n_axes, int64_t q_begin,
                          int64_t q_end, const double* d_eps, int strict, int32_t bias, int32_t* d_counts,
                          void* stream);
+
+/* The same counts for a prepared set with LAZY axes (ksg_prepare* with primary == -3, axes_mode > 0): no
+ * coordinate is sorted; whole value buckets inside the ball are counted by prefix sums, the buckets its two ends
+ * fall into value by value with the exact float64 predicate (csrc/axis_buckets.cuh has the exactness argument).
+ * *d_n_flagged is incremented when the counts could NOT all be settled this way (tied data fills single buckets
+ * with thousands of equal values): the caller then calls ksg_prepare_axes and ksg_axis_count_multi.  Takes the
+ * two float64 radix sorts per call off the mutual-information path (shannon.py:190-194). */
+int ksg_axis_count_buckets(const ksg_prepared* h_prep, const int32_t* h_axes, int n_axes, int64_t q_begin,
+                           int64_t q_end, const double* d_eps, int strict, int32_t bias, int32_t* d_counts,
+                           int32_t* d_n_flagged, void* stream);
+/* Build the exact per-coordinate sorts of a lazy set after all (in stream order, from the set's own float64
+ * copy); h_prep->axes_mode becomes 0.  No-op for an ordinary set. */
+int ksg_prepare_axes(ksg_prepared* h_prep, void* stream);
 
 /* The tail of an estimator step in ONE launch, for values of ALL n samples in the prepared order:
  *   ksg_psi_finish      v_i = the psi program of ksg_psi_epilogue over d_counts[s * n + i],

@@ -31,7 +31,7 @@ class Prepared(C.Structure):
         ("dim", C.c_int32),
         ("dim_padded", C.c_int32),
         ("primary", C.c_int32),
-        ("reserved", C.c_int32),
+        ("axes_mode", C.c_int32),
         ("ld", C.c_int64),
         ("n_padded", C.c_int64),
         ("perm", C.c_void_p),
@@ -115,6 +115,9 @@ SIGNATURES = {
     "ksg_axis_count": (C.c_int, [_c_prep, C.c_int, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int32, _c_vp, _c_vp]),
     "ksg_axis_count_multi": (C.c_int, [_c_prep, C.POINTER(C.c_int32), C.c_int, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int32,
                                        _c_vp, _c_vp]),
+    "ksg_axis_count_buckets": (C.c_int, [_c_prep, C.POINTER(C.c_int32), C.c_int, _c_i64, _c_i64, _c_vp, C.c_int, C.c_int32,
+                                         _c_vp, _c_vp, _c_vp]),
+    "ksg_prepare_axes": (C.c_int, [_c_prep, _c_vp]),
     "ksg_finish_workspace": (C.c_size_t, [_c_i64]),
     "ksg_psi_finish": (C.c_int, [_c_vp, _c_i64, C.c_int, C.POINTER(PsiStep), C.c_int, C.c_double, C.c_double, C.c_int,
                                  C.c_double, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),

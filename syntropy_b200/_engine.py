@@ -452,6 +452,7 @@ class Config:
     own_order = True          # windowed engine: low-dimensional marginals in their own order
     own_order_max_dim = 4     # ... when they have at most this many coordinates
     fused_tail = True         # single rank: psi program + sample order + sum in one launch (ksg_psi_finish)
+    lazy_axes = True          # speculative 1-D-marginal step: value buckets instead of the coordinate sorts
 
 
 config = Config()
@@ -486,6 +487,13 @@ class PreparedSet:
                                       C.byref(self.c), _stream())
         _cabi.check(rc, "ksg_prepare_rows")
         self.n, self.dim, self.ld = n, dim, int(self.c.ld)
+
+    def ensure_axes(self):
+        """A set prepared with lazy axes (primary = -3: value buckets instead of the per-coordinate sorts)
+        gets its exact sorted coordinates now, in stream order; no-op for an ordinary set."""
+        if int(self.c.axes_mode) != 0:
+            stats["lazy_axes_built"] += 1
+            _cabi.check(_cabi.load().ksg_prepare_axes(C.byref(self.c), _stream()), "ksg_prepare_axes")
 
     def __del__(self):
         # the exact coordinate sorts of an early-order set run on side streams of the library: order
@@ -633,6 +641,7 @@ def fast_counts(prep: PreparedSet, masks, eps: torch.Tensor, q0: int, q1: int, w
     lib = _cabi.load()
     nq = q1 - q0
     dev = prep.buf.device
+    prep.ensure_axes()  # (the count kernels read the exact per-coordinate sorts)
     counts = torch.empty((len(masks), nq), dtype=torch.int32, device=dev)
     multi = [s for s, m in enumerate(masks) if bin(m).count("1") > 1]
     single = [s for s, m in enumerate(masks) if bin(m).count("1") == 1]
@@ -680,7 +689,7 @@ def scatter_to_original(values_sorted: torch.Tensor, prep: PreparedSet) -> torch
 
 
 stats = {"knn_fallback_queries": 0, "count_fallback_queries": 0, "knn_deferred_queries": 0,
-         "knn_wide_margin_passes": 0}
+         "knn_wide_margin_passes": 0, "lazy_axes_built": 0}
 
 
 def _use_fast(dim: int, kprime: int = 1) -> bool:
@@ -722,7 +731,7 @@ class Status:
     def read_async(self) -> np.ndarray:
         """Enqueue the copy to page-locked host memory; valid after the stream is synchronised."""
         host = torch.empty(4, dtype=torch.int32, pin_memory=True)
-        host.copy_(self.buf, non_blocking=True)
+        host.copy_(self.buf[:4], non_blocking=True)
         return host.numpy()
 
 
@@ -943,12 +952,17 @@ def _ksg1_step_ext(pts, k, masks, prog: PsiProgram, n, q0, q1, windowed, row_rea
     table = psi_table(n + 2)
     steps = prog.steps
     ready = [int(ev.cuda_event) for ev in row_ready] if row_ready else []
+    # curve order with lazy axes (-3): the 1-D counts come from value buckets, no coordinate is sorted; the
+    # rare set the buckets cannot settle (tied data) is flagged like an unsettled k-NN query -> redo() below
+    primary = order_for(dim)
+    if primary == -1 and config.lazy_axes:
+        primary = -3
     # one rank owns every query: psi program, sample order and the sum are ONE launch (ksg_psi_finish)
     fused_tail = q0 == 0 and q1 == n and n > 0 and config.fused_tail
     ptw, prep_buf, prep_struct, eps, flags, _counts = ext.ksg1_step(
         pts, k, axes, prog.init, prog.psi_n, prog.scale is not None, 0.0 if prog.scale is None else prog.scale,
         [st[0] for st in steps], [st[1] for st in steps], [st[2] for st in steps], [st[3] for st in steps],
-        [st[4] for st in steps], table, q0, q1, windowed, order_for(dim), default_margin(windowed, k + 1, dim),
+        [st[4] for st in steps], table, q0, q1, windowed, primary, default_margin(windowed, k + 1, dim),
         status.nflag, ready, status.total if fused_tail else None, status.ticket if fused_tail else None)
     prep = PreparedSet.from_raw(prep_buf, prep_struct)
 

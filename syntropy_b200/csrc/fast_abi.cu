@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "exact_f64.cuh"
+#include "axis_buckets.cuh"
 #include "fast_count.cuh"
 #include "fast_knn.cuh"
 #include "fast_launch.h"
@@ -433,7 +434,14 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     KSG_REQUIRE(d_points && d_buffer && h_out, "ksg_prepare: null pointer");
     KSG_REQUIRE(n > 0 && n < (1ll << 31) - 1024 && ld >= n, "ksg_prepare: need 0 < n < 2^31 and ld >= n");
     KSG_REQUIRE(dim >= 1 && dim <= KSG_MAX_DIM, "ksg_prepare: dim out of range");
-    KSG_REQUIRE(primary >= -2 && primary < dim, "ksg_prepare: primary must be -2 (kd order), -1 (curve order) or a coordinate");
+    KSG_REQUIRE(primary >= -3 && primary < dim,
+                "ksg_prepare: primary must be -3 (curve order, lazy axes), -2 (kd order), -1 (curve order) or a coordinate");
+    // primary == -3: curve order with LAZY axes -- instead of the exact coordinate sorts the values of every
+    // coordinate are grouped into value buckets (axis_buckets.cuh), which is all ksg_axis_count_buckets needs;
+    // ksg_prepare_axes builds the sorted arrays later if somebody does need them.  Needs the early order
+    // (else the set is an ordinary primary == -1 one: check axes_mode).
+    bool lazy = primary == -3;
+    if (lazy) primary = -1;
     const PreparedLayout L = prepared_layout(n, dim);
     if (buffer_bytes < L.total) {
         set_error("ksg_prepare: buffer of %zu bytes needed, %zu given", L.total, buffer_bytes);
@@ -470,6 +478,9 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     if (primary == -1) P.curve_keys = (uint64_t*)(base + L.off_mkeys_out);
     SortLanes* lanes = sort_lanes_for_device();
 
+    if (!(primary == -1 && early_order() && lanes)) lazy = false;
+    const int bbits = bucket_bits(n);
+    const int n_buckets = 1 << bbits;
     if (primary == -1 && early_order() && lanes) {
         // ================= early order: the curve from approximate ranks on `st`, the exact coordinate
         // sorts (+ their remap into the prepared order) on the side streams, joined by P.axes_ready
@@ -493,13 +504,28 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
             curve_table_kernel<<<dim, 512, 0, st>>>(d_points, ld, n, stats, P.curve_table, P.center, P.maxabs);
             KSG_LAUNCHED2();
             const size_t tsmem = (size_t)dim * CURVE_TABLE * sizeof(float);
+            // lazy axes: per coordinate d, axis_pos row d = [start: n_buckets + 1 | cursor: n_buckets] (2^bbits < n / 8),
+            // the bucket ids live in the (otherwise unused) rank rows, the grouped values in axis_vals
+            int32_t* bstart = P.axis_pos;
+            int32_t* bcursor = lazy ? P.axis_pos + (n_buckets + 1) : nullptr;
+            uint32_t* bucket_id = lazy ? (uint32_t*)(base + L.off_ranks) : nullptr;
+            if (lazy)
+                for (int d = 0; d < dim; ++d)
+                    KSG_CUDA_TRY(cudaMemsetAsync(bcursor + (int64_t)d * L.ld, 0, (size_t)n_buckets * 4, st));
             switch (dim) {
-#define KSG_CKEY(D) case D: curve_key_kernel<D><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, nullptr); break;
+#define KSG_CKEY(D) case D: curve_key_kernel<D><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, nullptr, bbits, bcursor, L.ld, bucket_id, L.ld); break;
                 KSG_CKEY(1) KSG_CKEY(2) KSG_CKEY(3) KSG_CKEY(4) KSG_CKEY(5) KSG_CKEY(6) KSG_CKEY(7) KSG_CKEY(8)
 #undef KSG_CKEY
-                default: curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, nullptr);
+                default: curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, nullptr, bbits, bcursor, L.ld, bucket_id, L.ld);
             }
             KSG_LAUNCHED2();
+            if (lazy) {
+                bucket_scan_kernel<<<dim, 1024, 0, st>>>(bcursor, L.ld, bstart, L.ld, n_buckets, P.flags + 10);
+                KSG_LAUNCHED2();
+                bucket_scatter_kernel<<<dim3(nb, dim), 256, 0, st>>>(d_points, ld, n, bucket_id, L.ld, bcursor, L.ld,
+                                                                      P.axis_vals, L.ld);
+                KSG_LAUNCHED2();
+            }
             if (use_sample_sort(n)) {
                 const int rc2 = sample_sort_launch<unsigned long long>(cub_tmp, mkeys, mkeys_out, P.perm, n, st);
                 if (rc2) return rc2;
@@ -530,8 +556,15 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
             KSG_LAUNCHED2();
             return KSG_OK;
         };
-        rc = graph_cache().run(graph_key(GRAPH_PREPARE_EARLY, {d_points, d_buffer}, {n, ld}, {dim, primary}), st, early);
+        rc = graph_cache().run(graph_key(GRAPH_PREPARE_EARLY, {d_points, d_buffer}, {n, ld},
+                                         {dim, primary, fused_gather() ? 1 : 0, lazy ? 1 : 0}), st, early);
         if (rc) return rc;
+        if (lazy) {  // no coordinate sorts at all (ksg_prepare_axes builds them on demand)
+            P.axes_mode = bbits;
+            P.axes_ready = nullptr;
+            *h_out = P;
+            return KSG_OK;
+        }
         KSG_CUDA_TRY(cudaEventRecord(lanes->perm_ready, st));
         // The exact coordinate sorts start HERE, behind the curve path: three radix sorts side by side
         // slow each other down (every pass is latency bound and they share the SMs: measured, the curve
@@ -680,7 +713,7 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
         KSG_LAUNCHED2();
         return KSG_OK;
     };
-    rc = graph_cache().run(graph_key(GRAPH_PREPARE_TAIL, {d_points, d_buffer}, {n, ld}, {dim, primary}), st, tail);
+    rc = graph_cache().run(graph_key(GRAPH_PREPARE_TAIL, {d_points, d_buffer}, {n, ld}, {dim, primary, fused_gather() ? 1 : 0}), st, tail);
     if (rc) return rc;
     *h_out = P;
     return KSG_OK;
@@ -846,7 +879,7 @@ int ksg_cross_prepare(const ksg_prepared* P, const double* d_queries, int64_t ld
         // the candidates' curve was built from their coordinate table: place the queries with the same map
         const size_t tsmem = (size_t)dim * CURVE_TABLE * sizeof(float);
         if (tsmem > 48 * 1024) KSG_CUDA_TRY(cudaFuncSetAttribute(curve_key_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-        curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_queries, ldq, nq, dim, P->curve_table, P->center, bits, keys, iota);
+        curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_queries, ldq, nq, dim, P->curve_table, P->center, bits, keys, iota, 0, nullptr, 0, nullptr, 0);
     } else
     switch (dim) {
 #define KSG_CROSS(D) case D: cross_key_kernel<D><<<nb, 256, 0, st>>>(d_queries, ldq, nq, P->axis_vals, P->ld, P->n, dim, rank_bits, bits, keys, iota); break;
@@ -970,6 +1003,7 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
                 "ksg_fast_count: null pointer");
     KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_fast_count: bad query range");
     KSG_REQUIRE(n_subspaces >= 1 && n_subspaces <= KSG_MAX_SUBSPACES, "ksg_fast_count: subspace count");
+    KSG_REQUIRE(P->axes_mode == 0, "ksg_fast_count: the set has lazy axes (call ksg_prepare_axes first)");
     if (P->dim_padded > 8) {
         set_error("ksg_fast_count: the fp32 filter is instantiated for up to 8 dimensions (got %d)", P->dim);
         return KSG_EUNSUPPORTED;
@@ -1071,6 +1105,7 @@ int ksg_axis_count(const ksg_prepared* P, int axis, int64_t q_begin, int64_t q_e
                    int32_t bias, int32_t* d_counts, void* stream) {
     KSG_REQUIRE(P && d_eps && d_counts, "ksg_axis_count: null pointer");
     KSG_REQUIRE(axis >= 0 && axis < P->dim, "ksg_axis_count: axis out of range");
+    KSG_REQUIRE(P->axes_mode == 0, "ksg_axis_count: the set has lazy axes (ksg_axis_count_buckets, or ksg_prepare_axes first)");
     KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_axis_count: bad query range");
     const int64_t nq = q_end - q_begin;
     if (nq == 0) return KSG_OK;
@@ -1099,6 +1134,7 @@ int ksg_axis_count_multi(const ksg_prepared* P, const int32_t* h_axes, int n_axe
                          const double* d_eps, int strict, int32_t bias, int32_t* d_counts, void* stream) {
     KSG_REQUIRE(P && h_axes && d_eps && d_counts, "ksg_axis_count_multi: null pointer");
     KSG_REQUIRE(n_axes >= 1 && n_axes <= KSG_MAX_DIM, "ksg_axis_count_multi: 1 <= n_axes <= KSG_MAX_DIM");
+    KSG_REQUIRE(P->axes_mode == 0, "ksg_axis_count_multi: the set has lazy axes (ksg_axis_count_buckets, or ksg_prepare_axes first)");
     KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_axis_count_multi: bad query range");
     AxisList axes;
     for (int a = 0; a < n_axes; ++a) {
@@ -1112,6 +1148,48 @@ int ksg_axis_count_multi(const ksg_prepared* P, const int32_t* h_axes, int n_axe
     axis_count_sorted_multi_kernel<<<dim3((unsigned)ceil_div(P->n, 256), (unsigned)n_axes), 256, 0, as_stream2(stream)>>>(
         P->axis_vals, P->axis_pos, P->ld, axes, P->n, q_begin, nq, d_eps, strict ? 1 : 0, bias, d_counts);
     KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+int ksg_axis_count_buckets(const ksg_prepared* P, const int32_t* h_axes, int n_axes, int64_t q_begin, int64_t q_end,
+                           const double* d_eps, int strict, int32_t bias, int32_t* d_counts, int32_t* d_n_flagged,
+                           void* stream) {
+    KSG_REQUIRE(P && h_axes && d_eps && d_counts && d_n_flagged, "ksg_axis_count_buckets: null pointer");
+    KSG_REQUIRE(n_axes >= 1 && n_axes <= KSG_MAX_DIM, "ksg_axis_count_buckets: 1 <= n_axes <= KSG_MAX_DIM");
+    KSG_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= P->n, "ksg_axis_count_buckets: bad query range");
+    KSG_REQUIRE(P->axes_mode > 0 && P->axes_mode <= BUCKET_MAX_BITS && P->curve_table,
+                "ksg_axis_count_buckets: the set has no value buckets (prepare it with primary = -3)");
+    AxisList axes;
+    for (int a = 0; a < n_axes; ++a) {
+        KSG_REQUIRE(h_axes[a] >= 0 && h_axes[a] < P->dim, "ksg_axis_count_buckets: axis out of range");
+        axes.axis[a] = h_axes[a];
+    }
+    const int64_t nq = q_end - q_begin;
+    if (nq == 0) return KSG_OK;
+    axis_count_bucket_kernel<<<dim3((unsigned)ceil_div(nq, 256), (unsigned)n_axes), 256, 0, as_stream2(stream)>>>(
+        P->sorted_f64, P->ld, P->axis_vals, P->ld, P->axis_pos, P->ld, P->curve_table, P->center, P->axes_mode, axes,
+        q_begin, nq, d_eps, strict ? 1 : 0, bias, d_counts, P->flags + 10, d_n_flagged);
+    KSG_LAUNCHED2();
+    return KSG_OK;
+}
+
+int ksg_prepare_axes(ksg_prepared* P, void* stream) {
+    KSG_REQUIRE(P, "ksg_prepare_axes: null pointer");
+    if (P->axes_mode == 0) return KSG_OK;  // already exact
+    // sorted from the set's own float64 copy: keys = coordinate d in the prepared order, payload = the
+    // prepared position itself, so axis_pos needs no remap (ties come out in prepared order)
+    const PreparedLayout L = prepared_layout(P->n, P->dim);
+    char* base = (char*)P->perm - L.off_perm;
+    const int32_t* iota = (const int32_t*)(base + L.off_iota);
+    void* cub_tmp = base + L.off_cub;
+    cudaStream_t st = as_stream2(stream);
+    for (int d = 0; d < P->dim; ++d) {
+        const int rc = sort_pairs(cub_tmp, L.cub_bytes, P->sorted_f64 + (int64_t)d * P->ld, P->axis_vals + (int64_t)d * P->ld,
+                                  iota, P->axis_pos + (int64_t)d * P->ld, P->n, st);
+        if (rc) return rc;
+    }
+    P->axes_mode = 0;
+    P->axes_ready = nullptr;
     return KSG_OK;
 }
 

@@ -567,7 +567,7 @@ struct AxisList {
 };
 static __global__ void __launch_bounds__(256)
 axis_count_sorted_multi_kernel(const double* __restrict__ axis_vals, const int32_t* __restrict__ axis_pos, int64_t ld,
-                               const AxisList axes, int64_t n, int64_t q_begin, int64_t nq,
+                               const __grid_constant__ AxisList axes, int64_t n, int64_t q_begin, int64_t nq,
                                const double* __restrict__ eps, int strict, int32_t bias, int32_t* __restrict__ counts) {
     const int64_t a = axes.axis[blockIdx.y];
     axis_count_sorted_one(axis_vals + a * ld, axis_pos + a * ld, n, q_begin, nq, eps, strict, bias,

@@ -123,7 +123,8 @@ static int launch_wunits_kc(const KnnF32Args& a) {
 
 template <int DP>
 static int launch_wunits_dp(const KnnF32Args& a) {
-    switch (wunits_list_capacity(a.kcap)) {
+    static const int roomy = [] { const char* e = getenv("KSG_B200_WU_ROOMY"); return e ? atoi(e) : 0; }();
+    switch (wunits_list_capacity(a.kcap + (roomy > 0 && a.kcap <= 16 ? 4 : 0))) {
         case 8: return launch_wunits_kc<DP, 8>(a);
         case 12: return launch_wunits_kc<DP, 12>(a);
         case 16: return launch_wunits_kc<DP, 16>(a);

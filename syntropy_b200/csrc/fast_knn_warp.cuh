@@ -36,6 +36,8 @@ constexpr int wunits_min_blocks(int dp) { return dp <= 2 ? 10 : 8; }
 __host__ __device__ inline size_t wunits_smem_per_warp(int kc, int dp) {
     return (size_t)kc * 32 * 8 + (size_t)WU_QUEUE * 8 + (size_t)32 * dp * 4;
 }
+// (env KSG_B200_WU_ROOMY=1, read by the launcher: the next capacity up -- fewer full lists, i.e. fewer
+//  replace-the-maximum sweeps, for 1 KB more shared memory per warp)
 constexpr int wunits_list_capacity(int kcap) { return kcap <= 8 ? 8 : kcap <= 12 ? 12 : kcap <= 16 ? 16 : WU_MAX_KC; }
 
 // The refine of ONE list that still sits UNSORTED in shared memory (entries [0, nfill) of the lane's

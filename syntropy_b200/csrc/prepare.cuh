@@ -484,14 +484,17 @@ curve_table_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, const 
     }
 }
 
-// curve coordinate of the centred value x in [0, 2^bits): monotone in x (tb: CURVE_TABLE ascending values)
-__device__ __forceinline__ unsigned int curve_coord(float x, const float* __restrict__ tb, int bits) {
+// position of the centred value x among the CURVE_TABLE ascending table values, in [0, CURVE_TABLE - 1]:
+// the number of entries <= x, refined by linear interpolation inside the gap.  Monotone (non-decreasing) in x:
+// the entry count is, and inside a gap x - a, the product with the approximate reciprocal of b - a, the
+// clamps and the final sum are all monotone in x under round-to-nearest.
+__device__ __forceinline__ float curve_pos(float x, const float* __restrict__ tb) {
     int lo = 0, hi = CURVE_TABLE;  // number of table entries <= x
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (tb[mid] <= x) lo = mid + 1; else hi = mid;
     }
-    float pos = 0.0f;  // in [0, CURVE_TABLE - 1]
+    float pos = 0.0f;
     if (lo >= CURVE_TABLE) {
         pos = (float)(CURVE_TABLE - 1);
     } else if (lo > 0) {
@@ -501,10 +504,29 @@ __device__ __forceinline__ unsigned int curve_coord(float x, const float* __rest
         if (f > 1.0f) f = 1.0f;
         pos = (float)(lo - 1) + f;
     }
+    return pos;
+}
+// ... scaled to an integer in [0, 2^bits) (monotone in pos)
+__device__ __forceinline__ unsigned int curve_scale(float pos, int bits) {
     const float scaled = pos * ((float)(1u << bits) / (float)(CURVE_TABLE - 1));
     unsigned int c = (unsigned int)scaled;
     const unsigned int top = (1u << bits) - 1u;
     return c > top ? top : c;
+}
+// curve coordinate of the centred value x in [0, 2^bits): monotone in x (tb: CURVE_TABLE ascending values)
+__device__ __forceinline__ unsigned int curve_coord(float x, const float* __restrict__ tb, int bits) {
+    return curve_scale(curve_pos(x, tb), bits);
+}
+
+// ---- value buckets for the exact 1-D counts (axes_mode > 0, "lazy axes"; see axis_buckets.cuh).
+// bucket of a value = its curve position at `bbits` bits (~16 points per bucket for rank-uniform data).
+constexpr int BUCKET_MAX_BITS = 20;
+constexpr int BUCKET_HEAVY = 512;  // a fuller bucket makes the set "heavy": the bucketed counts give up (flag)
+static inline int bucket_bits(int64_t n) {
+    int rb = 1;
+    while ((1ll << rb) < n) ++rb;
+    int b = rb > 5 ? rb - 4 : 1;
+    return b > BUCKET_MAX_BITS ? BUCKET_MAX_BITS : b;
 }
 
 // keys[i] = Hilbert index of point i's curve coordinates.  Dynamic shared memory: dim * CURVE_TABLE floats.
@@ -512,7 +534,10 @@ template <int DIM>
 static __global__ void __launch_bounds__(256)
 curve_key_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, int dim_rt, const float* __restrict__ table,
                  const double* __restrict__ center, int bits, unsigned long long* __restrict__ keys,
-                 int32_t* __restrict__ iota) {
+                 int32_t* __restrict__ iota, int bbits, int32_t* __restrict__ bucket_hist, int64_t ldh,
+                 uint32_t* __restrict__ bucket_id, int64_t ldb) {
+    // bucket_hist / bucket_id (optional, lazy axes): bucket_id[d * ldb + i] = the value bucket of coordinate d of
+    // point i (its curve position at bbits bits), counted into bucket_hist[d * ldh + bucket]
     extern __shared__ float s_table[];
     const int dim = DIM > 0 ? DIM : dim_rt;
     for (int i = threadIdx.x; i < dim * CURVE_TABLE; i += 256) s_table[i] = table[i];
@@ -522,10 +547,63 @@ curve_key_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, int dim_
     unsigned int X[DIM > 0 ? DIM : KSG_MAX_DIM];
 #pragma unroll
     for (int d = 0; d < (DIM > 0 ? DIM : KSG_MAX_DIM); ++d)
-        if (d < dim)
-            X[d] = curve_coord(__double2float_rn(pts[(int64_t)d * ld + i] - center[d]), s_table + d * CURVE_TABLE, bits);
+        if (d < dim) {
+            const float pos = curve_pos(__double2float_rn(pts[(int64_t)d * ld + i] - center[d]), s_table + d * CURVE_TABLE);
+            X[d] = curve_scale(pos, bits);
+            if (bucket_hist) {
+                const unsigned int b = curve_scale(pos, bbits);
+                bucket_id[(int64_t)d * ldb + i] = b;
+                atomicAdd(&bucket_hist[(int64_t)d * ldh + b], 1);
+            }
+        }
     keys[i] = hilbert_index(X, dim, bits);
     if (iota) iota[i] = (int32_t)i;
+}
+
+// grid = dim CTAs of 1024 threads.  hist[d][0..B) -> start[d][0..B] (exclusive prefix sums, start[B] = n) and
+// cursor[d][b] = start[d][b] (the scatter's bump cursors, in place of the histogram);  heavy[0] |= 1 when a
+// bucket holds more than BUCKET_HEAVY values (tied data: the bucketed counts would scan too much).
+static __global__ void __launch_bounds__(1024)
+bucket_scan_kernel(int32_t* __restrict__ hist_cursor, int64_t ldh, int32_t* __restrict__ start, int64_t lds, int B,
+                   int32_t* __restrict__ heavy) {
+    __shared__ int s_part[1024];
+    int32_t* h = hist_cursor + (int64_t)blockIdx.x * ldh;
+    int32_t* st = start + (int64_t)blockIdx.x * lds;
+    const int tid = threadIdx.x;
+    const int per = (B + 1023) / 1024;
+    const int b0 = min(tid * per, B), b1 = min(b0 + per, B);
+    int sum = 0, mx = 0;
+    for (int b = b0; b < b1; ++b) { const int c = h[b]; sum += c; mx = max(mx, c); }
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // inclusive scan
+        const int v = tid >= off ? s_part[tid - off] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - sum;
+    for (int b = b0; b < b1; ++b) {
+        const int c = h[b];
+        st[b] = run;
+        h[b] = run;
+        run += c;
+    }
+    if (tid == 1023) st[B] = s_part[1023];
+    if (__syncthreads_or(mx > BUCKET_HEAVY) && tid == 0) atomicOr(heavy, 1);
+}
+
+// vals[d][cursor[d][bucket]++] = pts[d][i]: the values of every coordinate grouped by bucket (any order inside
+// a bucket: the counts do not depend on it).  grid = (blocks, dim).
+static __global__ void __launch_bounds__(256)
+bucket_scatter_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, const uint32_t* __restrict__ bucket_id,
+                      int64_t ldb, int32_t* __restrict__ cursor, int64_t ldh, double* __restrict__ vals, int64_t ldv) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int d = blockIdx.y;
+    const unsigned int b = bucket_id[(int64_t)d * ldb + i];
+    const int pos = atomicAdd(&cursor[(int64_t)d * ldh + b], 1);
+    vals[(int64_t)d * ldv + pos] = pts[(int64_t)d * ld_in + i];
 }
 
 // bits per coordinate of the curve for n points in `dim` coordinates (shared by ksg_prepare and

@@ -137,13 +137,19 @@ std::vector<at::Tensor> ksg1_step(at::Tensor pts, int64_t k, std::vector<int64_t
                                       ws_bytes, st),
                   "ksg_fast_knn_margin");
         }
-        // ---- the exact 1-D counts of all marginals, one launch
+        // ---- the exact 1-D counts of all marginals, one launch (lazy axes: from the value buckets; what they
+        //      cannot settle is counted into nflag like the k-NN stage's unsettled queries)
         {
             std::vector<int32_t> ax(axes.begin(), axes.end());
             Scope s("axis_count", st);
-            check(ksg_axis_count_multi(&P, ax.data(), (int)ax.size(), q0, q1, eps.data_ptr<double>(), 1, -1,
-                                       counts.data_ptr<int32_t>(), st),
-                  "ksg_axis_count_multi");
+            if (P.axes_mode > 0)
+                check(ksg_axis_count_buckets(&P, ax.data(), (int)ax.size(), q0, q1, eps.data_ptr<double>(), 1, -1,
+                                             counts.data_ptr<int32_t>(), nflag.data_ptr<int32_t>(), st),
+                      "ksg_axis_count_buckets");
+            else
+                check(ksg_axis_count_multi(&P, ax.data(), (int)ax.size(), q0, q1, eps.data_ptr<double>(), 1, -1,
+                                           counts.data_ptr<int32_t>(), st),
+                      "ksg_axis_count_multi");
         }
         // ---- psi program
         std::vector<ksg_psi_step> steps(step_sub.size() ? step_sub.size() : 1);

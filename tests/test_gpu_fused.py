@@ -173,7 +173,7 @@ def test_fused_tail_equals_epilogue_scatter_sum():
     rng = np.random.default_rng(6)
     for n in (1, 37, 1000, 300_001):
         dev = torch.device("cuda")
-        counts = torch.from_numpy(rng.integers(0, max(n - 1, 1), size=(3, n)).astype(np.int32)).to(dev)
+        counts = torch.from_numpy(rng.integers(1, max(n, 2), size=(3, n)).astype(np.int32)).to(dev)  # (psi(0) = -inf)
         perm = torch.from_numpy(rng.permutation(n).astype(np.int32)).to(dev)
         prog = E.PsiProgram(init=0.25, psi_n=E.psi_host(n), scale=0.5)
         prog.add(0, -1)
@@ -218,3 +218,87 @@ def test_public_call_is_the_same_with_and_without_the_fused_tail():
         E.config.fused_tail = True
     assert np.array_equal(ptw1, ptw0)
     assert abs(avg1 - avg0) <= 1e-13 * abs(avg0)
+
+
+def test_bucketed_axis_counts_equal_the_sorted_ones():
+    """ksg_axis_count_buckets on a set with lazy axes (primary = -3) == ksg_axis_count_multi on the ordinary
+    set; tied data raises the flag instead; ksg_prepare_axes then turns the lazy set into an ordinary one."""
+    import torch
+
+    from syntropy_b200 import _engine as E
+
+    lib = E._cabi.load()
+    rng = np.random.default_rng(31)
+    cases = [("normal", rng.standard_normal((2, 200_000)), False),
+             ("3d offset", rng.standard_normal((3, 50_000)) * 1e-6 + 1e3, False),
+             ("heavy", rng.standard_t(1.2, size=(2, 60_000)), False),
+             ("tiny", rng.standard_normal((2, 41)), False),
+             ("1d", rng.standard_normal((1, 9_000)), False),
+             ("decimal grid", np.round(rng.standard_normal((2, 100_000)), 2), None),   # few hundred values per level: may go either way
+             ("quantised", np.round(rng.standard_normal((2, 300_000)) * 8) / 8, True)]
+    for name, rows, expect_flag in cases:
+        pts = E.to_device_points(rows)
+        dim, n = rows.shape
+        ref = E.PreparedSet(pts, -1)
+        lazy = E.PreparedSet(pts, -3)
+        assert int(lazy.c.axes_mode) > 0 and int(ref.c.axes_mode) == 0, name
+        assert torch.equal(lazy.perm, ref.perm), name   # the same curve order
+        k = 4
+        eps = E.fast_knn(ref, k + 1, 0, n, True)
+        eps_lazy = E.fast_knn(lazy, k + 1, 0, n, True)   # (the k-NN stage never needs the axes)
+        assert torch.equal(eps, eps_lazy), name
+        eps[::17] = float("inf")
+        eps[5::23] = 0.0
+        axes = (C.c_int32 * dim)(*range(dim))
+        for q0, q1 in ((0, n), (n // 3 + 1, n // 2 + 7)):
+            nq = q1 - q0
+            e = eps[q0:q1].contiguous()
+            want = torch.empty((dim, nq), dtype=torch.int32, device=pts.device)
+            E._cabi.check(lib.ksg_axis_count_multi(C.byref(ref.c), axes, dim, q0, q1, E._ptr(e), 1, -1, E._ptr(want), E._stream()),
+                          "ksg_axis_count_multi")
+            for strict in (1, 0):
+                if not strict:
+                    E._cabi.check(lib.ksg_axis_count_multi(C.byref(ref.c), axes, dim, q0, q1, E._ptr(e), 0, 0, E._ptr(want),
+                                                           E._stream()), "ksg_axis_count_multi")
+                got = torch.full((dim, nq), -9, dtype=torch.int32, device=pts.device)
+                nflag = torch.zeros(1, dtype=torch.int32, device=pts.device)
+                E._cabi.check(lib.ksg_axis_count_buckets(C.byref(lazy.c), axes, dim, q0, q1, E._ptr(e), strict, -1 if strict else 0,
+                                                         E._ptr(got), E._ptr(nflag), E._stream()), "ksg_axis_count_buckets")
+                flagged = int(nflag.item()) != 0
+                if expect_flag is not None:
+                    assert flagged == expect_flag, (name, int(nflag.item()))
+                if not flagged:
+                    assert torch.equal(got, want), (name, q0, strict, int((got != want).sum().item()))
+        # exact entry points refuse a lazy set ...
+        one = torch.empty(n, dtype=torch.int32, device=pts.device)
+        assert lib.ksg_axis_count(C.byref(lazy.c), 0, 0, n, E._ptr(eps), 1, -1, E._ptr(one), E._stream()) != 0
+        # ... until its axes are built: then it counts like the ordinary set
+        lazy.ensure_axes()
+        assert int(lazy.c.axes_mode) == 0
+        got = E.fast_counts(lazy, [1 << d for d in range(dim)], eps, 0, n, True)
+        want = E.fast_counts(ref, [1 << d for d in range(dim)], eps, 0, n, True)
+        assert torch.equal(got, want), name
+
+
+def test_public_mi_with_and_without_lazy_axes():
+    from syntropy_b200 import _engine as E
+    from syntropy_b200 import knn, workloads
+
+    rng = np.random.default_rng(3)
+    sets = [workloads.c2_mi_1m(n=150_000)[0], np.round(rng.standard_normal((2, 120_000)) * 8) / 8,
+            rng.integers(0, 9, size=(2, 3_000)).astype(np.float64)]
+    built = []
+    for data in sets:
+        for key in E.stats:
+            E.stats[key] = 0
+        ptw1, avg1 = knn.mutual_information((0,), (1,), 4, data)
+        built.append(E.stats["lazy_axes_built"])
+        E.config.lazy_axes = False
+        try:
+            ptw0, avg0 = knn.mutual_information((0,), (1,), 4, data)
+        finally:
+            E.config.lazy_axes = True
+        assert np.array_equal(ptw1, ptw0, equal_nan=True)
+        assert avg1 == avg0 or abs(avg1 - avg0) <= 1e-13 * abs(avg0) or (np.isnan(avg1) and np.isnan(avg0)) or avg1 == avg0
+    assert built[0] == 0    # continuous data: settled from the value buckets, no coordinate was ever sorted
+    assert built[1] >= 1    # tied data went through the give-up path (flag -> ksg_prepare_axes -> sorted counts)
