@@ -50,20 +50,32 @@ axis_count_bucket_kernel(const double* __restrict__ sorted, int64_t ld, const do
     const int32_t* __restrict__ st = bstart + (int64_t)a * lds;
     // (1 +- 8u: four times the margin the argument needs)
     const double e_hi = __dmul_ru(e, 1.0 + 8.8817841970012523e-16), e_lo = __dmul_rd(e, 1.0 - 8.8817841970012523e-16);
-    auto bucket_of = [&](double t) -> int {
-        return (int)curve_scale(curve_pos(__double2float_rn(t - c), s_tb), bbits);
+    // the two values of an end (A, A' or B', B) almost always fall into the same gap of the table: one search
+    auto buckets_of = [&](double t1, double t2, int& b1, int& b2) {
+        const float f1 = __double2float_rn(t1 - c), f2 = __double2float_rn(t2 - c);
+        const int g1 = curve_gap(f1, s_tb);
+        b1 = (int)curve_scale(curve_pos_in_gap(f1, g1, s_tb), bbits);
+        const bool same = (g1 == 0 || s_tb[g1 - 1] <= f2) && (g1 >= CURVE_TABLE || !(s_tb[g1] <= f2));
+        b2 = (int)curve_scale(curve_pos_in_gap(f2, same ? g1 : curve_gap(f2, s_tb), s_tb), bbits);
     };
-    const int lo1 = bucket_of(__dsub_rd(x, e_hi)), lo2 = bucket_of(__dsub_ru(x, e_lo));
-    const int hi1 = bucket_of(__dadd_rd(x, e_lo)), hi2 = bucket_of(__dadd_ru(x, e_hi));
+    int lo1, lo2, hi1, hi2;
+    buckets_of(__dsub_rd(x, e_hi), __dsub_ru(x, e_lo), lo1, lo2);
+    buckets_of(__dadd_rd(x, e_lo), __dadd_ru(x, e_hi), hi1, hi2);
     int cnt = 0;
     bool too_long = false;
+    auto inside = [&](double vj) -> int {
+        const double d = fabs(x - vj);
+        return (strict ? d < e : d <= e) ? 1 : 0;
+    };
     auto scan = [&](int b0, int b1) {  // every value of the buckets [b0, b1], exact predicate
         const int s = st[b0], t = st[b1 + 1];
         if (t - s > BUCKET_SCAN_CAP) { too_long = true; return; }
-        for (int j = s; j < t; ++j) {
-            const double d = fabs(x - v[j]);
-            cnt += (strict ? d < e : d <= e) ? 1 : 0;
+        int j = s;
+        for (; j + 4 <= t; j += 4) {  // (independent loads first: the loop is latency-bound otherwise)
+            const double v0 = v[j], v1 = v[j + 1], v2 = v[j + 2], v3 = v[j + 3];
+            cnt += inside(v0) + inside(v1) + inside(v2) + inside(v3);
         }
+        for (; j < t; ++j) cnt += inside(v[j]);
     };
     if (lo2 < hi1) {
         scan(lo1, lo2);

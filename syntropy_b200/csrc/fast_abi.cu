@@ -481,6 +481,8 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     if (!(primary == -1 && early_order() && lanes)) lazy = false;
     const int bbits = bucket_bits(n);
     const int n_buckets = 1 << bbits;
+    // (the chunk sums of the bucket scan borrow the stats area: KSG_MAX_DIM * STATS_BLOCKS * 2 doubles)
+    if ((int64_t)dim * ceil_div(n_buckets, BUCKET_CHUNK) * 4 > (int64_t)KSG_MAX_DIM * STATS_BLOCKS * 2 * 8) lazy = false;
     if (primary == -1 && early_order() && lanes) {
         // ================= early order: the curve from approximate ranks on `st`, the exact coordinate
         // sorts (+ their remap into the prepared order) on the side streams, joined by P.axes_ready
@@ -520,10 +522,16 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
             }
             KSG_LAUNCHED2();
             if (lazy) {
-                bucket_scan_kernel<<<dim, 1024, 0, st>>>(bcursor, L.ld, bstart, L.ld, n_buckets, P.flags + 10);
+                const unsigned chunks = (unsigned)ceil_div(n_buckets, BUCKET_CHUNK);
+                int32_t* chunk_sum = (int32_t*)stats;  // (the min / max partials are spent: curve_table_kernel has run)
+                bucket_sum_kernel<<<dim3(chunks, dim), BUCKET_CHUNK, 0, st>>>(bcursor, L.ld, n_buckets, chunk_sum, chunks,
+                                                                               P.flags + 10);
                 KSG_LAUNCHED2();
-                bucket_scatter_kernel<<<dim3(nb, dim), 256, 0, st>>>(d_points, ld, n, bucket_id, L.ld, bcursor, L.ld,
-                                                                      P.axis_vals, L.ld);
+                bucket_scan_kernel<<<dim3(chunks, dim), BUCKET_CHUNK, 0, st>>>(bcursor, L.ld, bstart, L.ld, n_buckets,
+                                                                                chunk_sum, chunks);
+                KSG_LAUNCHED2();
+                bucket_scatter_kernel<<<dim3((unsigned)ceil_div(n, 256 * BUCKET_SCATTER_PER_THREAD), dim), 256, 0, st>>>(
+                    d_points, ld, n, bucket_id, L.ld, bcursor, L.ld, P.axis_vals, L.ld);
                 KSG_LAUNCHED2();
             }
             if (use_sample_sort(n)) {

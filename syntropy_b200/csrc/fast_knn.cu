@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include "fast_knn.cuh"
+#include "fast_knn_group.cuh"
 #include "fast_knn_warp.cuh"
 
 namespace ksg {
@@ -138,7 +139,12 @@ static int launch_units_dp(const KnnF32Args& a) {
         if (warp_units_enabled() && a.kcap <= WU_MAX_KC) return launch_wunits_dp<DP>(a);
     }
     constexpr int Q = UnitsQ<DP>::Q, ST = FastGeom<DP>::STAGES;
+    // many dimensions: 8-query groups inside the filter warps (fast_knn_group.cuh); KSG_B200_GROUPS=0: whole warps
+    static const bool grouped = [] { const char* e = getenv("KSG_B200_GROUPS"); return !(e && e[0] == '0'); }();
     auto kern = knn_units_kernel<DP, Q, ST, (DP <= 4)>;
+    if constexpr (DP >= 6 && UNITS_Q == 1) {
+        if (grouped) kern = knn_gunits_kernel<DP, ST>;
+    }
     const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float) +
                         (size_t)a.kcap * FAST_THREADS * Q * 8;
     if (smem > 32 * 1024) {

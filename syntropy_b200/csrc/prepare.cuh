@@ -488,12 +488,15 @@ curve_table_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, const 
 // the number of entries <= x, refined by linear interpolation inside the gap.  Monotone (non-decreasing) in x:
 // the entry count is, and inside a gap x - a, the product with the approximate reciprocal of b - a, the
 // clamps and the final sum are all monotone in x under round-to-nearest.
-__device__ __forceinline__ float curve_pos(float x, const float* __restrict__ tb) {
-    int lo = 0, hi = CURVE_TABLE;  // number of table entries <= x
+__device__ __forceinline__ int curve_gap(float x, const float* __restrict__ tb) {  // number of table entries <= x
+    int lo = 0, hi = CURVE_TABLE;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (tb[mid] <= x) lo = mid + 1; else hi = mid;
     }
+    return lo;
+}
+__device__ __forceinline__ float curve_pos_in_gap(float x, int lo, const float* __restrict__ tb) {  // lo = curve_gap(x, tb)
     float pos = 0.0f;
     if (lo >= CURVE_TABLE) {
         pos = (float)(CURVE_TABLE - 1);
@@ -505,6 +508,9 @@ __device__ __forceinline__ float curve_pos(float x, const float* __restrict__ tb
         pos = (float)(lo - 1) + f;
     }
     return pos;
+}
+__device__ __forceinline__ float curve_pos(float x, const float* __restrict__ tb) {
+    return curve_pos_in_gap(x, curve_gap(x, tb), tb);
 }
 // ... scaled to an integer in [0, 2^bits) (monotone in pos)
 __device__ __forceinline__ unsigned int curve_scale(float pos, int bits) {
@@ -520,12 +526,15 @@ __device__ __forceinline__ unsigned int curve_coord(float x, const float* __rest
 
 // ---- value buckets for the exact 1-D counts (axes_mode > 0, "lazy axes"; see axis_buckets.cuh).
 // bucket of a value = its curve position at `bbits` bits (~16 points per bucket for rank-uniform data).
-constexpr int BUCKET_MAX_BITS = 20;
+constexpr int BUCKET_MAX_BITS = 22;
 constexpr int BUCKET_HEAVY = 512;  // a fuller bucket makes the set "heavy": the bucketed counts give up (flag)
+constexpr int BUCKET_CHUNK = 1024; // buckets per CTA of the two scan kernels
+// 2^bits buckets, ~4 values each for rank-uniform data (2^bits < n / 2: start, cursor and chunk sums of a
+// coordinate fit into its axis_pos row)
 static inline int bucket_bits(int64_t n) {
     int rb = 1;
     while ((1ll << rb) < n) ++rb;
-    int b = rb > 5 ? rb - 4 : 1;
+    int b = rb > 3 ? rb - 2 : 1;
     return b > BUCKET_MAX_BITS ? BUCKET_MAX_BITS : b;
 }
 
@@ -560,50 +569,89 @@ curve_key_kernel(const double* __restrict__ pts, int64_t ld, int64_t n, int dim_
     if (iota) iota[i] = (int32_t)i;
 }
 
-// grid = dim CTAs of 1024 threads.  hist[d][0..B) -> start[d][0..B] (exclusive prefix sums, start[B] = n) and
-// cursor[d][b] = start[d][b] (the scatter's bump cursors, in place of the histogram);  heavy[0] |= 1 when a
-// bucket holds more than BUCKET_HEAVY values (tied data: the bucketed counts would scan too much).
-static __global__ void __launch_bounds__(1024)
-bucket_scan_kernel(int32_t* __restrict__ hist_cursor, int64_t ldh, int32_t* __restrict__ start, int64_t lds, int B,
-                   int32_t* __restrict__ heavy) {
-    __shared__ int s_part[1024];
-    int32_t* h = hist_cursor + (int64_t)blockIdx.x * ldh;
-    int32_t* st = start + (int64_t)blockIdx.x * lds;
-    const int tid = threadIdx.x;
-    const int per = (B + 1023) / 1024;
-    const int b0 = min(tid * per, B), b1 = min(b0 + per, B);
-    int sum = 0, mx = 0;
-    for (int b = b0; b < b1; ++b) { const int c = h[b]; sum += c; mx = max(mx, c); }
-    s_part[tid] = sum;
+// Exclusive prefix sums of the bucket histogram, two launches (grid = (chunks of BUCKET_CHUNK buckets, dim),
+// 1024 threads, one bucket per thread):  bucket_sum_kernel: chunk_sum[d][chunk] = values in the chunk, and
+// heavy[0] |= 1 when a bucket holds more than BUCKET_HEAVY values (tied data);  bucket_scan_kernel:
+// start[d][b] = values in the buckets before b (start[B] = n), cursor[d][b] = start[d][b] in place of the
+// histogram (the scatter's bump cursors).
+static __device__ __forceinline__ int block_sum_1024(int v, int* s_warp) {  // all threads get the total
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // inclusive scan
-        const int v = tid >= off ? s_part[tid - off] : 0;
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
+    if (lane == 0) s_warp[warp] = v;
+    __syncthreads();
+    int t = s_warp[lane];
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    return t;
+}
+static __global__ void __launch_bounds__(BUCKET_CHUNK)
+bucket_sum_kernel(const int32_t* __restrict__ hist, int64_t ldh, int B, int32_t* __restrict__ chunk_sum, int64_t ldc,
+                  int32_t* __restrict__ heavy) {
+    __shared__ int s_warp[32];
+    const int b = blockIdx.x * BUCKET_CHUNK + threadIdx.x;
+    const int c = b < B ? hist[(int64_t)blockIdx.y * ldh + b] : 0;
+    const int total = block_sum_1024(c, s_warp);
+    if (threadIdx.x == 0) chunk_sum[(int64_t)blockIdx.y * ldc + blockIdx.x] = total;
+    if (__syncthreads_or(c > BUCKET_HEAVY) && threadIdx.x == 0) atomicOr(heavy, 1);
+}
+static __global__ void __launch_bounds__(BUCKET_CHUNK)
+bucket_scan_kernel(int32_t* __restrict__ hist_cursor, int64_t ldh, int32_t* __restrict__ start, int64_t lds, int B,
+                   const int32_t* __restrict__ chunk_sum, int64_t ldc) {
+    __shared__ int s_warp[32], s_scan[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // values in the chunks before this one
+    int before = 0;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += BUCKET_CHUNK) before += chunk_sum[(int64_t)blockIdx.y * ldc + i];
+    before = block_sum_1024(before, s_warp);
+    const int b = blockIdx.x * BUCKET_CHUNK + threadIdx.x;
+    int32_t* h = hist_cursor + (int64_t)blockIdx.y * ldh;
+    const int c = b < B ? h[b] : 0;
+    int incl = c;  // inclusive scan over the CTA: warp scans, then the warp totals
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
     }
-    int run = s_part[tid] - sum;
-    for (int b = b0; b < b1; ++b) {
-        const int c = h[b];
-        st[b] = run;
-        h[b] = run;
-        run += c;
+    __syncthreads();
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int wt = s_scan[lane];
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, wt, off);
+        if (lane >= off) wt += v;
     }
-    if (tid == 1023) st[B] = s_part[1023];
-    if (__syncthreads_or(mx > BUCKET_HEAVY) && tid == 0) atomicOr(heavy, 1);
+    const int warp_before = __shfl_sync(0xffffffffu, wt, warp) - s_scan[warp];
+    const int excl = before + warp_before + incl - c;
+    if (b < B) {
+        start[(int64_t)blockIdx.y * lds + b] = excl;
+        h[b] = excl;
+        if (b == B - 1) start[(int64_t)blockIdx.y * lds + B] = excl + c;
+    }
 }
 
 // vals[d][cursor[d][bucket]++] = pts[d][i]: the values of every coordinate grouped by bucket (any order inside
-// a bucket: the counts do not depend on it).  grid = (blocks, dim).
+// a bucket: the counts do not depend on it).  grid = (blocks, dim), four points per thread (the atomics are
+// latency-bound: four independent ones in flight).
+constexpr int BUCKET_SCATTER_PER_THREAD = 4;
 static __global__ void __launch_bounds__(256)
 bucket_scatter_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, const uint32_t* __restrict__ bucket_id,
                       int64_t ldb, int32_t* __restrict__ cursor, int64_t ldh, double* __restrict__ vals, int64_t ldv) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
     const int d = blockIdx.y;
-    const unsigned int b = bucket_id[(int64_t)d * ldb + i];
-    const int pos = atomicAdd(&cursor[(int64_t)d * ldh + b], 1);
-    vals[(int64_t)d * ldv + pos] = pts[(int64_t)d * ld_in + i];
+    const int64_t i0 = (int64_t)blockIdx.x * (256 * BUCKET_SCATTER_PER_THREAD) + threadIdx.x;
+    unsigned int b[BUCKET_SCATTER_PER_THREAD];
+    double v[BUCKET_SCATTER_PER_THREAD];
+    int pos[BUCKET_SCATTER_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < BUCKET_SCATTER_PER_THREAD; ++u) {
+        const int64_t i = i0 + u * 256;
+        b[u] = i < n ? bucket_id[(int64_t)d * ldb + i] : 0u;
+        v[u] = i < n ? pts[(int64_t)d * ld_in + i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < BUCKET_SCATTER_PER_THREAD; ++u)
+        pos[u] = i0 + u * 256 < n ? atomicAdd(&cursor[(int64_t)d * ldh + b[u]], 1) : 0;
+#pragma unroll
+    for (int u = 0; u < BUCKET_SCATTER_PER_THREAD; ++u)
+        if (i0 + u * 256 < n) vals[(int64_t)d * ldv + pos[u]] = v[u];
 }
 
 // bits per coordinate of the curve for n points in `dim` coordinates (shared by ksg_prepare and

@@ -69,20 +69,32 @@ def _prepared_digest():
     return "|".join(out)
 
 
-def _knn_digest():
-    """sha1 over radii / flags / neighbour lists of the windowed k-NN stage (first pass, nothing escalated)."""
+def _knn_digest_high():
+    return _knn_digest(high=True)
+
+
+def _knn_digest(high=False):
+    """sha1 over radii / flags / neighbour lists of the windowed k-NN stage (first pass, nothing escalated);
+    ``high``: the sets of 5 to 8 coordinates instead of those of 1 to 4."""
     import torch
 
     from syntropy_b200 import _engine as E
 
     out = []
     rng = np.random.default_rng(23)
-    for name, rows in _sets():
+    sets = _sets()
+    if high:
+        r2 = np.random.default_rng(29)
+        sets = [s for s in sets if s[1].shape[0] > 4] + [
+            ("5d", r2.standard_normal((5, 30_000))), ("7d heavy", r2.standard_t(2.0, size=(7, 12_000))),
+            ("6d quantised", np.round(r2.standard_normal((6, 20_000)) * 4) / 4),
+            ("8d clusters", np.concatenate([r2.standard_normal((8, 4_000)) * 0.1 + 3 * c for c in range(4)], axis=1))]
+    for name, rows in sets:
         dim = rows.shape[0]
-        if dim > 4:
+        if (dim > 4) != high:
             continue
         pts = E.to_device_points(rows)
-        prep = E.PreparedSet(pts, -1)
+        prep = E.PreparedSet(pts, E.order_for(dim) if high else -1)
         n = prep.n
         # (k' + margin = 8, 12, 16, 24: the list capacities of the warp-level kernel, so that both kernels keep
         #  lists of the same length and flag the same tie-saturated queries; 44 and 36: too long for it)
@@ -104,7 +116,7 @@ def _knn_digest():
         q0, q1 = n // 3 + 5, n // 3 + 5 + min(n // 2, 4_321)
         eps, _, flags, _ = E._fast_knn_call(prep, 4, q0, q1, True)
         out.append("%s/slice:%s" % (name, hashlib.sha1(eps.cpu().numpy().tobytes() + flags.cpu().numpy().tobytes()).hexdigest()))
-        if dim >= 2 and n >= 1000:
+        if dim >= 2 and n >= 1000 and int(prep.c.primary) == -1:
             other = torch.from_numpy(np.ascontiguousarray(rows[:, ::-1] * 1.05 + 0.01 * rng.standard_normal(rows.shape))).cuda()
             cross = E.CrossSet(prep, other)
             r = E.fast_knn_cross(cross, 3, 0, other.shape[1])
@@ -134,6 +146,14 @@ def test_fused_gather_builds_identical_prepared_sets():
 def test_warp_level_knn_equals_the_cta_level_kernel():
     mine = _knn_digest()
     ref = _in_subprocess("_knn_digest", KSG_B200_UNITS="cta")
+    assert mine == ref, _diff(mine, ref)
+
+
+def test_grouped_knn_equals_the_whole_warp_kernel():
+    """knn_gunits_kernel (8-query groups inside the filter warps, 5 to 8 coordinates) == knn_units_kernel."""
+    mine = _knn_digest_high()
+    assert mine.count("|") > 20
+    ref = _in_subprocess("_knn_digest_high", KSG_B200_GROUPS="0")
     assert mine == ref, _diff(mine, ref)
 
 
