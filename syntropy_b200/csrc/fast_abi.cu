@@ -545,9 +545,10 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 note_launch();
             }
             if (fused_gather()) {
+                // (lazy axes: nothing is remapped, the inverse permutation is not needed)
                 gather_tile_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 256, 0, st>>>(
-                    d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, invperm,
-                    P.tile_box, P.sub_box, exact_info, exact_off, P.flags);
+                    d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32,
+                    lazy ? nullptr : invperm, P.tile_box, P.sub_box, exact_info, exact_off, P.flags);
                 KSG_LAUNCHED2();
                 return KSG_OK;
             }

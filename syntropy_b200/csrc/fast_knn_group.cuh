@@ -5,13 +5,15 @@
 // candidate boxes: even with the true radii a 32-query warp must scan 14 % (6-D) / 43 % (8-D) of all
 // pairs at n = 2e5, a group of 8 consecutive queries 5 % / 19 % (tools/pruning_sim.py,
 // profiles/r1aj_pruning_simulation.txt).  Here every filter warp keeps its 32 consecutive queries as
-// FOUR groups of 8, each with its own box, threshold and surviving sub-tiles; a lane is (stream s =
-// lane / 8, member m = lane % 8) and holds member m of every group.  A surviving (group, sub-tile) is
-// scanned by all 32 lanes at once: stream s takes the candidates c = 4 i + s (four neighbouring rows per
-// shared-memory read, conflict-free), 8 steps instead of 32, then the four streams' running minima are
-// folded (two shuffles) and only a group that saw something closer walks the sub-tile again (stream 0)
-// to insert.  Same tile ring, copy warp, planning pass, unit table, lists and refine as knn_units_kernel;
-// results are identical.
+// FOUR groups of 8, each with its own box, threshold and surviving sub-tiles.  Lane l owns query l (its
+// list, its threshold) and is (stream s = l / 8, member m = l % 8): the owners of group g are the lanes of
+// stream g.  A surviving (group, sub-tile) is scanned by all 32 lanes at once: every lane fetches member
+// m's query of that group from its owner (shuffles, once per group and tile), stream s takes the candidates
+// c = 4 i + s (four neighbouring rows per shared-memory read, conflict-free) -- 8 steps instead of 32 --
+// and keeps one hit bit per candidate; only when somebody saw a candidate below its threshold do the
+// owners collect the four streams' bits of their query (four shuffles) and insert exactly those candidates.
+// Same tile ring, copy warp, planning pass, unit table, lists and refine as knn_units_kernel; results are
+// identical.
 #pragma once
 
 #include "fast_knn.cuh"
@@ -20,7 +22,7 @@ namespace ksg {
 
 constexpr int GU_GROUPS = 4;  // query groups per filter warp
 constexpr int GU_GQ = 8;      // queries per group
-constexpr int gunits_min_blocks(int dp) { return dp <= 6 ? 4 : 4; }
+constexpr int gunits_min_blocks(int dp) { return dp <= 6 ? 6 : 5; }
 
 template <int DP, int STAGES>
 static __global__ void __launch_bounds__(UNITS_THREADS, gunits_min_blocks(DP))
@@ -86,39 +88,25 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
         const int nunits = unit_count[qblock];
         const bool refine_here = ra.fused && nunits == 1;
 
-        // ---------------- filter warps: member `mem` of every group, thresholds, group boxes, empty lists
-        float2 q[GU_GROUPS][DP / 2];
-        float thr[GU_GROUPS];    // insertion threshold of query (g, mem) -- the same in all four streams
-        float seed[GU_GROUPS];
-        int pmax[GU_GROUPS], nfill[GU_GROUPS];  // list state (meaningful in stream 0, which inserts)
-        float gthr[GU_GROUPS];   // largest threshold of group g (warp-uniform)
+        // ---------------- filter warps: lane l owns query warp * 32 + l (group l / 8, member l % 8)
+        float2 q[DP / 2];
+        float thr = -1.0f, seed = -1.0f;  // insertion threshold: min(seed, current list maximum)
+        int pmax = 0, nfill = 0;
+        bool alive = false;
+        float gthr[GU_GROUPS];  // largest threshold of every group (warp-uniform)
         if (!producer) {
-#pragma unroll
-            for (int g = 0; g < GU_GROUPS; ++g) {
-                const int64_t qi = qb0 + warp * 32 + g * GU_GQ + mem;
-                const bool in = qi < nq;
-                load_row<DP>((qshadow ? qshadow : shadow) + (q_begin + (in ? qi : 0)) * DP, q[g]);
-                const float s0 = in ? seed_thr[qi] : -1.0f;
-                seed[g] = s0 < 0.0f ? -1.0f : s0;  // deferred / dead slots never insert
-                thr[g] = seed[g];
-                pmax[g] = 0;
-                nfill[g] = 0;
-            }
-            // stream s folds group s: box and largest threshold over the members (xor 1, 2, 4 stay inside a stream)
-            float2 qs[DP / 2];
-            float ts = -1.0f;
-#pragma unroll
-            for (int g = 0; g < GU_GROUPS; ++g)
-                if (g == strm) {
-#pragma unroll
-                    for (int h = 0; h < DP / 2; ++h) qs[h] = q[g][h];
-                    ts = thr[g];
-                }
-            const bool in_box = ts >= 0.0f;
+            const int64_t qi = qb0 + warp * 32 + lane;
+            alive = qi < nq;
+            load_row<DP>((qshadow ? qshadow : shadow) + (q_begin + (alive ? qi : 0)) * DP, q);
+            const float s0 = alive ? seed_thr[qi] : -1.0f;
+            seed = s0 < 0.0f ? -1.0f : s0;  // deferred / dead slots never insert
+            thr = seed;
+            // a group's members are the 8 lanes of one stream: xor 1, 2, 4 fold inside it
+            const bool in_box = thr >= 0.0f;
 #pragma unroll
             for (int h = 0; h < DP / 2; ++h) {
-                float lx = in_box ? qs[h].x : CUDART_INF_F, hx = in_box ? qs[h].x : -CUDART_INF_F;
-                float ly = in_box ? qs[h].y : CUDART_INF_F, hy = in_box ? qs[h].y : -CUDART_INF_F;
+                float lx = in_box ? q[h].x : CUDART_INF_F, hx = in_box ? q[h].x : -CUDART_INF_F;
+                float ly = in_box ? q[h].y : CUDART_INF_F, hy = in_box ? q[h].y : -CUDART_INF_F;
 #pragma unroll
                 for (int off = 1; off < GU_GQ; off <<= 1) {
                     lx = fminf(lx, __shfl_xor_sync(FULL, lx, off)); hx = fmaxf(hx, __shfl_xor_sync(FULL, hx, off));
@@ -129,16 +117,14 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
                     s_gbox[warp][strm][2 * h + 1] = make_float2(ly, hy);
                 }
             }
+            float ts = thr;
 #pragma unroll
             for (int off = 1; off < GU_GQ; off <<= 1) ts = fmaxf(ts, __shfl_xor_sync(FULL, ts, off));
-            if (mem == 0) s_gthr[warp][strm] = ts;
-            float wt = ts;
-            wt = fmaxf(wt, __shfl_xor_sync(FULL, wt, 8));
-            wt = fmaxf(wt, __shfl_xor_sync(FULL, wt, 16));
-            if (lane == 0) *reinterpret_cast<volatile float*>(&s_wthr[warp]) = wt;
-            __syncwarp();
 #pragma unroll
-            for (int g = 0; g < GU_GROUPS; ++g) gthr[g] = s_gthr[warp][g];
+            for (int g = 0; g < GU_GROUPS; ++g) gthr[g] = __shfl_sync(FULL, ts, g * GU_GQ);
+            if (lane == 0)
+                *reinterpret_cast<volatile float*>(&s_wthr[warp]) = fmaxf(fmaxf(gthr[0], gthr[1]), fmaxf(gthr[2], gthr[3]));
+            __syncwarp();
             for (int r = 0; r < kcap; ++r) {
                 lst_d[(size_t)r * QB + tid] = CUDART_INF_F;
                 lst_i[(size_t)r * QB + tid] = -1;
@@ -185,13 +171,32 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
         }
 
         // ---------------- filter warps
+        auto insert = [&](float m, int32_t idx) -> bool {
+            lst_d[(size_t)pmax * QB + tid] = m;
+            lst_i[(size_t)pmax * QB + tid] = idx;
+            if (nfill + 1 < kcap) {  // free slots left: append, the threshold stays at the seed
+                pmax = ++nfill;
+                return false;
+            }
+            nfill = kcap;
+            float mx = -1.0f;
+            int p = 0;
+#pragma unroll 3
+            for (int r = 0; r < kcap; ++r) {
+                const float v = lst_d[(size_t)r * QB + tid];
+                if (v > mx) { mx = v; p = r; }
+            }
+            pmax = p;
+            thr = fminf(seed, mx);
+            return true;  // the threshold may have shrunk
+        };
         for (;;) {
             mbar_wait(&full_bar[slot], (phase_bits >> slot) & 1u);
             const int t = *reinterpret_cast<volatile int*>(&s_tile[slot]);
             if (t >= 0) {
                 const float* tile = tiles + (size_t)slot * SLOT_FLOATS;
                 const float2* boxes = reinterpret_cast<const float2*>(tile + TILE_FLOATS);
-                const int64_t tile_base = (int64_t)t * FAST_TILE;
+                const int32_t tile_base = (int32_t)((int64_t)t * FAST_TILE);
                 // round r: lanes 0..15 test the 16 sub-tiles against group 2 r, lanes 16..31 against group 2 r + 1
                 float my_gap[2];
                 uint32_t live[2];
@@ -211,6 +216,15 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
 #pragma unroll
                 for (int g = 0; g < GU_GROUPS; ++g) {
                     uint32_t todo = (g & 1) ? (live[g >> 1] >> 16) : (live[g >> 1] & 0xffffu);
+                    if (!todo) continue;  // warp-uniform
+                    // this lane scans for member `mem` of group g: its query and threshold come from their owner
+                    float2 qg[DP / 2];
+#pragma unroll
+                    for (int h = 0; h < DP / 2; ++h) {
+                        qg[h].x = __shfl_sync(FULL, q[h].x, g * GU_GQ + mem);
+                        qg[h].y = __shfl_sync(FULL, q[h].y, g * GU_GQ + mem);
+                    }
+                    float tg = __shfl_sync(FULL, thr, g * GU_GQ + mem);
 #pragma unroll 1
                     while (todo) {
                         const int sb = __ffs(todo) - 1;
@@ -219,54 +233,44 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
                         if (!(gap < gthr[g])) continue;  // warp-uniform: the group's threshold has shrunk since
                         ++scans_total;
                         const float* rows = tile + sb * FAST_SUB * DP;
-                        float mrun = CUDART_INF_F;
+                        // stream s takes the candidates 4 i + s; bit 7 - i of hm: candidate 4 i + s is closer than tg
+                        uint32_t hm = 0u;
 #pragma unroll
                         for (int i = 0; i < FAST_SUB / 4; ++i) {
                             float2 cc[DP / 2];
                             load_row<DP>(rows + (4 * i + strm) * DP, cc);
-                            mrun = fminf(mrun, cheb32<DP>(q[g], cc));
+                            hm = push_sign(hm, cheb32<DP>(qg, cc) - tg);
                         }
-                        mrun = fminf(mrun, __shfl_xor_sync(FULL, mrun, 8));
-                        mrun = fminf(mrun, __shfl_xor_sync(FULL, mrun, 16));
-                        const bool hit = mrun < thr[g];
-                        if (!__any_sync(FULL, hit)) continue;
+                        if (!__any_sync(FULL, hm != 0u)) continue;
+                        // the owners (stream g) collect the four streams' bits of their query and insert
+                        uint32_t hs[4];
+#pragma unroll
+                        for (int s2 = 0; s2 < 4; ++s2) hs[s2] = __shfl_sync(FULL, hm, s2 * GU_GQ + mem);
                         bool changed = false;
-                        if (hit && strm == 0) {
-                            const int col = warp * 32 + g * GU_GQ + mem;
-#pragma unroll 1
-                            for (int c = 0; c < FAST_SUB; ++c) {
-                                float2 cc[DP / 2];
-                                load_row<DP>(rows + c * DP, cc);
-                                const float m = cheb32<DP>(q[g], cc);
-                                if (m < thr[g]) {
-                                    lst_d[(size_t)pmax[g] * QB + col] = m;
-                                    lst_i[(size_t)pmax[g] * QB + col] = (int32_t)(tile_base + sb * FAST_SUB + c);
-                                    if (nfill[g] + 1 < kcap) {
-                                        pmax[g] = ++nfill[g];  // free slots left: append, the threshold stays at the seed
-                                    } else {
-                                        nfill[g] = kcap;
-                                        float mx = -1.0f;
-                                        int p = 0;
-#pragma unroll 3
-                                        for (int r = 0; r < kcap; ++r) {
-                                            const float v = lst_d[(size_t)r * QB + col];
-                                            if (v > mx) { mx = v; p = r; }
-                                        }
-                                        pmax[g] = p;
-                                        thr[g] = fminf(seed[g], mx);
-                                        changed = true;
-                                    }
+                        if (strm == g) {
+#pragma unroll
+                            for (int s2 = 0; s2 < 4; ++s2) {
+                                uint32_t mk = hs[s2];
+                                while (mk) {
+                                    const int b = 31 - __clz(mk);
+                                    mk &= ~(1u << b);
+                                    const int c = 4 * (FAST_SUB / 4 - 1 - b) + s2;
+                                    float2 cc[DP / 2];
+                                    load_row<DP>(rows + c * DP, cc);
+                                    const float m = cheb32<DP>(q, cc);
+                                    if (m < thr) changed |= insert(m, tile_base + sb * FAST_SUB + c);
                                 }
                             }
                         }
                         if (__any_sync(FULL, changed)) {
-                            thr[g] = __shfl_sync(FULL, thr[g], mem);  // stream 0 holds the new thresholds
-                            float gt = thr[g];
+                            tg = __shfl_sync(FULL, thr, g * GU_GQ + mem);
+                            float ts = thr;
 #pragma unroll
-                            for (int off = 1; off < GU_GQ; off <<= 1) gt = fmaxf(gt, __shfl_xor_sync(FULL, gt, off));
-                            gthr[g] = gt;
-                            float wt = fmaxf(fmaxf(gthr[0], gthr[1]), fmaxf(gthr[2], gthr[3]));
-                            if (lane == 0) *reinterpret_cast<volatile float*>(&s_wthr[warp]) = wt;
+                            for (int off = 1; off < GU_GQ; off <<= 1) ts = fmaxf(ts, __shfl_xor_sync(FULL, ts, off));
+                            gthr[g] = __shfl_sync(FULL, ts, g * GU_GQ);
+                            if (lane == 0)
+                                *reinterpret_cast<volatile float*>(&s_wthr[warp]) =
+                                    fmaxf(fmaxf(gthr[0], gthr[1]), fmaxf(gthr[2], gthr[3]));
                         }
                     }
                 }
@@ -277,22 +281,14 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
             if (t < 0) break;
         }
 
-        // ---------------- lane l now owns the list of query warp * 32 + l (filled by the stream-0 lane of its group)
-        __syncwarp();
-        int filled = 0;
-#pragma unroll
-        for (int g = 0; g < GU_GROUPS; ++g) {
-            const int v = __shfl_sync(FULL, nfill[g], lane & (GU_GQ - 1));
-            if (g == (lane >> 3)) filled = v;
-        }
+        // ---------------- sort each list (ascending); refine it here or emit it
         const int lq = warp * 32 + lane;
         const int64_t qi_l = qb0 + lq;
-        const bool alive = qi_l < nq;
-        const float s_l = alive ? seed_thr[qi_l] : -1.0f;
-        const float seed_l = s_l < 0.0f ? -1.0f : s_l;
+        const float seed_l = seed;
         {
             const int col = tid;
-            for (int a = 1; a < filled; ++a) {  // ascending; the rest of the column is +inf / -1
+            const int filled = nfill;  // the rest of the column is +inf / -1
+            for (int a = 1; a < filled; ++a) {
                 const float d = lst_d[(size_t)a * QB + col];
                 const int32_t i = lst_i[(size_t)a * QB + col];
                 int b = a - 1;

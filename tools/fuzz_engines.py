@@ -125,10 +125,11 @@ def main():
                 aa, bb = np.atleast_1d(np.asarray(a[0], dtype=np.float64)), np.atleast_1d(np.asarray(b[0], dtype=np.float64))
                 with np.errstate(all="ignore"):
                     worst = int(np.nanargmax(np.abs(aa - bb))) if aa.shape == bb.shape and aa.size else -1
-                print(f"API MISMATCH case {case}: {kind} dim={dim} n={n} k={k} output#{which} "
-                      f"n_diff={int((aa != bb).sum()) if aa.shape == bb.shape else -1} worst_at={worst} "
-                      f"exact={aa[worst] if worst >= 0 else None!r} windowed={bb[worst] if worst >= 0 else None!r} "
-                      f"avg_exact={a[1]!r} avg_windowed={b[1]!r}", flush=True)
+                ex = repr(aa[worst]) if worst >= 0 else "?"
+                wi = repr(bb[worst]) if worst >= 0 else "?"
+                nd = int((aa != bb).sum()) if aa.shape == bb.shape else -1
+                print(f"API MISMATCH case {case}: {kind} dim={dim} n={n} k={k} output#{which} n_diff={nd} "
+                      f"worst_at={worst} exact={ex} windowed={wi} avg_exact={a[1]!r} avg_windowed={b[1]!r}", flush=True)
         print(f"case {case}: {kind} dim={dim} n={n} k={k} subs={len(subs)} ok", flush=True)
     print("FUZZ_OK" if bad == 0 else f"FUZZ_FAILED {bad}")
     sys.exit(1 if bad else 0)
