@@ -469,14 +469,16 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
     const int64_t gather_blocks = ceil_div(L.n_padded, 256);
 
     KSG_CUDA_TRY(cudaMemsetAsync(P.flags, 0, 64, st));
-    iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
-    KSG_LAUNCHED2();
+    SortLanes* lanes = sort_lanes_for_device();
+    if (!(primary == -1 && early_order() && lanes)) {  // (early order: curve_key_kernel writes the identity order too)
+        iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(iota, n);
+        KSG_LAUNCHED2();
+    }
     const unsigned nb = (unsigned)ceil_div(n, 256);
     int rc;
     P.tile_box = (float*)(base + L.off_tile_box);
     P.sub_box = (float*)(base + L.off_sub_box);
     if (primary == -1) P.curve_keys = (uint64_t*)(base + L.off_mkeys_out);
-    SortLanes* lanes = sort_lanes_for_device();
 
     if (!(primary == -1 && early_order() && lanes)) lazy = false;
     const int bbits = bucket_bits(n);
@@ -515,10 +517,10 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 for (int d = 0; d < dim; ++d)
                     KSG_CUDA_TRY(cudaMemsetAsync(bcursor + (int64_t)d * L.ld, 0, (size_t)n_buckets * 4, st));
             switch (dim) {
-#define KSG_CKEY(D) case D: curve_key_kernel<D><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, nullptr, bbits, bcursor, L.ld, bucket_id, L.ld); break;
+#define KSG_CKEY(D) case D: curve_key_kernel<D><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, iota, bbits, bcursor, L.ld, bucket_id, L.ld); break;
                 KSG_CKEY(1) KSG_CKEY(2) KSG_CKEY(3) KSG_CKEY(4) KSG_CKEY(5) KSG_CKEY(6) KSG_CKEY(7) KSG_CKEY(8)
 #undef KSG_CKEY
-                default: curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, nullptr, bbits, bcursor, L.ld, bucket_id, L.ld);
+                default: curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, iota, bbits, bcursor, L.ld, bucket_id, L.ld);
             }
             KSG_LAUNCHED2();
             if (lazy) {

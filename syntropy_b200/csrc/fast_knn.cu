@@ -133,6 +133,41 @@ static int launch_wunits_dp(const KnnF32Args& a) {
     }
 }
 
+// many dimensions: 8-query groups inside the filter warps (fast_knn_group.cuh)
+template <int DP>
+static int launch_gunits_dp(const KnnF32Args& a) {
+    constexpr int ST = FastGeom<DP>::STAGES;
+    auto kern = knn_gunits_kernel<DP, ST>;
+    const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float) + (size_t)a.kcap * FAST_THREADS * 8;
+    if (smem > 32 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    }
+    static int cached_dev = -1, cached_per_sm = 0;
+    static size_t cached_smem = 0;
+    int dev = 0;
+    (void)cudaGetDevice(&dev);
+    int per_sm = 0;
+    cudaError_t e = cudaSuccess;
+    if (dev == cached_dev && smem == cached_smem && cached_per_sm > 0) {
+        per_sm = cached_per_sm;
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, UNITS_THREADS, smem);
+        if (e != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
+        cached_dev = dev; cached_smem = smem; cached_per_sm = per_sm;
+    }
+    int64_t grid = (int64_t)per_sm * sm_count();
+    if (grid > a.max_units) grid = a.max_units;
+    kern<<<(unsigned)grid, UNITS_THREADS, smem, a.st>>>(a.shadow, a.tile_box, a.sub_box, a.n_tiles, a.q_begin, a.nq, a.kcap, a.qshadow,
+                                                       a.qhome, a.seed_thr, (const int2*)a.plan, a.plan_count, a.plan_first,
+                                                       a.unit_first, a.unit_block, a.unit_meta, a.part_d32, a.part_idx,
+                                                       a.tile_counter, a.unit_done, a.ra);
+    note_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("knn_gunits_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    return KSG_OK;
+}
+
 template <int DP>
 static int launch_units_dp(const KnnF32Args& a) {
     if constexpr (DP <= 4 && UNITS_Q == 1) {
@@ -141,10 +176,10 @@ static int launch_units_dp(const KnnF32Args& a) {
     constexpr int Q = UnitsQ<DP>::Q, ST = FastGeom<DP>::STAGES;
     // many dimensions: 8-query groups inside the filter warps (fast_knn_group.cuh); KSG_B200_GROUPS=0: whole warps
     static const bool grouped = [] { const char* e = getenv("KSG_B200_GROUPS"); return !(e && e[0] == '0'); }();
-    auto kern = knn_units_kernel<DP, Q, ST, (DP <= 4)>;
     if constexpr (DP >= 6 && UNITS_Q == 1) {
-        if (grouped) kern = knn_gunits_kernel<DP, ST>;
+        if (grouped) return launch_gunits_dp<DP>(a);
     }
+    auto kern = knn_units_kernel<DP, Q, ST, (DP <= 4)>;
     const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float) +
                         (size_t)a.kcap * FAST_THREADS * Q * 8;
     if (smem > 32 * 1024) {

@@ -26,7 +26,8 @@ constexpr int gunits_min_blocks(int dp) { return dp <= 6 ? 6 : 5; }
 
 template <int DP, int STAGES>
 static __global__ void __launch_bounds__(UNITS_THREADS, gunits_min_blocks(DP))
-knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ sub_box, int64_t n_tiles,
+knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box,
+                  const float* __restrict__ sub_box, int64_t n_tiles,
                   int64_t q_begin, int64_t nq, int kcap, const float* __restrict__ qshadow,
                   const int32_t* __restrict__ qhome, const float* __restrict__ seed_thr,
                   const int2* __restrict__ plan, const int32_t* __restrict__ plan_count,
@@ -120,6 +121,7 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
             float ts = thr;
 #pragma unroll
             for (int off = 1; off < GU_GQ; off <<= 1) ts = fmaxf(ts, __shfl_xor_sync(FULL, ts, off));
+            if (mem == 0) *reinterpret_cast<volatile float*>(&s_gthr[warp][strm]) = ts;
 #pragma unroll
             for (int g = 0; g < GU_GROUPS; ++g) gthr[g] = __shfl_sync(FULL, ts, g * GU_GQ);
             if (lane == 0)
@@ -151,6 +153,23 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
                         if (!(__int_as_float(e.y) < R)) continue;
                         tile = e.x;
                     }
+                    // Does ANY of the CTA's 16 query groups reach into the tile?  (lane l < 16: group l % 4 of
+                    // filter warp l / 4; thresholds only shrink, a stale one is merely conservative.)  A tile
+                    // nobody needs is neither copied nor waited for: with 8-query groups that is most of a
+                    // planned list, and the tile feed -- not the arithmetic -- was what the filter warps waited on.
+                    bool reach = false;
+                    if (lane < (FAST_THREADS / 32) * GU_GROUPS) {
+                        const int w = lane >> 2, g = lane & 3;
+                        float gap = 0.0f;
+#pragma unroll
+                        for (int d = 0; d < DP; ++d) {
+                            const float2 bx = reinterpret_cast<const float2*>(tile_box)[(int64_t)tile * DP + d];
+                            const float2 gb = s_gbox[w][g][d];
+                            gap = fmaxf(gap, fmaxf(bx.x - gb.y, gb.x - bx.y));
+                        }
+                        reach = gap < *reinterpret_cast<volatile float*>(&s_gthr[w][g]);
+                    }
+                    if (!__any_sync(FULL, reach)) continue;
                 }
                 mbar_wait_relaxed(&empty_bar[slot], (phase_bits >> slot) & 1u);
                 if (lane == 0) {
@@ -268,9 +287,11 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
 #pragma unroll
                             for (int off = 1; off < GU_GQ; off <<= 1) ts = fmaxf(ts, __shfl_xor_sync(FULL, ts, off));
                             gthr[g] = __shfl_sync(FULL, ts, g * GU_GQ);
-                            if (lane == 0)
+                            if (lane == 0) {
+                                *reinterpret_cast<volatile float*>(&s_gthr[warp][g]) = gthr[g];
                                 *reinterpret_cast<volatile float*>(&s_wthr[warp]) =
                                     fmaxf(fmaxf(gthr[0], gthr[1]), fmaxf(gthr[2], gthr[3]));
+                            }
                         }
                     }
                 }

@@ -80,6 +80,8 @@ def main():
     ap.add_argument("--cases", type=int, default=60)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--big", action="store_true", help="sizes 5e4 .. 3e5 instead of 37 .. 2e4")
+    ap.add_argument("--only", type=int, default=-1, help="evaluate this case only (the others just advance the generator)")
+    ap.add_argument("--repeat", type=int, default=1, help="evaluate every selected case this many times")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     bad = 0
@@ -90,47 +92,50 @@ def main():
         k = int(rng.integers(1, min(12, n - 1)))
         kind, rows = make_data(rng, dim, n)
         subs = subspaces(rng, dim)
-        E.config.engine, E.config.primary = "exact", -1
-        ref = radius_and_counts(rows, k, subs)
-        for engine, primary in (("windowed", -1), ("windowed", -2), ("dense", -1)):
-            E.config.engine, E.config.primary = engine, primary
-            got = radius_and_counts(rows, k, subs)
-            ok = np.array_equal(got[0], ref[0], equal_nan=True) and np.array_equal(got[1], ref[1])
-            if not ok:
-                bad += 1
-                print(f"MISMATCH case {case}: {kind} dim={dim} n={n} k={k} engine={engine} primary={primary} "
-                      f"eps_diff={int((got[0] != ref[0]).sum())} count_diff={int((got[1] != ref[1]).sum())}", flush=True)
-        # public API under the production engine vs the exact engine
-        api = {}
-        for engine in ("exact", "windowed"):
-            E.config.engine, E.config.primary = engine, -1
-            out = [knn.differential_entropy(rows, k)]
-            if dim >= 2:
-                cut = dim // 2
-                x, y = tuple(range(cut)), tuple(range(cut, dim))
-                out.append(knn.mutual_information(x, y, k, rows))
-                if kind not in ("duplicates", "quantised", "constant_dim"):   # KSG-2: tie-free data only
-                    out.append(knn.mutual_information(x, y, k, rows, algorithm=2))
-                other = rows[:, ::-1] * 1.1 + 0.05
-                out.append(knn.kullback_leibler_divergence(rows, np.ascontiguousarray(other[:, : max(k + 2, n // 2)]), k))
-            if n >= 200:
-                out.append((np.array([knn.sample_entropy((0,), rows, m=2, r=0.3)]), 0.0))
-            api[engine] = out
-        for which, (a, b) in enumerate(zip(api["exact"], api["windowed"])):
-            with np.errstate(all="ignore"):
-                same = np.array_equal(np.asarray(a[0]), np.asarray(b[0]), equal_nan=True)
-                close = np.allclose(np.asarray(a[0]), np.asarray(b[0]), rtol=1e-12, atol=1e-12, equal_nan=True)
-            if not (same or close):
-                bad += 1
-                aa, bb = np.atleast_1d(np.asarray(a[0], dtype=np.float64)), np.atleast_1d(np.asarray(b[0], dtype=np.float64))
+        if args.only >= 0 and case != args.only:
+            continue
+        for _rep in range(args.repeat):
+            E.config.engine, E.config.primary = "exact", -1
+            ref = radius_and_counts(rows, k, subs)
+            for engine, primary in (("windowed", -1), ("windowed", -2), ("dense", -1)):
+                E.config.engine, E.config.primary = engine, primary
+                got = radius_and_counts(rows, k, subs)
+                ok = np.array_equal(got[0], ref[0], equal_nan=True) and np.array_equal(got[1], ref[1])
+                if not ok:
+                    bad += 1
+                    print(f"MISMATCH case {case}: {kind} dim={dim} n={n} k={k} engine={engine} primary={primary} "
+                          f"eps_diff={int((got[0] != ref[0]).sum())} count_diff={int((got[1] != ref[1]).sum())}", flush=True)
+            # public API under the production engine vs the exact engine
+            api = {}
+            for engine in ("exact", "windowed"):
+                E.config.engine, E.config.primary = engine, -1
+                out = [knn.differential_entropy(rows, k)]
+                if dim >= 2:
+                    cut = dim // 2
+                    x, y = tuple(range(cut)), tuple(range(cut, dim))
+                    out.append(knn.mutual_information(x, y, k, rows))
+                    if kind not in ("duplicates", "quantised", "constant_dim"):   # KSG-2: tie-free data only
+                        out.append(knn.mutual_information(x, y, k, rows, algorithm=2))
+                    other = rows[:, ::-1] * 1.1 + 0.05
+                    out.append(knn.kullback_leibler_divergence(rows, np.ascontiguousarray(other[:, : max(k + 2, n // 2)]), k))
+                if n >= 200:
+                    out.append((np.array([knn.sample_entropy((0,), rows, m=2, r=0.3)]), 0.0))
+                api[engine] = out
+            for which, (a, b) in enumerate(zip(api["exact"], api["windowed"])):
                 with np.errstate(all="ignore"):
-                    worst = int(np.nanargmax(np.abs(aa - bb))) if aa.shape == bb.shape and aa.size else -1
-                ex = repr(aa[worst]) if worst >= 0 else "?"
-                wi = repr(bb[worst]) if worst >= 0 else "?"
-                nd = int((aa != bb).sum()) if aa.shape == bb.shape else -1
-                print(f"API MISMATCH case {case}: {kind} dim={dim} n={n} k={k} output#{which} n_diff={nd} "
-                      f"worst_at={worst} exact={ex} windowed={wi} avg_exact={a[1]!r} avg_windowed={b[1]!r}", flush=True)
-        print(f"case {case}: {kind} dim={dim} n={n} k={k} subs={len(subs)} ok", flush=True)
+                    same = np.array_equal(np.asarray(a[0]), np.asarray(b[0]), equal_nan=True)
+                    close = np.allclose(np.asarray(a[0]), np.asarray(b[0]), rtol=1e-12, atol=1e-12, equal_nan=True)
+                if not (same or close):
+                    bad += 1
+                    aa, bb = np.asarray(a[0], dtype=np.float64).ravel(), np.asarray(b[0], dtype=np.float64).ravel()
+                    with np.errstate(all="ignore"):
+                        worst = int(np.nanargmax(np.abs(aa - bb))) if aa.shape == bb.shape and aa.size else -1
+                    ex = repr(aa[worst]) if worst >= 0 else "?"
+                    wi = repr(bb[worst]) if worst >= 0 else "?"
+                    nd = int((aa != bb).sum()) if aa.shape == bb.shape else -1
+                    print(f"API MISMATCH case {case}: {kind} dim={dim} n={n} k={k} output#{which} n_diff={nd} "
+                          f"worst_at={worst} exact={ex} windowed={wi} avg_exact={a[1]!r} avg_windowed={b[1]!r}", flush=True)
+            print(f"case {case}: {kind} dim={dim} n={n} k={k} subs={len(subs)} ok", flush=True)
     print("FUZZ_OK" if bad == 0 else f"FUZZ_FAILED {bad}")
     sys.exit(1 if bad else 0)
 
