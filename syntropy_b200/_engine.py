@@ -487,6 +487,9 @@ class PreparedSet:
                                       C.byref(self.c), _stream())
         _cabi.check(rc, "ksg_prepare_rows")
         self.n, self.dim, self.ld = n, dim, int(self.c.ld)
+        # the library's side streams may still be at work on this set when the constructor returns (see
+        # __del__): nothing they could touch goes back to the caching allocator before that join
+        self._pts = pts
 
     def ensure_axes(self):
         """A set prepared with lazy axes (primary = -3: value buckets instead of the per-coordinate sorts)

@@ -547,10 +547,10 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 note_launch();
             }
             if (fused_gather()) {
-                // (lazy axes: nothing is remapped, the inverse permutation is not needed)
+                // (the coordinate sorts of this path run on the prepared copy: no inverse permutation, no remap)
                 gather_tile_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 256, 0, st>>>(
                     d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32,
-                    lazy ? nullptr : invperm, P.tile_box, P.sub_box, exact_info, exact_off, P.flags);
+                    nullptr, P.tile_box, P.sub_box, exact_info, exact_off, P.flags);
                 KSG_LAUNCHED2();
                 return KSG_OK;
             }
@@ -580,12 +580,16 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
         // The exact coordinate sorts start HERE, behind the curve path: three radix sorts side by side
         // slow each other down (every pass is latency bound and they share the SMs: measured, the curve
         // path took 2.5x as long with the coordinate sorts running beside it), whereas the k-NN kernels
-        // the caller enqueues next leave issue slots free.  Side lane 0 then remaps axis_pos.
+        // the caller enqueues next leave issue slots free.
+        // They read the set's OWN float64 copy (prepared order), not the caller's array: the caller may free
+        // or overwrite d_points as soon as this function has returned and its stream work is ordered -- the
+        // side streams are not -- and the payload is then the prepared position itself (no remap pass; ties
+        // come out in prepared order).
         for (int l = 0; l < n_side && l < dim; ++l) KSG_CUDA_TRY(cudaStreamWaitEvent(lanes->helper[l], lanes->perm_ready, 0));
         for (int d = 0; d < dim; ++d) {
             cudaStream_t ls = lanes->helper[d % n_side];
             void* lane_tmp = cub_base + (size_t)(1 + d % n_side) * L.cub_bytes;  // (area 0: the key sort on `st`)
-            const double* keys_in = d_points + (int64_t)d * ld;
+            const double* keys_in = P.sorted_f64 + (int64_t)d * L.ld;
             double* keys_out = P.axis_vals + (int64_t)d * L.ld;
             int32_t* pos_out = P.axis_pos + (int64_t)d * L.ld;
             rc = graph_cache().run(graph_key(GRAPH_AXIS_SORT, {keys_in, keys_out, iota, pos_out, lane_tmp}, {n}, {}), ls,
@@ -599,8 +603,6 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
             KSG_CUDA_TRY(cudaEventRecord(lanes->join[l], lanes->helper[l]));
             KSG_CUDA_TRY(cudaStreamWaitEvent(s0, lanes->join[l], 0));
         }
-        remap_axis_kernel<<<dim3(nb, dim), 256, 0, s0>>>(P.axis_pos, L.ld, n, invperm);
-        KSG_LAUNCHED2();
         cudaEvent_t done = lanes->axes_ready[lanes->next_axes++ % AXES_EVENTS];
         KSG_CUDA_TRY(cudaEventRecord(done, s0));
         P.axes_ready = (void*)done;
