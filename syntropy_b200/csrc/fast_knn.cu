@@ -134,9 +134,8 @@ static int launch_wunits_dp(const KnnF32Args& a) {
 }
 
 // many dimensions: 8-query groups inside the filter warps (fast_knn_group.cuh)
-template <int DP>
-static int launch_gunits_dp(const KnnF32Args& a) {
-    constexpr int ST = FastGeom<DP>::STAGES;
+template <int DP, int ST>
+static int launch_gunits_st(const KnnF32Args& a) {
     auto kern = knn_gunits_kernel<DP, ST>;
     const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float) + (size_t)a.kcap * FAST_THREADS * 8;
     if (smem > 32 * 1024) {
@@ -166,6 +165,19 @@ static int launch_gunits_dp(const KnnF32Args& a) {
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_gunits_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
     return KSG_OK;
+}
+
+// ring depth of the grouped kernel: the filter warps of a CTA do very different amounts of work per tile, a
+// deeper ring lets the fast ones run further ahead (KSG_B200_GU_STAGES=2|3|4 to compare)
+template <int DP>
+static int launch_gunits_dp(const KnnF32Args& a) {
+    static const int stages = [] { const char* e = getenv("KSG_B200_GU_STAGES"); return e ? atoi(e) : 0; }();
+    switch (stages) {
+        case 3: return launch_gunits_st<DP, 3>(a);
+        case 4: return launch_gunits_st<DP, 4>(a);
+        case 2: return launch_gunits_st<DP, 2>(a);
+        default: return launch_gunits_st<DP, FastGeom<DP>::STAGES>(a);
+    }
 }
 
 template <int DP>
