@@ -44,6 +44,19 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     return r;
 }
 
+// acc + a * b on both halves (exact here: every operand is a small integer)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
 // Mq of the query at `row` of the fp32 shadow (upper bound of max_d |x_d - centre_d|)
 __device__ __forceinline__ double query_maxabs(const float* __restrict__ shadow, int64_t row, int dim_padded) {
     float m = 0.0f;
@@ -101,6 +114,7 @@ __device__ __forceinline__ float max_range(const float* a) {
 template <int DX, int DY>
 struct SpecPair {
     static constexpr int D = DX + DY, DP = (D + 1) & ~1, S = 2;
+    static constexpr bool INDICATOR_SUM = false;
     __device__ __forceinline__ static void eval(const float* a, float* m) {
         m[0] = max_range<0, DX>(a);
         m[1] = max_range<DX, DX + DY>(a);
@@ -111,6 +125,7 @@ struct SpecPair {
 template <int DX, int DY, int DZ>
 struct SpecCmi {
     static constexpr int D = DX + DY + DZ, DP = (D + 1) & ~1, S = 3;
+    static constexpr bool INDICATOR_SUM = false;
     __device__ __forceinline__ static void eval(const float* a, float* m) {
         const float mz = max_range<DX + DY, D>(a);
         m[0] = mz;
@@ -124,9 +139,24 @@ struct SpecCmi {
 };
 
 // all D leave-one-out subspaces                               (DTC, O-, S-information)
+//
+// From 5 coordinates up the kernel shares the work between the two FP pipes (INDICATOR_SUM below; ncu on
+// C4: the D separate maxima are 14 FMNMX / FMNMX3 per pair on the half-rate ALU pipe, an all-FMA-pipe
+// variant with packed indicator sums is bound by the packed instructions, which occupy that pipe for two
+// cycles each).  With the coordinates taken in pairs h = (2h, 2h+1), p_h = max of the pair's |differences|
+// and t_h = max of the OTHER pairs' p (ALU pipe: DP/2 FMNMX + DP/2 FMNMX3), the subspace that leaves out
+// coordinate 2h has  max_{d != 2h} a_d = max(a_2h+1, t_h),  so
+//     (count_2h+1, count_2h) += (i_2h, i_2h+1) * [t_h < T],      i_d = [a_d < T]
+// -- DP + DP/2 saturating FMAs and DP/2 packed FMAs on the FMA pipe.  [max(a, t) < T] = [a < T] [t < T]:
+// the same predicate as the maxima form, evaluated by the same saturating FMA.
 template <int DD>
 struct SpecLoo {
     static constexpr int D = DD, DP = (D + 1) & ~1, S = DD;
+#ifdef KSG_LOO_MAXIMA
+    static constexpr bool INDICATOR_SUM = false;
+#else
+    static constexpr bool INDICATOR_SUM = DD >= 5;
+#endif
     __device__ __forceinline__ static void eval(const float* a, float* m) {
         if constexpr (D == 3) {
             m[0] = fmaxf(a[1], a[2]); m[1] = fmaxf(a[0], a[2]); m[2] = fmaxf(a[0], a[1]);
@@ -165,6 +195,7 @@ struct SpecLoo {
 template <int DPP>
 struct SpecMasked {
     static constexpr int D = DPP, DP = DPP, S = 4;
+    static constexpr bool INDICATOR_SUM = false;
 };
 
 struct MaskQuad {
@@ -249,6 +280,46 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
     };
     auto refresh = [&]() {};
     auto compute = [&](const float* tile, int64_t) {
+        if constexpr (Spec::INDICATOR_SUM) {
+            // acc[j][h] = sum over the tile of (i_2h, i_2h+1) * [t_h < T] = (count of subspace 2h+1, of 2h)
+            // -- see SpecLoo.  Small integers: every operation is exact.
+            constexpr int H = DP / 2;
+            float2 acc[Q][H];
+#pragma unroll
+            for (int j = 0; j < Q; ++j)
+#pragma unroll
+                for (int h = 0; h < H; ++h) acc[j][h] = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+            for (int c = 0; c < FAST_TILE; ++c) {
+                float2 cc[H];
+                load_row<DP>(tile + c * DP, cc);
+#pragma unroll
+                for (int j = 0; j < Q; ++j) {
+                    float2 ind[H];
+                    float p[H];
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        const float2 d = sub2(q[j][h], cc[h]);
+                        const float ax = fabsf(d.x), ay = fabsf(d.y);
+                        p[h] = fmaxf(ax, ay);                                             // ALU pipe
+                        ind[h] = make_float2(ind_lt(ax, sc[j]), ind_lt(ay, sc[j]));       // FMA pipe
+                    }
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        float t;  // the largest |difference| outside pair h
+                        if constexpr (H == 3) t = fmaxf(p[(h + 1) % 3], p[(h + 2) % 3]);
+                        else t = max3f(p[(h + 1) & 3], p[(h + 2) & 3], p[(h + 3) & 3]);
+                        const float it = ind_lt(t, sc[j]);
+                        acc[j][h] = fma2(ind[h], make_float2(it, it), acc[j][h]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j)
+#pragma unroll
+                for (int s = 0; s < S; ++s) cnt[j][s] += (int)((s & 1) ? acc[j][s / 2].x : acc[j][s / 2].y);
+            return;
+        } else {
         float2 acc[Q][SP];
 #pragma unroll
         for (int j = 0; j < Q; ++j)
@@ -282,6 +353,7 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
         for (int j = 0; j < Q; ++j)
 #pragma unroll
             for (int s = 0; s < S; ++s) cnt[j][s] += (int)((s & 1) ? acc[j][s / 2].y : acc[j][s / 2].x);
+        }
     };
 
     const int64_t mid = q_begin + min(qb0 + QB / 2, nq - 1);
