@@ -57,6 +57,13 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
     return r;
 }
+// sat(x + c): 0 below -c, 1 above 1 - c
+__device__ __forceinline__ float add_sat(float x, float c) {
+    float r;
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(c));
+    return r;
+}
+
 // Mq of the query at `row` of the fp32 shadow (upper bound of max_d |x_d - centre_d|)
 __device__ __forceinline__ double query_maxabs(const float* __restrict__ shadow, int64_t row, int dim_padded) {
     float m = 0.0f;
@@ -140,15 +147,18 @@ struct SpecCmi {
 
 // all D leave-one-out subspaces                               (DTC, O-, S-information)
 //
-// From 5 coordinates up the kernel shares the work between the two FP pipes (INDICATOR_SUM below; ncu on
-// C4: the D separate maxima are 14 FMNMX / FMNMX3 per pair on the half-rate ALU pipe, an all-FMA-pipe
-// variant with packed indicator sums is bound by the packed instructions, which occupy that pipe for two
-// cycles each).  With the coordinates taken in pairs h = (2h, 2h+1), p_h = max of the pair's |differences|
-// and t_h = max of the OTHER pairs' p (ALU pipe: DP/2 FMNMX + DP/2 FMNMX3), the subspace that leaves out
-// coordinate 2h has  max_{d != 2h} a_d = max(a_2h+1, t_h),  so
-//     (count_2h+1, count_2h) += (i_2h, i_2h+1) * [t_h < T],      i_d = [a_d < T]
-// -- DP + DP/2 saturating FMAs and DP/2 packed FMAs on the FMA pipe.  [max(a, t) < T] = [a < T] [t < T]:
-// the same predicate as the maxima form, evaluated by the same saturating FMA.
+// From 5 coordinates up the kernel does not form the D maxima at all (INDICATOR_SUM below).  With
+// i_d = [a_d < T] per COORDINATE (the same saturating FMA, so the same predicate: max_{d != s} a_d < T
+// <=> every i_d, d != s, is 1) and sigma = sum_d i_d,
+//     count_s += [sigma == DP] + [sigma == DP - 1] * (1 - i_s)
+// -- a candidate counts in every subspace when all coordinates are inside, and otherwise in exactly the one
+// subspace that drops its only outside coordinate.  DP FFMA.SAT, a packed add tree, two saturating adds,
+// DP/2 packed FMAs: 36 FP32 lane-operations per pair for D = 8, all on the FMA pipe.  Measured on the
+// inner loop in isolation (profiles/pipe_microbench2.cu, r2s_pipe_microbench2.txt; a 250 000-sample pass):
+// maxima form (24 FMA-pipe lane-ops + 14 FMNMX / FMNMX3) 81.0 ms, this form 70.8 ms, pair maxima on the ALU
+// pipe + 12 indicators 80.8 ms, integer sign-bit forms 85-89 ms: on sm_100a the 16-lane ALU pipe does not
+// overlap with the FMA pipe in such a loop (the times follow the SUM of both pipes' cycles, a packed
+// FADD2 / FFMA2 occupying the FMA pipe for two), so the cheapest form is the one with the fewest lane-ops.
 template <int DD>
 struct SpecLoo {
     static constexpr int D = DD, DP = (D + 1) & ~1, S = DD;
@@ -281,14 +291,16 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
     auto refresh = [&]() {};
     auto compute = [&](const float* tile, int64_t) {
         if constexpr (Spec::INDICATOR_SUM) {
-            // acc[j][h] = sum over the tile of (i_2h, i_2h+1) * [t_h < T] = (count of subspace 2h+1, of 2h)
-            // -- see SpecLoo.  Small integers: every operation is exact.
+            // acc[j][h] = sum over the tile of e * (i_2h, i_2h+1);  ae[j] = sum of ([sigma == DP], e),
+            // e = [sigma == DP - 1]  (see SpecLoo).  Small integers: every operation is exact.
             constexpr int H = DP / 2;
-            float2 acc[Q][H];
+            float2 acc[Q][H], ae[Q];
 #pragma unroll
-            for (int j = 0; j < Q; ++j)
+            for (int j = 0; j < Q; ++j) {
+                ae[j] = make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int h = 0; h < H; ++h) acc[j][h] = make_float2(0.0f, 0.0f);
+            }
 #pragma unroll 2
             for (int c = 0; c < FAST_TILE; ++c) {
                 float2 cc[H];
@@ -296,28 +308,30 @@ count_f32_kernel(const float* __restrict__ shadow, const float* __restrict__ til
 #pragma unroll
                 for (int j = 0; j < Q; ++j) {
                     float2 ind[H];
-                    float p[H];
 #pragma unroll
                     for (int h = 0; h < H; ++h) {
                         const float2 d = sub2(q[j][h], cc[h]);
-                        const float ax = fabsf(d.x), ay = fabsf(d.y);
-                        p[h] = fmaxf(ax, ay);                                             // ALU pipe
-                        ind[h] = make_float2(ind_lt(ax, sc[j]), ind_lt(ay, sc[j]));       // FMA pipe
+                        ind[h] = make_float2(ind_lt(fabsf(d.x), sc[j]), ind_lt(fabsf(d.y), sc[j]));
                     }
+                    float2 s2 = ind[0];
 #pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        float t;  // the largest |difference| outside pair h
-                        if constexpr (H == 3) t = fmaxf(p[(h + 1) % 3], p[(h + 2) % 3]);
-                        else t = max3f(p[(h + 1) & 3], p[(h + 2) & 3], p[(h + 3) & 3]);
-                        const float it = ind_lt(t, sc[j]);
-                        acc[j][h] = fma2(ind[h], make_float2(it, it), acc[j][h]);
-                    }
+                    for (int h = 1; h < H; ++h) s2 = add2(s2, ind[h]);
+                    const float sigma = s2.x + s2.y;
+                    const float all = add_sat(sigma, -(float)(DP - 1));      // [sigma == DP]
+                    const float e = add_sat(sigma, -(float)(DP - 2)) - all;  // [sigma == DP - 1]
+                    ae[j] = add2(ae[j], make_float2(all, e));
+                    const float2 ee = make_float2(e, e);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) acc[j][h] = fma2(ind[h], ee, acc[j][h]);
                 }
             }
 #pragma unroll
             for (int j = 0; j < Q; ++j)
 #pragma unroll
-                for (int s = 0; s < S; ++s) cnt[j][s] += (int)((s & 1) ? acc[j][s / 2].x : acc[j][s / 2].y);
+                for (int s = 0; s < S; ++s) {
+                    const float in_s = (s & 1) ? acc[j][s / 2].y : acc[j][s / 2].x;
+                    cnt[j][s] += (int)(ae[j].x + (ae[j].y - in_s));
+                }
             return;
         } else {
         float2 acc[Q][SP];
