@@ -19,7 +19,11 @@
  *  - `stream` is a cudaStream_t passed as void*; work is only enqueued, the caller
  *    synchronises;
  *  - there is no CPU fallback anywhere: without a CUDA device every compute entry
- *    point returns KSG_ECUDA.
+ *    point returns KSG_ECUDA;
+ *  - threading: ONE host thread per device at a time.  ksg_prepare* share per-device helper
+ *    streams, fork / join events and a graph cache; two threads (or two user streams)
+ *    preparing on the same device concurrently must be serialised by the caller.  Different
+ *    devices (one process or thread per GPU) are independent.
  */
 #ifndef KSG_B200_H
 #define KSG_B200_H

@@ -7,6 +7,7 @@ There is no CPU fallback: without a CUDA device ``require_cuda`` raises.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -267,23 +268,37 @@ def to_device_points_sharded(rows):
 
 SHARDED_UPLOAD_MIN = 1 << 16  # samples; below, the collectives cost more than the copies they save
 
-PINNED_RESULT_MAX_BYTES = 64 << 20
+PINNED_RESULT_MAX_BYTES = 64 << 20     # one result
+PINNED_RESULT_TOTAL_BYTES = 512 << 20  # all results alive at a time
+_pinned_live = 0
+
+
+def _release_pinned(nbytes: int) -> None:
+    global _pinned_live
+    _pinned_live -= nbytes
+
 
 
 def to_host(values: torch.Tensor) -> np.ndarray:
     """Device vector -> numpy array owned by the caller.
 
-    Up to 64 MiB the array is backed by a page-locked block from torch's caching host allocator
+    Up to 64 MiB (and while less than 512 MiB of such results are alive) the array is backed by a page-locked block from torch's caching host allocator
     (recycled when the array is garbage-collected): the DMA lands directly in the memory that is
     returned -- no second host copy, no first-touch page faults of a fresh allocation.  Larger
     results go through the reusable staging buffer into ordinary memory."""
+    global _pinned_live
     n = values.numel()
     nbytes = n * values.element_size()
-    if 0 < nbytes <= PINNED_RESULT_MAX_BYTES:
+    if 0 < nbytes <= PINNED_RESULT_MAX_BYTES and _pinned_live + nbytes <= PINNED_RESULT_TOTAL_BYTES:
         out_t = torch.empty(n, dtype=values.dtype, pin_memory=True)
         out_t.copy_(values.reshape(-1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return out_t.numpy()
+        out = out_t.numpy()
+        # callers that keep many results (sweeps) must not pile up page-locked memory (ADVICE r1): the bytes
+        # handed out are counted until the array dies; above the cap results land in ordinary memory
+        _pinned_live += nbytes
+        weakref.finalize(out, _release_pinned, nbytes)
+        return out
     stage = _pinned_buffer(values.device, "out", nbytes)[:nbytes].view(values.dtype)
     stage.copy_(values.reshape(-1), non_blocking=True)
     torch.cuda.current_stream().synchronize()
