@@ -153,6 +153,34 @@ int ksg_psi_epilogue(const int32_t* d_counts, int64_t nq, int n_subspaces,
                      double* d_ptw, void* stream);
 
 /*
+ * Peer-memory exchange of the sharded path (one process per GPU; SURVEY.md 8e: query rows shard, every rank
+ * needs the whole pointwise vector -- the reference has no counterpart, its ptw array simply lives in one
+ * address space, shannon.py:188-196).  The producing kernel stores its results straight into EVERY rank's
+ * buffer over NVLink (h_peer_*: host arrays of `world` device pointers, the peers' memory mapped into this
+ * process by the caller, own rank included) and releases one flag per peer when its last block is done; the
+ * consumer acquires the `world` flags of its own array.  Flags carry the epoch of the exchange (they only
+ * grow, nothing is reset); the caller double-buffers the payload by the epoch's parity.  d_ticket: one int32,
+ * 0 on entry, 0 again on exit.  No library collective, no host synchronisation.
+ *   ksg_psi_epilogue_push  ksg_psi_epilogue whose values land at [q_begin, q_begin + nq) of every rank's
+ *                          vector; *d_nflag (this rank's unsettled-query counter, may be null) goes to
+ *                          slot `rank` of every rank's aux array;
+ *   ksg_p2p_push           `bytes` of device memory to byte offset dst_offset of every rank's buffer (multiples
+ *                          of 8); several pushes of one exchange use consecutive epochs, the consumer waits for the last;
+ *   ksg_p2p_wait           returns (in stream order) once all `world` flags have reached `epoch`;
+ *                          *d_aux_sum = sum of the aux slots (every rank gets the same number).
+ */
+int ksg_psi_epilogue_push(const int32_t* d_counts, int64_t nq, int n_subspaces, const ksg_psi_step* h_steps, int n_steps,
+                          double init, double psi_n, int apply_scale, double scale, const double* d_psi_table,
+                          int64_t table_entries, void* const* h_peer_values, int64_t q_begin,
+                          const int32_t* d_nflag, int32_t* const* h_peer_aux, unsigned long long* const* h_peer_flags,
+                          int rank, int world, unsigned long long epoch, int32_t* d_ticket, void* stream);
+int ksg_p2p_push(const void* d_src, size_t bytes, void* const* h_peer_dst, size_t dst_offset,
+                 unsigned long long* const* h_peer_flags, int rank, int world, unsigned long long epoch,
+                 int32_t* d_ticket, void* stream);
+int ksg_p2p_wait(const unsigned long long* d_flags, int world, unsigned long long epoch, const int32_t* d_aux,
+                 int32_t* d_aux_sum, void* stream);
+
+/*
  * ptw[i] = 0 + ((-psi_k + psi_n) + dim * log(2 * eps[i]))   -- Kozachenko-Leonenko,
  * syntropy/knn/shannon.py:84-85.
  */

@@ -122,6 +122,13 @@ SIGNATURES = {
     "ksg_psi_finish": (C.c_int, [_c_vp, _c_i64, C.c_int, C.POINTER(PsiStep), C.c_int, C.c_double, C.c_double, C.c_int,
                                  C.c_double, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),
     "ksg_scatter_sum_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, C.c_size_t, _c_vp]),
+    "ksg_psi_epilogue_push": (C.c_int, [_c_vp, _c_i64, C.c_int, C.POINTER(PsiStep), C.c_int, C.c_double, C.c_double, C.c_int,
+                                        C.c_double, _c_vp, _c_i64, C.POINTER(C.c_void_p), _c_i64, _c_vp,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_ulonglong,
+                                        _c_vp, _c_vp]),
+    "ksg_p2p_push": (C.c_int, [_c_vp, C.c_size_t, C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(C.c_void_p), C.c_int,
+                               C.c_int, C.c_ulonglong, _c_vp, _c_vp]),
+    "ksg_p2p_wait": (C.c_int, [_c_vp, C.c_int, C.c_ulonglong, _c_vp, _c_vp, _c_vp]),
     "ksg_scatter_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_scatter_i32": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "ksg_gather_f64": (C.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),

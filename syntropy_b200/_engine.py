@@ -257,6 +257,24 @@ def to_device_points_sharded(rows):
     c = _dist.chunk_len(n, ws)
     q0, q1 = _dist.slice_of(n, rank, ws)
     local_rows = RowSelection(rows.data[:, q0:q1], rows.idxs) if q1 > q0 else None
+    ex = _dist.peer_exchange("pts", dim * ws * c * 8, dev)
+    if ex is not None:
+        # peer memory: the uploaded columns are stored straight into every rank's (D, G * c) array by a copy
+        # kernel (one launch per row, ksg_p2p_push); the consumer's stream then waits for the G flags
+        lib = _cabi.load()
+        mine = to_device_points(local_rows) if local_rows is not None else None
+        last, parity = ex.begin(pushes=dim)
+        dst = (C.c_void_p * ws)(*ex.payload_ptrs(parity))
+        flg = (C.c_void_p * ws)(*ex.flag_ptrs())
+        nbytes = (q1 - q0) * 8 if mine is not None else 0
+        for d in range(dim):
+            _cabi.check(lib.ksg_p2p_push(_ptr(mine[d]) if mine is not None else None, nbytes, dst,
+                                         (d * ws * c + rank * c) * 8, flg, rank, ws, last - dim + 1 + d, ex.my_ticket,
+                                         _stream()),
+                        "ksg_p2p_push")
+        epoch = last
+        _cabi.check(lib.ksg_p2p_wait(ex.my_flags, ws, epoch, None, None, _stream()), "ksg_p2p_wait")
+        return ex.payload(parity, torch.float64)[: dim * ws * c].view(dim, ws * c)[:, :n]
     local = torch.zeros((dim, c), dtype=torch.float64, device=dev)
     if local_rows is not None:
         local[:, : q1 - q0].copy_(to_device_points(local_rows))
@@ -728,9 +746,14 @@ def _use_fast(dim: int, kprime: int = 1) -> bool:
 def check_finite(points: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """flag (int32[1], or ``out``: only ever set, never cleared) = 1 if any entry is NaN or infinite."""
     flag = torch.zeros(1, dtype=torch.int32, device=points.device) if out is None else out
-    assert points.is_contiguous()
-    rc = _cabi.load().ksg_check_finite(_ptr(points), points.numel(), _ptr(flag), _stream())
-    _cabi.check(rc, "ksg_check_finite")
+    lib = _cabi.load()
+    if points.is_contiguous():
+        _cabi.check(lib.ksg_check_finite(_ptr(points), points.numel(), _ptr(flag), _stream()), "ksg_check_finite")
+        return flag
+    # (a (D, n) view of an assembled, padded array: rows with unit column stride)
+    assert points.dim() == 2 and points.stride(1) == 1
+    for d in range(points.shape[0]):
+        _cabi.check(lib.ksg_check_finite(_ptr(points[d]), points.shape[1], _ptr(flag), _stream()), "ksg_check_finite")
     return flag
 
 
@@ -764,9 +787,13 @@ class Pointwise:
     ``Status.nflag`` they were computed under reads 0; otherwise ``redo()`` returns the settled
     Pointwise."""
 
-    def __init__(self, values, prep=None, full=False, preps=(), redo=None, summed=False):
+    def __init__(self, values, prep=None, full=False, preps=(), redo=None, summed=False, pushed=None):
         self.values, self.prep, self.full, self.preps, self.redo = values, prep, full, list(preps), redo
         self.summed = summed  # full values whose sum already sits in the Status block (fused tail launch)
+        # (exchange, epoch, parity): the slices of ALL ranks are being stored into this rank's peer-memory
+        # vector by the ranks' psi kernels (ksg_psi_epilogue_push); `values` is unused then
+        self.pushed = pushed
+        self.flags_summed = False  # Status.nflag already holds the sum over the ranks (ksg_p2p_wait)
 
     def pairs_evaluated(self):
         a = b = 0
@@ -788,12 +815,20 @@ def finish_device(pw: Pointwise, n_total: int, out: torch.Tensor | None = None, 
         if pw.summed and status is not None:
             return pw.values, out
         ptw_full = pw.values
+    elif pw.pushed is not None and status is not None:
+        # peer-memory exchange: wait for the G flags (folding the ranks' unsettled-query counters into
+        # status.nflag), then sample order + sum -- two launches, no library collective, no host sync
+        ex, epoch, parity = pw.pushed
+        gathered = ex.payload(parity, torch.float64)[:n_total]
+        pw.flags_summed = True
+        return _text.load().finish_step(gathered, pw.prep.struct_bytes, out, ticket, ex.my_flags, ex.world, epoch,
+                                        ex.my_aux(parity), status.nflag), out
     else:
         ptw_full = _dist.gather_slices(pw.values, n_total)
         if pw.prep is not None:
             if out is not None and _text.enabled() and getattr(pw.prep, "struct_bytes", None) is not None:
                 # scatter + sum, one call (one launch with a ticket)
-                return _text.load().finish_step(ptw_full, pw.prep.struct_bytes, out, ticket), out
+                return _text.load().finish_step(ptw_full, pw.prep.struct_bytes, out, ticket, 0, 0, 0, 0, None), out
             ptw_full = scatter_to_original(ptw_full, pw.prep)
     return ptw_full, device_sum(ptw_full, out=out)
 
@@ -804,7 +839,8 @@ def settle(pw: Pointwise, n_total: int, status: Status, ptw_full: torch.Tensor, 
     Returns the final ``(pw, ptw_full, total)``."""
     if pw.redo is None:
         return pw, ptw_full, total
-    _dist.sum_counts(status.nflag)  # unsettled queries of ALL ranks: every rank takes the same branch
+    if not pw.flags_summed:
+        _dist.sum_counts(status.nflag)  # unsettled queries of ALL ranks: every rank takes the same branch
     host = status.read_async()
     torch.cuda.current_stream().synchronize()
     if int(host[3]) == 0:
@@ -818,7 +854,7 @@ def settle(pw: Pointwise, n_total: int, status: Status, ptw_full: torch.Tensor, 
 def _finish(pw: Pointwise, n_total: int, status: Status):
     """Gather the pointwise slices of all ranks, reduce deterministically, copy out."""
     ptw_full, _ = finish_device(pw, n_total, status=status)
-    if pw.redo is not None:
+    if pw.redo is not None and not pw.flags_summed:
         _dist.sum_counts(status.nflag)  # unsettled queries of ALL ranks: every rank takes the same branch
     host = status.read_async()
     ptw = to_host(ptw_full)  # synchronises the stream: the status block has landed too
@@ -977,11 +1013,20 @@ def _ksg1_step_ext(pts, k, masks, prog: PsiProgram, n, q0, q1, windowed, row_rea
         primary = -3
     # one rank owns every query: psi program, sample order and the sum are ONE launch (ksg_psi_finish)
     fused_tail = q0 == 0 and q1 == n and n > 0 and config.fused_tail
+    # several ranks: the psi kernel pushes its slice into every rank's vector over NVLink (csrc/p2p.cuh)
+    rank, ws = _dist.world()
+    ex = _dist.peer_exchange("ptw", ws * _dist.chunk_len(n, ws) * 8, pts.device) if ws > 1 and n > 0 else None
+    pushed = None
+    p2p_args = ([], [], [], 0, 0, 0)
+    if ex is not None:
+        epoch, parity = ex.begin()
+        pushed = (ex, epoch, parity)
+        p2p_args = (ex.payload_ptrs(parity), ex.aux_ptrs(parity), ex.flag_ptrs(), rank, epoch, ex.my_ticket)
     ptw, prep_buf, prep_struct, eps, flags, _counts = ext.ksg1_step(
         pts, k, axes, prog.init, prog.psi_n, prog.scale is not None, 0.0 if prog.scale is None else prog.scale,
         [st[0] for st in steps], [st[1] for st in steps], [st[2] for st in steps], [st[3] for st in steps],
         [st[4] for st in steps], table, q0, q1, windowed, primary, default_margin(windowed, k + 1, dim),
-        status.nflag, ready, status.total if fused_tail else None, status.ticket if fused_tail else None)
+        status.nflag, ready, status.total if fused_tail else None, status.ticket if fused_tail else None, *p2p_args)
     prep = PreparedSet.from_raw(prep_buf, prep_struct)
 
     def redo():
@@ -991,7 +1036,7 @@ def _ksg1_step_ext(pts, k, masks, prog: PsiProgram, n, q0, q1, windowed, row_rea
 
     if fused_tail:
         return Pointwise(ptw, full=True, preps=[prep], redo=redo, summed=True)
-    return Pointwise(ptw, prep=prep, preps=[prep], redo=redo)
+    return Pointwise(ptw, prep=prep, preps=[prep], redo=redo, pushed=pushed)
 
 
 def ksg2_family(rows, k: int, masks, prog_builder):

@@ -392,7 +392,7 @@ static FastKnnPlan fast_knn_plan(int64_t n, int64_t nq, int dim, int kprime, int
         p.first_bytes = align_up((size_t)2 * (p.qblocks + 1) * sizeof(int32_t), 256);  // starts + counts
         p.ublock_bytes = align_up((size_t)p.max_units * sizeof(int32_t), 256);
         p.meta_bytes = 256;
-        p.done_bytes = align_up((size_t)p.qblocks * sizeof(int32_t), 256);
+        p.done_bytes = align_up((size_t)4 * p.qblocks * sizeof(int32_t), 256);  // (four counters per block)
     } else {
         // partial lists per candidate split: [split][rank][nq]
         p.splits = choose_splits(p.qblocks, n, FAST_TILE);

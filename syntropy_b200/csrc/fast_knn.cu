@@ -70,8 +70,11 @@ static int launch_plan_kc(const KnnF32Args& a) {
     note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_plan_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
+    // KSG_B200_UNIT_TILES (experiments): shortest unit, in tiles
+    static const int min_tiles_env = [] { const char* e = getenv("KSG_B200_UNIT_TILES"); return e ? atoi(e) : 0; }();
     knn_unit_table_kernel<<<1, 1024, 0, a.st>>>(a.plan_count, ceil_div(a.nq, FAST_THREADS * Q), a.max_units,
-                                                 KNN_UNIT_MIN_TILES, a.unit_first, a.unit_block, a.unit_meta);
+                                                 min_tiles_env > 0 ? min_tiles_env : KNN_UNIT_MIN_TILES, a.unit_first,
+                                                 a.unit_block, a.unit_meta);
     note_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("knn_unit_table_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }

@@ -167,7 +167,9 @@ knn_plan_kernel(const float* __restrict__ shadow, const float* __restrict__ tile
     const int64_t qb0 = (int64_t)blockIdx.x * QB;
     (void)maxabs; (void)dim;
     const int64_t n_rows = n_tiles * FAST_TILE;
-    if (tid == 0 && unit_done) unit_done[blockIdx.x] = 0;  // finished work units of this block (knn_units_kernel)
+    // finished work units of this block: [0] for the CTA-level kernels, one counter per 32-query quarter for
+    // the warp-level kernel
+    if (tid < 4 && unit_done) unit_done[4 * blockIdx.x + tid] = 0;
 
     // ---- pass 1: seed every query's threshold from its neighbours in the prepared order
     float blo[DP], bhi[DP];
@@ -1043,7 +1045,7 @@ knn_units_kernel(const float* __restrict__ shadow, const float* __restrict__ sub
             // bumped once per unit, and the CTA that brings it to nunits reads everybody's lists
             __threadfence();
             filter_warps_barrier();
-            if (tid == 0) s_last = atomicAdd(&unit_done[qblock], 1) == nunits - 1;
+            if (tid == 0) s_last = atomicAdd(&unit_done[4 * qblock], 1) == nunits - 1;
             filter_warps_barrier();
             if (s_last) {
                 __threadfence();

@@ -334,7 +334,7 @@ knn_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ ti
         if (ra.fused && !refine_here) {
             __threadfence();
             filter_warps_barrier();
-            if (tid == 0) s_last = atomicAdd(&unit_done[qblock], 1) == nunits - 1;
+            if (tid == 0) s_last = atomicAdd(&unit_done[4 * qblock], 1) == nunits - 1;
             filter_warps_barrier();
             if (s_last) {
                 __threadfence();

@@ -18,7 +18,8 @@
 //      already in flight while the current one is scanned from shared memory (LDS.128 broadcasts),
 //   4. keeps the per-query lists exactly as knn_units_kernel does and ends the same way: single-unit
 //      blocks are refined from shared memory, units of longer lists emit partial lists and the warp
-//      that finishes a block's LAST item merges them (unit_done counts items, 4 per unit).
+//      that finishes the LAST item of a (block, quarter) merges that quarter's 32 queries (unit_done: four
+//      counters per block).
 // Same planning pass, unit table, list format and refine functions; results are identical.
 // Sets of 5 to 8 coordinates keep knn_units_kernel: there a warp scans a large share of every staged
 // tile and four warps sharing one staged copy is what keeps the L2 traffic down.
@@ -384,22 +385,21 @@ knn_wunits_kernel(const float* __restrict__ shadow, const float* __restrict__ su
             part_idx[o] = col_i[r * 32];
         }
         if (ra.fused) {
-            // last-item-done merge: the lists above are published (fence), the block's counter is bumped
-            // once per item, and the warp that brings it to 4 * nunits merges all of the block's queries
+            // last-item-done merge, PER QUARTER: the lists above are published (fence), the counter of this
+            // (block, quarter) is bumped once per item, and the warp that brings it to nunits merges the 32
+            // queries of the quarter -- the four merges of a heavy block run side by side instead of one warp
+            // walking all 128 queries after the block's very last item (that merge alone was 60-80 us of a
+            // 221 us launch when a rank owns 1/8 of C2's queries: per-item trace)
             __threadfence();
             __syncwarp();
             int is_last = 0;
-            if (lane == 0) is_last = atomicAdd(&unit_done[qblock], 1) == 4 * nunits - 1;
+            if (lane == 0) is_last = atomicAdd(&unit_done[4 * qblock + quarter], 1) == nunits - 1;
             is_last = __shfl_sync(FULL, is_last, 0);
             if (is_last) {
                 __threadfence();
-#pragma unroll 1
-                for (int j = 0; j < QB / 32; ++j) {
-                    const int l2 = j * 32 + lane;
-                    if (qb0 + l2 < nq)
-                        refine_merge_lists(part_d32, part_idx, kcap, ufirst, ufirst + nunits, QB, l2, true,
-                                           seed_thr[qb0 + l2], q_begin + qb0 + l2, qb0 + l2, ra);
-                }
+                if (alive)
+                    refine_merge_lists(part_d32, part_idx, kcap, ufirst, ufirst + nunits, QB, lq, true, seed_thr[qi],
+                                       q_begin + qi, qi, ra);
             }
         }
     }

@@ -9,6 +9,7 @@
 #include "exact_f64.cuh"
 #include "fast_launch.h"
 #include "minkowski_f64.cuh"
+#include "p2p.cuh"
 
 namespace ksg {
 
@@ -368,6 +369,72 @@ int ksg_scatter_sum_f64(const double* d_values_sorted, const int32_t* d_perm, in
     finish_kernel<false><<<SUM_BLOCKS, SUM_THREADS, 0, as_stream(stream)>>>(nullptr, d_values_sorted, n, prog, nullptr, 0,
                                                                            d_perm, d_out, (double*)d_workspace,
                                                                            d_ticket, d_total);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+// ---- peer-memory exchange of the sharded path (csrc/p2p.cuh)
+static int fill_peer_list(PeerList& peers, void* const* h_peer_payload, unsigned long long* const* h_peer_flags,
+                          int32_t* const* h_peer_aux, int rank, int world) {
+    KSG_REQUIRE(h_peer_payload && h_peer_flags, "peer list: null pointer");
+    KSG_REQUIRE(world >= 1 && world <= P2P_MAX_RANKS && rank >= 0 && rank < world, "peer list: bad rank / world size");
+    memset(&peers, 0, sizeof(peers));
+    peers.world = world;
+    peers.rank = rank;
+    for (int r = 0; r < world; ++r) {
+        KSG_REQUIRE(h_peer_payload[r] && h_peer_flags[r], "peer list: null peer pointer");
+        peers.payload[r] = h_peer_payload[r];
+        peers.flags[r] = h_peer_flags[r];
+        peers.aux[r] = h_peer_aux ? h_peer_aux[r] : nullptr;
+    }
+    return KSG_OK;
+}
+
+int ksg_psi_epilogue_push(const int32_t* d_counts, int64_t nq, int n_subspaces, const ksg_psi_step* h_steps, int n_steps,
+                          double init, double psi_n, int apply_scale, double scale, const double* d_psi_table,
+                          int64_t table_entries, void* const* h_peer_values, int64_t q_begin,
+                          const int32_t* d_nflag, int32_t* const* h_peer_aux, unsigned long long* const* h_peer_flags,
+                          int rank, int world, unsigned long long epoch, int32_t* d_ticket, void* stream) {
+    KSG_REQUIRE(d_psi_table && d_ticket && h_steps, "ksg_psi_epilogue_push: null pointer");
+    KSG_REQUIRE(nq >= 0 && q_begin >= 0 && table_entries >= 1 && (nq == 0 || d_counts), "ksg_psi_epilogue_push: bad sizes");
+    PsiProgram prog;
+    int rc = fill_psi_program(prog, n_subspaces, h_steps, n_steps, init, psi_n, apply_scale, scale);
+    if (rc) return rc;
+    PeerList peers;
+    rc = fill_peer_list(peers, h_peer_values, h_peer_flags, h_peer_aux, rank, world);
+    if (rc) return rc;
+    // (a rank with an empty slice still publishes its flags: one block)
+    int64_t nb = nq > 0 ? ceil_div(nq, 256 * 4) : 1;
+    if (nb > 148 * 4) nb = 148 * 4;
+    const unsigned blocks = (unsigned)nb;
+    psi_push_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_counts, nq, prog, d_psi_table, table_entries, peers, q_begin,
+                                                           d_nflag, epoch, d_ticket);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_p2p_push(const void* d_src, size_t bytes, void* const* h_peer_dst, size_t dst_offset,
+                 unsigned long long* const* h_peer_flags, int rank, int world, unsigned long long epoch,
+                 int32_t* d_ticket, void* stream) {
+    KSG_REQUIRE(d_ticket && (bytes == 0 || d_src), "ksg_p2p_push: null pointer");
+    KSG_REQUIRE(bytes % 8 == 0 && dst_offset % 8 == 0 && ((uintptr_t)d_src % 8) == 0,
+                "ksg_p2p_push: sizes, offsets and pointers must be multiples of 8 bytes");
+    PeerList peers;
+    const int rc = fill_peer_list(peers, h_peer_dst, h_peer_flags, nullptr, rank, world);
+    if (rc) return rc;
+    const int64_t n8 = (int64_t)(bytes / 8);
+    int64_t blocks = ceil_div(n8 > 0 ? n8 : 1, 256 * 4);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    p2p_push_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const uint2*)d_src, n8, peers, (int64_t)dst_offset,
+                                                                     epoch, d_ticket);
+    KSG_LAUNCHED();
+    return KSG_OK;
+}
+
+int ksg_p2p_wait(const unsigned long long* d_flags, int world, unsigned long long epoch, const int32_t* d_aux,
+                 int32_t* d_aux_sum, void* stream) {
+    KSG_REQUIRE(d_flags && world >= 1 && world <= P2P_MAX_RANKS, "ksg_p2p_wait: bad argument");
+    p2p_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(d_flags, world, epoch, d_aux, d_aux_sum);
     KSG_LAUNCHED();
     return KSG_OK;
 }

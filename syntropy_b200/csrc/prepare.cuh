@@ -15,6 +15,8 @@
 //     of candidates whose coordinate difference is within the band of the radius.
 #pragma once
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sample_sort.cuh"
 
@@ -660,12 +662,29 @@ bucket_scatter_kernel(const double* __restrict__ pts, int64_t ld_in, int64_t n, 
 // coordinate a rank slice holds <= 16 points, so even when the coordinates are functions of each
 // other (all points of a slice in ONE cell) a cell is smaller than a 32-row sub-tile; everything
 // finer would only lengthen the key sort (one radix pass per 8 bits of dim * b).
+// KSG_B200_KEY_BITS (read once): cap on the TOTAL width of a curve key.  The key sort is latency-bound radix
+// passes of 8 bits each; a coarser curve (ties keep their input order: the sort is stable) trades passes
+// against slightly wider sub-tile boxes.  Any order gives the same radii and counts.
+static inline int curve_key_bits_cap() {
+    static const int cap = [] {
+        const char* e = getenv("KSG_B200_KEY_BITS");
+        return e ? atoi(e) : 0;
+    }();
+    return cap;
+}
 static inline void curve_bits(int64_t n, int dim, int* rank_bits, int* bits) {
     int rb = 1;
     while ((1ll << rb) < n) ++rb;
     int b = 63 / dim;
     const int need = rb > 5 ? rb - 4 : 1;
     if (b > need) b = need;
+    // Scalar pairs (the headline step): 16x as many curve cells as points is enough -- at n = 1e6 a 24-bit key
+    // (three radix passes) against 32 bits (four) costs 0.9 % more evaluated pairs and saves 22 us of the
+    // 225 us prepare (profiles/r2t_key_bits.txt); 20 bits: +15 % pairs.  More coordinates keep the full width
+    // (prepare is negligible against their pair work, and coarse cells hurt where the points are dense).
+    int cap = curve_key_bits_cap();
+    if (cap <= 0 && dim <= 2) cap = rb + 4 > 24 ? rb + 4 : 24;
+    if (cap > 0 && b * dim > cap) b = cap / dim > 1 ? cap / dim : 1;
     *rank_bits = rb;
     *bits = b;
 }

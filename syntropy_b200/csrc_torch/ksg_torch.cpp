@@ -97,7 +97,9 @@ std::vector<at::Tensor> ksg1_step(at::Tensor pts, int64_t k, std::vector<int64_t
                                   std::vector<int64_t> step_centered, std::vector<double> step_div,
                                   at::Tensor psi_table, int64_t q0, int64_t q1, bool windowed, int64_t primary,
                                   int64_t margin, at::Tensor nflag, std::vector<int64_t> row_ready,
-                                  c10::optional<at::Tensor> total, c10::optional<at::Tensor> ticket) {
+                                  c10::optional<at::Tensor> total, c10::optional<at::Tensor> ticket,
+                                  std::vector<int64_t> peer_values, std::vector<int64_t> peer_aux,
+                                  std::vector<int64_t> peer_flags, int64_t rank, int64_t epoch, int64_t p2p_ticket) {
     TORCH_CHECK(pts.is_cuda() && pts.scalar_type() == at::kDouble && pts.dim() == 2 && pts.stride(1) == 1,
                 "pts must be a (D, n) float64 CUDA tensor with unit column stride");
     c10::cuda::CUDAGuard guard(pts.device());
@@ -173,23 +175,68 @@ std::vector<at::Tensor> ksg1_step(at::Tensor pts, int64_t k, std::vector<int64_t
                   "ksg_psi_finish");
             return {ptw, prep_buf, prep_struct, eps, flags, counts};
         }
+        if (!peer_values.empty()) {
+            // several ranks: the psi kernel stores this rank's slice straight into EVERY rank's vector over
+            // NVLink and publishes the unsettled-query counter with it (no library collective in the step)
+            const int world = (int)peer_values.size();
+            std::vector<void*> pv(world), pa(world);
+            std::vector<unsigned long long*> pf(world);
+            for (int r = 0; r < world; ++r) {
+                pv[r] = (void*)(intptr_t)peer_values[r];
+                pa[r] = (void*)(intptr_t)peer_aux[r];
+                pf[r] = (unsigned long long*)(intptr_t)peer_flags[r];
+            }
+            Scope s("psi_push", st);
+            check(ksg_psi_epilogue_push(counts.data_ptr<int32_t>(), nq, (int)axes.size(), steps.data(), (int)step_sub.size(),
+                                        init, psi_n, apply_scale ? 1 : 0, scale, psi_table.data_ptr<double>(),
+                                        psi_table.numel(), pv.data(), q0, nflag.data_ptr<int32_t>(), (int32_t* const*)pa.data(),
+                                        pf.data(), (int)rank, world, (unsigned long long)epoch,
+                                        (int32_t*)(intptr_t)p2p_ticket, st),
+                  "ksg_psi_epilogue_push");
+            return {ptw, prep_buf, prep_struct, eps, flags, counts};
+        }
         Scope s("psi_epilogue", st);
         check(ksg_psi_epilogue(counts.data_ptr<int32_t>(), nq, (int)axes.size(), steps.data(), (int)step_sub.size(), init,
                                psi_n, apply_scale ? 1 : 0, scale, psi_table.data_ptr<double>(), psi_table.numel(),
                                ptw.data_ptr<double>(), st),
               "ksg_psi_epilogue");
+    } else if (!peer_values.empty()) {
+        // an empty slice still has to publish its flags (the peers wait for every rank)
+        const int world = (int)peer_values.size();
+        std::vector<void*> pv(world), pa(world);
+        std::vector<unsigned long long*> pf(world);
+        for (int r = 0; r < world; ++r) {
+            pv[r] = (void*)(intptr_t)peer_values[r];
+            pa[r] = (void*)(intptr_t)peer_aux[r];
+            pf[r] = (unsigned long long*)(intptr_t)peer_flags[r];
+        }
+        ksg_psi_step none{};
+        check(ksg_psi_epilogue_push(nullptr, 0, (int)axes.size(), &none, 0, init, psi_n, 0, scale,
+                                    psi_table.data_ptr<double>(), psi_table.numel(), pv.data(), q0,
+                                    nflag.data_ptr<int32_t>(), (int32_t* const*)pa.data(), pf.data(), (int)rank, world,
+                                    (unsigned long long)epoch, (int32_t*)(intptr_t)p2p_ticket, st),
+              "ksg_psi_epilogue_push");
     }
     return {ptw, prep_buf, prep_struct, eps, flags, counts};
 }
 
 // full pointwise vector (prepared order) -> caller's sample order + fixed-order sum into `total`
+// (wait_flags != 0: values_sorted is this rank's peer-written vector -- first acquire the `world` flags of
+//  exchange `epoch` and fold the ranks' unsettled-query counters into *nflag, see ksg_p2p_wait)
 at::Tensor finish_step(at::Tensor values_sorted, at::Tensor prep_struct, at::Tensor total,
-                       c10::optional<at::Tensor> ticket) {
+                       c10::optional<at::Tensor> ticket, int64_t wait_flags, int64_t world, int64_t epoch,
+                       int64_t wait_aux, c10::optional<at::Tensor> nflag) {
     c10::cuda::CUDAGuard guard(values_sorted.device());
     ksg_prepared P;
     std::memcpy(&P, prep_struct.data_ptr(), sizeof(P));
     const int64_t n = values_sorted.numel();
     void* st = stream_of(values_sorted);
+    if (wait_flags != 0) {
+        Scope s("p2p_wait", st);
+        check(ksg_p2p_wait((const unsigned long long*)(intptr_t)wait_flags, (int)world, (unsigned long long)epoch,
+                           (const int32_t*)(intptr_t)wait_aux, nflag.has_value() ? nflag->data_ptr<int32_t>() : nullptr, st),
+              "ksg_p2p_wait");
+    }
     at::Tensor out = at::empty_like(values_sorted);
     if (ticket.has_value()) {  // scatter + both stages of the sum in one launch
         const size_t fin_bytes = ksg_finish_workspace(n);

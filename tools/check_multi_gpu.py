@@ -26,6 +26,12 @@ def main():
     cases = []
     d, c = workloads.c1_readme_mi(n=20_011, seed=1)
     cases.append(("mi 1D;1D", lambda: knn.mutual_information(c["idxs_x"], c["idxs_y"], c["k"], d)))
+    # above the sharded-upload threshold, odd chunk length (peer-memory upload + psi push: csrc/p2p.cuh)
+    dl, cl = workloads.c1_readme_mi(n=200_003, seed=11)
+    cases.append(("mi 1D;1D n=200003 (sharded upload)", lambda: knn.mutual_information(cl["idxs_x"], cl["idxs_y"], cl["k"], dl)))
+    # decimal-quantised data: the speculative step flags queries on every rank -> collective redo
+    dq = np.round(dl[:, :70_001] / 0.03) * 0.03
+    cases.append(("mi 1D;1D, multiples of 0.03 (collective redo)", lambda: knn.mutual_information(cl["idxs_x"], cl["idxs_y"], cl["k"], dq)))
     d3, c3 = workloads.c3_cmi(n=30_007, seed=2)
     cases.append(("cmi 2D;2D|2D (own-order marginals)", lambda: knn.conditional_mutual_information(
         c3["idxs_x"], c3["idxs_y"], c3["idxs_z"], c3["k"], d3)))
