@@ -25,6 +25,8 @@ def _worker(rank, world_size, port, n, out_dir):
 
         data, call = workloads.c1_readme_mi(n=n, seed=3)
         assert dist.world() == (rank, world_size)
+        # the peer-memory exchange needs NCCL ranks with CUDA devices: on gloo the collectives stay
+        assert dist.peer_exchange("ptw", 8 * n, torch.device("cpu")) is None
         q0, q1 = dist.my_slice(n)
         # stand-in for K1 -> K2 -> K3 on this rank's query rows
         eps = orc.knn_radius(data, 6, queries=data[:, q0:q1])  # k+1: self is a candidate
@@ -67,3 +69,31 @@ def test_two_rank_gather_matches_unsharded(tmp_path, n):
         got = np.load(tmp_path / f"ptw_{rank}.npy")
         assert np.array_equal(got, ref)
         assert list(np.load(tmp_path / f"cnt_{rank}.npy")) == [n, 2 * n]
+
+
+def test_peer_exchange_layout():
+    """Pointer arithmetic of dist.PeerExchange (control block, two payload parities, epochs of multi-push
+    exchanges) without any device: the layout the kernels of csrc/p2p.cuh are handed."""
+    from syntropy_b200 import dist
+
+    ex = dist.PeerExchange.__new__(dist.PeerExchange)  # (no allocation: fields filled by hand)
+    ex.payload_bytes, ex.ptrs, ex.rank, ex.world, ex.epoch, ex.round = 4096, [0x10000, 0x90000, 0x110000], 1, 3, 0, 0
+    assert ex.flag_ptrs() == ex.ptrs and ex.my_flags == 0x90000
+    assert ex.aux_ptrs(0) == [p + 256 for p in ex.ptrs] and ex.aux_ptrs(1) == [p + 320 for p in ex.ptrs]
+    assert ex.my_aux(1) == 0x90000 + 320 and ex.my_ticket == 0x90000 + 512
+    assert ex.payload_ptrs(0) == [p + 4096 for p in ex.ptrs] and ex.payload_ptrs(1) == [p + 8192 for p in ex.ptrs]
+    # flags (16 x 8 B), aux (2 x 16 x 4 B) and the ticket do not overlap and stay inside the control block
+    assert 16 * 8 <= dist.PeerExchange.AUX_OFF and dist.PeerExchange.AUX_OFF + 2 * 64 <= dist.PeerExchange.TICKET_OFF
+    assert dist.PeerExchange.TICKET_OFF + 4 <= dist.PeerExchange.CTRL
+    # one push per exchange: epochs 1, 2, 3 ... with alternating parity
+    assert [ex.begin() for _ in range(3)] == [(1, 1), (2, 0), (3, 1)]
+    # a two-row upload publishes epochs last - 1 and last; the parity still alternates per EXCHANGE
+    assert ex.begin(pushes=2) == (5, 0) and ex.begin(pushes=2) == (7, 1)
+
+
+def test_peer_exchange_is_off_without_a_process_group(monkeypatch):
+    from syntropy_b200 import dist
+
+    assert dist.world() == (0, 1)
+    assert dist.peer_exchange("ptw", 1024, torch.device("cpu")) is None
+
