@@ -14,6 +14,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <torch/extension.h>
 
 #include <cstring>
@@ -55,11 +56,14 @@ cudaEvent_t take_event() {
     return e;
 }
 
+// (every stage is also an NVTX range -- prepare / fast_knn / axis_count / psi_* / p2p_wait / scatter_sum -- so a
+//  timeline tool shows the step's structure; a push / pop without a tool attached costs nanoseconds)
 struct Scope {
     bool on;
     size_t at = 0;
     cudaStream_t st;
     Scope(const char* name, void* stream) : on(g_timing), st((cudaStream_t)stream) {
+        nvtxRangePushA(name);
         if (!on) return;
         g_spans.push_back(Span{name, take_event(), take_event()});
         at = g_spans.size() - 1;
@@ -67,6 +71,7 @@ struct Scope {
     }
     ~Scope() {
         if (on) cudaEventRecord(g_spans[at].b, st);
+        nvtxRangePop();
     }
 };
 
