@@ -51,7 +51,10 @@ static int plan_seed_width(int dp) {
         return e ? atoi(e) : 0;
     }();
     if (forced > 0) return forced;
-    return dp <= 4 ? KNN_SEED_W : 4 * KNN_SEED_W;
+    // 6-D / 8-D: +-24 rows of the curve are a poor sample of a query's neighbourhood (seed / true radius 1.5); the
+    // sweep (profiles/r2ab_seed_window.txt) has C3 k-NN 42.2 -> 30.1 ms, C5 699 -> 603 ms, C4 25.6 -> 23.4 ms going
+    // from +-96 to +-768 rows, flat beyond (the planning pass then costs what the tighter seeds save)
+    return dp <= 4 ? KNN_SEED_W : 32 * KNN_SEED_W;
 }
 
 template <int DP, int KC>
