@@ -1,6 +1,6 @@
 // Single-subspace windowed count pass: instantiations (DP = 2, 4, 6, 8) and launcher.
 #include "fast_count_launch.cuh"
-#include "fast_count_units.cuh"
+#include "fast_count_group.cuh"
 
 namespace ksg {
 

@@ -304,36 +304,4 @@ count_units_kernel(const float* __restrict__ shadow, const float* __restrict__ s
         atomicAdd(pair_counter, scans_total * (unsigned long long)(FAST_SUB * 32 * Q));
 }
 
-template <int DP>
-static int launch_count_full_dp(const CountF32Args& a, const CountUnitsArgs& w) {
-    constexpr int Q = COUNT_UNITS_Q, ST = FastGeom<DP>::STAGES;
-    const int64_t qblocks = ceil_div(a.nq, FAST_THREADS * Q);
-    if (cudaMemsetAsync(w.unit_meta, 0, 32, a.st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return KSG_ECUDA; }
-    count_plan_kernel<DP, Q><<<(unsigned)qblocks, FAST_THREADS, 0, a.st>>>(
-        a.shadow, a.tile_box, a.n_tiles, a.q_begin, a.nq, a.thresholds, (int2*)w.plan, w.plan_capacity, w.plan_count,
-        w.plan_first, w.unit_meta, a.counts);
-    note_launch();
-    knn_unit_table_kernel<<<1, 1024, 0, a.st>>>(w.plan_count, qblocks, w.max_units, COUNT_UNIT_MIN_TILES, w.unit_first,
-                                                 w.unit_block, w.unit_meta);
-    note_launch();
-    auto kern = count_units_kernel<DP, Q, ST>;
-    const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float);
-    if (smem > 32 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
-    }
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, UNITS_THREADS, smem);
-    if (e != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
-    int64_t grid = (int64_t)per_sm * sm_count();
-    if (grid > w.max_units) grid = w.max_units;
-    kern<<<(unsigned)grid, UNITS_THREADS, smem, a.st>>>(a.shadow, w.sub_box, a.n_tiles, a.q_begin, a.nq, a.thresholds,
-                                                       (const int2*)w.plan, w.plan_count, w.plan_first, w.unit_first,
-                                                       w.unit_block, w.unit_meta, a.counts, a.tile_counter);
-    note_launch();
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("count_units_kernel launch: %s", cudaGetErrorString(e)); return KSG_ECUDA; }
-    return KSG_OK;
-}
-
 }  // namespace ksg
