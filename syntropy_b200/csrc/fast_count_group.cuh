@@ -27,9 +27,7 @@
 
 namespace ksg {
 
-constexpr int CG_GROUPS = 4, CG_GQ = 8;
-
-template <int DP, int STAGES>
+template <int DP, int STAGES, int CG_GROUPS>
 static __global__ void __launch_bounds__(UNITS_THREADS)
 count_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ sub_box, int64_t n_tiles,
                     int64_t q_begin, int64_t nq, const float* __restrict__ thresholds,
@@ -38,6 +36,8 @@ count_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ 
                     const int32_t* __restrict__ unit_block, int32_t* __restrict__ meta,
                     int32_t* __restrict__ counts, unsigned long long* __restrict__ pair_counter) {
     static_assert(FAST_THREADS == 128 && FAST_NSUB == 16 && FAST_SUB == 32, "geometry of the lane / group mapping");
+    static_assert(CG_GROUPS == 4 || CG_GROUPS == 8, "four groups of 8 queries or eight groups of 4");
+    constexpr int CG_GQ = 32 / CG_GROUPS;  // queries per group = lanes per candidate stream
     constexpr int QB = FAST_THREADS;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int TILE_FLOATS = FAST_TILE * DP;
@@ -52,7 +52,7 @@ count_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ 
     __shared__ float2 s_gthr[FAST_THREADS / 32][CG_GROUPS];      // (smallest, largest) threshold of the group
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int strm = lane >> 3, mem = lane & 7;
+    const int strm = lane / CG_GQ, mem = lane % CG_GQ;
     const bool producer = warp == FAST_THREADS / 32;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -152,12 +152,12 @@ count_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ 
             if (t >= 0) {
                 const float* tile = tiles + (size_t)slot * SLOT_FLOATS;
                 const float2* boxes = reinterpret_cast<const float2*>(tile + TILE_FLOATS);
-                // ---- classify 16 sub-tiles x 4 groups: lane = (half, sub-tile), groups 2 * half + {0, 1}
+                // ---- classify 16 sub-tiles x CG_GROUPS groups: lane = (half, sub-tile), groups half * CG_GROUPS / 2 + k
                 unsigned scan_m[CG_GROUPS], in_m[CG_GROUPS];
                 const int sb_l = lane & 15, half = lane >> 4;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int g = 2 * half + k;
+                for (int k = 0; k < CG_GROUPS / 2; ++k) {
+                    const int g = half * (CG_GROUPS / 2) + k;
                     float near = 0.0f, far = 0.0f;
 #pragma unroll
                     for (int d = 0; d < DP; ++d) {
@@ -172,8 +172,8 @@ count_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ 
                     const bool all_in = reach && far < th.x;   // every pair is inside
                     const unsigned b_scan = __ballot_sync(FULL, reach && !all_in);
                     const unsigned b_in = __ballot_sync(FULL, all_in);
-                    scan_m[k] = b_scan & 0xffffu;      scan_m[2 + k] = b_scan >> 16;
-                    in_m[k] = b_in & 0xffffu;          in_m[2 + k] = b_in >> 16;
+                    scan_m[k] = b_scan & 0xffffu;      scan_m[CG_GROUPS / 2 + k] = b_scan >> 16;
+                    in_m[k] = b_in & 0xffffu;          in_m[CG_GROUPS / 2 + k] = b_in >> 16;
                 }
 #pragma unroll
                 for (int g = 0; g < CG_GROUPS; ++g) {
@@ -187,9 +187,9 @@ count_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ 
                         const float* rows = tile + (sb * FAST_SUB + strm) * DP;
                         float a = 0.0f;
 #pragma unroll
-                        for (int i = 0; i < FAST_SUB / 4; ++i) {
+                        for (int i = 0; i < FAST_SUB / CG_GROUPS; ++i) {  // candidates CG_GROUPS * i + strm
                             float2 cc[DP / 2];
-                            load_row<DP>(rows + 4 * i * DP, cc);
+                            load_row<DP>(rows + CG_GROUPS * i * DP, cc);
                             a += (cheb32<DP>(qm[g], cc) < Tm[g]) ? 1.0f : 0.0f;
                         }
                         acc[g] += (int)a;
@@ -206,8 +206,8 @@ count_gunits_kernel(const float* __restrict__ shadow, const float* __restrict__ 
 #pragma unroll
         for (int g = 0; g < CG_GROUPS; ++g) {
             int v = acc[g];
-            v += __shfl_xor_sync(FULL, v, 8);
-            v += __shfl_xor_sync(FULL, v, 16);
+#pragma unroll
+            for (int off = CG_GQ; off < 32; off <<= 1) v += __shfl_xor_sync(FULL, v, off);
             if (strm == g) mine = v + inside_g[g] * FAST_SUB;
         }
         const int64_t qi = qb0 + warp * 32 + lane;
@@ -231,8 +231,8 @@ static int launch_count_full_dp(const CountF32Args& a, const CountUnitsArgs& w) 
     note_launch();
     // 8-query groups inside the filter warps (this file); KSG_B200_COUNT_GROUPS=0: whole warps (A/B runs, identity tests)
     static_assert(COUNT_UNITS_Q == 1, "the grouped kernel keeps one query per lane");
-    static const bool grouped = [] { const char* e = getenv("KSG_B200_COUNT_GROUPS"); return !(e && e[0] == '0'); }();
-    auto kern = grouped ? count_gunits_kernel<DP, ST> : count_units_kernel<DP, Q, ST>;
+    static const int groups = [] { const char* e = getenv("KSG_B200_COUNT_GROUPS"); return e ? atoi(e) : 4; }();
+    auto kern = groups == 8 ? count_gunits_kernel<DP, ST, 8> : groups == 4 ? count_gunits_kernel<DP, ST, 4> : count_units_kernel<DP, Q, ST>;
     const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float);
     if (smem > 32 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
