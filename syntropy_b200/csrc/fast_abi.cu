@@ -1055,6 +1055,7 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
     a.windowed = windowed ? 1 : 0;
     a.n_sub = n_subspaces; a.counts = d_counts; a.st = st;
     a.tile_counter = (unsigned long long*)((char*)P->flags + 24);
+    a.sub_box = P->sub_box;
     const int64_t qblocks = ceil_div(nq, count_f32_queries_per_block(P->dim_padded));
     a.splits = choose_splits(qblocks, P->n, FAST_TILE);  // (the pruned walk interleaves the splits too)
 
@@ -1089,7 +1090,12 @@ int ksg_fast_count(const ksg_prepared* P, int64_t q_begin, int64_t q_end, const 
     if (rc == KSG_EUNSUPPORTED && n_subspaces == dim && dim >= 3) {
         bool loo = true;
         for (int s = 0; s < dim; ++s) loo = loo && (h_masks[s] == (all & ~(1u << s)));
-        if (loo) rc = launch_count_loo(dim, a);
+        if (loo) {
+            // 8-query groups + sub-tile culling on the second-largest box gap (fast_count_loo_group.cu); small or
+            // low-dimensional cases keep the block-level kernel
+            rc = launch_count_loo_grouped(dim, a);
+            if (rc == KSG_EUNSUPPORTED) rc = launch_count_loo(dim, a);
+        }
     }
     if (rc == KSG_EUNSUPPORTED) {
         // generic: four run-time masks per launch

@@ -84,6 +84,7 @@ struct CountF32Args {
     int splits;
     unsigned long long* tile_counter;
     cudaStream_t st;
+    const float* sub_box;  // boxes of the 32-row sub-tiles (grouped leave-one-out kernel), may be null
 };
 // planning / work-unit buffers of the single-subspace windowed pass (see fast_count_units.cuh)
 struct CountUnitsArgs {
@@ -102,6 +103,7 @@ int launch_count_full(int dim_padded, const CountF32Args& a, const CountUnitsArg
 int launch_count_pair(int dx, int dy, const CountF32Args& a);          // subspaces x, y
 int launch_count_cmi(int dx, int dy, int dz, const CountF32Args& a);   // subspaces z, xz, yz
 int launch_count_loo(int d, const CountF32Args& a);                    // all leave-one-out subspaces
+int launch_count_loo_grouped(int d, const CountF32Args& a);            // ... 8-query groups, sub-tile culling (or KSG_EUNSUPPORTED)
 int launch_count_masked(int dim_padded, const CountF32Args& a);        // <= 4 run-time masks
 
 void note_launch();  // launch counter (ksg_launch_count)

@@ -149,6 +149,48 @@ def test_warp_level_knn_equals_the_cta_level_kernel():
     assert mine == ref, _diff(mine, ref)
 
 
+def _count_digest():
+    """sha1 over the raw marginal counts of the windowed count kernels: all leave-one-out subspaces of 5- to 8-D sets
+    (fused pass) and the full space of 2- to 4-D sets (own-order pass), for radii taken from the k-NN stage,
+    whole sets and a query slice that starts inside a block."""
+    import torch
+
+    from syntropy_b200 import _engine as E
+
+    out = []
+    r2 = np.random.default_rng(31)
+    sets = [("5d", r2.standard_normal((5, 9_000))), ("6d quantised", np.round(r2.standard_normal((6, 7_000)) * 4) / 4),
+            ("7d heavy", r2.standard_t(2.0, size=(7, 6_000))), ("8d", r2.standard_normal((8, 9_000))),
+            ("8d clusters", np.concatenate([r2.standard_normal((8, 2_500)) * 0.1 + 3 * c for c in range(4)], axis=1)),
+            ("8d duplicates", np.repeat(r2.standard_normal((8, 1_500)), 3, axis=1)),
+            ("2d", r2.standard_normal((2, 30_000))), ("3d heavy", r2.standard_t(1.5, size=(3, 20_000))),
+            ("4d", r2.standard_normal((4, 40_000))), ("4d quantised", np.round(r2.standard_normal((4, 15_000)) * 8) / 8),
+            ("4d small", r2.standard_normal((4, 300)))]
+    for name, rows in sets:
+        dim, n = rows.shape
+        pts = E.to_device_points(rows)
+        prep = E.PreparedSet(pts, E.order_for(dim))
+        eps = E.fast_knn(prep, 5, 0, n, True)
+        full = (1 << dim) - 1
+        masks = [full & ~(1 << s) for s in range(dim)] if dim >= 5 else [full]
+        for q0, q1 in ((0, n), (n // 3 + 5, n // 3 + 5 + min(n // 2, 4_321))):
+            for strict in (True, False):
+                c = E.fast_counts(prep, masks, eps[q0:q1].contiguous(), q0, q1, True, strict=strict)
+                torch.cuda.synchronize()
+                out.append("%s/%d-%d/%d:%s" % (name, q0, q1, strict, hashlib.sha1(c.cpu().numpy().tobytes()).hexdigest()))
+    return "|".join(out)
+
+
+def test_grouped_count_kernels_equal_the_whole_warp_and_block_level_kernels():
+    """8-query groups (own-order marginal pass, fused leave-one-out pass with sub-tile culling on the second-largest
+    box gap) against the kernels they replace; the leave-one-out kernel is forced on for these small sets."""
+    mine = _in_subprocess("_count_digest", KSG_B200_LOO_GROUPS="force")
+    ref = _in_subprocess("_count_digest", KSG_B200_LOO_GROUPS="0", KSG_B200_COUNT_GROUPS="0")
+    assert mine == ref, _diff(mine, ref)
+    eight = _in_subprocess("_count_digest", KSG_B200_LOO_GROUPS="0", KSG_B200_COUNT_GROUPS="8")
+    assert eight == ref, _diff(eight, ref)
+
+
 def test_grouped_knn_equals_the_whole_warp_kernel():
     """knn_gunits_kernel (8-query groups inside the filter warps, 5 to 8 coordinates) == knn_units_kernel."""
     mine = _knn_digest_high()
