@@ -9,10 +9,10 @@
 //     the tile boxes against the block's box (32 tiles per round, one per lane) and streams the surviving tiles
 //     + their sub-tile boxes through a bulk-copy ring;
 //   * a filter warp keeps its 32 queries as four groups of 8: lane l = (stream s = l / 8, member m = l % 8)
-//     holds member m's query of every group and that query's accumulators; the 16 sub-tiles x 4 groups of a
+//     holds member m's query of every group in registers, that query's accumulators in shared memory; the 16 sub-tiles x 4 groups of a
 //     tile are classified by the 32 lanes at once (two per lane, two ballots);
 //   * a surviving (group, sub-tile) is scanned by all lanes -- stream s takes the candidates 4 i + s -- with the
-//     indicator-sum arithmetic of SpecLoo (count_s += [sigma == DP] + [sigma == DP - 1] (1 - i_s)): the same
+//     indicator-sum arithmetic of SpecLoo (count_s += [sigma >= DP - 1] - [sigma == DP - 1] i_s): the same
 //     saturating-FMA predicate per coordinate, hence the same counts as count_f32_kernel;
 //   * at the end two shuffles per (group, subspace) add the four streams' shares; the owner lane writes.
 // Counts are float accumulators of small integers (exact below 2^24 per stream: n < 6.7e7).
@@ -23,7 +23,7 @@
 namespace ksg {
 
 template <int DD, int STAGES>
-static __global__ void __launch_bounds__(UNITS_THREADS, 3)
+static __global__ void __launch_bounds__(UNITS_THREADS, 4)
 count_loo_group_kernel(const float* __restrict__ shadow, const float* __restrict__ tile_box,
                        const float* __restrict__ sub_box, int64_t n_tiles, int64_t q_begin, int64_t nq,
                        const float* __restrict__ thresholds, int32_t* __restrict__ counts,
@@ -41,6 +41,10 @@ count_loo_group_kernel(const float* __restrict__ shadow, const float* __restrict
     __shared__ int s_tile[STAGES];
     __shared__ float2 s_gbox[FAST_THREADS / 32][NG][DP];  // (lo, hi) of every group's live queries
     __shared__ float s_gthr[FAST_THREADS / 32][NG];       // largest threshold of the group
+    // the accumulators of the three groups a lane is NOT scanning live here ([group][word][thread]: conflict-free);
+    // in registers they cost 40 per thread and a fourth CTA per SM
+    __shared__ float2 s_acc[NG][H][FAST_THREADS];
+    __shared__ float s_ge[NG][FAST_THREADS];  // sum of [sigma >= DP - 1] = [all inside] + [exactly one outside]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int strm = lane / GQ, mem = lane % GQ;
@@ -131,7 +135,6 @@ count_loo_group_kernel(const float* __restrict__ shadow, const float* __restrict
     // ---------------- filter warps: member `mem` of every group, scales, group boxes
     float2 qm[NG][H];
     IndScale sc[NG];
-    float2 ae[NG], acc[NG][H];
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         const int64_t qi = qb0 + warp * 32 + g * GQ + mem;
@@ -139,9 +142,9 @@ count_loo_group_kernel(const float* __restrict__ shadow, const float* __restrict
         load_row<DP>(shadow + (q_begin + (in ? qi : 0)) * DP, qm[g]);
         const float T = in ? thresholds[qi] : -1.0f;  // dead slots count nothing
         sc[g] = make_ind_scale(T);
-        ae[g] = make_float2(0.0f, 0.0f);
+        s_ge[g][tid] = 0.0f;
 #pragma unroll
-        for (int h = 0; h < H; ++h) acc[g][h] = make_float2(0.0f, 0.0f);
+        for (int h = 0; h < H; ++h) s_acc[g][h][tid] = make_float2(0.0f, 0.0f);
         float lo[DP], hi[DP];
         float tmax = in ? T : -CUDART_INF_F;
 #pragma unroll
@@ -197,6 +200,11 @@ count_loo_group_kernel(const float* __restrict__ shadow, const float* __restrict
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 unsigned m = scan_m[g];
+                if (m == 0u) continue;  // (warp-uniform)
+                float sge = s_ge[g][tid];
+                float2 acc[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) acc[h] = s_acc[g][h][tid];
 #pragma unroll 1
                 while (m) {
                     const int sb = __ffs(m) - 1;
@@ -217,14 +225,18 @@ count_loo_group_kernel(const float* __restrict__ shadow, const float* __restrict
 #pragma unroll
                         for (int h = 1; h < H; ++h) s2 = add2(s2, ind[h]);
                         const float sigma = s2.x + s2.y;
-                        const float all = add_sat(sigma, -(float)(DP - 1));      // [sigma == DP]
-                        const float e = add_sat(sigma, -(float)(DP - 2)) - all;  // [sigma == DP - 1]
-                        ae[g] = add2(ae[g], make_float2(all, e));
+                        // count_s += [sigma == DP] + [sigma == DP - 1] (1 - i_s) = [sigma >= DP - 1] - [sigma == DP - 1] i_s
+                        const float ge = add_sat(sigma, -(float)(DP - 2));       // [sigma >= DP - 1]
+                        const float e = ge - add_sat(sigma, -(float)(DP - 1));   // [sigma == DP - 1]
+                        sge += ge;
                         const float2 ee = make_float2(e, e);
 #pragma unroll
-                        for (int h = 0; h < H; ++h) acc[g][h] = fma2(ind[h], ee, acc[g][h]);
+                        for (int h = 0; h < H; ++h) acc[h] = fma2(ind[h], ee, acc[h]);
                     }
                 }
+                s_ge[g][tid] = sge;
+#pragma unroll
+                for (int h = 0; h < H; ++h) s_acc[g][h][tid] = acc[h];
             }
         }
         __syncwarp();
@@ -239,8 +251,9 @@ count_loo_group_kernel(const float* __restrict__ shadow, const float* __restrict
         int mine = 0;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-            const float in_s = (s & 1) ? acc[g][s / 2].y : acc[g][s / 2].x;
-            int v = (int)(ae[g].x + (ae[g].y - in_s));
+            const float2 a2 = s_acc[g][s / 2][tid];
+            const float in_s = (s & 1) ? a2.y : a2.x;
+            int v = (int)(s_ge[g][tid] - in_s);
             v += __shfl_xor_sync(FULL, v, 8);
             v += __shfl_xor_sync(FULL, v, 16);
             if (strm == g) mine = v;
