@@ -266,8 +266,11 @@ count_loo_group_kernel(const float* __restrict__ shadow, const float* __restrict
 
 template <int DD>
 static int launch_loo_group(const CountF32Args& a) {
-    constexpr int DP = (DD + 1) & ~1, ST = 2;
-    auto kern = count_loo_group_kernel<DD, ST>;
+    constexpr int DP = (DD + 1) & ~1;
+    // ring depth: 2 (four CTAs per SM at D = 8); KSG_B200_LOO_STAGES=3 for experiments
+    static const int st_env = [] { const char* e = getenv("KSG_B200_LOO_STAGES"); return e ? atoi(e) : 2; }();
+    const int ST = st_env == 3 ? 3 : 2;
+    auto kern = ST == 3 ? count_loo_group_kernel<DD, 3> : count_loo_group_kernel<DD, 2>;
     const size_t smem = (size_t)ST * (FAST_TILE * DP + FAST_NSUB * DP * 2) * sizeof(float);
     if (smem > 32 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
