@@ -523,19 +523,34 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                 default: curve_key_kernel<0><<<nb, 256, tsmem, st>>>(d_points, ld, n, dim, P.curve_table, P.center, bits, mkeys, iota, bbits, bcursor, L.ld, bucket_id, L.ld);
             }
             KSG_LAUNCHED2();
+            // The bucket build (needed by the 1-D counts only) runs on a side stream BESIDE the key sort and the
+            // gather (three latency-bound radix passes that leave most SMs idle): forked here, joined at the end of
+            // this sequence -- inside a capture both become branches of the same graph.  KSG_B200_BUCKET_FORK=0: in line.
+            static const bool fork_buckets = [] { const char* e = getenv("KSG_B200_BUCKET_FORK"); return !(e && e[0] == '0'); }();
+            const bool forked = lazy && fork_buckets;
+            cudaStream_t bs = forked ? lanes->helper[0] : st;
             if (lazy) {
+                if (forked) {
+                    KSG_CUDA_TRY(cudaEventRecord(lanes->fork, st));
+                    KSG_CUDA_TRY(cudaStreamWaitEvent(bs, lanes->fork, 0));
+                }
                 const unsigned chunks = (unsigned)ceil_div(n_buckets, BUCKET_CHUNK);
                 int32_t* chunk_sum = (int32_t*)stats;  // (the min / max partials are spent: curve_table_kernel has run)
-                bucket_sum_kernel<<<dim3(chunks, dim), BUCKET_CHUNK, 0, st>>>(bcursor, L.ld, n_buckets, chunk_sum, chunks,
+                bucket_sum_kernel<<<dim3(chunks, dim), BUCKET_CHUNK, 0, bs>>>(bcursor, L.ld, n_buckets, chunk_sum, chunks,
                                                                                P.flags + 10);
                 KSG_LAUNCHED2();
-                bucket_scan_kernel<<<dim3(chunks, dim), BUCKET_CHUNK, 0, st>>>(bcursor, L.ld, bstart, L.ld, n_buckets,
+                bucket_scan_kernel<<<dim3(chunks, dim), BUCKET_CHUNK, 0, bs>>>(bcursor, L.ld, bstart, L.ld, n_buckets,
                                                                                 chunk_sum, chunks);
                 KSG_LAUNCHED2();
-                bucket_scatter_kernel<<<dim3((unsigned)ceil_div(n, 256 * BUCKET_SCATTER_PER_THREAD), dim), 256, 0, st>>>(
+                bucket_scatter_kernel<<<dim3((unsigned)ceil_div(n, 256 * BUCKET_SCATTER_PER_THREAD), dim), 256, 0, bs>>>(
                     d_points, ld, n, bucket_id, L.ld, bcursor, L.ld, P.axis_vals, L.ld);
                 KSG_LAUNCHED2();
+                if (forked) KSG_CUDA_TRY(cudaEventRecord(lanes->join[0], bs));
             }
+            auto join_buckets = [&]() -> int {
+                if (forked) KSG_CUDA_TRY(cudaStreamWaitEvent(st, lanes->join[0], 0));
+                return KSG_OK;
+            };
             if (use_sample_sort(n)) {
                 const int rc2 = sample_sort_launch<unsigned long long>(cub_tmp, mkeys, mkeys_out, P.perm, n, st);
                 if (rc2) return rc2;
@@ -552,7 +567,7 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
                     d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32,
                     nullptr, P.tile_box, P.sub_box, exact_info, exact_off, P.flags);
                 KSG_LAUNCHED2();
-                return KSG_OK;
+                return join_buckets();
             }
             gather_sorted_kernel<<<(unsigned)gather_blocks, 256, 0, st>>>(
                 d_points, ld, n, dim, L.dim_padded, P.perm, P.center, P.sorted_f64, L.ld, P.shadow_f32, L.n_padded,
@@ -565,7 +580,7 @@ int ksg_prepare_rows(const double* d_points, int64_t ld, int64_t n, int dim, int
             tile_box_kernel<<<(unsigned)(L.n_padded / FAST_TILE), 128, 0, st>>>(P.shadow_f32, L.dim_padded, P.tile_box,
                                                                                  P.sub_box);
             KSG_LAUNCHED2();
-            return KSG_OK;
+            return join_buckets();
         };
         rc = graph_cache().run(graph_key(GRAPH_PREPARE_EARLY, {d_points, d_buffer}, {n, ld},
                                          {dim, primary, fused_gather() ? 1 : 0, lazy ? 1 : 0}), st, early);
