@@ -824,6 +824,8 @@ def finish_device(pw: Pointwise, n_total: int, out: torch.Tensor | None = None, 
         return _text.load().finish_step(gathered, pw.prep.struct_bytes, out, ticket, ex.my_flags, ex.world, epoch,
                                         ex.my_aux(parity), status.nflag), out
     else:
+        if pw.pushed is not None:  # (the slices sit in peer memory; only the status-block path consumes them)
+            raise RuntimeError("finish_device: a peer-memory exchange is pending; pass the call's Status")
         ptw_full = _dist.gather_slices(pw.values, n_total)
         if pw.prep is not None:
             if out is not None and _text.enabled() and getattr(pw.prep, "struct_bytes", None) is not None:
