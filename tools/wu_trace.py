@@ -1,5 +1,10 @@
 #!/usr/bin/env python
-"""DEBUG (needs the trace build of fast_knn_warp.cuh): per-item timeline of knn_wunits_kernel for one rank's slice."""
+"""DEBUG: per-item timeline of knn_wunits_kernel for one rank's slice (usage: wu_trace.py WORLD RANK).
+
+Needs a TRACE BUILD of the library: knn_wunits_kernel writing (globaltimer at item start, scan end, merge end; tiles,
+units, sub-tile scans) per work item into a __device__ array g_wu_trace[65536 * 4] and an exported
+`ksg_debug_wu_trace(unsigned long long* host_out, int n_items)` that copies it out -- the patch is described in
+profiles/r2y_wunits_item_trace_slice0of8.txt and is not part of the shipped kernel."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import numpy as np, torch
@@ -18,6 +23,8 @@ for it in range(4):
 lib = _cabi.load()._lib if hasattr(_cabi.load(), "_lib") else C.CDLL(os.path.join(ROOT, "syntropy_b200/lib/libksg_b200.so"))
 n_items = min(65536, 4 * 3 * (-(-(q1 - q0) // 128)))
 buf = (C.c_ulonglong * (4 * n_items))()
+if not hasattr(lib, "ksg_debug_wu_trace"):
+    raise SystemExit("this library is not a trace build (no ksg_debug_wu_trace): see the docstring")
 lib.ksg_debug_wu_trace.argtypes = [C.c_void_p, C.c_int]
 print("rc", lib.ksg_debug_wu_trace(buf, n_items))
 a = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 4)
