@@ -289,7 +289,11 @@ static int launch_loo_group(const CountF32Args& a) {
 int launch_count_loo_grouped(int d, const CountF32Args& a) {
     // KSG_B200_LOO_GROUPS: 0 = off, "force" = also for small query sets (tests)
     static const int mode = [] { const char* e = getenv("KSG_B200_LOO_GROUPS"); return !e ? 1 : (e[0] == '0' ? 0 : (e[0] == 'f' ? 2 : 1)); }();
-    if (mode == 0 || !a.sub_box || !a.windowed || (mode == 1 && a.nq < 64 * FAST_THREADS) ||
+    // one CTA per 128 queries, no candidate splits: it needs at least one full wave of CTAs (4 per SM) to use the
+    // machine -- below that (small sets, a rank's slice of an 8-GPU run) the block-level kernel with its candidate
+    // splits is the better choice (C4 on 8 ranks: 31 250 queries per rank = 244 CTAs for 592 slots)
+    const int64_t min_queries = (int64_t)sm_count() * 4 * FAST_THREADS;
+    if (mode == 0 || !a.sub_box || !a.windowed || (mode == 1 && a.nq < min_queries) ||
         a.n_tiles * (int64_t)FAST_TILE >= (1ll << 26))
         return KSG_EUNSUPPORTED;
     switch (d) {
